@@ -1,0 +1,88 @@
+/*
+ * oracle.h — CPU restatement of the reference algorithms (TEST INFRASTRUCTURE ONLY).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library. The product path (wfmash_b200/csrc, libwfmash_b200.so) never links, loads or
+ * calls anything under oracle/.
+ *
+ * Parity pinning:
+ *   - wfa_oracle.c is pinned against the reference's own known-answer vectors
+ *     deps/WFA2-lib/tests/wfa.utest.seq + tests/wfa.utest.check/test.biwfa.affine2p.alg
+ *     (305 pairs, fixtures committed under tests/golden/) and differentially against
+ *     oracle/_ref/libwfa2ref.so (the unmodified reference sources compiled in place).
+ *   - map_oracle.c: the reference has no byte-exact tests for src/map ("parity unpinned" by the
+ *     reference's own tests); it is pinned differentially against
+ *     oracle/_ref/libmapref.so (reference commonFunc.hpp compiled unmodified) and by committed
+ *     fixtures generated from it (tests/golden/make_map_golden.py).
+ */
+#ifndef WFMASH_B200_ORACLE_H
+#define WFMASH_B200_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- path 2: gap-affine-2p WFA / biWFA ------------------------------------------------- */
+
+typedef struct {
+  int x;   /* mismatch */
+  int o1;  /* gap_opening1 */
+  int e1;  /* gap_extension1 */
+  int o2;  /* gap_opening2 */
+  int e2;  /* gap_extension2 */
+} orc_penalties_t;
+
+/* Work counters: C = wavefront cells computed, E = matched chars in extend,
+ * O = diagonals tested in breakpoint overlap scans. */
+typedef struct {
+  int64_t cells;
+  int64_t extend_matches;
+  int64_t overlap_tests;
+  int64_t score_steps;
+} orc_wfa_counters_t;
+
+/* biWFA end-to-end alignment (restates wavefront_bialign, wavefront_bialign.c:1266).
+ * pattern = target slice, text = query slice (wflign.cpp:148).
+ * ops_out receives M/X/I/D chars in alignment order (cigar->operations[begin_offset..end_offset)).
+ * Returns 0 on success (WF_STATUS_ALG_COMPLETED), negative otherwise. */
+int orc_biwfa_align(const char* pattern, int plen, const char* text, int tlen,
+                    const orc_penalties_t* pen, char* ops_out, int ops_cap, int* ops_len,
+                    int* score, orc_wfa_counters_t* counters);
+
+/* Unidirectional full-memory WFA + backtrace (restates wavefront_unialign.c:242 +
+ * wavefront_backtrace.c:320), end-to-end, components M->M. */
+int orc_wfa_align(const char* pattern, int plen, const char* text, int tlen,
+                  const orc_penalties_t* pen, char* ops_out, int ops_cap, int* ops_len,
+                  int* score, orc_wfa_counters_t* counters);
+
+/* Gap-affine-2p score of an ops string (restates cigar_score_gap_affine2p, alignment/cigar.c);
+ * returned as a non-negative penalty. */
+int orc_cigar_score(const char* ops, int n, const orc_penalties_t* pen);
+
+/* Check that ops is a valid end-to-end transcript of pattern -> text. 1 = valid. */
+int orc_cigar_check(const char* pattern, int plen, const char* text, int tlen, const char* ops, int n);
+
+/* ---- path 1: MashMap 3.5 sketching ------------------------------------------------------ */
+
+/* MinmerInfo, base_types.hpp:79-110 (32 bytes). strand: FWD=1, AMBIG=0, REV=-1. */
+typedef struct {
+  uint64_t hash;
+  int64_t wpos;
+  int64_t wpos_end;
+  int32_t seqId;
+  int16_t strand;
+  int16_t pad_;
+} orc_minmer_t;
+
+/* MurmurHash3_x64_128 low 64 bits, seed 42 (commonFunc.hpp:173-182, murmur3.h:226-303). */
+uint64_t orc_kmer_hash(const char* kmer, int k);
+
+/* sketchSequence (commonFunc.hpp:217-323): bottom-s distinct canonical hashes of one fragment.
+ * seq must already be upper-cased/N-masked (makeUpperCaseAndValidDNA). Returns count written. */
+int orc_sketch_fragment(const char* seq, int len, int k, int s, int32_t seqId, orc_minmer_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,326 @@
+#!/usr/bin/env python3
+"""bench.py — the driver's measurement contract for wfmash_b200.
+
+A "step" = one pass of the hot path over one batch of synthetic mapping records shaped like
+BASELINE.json configs[1] (LPA.subset self all-vs-all, -k15 -w1k -P50k: 861 records / 13.0 Mbp of
+query, doc/performance-tuning.md:311-319; the real FASTA lives in /root/reference and does not exist
+on the GPU box, so the records are seeded synthetic ones of that shape).
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N ...          # the reference's CPU biWFA on the host cores
+
+Prints ONE JSON line (rank 0). `value` = aligned bp/s with the sequences resident in HBM (CUDA-event
+time), `e2e` = the same through the host-buffer C ABI with H2D/D2H inside the timed region.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = {
+    "workload": "C2-shaped synthetic mapping records -> biWFA (wfmash path 2): 861 records, query 5-25 kb "
+                "(mean 15 kb, 13 Mbp/step), target = query mutated at 1/2/5/10 % (sub:ins:del 8:1:1) + 1 kb flanks "
+                "each side (wfmash target padding), penalties 0,5,8,2,24,1",
+    "records": 861, "len_lo": 5000, "len_hi": 25000, "divergences": [0.01, 0.02, 0.05, 0.10], "pad": 1000,
+}
+METRIC = "aligned bp/s (biWFA base-level alignment of mapping records)"
+UNIT = "bp/s"
+PEN = (5, 8, 2, 24, 1)
+
+
+def make_records(rank, n=None):
+    from wfmash_b200 import synth
+    return synth.mapping_records(n or WORKLOAD["records"], seed=1234 + 7919 * rank, len_lo=WORKLOAD["len_lo"],
+                                 len_hi=WORKLOAD["len_hi"], divergences=WORKLOAD["divergences"], pad=WORKLOAD["pad"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU side: the reference's own biWFA (oracle/_ref, unmodified WFA2-lib compiled in place) or, when that
+# is absent, the oracle port. Test/measurement infrastructure only.
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_lib():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libwfa2ref.so")
+    if os.path.exists(ref):
+        return ctypes.CDLL(ref), "reference"
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(orc):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
+    return ctypes.CDLL(orc), "port"
+
+
+def cpu_align_records(lib, kind, recs, threads):
+    """Align recs with `threads` host threads (one aligner per record, like wfmash). Returns (bp, seconds)."""
+    class Pen(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_int) for n in "x o1 e1 o2 e2".split()]
+
+    def one(rec):
+        p, t, _ = rec
+        buf = ctypes.create_string_buffer(len(p) + len(t) + 16)
+        n, sc = ctypes.c_int(), ctypes.c_int()
+        if kind == "reference":
+            st = lib.ref_wfa_end2end(p, len(p), t, len(t), *PEN, 3, buf, len(buf), ctypes.byref(n), ctypes.byref(sc))
+        else:
+            P = Pen(*PEN)
+            st = lib.orc_biwfa_align(p, len(p), t, len(t), ctypes.byref(P), buf, len(buf), ctypes.byref(n), ctypes.byref(sc), None)
+        return len(t) if st == 0 else 0
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        bp = sum(ex.map(one, recs))
+    return bp, time.perf_counter() - t0
+
+
+def est_score(rec):
+    """Rough optimal-score estimate of a record: events * mean penalty + the two flank deletions."""
+    p, t, d = rec
+    return len(t) * d * 6.4 + 2 * (24 + WORKLOAD["pad"]) + 10.0
+
+
+def run_cpu_sample(recs, target_s, threads):
+    lib, kind = cpu_reference_lib()
+    # calibrate the cost model c * score^2 core-seconds on the cheapest record, then take the prefix of
+    # the step's records that fills about target_s seconds on `threads` cores
+    probe = min(recs, key=est_score)
+    bp, dt = cpu_align_records(lib, kind, [probe], 1)
+    unit = dt / est_score(probe) ** 2
+    budget = target_s * threads
+    sample, acc = [], 0.0
+    for r in recs:
+        c = unit * est_score(r) ** 2
+        if len(sample) >= threads and acc + c > budget:
+            break
+        sample.append(r)
+        acc += c
+    bp, dt = cpu_align_records(lib, kind, sample, threads)
+    return {"value": bp / dt, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"first {len(sample)} of {len(recs)} records of the step ({bp} query bp), {dt:.1f} s wall on {threads} threads"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--records", type=int, default=0, help="override records per step (debug)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        recs = make_records(0, args.records or None)
+        vals, last = [], None
+        for i in range(args.warmup + args.steps):
+            last = run_cpu_sample(recs, max(2.0, args.cpu_seconds / max(1, args.steps)), cores)
+            if i >= args.warmup:
+                vals.append(last["value"])
+        v = statistics.mean(vals)
+        last["value"] = v
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": dict(WORKLOAD), "cpu_baseline": last,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import wfmash_b200 as wb
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    assert wb.device_count() > dev, "no CUDA device: wfmash_b200 has no CPU path"
+    recs = make_records(rank, args.records or None)
+    pairs = [(p, t) for p, t, _ in recs]
+    n = len(pairs)
+    bp_step = sum(len(t) for _, t in pairs)
+    L = wb.lib()
+    al = wb.Aligner(dev)
+    # device-resident copy of the inputs for the `value` leg
+    blob = b"".join(p + t for p, t in pairs)
+    d_blob = L.wfb_device_malloc(dev, len(blob) + 64)
+    assert d_blob and L.wfb_memcpy_h2d(dev, d_blob, blob, len(blob)) == 0
+    poff = np.zeros(n, dtype=np.int64); toff = np.zeros(n, dtype=np.int64)
+    plen = np.zeros(n, dtype=np.int32); tlen = np.zeros(n, dtype=np.int32)
+    o = 0
+    for i, (p, t) in enumerate(pairs):
+        poff[i] = o; plen[i] = len(p); o += len(p)
+        toff[i] = o; tlen[i] = len(t); o += len(t)
+    cap = int(plen.sum() + tlen.sum()) + 16
+    ops = ctypes.create_string_buffer(cap)
+    res = (wb._Res * n)()
+    arr = (wb._Pair * n)(*[wb._Pair(p, len(p), t, len(t)) for p, t in pairs])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")  # > 126 MB L2
+
+    def step_device(stats):
+        rc = L.wfb_align_batch_device(al._h, d_blob, poff.ctypes.data, plen.ctypes.data, toff.ctypes.data, tlen.ctypes.data,
+                                      n, ops, cap, res, ctypes.byref(stats))
+        assert rc == 0, L.wfb_last_error()
+
+    def step_host(stats):
+        rc = L.wfb_align_batch(al._h, arr, n, ops, cap, res, ctypes.byref(stats))
+        assert rc == 0, L.wfb_last_error()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        st = wb.AlignStats()
+        for _ in range(warmup):
+            fn(st)
+        wall, dev_ms, brk_ms, last = [], [], [], None
+        launches0 = wb.launch_count()
+        barrier()
+        for _ in range(steps):
+            flush.fill_(1)  # flush L2 between timed iterations (outside the per-step timers)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(st)
+            torch.cuda.synchronize()
+            wall.append(time.perf_counter() - t0)
+            dev_ms.append(st.kernel_ms); brk_ms.append(st.break_kernel_ms)
+            last = st.as_dict()
+        barrier()
+        return wall, dev_ms, brk_ms, last, wb.launch_count() - launches0
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    wall_d, devms_d, brk_d, stats_d, launches_d = timed(step_device, args.steps, args.warmup)
+    wall_h, devms_h, brk_h, stats_h, launches_h = timed(step_host, args.steps, max(1, min(args.warmup, 1)))
+    clocks = sampler.stop()
+    ok = sum(1 for r in res if r.status == 0)
+    aligned_bp = sum(int(tlen[i]) for i in range(n) if res[i].status == 0)
+
+    t_dev = sum(devms_d) / 1e3          # CUDA-event seconds for K steps
+    t_host = sum(wall_h)                # wall seconds for K steps, H2D + D2H inside
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([t_dev, t_host], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_host = float(tt[0]), float(tt[1])
+        tb = torch.tensor([aligned_bp], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        total_bp = float(tb[0])
+    else:
+        total_bp = float(aligned_bp)
+    value = total_bp * args.steps / t_dev
+    e2e = total_bp * args.steps / t_host
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        # roofline of the dominant kernel (wfb_break_kernel): algorithmic bytes of SURVEY §8d
+        # = 48 B/cell + 2 B/extended base + 8 B/overlap test, per step, over its CUDA-event time
+        alg_bytes = 48 * stats_d["cells"] + 2 * stats_d["extend_matches"] + 8 * stats_d["overlap_tests"]
+        brk_s = (sum(brk_d) / len(brk_d)) / 1e3
+        n_brk_launch = max(1, int(stats_d["levels"]))
+        achieved = alg_bytes / brk_s / 1e9 if brk_s > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": "wfb_break_kernel", "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": brk_s * 1e3, "launches_per_step": n_brk_launch,
+                    "cells_per_step": stats_d["cells"], "gcells_per_s": stats_d["cells"] / brk_s / 1e9 if brk_s > 0 else 0.0}
+        cpu = run_cpu_sample(recs, args.cpu_seconds, cores) if world == 1 else None
+        h2d = int(plen.sum() + tlen.sum()) + 64 * n
+        d2h = sum(r.ops_len for r in res) + 24 * n
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": dict(WORKLOAD, l2="flushed between timed iterations (256 MiB write); per-step workspace >> L2",
+                           records_per_gpu=n, query_bp_per_gpu=bp_step, completed=ok,
+                           timing="value: CUDA events on the library stream; e2e: host wall clock around the C-ABI call",
+                           stats=stats_d),
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_host / args.steps},
+            "gpu_launches": int(launches_d),
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

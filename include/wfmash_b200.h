@@ -1,0 +1,152 @@
+/*
+ * wfmash_b200.h — C ABI of libwfmash_b200.so, the B200-native (sm_100a) replacement for wfmash's two
+ * data-parallel hot paths. Plain pointers and sizes only; no torch / CUDA types in the signatures.
+ * Every entry point names the reference interface it replaces (paths relative to the wfmash tree).
+ *
+ * All functions return 0 on success or a negative WFB_E* code; they never fall back to a CPU
+ * implementation: without a CUDA device they fail with WFB_ENODEV.
+ */
+#ifndef WFMASH_B200_H
+#define WFMASH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFB_OK 0
+#define WFB_ENODEV (-1)   /* no CUDA device / driver */
+#define WFB_ECUDA (-2)    /* CUDA runtime error (see wfb_last_error) */
+#define WFB_EINVAL (-3)   /* bad argument */
+#define WFB_ENOMEM (-4)   /* device or host allocation failed */
+#define WFB_ECAP (-5)     /* output capacity too small */
+
+/* Human-readable description of the last error on this thread. */
+const char* wfb_last_error(void);
+/* Library / build info: "wfmash_b200 <version> sm_100a". */
+const char* wfb_version(void);
+/* Number of visible CUDA devices (0 when there is none; never negative). */
+int wfb_device_count(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */
+uint64_t wfb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path 2 — biWFA base-level aligner.
+ * Replaces wflign::wavefront::do_biwfa_alignment's call
+ *   wfa::WFAlignerGapAffine2Pieces(0,x,o1,e1,o2,e2,Alignment,MemoryUltralow).alignEnd2End(target,query)
+ * (src/common/wflign/src/wflign.cpp:136-148; deps/WFA2-lib/bindings/cpp/WFAligner.cpp:68-78,449-468;
+ *  C API wavefront_align, deps/WFA2-lib/wavefront/wavefront_align.c:212) for a BATCH of mapping
+ * records. The caller (the align::Aligner batch builder, src/align/include/computeAlignments.hpp:661-720)
+ * owns every buffer.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* wflign_penalties_t (src/common/wflign/src/wflign.hpp) / affine2p_penalties_t; match is always 0. */
+typedef struct {
+  int32_t mismatch;
+  int32_t gap_opening1;
+  int32_t gap_extension1;
+  int32_t gap_opening2;
+  int32_t gap_extension2;
+} wfb_penalties_t;
+
+/* One alignment problem: pattern = target slice, text = (strand-corrected) query slice, ASCII,
+ * upper-cased / N-masked by the caller exactly as processAlignment does (computeAlignments.hpp:671-681). */
+typedef struct {
+  const char* pattern;
+  int32_t pattern_len;
+  const char* text;
+  int32_t text_len;
+} wfb_pair_t;
+
+/* Per-pair result. ops are the M/X/I/D characters of cigar_t::operations[begin_offset,end_offset)
+ * (deps/WFA2-lib/alignment/cigar.h), i.e. what wflign_edit_cigar_copy consumes
+ * (src/common/wflign/src/wflign_alignment.cpp:665-678). status mirrors wavefront_align's return:
+ * 0 = WF_STATUS_ALG_COMPLETED, negative = unattainable (the reference then writes no record,
+ * wflign.cpp:150-152). score is the reference's cigar score convention: -(gap-affine-2p penalty). */
+typedef struct {
+  int32_t status;
+  int32_t score;
+  int64_t ops_offset; /* into the ops buffer passed to wfb_align_batch */
+  int32_t ops_len;
+  int32_t reserved_;
+} wfb_aln_result_t;
+
+/* Work counters summed over the batch (C cells, E extended matches, O overlap tests),
+ * split by kernel so that the roofline of the dominant (breakpoint) kernel can be computed. */
+typedef struct {
+  uint64_t cells;           /* breakpoint kernel: wavefront cells computed                */
+  uint64_t extend_matches;  /* breakpoint kernel: matched bases in extend                 */
+  uint64_t overlap_tests;   /* breakpoint kernel: diagonals scanned by overlap detection  */
+  uint64_t score_steps;     /* breakpoint kernel: score steps (both directions)           */
+  uint64_t break_tasks;
+  uint64_t base_tasks;
+  uint64_t base_cells;          /* base kernel share */
+  uint64_t base_extend_matches;
+  uint64_t base_score_steps;
+  uint64_t levels;
+  double kernel_ms;      /* CUDA-event time of all kernels of the call (on the call's stream)   */
+  double break_kernel_ms; /* ... of the breakpoint (bidirectional wavefront) kernel launches only */
+} wfb_align_stats_t;
+
+typedef struct wfb_aligner wfb_aligner_t;
+
+/* Create / destroy an aligner bound to one device. workspace_bytes = 0 picks a default
+ * (a fraction of free HBM); the workspace bounds how many alignments are resident at once. */
+wfb_aligner_t* wfb_aligner_create(int device, const wfb_penalties_t* penalties, uint64_t workspace_bytes);
+void wfb_aligner_destroy(wfb_aligner_t*);
+
+/* Align n pairs end-to-end with HOST buffers (copies H2D / D2H inside).
+ *   ops / ops_cap : caller buffer receiving all operation strings back to back; needs
+ *                   sum(pattern_len+text_len) bytes in the worst case (WFB_ECAP otherwise).
+ *   results[n]    : per pair.
+ *   stats         : optional. */
+int wfb_align_batch(wfb_aligner_t*, const wfb_pair_t* pairs, int32_t n, char* ops, int64_t ops_cap,
+                    wfb_aln_result_t* results, wfb_align_stats_t* stats);
+
+/* Same with the sequences already resident in device memory (used by bench.py's HBM-resident
+ * `value` leg). d_seq holds all sequences; pattern_off/text_off are byte offsets into it.
+ * The results (ops + wfb_aln_result_t) still come back to the host buffers. */
+int wfb_align_batch_device(wfb_aligner_t*, const char* d_seq, const int64_t* pattern_off, const int32_t* pattern_len,
+                           const int64_t* text_off, const int32_t* text_len, int32_t n, char* ops, int64_t ops_cap,
+                           wfb_aln_result_t* results, wfb_align_stats_t* stats);
+
+/* Device memory helpers so callers without a CUDA binding (ctypes) can stage inputs. */
+void* wfb_device_malloc(int device, uint64_t bytes);
+void wfb_device_free(int device, void* p);
+int wfb_memcpy_h2d(int device, void* dst, const void* src, uint64_t bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path 1 — MashMap 3.5 query-fragment sketch.
+ * Replaces skch::CommonFunc::sketchSequence as called by MappingCore::getSeedHits
+ * (src/map/include/commonFunc.hpp:217-323; src/map/include/mappingCore.hpp:61-76) for a BATCH of
+ * fragments.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* skch::MinmerInfo (src/map/include/base_types.hpp:28-60), 32-byte reference layout. */
+typedef struct {
+  uint64_t hash;
+  int64_t wpos;
+  int64_t wpos_end;
+  int32_t seqId;
+  int16_t strand; /* FWD = 1, AMBIG = 0, REV = -1 (base_types.hpp:101-106) */
+  int16_t pad_;
+} wfb_minmer_t;
+
+typedef struct {
+  int64_t seq_offset; /* fragment start within seq_base                  */
+  int32_t len;        /* fragment length (param.windowLength on the CLI path) */
+  int32_t seq_id;     /* copied into MinmerInfo::seqId                   */
+} wfb_frag_t;
+
+/* Sketch n fragments: out[i*sketch_size .. i*sketch_size+out_count[i]) receives the fragment's
+ * minmers sorted ascending by hash, as sketchSequence leaves them. seq_base is raw FASTA bases
+ * (any case); upper-casing / N-masking (makeUpperCaseAndValidDNA, commonFunc.hpp:132-142) is fused
+ * into the kernel. kmer_size <= 32. */
+int wfb_sketch_fragments(int device, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags, int32_t n,
+                         int32_t kmer_size, int32_t sketch_size, wfb_minmer_t* out, int32_t* out_count,
+                         double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,46 @@
+"""Builds libwfmash_b200.so (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc.
+
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = [os.path.join(HERE, "csrc", f) for f in ("wfa_host.cu", "sketch.cu")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("wfa_kernels.h", "wfb_rt.h")] + [os.path.join(ROOT, "include", "wfmash_b200.h")]
+OUT = os.path.join(HERE, "libwfmash_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+
+
+def nvcc_path():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(f) > t for f in SRC + HDR if os.path.exists(f))
+
+
+def build(force=False, verbose=False):
+    srcs = [s for s in SRC if os.path.exists(s)]
+    if not force and not needs_build():
+        return OUT
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", OUT] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(OUT)

@@ -1,0 +1,512 @@
+// wfa_host.cu — host side of the batched biWFA aligner behind the C ABI (include/wfmash_b200.h).
+//
+// Drives the kernels of wfa_kernels.h: stages the sequences in HBM (forward + reversed copies),
+// seeds the task queues with one task per mapping record, then drains breakpoint / base tasks level
+// by level (the reference's recursion wavefront_bialign_alignment, wavefront_bialign.c:1144-1221,
+// unrolled breadth-first), compacts the operation strings and returns them.
+//
+// Compiled by nvcc for sm_100a into libwfmash_b200.so. With -DWFB_EMU (tests/emu only) the same file
+// compiles with g++ and runs every kernel body as one host thread per CTA; see wfb_rt.h.
+#include "wfa_kernels.h"
+#include "../../include/wfmash_b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+void wfb_set_last_error_(const std::string& s) { g_last_error = s; }
+void wfb_count_launch_() { g_launches.fetch_add(1); }
+
+#ifndef WFB_EMU
+#define WFB_CHECK(call)                                                                              \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      g_last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+      return (e_ == cudaErrorMemoryAllocation) ? WFB_ENOMEM : WFB_ECUDA;                             \
+    }                                                                                                \
+  } while (0)
+#define WFB_LAUNCH(kernel, grid, block, stream, ...)                                                 \
+  do {                                                                                               \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                           \
+    g_launches.fetch_add(1);                                                                         \
+  } while (0)
+typedef cudaStream_t wfb_stream_t;
+static int dev_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess ? 0 : -1; }
+static void dev_free(void* p) { if (p) cudaFree(p); }
+static int host_malloc(void** p, size_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? 0 : -1; }
+static void host_free(void* p) { if (p) cudaFreeHost(p); }
+#define WFB_H2D(dst, src, bytes, s) WFB_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s))
+#define WFB_D2H(dst, src, bytes, s) WFB_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s))
+#define WFB_D2D(dst, src, bytes, s) WFB_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s))
+#define WFB_MEMSET(dst, v, bytes, s) WFB_CHECK(cudaMemsetAsync(dst, v, bytes, s))
+#define WFB_STREAM_SYNC(s) WFB_CHECK(cudaStreamSynchronize(s))
+#else
+#define WFB_CHECK(call) do { (void)(call); } while (0)
+#define WFB_LAUNCH(kernel, grid, block, stream, ...)                                                 \
+  do {                                                                                               \
+    for (int bid_ = 0; bid_ < (int)(grid); ++bid_) kernel(bid_, (int)(grid), __VA_ARGS__);           \
+    g_launches.fetch_add(1);                                                                         \
+  } while (0)
+typedef int wfb_stream_t;
+static int dev_malloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -1; }
+static void dev_free(void* p) { free(p); }
+static int host_malloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -1; }
+static void host_free(void* p) { free(p); }
+#define WFB_H2D(dst, src, bytes, s) memcpy(dst, src, bytes)
+#define WFB_D2H(dst, src, bytes, s) memcpy(dst, src, bytes)
+#define WFB_D2D(dst, src, bytes, s) memcpy(dst, src, bytes)
+#define WFB_MEMSET(dst, v, bytes, s) memset(dst, v, bytes)
+#define WFB_STREAM_SYNC(s) ((void)0)
+#endif
+
+namespace {
+
+// Grow-only device / pinned-host buffers owned by the aligner.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    dev_free(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (dev_malloc(&p, want) != 0) { p = nullptr; return -1; }
+    cap = want;
+    return 0;
+  }
+  void release() { dev_free(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    host_free(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (host_malloc(&p, want) != 0) { p = nullptr; return -1; }
+    cap = want;
+    return 0;
+  }
+  void release() { host_free(p); p = nullptr; cap = 0; }
+};
+
+inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct wfb_aligner {
+  int device = 0;
+  WfbPen pen{};
+  uint64_t workspace_bytes = 0;
+  int sm_count = 148;
+  wfb_stream_t stream{};
+  DevBuf d_seq, d_pairs, d_slots, d_dense, d_len, d_status, d_counters, d_ctrl;
+  DevBuf d_q[4]; /* break[0], break[1], base[0], base[1] */
+  DevBuf d_ws, d_arena, d_log, d_runs, d_srcoff;
+  HostBuf h_seq, h_dense, h_misc;
+#ifndef WFB_EMU
+  cudaEvent_t ev[4]{};
+#endif
+};
+
+static const int kBreakThreads = 256;
+static const int kBaseThreads = 64;
+
+extern "C" const char* wfb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* wfb_version(void) {
+#ifdef WFB_EMU
+  return "wfmash_b200 0.1 host-emulation (tests only)";
+#else
+  return "wfmash_b200 0.1 sm_100a";
+#endif
+}
+extern "C" uint64_t wfb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int wfb_device_count(void) {
+#ifndef WFB_EMU
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+#else
+  return 1;
+#endif
+}
+
+extern "C" wfb_aligner_t* wfb_aligner_create(int device, const wfb_penalties_t* p, uint64_t workspace_bytes) {
+  if (!p) { g_last_error = "penalties == NULL"; return nullptr; }
+  /* the kernels rely on 0 <= o1 <= o2 (see wfb_overlap) and positive extensions */
+  if (p->mismatch <= 0 || p->gap_extension1 <= 0 || p->gap_extension2 <= 0 || p->gap_opening1 < 0 ||
+      p->gap_opening2 < p->gap_opening1) {
+    g_last_error = "unsupported penalties (need x>0, e1>0, e2>0, 0<=o1<=o2)";
+    return nullptr;
+  }
+  WfbPen pen;
+  pen.x = p->mismatch; pen.o1 = p->gap_opening1; pen.e1 = p->gap_extension1;
+  pen.o2 = p->gap_opening2; pen.e2 = p->gap_extension2;
+  pen.scope = std::max(std::max(pen.o2 + pen.e2, pen.o1 + pen.e1), pen.x) + 1;
+  pen.R = pen.scope + 1;
+  if (pen.R > WFB_RMAX) { g_last_error = "penalties too large for the wavefront ring (scope+1 > 40)"; return nullptr; }
+#ifndef WFB_EMU
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    g_last_error = "no CUDA device (this library has no CPU path)";
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { g_last_error = "bad device index"; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return nullptr; }
+#endif
+  wfb_aligner* a = new wfb_aligner();
+  a->device = device;
+  a->pen = pen;
+#ifndef WFB_EMU
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) a->sm_count = prop.multiProcessorCount;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if (workspace_bytes == 0) workspace_bytes = (uint64_t)(free_b * 0.45);
+  if (cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking) != cudaSuccess) { delete a; g_last_error = "stream"; return nullptr; }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&a->ev[i]);
+#else
+  if (workspace_bytes == 0) workspace_bytes = 1ull << 30;
+  a->sm_count = 2;
+#endif
+  a->workspace_bytes = workspace_bytes;
+  return a;
+}
+
+extern "C" void wfb_aligner_destroy(wfb_aligner_t* a) {
+  if (!a) return;
+#ifndef WFB_EMU
+  cudaSetDevice(a->device);
+  cudaStreamSynchronize(a->stream);
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(a->ev[i]);
+  cudaStreamDestroy(a->stream);
+#endif
+  DevBuf* bufs[] = {&a->d_seq, &a->d_pairs, &a->d_slots, &a->d_dense, &a->d_len, &a->d_status, &a->d_counters, &a->d_ctrl,
+                    &a->d_q[0], &a->d_q[1], &a->d_q[2], &a->d_q[3], &a->d_ws, &a->d_arena, &a->d_log, &a->d_runs, &a->d_srcoff};
+  for (DevBuf* b : bufs) b->release();
+  a->h_seq.release();
+  a->h_dense.release();
+  a->h_misc.release();
+  delete a;
+}
+
+/* gather sequences that already live in device memory into the aligner's staging layout */
+WFB_KERNEL(wfb_gather_kernel, const WfbPairDesc* pairs, int npairs, const uint8_t* src, const long long* src_p_off,
+           const long long* src_t_off, uint8_t* seq) {
+  WFB_KERNEL_PROLOGUE
+  for (int i = bid; i < npairs; i += nblocks) {
+    const WfbPairDesc pd = pairs[i];
+    const uint8_t* sp = src + src_p_off[i];
+    const uint8_t* st = src + src_t_off[i];
+    for (int j = WFB_TID; j < pd.plen; j += WFB_NT) seq[pd.p_off + j] = sp[j];
+    for (int j = WFB_TID; j < pd.tlen; j += WFB_NT) seq[pd.t_off + j] = st[j];
+  }
+}
+
+static int gap_affine2p_score(const char* ops, int n, const WfbPen& p) {
+  /* cigar_score_gap_affine2p, deps/WFA2-lib/alignment/cigar.c:304-342 (match = 0) */
+  int score = 0, i = 0;
+  while (i < n) {
+    int j = i;
+    while (j < n && ops[j] == ops[i]) ++j;
+    const int len = j - i;
+    if (ops[i] == 'X') score += p.x * len;
+    else if (ops[i] == 'I' || ops[i] == 'D') score += std::min(p.o1 + p.e1 * len, p.o2 + p.e2 * len);
+    i = j;
+  }
+  return -score;
+}
+
+/* Core: sequences are described by (host pointers) or (device buffer + offsets). */
+static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const char* d_src, const int64_t* src_p_off,
+                      const int32_t* src_p_len, const int64_t* src_t_off, const int32_t* src_t_len, char* ops,
+                      int64_t ops_cap, wfb_aln_result_t* results, wfb_align_stats_t* stats) {
+  if (!a || n < 0 || (n > 0 && (!results || !ops))) { g_last_error = "bad argument"; return WFB_EINVAL; }
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return WFB_OK;
+#ifndef WFB_EMU
+  WFB_CHECK(cudaSetDevice(a->device));
+#endif
+  const WfbPen pen = a->pen;
+  wfb_stream_t s = a->stream;
+  /* ---- layout ---- */
+  std::vector<WfbPairDesc> pd((size_t)n);
+  long long seq_bytes = 16, slot_bytes = 0;
+  int maxP = 0, maxT = 0;
+  for (int i = 0; i < n; ++i) {
+    const int plen = hpairs ? hpairs[i].pattern_len : src_p_len[i];
+    const int tlen = hpairs ? hpairs[i].text_len : src_t_len[i];
+    if (plen < 0 || tlen < 0 || (hpairs && ((plen && !hpairs[i].pattern) || (tlen && !hpairs[i].text)))) {
+      g_last_error = "bad pair";
+      return WFB_EINVAL;
+    }
+    pd[i].plen = plen; pd[i].tlen = tlen;
+    pd[i].p_off = seq_bytes;    seq_bytes = align_up(seq_bytes + plen + 16, 16);
+    pd[i].t_off = seq_bytes;    seq_bytes = align_up(seq_bytes + tlen + 16, 16);
+    pd[i].prev_off = seq_bytes; seq_bytes = align_up(seq_bytes + plen + 16, 16);
+    pd[i].trev_off = seq_bytes; seq_bytes = align_up(seq_bytes + tlen + 16, 16);
+    pd[i].ops_off = slot_bytes; slot_bytes = align_up(slot_bytes + plen + tlen + 8, 8);
+    maxP = std::max(maxP, plen); maxT = std::max(maxT, tlen);
+  }
+  {
+    /* worst case a pair needs plen+tlen ops; demand that much so no result can be truncated */
+    long long need = 0;
+    for (int i = 0; i < n; ++i) need += pd[i].plen + pd[i].tlen;
+    if (need > ops_cap) { g_last_error = "ops buffer too small (need sum(pattern_len+text_len))"; return WFB_ECAP; }
+  }
+  /* ---- device buffers ---- */
+  if (a->d_seq.ensure((size_t)seq_bytes + 64) || a->d_pairs.ensure(sizeof(WfbPairDesc) * (size_t)n) ||
+      a->d_slots.ensure((size_t)slot_bytes + 64) || a->d_dense.ensure((size_t)slot_bytes + 64) ||
+      a->d_len.ensure(sizeof(int) * (size_t)n) || a->d_status.ensure(sizeof(int) * (size_t)n) ||
+      a->d_counters.ensure(sizeof(WfbCounters)) || a->d_ctrl.ensure(sizeof(int) * 16)) {
+    g_last_error = "device allocation failed (inputs)";
+    return WFB_ENOMEM;
+  }
+  uint8_t* d_seq = (uint8_t*)a->d_seq.p;
+  WfbPairDesc* d_pairs = (WfbPairDesc*)a->d_pairs.p;
+  char* d_slots = (char*)a->d_slots.p;
+  char* d_dense = (char*)a->d_dense.p;
+  int* d_len = (int*)a->d_len.p;
+  int* d_status = (int*)a->d_status.p;
+  WfbCounters* d_counters = (WfbCounters*)a->d_counters.p;
+  int* d_ctrl = (int*)a->d_ctrl.p; /* [0] break task counter, [1] base task counter, [2] n_break_next, [3] n_base_next */
+#ifndef WFB_EMU
+  WFB_CHECK(cudaEventRecord(a->ev[0], s));
+#endif
+  WFB_H2D(d_pairs, pd.data(), sizeof(WfbPairDesc) * (size_t)n, s);
+  if (hpairs) {
+    /* pack the forward copies in pinned memory, one H2D */
+    if (a->h_seq.ensure((size_t)seq_bytes)) { g_last_error = "pinned allocation failed"; return WFB_ENOMEM; }
+    uint8_t* hs = (uint8_t*)a->h_seq.p;
+    /* only the forward regions are written; the device-side reversed regions are filled by a kernel.
+     * Copy the span [first p_off, last t_off+tlen) in one go. */
+    for (int i = 0; i < n; ++i) {
+      memcpy(hs + pd[i].p_off, hpairs[i].pattern, (size_t)pd[i].plen);
+      memset(hs + pd[i].p_off + pd[i].plen, 0, 16);
+      memcpy(hs + pd[i].t_off, hpairs[i].text, (size_t)pd[i].tlen);
+      memset(hs + pd[i].t_off + pd[i].tlen, 0, 16);
+    }
+    WFB_H2D(d_seq, hs, (size_t)seq_bytes, s);
+  } else {
+    if (a->d_srcoff.ensure(sizeof(long long) * 2 * (size_t)n)) { g_last_error = "device allocation failed"; return WFB_ENOMEM; }
+    long long* d_off = (long long*)a->d_srcoff.p;
+    std::vector<long long> tmp((size_t)2 * n);
+    for (int i = 0; i < n; ++i) { tmp[i] = src_p_off[i]; tmp[n + i] = src_t_off[i]; }
+    WFB_H2D(d_off, tmp.data(), sizeof(long long) * 2 * (size_t)n, s);
+    WFB_STREAM_SYNC(s); /* tmp goes out of scope */
+    WFB_MEMSET(d_seq, 0, (size_t)seq_bytes, s);
+    WFB_LAUNCH(wfb_gather_kernel, std::min(n, a->sm_count * 8), 256, s, d_pairs, n, (const uint8_t*)d_src, d_off, d_off + n, d_seq);
+  }
+  WFB_LAUNCH(wfb_reverse_kernel, std::min(n, a->sm_count * 8), 256, s, d_pairs, n, d_seq);
+  WFB_MEMSET(d_slots, 0, (size_t)slot_bytes, s);
+  WFB_MEMSET(d_status, 0, sizeof(int) * (size_t)n, s);
+  WFB_MEMSET(d_counters, 0, sizeof(WfbCounters), s);
+  /* ---- initial tasks (wavefront_bialign :1279-1283) ---- */
+  std::vector<WfbTask> t_break, t_base;
+  for (int i = 0; i < n; ++i) {
+    WfbTask t;
+    t.pair = i; t.pb = 0; t.pe = pd[i].plen; t.tb = 0; t.te = pd[i].tlen;
+    t.cbegin = WFB_M; t.cend = WFB_M;
+    const bool min_length = std::max(pd[i].plen, pd[i].tlen) <= WFB_FALLBACK_MIN_LENGTH;
+    t.score_remaining = min_length ? 0 : INT_MAX;
+    if (pd[i].plen == 0 || pd[i].tlen == 0 || !min_length) t_break.push_back(t);
+    else t_base.push_back(t);
+  }
+  /* longest first: the level's makespan is bounded by its slowest CTA */
+  std::stable_sort(t_break.begin(), t_break.end(), [](const WfbTask& x, const WfbTask& y) {
+    return (long long)(x.pe + x.te) > (long long)(y.pe + y.te);
+  });
+  /* ---- workspaces ---- */
+  const int W = (int)align_up(maxP + maxT + 8, 8);
+  const long long ws_stride = 2LL * pen.R * 5 * W;
+  const int score_cap = std::max(WFB_RECOVERY_MIN_SCORE, pen.x * WFB_FALLBACK_MIN_LENGTH) + 12;
+  const long long arena_stride = 5LL * (score_cap + 2) * (score_cap + 2) + 64;
+  const int maxruns = 2 * score_cap + 16;
+  const size_t base_cta_bytes = (size_t)arena_stride * 4 + (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta) + (size_t)maxruns * sizeof(WfbRun);
+  int cta_base = a->sm_count * 8;
+  int cta_break = a->sm_count * 3;
+  {
+    const uint64_t budget = a->workspace_bytes;
+    const uint64_t base_budget = std::min<uint64_t>(budget / 4, (uint64_t)cta_base * base_cta_bytes);
+    cta_base = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)cta_base, base_budget / base_cta_bytes));
+    const uint64_t break_budget = budget - (uint64_t)cta_base * base_cta_bytes;
+    const uint64_t per = (uint64_t)ws_stride * 4;
+    cta_break = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)cta_break, break_budget / per));
+    /* indices inside one CTA's workspace are 32-bit */
+    if (ws_stride >= (1LL << 31)) { g_last_error = "pair too long for 32-bit wavefront indexing"; return WFB_EINVAL; }
+  }
+  cta_break = std::max(1, std::min<int>(cta_break, (int)std::max<size_t>(1, std::max(t_break.size(), (size_t)n))));
+  if (a->d_ws.ensure((size_t)cta_break * (size_t)ws_stride * 4) || a->d_arena.ensure((size_t)cta_base * (size_t)arena_stride * 4) ||
+      a->d_log.ensure((size_t)cta_base * (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta)) ||
+      a->d_runs.ensure((size_t)cta_base * (size_t)maxruns * sizeof(WfbRun))) {
+    g_last_error = "device allocation failed (workspace)";
+    return WFB_ENOMEM;
+  }
+  /* ---- level loop ---- */
+  size_t n_break = t_break.size(), n_base = t_base.size();
+  int cur = 0;
+  {
+    if (a->d_q[0].ensure(sizeof(WfbTask) * std::max<size_t>(n_break, 1)) || a->d_q[2].ensure(sizeof(WfbTask) * std::max<size_t>(n_base, 1))) {
+      g_last_error = "device allocation failed (queues)";
+      return WFB_ENOMEM;
+    }
+    if (n_break) WFB_H2D(a->d_q[0].p, t_break.data(), sizeof(WfbTask) * n_break, s);
+    if (n_base) WFB_H2D(a->d_q[2].p, t_base.data(), sizeof(WfbTask) * n_base, s);
+    WFB_STREAM_SYNC(s); /* host vectors + pd must stay alive until copied */
+  }
+  double break_ms = 0.0;
+  uint64_t levels = 0;
+  while (n_break || n_base) {
+    ++levels;
+    const int nxt = cur ^ 1;
+    const size_t cap_next = std::max<size_t>(2 * n_break, 1);
+    if (a->d_q[nxt].ensure(sizeof(WfbTask) * cap_next) || a->d_q[2 + nxt].ensure(sizeof(WfbTask) * cap_next)) {
+      g_last_error = "device allocation failed (queues)";
+      return WFB_ENOMEM;
+    }
+    WFB_MEMSET(d_ctrl, 0, sizeof(int) * 16, s);
+    WfbQueue qb, qs;
+    qb.tasks = (WfbTask*)a->d_q[nxt].p; qb.count = d_ctrl + 2; qb.cap = (int)cap_next;
+    qs.tasks = (WfbTask*)a->d_q[2 + nxt].p; qs.count = d_ctrl + 3; qs.cap = (int)cap_next;
+    if (n_break) {
+#ifndef WFB_EMU
+      WFB_CHECK(cudaEventRecord(a->ev[2], s));
+#endif
+      WFB_LAUNCH(wfb_break_kernel, (int)std::min<size_t>(n_break, (size_t)cta_break), kBreakThreads, s,
+                 (const WfbTask*)a->d_q[cur].p, (int)n_break, d_ctrl + 0, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq,
+                 (int32_t*)a->d_ws.p, ws_stride, W, pen, qb, qs, d_slots, d_status, d_counters);
+#ifndef WFB_EMU
+      WFB_CHECK(cudaEventRecord(a->ev[3], s));
+#endif
+    }
+    if (n_base) {
+      WFB_LAUNCH(wfb_base_kernel, (int)std::min<size_t>(n_base, (size_t)cta_base), kBaseThreads, s,
+                 (const WfbTask*)a->d_q[2 + cur].p, (int)n_base, d_ctrl + 1, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq,
+                 (int32_t*)a->d_arena.p, arena_stride, (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, pen,
+                 d_slots, d_status, d_counters);
+    }
+    int ctrl[4] = {0, 0, 0, 0};
+    WFB_D2H(ctrl, d_ctrl, sizeof(int) * 4, s);
+    WFB_STREAM_SYNC(s);
+#ifndef WFB_EMU
+    {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { g_last_error = std::string("kernel: ") + cudaGetErrorString(e); return WFB_ECUDA; }
+      if (n_break) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a->ev[2], a->ev[3]);
+        break_ms += ms;
+      }
+    }
+#endif
+    n_break = (size_t)std::min<long long>(ctrl[2], (long long)cap_next);
+    n_base = (size_t)std::min<long long>(ctrl[3], (long long)cap_next);
+    cur = nxt;
+    if (levels > 4096) { g_last_error = "task recursion did not converge"; return WFB_ECUDA; }
+  }
+  /* ---- compaction + results ---- */
+  WFB_LAUNCH(wfb_compact_kernel, std::min(n, a->sm_count * 8), 256, s, (const WfbPairDesc*)d_pairs, n, (const char*)d_slots, d_dense, d_len);
+#ifndef WFB_EMU
+  WFB_CHECK(cudaEventRecord(a->ev[1], s));
+#endif
+  if (a->h_dense.ensure((size_t)slot_bytes + 64) || a->h_misc.ensure(sizeof(int) * 2 * (size_t)n + sizeof(WfbCounters))) {
+    g_last_error = "pinned allocation failed";
+    return WFB_ENOMEM;
+  }
+  char* h_dense = (char*)a->h_dense.p;
+  int* h_len = (int*)a->h_misc.p;
+  int* h_status = h_len + n;
+  WfbCounters* h_cnt = (WfbCounters*)(h_status + n);
+  WFB_D2H(h_len, d_len, sizeof(int) * (size_t)n, s);
+  WFB_D2H(h_status, d_status, sizeof(int) * (size_t)n, s);
+  WFB_D2H(h_cnt, d_counters, sizeof(WfbCounters), s);
+  WFB_D2H(h_dense, d_dense, (size_t)slot_bytes, s);
+  WFB_STREAM_SYNC(s);
+  int64_t out_off = 0;
+  for (int i = 0; i < n; ++i) {
+    wfb_aln_result_t& r = results[i];
+    r.status = h_status[i];
+    r.ops_offset = out_off;
+    r.ops_len = 0;
+    r.score = 0;
+    r.reserved_ = 0;
+    if (r.status == 0) {
+      const int len = h_len[i];
+      if (out_off + len > ops_cap) { g_last_error = "ops buffer too small"; return WFB_ECAP; }
+      memcpy(ops + out_off, h_dense + pd[i].ops_off, (size_t)len);
+      r.ops_len = len;
+      r.score = gap_affine2p_score(ops + out_off, len, pen);
+      out_off += len;
+    }
+  }
+  if (stats) {
+    stats->cells = h_cnt->cells;
+    stats->extend_matches = h_cnt->extend_matches;
+    stats->overlap_tests = h_cnt->overlap_tests;
+    stats->score_steps = h_cnt->score_steps;
+    stats->break_tasks = h_cnt->break_tasks;
+    stats->base_tasks = h_cnt->base_tasks;
+    stats->base_cells = h_cnt->base_cells;
+    stats->base_extend_matches = h_cnt->base_extend_matches;
+    stats->base_score_steps = h_cnt->base_score_steps;
+    stats->levels = levels;
+    stats->break_kernel_ms = break_ms;
+#ifndef WFB_EMU
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a->ev[0], a->ev[1]);
+    stats->kernel_ms = ms;
+#endif
+  }
+  return WFB_OK;
+}
+
+extern "C" int wfb_align_batch(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_t n, char* ops, int64_t ops_cap,
+                               wfb_aln_result_t* results, wfb_align_stats_t* stats) {
+  if (n > 0 && !pairs) { g_last_error = "pairs == NULL"; return WFB_EINVAL; }
+  return align_impl(a, n, pairs, nullptr, nullptr, nullptr, nullptr, nullptr, ops, ops_cap, results, stats);
+}
+
+extern "C" int wfb_align_batch_device(wfb_aligner_t* a, const char* d_seq, const int64_t* pattern_off, const int32_t* pattern_len,
+                                      const int64_t* text_off, const int32_t* text_len, int32_t n, char* ops, int64_t ops_cap,
+                                      wfb_aln_result_t* results, wfb_align_stats_t* stats) {
+  if (n > 0 && (!d_seq || !pattern_off || !pattern_len || !text_off || !text_len)) { g_last_error = "NULL argument"; return WFB_EINVAL; }
+  return align_impl(a, n, nullptr, d_seq, pattern_off, pattern_len, text_off, text_len, ops, ops_cap, results, stats);
+}
+
+extern "C" void* wfb_device_malloc(int device, uint64_t bytes) {
+#ifndef WFB_EMU
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+#endif
+  void* p = nullptr;
+  if (dev_malloc(&p, (size_t)bytes) != 0) return nullptr;
+  return p;
+}
+extern "C" void wfb_device_free(int device, void* p) {
+#ifndef WFB_EMU
+  cudaSetDevice(device);
+#endif
+  (void)device;
+  dev_free(p);
+}
+extern "C" int wfb_memcpy_h2d(int device, void* dst, const void* src, uint64_t bytes) {
+#ifndef WFB_EMU
+  WFB_CHECK(cudaSetDevice(device));
+  WFB_CHECK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+#else
+  (void)device;
+  memcpy(dst, src, (size_t)bytes);
+#endif
+  return WFB_OK;
+}

@@ -1,0 +1,905 @@
+// wfa_kernels.h — gap-affine-2p biWFA on the GPU (sm_100a), batched over mapping records.
+//
+// What it computes (bit-identical operation strings to the reference):
+//   wavefront_bialign            deps/WFA2-lib/wavefront/wavefront_bialign.c:1266-1293
+//   wavefront_bialign_alignment  :1144-1221   (recursion -> level-synchronous task queues here)
+//   ..._find_breakpoint          :974-1082    (wfb_break_kernel: one CTA per sub-problem)
+//   ..._overlap / breakpoint_*   :877-955, 508-571, 828-872
+//   wavefront_compute_affine2p   wavefront_compute_affine2p.c:45-106,334-368 + wavefront_compute.c
+//   wavefront_extend_end2end     wavefront_extend.c:86-211, wavefront_extend_kernels.c:68-152
+//   wavefront_bialign_base       wavefront_bialign.c:159-189 = unialign + backtrace_affine
+//                                (wfb_base_kernel: one small CTA per sub-problem)
+//
+// B200 mapping (not a translation of the CPU code):
+//   * the reference's recursive divide & conquer becomes two device-resident task queues
+//     (breakpoint tasks, base tasks) drained level by level; children are appended with atomics;
+//   * one CTA owns one sub-problem; diagonals are spread over the CTA's threads (coalesced 32-bit
+//     offsets), compute + extend + trim are FUSED in one pass with ONE __syncthreads per score;
+//   * wavefront metadata ([lo,hi], existence) lives in shared memory as a ring of scope+1 scores,
+//     trimmed ends are found with warp redux + shared-memory atomics instead of serial scans;
+//   * the forward and reverse aligners read the sequences from a forward and a pre-reversed copy so
+//     that extension is always an ascending, word-wise (4 bases / iteration) compare;
+//   * operation strings are written straight to their final anti-diagonal slot (v+h) of the pair's
+//     output buffer by whichever task produces them, then compacted — no serial concatenation.
+#pragma once
+#include "wfb_rt.h"
+
+#define WFB_OFFSET_NULL (INT32_MIN / 2) /* wavefront_offset.h:44 */
+#define WFB_RMAX 40                     /* max ring slots = max_score_scope + 1 */
+#define WFB_FALLBACK_MIN_SCORE 250      /* wavefront_bialign.c:52 */
+#define WFB_FALLBACK_MIN_LENGTH 100     /* :53 */
+#define WFB_RECOVERY_MIN_SCORE 500      /* :54 */
+
+enum { WFB_M = 0, WFB_I1 = 1, WFB_I2 = 2, WFB_D1 = 3, WFB_D2 = 4 };
+enum { WFB_ST_OK = 0, WFB_ST_END_REACHED = 1, WFB_ST_END_UNREACHABLE = 2 };
+/* per-pair status codes written by the kernels (0 = fine) */
+enum { WFB_PAIR_OK = 0, WFB_PAIR_UNATTAINABLE = -3, WFB_PAIR_BASE_SCORE_CAP = -4, WFB_PAIR_QUEUE_OVERFLOW = -5,
+       WFB_PAIR_BACKTRACE = -6 };
+
+struct WfbPen {
+  int x, o1, e1, o2, e2;
+  int scope; /* max_score_scope = max(x, o1+e1, o2+e2) + 1, wavefront_components.c:101-112 */
+  int R;     /* ring slots = scope + 1 */
+};
+
+struct WfbTask { /* one sub-problem [pb,pe) x [tb,te) of a pair */
+  int pair;
+  int pb, pe, tb, te;
+  int cbegin, cend;
+  int score_remaining;
+};
+
+struct WfbPairDesc {
+  long long p_off, t_off;       /* forward copies inside the sequence buffer            */
+  long long prev_off, trev_off; /* reversed copies                                      */
+  long long ops_off;            /* first byte of this pair's (plen+tlen) op slots       */
+  int plen, tlen;
+};
+
+struct WfbQueue {
+  WfbTask* tasks;
+  int* count;
+  int cap;
+};
+
+struct WfbCounters {
+  unsigned long long cells, extend_matches, overlap_tests, score_steps, break_tasks, base_tasks;
+  unsigned long long base_cells, base_extend_matches, base_score_steps; /* base kernel's share */
+};
+
+struct WfbRing { /* shared-memory wavefront metadata of the last R scores */
+  int lo[WFB_RMAX][5];
+  int hi[WFB_RMAX][5];
+  int boff[WFB_RMAX][5]; /* element offset so that cell(k) = basep[boff + k] */
+  unsigned char ex[WFB_RMAX][5];
+};
+
+struct WfbIn {
+  const int32_t* p;
+  int lo, hi;
+};
+
+struct WfbBreakpoint {
+  int score, score_forward, score_reverse;
+  int k_forward, k_reverse, offset_forward, offset_reverse;
+  int component;
+};
+
+/* wavefront_compute_get_*wavefront (wavefront_compute.c:266-305): null => lo=1, hi=-1 */
+WFB_DEV WfbIn wfb_fetch(const WfbRing& r, const int32_t* basep, int R, int comp, int score) {
+  WfbIn w;
+  w.p = basep;
+  w.lo = 1;
+  w.hi = -1;
+  if (score >= 0) {
+    const int s = score % R;
+    if (r.ex[s][comp] && r.lo[s][comp] <= r.hi[s][comp]) {
+      w.lo = r.lo[s][comp];
+      w.hi = r.hi[s][comp];
+      w.p = basep + r.boff[s][comp];
+    }
+  }
+  return w;
+}
+WFB_DEV int32_t wfb_get(const WfbIn& w, int k) { return (k >= w.lo && k <= w.hi) ? w.p[k] : WFB_OFFSET_NULL; }
+
+/* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 7 bytes past
+ * the cap (sequence buffers are padded). wavefront_extend_kernels.c:68-92 does the same 8 bytes at a
+ * time on the CPU. */
+WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
+#ifdef WFB_EMU
+  int n = 0;
+  while (n < limit && p[n] == t[n]) ++n;
+  return n;
+#else
+  if (limit <= 0) return 0;
+  const uintptr_t pa = (uintptr_t)p, ta = (uintptr_t)t;
+  const uint32_t* pw = (const uint32_t*)(pa & ~(uintptr_t)3);
+  const uint32_t* tw = (const uint32_t*)(ta & ~(uintptr_t)3);
+  const unsigned ps = (unsigned)(pa & 3) * 8u, ts = (unsigned)(ta & 3) * 8u;
+  uint32_t p0 = wfb_ldg32(pw), t0 = wfb_ldg32(tw);
+  int n = 0;
+  while (n < limit) {
+    const uint32_t p1 = wfb_ldg32(++pw), t1 = wfb_ldg32(++tw);
+    const uint32_t x = __funnelshift_r(p0, p1, ps) ^ __funnelshift_r(t0, t1, ts);
+    if (x) {
+      n += (__ffs((int)x) - 1) >> 3;
+      break;
+    }
+    n += 4;
+    p0 = p1;
+    t0 = t1;
+  }
+  return n < limit ? n : limit;
+#endif
+}
+
+WFB_DEV bool wfb_inbounds(int32_t off, int k, int plen, int tlen) {
+  return (uint32_t)off <= (uint32_t)tlen && (uint32_t)(off - k) <= (uint32_t)plen;
+}
+
+/* Per-thread accumulators that live in registers for the whole task. */
+struct WfbAcc {
+  unsigned long long cells;   /* uniform, counted by thread 0 */
+  unsigned long long overlap; /* uniform, counted by thread 0 */
+  unsigned long long matches; /* per thread */
+  unsigned long long steps;   /* uniform */
+};
+
+/*
+ * One score step of one direction: compute the five component wavefronts of `score` from the ring,
+ * extend M along matches, trim the ends, detect end-of-alignment. Exactly one barrier.
+ * Returns WFB_ST_OK / WFB_ST_END_REACHED / WFB_ST_END_UNREACHABLE (uniform over the CTA).
+ *   alloc(slot, lo, hi, ob[5]) assigns storage for the outputs (uniform).
+ *   red_maxak[3] : shared-memory reduction slots, rotated by score % 3.
+ */
+template <class Alloc>
+WFB_DEV int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
+                     const uint8_t* tseq, int plen, int tlen, int cend, int& num_null, Alloc& alloc, int* red_maxak,
+                     int& max_ak_out, WfbAcc& acc) {
+  const int R = pen.R, slot = score % R, nslot = (score + 1) % R;
+  const int par = score % 3, npar = (score + 1) % 3;
+  const WfbIn m_misms = wfb_fetch(ring, basep, R, WFB_M, score - pen.x);
+  const WfbIn m_open1 = wfb_fetch(ring, basep, R, WFB_M, score - pen.o1 - pen.e1);
+  const WfbIn m_open2 = wfb_fetch(ring, basep, R, WFB_M, score - pen.o2 - pen.e2);
+  const WfbIn i1_ext = wfb_fetch(ring, basep, R, WFB_I1, score - pen.e1);
+  const WfbIn i2_ext = wfb_fetch(ring, basep, R, WFB_I2, score - pen.e2);
+  const WfbIn d1_ext = wfb_fetch(ring, basep, R, WFB_D1, score - pen.e1);
+  const WfbIn d2_ext = wfb_fetch(ring, basep, R, WFB_D2, score - pen.e2);
+  const bool n_m = m_misms.lo > m_misms.hi, n_o1 = m_open1.lo > m_open1.hi, n_o2 = m_open2.lo > m_open2.hi;
+  const bool n_i1 = i1_ext.lo > i1_ext.hi, n_i2 = i2_ext.lo > i2_ext.hi;
+  const bool n_d1 = d1_ext.lo > d1_ext.hi, n_d2 = d2_ext.lo > d2_ext.hi;
+  max_ak_out = 0;
+  acc.steps += 1;
+  if (n_m && n_o1 && n_o2 && n_i1 && n_i2 && n_d1 && n_d2) {
+    /* wavefront_compute_affine2p.c:341-351 + wavefront_extend.c:95-103 */
+    num_null++;
+    if (WFB_TID == 0) {
+      for (int c = 0; c < 5; ++c) {
+        ring.ex[slot][c] = 0;
+        ring.lo[nslot][c] = INT_MAX;
+        ring.hi[nslot][c] = INT_MIN;
+      }
+      red_maxak[npar] = 0;
+    }
+    WFB_SYNC();
+    return (num_null > pen.scope) ? WFB_ST_END_UNREACHABLE : WFB_ST_OK;
+  }
+  num_null = 0;
+  /* wavefront_compute_limits_input, wavefront_compute.c:40-86 */
+  int lo = m_misms.lo, hi = m_misms.hi;
+  lo = min(lo, m_open1.lo - 1); hi = max(hi, m_open1.hi + 1);
+  lo = min(lo, i1_ext.lo + 1);  hi = max(hi, i1_ext.hi + 1);
+  lo = min(lo, d1_ext.lo - 1);  hi = max(hi, d1_ext.hi - 1);
+  lo = min(lo, m_open2.lo - 1); hi = max(hi, m_open2.hi + 1);
+  lo = min(lo, i2_ext.lo + 1);  hi = max(hi, i2_ext.hi + 1);
+  lo = min(lo, d2_ext.lo - 1);  hi = max(hi, d2_ext.hi - 1);
+  /* wavefront_compute_allocate_output, wavefront_compute.c:447-493 */
+  const bool ex_i1 = !n_o1 || !n_i1, ex_d1 = !n_o1 || !n_d1;
+  const bool ex_i2 = !n_o2 || !n_i2, ex_d2 = !n_o2 || !n_d2;
+  int ob[5];
+  alloc(slot, lo, hi, ob);
+  if (WFB_TID == 0) {
+    ring.ex[slot][WFB_M] = 1;
+    ring.ex[slot][WFB_I1] = ex_i1;
+    ring.ex[slot][WFB_I2] = ex_i2;
+    ring.ex[slot][WFB_D1] = ex_d1;
+    ring.ex[slot][WFB_D2] = ex_d2;
+    for (int c = 0; c < 5; ++c) {
+      ring.boff[slot][c] = ob[c];
+      ring.lo[nslot][c] = INT_MAX;
+      ring.hi[nslot][c] = INT_MIN;
+    }
+    red_maxak[npar] = 0;
+    acc.cells += (unsigned long long)(hi - lo + 1);
+  }
+  int32_t* const out_m = basep + ob[WFB_M];
+  int32_t* const out_i1 = basep + ob[WFB_I1];
+  int32_t* const out_i2 = basep + ob[WFB_I2];
+  int32_t* const out_d1 = basep + ob[WFB_D1];
+  int32_t* const out_d2 = basep + ob[WFB_D2];
+  int tlo_m = INT_MAX, thi_m = INT_MIN, tlo_i1 = INT_MAX, thi_i1 = INT_MIN, tlo_i2 = INT_MAX, thi_i2 = INT_MIN;
+  int tlo_d1 = INT_MAX, thi_d1 = INT_MIN, tlo_d2 = INT_MAX, thi_d2 = INT_MIN;
+  int tmax = 0;
+  /* wavefront_compute_affine2p_idm (wavefront_compute_affine2p.c:45-106) fused with
+   * wavefront_extend_matches_packed_end2end_max (wavefront_extend_kernels.c:125-152) and
+   * wavefront_compute_trim_ends (wavefront_compute.c:579-613) */
+  for (int k = lo + WFB_TID; k <= hi; k += WFB_NT) {
+    const int32_t ins1 = max(wfb_get(m_open1, k - 1), wfb_get(i1_ext, k - 1)) + 1;
+    const int32_t ins2 = max(wfb_get(m_open2, k - 1), wfb_get(i2_ext, k - 1)) + 1;
+    const int32_t del1 = max(wfb_get(m_open1, k + 1), wfb_get(d1_ext, k + 1));
+    const int32_t del2 = max(wfb_get(m_open2, k + 1), wfb_get(d2_ext, k + 1));
+    const int32_t misms = wfb_get(m_misms, k) + 1;
+    int32_t mx = max(max(del1, del2), max(misms, max(ins1, ins2)));
+    if (wfb_inbounds(mx, k, plen, tlen)) {
+      const int v = mx - k, h = mx;
+      const int run = wfb_match_run(pseq + v, tseq + h, min(plen - v, tlen - h));
+      mx += run;
+      acc.matches += (unsigned)run;
+      tmax = max(tmax, 2 * mx - k);
+      tlo_m = min(tlo_m, k);
+      thi_m = max(thi_m, k);
+    } else {
+      mx = WFB_OFFSET_NULL;
+    }
+    out_m[k] = mx;
+    if (ex_i1) { out_i1[k] = ins1; if (wfb_inbounds(ins1, k, plen, tlen)) { tlo_i1 = min(tlo_i1, k); thi_i1 = max(thi_i1, k); } }
+    if (ex_i2) { out_i2[k] = ins2; if (wfb_inbounds(ins2, k, plen, tlen)) { tlo_i2 = min(tlo_i2, k); thi_i2 = max(thi_i2, k); } }
+    if (ex_d1) { out_d1[k] = del1; if (wfb_inbounds(del1, k, plen, tlen)) { tlo_d1 = min(tlo_d1, k); thi_d1 = max(thi_d1, k); } }
+    if (ex_d2) { out_d2[k] = del2; if (wfb_inbounds(del2, k, plen, tlen)) { tlo_d2 = min(tlo_d2, k); thi_d2 = max(thi_d2, k); } }
+  }
+  /* trimmed [lo,hi] of each component = min / max diagonal holding an in-bounds offset */
+  {
+    const int lane = wfb_lane();
+    int v;
+    v = wfb_warp_min(tlo_m);  if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_M], v);
+    v = wfb_warp_max(thi_m);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_M], v);
+    if (ex_i1) {
+      v = wfb_warp_min(tlo_i1); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_I1], v);
+      v = wfb_warp_max(thi_i1); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_I1], v);
+    }
+    if (ex_i2) {
+      v = wfb_warp_min(tlo_i2); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_I2], v);
+      v = wfb_warp_max(thi_i2); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_I2], v);
+    }
+    if (ex_d1) {
+      v = wfb_warp_min(tlo_d1); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_D1], v);
+      v = wfb_warp_max(thi_d1); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_D1], v);
+    }
+    if (ex_d2) {
+      v = wfb_warp_min(tlo_d2); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_D2], v);
+      v = wfb_warp_max(thi_d2); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_D2], v);
+    }
+    v = wfb_warp_max(tmax);   if (lane == 0 && v > 0) wfb_smem_max(&red_maxak[par], v);
+  }
+  WFB_SYNC();
+  max_ak_out = red_maxak[par];
+  /* wavefront_termination_end2end, wavefront_termination.c:37-114 */
+  const int ak = tlen - plen;
+  if (ring.ex[slot][cend] && ring.lo[slot][cend] <= ak && ak <= ring.hi[slot][cend]) {
+    if (basep[ring.boff[slot][cend] + ak] >= tlen) return WFB_ST_END_REACHED;
+  }
+  return WFB_ST_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Breakpoint overlap scan: wavefront_bialign_overlap (:877-955) with breakpoint_indel2indel
+ * (:508-571) / breakpoint_m2m (:828-872). All candidate (score_i, component) pairs are scanned in
+ * parallel for their first satisfying diagonal; thread 0 then replays the reference's sequential
+ * "first strictly better candidate wins" rule over those results. Two barriers.
+ * `found` (shared, scope*5 ints) must be all INT_MAX on entry and is restored on exit.
+ * ---------------------------------------------------------------------------------------------- */
+WFB_DEV int wfb_gap_of(const WfbPen& pen, int comp) {
+  return comp == WFB_M ? 0 : ((comp == WFB_I1 || comp == WFB_D1) ? pen.o1 : pen.o2);
+}
+
+WFB_DEV void wfb_overlap(const WfbRing& r0, const int32_t* base0, const WfbRing& r1, const int32_t* base1,
+                         const WfbPen& pen, int score_0, int score_1, bool bp_forward, int plen, int tlen,
+                         WfbBreakpoint* bp, int* found, WfbAcc& acc) {
+  const int R = pen.R, s0 = score_0 % R;
+  if (!r0.ex[s0][WFB_M]) return; /* uniform */
+  const int best0 = bp->score;
+  const int kinv = tlen - plen;
+  const int order[5] = {WFB_D2, WFB_I2, WFB_D1, WFB_I1, WFB_M};
+  for (int i = 0; i < pen.scope; ++i) {
+    const int score_i = score_1 - i;
+    if (score_i < 0) break;
+    const int si = score_i % R;
+    for (int j = 0; j < 5; ++j) {
+      const int c = order[j];
+      if (score_0 + score_i - wfb_gap_of(pen, c) >= best0) continue;
+      if (!r0.ex[s0][c] || !r1.ex[si][c]) continue;
+      const int lo_0 = r0.lo[s0][c], hi_0 = r0.hi[s0][c];
+      const int lo1r = r1.lo[si][c], hi1r = r1.hi[si][c];
+      if (lo_0 > hi_0 || lo1r > hi1r) continue;
+      const int lo_1 = kinv - hi1r, hi_1 = kinv - lo1r;
+      const int max_lo = max(lo_0, lo_1), min_hi = min(hi_0, hi_1);
+      if (min_hi < max_lo) continue;
+      const int32_t* p0 = base0 + r0.boff[s0][c];
+      const int32_t* p1 = base1 + r1.boff[si][c];
+      int kfound = INT_MAX;
+      for (int k0 = max_lo + WFB_TID; k0 <= min_hi; k0 += WFB_NT) {
+        const int k1 = kinv - k0;
+        const int32_t o0 = p0[k0], o1 = p1[k1];
+        if (o0 + o1 >= tlen) {
+          if (c != WFB_M) {
+            const int kk = bp_forward ? k0 : k1;
+            const int32_t oo = bp_forward ? o0 : o1;
+            if (oo - kk > plen || oo > tlen) continue;
+          }
+          kfound = k0;
+          break;
+        }
+      }
+      kfound = wfb_warp_min(kfound);
+      if (wfb_lane() == 0 && kfound != INT_MAX) wfb_smem_min(&found[i * 5 + j], kfound);
+      if (WFB_TID == 0) acc.overlap += (unsigned long long)(min_hi - max_lo + 1);
+    }
+  }
+  WFB_SYNC();
+  if (WFB_TID == 0) {
+    for (int i = 0; i < pen.scope; ++i) {
+      const int score_i = score_1 - i;
+      if (score_i < 0) break;
+      const int si = score_i % R;
+      for (int j = 0; j < 5; ++j) {
+        const int c = order[j];
+        const int cand = score_0 + score_i - wfb_gap_of(pen, c);
+        /* the reference `continue`s to the next i when a class (o2, o1, M) cannot improve; with
+         * o2 >= o1 >= 0 (checked on the host) that equals skipping each candidate individually */
+        const int k0 = found[i * 5 + j];
+        found[i * 5 + j] = INT_MAX;
+        if (cand >= bp->score || k0 == INT_MAX) continue;
+        const int k1 = kinv - k0;
+        const int32_t o0 = (base0 + r0.boff[s0][c])[k0];
+        const int32_t o1 = (base1 + r1.boff[si][c])[k1];
+        if (bp_forward) {
+          bp->score_forward = score_0; bp->score_reverse = score_i;
+          bp->k_forward = k0; bp->k_reverse = k1;
+          bp->offset_forward = o0; bp->offset_reverse = o1;
+        } else {
+          bp->score_forward = score_i; bp->score_reverse = score_0;
+          bp->k_forward = k1; bp->k_reverse = k0;
+          bp->offset_forward = o1; bp->offset_reverse = o0;
+        }
+        bp->score = cand;
+        bp->component = c;
+      }
+    }
+  }
+  WFB_SYNC();
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Task plumbing
+ * ---------------------------------------------------------------------------------------------- */
+WFB_DEV void wfb_push(const WfbQueue& q, const WfbTask& t, int* pair_status) {
+  const int idx = wfb_atomic_add(q.count, 1);
+  if (idx < q.cap) q.tasks[idx] = t;
+  else pair_status[t.pair] = WFB_PAIR_QUEUE_OVERFLOW;
+}
+
+/* Fill n ops of kind `op` starting at DP cell (v,h) (absolute pair coordinates); all threads. */
+WFB_DEV void wfb_fill_ops(char* ops, int v, int h, char op, int n) {
+  const int stride = (op == 'M' || op == 'X') ? 2 : 1;
+  for (int j = WFB_TID; j < n; j += WFB_NT) ops[v + h + j * stride] = op;
+}
+
+/* Dispatch one child sub-problem (wavefront_bialign_alignment :1159-1170): trivial cases are
+ * written immediately (all threads), the rest is queued by thread 0. */
+WFB_DEV void wfb_dispatch_child(const WfbTask& c, char* ops, const WfbQueue& q_break, const WfbQueue& q_base,
+                                int* pair_status) {
+  const int plen = c.pe - c.pb, tlen = c.te - c.tb;
+  if (tlen == 0) {
+    wfb_fill_ops(ops, c.pb, c.tb, 'D', plen);
+  } else if (plen == 0) {
+    wfb_fill_ops(ops, c.pb, c.tb, 'I', tlen);
+  } else if (WFB_TID == 0) {
+    if (c.score_remaining <= WFB_FALLBACK_MIN_SCORE) wfb_push(q_base, c, pair_status);
+    else wfb_push(q_break, c, pair_status);
+  }
+}
+
+struct WfbBreakShared {
+  WfbRing ring[2];
+  WfbBreakpoint bp;
+  int found[WFB_RMAX * 5];
+  int red_maxak[2][3];
+  int task_idx;
+};
+
+struct WfbAllocFixed { /* breakpoint kernel: every (slot, component) has a fixed row of W ints */
+  int dirbase; /* dir * R * 5 * W + kshift */
+  int W;
+  WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) const {
+    (void)lo; (void)hi;
+    for (int c = 0; c < 5; ++c) ob[c] = dirbase + (slot * 5 + c) * W;
+  }
+};
+
+WFB_DEV void wfb_ring_reset(WfbRing& r, int R) {
+  for (int i = WFB_TID; i < R * 5; i += WFB_NT) {
+    r.lo[i / 5][i % 5] = INT_MAX;
+    r.hi[i / 5][i % 5] = INT_MIN;
+    r.ex[i / 5][i % 5] = 0;
+    r.boff[i / 5][i % 5] = 0;
+  }
+}
+
+/* Score-0 wavefront + its extension (wavefront_aligner_init_wf, wavefront_aligner.c:314-383;
+ * first extend of wavefront_bialign_find_breakpoint :1003-1006 / wavefront_unialign :253).
+ * Thread 0 only; caller syncs. Returns via *st / *max_ak (shared). */
+WFB_DEV void wfb_init_score0(WfbRing& ring, int32_t* basep, int boff0, int cbegin, int cend, const uint8_t* pseq,
+                             const uint8_t* tseq, int plen, int tlen, int* st, int* max_ak, WfbAcc& acc) {
+  ring.ex[0][cbegin] = 1;
+  ring.lo[0][cbegin] = 0;
+  ring.hi[0][cbegin] = 0;
+  ring.boff[0][cbegin] = boff0;
+  int32_t off = 0;
+  *st = WFB_ST_OK;
+  *max_ak = 0;
+  if (cbegin == WFB_M) {
+    const int run = wfb_match_run(pseq, tseq, min(plen, tlen));
+    off = run;
+    acc.matches += (unsigned)run;
+    *max_ak = 2 * off;
+    /* termination (:37-114): needs the end component's wavefront at score 0 */
+    if (cend == WFB_M && tlen - plen == 0 && off >= tlen) *st = WFB_ST_END_REACHED;
+  }
+  basep[boff0 + 0] = off;
+}
+
+/*
+ * Breakpoint kernel: one CTA per sub-problem. Restates wavefront_bialign_find_breakpoint
+ * (wavefront_bialign.c:974-1082) + the dispatch of both halves (:1188-1212) + the exception path
+ * (:1083-1110).
+ */
+WFB_KERNEL(wfb_break_kernel, const WfbTask* tasks, int ntasks, int* task_counter, const WfbPairDesc* pairs,
+           const uint8_t* seq, int32_t* ws_all, long long ws_stride /* ints per CTA */, int W, WfbPen pen,
+           WfbQueue q_break, WfbQueue q_base, char* ops_all, int* pair_status, WfbCounters* counters) {
+  WFB_KERNEL_PROLOGUE
+  WFB_SHARED WfbBreakShared sh;
+  WFB_SHARED int sh_st[2];
+  WFB_SHARED int sh_ak[2];
+  int32_t* const ws = ws_all + (long long)bid * ws_stride;
+  WfbAcc acc;
+  acc.cells = acc.overlap = acc.matches = acc.steps = 0;
+  unsigned long long ntask_done = 0;
+  for (;;) {
+    WFB_SYNC();
+    if (WFB_TID == 0) sh.task_idx = wfb_atomic_add(task_counter, 1);
+    WFB_SYNC();
+    const int ti = sh.task_idx;
+    if (ti >= ntasks) break;
+    const WfbTask t = tasks[ti];
+    const WfbPairDesc pd = pairs[t.pair];
+    char* const ops = ops_all + pd.ops_off;
+    const int plen = t.pe - t.pb, tlen = t.te - t.tb;
+    ntask_done++;
+    /* trivial cases, wavefront_bialign.c:1160-1165 */
+    if (tlen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'D', plen); continue; }
+    if (plen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'I', tlen); continue; }
+    /* sequence views: forward reads the forward copies, reverse the reversed copies
+     * (wavefront_sequences.c:288-295) */
+    const uint8_t* pf = seq + pd.p_off + t.pb;
+    const uint8_t* tf = seq + pd.t_off + t.tb;
+    const uint8_t* pr = seq + pd.prev_off + (pd.plen - t.pe);
+    const uint8_t* tr = seq + pd.trev_off + (pd.tlen - t.te);
+    const int R = pen.R;
+    const int kshift = plen + 1;
+    WfbAllocFixed af, ar;
+    af.W = ar.W = W;
+    af.dirbase = kshift;
+    ar.dirbase = R * 5 * W + kshift;
+    wfb_ring_reset(sh.ring[0], R);
+    wfb_ring_reset(sh.ring[1], R);
+    for (int i = WFB_TID; i < WFB_RMAX * 5; i += WFB_NT) sh.found[i] = INT_MAX;
+    if (WFB_TID == 0) {
+      for (int d = 0; d < 2; ++d) for (int j = 0; j < 3; ++j) sh.red_maxak[d][j] = 0;
+      sh.bp.score = INT_MAX;
+    }
+    WFB_SYNC();
+    if (WFB_TID == 0) {
+      /* wavefront_bialign_init :114-143: reverse aligner swaps begin/end components */
+      int ob[5];
+      af(0, 0, 0, ob);
+      wfb_init_score0(sh.ring[0], ws, ob[t.cbegin], t.cbegin, t.cend, pf, tf, plen, tlen, &sh_st[0], &sh_ak[0], acc);
+      ar(0, 0, 0, ob);
+      wfb_init_score0(sh.ring[1], ws, ob[t.cend], t.cend, t.cbegin, pr, tr, plen, tlen, &sh_st[1], &sh_ak[1], acc);
+    }
+    WFB_SYNC();
+    int status = WFB_ST_OK; /* != OK => a direction reached the end (or is unreachable) */
+    int score_reached = 0;
+    int score_forward = 0, score_reverse = 0;
+    int forward_max_ak = sh_ak[0], reverse_max_ak = sh_ak[1];
+    int null_f = 0, null_r = 0;
+    if (sh_st[0] != WFB_ST_OK) { status = sh_st[0]; score_reached = 0; }
+    else if (sh_st[1] != WFB_ST_OK) { status = sh_st[1]; score_reached = 0; }
+    const int max_antidiagonal = plen + tlen - 1;
+    bool last_wf_forward = false;
+    int max_ak = 0;
+    /* phase 1 (:1010-1043): alternate until the furthest points of both directions may collide */
+    while (status == WFB_ST_OK) {
+      if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
+      ++score_forward;
+      int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], max_ak, acc);
+      if (forward_max_ak < max_ak) forward_max_ak = max_ak;
+      last_wf_forward = true;
+      if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
+      if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
+      ++score_reverse;
+      st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], max_ak, acc);
+      if (reverse_max_ak < max_ak) reverse_max_ak = max_ak;
+      last_wf_forward = false;
+      if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
+    }
+    /* phase 2 (:1045-1079): advance while scanning for overlaps */
+    const int gap_opening = max(pen.o1, pen.o2);
+    while (status == WFB_ST_OK) {
+      if (last_wf_forward) {
+        const int min_score_reverse = (score_reverse > pen.scope - 1) ? score_reverse - (pen.scope - 1) : 0;
+        if (score_forward + min_score_reverse - gap_opening >= sh.bp.score) break;
+        wfb_overlap(sh.ring[0], ws, sh.ring[1], ws, pen, score_forward, score_reverse, true, plen, tlen, &sh.bp, sh.found, acc);
+        ++score_reverse;
+        const int st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], max_ak, acc);
+        if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
+      }
+      const int min_score_forward = (score_forward > pen.scope - 1) ? score_forward - (pen.scope - 1) : 0;
+      if (min_score_forward + score_reverse - gap_opening >= sh.bp.score) break;
+      wfb_overlap(sh.ring[1], ws, sh.ring[0], ws, pen, score_reverse, score_forward, false, plen, tlen, &sh.bp, sh.found, acc);
+      ++score_forward;
+      const int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], max_ak, acc);
+      if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
+      last_wf_forward = true;
+    }
+    if (status != WFB_ST_OK) {
+      /* wavefront_bialign_find_breakpoint_exception :1083-1110 */
+      if (WFB_TID == 0) {
+        if (status == WFB_ST_END_REACHED && score_reached <= WFB_RECOVERY_MIN_SCORE) {
+          WfbTask c = t;
+          c.score_remaining = 0;
+          wfb_push(q_base, c, pair_status);
+        } else {
+          pair_status[t.pair] = WFB_PAIR_UNATTAINABLE;
+        }
+      }
+      continue;
+    }
+    /* both halves, :1188-1212 */
+    const WfbBreakpoint bp = sh.bp;
+    const int bh = bp.offset_forward, bv = bp.offset_forward - bp.k_forward;
+    WfbTask c0, c1;
+    c0.pair = t.pair; c0.pb = t.pb; c0.pe = t.pb + bv; c0.tb = t.tb; c0.te = t.tb + bh;
+    c0.cbegin = t.cbegin; c0.cend = bp.component; c0.score_remaining = bp.score_forward;
+    c1.pair = t.pair; c1.pb = t.pb + bv; c1.pe = t.pe; c1.tb = t.tb + bh; c1.te = t.te;
+    c1.cbegin = bp.component; c1.cend = t.cend; c1.score_remaining = bp.score_reverse;
+    wfb_dispatch_child(c0, ops, q_break, q_base, pair_status);
+    wfb_dispatch_child(c1, ops, q_break, q_base, pair_status);
+  }
+  /* counters */
+  {
+    unsigned long long m = acc.matches;
+#ifndef WFB_EMU
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_down_sync(0xffffffffu, m, o);
+#endif
+    if (wfb_lane() == 0 && m) wfb_atomic_add64(&counters->extend_matches, m);
+    if (WFB_TID == 0) {
+      wfb_atomic_add64(&counters->cells, acc.cells);
+      wfb_atomic_add64(&counters->overlap_tests, acc.overlap);
+      wfb_atomic_add64(&counters->score_steps, acc.steps);
+      wfb_atomic_add64(&counters->break_tasks, ntask_done);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Base kernel: unidirectional full-memory WFA + backtrace on small-score sub-problems.
+ * wavefront_bialign_base (:159-189) = wavefront_unialign (wavefront_unialign.c:242-273) +
+ * wavefront_backtrace_affine (wavefront_backtrace.c:320-529).
+ * Per-CTA global scratch:  arena (offsets of every score), a metadata log per score for the
+ * backtrace, and a run list.
+ * ---------------------------------------------------------------------------------------------- */
+struct WfbBaseMeta { /* one per (score, component) */
+  int lo, hi, boff, ex;
+};
+
+struct WfbRun {
+  int idx;   /* first op slot (v+h, absolute) */
+  int count;
+  int op;
+};
+
+struct WfbAllocBump {
+  int bump; /* next free int in the arena */
+  WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) {
+    (void)slot;
+    const int n = hi - lo + 1;
+    for (int c = 0; c < 5; ++c) ob[c] = bump + c * n - lo;
+    bump += 5 * n;
+  }
+};
+
+#define WFB_BT_SET(off, type) ((((long long)(off)) << 4) | (type))
+
+/* wavefront_backtrace_{misms,ins*,del*} (wavefront_backtrace.c:64-219) over the metadata log */
+WFB_DEV long long wfb_bt_src(const WfbBaseMeta* log, const int32_t* arena, int nscores, int comp, int score, int k, int dk,
+                             int plus, int type) {
+  if (score < 0 || score >= nscores) return WFB_OFFSET_NULL;
+  const WfbBaseMeta m = log[score * 5 + comp];
+  if (m.ex && m.lo <= k + dk && k + dk <= m.hi) return WFB_BT_SET(arena[m.boff + k + dk] + plus, type);
+  return WFB_OFFSET_NULL;
+}
+WFB_DEV long long wfb_max64(long long a, long long b) { return a > b ? a : b; }
+
+WFB_DEV void wfb_emit(WfbRun* runs, int& nruns, int maxruns, int& err, int op, int count, int idx) {
+  if (count <= 0) return;
+  if (nruns > 0 && runs[nruns - 1].op == op && (op == 'M' || op == 'X' ? idx + 2 * count : idx + count) == runs[nruns - 1].idx) {
+    runs[nruns - 1].idx = idx;
+    runs[nruns - 1].count += count;
+    return;
+  }
+  if (nruns >= maxruns) { err = 1; return; }
+  runs[nruns].idx = idx;
+  runs[nruns].count = count;
+  runs[nruns].op = op;
+  ++nruns;
+}
+
+/* Thread 0: wavefront_backtrace_affine (wavefront_backtrace.c:320-529). Emits runs (right to left);
+ * `base_idx` = pb + tb turns local (v,h) into the pair's op-slot index. */
+WFB_DEV int wfb_backtrace(const WfbBaseMeta* log, const int32_t* arena, int nscores, const WfbPen& pen, int cbegin, int cend,
+                          int plen, int tlen, int alignment_score, int base_idx, WfbRun* runs, int maxruns, int* nruns_out) {
+  enum { BT_M = 9, BT_D2_EXT = 8, BT_D2_OPEN = 7, BT_D1_EXT = 6, BT_D1_OPEN = 5, BT_I2_EXT = 4, BT_I2_OPEN = 3,
+         BT_I1_EXT = 2, BT_I1_OPEN = 1 };
+  (void)cbegin;
+  int nruns = 0, err = 0;
+  int matrix_type = cend;
+  int score = alignment_score;
+  int k = tlen - plen;
+  int offset = tlen;
+  int v = plen, h = tlen;
+  while (v > 0 && h > 0 && score > 0) {
+    const int mismatch = score - pen.x;
+    const int gap_open1 = score - pen.o1 - pen.e1, gap_open2 = score - pen.o2 - pen.e2;
+    const int gap_extend1 = score - pen.e1, gap_extend2 = score - pen.e2;
+    long long max_all;
+    if (matrix_type == WFB_M) {
+      const long long misms = wfb_bt_src(log, arena, nscores, WFB_M, mismatch, k, 0, 1, BT_M);
+      const long long max_ins1 = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open1, k, -1, 1, BT_I1_OPEN),
+                                           wfb_bt_src(log, arena, nscores, WFB_I1, gap_extend1, k, -1, 1, BT_I1_EXT));
+      const long long max_del1 = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open1, k, +1, 0, BT_D1_OPEN),
+                                           wfb_bt_src(log, arena, nscores, WFB_D1, gap_extend1, k, +1, 0, BT_D1_EXT));
+      const long long max_ins2 = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open2, k, -1, 1, BT_I2_OPEN),
+                                           wfb_bt_src(log, arena, nscores, WFB_I2, gap_extend2, k, -1, 1, BT_I2_EXT));
+      const long long max_del2 = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open2, k, +1, 0, BT_D2_OPEN),
+                                           wfb_bt_src(log, arena, nscores, WFB_D2, gap_extend2, k, +1, 0, BT_D2_EXT));
+      max_all = wfb_max64(misms, wfb_max64(wfb_max64(max_ins1, max_ins2), wfb_max64(max_del1, max_del2)));
+    } else if (matrix_type == WFB_I1) {
+      max_all = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open1, k, -1, 1, BT_I1_OPEN),
+                          wfb_bt_src(log, arena, nscores, WFB_I1, gap_extend1, k, -1, 1, BT_I1_EXT));
+    } else if (matrix_type == WFB_I2) {
+      max_all = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open2, k, -1, 1, BT_I2_OPEN),
+                          wfb_bt_src(log, arena, nscores, WFB_I2, gap_extend2, k, -1, 1, BT_I2_EXT));
+    } else if (matrix_type == WFB_D1) {
+      max_all = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open1, k, +1, 0, BT_D1_OPEN),
+                          wfb_bt_src(log, arena, nscores, WFB_D1, gap_extend1, k, +1, 0, BT_D1_EXT));
+    } else {
+      max_all = wfb_max64(wfb_bt_src(log, arena, nscores, WFB_M, gap_open2, k, +1, 0, BT_D2_OPEN),
+                          wfb_bt_src(log, arena, nscores, WFB_D2, gap_extend2, k, +1, 0, BT_D2_EXT));
+    }
+    if (max_all < 0) break;
+    if (matrix_type == WFB_M) {
+      const int max_offset = (int)(max_all >> 4);
+      const int num_matches = offset - max_offset;
+      wfb_emit(runs, nruns, maxruns, err, 'M', num_matches, base_idx + (v - num_matches) + (h - num_matches));
+      offset = max_offset;
+      v = offset - k;
+      h = offset;
+      if (v <= 0 || h <= 0) break;
+    }
+    const int bt = (int)(max_all & 0xF);
+    switch (bt) {
+      case BT_M: score = mismatch; matrix_type = WFB_M; break;
+      case BT_I1_OPEN: score = gap_open1; matrix_type = WFB_M; break;
+      case BT_I1_EXT: score = gap_extend1; matrix_type = WFB_I1; break;
+      case BT_I2_OPEN: score = gap_open2; matrix_type = WFB_M; break;
+      case BT_I2_EXT: score = gap_extend2; matrix_type = WFB_I2; break;
+      case BT_D1_OPEN: score = gap_open1; matrix_type = WFB_M; break;
+      case BT_D1_EXT: score = gap_extend1; matrix_type = WFB_D1; break;
+      case BT_D2_OPEN: score = gap_open2; matrix_type = WFB_M; break;
+      case BT_D2_EXT: score = gap_extend2; matrix_type = WFB_D2; break;
+      default: *nruns_out = 0; return 1;
+    }
+    if (bt == BT_M) { wfb_emit(runs, nruns, maxruns, err, 'X', 1, base_idx + (v - 1) + (h - 1)); --offset; }
+    else if (bt <= BT_I2_EXT) { wfb_emit(runs, nruns, maxruns, err, 'I', 1, base_idx + v + (h - 1)); --k; --offset; }
+    else { wfb_emit(runs, nruns, maxruns, err, 'D', 1, base_idx + (v - 1) + h); ++k; }
+    v = offset - k;
+    h = offset;
+  }
+  if (matrix_type == WFB_M) {
+    if (v > 0 && h > 0) {
+      const int num_matches = min(v, h);
+      wfb_emit(runs, nruns, maxruns, err, 'M', num_matches, base_idx + (v - num_matches) + (h - num_matches));
+      v -= num_matches;
+      h -= num_matches;
+    }
+    if (v > 0) { wfb_emit(runs, nruns, maxruns, err, 'D', v, base_idx + 0 + h); v = 0; }
+    if (h > 0) { wfb_emit(runs, nruns, maxruns, err, 'I', h, base_idx + 0 + 0); h = 0; }
+  } else {
+    if (v != 0 || h != 0 || score != 0) err = 1; /* the reference aborts here (:519-524) */
+  }
+  *nruns_out = nruns;
+  return err;
+}
+
+struct WfbBaseShared {
+  WfbRing ring;
+  int red_maxak[3];
+  int task_idx;
+  int st0, ak0;
+  int nruns, bt_err;
+};
+
+WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter, const WfbPairDesc* pairs,
+           const uint8_t* seq, int32_t* arena_all, long long arena_stride /* ints per CTA */, WfbBaseMeta* log_all,
+           int score_cap, WfbRun* runs_all, int maxruns, WfbPen pen, char* ops_all, int* pair_status,
+           WfbCounters* counters) {
+  WFB_KERNEL_PROLOGUE
+  WFB_SHARED WfbBaseShared sh;
+  int32_t* const arena = arena_all + (long long)bid * arena_stride;
+  WfbBaseMeta* const log = log_all + (long long)bid * (score_cap + 1) * 5;
+  WfbRun* const runs = runs_all + (long long)bid * maxruns;
+  WfbAcc acc;
+  acc.cells = acc.overlap = acc.matches = acc.steps = 0;
+  unsigned long long ntask_done = 0;
+  for (;;) {
+    WFB_SYNC();
+    if (WFB_TID == 0) sh.task_idx = wfb_atomic_add(task_counter, 1);
+    WFB_SYNC();
+    const int ti = sh.task_idx;
+    if (ti >= ntasks) break;
+    const WfbTask t = tasks[ti];
+    const WfbPairDesc pd = pairs[t.pair];
+    char* const ops = ops_all + pd.ops_off;
+    const int plen = t.pe - t.pb, tlen = t.te - t.tb;
+    ntask_done++;
+    if (tlen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'D', plen); continue; }
+    if (plen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'I', tlen); continue; }
+    const uint8_t* pf = seq + pd.p_off + t.pb;
+    const uint8_t* tf = seq + pd.t_off + t.tb;
+    const int R = pen.R;
+    wfb_ring_reset(sh.ring, R);
+    if (WFB_TID == 0) { sh.red_maxak[0] = sh.red_maxak[1] = sh.red_maxak[2] = 0; }
+    WFB_SYNC();
+    WfbAllocBump ab;
+    ab.bump = 1; /* cell 0 = the score-0 wavefront */
+    if (WFB_TID == 0) {
+      wfb_init_score0(sh.ring, arena, 0, t.cbegin, t.cend, pf, tf, plen, tlen, &sh.st0, &sh.ak0, acc);
+      for (int c = 0; c < 5; ++c) {
+        WfbBaseMeta m;
+        m.lo = 0; m.hi = 0; m.boff = 0; m.ex = (c == t.cbegin);
+        log[c] = m;
+      }
+    }
+    WFB_SYNC();
+    int status = sh.st0;
+    int score = 0, num_null = 0, max_ak = 0;
+    /* wavefront_unialign, wavefront_unialign.c:251-270 */
+    while (status == WFB_ST_OK) {
+      ++score;
+      if (score > score_cap || (long long)ab.bump + 5LL * (2 * score + 3) > arena_stride) { status = -1; break; }
+      status = wfb_step(sh.ring, arena, pen, score, pf, tf, plen, tlen, t.cend, num_null, ab, sh.red_maxak, max_ak, acc);
+      if (WFB_TID == 0) {
+        const int slot = score % R;
+        for (int c = 0; c < 5; ++c) {
+          WfbBaseMeta m;
+          m.lo = sh.ring.lo[slot][c]; m.hi = sh.ring.hi[slot][c]; m.boff = sh.ring.boff[slot][c]; m.ex = sh.ring.ex[slot][c];
+          log[score * 5 + c] = m;
+        }
+      }
+    }
+    if (status != WFB_ST_END_REACHED) {
+      if (WFB_TID == 0) pair_status[t.pair] = (status == -1) ? WFB_PAIR_BASE_SCORE_CAP : WFB_PAIR_UNATTAINABLE;
+      continue;
+    }
+    if (WFB_TID == 0) {
+      int nr = 0;
+      sh.bt_err = wfb_backtrace(log, arena, score + 1, pen, t.cbegin, t.cend, plen, tlen, score, t.pb + t.tb, runs, maxruns, &nr);
+      sh.nruns = nr;
+    }
+    WFB_SYNC();
+    if (sh.bt_err) {
+      if (WFB_TID == 0) pair_status[t.pair] = WFB_PAIR_BACKTRACE;
+      continue;
+    }
+    const int nr = sh.nruns;
+    for (int r = 0; r < nr; ++r) {
+      const WfbRun ru = runs[r];
+      const int stride = (ru.op == 'M' || ru.op == 'X') ? 2 : 1;
+      for (int j = WFB_TID; j < ru.count; j += WFB_NT) ops[ru.idx + j * stride] = (char)ru.op;
+    }
+  }
+  {
+    unsigned long long m = acc.matches;
+#ifndef WFB_EMU
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_down_sync(0xffffffffu, m, o);
+#endif
+    if (wfb_lane() == 0 && m) wfb_atomic_add64(&counters->base_extend_matches, m);
+    if (WFB_TID == 0) {
+      wfb_atomic_add64(&counters->base_cells, acc.cells);
+      wfb_atomic_add64(&counters->base_score_steps, acc.steps);
+      wfb_atomic_add64(&counters->base_tasks, ntask_done);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Sequence staging: reversed copies (wavefront_sequences.c:83-101 does this per aligner on the CPU).
+ * ---------------------------------------------------------------------------------------------- */
+WFB_KERNEL(wfb_reverse_kernel, const WfbPairDesc* pairs, int npairs, uint8_t* seq) {
+  WFB_KERNEL_PROLOGUE
+  for (int i = bid; i < npairs; i += nblocks) {
+    const WfbPairDesc pd = pairs[i];
+    for (int j = WFB_TID; j < pd.plen; j += WFB_NT) seq[pd.prev_off + j] = seq[pd.p_off + pd.plen - 1 - j];
+    for (int j = WFB_TID; j < pd.tlen; j += WFB_NT) seq[pd.trev_off + j] = seq[pd.t_off + pd.tlen - 1 - j];
+  }
+}
+
+/* Compaction of a pair's op slots (zero = hole) into a dense operation string, in place is not
+ * possible in parallel, so dense output goes to ops_out + ops_off. One CTA per pair, chunked scan. */
+WFB_KERNEL(wfb_compact_kernel, const WfbPairDesc* pairs, int npairs, const char* ops_slots, char* ops_out, int* ops_len) {
+  WFB_KERNEL_PROLOGUE
+  WFB_SHARED int sh_warp[32];
+  WFB_SHARED int sh_base;
+  for (int i = bid; i < npairs; i += nblocks) {
+    const WfbPairDesc pd = pairs[i];
+    const int n = pd.plen + pd.tlen;
+    const char* src = ops_slots + pd.ops_off;
+    char* dst = ops_out + pd.ops_off;
+    WFB_SYNC();
+    if (WFB_TID == 0) sh_base = 0;
+    WFB_SYNC();
+    for (int start = 0; start < n; start += WFB_NT * 8) {
+      /* each thread owns 8 consecutive slots */
+      const int b = start + WFB_TID * 8;
+      char loc[8];
+      int cnt = 0;
+      for (int j = 0; j < 8; ++j) {
+        const char ch = (b + j < n) ? src[b + j] : 0;
+        if (ch) loc[cnt++] = ch;
+      }
+      int incl = cnt;
+#ifndef WFB_EMU
+      const int lane = wfb_lane(), wid = WFB_TID >> 5;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      if (lane == 31) sh_warp[wid] = incl;
+      WFB_SYNC();
+      if (wid == 0) {
+        const int nw = (WFB_NT + 31) >> 5;
+        int w = lane < nw ? sh_warp[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, w, o);
+          if (lane >= o) w += y;
+        }
+        sh_warp[lane] = w; /* inclusive scan of warp totals */
+      }
+      WFB_SYNC();
+      const int woff = wid ? sh_warp[wid - 1] : 0;
+      const int total = sh_warp[((WFB_NT + 31) >> 5) - 1];
+#else
+      const int woff = 0;
+      const int total = incl;
+      (void)sh_warp;
+#endif
+      const int pos = sh_base + woff + incl - cnt;
+      for (int j = 0; j < cnt; ++j) dst[pos + j] = loc[j];
+      WFB_SYNC();
+      if (WFB_TID == 0) sh_base += total;
+      WFB_SYNC();
+    }
+    if (WFB_TID == 0) ops_len[i] = sh_base;
+  }
+}

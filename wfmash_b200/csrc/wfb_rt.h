@@ -1,0 +1,57 @@
+// wfb_rt.h — thin execution layer under the kernels.
+//
+// Product build (nvcc, sm_100a): the macros below are the CUDA built-ins.
+// Test-only build (-DWFB_EMU, plain g++): every kernel body runs as ONE thread per block, blocks
+// run one after another on the host. This exists only so that the kernels' control flow, indexing
+// and tie-breaking can be debugged in a container without a GPU (tests/emu/); it is never compiled
+// into libwfmash_b200.so and is not a fallback: the product library fails with WFB_ENODEV when no
+// device is present.
+#pragma once
+#include <stdint.h>
+#include <limits.h>
+
+#ifndef WFB_EMU
+#include <cuda_runtime.h>
+#define WFB_DEV __device__ __forceinline__
+#define WFB_DEV_MEMBER __device__ __forceinline__
+#define WFB_DEV_NOINLINE __device__ __noinline__
+#define WFB_SHARED __shared__
+#define WFB_TID ((int)threadIdx.x)
+#define WFB_NT ((int)blockDim.x)
+#define WFB_SYNC() __syncthreads()
+#define WFB_KERNEL_PROLOGUE const int bid = (int)blockIdx.x; const int nblocks = (int)gridDim.x; (void)bid; (void)nblocks;
+#define WFB_KERNEL(name, ...) __global__ void name(__VA_ARGS__)
+WFB_DEV int wfb_warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+WFB_DEV int wfb_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+WFB_DEV unsigned wfb_warp_add(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+WFB_DEV int wfb_lane() { return (int)(threadIdx.x & 31); }
+WFB_DEV void wfb_smem_min(int* p, int v) { atomicMin(p, v); }
+WFB_DEV void wfb_smem_max(int* p, int v) { atomicMax(p, v); }
+WFB_DEV int wfb_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+WFB_DEV void wfb_atomic_add64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+WFB_DEV uint32_t wfb_ldg32(const uint32_t* p) { return __ldg(p); }
+WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { return __ldg(p); }
+#else
+#include <string.h>
+#define WFB_DEV static inline
+#define WFB_DEV_MEMBER inline
+#define WFB_DEV_NOINLINE static
+#define WFB_SHARED static
+#define WFB_TID 0
+#define WFB_NT 1
+#define WFB_SYNC() ((void)0)
+#define WFB_KERNEL_PROLOGUE
+#define WFB_KERNEL(name, ...) static void name(int bid, int nblocks, __VA_ARGS__)
+WFB_DEV int wfb_warp_min(int v) { return v; }
+WFB_DEV int wfb_warp_max(int v) { return v; }
+WFB_DEV unsigned wfb_warp_add(unsigned v) { return v; }
+WFB_DEV int wfb_lane() { return 0; }
+WFB_DEV void wfb_smem_min(int* p, int v) { if (v < *p) *p = v; }
+WFB_DEV void wfb_smem_max(int* p, int v) { if (v > *p) *p = v; }
+WFB_DEV int wfb_atomic_add(int* p, int v) { const int o = *p; *p = o + v; return o; }
+WFB_DEV void wfb_atomic_add64(unsigned long long* p, unsigned long long v) { *p += v; }
+WFB_DEV uint32_t wfb_ldg32(const uint32_t* p) { return *p; }
+WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+#endif

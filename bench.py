@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--records", type=int, default=0, help="override records per step (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning sweeps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -296,7 +297,7 @@ def main():
                     "kernel": "wfb_break_kernel", "peak_source": peak_src,
                     "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": brk_s * 1e3, "launches_per_step": n_brk_launch,
                     "cells_per_step": stats_d["cells"], "gcells_per_s": stats_d["cells"] / brk_s / 1e9 if brk_s > 0 else 0.0}
-        cpu = run_cpu_sample(recs, args.cpu_seconds, cores) if world == 1 else None
+        cpu = run_cpu_sample(recs, args.cpu_seconds, cores) if (world == 1 and not args.no_cpu) else None
         h2d = int(plen.sum() + tlen.sum()) + 64 * n
         d2h = sum(r.ops_len for r in res) + 24 * n
         line = {

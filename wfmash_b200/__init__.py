@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwfmash_b200.so")
+# WFB_LIB lets tuning sweeps point at a differently-compiled build of the same sources
+LIB_PATH = os.environ.get("WFB_LIB") or os.path.join(_HERE, "libwfmash_b200.so")
 
 # wflign_penalties_t defaults of the CLI (src/interface/parse_args.hpp -> align::Parameters;
 # do_biwfa_alignment is called with mismatch 5, gap1 (8,2), gap2 (24,1); src/align/include/computeAlignments.hpp:684-690)

@@ -29,11 +29,25 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in SRC + HDR if os.path.exists(f))
 
 
+# tuned defaults of the breakpoint kernel (see DESIGN.md / profiles/): __launch_bounds__ and call style
+DEFAULT_DEFS = ["-DWFB_BREAK_MAXTHREADS=256", "-DWFB_BREAK_MINBLOCKS=2"]
+
+
+def build_variant(out, defs, verbose=False):
+    """Build the library with other compile-time knobs (used by tuning sweeps only)."""
+    srcs = [s for s in SRC if os.path.exists(s)]
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(defs) + ["-I", os.path.join(ROOT, "include"), "-o", out] + srcs
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build(force=False, verbose=False):
     srcs = [s for s in SRC if os.path.exists(s)]
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", OUT] + srcs
+    cmd = [nvcc_path()] + NVCC_FLAGS + DEFAULT_DEFS + ["-I", os.path.join(ROOT, "include"), "-o", OUT] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

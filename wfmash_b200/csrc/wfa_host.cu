@@ -119,7 +119,21 @@ struct wfb_aligner {
 #endif
 };
 
-static const int kBreakThreads = 256;
+static int env_int(const char* name, int def) {
+  const char* v = getenv(name);
+  if (!v || !*v) return def;
+  const int x = atoi(v);
+  return x > 0 ? x : def;
+}
+/* CTA shapes; the breakpoint kernel's can be tuned without rebuilding (WFB_BREAK_THREADS), bounded by
+ * the __launch_bounds__ the library was compiled with. */
+static int break_threads() {
+  int t = env_int("WFB_BREAK_THREADS", 256);
+  t = (t / 32) * 32;
+  if (t < 32) t = 32;
+  if (t > WFB_BREAK_MAXTHREADS) t = WFB_BREAK_MAXTHREADS;
+  return t;
+}
 static const int kBaseThreads = 64;
 
 extern "C" const char* wfb_last_error(void) { return g_last_error.c_str(); }
@@ -335,8 +349,20 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
   const long long arena_stride = 5LL * (score_cap + 2) * (score_cap + 2) + 64;
   const int maxruns = 2 * score_cap + 16;
   const size_t base_cta_bytes = (size_t)arena_stride * 4 + (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta) + (size_t)maxruns * sizeof(WfbRun);
+  const int kBreakThreads = break_threads();
   int cta_base = a->sm_count * 8;
-  int cta_break = a->sm_count * 3;
+  int cta_break = a->sm_count * 2;
+#ifndef WFB_EMU
+  {
+    /* persistent CTAs pulling tasks from a queue: exactly as many as can be resident */
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfb_break_kernel, kBreakThreads, 0) == cudaSuccess && nb > 0)
+      cta_break = a->sm_count * nb;
+    int nb2 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, wfb_base_kernel, kBaseThreads, 0) == cudaSuccess && nb2 > 0)
+      cta_base = a->sm_count * nb2;
+  }
+#endif
   {
     const uint64_t budget = a->workspace_bytes;
     const uint64_t base_budget = std::min<uint64_t>(budget / 4, (uint64_t)cta_base * base_cta_bytes);

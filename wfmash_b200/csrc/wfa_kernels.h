@@ -24,6 +24,14 @@
 #pragma once
 #include "wfb_rt.h"
 
+#ifndef WFB_STEP_INLINE
+#ifdef WFB_STEP_NOINLINE
+#define WFB_STEP_INLINE WFB_DEV_NOINLINE
+#else
+#define WFB_STEP_INLINE WFB_DEV
+#endif
+#endif
+
 #define WFB_OFFSET_NULL (INT32_MIN / 2) /* wavefront_offset.h:44 */
 #define WFB_RMAX 40                     /* max ring slots = max_score_scope + 1 */
 #define WFB_FALLBACK_MIN_SCORE 250      /* wavefront_bialign.c:52 */
@@ -71,11 +79,12 @@ struct WfbRing { /* shared-memory wavefront metadata of the last R scores */
   int lo[WFB_RMAX][5];
   int hi[WFB_RMAX][5];
   int boff[WFB_RMAX][5]; /* element offset so that cell(k) = basep[boff + k] */
+  int mak[WFB_RMAX][5];  /* max anti-diagonal 2*offset-k over the computed cells (overlap pruning) */
   unsigned char ex[WFB_RMAX][5];
 };
 
 struct WfbIn {
-  const int32_t* p;
+  int off; /* cell(k) = basep[off + k] */
   int lo, hi;
 };
 
@@ -87,8 +96,9 @@ struct WfbBreakpoint {
 
 /* wavefront_compute_get_*wavefront (wavefront_compute.c:266-305): null => lo=1, hi=-1 */
 WFB_DEV WfbIn wfb_fetch(const WfbRing& r, const int32_t* basep, int R, int comp, int score) {
+  (void)basep;
   WfbIn w;
-  w.p = basep;
+  w.off = 0;
   w.lo = 1;
   w.hi = -1;
   if (score >= 0) {
@@ -96,12 +106,14 @@ WFB_DEV WfbIn wfb_fetch(const WfbRing& r, const int32_t* basep, int R, int comp,
     if (r.ex[s][comp] && r.lo[s][comp] <= r.hi[s][comp]) {
       w.lo = r.lo[s][comp];
       w.hi = r.hi[s][comp];
-      w.p = basep + r.boff[s][comp];
+      w.off = r.boff[s][comp];
     }
   }
   return w;
 }
-WFB_DEV int32_t wfb_get(const WfbIn& w, int k) { return (k >= w.lo && k <= w.hi) ? w.p[k] : WFB_OFFSET_NULL; }
+WFB_DEV int32_t wfb_get(const int32_t* basep, const WfbIn& w, int k) {
+  return (k >= w.lo && k <= w.hi) ? basep[w.off + k] : WFB_OFFSET_NULL;
+}
 
 /* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 7 bytes past
  * the cap (sequence buffers are padded). wavefront_extend_kernels.c:68-92 does the same 8 bytes at a
@@ -154,7 +166,7 @@ struct WfbAcc {
  *   red_maxak[3] : shared-memory reduction slots, rotated by score % 3.
  */
 template <class Alloc>
-WFB_DEV int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
+WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
                      const uint8_t* tseq, int plen, int tlen, int cend, int& num_null, Alloc& alloc, int* red_maxak,
                      int& max_ak_out, WfbAcc& acc) {
   const int R = pen.R, slot = score % R, nslot = (score + 1) % R;
@@ -179,6 +191,7 @@ WFB_DEV int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score
         ring.ex[slot][c] = 0;
         ring.lo[nslot][c] = INT_MAX;
         ring.hi[nslot][c] = INT_MIN;
+        ring.mak[nslot][c] = INT_MIN;
       }
       red_maxak[npar] = 0;
     }
@@ -209,27 +222,24 @@ WFB_DEV int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score
       ring.boff[slot][c] = ob[c];
       ring.lo[nslot][c] = INT_MAX;
       ring.hi[nslot][c] = INT_MIN;
+      ring.mak[nslot][c] = INT_MIN;
     }
     red_maxak[npar] = 0;
     acc.cells += (unsigned long long)(hi - lo + 1);
   }
-  int32_t* const out_m = basep + ob[WFB_M];
-  int32_t* const out_i1 = basep + ob[WFB_I1];
-  int32_t* const out_i2 = basep + ob[WFB_I2];
-  int32_t* const out_d1 = basep + ob[WFB_D1];
-  int32_t* const out_d2 = basep + ob[WFB_D2];
   int tlo_m = INT_MAX, thi_m = INT_MIN, tlo_i1 = INT_MAX, thi_i1 = INT_MIN, tlo_i2 = INT_MAX, thi_i2 = INT_MIN;
   int tlo_d1 = INT_MAX, thi_d1 = INT_MIN, tlo_d2 = INT_MAX, thi_d2 = INT_MIN;
   int tmax = 0;
+  int ak_i1 = INT_MIN, ak_i2 = INT_MIN, ak_d1 = INT_MIN, ak_d2 = INT_MIN;
   /* wavefront_compute_affine2p_idm (wavefront_compute_affine2p.c:45-106) fused with
    * wavefront_extend_matches_packed_end2end_max (wavefront_extend_kernels.c:125-152) and
    * wavefront_compute_trim_ends (wavefront_compute.c:579-613) */
   for (int k = lo + WFB_TID; k <= hi; k += WFB_NT) {
-    const int32_t ins1 = max(wfb_get(m_open1, k - 1), wfb_get(i1_ext, k - 1)) + 1;
-    const int32_t ins2 = max(wfb_get(m_open2, k - 1), wfb_get(i2_ext, k - 1)) + 1;
-    const int32_t del1 = max(wfb_get(m_open1, k + 1), wfb_get(d1_ext, k + 1));
-    const int32_t del2 = max(wfb_get(m_open2, k + 1), wfb_get(d2_ext, k + 1));
-    const int32_t misms = wfb_get(m_misms, k) + 1;
+    const int32_t ins1 = max(wfb_get(basep, m_open1, k - 1), wfb_get(basep, i1_ext, k - 1)) + 1;
+    const int32_t ins2 = max(wfb_get(basep, m_open2, k - 1), wfb_get(basep, i2_ext, k - 1)) + 1;
+    const int32_t del1 = max(wfb_get(basep, m_open1, k + 1), wfb_get(basep, d1_ext, k + 1));
+    const int32_t del2 = max(wfb_get(basep, m_open2, k + 1), wfb_get(basep, d2_ext, k + 1));
+    const int32_t misms = wfb_get(basep, m_misms, k) + 1;
     int32_t mx = max(max(del1, del2), max(misms, max(ins1, ins2)));
     if (wfb_inbounds(mx, k, plen, tlen)) {
       const int v = mx - k, h = mx;
@@ -242,11 +252,13 @@ WFB_DEV int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score
     } else {
       mx = WFB_OFFSET_NULL;
     }
-    out_m[k] = mx;
-    if (ex_i1) { out_i1[k] = ins1; if (wfb_inbounds(ins1, k, plen, tlen)) { tlo_i1 = min(tlo_i1, k); thi_i1 = max(thi_i1, k); } }
-    if (ex_i2) { out_i2[k] = ins2; if (wfb_inbounds(ins2, k, plen, tlen)) { tlo_i2 = min(tlo_i2, k); thi_i2 = max(thi_i2, k); } }
-    if (ex_d1) { out_d1[k] = del1; if (wfb_inbounds(del1, k, plen, tlen)) { tlo_d1 = min(tlo_d1, k); thi_d1 = max(thi_d1, k); } }
-    if (ex_d2) { out_d2[k] = del2; if (wfb_inbounds(del2, k, plen, tlen)) { tlo_d2 = min(tlo_d2, k); thi_d2 = max(thi_d2, k); } }
+    basep[ob[WFB_M] + k] = mx;
+    /* anti-diagonal maxima are taken over EVERY computed cell (raw values, also out-of-bounds ones):
+     * a superset of what the overlap scan can see, so pruning on them never hides a hit */
+    if (ex_i1) { basep[ob[WFB_I1] + k] = ins1; ak_i1 = max(ak_i1, 2 * ins1 - k); if (wfb_inbounds(ins1, k, plen, tlen)) { tlo_i1 = min(tlo_i1, k); thi_i1 = max(thi_i1, k); } }
+    if (ex_i2) { basep[ob[WFB_I2] + k] = ins2; ak_i2 = max(ak_i2, 2 * ins2 - k); if (wfb_inbounds(ins2, k, plen, tlen)) { tlo_i2 = min(tlo_i2, k); thi_i2 = max(thi_i2, k); } }
+    if (ex_d1) { basep[ob[WFB_D1] + k] = del1; ak_d1 = max(ak_d1, 2 * del1 - k); if (wfb_inbounds(del1, k, plen, tlen)) { tlo_d1 = min(tlo_d1, k); thi_d1 = max(thi_d1, k); } }
+    if (ex_d2) { basep[ob[WFB_D2] + k] = del2; ak_d2 = max(ak_d2, 2 * del2 - k); if (wfb_inbounds(del2, k, plen, tlen)) { tlo_d2 = min(tlo_d2, k); thi_d2 = max(thi_d2, k); } }
   }
   /* trimmed [lo,hi] of each component = min / max diagonal holding an in-bounds offset */
   {
@@ -257,20 +269,28 @@ WFB_DEV int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score
     if (ex_i1) {
       v = wfb_warp_min(tlo_i1); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_I1], v);
       v = wfb_warp_max(thi_i1); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_I1], v);
+      v = wfb_warp_max(ak_i1);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_I1], v);
     }
     if (ex_i2) {
       v = wfb_warp_min(tlo_i2); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_I2], v);
       v = wfb_warp_max(thi_i2); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_I2], v);
+      v = wfb_warp_max(ak_i2);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_I2], v);
     }
     if (ex_d1) {
       v = wfb_warp_min(tlo_d1); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_D1], v);
       v = wfb_warp_max(thi_d1); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_D1], v);
+      v = wfb_warp_max(ak_d1);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_D1], v);
     }
     if (ex_d2) {
       v = wfb_warp_min(tlo_d2); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_D2], v);
       v = wfb_warp_max(thi_d2); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_D2], v);
+      v = wfb_warp_max(ak_d2);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_D2], v);
     }
-    v = wfb_warp_max(tmax);   if (lane == 0 && v > 0) wfb_smem_max(&red_maxak[par], v);
+    v = wfb_warp_max(tmax);
+    if (lane == 0) {
+      if (v > 0) wfb_smem_max(&red_maxak[par], v);
+      wfb_smem_max(&ring.mak[slot][WFB_M], v); /* v >= 0 even without in-bounds cells: a superset bound */
+    }
   }
   WFB_SYNC();
   max_ak_out = red_maxak[par];
@@ -293,7 +313,7 @@ WFB_DEV int wfb_gap_of(const WfbPen& pen, int comp) {
   return comp == WFB_M ? 0 : ((comp == WFB_I1 || comp == WFB_D1) ? pen.o1 : pen.o2);
 }
 
-WFB_DEV void wfb_overlap(const WfbRing& r0, const int32_t* base0, const WfbRing& r1, const int32_t* base1,
+WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const WfbRing& r1, const int32_t* base1,
                          const WfbPen& pen, int score_0, int score_1, bool bp_forward, int plen, int tlen,
                          WfbBreakpoint* bp, int* found, WfbAcc& acc) {
   const int R = pen.R, s0 = score_0 % R;
@@ -312,6 +332,9 @@ WFB_DEV void wfb_overlap(const WfbRing& r0, const int32_t* base0, const WfbRing&
       const int lo_0 = r0.lo[s0][c], hi_0 = r0.hi[s0][c];
       const int lo1r = r1.lo[si][c], hi1r = r1.hi[si][c];
       if (lo_0 > hi_0 || lo1r > hi1r) continue;
+      /* off0[k0] + off1[kinv-k0] >= tlen  <=>  ak0 + ak1 >= plen + tlen (ak = 2*off - k): no diagonal can
+       * satisfy it unless the two wavefronts' maximal anti-diagonals do */
+      if ((long long)r0.mak[s0][c] + (long long)r1.mak[si][c] < (long long)plen + tlen) continue;
       const int lo_1 = kinv - hi1r, hi_1 = kinv - lo1r;
       const int max_lo = max(lo_0, lo_1), min_hi = min(hi_0, hi_1);
       if (min_hi < max_lo) continue;
@@ -423,6 +446,7 @@ WFB_DEV void wfb_ring_reset(WfbRing& r, int R) {
     r.hi[i / 5][i % 5] = INT_MIN;
     r.ex[i / 5][i % 5] = 0;
     r.boff[i / 5][i % 5] = 0;
+    r.mak[i / 5][i % 5] = INT_MIN;
   }
 }
 
@@ -447,6 +471,7 @@ WFB_DEV void wfb_init_score0(WfbRing& ring, int32_t* basep, int boff0, int cbegi
     if (cend == WFB_M && tlen - plen == 0 && off >= tlen) *st = WFB_ST_END_REACHED;
   }
   basep[boff0 + 0] = off;
+  ring.mak[0][cbegin] = 2 * off;
 }
 
 /*
@@ -454,7 +479,13 @@ WFB_DEV void wfb_init_score0(WfbRing& ring, int32_t* basep, int boff0, int cbegi
  * (wavefront_bialign.c:974-1082) + the dispatch of both halves (:1188-1212) + the exception path
  * (:1083-1110).
  */
-WFB_KERNEL(wfb_break_kernel, const WfbTask* tasks, int ntasks, int* task_counter, const WfbPairDesc* pairs,
+#ifndef WFB_BREAK_MAXTHREADS
+#define WFB_BREAK_MAXTHREADS 256
+#endif
+#ifndef WFB_BREAK_MINBLOCKS
+#define WFB_BREAK_MINBLOCKS 2
+#endif
+WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const WfbTask* tasks, int ntasks, int* task_counter, const WfbPairDesc* pairs,
            const uint8_t* seq, int32_t* ws_all, long long ws_stride /* ints per CTA */, int W, WfbPen pen,
            WfbQueue q_break, WfbQueue q_base, char* ops_all, int* pair_status, WfbCounters* counters) {
   WFB_KERNEL_PROLOGUE

@@ -21,6 +21,7 @@
 #define WFB_SYNC() __syncthreads()
 #define WFB_KERNEL_PROLOGUE const int bid = (int)blockIdx.x; const int nblocks = (int)gridDim.x; (void)bid; (void)nblocks;
 #define WFB_KERNEL(name, ...) __global__ void name(__VA_ARGS__)
+#define WFB_KERNEL_LB(name, maxthreads, minblocks, ...) __global__ void __launch_bounds__(maxthreads, minblocks) name(__VA_ARGS__)
 WFB_DEV int wfb_warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 WFB_DEV int wfb_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 WFB_DEV unsigned wfb_warp_add(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
@@ -42,6 +43,7 @@ WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { return __ldg(p); }
 #define WFB_SYNC() ((void)0)
 #define WFB_KERNEL_PROLOGUE
 #define WFB_KERNEL(name, ...) static void name(int bid, int nblocks, __VA_ARGS__)
+#define WFB_KERNEL_LB(name, maxthreads, minblocks, ...) static void name(int bid, int nblocks, __VA_ARGS__)
 WFB_DEV int wfb_warp_min(int v) { return v; }
 WFB_DEV int wfb_warp_max(int v) { return v; }
 WFB_DEV unsigned wfb_warp_add(unsigned v) { return v; }

@@ -3,8 +3,7 @@
 Each config = (library variant, WFB_BREAK_THREADS); prints one line per config."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-configs = [("inl_256_2", 256), ("noinl_256_3", 256), ("noinl_1024_1", 256), ("noinl_1024_1", 512), ("noinl_1024_1", 1024),
-           ("inl_512_1", 512), ("noinl_256_3", 128)]
+configs = [("v_256_2", 256), ("v_256_2", 128), ("v_512_1", 512), ("v_256_3", 256), ("v_1024_1", 512), ("v_1024_1", 1024), ("v_256_2_pf1", 256)]
 recs = sys.argv[1] if len(sys.argv) > 1 else "861"
 for var, thr in configs:
     env = dict(os.environ, WFB_LIB=os.path.join(ROOT, "wfmash_b200", "variants", f"lib_{var}.so"), WFB_BREAK_THREADS=str(thr))

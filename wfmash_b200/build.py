@@ -30,7 +30,7 @@ def needs_build():
 
 
 # tuned defaults of the breakpoint kernel (see DESIGN.md / profiles/): __launch_bounds__ and call style
-DEFAULT_DEFS = ["-DWFB_BREAK_MAXTHREADS=256", "-DWFB_BREAK_MINBLOCKS=2"]
+DEFAULT_DEFS = ["-DWFB_BREAK_MAXTHREADS=256", "-DWFB_BREAK_MINBLOCKS=2", "-DWFB_PREFETCH_DIST=0"]
 
 
 def build_variant(out, defs, verbose=False):

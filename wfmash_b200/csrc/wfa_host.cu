@@ -112,7 +112,7 @@ struct wfb_aligner {
   wfb_stream_t stream{};
   DevBuf d_seq, d_pairs, d_slots, d_dense, d_len, d_status, d_counters, d_ctrl;
   DevBuf d_q[4]; /* break[0], break[1], base[0], base[1] */
-  DevBuf d_ws, d_arena, d_log, d_runs, d_srcoff;
+  DevBuf d_ws, d_arena, d_log, d_runs, d_srcoff, d_tasklog;
   HostBuf h_seq, h_dense, h_misc;
 #ifndef WFB_EMU
   cudaEvent_t ev[4]{};
@@ -208,7 +208,7 @@ extern "C" void wfb_aligner_destroy(wfb_aligner_t* a) {
   cudaStreamDestroy(a->stream);
 #endif
   DevBuf* bufs[] = {&a->d_seq, &a->d_pairs, &a->d_slots, &a->d_dense, &a->d_len, &a->d_status, &a->d_counters, &a->d_ctrl,
-                    &a->d_q[0], &a->d_q[1], &a->d_q[2], &a->d_q[3], &a->d_ws, &a->d_arena, &a->d_log, &a->d_runs, &a->d_srcoff};
+                    &a->d_q[0], &a->d_q[1], &a->d_q[2], &a->d_q[3], &a->d_ws, &a->d_arena, &a->d_log, &a->d_runs, &a->d_srcoff, &a->d_tasklog};
   for (DevBuf* b : bufs) b->release();
   a->h_seq.release();
   a->h_dense.release();
@@ -394,6 +394,10 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
   }
   double break_ms = 0.0;
   uint64_t levels = 0;
+  const char* dbg_path = getenv("WFB_DEBUG_TASKS"); /* per-task timeline dump (tuning only) */
+  FILE* dbg_f = dbg_path ? fopen(dbg_path, "w") : nullptr;
+  if (!dbg_f) dbg_path = nullptr;
+  if (dbg_f) fprintf(dbg_f, "level\ttask\tt0_ns\tt1_ns\tsmid\tsteps\tscore_f\tscore_r\tplen\ttlen\tstatus\tlevel_ms\n");
   while (n_break || n_base) {
     ++levels;
     const int nxt = cur ^ 1;
@@ -406,13 +410,19 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     WfbQueue qb, qs;
     qb.tasks = (WfbTask*)a->d_q[nxt].p; qb.count = d_ctrl + 2; qb.cap = (int)cap_next;
     qs.tasks = (WfbTask*)a->d_q[2 + nxt].p; qs.count = d_ctrl + 3; qs.cap = (int)cap_next;
+    WfbTaskLog* d_tasklog = nullptr;
+    if (dbg_path && n_break) {
+      if (a->d_tasklog.ensure(sizeof(WfbTaskLog) * n_break)) { g_last_error = "device allocation failed (tasklog)"; return WFB_ENOMEM; }
+      d_tasklog = (WfbTaskLog*)a->d_tasklog.p;
+      WFB_MEMSET(d_tasklog, 0, sizeof(WfbTaskLog) * n_break, s);
+    }
     if (n_break) {
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[2], s));
 #endif
       WFB_LAUNCH(wfb_break_kernel, (int)std::min<size_t>(n_break, (size_t)cta_break), kBreakThreads, s,
                  (const WfbTask*)a->d_q[cur].p, (int)n_break, d_ctrl + 0, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq,
-                 (int32_t*)a->d_ws.p, ws_stride, W, pen, qb, qs, d_slots, d_status, d_counters);
+                 (int32_t*)a->d_ws.p, ws_stride, W, pen, qb, qs, d_slots, d_status, d_counters, d_tasklog);
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[3], s));
 #endif
@@ -437,11 +447,24 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
       }
     }
 #endif
+    if (dbg_f && n_break) {
+      std::vector<WfbTaskLog> tl(n_break);
+      WFB_D2H(tl.data(), d_tasklog, sizeof(WfbTaskLog) * n_break, s);
+      WFB_STREAM_SYNC(s);
+      float lms = 0.f;
+#ifndef WFB_EMU
+      cudaEventElapsedTime(&lms, a->ev[2], a->ev[3]);
+#endif
+      for (size_t i = 0; i < n_break; ++i)
+        fprintf(dbg_f, "%llu\t%zu\t%lld\t%lld\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%.3f\n", (unsigned long long)levels, i, tl[i].t0, tl[i].t1,
+                tl[i].smid, tl[i].steps, tl[i].score_f, tl[i].score_r, tl[i].plen, tl[i].tlen, tl[i].status, lms);
+    }
     n_break = (size_t)std::min<long long>(ctrl[2], (long long)cap_next);
     n_base = (size_t)std::min<long long>(ctrl[3], (long long)cap_next);
     cur = nxt;
     if (levels > 4096) { g_last_error = "task recursion did not converge"; return WFB_ECUDA; }
   }
+  if (dbg_f) fclose(dbg_f);
   /* ---- compaction + results ---- */
   WFB_LAUNCH(wfb_compact_kernel, std::min(n, a->sm_count * 8), 256, s, (const WfbPairDesc*)d_pairs, n, (const char*)d_slots, d_dense, d_len);
 #ifndef WFB_EMU

@@ -24,6 +24,12 @@
 #pragma once
 #include "wfb_rt.h"
 
+#ifndef WFB_UNROLL
+#define WFB_UNROLL 1
+#endif
+#ifndef WFB_PREFETCH_DIST
+#define WFB_PREFETCH_DIST 1
+#endif
 #ifndef WFB_STEP_INLINE
 #ifdef WFB_STEP_NOINLINE
 #define WFB_STEP_INLINE WFB_DEV_NOINLINE
@@ -75,6 +81,30 @@ struct WfbCounters {
   unsigned long long base_cells, base_extend_matches, base_score_steps; /* base kernel's share */
 };
 
+struct WfbTaskLog { /* optional per-task timeline (WFB_DEBUG_TASKS), one entry per breakpoint task */
+  long long t0, t1; /* globaltimer ns */
+  int smid, steps, score_f, score_r, plen, tlen, status, pad_;
+};
+
+WFB_DEV long long wfb_globaltimer() {
+#ifndef WFB_EMU
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#else
+  return 0;
+#endif
+}
+WFB_DEV int wfb_smid() {
+#ifndef WFB_EMU
+  int s;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+  return s;
+#else
+  return 0;
+#endif
+}
+
 struct WfbRing { /* shared-memory wavefront metadata of the last R scores */
   int lo[WFB_RMAX][5];
   int hi[WFB_RMAX][5];
@@ -115,7 +145,7 @@ WFB_DEV int32_t wfb_get(const int32_t* basep, const WfbIn& w, int k) {
   return (k >= w.lo && k <= w.hi) ? basep[w.off + k] : WFB_OFFSET_NULL;
 }
 
-/* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 7 bytes past
+/* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 15 bytes past
  * the cap (sequence buffers are padded). wavefront_extend_kernels.c:68-92 does the same 8 bytes at a
  * time on the CPU. */
 WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
@@ -132,17 +162,35 @@ WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
   uint32_t p0 = wfb_ldg32(pw), t0 = wfb_ldg32(tw);
   int n = 0;
   while (n < limit) {
-    const uint32_t p1 = wfb_ldg32(++pw), t1 = wfb_ldg32(++tw);
-    const uint32_t x = __funnelshift_r(p0, p1, ps) ^ __funnelshift_r(t0, t1, ts);
-    if (x) {
-      n += (__ffs((int)x) - 1) >> 3;
+    /* two words of each sequence per trip, the four loads are independent */
+    const uint32_t p1 = wfb_ldg32(pw + 1), t1 = wfb_ldg32(tw + 1);
+    const uint32_t p2 = wfb_ldg32(pw + 2), t2 = wfb_ldg32(tw + 2);
+    const uint32_t x1 = __funnelshift_r(p0, p1, ps) ^ __funnelshift_r(t0, t1, ts);
+    if (x1) {
+      n += (__ffs((int)x1) - 1) >> 3;
       break;
     }
-    n += 4;
-    p0 = p1;
-    t0 = t1;
+    const uint32_t x2 = __funnelshift_r(p1, p2, ps) ^ __funnelshift_r(t1, t2, ts);
+    if (x2) {
+      n += 4 + ((__ffs((int)x2) - 1) >> 3);
+      break;
+    }
+    n += 8;
+    p0 = p2;
+    t0 = t2;
+    pw += 2;
+    tw += 2;
   }
   return n < limit ? n : limit;
+#endif
+}
+
+/* L2 prefetch of one 128-byte line (the rows a later score step will read come from DRAM otherwise) */
+WFB_DEV void wfb_prefetch_l2(const void* p) {
+#ifndef WFB_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
 #endif
 }
 
@@ -168,7 +216,7 @@ struct WfbAcc {
 template <class Alloc>
 WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
                      const uint8_t* tseq, int plen, int tlen, int cend, int& num_null, Alloc& alloc, int* red_maxak,
-                     int& max_ak_out, WfbAcc& acc) {
+                     int* red_end, int& max_ak_out, WfbAcc& acc) {
   const int R = pen.R, slot = score % R, nslot = (score + 1) % R;
   const int par = score % 3, npar = (score + 1) % 3;
   const WfbIn m_misms = wfb_fetch(ring, basep, R, WFB_M, score - pen.x);
@@ -227,77 +275,145 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     red_maxak[npar] = 0;
     acc.cells += (unsigned long long)(hi - lo + 1);
   }
-  int tlo_m = INT_MAX, thi_m = INT_MIN, tlo_i1 = INT_MAX, thi_i1 = INT_MIN, tlo_i2 = INT_MAX, thi_i2 = INT_MIN;
-  int tlo_d1 = INT_MAX, thi_d1 = INT_MIN, tlo_d2 = INT_MAX, thi_d2 = INT_MIN;
-  int tmax = 0;
-  int ak_i1 = INT_MIN, ak_i2 = INT_MIN, ak_d1 = INT_MIN, ak_d2 = INT_MIN;
-  /* wavefront_compute_affine2p_idm (wavefront_compute_affine2p.c:45-106) fused with
-   * wavefront_extend_matches_packed_end2end_max (wavefront_extend_kernels.c:125-152) and
-   * wavefront_compute_trim_ends (wavefront_compute.c:579-613) */
-  for (int k = lo + WFB_TID; k <= hi; k += WFB_NT) {
-    const int32_t ins1 = max(wfb_get(basep, m_open1, k - 1), wfb_get(basep, i1_ext, k - 1)) + 1;
-    const int32_t ins2 = max(wfb_get(basep, m_open2, k - 1), wfb_get(basep, i2_ext, k - 1)) + 1;
-    const int32_t del1 = max(wfb_get(basep, m_open1, k + 1), wfb_get(basep, d1_ext, k + 1));
-    const int32_t del2 = max(wfb_get(basep, m_open2, k + 1), wfb_get(basep, d2_ext, k + 1));
-    const int32_t misms = wfb_get(basep, m_misms, k) + 1;
-    int32_t mx = max(max(del1, del2), max(misms, max(ins1, ins2)));
-    if (wfb_inbounds(mx, k, plen, tlen)) {
-      const int v = mx - k, h = mx;
-      const int run = wfb_match_run(pseq + v, tseq + h, min(plen - v, tlen - h));
-      mx += run;
-      acc.matches += (unsigned)run;
-      tmax = max(tmax, 2 * mx - k);
-      tlo_m = min(tlo_m, k);
-      thi_m = max(thi_m, k);
-    } else {
-      mx = WFB_OFFSET_NULL;
-    }
-    basep[ob[WFB_M] + k] = mx;
-    /* anti-diagonal maxima are taken over EVERY computed cell (raw values, also out-of-bounds ones):
-     * a superset of what the overlap scan can see, so pruning on them never hides a hit */
-    if (ex_i1) { basep[ob[WFB_I1] + k] = ins1; ak_i1 = max(ak_i1, 2 * ins1 - k); if (wfb_inbounds(ins1, k, plen, tlen)) { tlo_i1 = min(tlo_i1, k); thi_i1 = max(thi_i1, k); } }
-    if (ex_i2) { basep[ob[WFB_I2] + k] = ins2; ak_i2 = max(ak_i2, 2 * ins2 - k); if (wfb_inbounds(ins2, k, plen, tlen)) { tlo_i2 = min(tlo_i2, k); thi_i2 = max(thi_i2, k); } }
-    if (ex_d1) { basep[ob[WFB_D1] + k] = del1; ak_d1 = max(ak_d1, 2 * del1 - k); if (wfb_inbounds(del1, k, plen, tlen)) { tlo_d1 = min(tlo_d1, k); thi_d1 = max(thi_d1, k); } }
-    if (ex_d2) { basep[ob[WFB_D2] + k] = del2; ak_d2 = max(ak_d2, 2 * del2 - k); if (wfb_inbounds(del2, k, plen, tlen)) { tlo_d2 = min(tlo_d2, k); thi_d2 = max(thi_d2, k); } }
+  /* per-thread trim / anti-diagonal accumulators */
+  int tlo[5], thi[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) { tlo[c] = INT_MAX; thi[c] = INT_MIN; }
+  int tmax = 0;        /* max anti-diagonal of extended in-bounds M cells (wavefront_extend_*_max)        */
+  int tak = INT_MIN;   /* max anti-diagonal over EVERY computed value of every component (overlap pruning;
+                          raw values incl. out-of-bounds ones: a superset of what the overlap scan sees) */
+  const int ak_end = tlen - plen; /* the diagonal wavefront_termination_end2end looks at */
+
+  /* One wavefront cell (wavefront_compute_affine2p_idm, wavefront_compute_affine2p.c:71-105) fused with
+   * its extension (wavefront_extend_kernels.c:125-152) and trim bookkeeping (wavefront_compute.c:579-613). */
+#define WFB_CELL(K, O1M, O1P, O2M, O2P, I1V, I2V, D1V, D2V, MMV, OUT_M, OUT_I1, OUT_I2, OUT_D1, OUT_D2)      \
+  {                                                                                                       \
+    const int k_ = (K);                                                                                   \
+    const int32_t ins1 = max((O1M), (I1V)) + 1;                                                           \
+    const int32_t ins2 = max((O2M), (I2V)) + 1;                                                           \
+    const int32_t del1 = max((O1P), (D1V));                                                               \
+    const int32_t del2 = max((O2P), (D2V));                                                               \
+    int32_t mx = max(max(del1, del2), max((MMV) + 1, max(ins1, ins2)));                                   \
+    if (mx >= 0) tak = max(tak, 2 * mx - k_); /* negative (null-ish) values can never be part of a hit */ \
+    if (wfb_inbounds(mx, k_, plen, tlen)) {                                                               \
+      const int v_ = mx - k_;                                                                             \
+      const int run = wfb_match_run(pseq + v_, tseq + mx, min(plen - v_, tlen - mx));                     \
+      mx += run;                                                                                          \
+      acc.matches += (unsigned)run;                                                                       \
+      tmax = max(tmax, 2 * mx - k_);                                                                      \
+      tlo[WFB_M] = min(tlo[WFB_M], k_);                                                                   \
+      thi[WFB_M] = max(thi[WFB_M], k_);                                                                   \
+    } else {                                                                                              \
+      mx = WFB_OFFSET_NULL;                                                                               \
+    }                                                                                                     \
+    /* I keeps v of an in-bounds source, D keeps h: one unsigned compare decides in-bounds */             \
+    if (ex_i1 && (uint32_t)ins1 <= (uint32_t)tlen && (uint32_t)(ins1 - k_) <= (uint32_t)plen) { tlo[WFB_I1] = min(tlo[WFB_I1], k_); thi[WFB_I1] = max(thi[WFB_I1], k_); } \
+    if (ex_i2 && (uint32_t)ins2 <= (uint32_t)tlen && (uint32_t)(ins2 - k_) <= (uint32_t)plen) { tlo[WFB_I2] = min(tlo[WFB_I2], k_); thi[WFB_I2] = max(thi[WFB_I2], k_); } \
+    if (ex_d1 && (uint32_t)del1 <= (uint32_t)tlen && (uint32_t)(del1 - k_) <= (uint32_t)plen) { tlo[WFB_D1] = min(tlo[WFB_D1], k_); thi[WFB_D1] = max(thi[WFB_D1], k_); } \
+    if (ex_d2 && (uint32_t)del2 <= (uint32_t)tlen && (uint32_t)(del2 - k_) <= (uint32_t)plen) { tlo[WFB_D2] = min(tlo[WFB_D2], k_); thi[WFB_D2] = max(thi[WFB_D2], k_); } \
+    if (k_ == ak_end) /* hand the end component's offset on the final diagonal to the termination test */ \
+      red_end[par] = cend == WFB_M ? mx : cend == WFB_I1 ? ins1 : cend == WFB_I2 ? ins2 : cend == WFB_D1 ? del1 : del2; \
+    (OUT_M) = mx; (OUT_I1) = ins1; (OUT_I2) = ins2; (OUT_D1) = del1; (OUT_D2) = del2;                       \
   }
+
+  const int kalign = alloc.kalign;
+#ifndef WFB_EMU
+  const bool vec_ok = kalign >= 0;
+#else
+  const bool vec_ok = false;
+#endif
+  if (vec_ok) {
+#ifndef WFB_EMU
+    /* groups of 4 diagonals whose cells are 16-byte aligned in every row: 128-bit loads / stores, range
+     * checks once per group; ragged groups at the ends of any input take the scalar path */
+    int safe_lo = lo, safe_hi = hi; /* diagonals k with [k-1, k+4] inside every non-null input */
+    if (!n_m)  { safe_lo = max(safe_lo, m_misms.lo + 1); safe_hi = min(safe_hi, m_misms.hi - 4); }
+    if (!n_o1) { safe_lo = max(safe_lo, m_open1.lo + 1); safe_hi = min(safe_hi, m_open1.hi - 4); }
+    if (!n_o2) { safe_lo = max(safe_lo, m_open2.lo + 1); safe_hi = min(safe_hi, m_open2.hi - 4); }
+    if (!n_i1) { safe_lo = max(safe_lo, i1_ext.lo + 1);  safe_hi = min(safe_hi, i1_ext.hi - 4); }
+    if (!n_i2) { safe_lo = max(safe_lo, i2_ext.lo + 1);  safe_hi = min(safe_hi, i2_ext.hi - 4); }
+    if (!n_d1) { safe_lo = max(safe_lo, d1_ext.lo + 1);  safe_hi = min(safe_hi, d1_ext.hi - 4); }
+    if (!n_d2) { safe_lo = max(safe_lo, d2_ext.lo + 1);  safe_hi = min(safe_hi, d2_ext.hi - 4); }
+    safe_hi = min(safe_hi, hi - 3);
+    const int kfirst = lo - ((lo + kalign) & 3); /* first group start (<= lo) */
+    for (int k0 = kfirst + 4 * WFB_TID; k0 <= hi; k0 += 4 * WFB_NT) {
+      int32_t rm[4], ri1[4], ri2[4], rd1[4], rd2[4];
+      if (k0 >= safe_lo && k0 <= safe_hi) {
+        const int4 NUL4 = make_int4(WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL);
+        int4 vo1 = NUL4, vo2 = NUL4, vi1 = NUL4, vi2 = NUL4, vd1 = NUL4, vd2 = NUL4, vmm = NUL4;
+        int32_t so1m = WFB_OFFSET_NULL, so1p = WFB_OFFSET_NULL, so2m = WFB_OFFSET_NULL, so2p = WFB_OFFSET_NULL;
+        int32_t si1 = WFB_OFFSET_NULL, si2 = WFB_OFFSET_NULL, sd1 = WFB_OFFSET_NULL, sd2 = WFB_OFFSET_NULL;
+        if (!n_o1) { const int32_t* p = basep + m_open1.off + k0; vo1 = *(const int4*)p; so1m = p[-1]; so1p = p[4]; }
+        if (!n_o2) { const int32_t* p = basep + m_open2.off + k0; vo2 = *(const int4*)p; so2m = p[-1]; so2p = p[4]; }
+        if (!n_i1) { const int32_t* p = basep + i1_ext.off + k0; vi1 = *(const int4*)p; si1 = p[-1]; }
+        if (!n_i2) { const int32_t* p = basep + i2_ext.off + k0; vi2 = *(const int4*)p; si2 = p[-1]; }
+        if (!n_d1) { const int32_t* p = basep + d1_ext.off + k0; vd1 = *(const int4*)p; sd1 = p[4]; }
+        if (!n_d2) { const int32_t* p = basep + d2_ext.off + k0; vd2 = *(const int4*)p; sd2 = p[4]; }
+        if (!n_m)  { vmm = *(const int4*)(basep + m_misms.off + k0); }
+        WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+        WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+        WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+        WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+        *(int4*)(basep + ob[WFB_M] + k0) = make_int4(rm[0], rm[1], rm[2], rm[3]);
+        if (ex_i1) *(int4*)(basep + ob[WFB_I1] + k0) = make_int4(ri1[0], ri1[1], ri1[2], ri1[3]);
+        if (ex_i2) *(int4*)(basep + ob[WFB_I2] + k0) = make_int4(ri2[0], ri2[1], ri2[2], ri2[3]);
+        if (ex_d1) *(int4*)(basep + ob[WFB_D1] + k0) = make_int4(rd1[0], rd1[1], rd1[2], rd1[3]);
+        if (ex_d2) *(int4*)(basep + ob[WFB_D2] + k0) = make_int4(rd2[0], rd2[1], rd2[2], rd2[3]);
+      } else {
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u;
+          if (k < lo || k > hi) continue;
+          WFB_CELL(k, wfb_get(basep, m_open1, k - 1), wfb_get(basep, m_open1, k + 1), wfb_get(basep, m_open2, k - 1),
+                   wfb_get(basep, m_open2, k + 1), wfb_get(basep, i1_ext, k - 1), wfb_get(basep, i2_ext, k - 1),
+                   wfb_get(basep, d1_ext, k + 1), wfb_get(basep, d2_ext, k + 1), wfb_get(basep, m_misms, k),
+                   rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+          basep[ob[WFB_M] + k] = rm[0];
+          if (ex_i1) basep[ob[WFB_I1] + k] = ri1[0];
+          if (ex_i2) basep[ob[WFB_I2] + k] = ri2[0];
+          if (ex_d1) basep[ob[WFB_D1] + k] = rd1[0];
+          if (ex_d2) basep[ob[WFB_D2] + k] = rd2[0];
+        }
+      }
+    }
+#endif
+  } else {
+    for (int k = lo + WFB_TID; k <= hi; k += WFB_NT) {
+      int32_t rm, ri1, ri2, rd1, rd2;
+      WFB_CELL(k, wfb_get(basep, m_open1, k - 1), wfb_get(basep, m_open1, k + 1), wfb_get(basep, m_open2, k - 1),
+               wfb_get(basep, m_open2, k + 1), wfb_get(basep, i1_ext, k - 1), wfb_get(basep, i2_ext, k - 1),
+               wfb_get(basep, d1_ext, k + 1), wfb_get(basep, d2_ext, k + 1), wfb_get(basep, m_misms, k), rm, ri1, ri2, rd1, rd2)
+      basep[ob[WFB_M] + k] = rm;
+      if (ex_i1) basep[ob[WFB_I1] + k] = ri1;
+      if (ex_i2) basep[ob[WFB_I2] + k] = ri2;
+      if (ex_d1) basep[ob[WFB_D1] + k] = rd1;
+      if (ex_d2) basep[ob[WFB_D2] + k] = rd2;
+    }
+  }
+#undef WFB_CELL
   /* trimmed [lo,hi] of each component = min / max diagonal holding an in-bounds offset */
   {
     const int lane = wfb_lane();
-    int v;
-    v = wfb_warp_min(tlo_m);  if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_M], v);
-    v = wfb_warp_max(thi_m);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_M], v);
-    if (ex_i1) {
-      v = wfb_warp_min(tlo_i1); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_I1], v);
-      v = wfb_warp_max(thi_i1); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_I1], v);
-      v = wfb_warp_max(ak_i1);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_I1], v);
+    const bool exs[5] = {true, ex_i1, ex_i2, ex_d1, ex_d2};
+    const int vak = wfb_warp_max(tak);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      if (!exs[c]) continue;
+      int v = wfb_warp_min(tlo[c]); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][c], v);
+      v = wfb_warp_max(thi[c]);     if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][c], v);
+      if (lane == 0 && vak != INT_MIN) wfb_smem_max(&ring.mak[slot][c], vak);
     }
-    if (ex_i2) {
-      v = wfb_warp_min(tlo_i2); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_I2], v);
-      v = wfb_warp_max(thi_i2); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_I2], v);
-      v = wfb_warp_max(ak_i2);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_I2], v);
-    }
-    if (ex_d1) {
-      v = wfb_warp_min(tlo_d1); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_D1], v);
-      v = wfb_warp_max(thi_d1); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_D1], v);
-      v = wfb_warp_max(ak_d1);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_D1], v);
-    }
-    if (ex_d2) {
-      v = wfb_warp_min(tlo_d2); if (lane == 0 && v != INT_MAX) wfb_smem_min(&ring.lo[slot][WFB_D2], v);
-      v = wfb_warp_max(thi_d2); if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.hi[slot][WFB_D2], v);
-      v = wfb_warp_max(ak_d2);  if (lane == 0 && v != INT_MIN) wfb_smem_max(&ring.mak[slot][WFB_D2], v);
-    }
-    v = wfb_warp_max(tmax);
+    const int v = wfb_warp_max(tmax);
     if (lane == 0) {
       if (v > 0) wfb_smem_max(&red_maxak[par], v);
-      wfb_smem_max(&ring.mak[slot][WFB_M], v); /* v >= 0 even without in-bounds cells: a superset bound */
+      wfb_smem_max(&ring.mak[slot][WFB_M], v); /* extended M cells can exceed the raw bound */
     }
   }
   WFB_SYNC();
   max_ak_out = red_maxak[par];
   /* wavefront_termination_end2end, wavefront_termination.c:37-114 */
-  const int ak = tlen - plen;
-  if (ring.ex[slot][cend] && ring.lo[slot][cend] <= ak && ak <= ring.hi[slot][cend]) {
-    if (basep[ring.boff[slot][cend] + ak] >= tlen) return WFB_ST_END_REACHED;
+  if (ring.ex[slot][cend] && ring.lo[slot][cend] <= ak_end && ak_end <= ring.hi[slot][cend]) {
+    /* ak_end lies inside the trimmed range => it was computed in this step => red_end[par] is fresh */
+    if (red_end[par] >= tlen) return WFB_ST_END_REACHED;
   }
   return WFB_ST_OK;
 }
@@ -313,66 +429,123 @@ WFB_DEV int wfb_gap_of(const WfbPen& pen, int comp) {
   return comp == WFB_M ? 0 : ((comp == WFB_I1 || comp == WFB_D1) ? pen.o1 : pen.o2);
 }
 
+/* Shared scratch of the overlap scan. */
+struct WfbOverlapShared {
+  int found[WFB_RMAX * 5]; /* first satisfying k0 per candidate q = i*5+j; INT_MAX = none (kept clean between calls) */
+  int cand[WFB_RMAX * 5];  /* compact list of candidate q's that survive the cheap tests */
+  int ncand;
+  unsigned hitmask[(WFB_RMAX * 5 + 31) / 32]; /* bit q set <=> found[q] valid */
+};
+
 WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const WfbRing& r1, const int32_t* base1,
                          const WfbPen& pen, int score_0, int score_1, bool bp_forward, int plen, int tlen,
-                         WfbBreakpoint* bp, int* found, WfbAcc& acc) {
+                         WfbBreakpoint* bp, WfbOverlapShared* os, WfbAcc& acc) {
   const int R = pen.R, s0 = score_0 % R;
   if (!r0.ex[s0][WFB_M]) return; /* uniform */
   const int best0 = bp->score;
   const int kinv = tlen - plen;
-  const int order[5] = {WFB_D2, WFB_I2, WFB_D1, WFB_I1, WFB_M};
-  for (int i = 0; i < pen.scope; ++i) {
+  const int npairs = pen.scope * 5;
+  /* 1) one thread per candidate (score_i, component): O(1) tests in parallel instead of a serial loop.
+   *    q = i*5 + j with j indexing the reference's scan order D2, I2, D1, I1, M (:911-953). */
+  for (int q = WFB_TID; q < npairs; q += WFB_NT) {
+    const int i = q / 5, j = q - i * 5;
+    const int c = j == 0 ? WFB_D2 : j == 1 ? WFB_I2 : j == 2 ? WFB_D1 : j == 3 ? WFB_I1 : WFB_M;
     const int score_i = score_1 - i;
-    if (score_i < 0) break;
-    const int si = score_i % R;
-    for (int j = 0; j < 5; ++j) {
-      const int c = order[j];
-      if (score_0 + score_i - wfb_gap_of(pen, c) >= best0) continue;
-      if (!r0.ex[s0][c] || !r1.ex[si][c]) continue;
-      const int lo_0 = r0.lo[s0][c], hi_0 = r0.hi[s0][c];
-      const int lo1r = r1.lo[si][c], hi1r = r1.hi[si][c];
-      if (lo_0 > hi_0 || lo1r > hi1r) continue;
+    bool ok = score_i >= 0;
+    if (ok) {
+      const int si = score_i % R;
+      ok = (score_0 + score_i - wfb_gap_of(pen, c) < best0) && r0.ex[s0][c] && r1.ex[si][c];
       /* off0[k0] + off1[kinv-k0] >= tlen  <=>  ak0 + ak1 >= plen + tlen (ak = 2*off - k): no diagonal can
        * satisfy it unless the two wavefronts' maximal anti-diagonals do */
-      if ((long long)r0.mak[s0][c] + (long long)r1.mak[si][c] < (long long)plen + tlen) continue;
-      const int lo_1 = kinv - hi1r, hi_1 = kinv - lo1r;
-      const int max_lo = max(lo_0, lo_1), min_hi = min(hi_0, hi_1);
-      if (min_hi < max_lo) continue;
-      const int32_t* p0 = base0 + r0.boff[s0][c];
-      const int32_t* p1 = base1 + r1.boff[si][c];
-      int kfound = INT_MAX;
-      for (int k0 = max_lo + WFB_TID; k0 <= min_hi; k0 += WFB_NT) {
+      ok = ok && ((long long)r0.mak[s0][c] + (long long)r1.mak[si][c] >= (long long)plen + tlen);
+      if (ok) {
+        const int lo_0 = r0.lo[s0][c], hi_0 = r0.hi[s0][c];
+        const int lo1r = r1.lo[si][c], hi1r = r1.hi[si][c];
+        ok = lo_0 <= hi_0 && lo1r <= hi1r && min(hi_0, kinv - lo1r) >= max(lo_0, kinv - hi1r);
+      }
+    }
+    if (ok) os->cand[wfb_atomic_add(&os->ncand, 1)] = q;
+  }
+  WFB_SYNC();
+  const int ncand = os->ncand;
+  if (ncand == 0) return; /* uniform: nothing can overlap yet (ncand stays 0 for the next call) */
+  /* 2) candidates are dealt round-robin to the warps; a warp scans its pair's diagonal range 32 at a
+   *    time and stops at the first chunk holding a hit (ballot + ffs = lowest satisfying k0, exactly the
+   *    reference's ascending scan :530-569, :841-870) */
+#ifndef WFB_EMU
+  const int nwarps = WFB_NT >> 5, warp_id = WFB_TID >> 5, lane = WFB_TID & 31;
+#else
+  const int nwarps = 1, warp_id = 0, lane = 0;
+#endif
+  for (int ci = warp_id; ci < ncand; ci += nwarps) {
+    const int q = os->cand[ci];
+    const int i = q / 5, j = q - i * 5;
+    const int c = j == 0 ? WFB_D2 : j == 1 ? WFB_I2 : j == 2 ? WFB_D1 : j == 3 ? WFB_I1 : WFB_M;
+    const int si = (score_1 - i) % R;
+    const int lo_0 = r0.lo[s0][c], hi_0 = r0.hi[s0][c];
+    const int lo_1 = kinv - r1.hi[si][c], hi_1 = kinv - r1.lo[si][c];
+    const int max_lo = max(lo_0, lo_1), min_hi = min(hi_0, hi_1);
+    const int32_t* p0 = base0 + r0.boff[s0][c];
+    const int32_t* p1 = base1 + r1.boff[si][c];
+    int kfound = INT_MAX;
+    for (int kb = max_lo; kb <= min_hi; kb += 32) {
+      const int k0 = kb + lane;
+      bool hit = false;
+      if (k0 <= min_hi) {
         const int k1 = kinv - k0;
         const int32_t o0 = p0[k0], o1 = p1[k1];
         if (o0 + o1 >= tlen) {
+          hit = true;
           if (c != WFB_M) {
             const int kk = bp_forward ? k0 : k1;
             const int32_t oo = bp_forward ? o0 : o1;
-            if (oo - kk > plen || oo > tlen) continue;
+            if (oo - kk > plen || oo > tlen) hit = false; /* out-of-bounds coordinates: keep scanning */
           }
-          kfound = k0;
-          break;
         }
       }
-      kfound = wfb_warp_min(kfound);
-      if (wfb_lane() == 0 && kfound != INT_MAX) wfb_smem_min(&found[i * 5 + j], kfound);
-      if (WFB_TID == 0) acc.overlap += (unsigned long long)(min_hi - max_lo + 1);
+#ifndef WFB_EMU
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) { kfound = kb + __ffs((int)bal) - 1; break; }
+#else
+      if (hit) { kfound = k0; break; }
+      kb -= 31; /* one diagonal per trip in the single-thread emulation */
+#endif
+    }
+    if (lane == 0) {
+      if (kfound != INT_MAX) {
+        os->found[q] = kfound;
+#ifndef WFB_EMU
+        atomicOr(&os->hitmask[q >> 5], 1u << (q & 31));
+#else
+        os->hitmask[q >> 5] |= 1u << (q & 31);
+#endif
+      }
+      acc.overlap += (unsigned long long)(min_hi - max_lo + 1);
     }
   }
   WFB_SYNC();
+  /* 3) thread 0 replays the reference's sequential rule over the hits in scan order: a candidate
+   *    replaces the breakpoint only if it is strictly better than the best so far (:527,:564,:912-947;
+   *    with 0 <= o1 <= o2, checked on the host, the per-class `continue`s equal per-candidate tests) */
   if (WFB_TID == 0) {
-    for (int i = 0; i < pen.scope; ++i) {
-      const int score_i = score_1 - i;
-      if (score_i < 0) break;
-      const int si = score_i % R;
-      for (int j = 0; j < 5; ++j) {
-        const int c = order[j];
+    for (int w = 0; w < (npairs + 31) / 32; ++w) {
+      unsigned m = os->hitmask[w];
+      os->hitmask[w] = 0;
+      while (m) {
+#ifndef WFB_EMU
+        const int b = __ffs((int)m) - 1;
+#else
+        const int b = __builtin_ctz(m);
+#endif
+        m &= m - 1;
+        const int q = w * 32 + b;
+        const int i = q / 5, j = q - i * 5;
+        const int c = j == 0 ? WFB_D2 : j == 1 ? WFB_I2 : j == 2 ? WFB_D1 : j == 3 ? WFB_I1 : WFB_M;
+        const int score_i = score_1 - i, si = score_i % R;
         const int cand = score_0 + score_i - wfb_gap_of(pen, c);
-        /* the reference `continue`s to the next i when a class (o2, o1, M) cannot improve; with
-         * o2 >= o1 >= 0 (checked on the host) that equals skipping each candidate individually */
-        const int k0 = found[i * 5 + j];
-        found[i * 5 + j] = INT_MAX;
-        if (cand >= bp->score || k0 == INT_MAX) continue;
+        const int k0 = os->found[q];
+        os->found[q] = INT_MAX;
+        if (cand >= bp->score) continue;
         const int k1 = kinv - k0;
         const int32_t o0 = (base0 + r0.boff[s0][c])[k0];
         const int32_t o1 = (base1 + r1.boff[si][c])[k1];
@@ -389,6 +562,7 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
         bp->component = c;
       }
     }
+    os->ncand = 0;
   }
   WFB_SYNC();
 }
@@ -426,14 +600,16 @@ WFB_DEV void wfb_dispatch_child(const WfbTask& c, char* ops, const WfbQueue& q_b
 struct WfbBreakShared {
   WfbRing ring[2];
   WfbBreakpoint bp;
-  int found[WFB_RMAX * 5];
+  WfbOverlapShared os;
   int red_maxak[2][3];
+  int red_end[2][3];
   int task_idx;
 };
 
 struct WfbAllocFixed { /* breakpoint kernel: every (slot, component) has a fixed row of W ints */
   int dirbase; /* dir * R * 5 * W + kshift */
   int W;
+  int kalign;  /* (k + kalign) % 4 == 0  <=>  cell(k) is 16-byte aligned, the same for every row (W % 8 == 0) */
   WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) const {
     (void)lo; (void)hi;
     for (int c = 0; c < 5; ++c) ob[c] = dirbase + (slot * 5 + c) * W;
@@ -487,7 +663,7 @@ WFB_DEV void wfb_init_score0(WfbRing& ring, int32_t* basep, int boff0, int cbegi
 #endif
 WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const WfbTask* tasks, int ntasks, int* task_counter, const WfbPairDesc* pairs,
            const uint8_t* seq, int32_t* ws_all, long long ws_stride /* ints per CTA */, int W, WfbPen pen,
-           WfbQueue q_break, WfbQueue q_base, char* ops_all, int* pair_status, WfbCounters* counters) {
+           WfbQueue q_break, WfbQueue q_base, char* ops_all, int* pair_status, WfbCounters* counters, WfbTaskLog* tasklog) {
   WFB_KERNEL_PROLOGUE
   WFB_SHARED WfbBreakShared sh;
   WFB_SHARED int sh_st[2];
@@ -507,6 +683,8 @@ WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const
     char* const ops = ops_all + pd.ops_off;
     const int plen = t.pe - t.pb, tlen = t.te - t.tb;
     ntask_done++;
+    const long long tl_t0 = tasklog ? wfb_globaltimer() : 0;
+    const unsigned long long tl_s0 = acc.steps;
     /* trivial cases, wavefront_bialign.c:1160-1165 */
     if (tlen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'D', plen); continue; }
     if (plen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'I', tlen); continue; }
@@ -520,14 +698,17 @@ WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const
     const int kshift = plen + 1;
     WfbAllocFixed af, ar;
     af.W = ar.W = W;
+    af.kalign = ar.kalign = kshift & 3; /* dirbase = (multiple of 8) + kshift */
     af.dirbase = kshift;
     ar.dirbase = R * 5 * W + kshift;
     wfb_ring_reset(sh.ring[0], R);
     wfb_ring_reset(sh.ring[1], R);
-    for (int i = WFB_TID; i < WFB_RMAX * 5; i += WFB_NT) sh.found[i] = INT_MAX;
+    for (int i = WFB_TID; i < WFB_RMAX * 5; i += WFB_NT) sh.os.found[i] = INT_MAX;
+    if (WFB_TID < (WFB_RMAX * 5 + 31) / 32) sh.os.hitmask[WFB_TID] = 0;
     if (WFB_TID == 0) {
       for (int d = 0; d < 2; ++d) for (int j = 0; j < 3; ++j) sh.red_maxak[d][j] = 0;
       sh.bp.score = INT_MAX;
+      sh.os.ncand = 0;
     }
     WFB_SYNC();
     if (WFB_TID == 0) {
@@ -553,13 +734,13 @@ WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const
     while (status == WFB_ST_OK) {
       if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
       ++score_forward;
-      int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], max_ak, acc);
+      int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
       if (forward_max_ak < max_ak) forward_max_ak = max_ak;
       last_wf_forward = true;
       if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
       if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
       ++score_reverse;
-      st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], max_ak, acc);
+      st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
       if (reverse_max_ak < max_ak) reverse_max_ak = max_ak;
       last_wf_forward = false;
       if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
@@ -570,18 +751,24 @@ WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const
       if (last_wf_forward) {
         const int min_score_reverse = (score_reverse > pen.scope - 1) ? score_reverse - (pen.scope - 1) : 0;
         if (score_forward + min_score_reverse - gap_opening >= sh.bp.score) break;
-        wfb_overlap(sh.ring[0], ws, sh.ring[1], ws, pen, score_forward, score_reverse, true, plen, tlen, &sh.bp, sh.found, acc);
+        wfb_overlap(sh.ring[0], ws, sh.ring[1], ws, pen, score_forward, score_reverse, true, plen, tlen, &sh.bp, &sh.os, acc);
         ++score_reverse;
-        const int st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], max_ak, acc);
+        const int st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
         if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
       }
       const int min_score_forward = (score_forward > pen.scope - 1) ? score_forward - (pen.scope - 1) : 0;
       if (min_score_forward + score_reverse - gap_opening >= sh.bp.score) break;
-      wfb_overlap(sh.ring[1], ws, sh.ring[0], ws, pen, score_reverse, score_forward, false, plen, tlen, &sh.bp, sh.found, acc);
+      wfb_overlap(sh.ring[1], ws, sh.ring[0], ws, pen, score_reverse, score_forward, false, plen, tlen, &sh.bp, &sh.os, acc);
       ++score_forward;
-      const int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], max_ak, acc);
+      const int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
       if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
       last_wf_forward = true;
+    }
+    if (tasklog && WFB_TID == 0) {
+      WfbTaskLog tl;
+      tl.t0 = tl_t0; tl.t1 = wfb_globaltimer(); tl.smid = wfb_smid(); tl.steps = (int)(acc.steps - tl_s0);
+      tl.score_f = score_forward; tl.score_r = score_reverse; tl.plen = plen; tl.tlen = tlen; tl.status = status; tl.pad_ = 0;
+      tasklog[ti] = tl;
     }
     if (status != WFB_ST_OK) {
       /* wavefront_bialign_find_breakpoint_exception :1083-1110 */
@@ -614,9 +801,10 @@ WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const
     for (int o = 16; o > 0; o >>= 1) m += __shfl_down_sync(0xffffffffu, m, o);
 #endif
     if (wfb_lane() == 0 && m) wfb_atomic_add64(&counters->extend_matches, m);
+    if (wfb_lane() == 0 && acc.overlap) wfb_atomic_add64(&counters->overlap_tests, acc.overlap);
     if (WFB_TID == 0) {
       wfb_atomic_add64(&counters->cells, acc.cells);
-      wfb_atomic_add64(&counters->overlap_tests, acc.overlap);
+
       wfb_atomic_add64(&counters->score_steps, acc.steps);
       wfb_atomic_add64(&counters->break_tasks, ntask_done);
     }
@@ -641,6 +829,7 @@ struct WfbRun {
 };
 
 struct WfbAllocBump {
+  static const int kalign = -1; /* rows are packed back to back: no common alignment, scalar path only */
   int bump; /* next free int in the arena */
   WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) {
     (void)slot;
@@ -766,6 +955,7 @@ WFB_DEV int wfb_backtrace(const WfbBaseMeta* log, const int32_t* arena, int nsco
 struct WfbBaseShared {
   WfbRing ring;
   int red_maxak[3];
+  int red_end[3];
   int task_idx;
   int st0, ak0;
   int nruns, bt_err;
@@ -819,7 +1009,7 @@ WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter,
     while (status == WFB_ST_OK) {
       ++score;
       if (score > score_cap || (long long)ab.bump + 5LL * (2 * score + 3) > arena_stride) { status = -1; break; }
-      status = wfb_step(sh.ring, arena, pen, score, pf, tf, plen, tlen, t.cend, num_null, ab, sh.red_maxak, max_ak, acc);
+      status = wfb_step(sh.ring, arena, pen, score, pf, tf, plen, tlen, t.cend, num_null, ab, sh.red_maxak, sh.red_end, max_ak, acc);
       if (WFB_TID == 0) {
         const int slot = score % R;
         for (int c = 0; c < 5; ++c) {

@@ -146,6 +146,31 @@ int wfb_sketch_fragments(int device, const char* seq_base, int64_t seq_bytes, co
                          int32_t kmer_size, int32_t sketch_size, wfb_minmer_t* out, int32_t* out_count,
                          double* kernel_ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 1 — reference-side windowed minmers.
+ * Replaces skch::CommonFunc::addMinmers as run per target sequence by Sketch::buildHelper
+ * (src/map/include/commonFunc.hpp:439-708; src/map/include/winSketch.hpp:467-499) for a BATCH of target
+ * sequences. Output = the concatenation Sketch::build makes of the per-sequence results
+ * (winSketch.hpp:424-429): ordered by sequence (input order), then (wpos, wpos_end); records with equal
+ * (wpos, wpos_end) — whose order the reference's unstable std::sort leaves unspecified — by hash.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double stream_kernel_ms; /* CUDA-event time of the streaming-window kernel             */
+  double total_kernel_ms;  /* ... of all kernels incl. stitch, post passes and sorts      */
+  uint64_t bases;          /* target bases processed                                      */
+  uint64_t raw_records;    /* records emitted by the stream before the post passes        */
+  uint64_t chunks;         /* independent chunks (threads) of the stream kernel           */
+  uint64_t stale_absorbed; /* expired heap entries absorbed into a sketch entry (commonFunc.hpp:635-641):
+                              the only situation in which chunking can deviate from the reference  */
+  uint64_t stitch_miss;    /* interval starts that could not be inherited across a chunk boundary (0 = exact) */
+} wfb_minmer_stats_t;
+
+/* seq_ptrs[i] / seq_lens[i] : raw FASTA bases of target i (any case); seq_ids[i] -> MinmerInfo::seqId.
+ * Sequences shorter than window_size are skipped like Sketch::build does (winSketch.hpp:218-232). */
+int wfb_minmers_build(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
+                      int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
+                      int64_t* out_count, wfb_minmer_stats_t* stats);
+
 #ifdef __cplusplus
 }
 #endif

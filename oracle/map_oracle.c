@@ -98,3 +98,306 @@ int orc_sketch_fragment(const char* seq, int len, int k, int s, int32_t seqId, o
   free(all); free(rc);
   return m;
 }
+
+/* =================================================================================================
+ * addMinmers (commonFunc.hpp:439-708): the reference's streaming window sketch, restated with
+ * explicit containers so that every history-dependent quirk is preserved:
+ *   Q            std::deque<(hash,strand,pos)>   -> ring buffer
+ *   sortedWindow std::map<hash,(MinmerInfo,deque<KmerInfo>)> -> array sorted by hash, occurrence
+ *                lists as singly linked lists in a node pool
+ *   heapWindow   std::vector<KmerInfo> + push_heap/pop_heap with (hash,pos) ascending at the front
+ *                -> binary min-heap (only front() and size() are observable, so any heap works)
+ * chunk_begin/chunk_end/warm model the GPU decomposition (see orc_add_minmers_chunked).
+ * ================================================================================================= */
+typedef struct { uint64_t hash; int64_t pos; int16_t strand; } orc_kmer_t;
+typedef struct { orc_kmer_t k; int next; } orc_node_t;
+typedef struct { uint64_t hash; orc_minmer_t mi; int head, tail, count; } orc_went_t;
+
+typedef struct {
+  orc_kmer_t* a; int n, cap;
+} orc_heap_t;
+
+static int kmer_less(const orc_kmer_t* x, const orc_kmer_t* y) {
+  return x->hash < y->hash || (x->hash == y->hash && x->pos < y->pos);
+}
+static void heap_push(orc_heap_t* h, orc_kmer_t v) {
+  if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 1024; h->a = (orc_kmer_t*)realloc(h->a, (size_t)h->cap * sizeof(orc_kmer_t)); }
+  int i = h->n++;
+  while (i > 0) {
+    const int p = (i - 1) / 2;
+    if (!kmer_less(&v, &h->a[p])) break;
+    h->a[i] = h->a[p];
+    i = p;
+  }
+  h->a[i] = v;
+}
+static void heap_sift_down(orc_heap_t* h, int i) {
+  const orc_kmer_t v = h->a[i];
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= h->n) break;
+    if (c + 1 < h->n && kmer_less(&h->a[c + 1], &h->a[c])) ++c;
+    if (!kmer_less(&h->a[c], &v)) break;
+    h->a[i] = h->a[c];
+    i = c;
+  }
+  h->a[i] = v;
+}
+static void heap_pop(orc_heap_t* h) {
+  h->a[0] = h->a[--h->n];
+  if (h->n > 0) heap_sift_down(h, 0);
+}
+
+typedef struct {
+  orc_minmer_t* v; int64_t n, cap;
+} orc_mivec_t;
+static void mivec_push(orc_mivec_t* o, orc_minmer_t m) {
+  if (o->n == o->cap) { o->cap = o->cap ? o->cap * 2 : 4096; o->v = (orc_minmer_t*)realloc(o->v, (size_t)o->cap * sizeof(orc_minmer_t)); }
+  o->v[o->n++] = m;
+}
+
+typedef struct {
+  orc_node_t* nodes; int ncap, nfree; /* free list head */
+} orc_pool_t;
+static int pool_alloc(orc_pool_t* p) {
+  if (p->nfree < 0) {
+    const int old = p->ncap;
+    p->ncap = old ? old * 2 : 4096;
+    p->nodes = (orc_node_t*)realloc(p->nodes, (size_t)p->ncap * sizeof(orc_node_t));
+    for (int i = old; i < p->ncap; ++i) p->nodes[i].next = (i + 1 < p->ncap) ? i + 1 : -1;
+    p->nfree = old;
+  }
+  const int i = p->nfree;
+  p->nfree = p->nodes[i].next;
+  return i;
+}
+static void pool_free(orc_pool_t* p, int i) { p->nodes[i].next = p->nfree; p->nfree = i; }
+
+static void went_push_back(orc_pool_t* p, orc_went_t* e, orc_kmer_t k) {
+  const int n = pool_alloc(p);
+  p->nodes[n].k = k; p->nodes[n].next = -1;
+  if (e->tail >= 0) p->nodes[e->tail].next = n; else e->head = n;
+  e->tail = n; e->count++;
+}
+static void went_pop_front(orc_pool_t* p, orc_went_t* e) {
+  const int n = e->head;
+  e->head = p->nodes[n].next;
+  if (e->head < 0) e->tail = -1;
+  e->count--;
+  pool_free(p, n);
+}
+static void went_clear(orc_pool_t* p, orc_went_t* e) { while (e->head >= 0) went_pop_front(p, e); }
+
+static int cmp_mi_pos(const void* a, const void* b) {
+  const orc_minmer_t* x = (const orc_minmer_t*)a; const orc_minmer_t* y = (const orc_minmer_t*)b;
+  if (x->wpos != y->wpos) return x->wpos < y->wpos ? -1 : 1;
+  if (x->wpos_end != y->wpos_end) return x->wpos_end < y->wpos_end ? -1 : 1;
+  return 0;
+}
+
+/* The stream part of addMinmers (:477-658) over positions [0, len-k]. Raw (pre-post-pass) records are
+ * appended to raw. */
+/* [run_begin, run_end): k-mer start positions processed (a sub-range models one GPU chunk incl. its
+ * warm-up); records are kept only when emitted at a step >= keep_from; final_flush = the :646-658 tail. */
+static void add_minmers_stream_range(const char* seq, int64_t len, int k, int w, int s, int32_t seqId, orc_mivec_t* raw,
+                                     int64_t run_begin, int64_t run_end, int64_t keep_from, int final_flush, orc_mivec_t* open_out);
+static void add_minmers_stream(const char* seq, int64_t len, int k, int w, int s, int32_t seqId, orc_mivec_t* raw) {
+  add_minmers_stream_range(seq, len, k, w, s, seqId, raw, 0, len - k + 1, 0, 1, 0);
+}
+static void add_minmers_stream_range(const char* seq, int64_t len, int k, int w, int s, int32_t seqId, orc_mivec_t* raw,
+                                     int64_t run_begin, int64_t run_end, int64_t keep_from, int final_flush, orc_mivec_t* open_out) {
+  orc_kmer_t* Q = (orc_kmer_t*)malloc((size_t)(w + 2) * sizeof(orc_kmer_t));
+  int qh = 0, qn = 0; const int qcap = w + 2;
+  orc_went_t* W = (orc_went_t*)calloc((size_t)s + 2, sizeof(orc_went_t));
+  int wn = 0;
+  orc_heap_t H = {0, 0, 0};
+  orc_pool_t P = {0, 0, -1};
+  char* rc = (char*)malloc((size_t)k);
+  int ambig = 0;
+  if (run_begin > 0) { /* the counter a run from position 0 would hold here (armed by N at index >= k-1) */
+    for (int64_t j = run_begin + k - 2; j >= run_begin && j >= k - 1; --j)
+      if (seq[j] == 'N') { ambig = (int)(j - run_begin + 1); break; }
+  }
+  const int64_t raw_n0 = raw->n;
+  int64_t keep_mark = -1; /* raw->n when step keep_from starts */
+  for (int64_t i = run_begin; i < run_end; ++i) {
+    if (i == keep_from) keep_mark = raw->n;
+    const int64_t win = i + k - w; /* currentWindowId */
+    if (H.n > 2 * w) { /* :485-495 */
+      int m = 0;
+      for (int j = 0; j < H.n; ++j) if (!(H.a[j].pos < win)) H.a[m++] = H.a[j];
+      H.n = m;
+      for (int j = H.n / 2 - 1; j >= 0; --j) heap_sift_down(&H, j);
+    }
+    revcomp(seq + i, rc, k);
+    const uint64_t hf = orc_kmer_hash(seq + i, k), hb = orc_kmer_hash(rc, k);
+    const uint64_t cur = hf < hb ? hf : hb;
+    const int16_t cur_strand = hf < hb ? 1 : -1;
+    /* leaving k-mer (:517-551) */
+    if (qn > 0 && Q[qh].pos < win) {
+      const orc_kmer_t lv = Q[qh];
+      if (wn > 0 && lv.hash <= W[wn - 1].hash) {
+        int lo = 0, hi = wn; /* find */
+        while (lo < hi) { const int mid = (lo + hi) / 2; if (W[mid].hash < lv.hash) lo = mid + 1; else hi = mid; }
+        if (lo < wn && W[lo].hash == lv.hash) {
+          orc_went_t* e = &W[lo];
+          if (e->count == 1) {
+            e->mi.wpos_end = win;
+            mivec_push(raw, e->mi);
+            went_clear(&P, e);
+            memmove(&W[lo], &W[lo + 1], (size_t)(wn - lo - 1) * sizeof(orc_went_t));
+            --wn;
+          } else {
+            if (e->mi.strand - lv.strand == 0 || e->mi.strand == 0) {
+              e->mi.wpos_end = win;
+              mivec_push(raw, e->mi);
+              e->mi.wpos = win;
+              e->mi.wpos_end = -1;
+            }
+            e->mi.strand = (int16_t)(e->mi.strand - lv.strand);
+            went_pop_front(&P, e);
+          }
+        } /* else: the reference dereferences end() here (undefined); unreachable with a consistent state */
+      }
+      qh = (qh + 1) % qcap; --qn;
+    }
+    if (seq[i + k - 1] == 'N') ambig = k;
+    if (hb != hf && ambig == 0) {
+      orc_kmer_t kk; kk.hash = cur; kk.pos = i; kk.strand = cur_strand;
+      Q[(qh + qn) % qcap] = kk; ++qn;
+      int lo = 0, hi = wn;
+      while (lo < hi) { const int mid = (lo + hi) / 2; if (W[mid].hash < cur) lo = mid + 1; else hi = mid; }
+      if (lo < wn && W[lo].hash == cur) {
+        orc_went_t* e = &W[lo];
+        went_push_back(&P, e, kk);
+        if (e->mi.strand + cur_strand == 0 || e->mi.strand == 0) {
+          e->mi.wpos_end = win;
+          mivec_push(raw, e->mi);
+          e->mi.wpos = win;
+          e->mi.wpos_end = -1;
+        }
+        e->mi.strand = (int16_t)(e->mi.strand + cur_strand);
+      } else {
+        heap_push(&H, kk);
+      }
+    }
+    if (ambig > 0) --ambig;
+    if (win >= run_begin) { /* :593-643 (win >= 0 in a run from the sequence start) */
+      while (H.n > 0 && H.a[0].pos < win) heap_pop(&H);
+      if (wn > 0 && H.n > 0 && wn == s && H.a[0].hash < W[wn - 1].hash) {
+        orc_went_t* e = &W[wn - 1];
+        e->mi.wpos_end = win;
+        mivec_push(raw, e->mi);
+        for (int n = e->head; n >= 0; n = P.nodes[n].next)
+          if (P.nodes[n].k.pos > win) heap_push(&H, P.nodes[n].k);
+        went_clear(&P, e);
+        --wn;
+      }
+      while (H.n > 0 && wn < s) {
+        if (H.a[0].pos < win) heap_pop(&H);
+        /* if that emptied the heap the reference reads front() of an empty vector; in practice it sees the
+         * element just popped, which still sits in the vector's storage (heap_pop leaves a[0] in place) */
+        const orc_kmer_t nk = H.a[0];
+        int lo = 0, hi = wn;
+        while (lo < hi) { const int mid = (lo + hi) / 2; if (W[mid].hash < nk.hash) lo = mid + 1; else hi = mid; }
+        if (!(lo < wn && W[lo].hash == nk.hash)) {
+          memmove(&W[lo + 1], &W[lo], (size_t)(wn - lo) * sizeof(orc_went_t));
+          ++wn;
+          W[lo].head = W[lo].tail = -1; W[lo].count = 0;
+        } /* else: operator[] on an existing key assigns .first only and keeps the occurrence list */
+        W[lo].hash = nk.hash;
+        W[lo].mi.hash = nk.hash; W[lo].mi.wpos = win; W[lo].mi.wpos_end = -1; W[lo].mi.seqId = seqId; W[lo].mi.strand = 0; W[lo].mi.pad_ = 0;
+        while (H.n > 0 && H.a[0].hash == nk.hash) {
+          went_push_back(&P, &W[lo], H.a[0]);
+          W[lo].mi.strand = (int16_t)(W[lo].mi.strand + H.a[0].strand);
+          heap_pop(&H);
+        }
+      }
+    }
+  }
+  if (keep_mark < 0) keep_mark = raw->n;
+  if (keep_mark > raw_n0) { /* drop what the warm-up emitted */
+    memmove(raw->v + raw_n0, raw->v + keep_mark, (size_t)(raw->n - keep_mark) * sizeof(orc_minmer_t));
+    raw->n -= keep_mark - raw_n0;
+  }
+  if (open_out) for (int j = 0; j < wn; ++j) mivec_push(open_out, W[j].mi);
+  /* :646-658 */
+  if (final_flush) for (int j = 0; j < wn && j < s; ++j) {
+    if (W[j].mi.wpos != -1) {
+      W[j].mi.wpos_end = len - k + 1;
+      mivec_push(raw, W[j].mi);
+    }
+  }
+  for (int j = 0; j < wn; ++j) went_clear(&P, &W[j]);
+  free(Q); free(W); free(H.a); free(P.nodes); free(rc);
+}
+
+/* Post passes (:660-706): drop degenerate, strand sign, chunk > w, sort by (wpos,wpos_end), unique on
+ * (wpos,hash). std::sort is unstable: records with equal (wpos,wpos_end) may come out in any order in
+ * the reference; this restatement breaks such ties by hash, tests compare per-key multisets. */
+static int64_t add_minmers_post(orc_mivec_t* raw, int w, orc_minmer_t* out, int64_t cap) {
+  orc_mivec_t v = {0, 0, 0};
+  for (int64_t i = 0; i < raw->n; ++i) {
+    orc_minmer_t m = raw->v[i];
+    if (m.wpos < 0 || m.wpos_end < 0 || m.wpos == m.wpos_end) continue;
+    m.strand = m.strand < 0 ? -1 : 1;
+    if (m.wpos_end > m.wpos + w) {
+      const int nch = (int)ceilf((float)(m.wpos_end - m.wpos) / (float)w);
+      for (int c = 0; c < nch; ++c) {
+        orc_minmer_t p = m;
+        p.wpos = m.wpos + (int64_t)c * w;
+        p.wpos_end = (m.wpos + (int64_t)c * w + w < m.wpos_end) ? m.wpos + (int64_t)c * w + w : m.wpos_end;
+        mivec_push(&v, p);
+      }
+    } else {
+      mivec_push(&v, m);
+    }
+  }
+  /* the reference appends the chunked pieces after the unchunked ones before sorting; with a total
+   * order on (wpos,wpos_end,hash) the result is the same */
+  for (int64_t i = 1; i < v.n; ++i) (void)0;
+  qsort(v.v, (size_t)v.n, sizeof(orc_minmer_t), cmp_mi_pos);
+  /* stable tie-break by hash inside equal (wpos,wpos_end) runs */
+  for (int64_t i = 0; i < v.n;) {
+    int64_t j = i;
+    while (j < v.n && v.v[j].wpos == v.v[i].wpos && v.v[j].wpos_end == v.v[i].wpos_end) ++j;
+    if (j - i > 1) qsort(v.v + i, (size_t)(j - i), sizeof(orc_minmer_t), cmp_minmer_hash);
+    i = j;
+  }
+  int64_t n = 0;
+  for (int64_t i = 0; i < v.n; ++i) {
+    if (n > 0 && i > 0 && v.v[i].wpos == v.v[i - 1].wpos && v.v[i].hash == v.v[i - 1].hash) continue; /* std::unique vs previous KEPT == previous element here */
+    if (n < cap) out[n] = v.v[i];
+    ++n;
+  }
+  free(v.v);
+  return n;
+}
+
+int64_t orc_add_minmers(const char* seq, int64_t len, int k, int w, int s, int32_t seqId, orc_minmer_t* out, int64_t cap) {
+  orc_mivec_t raw = {0, 0, 0};
+  add_minmers_stream(seq, len, k, w, s, seqId, &raw);
+  const int64_t n = add_minmers_post(&raw, w, out, cap);
+  free(raw.v);
+  return n;
+}
+
+/* TEST PROBE for the GPU decomposition: raw (pre-post-pass) records of the stream, either from one run
+ * over the whole sequence (chunk <= 0) or from independent chunks of `chunk` positions each preceded by
+ * `warm` warm-up positions. Records carry the state machine's own wpos (not stitched). */
+int64_t orc_add_minmers_raw(const char* seq, int64_t len, int k, int w, int s, int32_t seqId, int64_t chunk, int64_t warm,
+                            orc_minmer_t* out, int64_t cap) {
+  orc_mivec_t raw = {0, 0, 0};
+  const int64_t npos = len - k + 1;
+  if (chunk <= 0) add_minmers_stream_range(seq, len, k, w, s, seqId, &raw, 0, npos, 0, 1, 0);
+  else
+    for (int64_t cb = 0; cb < npos; cb += chunk) {
+      const int64_t ce = cb + chunk < npos ? cb + chunk : npos;
+      const int64_t rb = cb - warm > 0 ? cb - warm : 0;
+      add_minmers_stream_range(seq, len, k, w, s, seqId, &raw, rb, ce, cb, ce == npos, 0);
+    }
+  for (int64_t i = 0; i < raw.n && i < cap; ++i) out[i] = raw.v[i];
+  const int64_t n = raw.n;
+  free(raw.v);
+  return n;
+}

@@ -82,6 +82,10 @@ uint64_t orc_kmer_hash(const char* kmer, int k);
  * seq must already be upper-cased/N-masked (makeUpperCaseAndValidDNA). Returns count written. */
 int orc_sketch_fragment(const char* seq, int len, int k, int s, int32_t seqId, orc_minmer_t* out);
 
+/* addMinmers (commonFunc.hpp:439-708): windowed minmer intervals of one target sequence (seq already
+ * upper-cased / N-masked). Returns the number of records (may exceed cap; only cap are written). */
+int64_t orc_add_minmers(const char* seq, int64_t len, int k, int w, int s, int32_t seqId, orc_minmer_t* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,9 @@
 #include <string>
 #include <cstring>
 #include <cstdint>
+#include <cstdio>
+#include <fcntl.h>
+#include <unistd.h>
 #include "map/include/base_types.hpp"
 #include "map/include/commonFunc.hpp"
 
@@ -33,7 +36,7 @@ int ref_sketch_fragment(char* seq, int64_t len, int k, int s, int32_t seqId, ref
 /* commonFunc.hpp:440 */
 int64_t ref_add_minmers(char* seq, int64_t len, int k, int w, int s, int32_t seqId, ref_minmer_t* out, int64_t cap) {
   std::vector<skch::MinmerInfo> v;
-  progress_meter::ProgressMeter pm(0, "", true);
+  progress_meter::ProgressMeter pm(0, "", true); /* chats on stderr; callers may redirect fd 2 */
   skch::CommonFunc::addMinmers(v, seq, len, k, w, 4, s, seqId, &pm);
   int64_t n = 0;
   for (auto& m : v) {

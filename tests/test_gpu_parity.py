@@ -169,3 +169,59 @@ def test_sketch_full_size_properties(wb, oracle):
         nb = oracle.orc_sketch_fragment(seq[j * w: (j + 1) * w], w, k, s, int(frs["seq_id"][j]), b)
         got = [(int(x["hash"]), int(x["wpos"]), int(x["wpos_end"]), int(x["seqId"]), int(x["strand"])) for x in mm[j, :nb]]
         assert got == [(x.hash, x.wpos, x.wpos_end, x.seqId, x.strand) for x in b[:nb]]
+
+
+def _orc_add_minmers(oracle, seq, k, w, s, sid):
+    import re
+    oracle.orc_add_minmers.restype = ctypes.c_int64
+    cl = re.sub(rb"[^ACGT]", b"N", seq.upper())
+    cap = len(cl) // 2 + 1000
+    out = np.zeros(cap, dtype=np.dtype([("hash", "<u8"), ("wpos", "<i8"), ("wpos_end", "<i8"), ("seqId", "<i4"), ("strand", "<i2"), ("pad_", "<i2")]))
+    n = oracle.orc_add_minmers(cl, ctypes.c_int64(len(cl)), k, w, s, sid, ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(cap))
+    assert n <= cap
+    return out[:n]
+
+
+def test_reference_minmers_match_oracle(wb, oracle):
+    # addMinmers parity incl. order: random, tandem repeats (stale-heap / tally-split stress), N runs,
+    # lower case, sequences shorter than w (skipped), several (k, w, s)
+    import random
+    from wfmash_b200 import synth
+    rng = np.random.default_rng(12)
+    r1 = synth.random_seq(60000, rng).tobytes()
+    unit = synth.random_seq(317, rng).tobytes()
+    rep = synth.mutate(np.frombuffer(unit * 90, dtype=np.uint8), 0.02, rng).tobytes()
+    nrun = b"N" * 3000 + r1[:6000] + b"N" * 50 + r1[7000:12000] + b"NNACGTNN" * 40
+    lowc = bytes(random.Random(1).choice(b"AC") for _ in range(9000))
+    cases = [([r1, rep, b"ACGT" * 100, nrun, r1.lower()[:20000], lowc], 15, 1000, 29),
+             ([rep, r1[:30000]], 15, 1000, 59), ([r1[:40000], rep], 19, 500, 17), ([r1[:5000]], 11, 200, 5)]
+    for seqs, k, w, s in cases:
+        ids = [7 + 3 * i for i in range(len(seqs))]
+        got, st = wb.minmers_build(seqs, ids, k, w, s)
+        exp = [_orc_add_minmers(oracle, sq, k, w, s, sid) for sq, sid in zip(seqs, ids) if len(sq) >= w]
+        exp = np.concatenate(exp)
+        assert st.stitch_miss == 0
+        assert len(got) == len(exp)
+        for f in ("hash", "wpos", "wpos_end", "seqId", "strand"):
+            assert (got[f] == exp[f]).all(), f
+
+
+def test_reference_minmers_full_size_properties(wb, oracle):
+    # C3-sized input (8 x 12 Mbp): global properties + bit-exact spot check of two sequences
+    from wfmash_b200 import synth
+    rng = np.random.default_rng(3)
+    root = synth.random_seq(12_000_000, rng)
+    seqs = [root.tobytes()] + [synth.mutate(root, 0.03, rng).tobytes() for _ in range(7)]
+    k, w, s = 15, 1000, 29
+    got, st = wb.minmers_build(seqs, list(range(8)), k, w, s)
+    assert st.stitch_miss == 0 and st.bases == sum(len(x) for x in seqs)
+    assert (got["wpos"] >= 0).all() and (got["wpos_end"] > got["wpos"]).all() and (got["wpos_end"] - got["wpos"] <= w).all()
+    key = got["seqId"].astype(np.int64) * (1 << 40) + got["wpos"]
+    assert (key[1:] >= key[:-1]).all()
+    dens = len(got) / st.bases
+    assert 0.04 < dens < 0.12  # ~0.0027*s windows per base
+    for sid in (0, 7):
+        sub = got[got["seqId"] == sid]
+        exp = _orc_add_minmers(oracle, seqs[sid][:600_000], k, w, s, sid)
+        m = exp["wpos_end"] < 590_000  # away from the truncation point
+        assert (sub[: m.sum()][["hash", "wpos", "wpos_end", "strand"]] == exp[m][["hash", "wpos", "wpos_end", "strand"]]).all()

@@ -171,6 +171,34 @@ class Aligner:
         return self.align_end2end_batch([(pattern, text)])[0]
 
 
+class MinmerStats(ctypes.Structure):
+    _fields_ = [("stream_kernel_ms", ctypes.c_double), ("total_kernel_ms", ctypes.c_double), ("bases", ctypes.c_uint64),
+                ("raw_records", ctypes.c_uint64), ("chunks", ctypes.c_uint64), ("stale_absorbed", ctypes.c_uint64),
+                ("stitch_miss", ctypes.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def minmers_build(seqs, seq_ids, kmer_size: int, window_size: int, sketch_size: int, device: int = 0):
+    """Batched CommonFunc::addMinmers over target sequences (src/map/include/commonFunc.hpp:439-708), output in
+    Sketch::build's order (winSketch.hpp:424-429). seqs: list of bytes. Returns (minmers, MinmerStats)."""
+    L = lib()
+    n = len(seqs)
+    ptrs = (ctypes.c_char_p * max(n, 1))(*seqs)
+    lens = (ctypes.c_int64 * max(n, 1))(*[len(s) for s in seqs])
+    ids = (ctypes.c_int32 * max(n, 1))(*seq_ids)
+    cap = int(sum(len(s) for s in seqs) * (0.01 * sketch_size + 0.05)) + 4096
+    out = np.zeros(cap, dtype=MINMER_DTYPE)
+    cnt = ctypes.c_int64(0)
+    st = MinmerStats()
+    rc = L.wfb_minmers_build(device, ptrs, lens, ids, n, kmer_size, window_size, sketch_size,
+                             ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(cap), ctypes.byref(cnt), ctypes.byref(st))
+    if rc != 0:
+        raise _err(rc)
+    return out[: cnt.value], st
+
+
 def sketch_fragments(seq: bytes, frags, kmer_size: int, sketch_size: int, device: int = 0):
     """Batched CommonFunc::sketchSequence (src/map/include/commonFunc.hpp:217-323).
     frags: array-like of (seq_offset, len, seq_id). Returns (minmers[n, sketch_size], counts[n], kernel_ms)."""

@@ -1,0 +1,336 @@
+// minmer_host.cu — host side of the reference-side minmer pipeline behind the C ABI:
+//   wfb_minmers_build : addMinmers for a batch of target sequences (commonFunc.hpp:439-708 via
+//                       Sketch::buildHelper, winSketch.hpp:467-499), output in Sketch::build's order.
+// Kernels: minmer_kernels.h (hand-written). Sorting / scanning between them uses CUB (library code,
+// plumbing between the kernels, not the hot loop).
+#include "minmer_kernels.h"
+#include "../../include/wfmash_b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#ifndef WFB_EMU
+#include <cub/cub.cuh>
+#endif
+
+void wfb_set_last_error_(const std::string& s); /* wfa_host.cu */
+void wfb_count_launch_();
+
+#ifndef WFB_EMU
+#define MM_CHECK(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      wfb_set_last_error_(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+      rc = (e_ == cudaErrorMemoryAllocation) ? WFB_ENOMEM : WFB_ECUDA;                   \
+      goto done;                                                                         \
+    }                                                                                    \
+  } while (0)
+#define MM_LAUNCH(kernel, grid, block, ...)                                              \
+  do {                                                                                   \
+    kernel<<<(grid), (block)>>>(__VA_ARGS__);                                            \
+    wfb_count_launch_();                                                                 \
+  } while (0)
+#endif
+
+/* upper-case / N-mask the concatenated targets in place (makeUpperCaseAndValidDNA) */
+WFB_KERNEL(mm_clean_kernel, uint8_t* buf, long long n) {
+  WFB_KERNEL_PROLOGUE
+  for (long long i = (long long)bid * WFB_NT + WFB_TID; i < n; i += (long long)nblocks * WFB_NT) buf[i] = mm_clean_base(buf[i]);
+}
+
+struct MmFinal { /* post-pass record */
+  uint64_t hash;
+  long long wpos, wpos_end;
+  int seq, strand;
+};
+
+/* post pass 1 (:660-693): number of output pieces of every raw record (0 = dropped) */
+WFB_KERNEL(mm_pieces_kernel, const MmRecord* recs, long long n, int w, int* pieces) {
+  WFB_KERNEL_PROLOGUE
+  for (long long r = (long long)bid * WFB_NT + WFB_TID; r < n; r += (long long)nblocks * WFB_NT) {
+    const MmRecord m = recs[r];
+    int p = 1;
+    if (m.wpos < 0 || m.wpos_end < 0 || m.wpos == m.wpos_end) p = 0;
+    else if (m.wpos_end > m.wpos + w) p = (int)ceilf((float)(m.wpos_end - m.wpos) / (float)w);
+    pieces[r] = p;
+  }
+}
+/* post pass 2: write the pieces (strand sign :672, chunking :673-685) */
+WFB_KERNEL(mm_expand_kernel, const MmRecord* recs, long long n, int w, const int* pieces, const long long* offs, MmFinal* out) {
+  WFB_KERNEL_PROLOGUE
+  for (long long r = (long long)bid * WFB_NT + WFB_TID; r < n; r += (long long)nblocks * WFB_NT) {
+    const int p = pieces[r];
+    if (p == 0) continue;
+    const MmRecord m = recs[r];
+    MmFinal f;
+    f.hash = m.hash; f.seq = m.seq; f.strand = m.strand < 0 ? -1 : 1;
+    if (p == 1 && !(m.wpos_end > m.wpos + w)) {
+      f.wpos = m.wpos; f.wpos_end = m.wpos_end;
+      out[offs[r]] = f;
+    } else {
+      for (int c = 0; c < p; ++c) {
+        f.wpos = m.wpos + (long long)c * w;
+        const long long e = m.wpos + (long long)c * w + w;
+        f.wpos_end = e < m.wpos_end ? e : m.wpos_end;
+        out[offs[r] + c] = f;
+      }
+    }
+  }
+}
+/* sort-key extraction for the three stable LSD passes: hash, wpos_end, (seq, wpos) */
+WFB_KERNEL(mm_keys_kernel, const MmFinal* f, const int* perm, long long n, int which, unsigned long long* keys) {
+  WFB_KERNEL_PROLOGUE
+  for (long long i = (long long)bid * WFB_NT + WFB_TID; i < n; i += (long long)nblocks * WFB_NT) {
+    const MmFinal& m = f[perm ? perm[i] : i];
+    keys[i] = which == 0 ? m.hash : which == 1 ? (unsigned long long)m.wpos_end
+                                               : (((unsigned long long)(unsigned)m.seq << 40) | (unsigned long long)m.wpos);
+  }
+}
+WFB_KERNEL(mm_iota_kernel, int* p, long long n) {
+  WFB_KERNEL_PROLOGUE
+  for (long long i = (long long)bid * WFB_NT + WFB_TID; i < n; i += (long long)nblocks * WFB_NT) p[i] = (int)i;
+}
+/* :698-706 std::unique on (wpos, hash): keep[i] = first of its run in sorted order (per sequence) */
+WFB_KERNEL(mm_unique_flag_kernel, const MmFinal* f, const int* perm, long long n, int* keep) {
+  WFB_KERNEL_PROLOGUE
+  for (long long i = (long long)bid * WFB_NT + WFB_TID; i < n; i += (long long)nblocks * WFB_NT) {
+    int kp = 1;
+    if (i > 0) {
+      const MmFinal& a = f[perm[i - 1]];
+      const MmFinal& b = f[perm[i]];
+      if (a.seq == b.seq && a.wpos == b.wpos && a.hash == b.hash) kp = 0;
+    }
+    keep[i] = kp;
+  }
+}
+WFB_KERNEL(mm_gather_out_kernel, const MmFinal* f, const int* perm, const int* keep, const long long* offs, long long n,
+           const MmSeq* seqs, wfb_minmer_t* out) {
+  WFB_KERNEL_PROLOGUE
+  for (long long i = (long long)bid * WFB_NT + WFB_TID; i < n; i += (long long)nblocks * WFB_NT) {
+    if (!keep[i]) continue;
+    const MmFinal& m = f[perm[i]];
+    wfb_minmer_t o;
+    o.hash = m.hash; o.wpos = m.wpos; o.wpos_end = m.wpos_end; o.seqId = seqs[m.seq].seq_id; o.strand = (int16_t)m.strand; o.pad_ = 0;
+    out[offs[i]] = o;
+  }
+}
+
+extern "C" int wfb_minmers_build(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
+                                 int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
+                                 int64_t* out_count, wfb_minmer_stats_t* stats) {
+  if (nseq < 0 || kmer_size <= 0 || kmer_size > 32 || window_size <= kmer_size || sketch_size <= 0 || !out_count ||
+      (nseq > 0 && (!seq_ptrs || !seq_lens || !seq_ids))) {
+    wfb_set_last_error_("bad argument");
+    return WFB_EINVAL;
+  }
+  *out_count = 0;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  int rc = WFB_OK;
+  const int k = kmer_size, w = window_size, s = sketch_size;
+  /* sequences shorter than w are skipped by Sketch::build (winSketch.hpp:218-232) */
+  std::vector<MmSeq> seqs;
+  std::vector<int> src_index;
+  long long total = 16;
+  for (int i = 0; i < nseq; ++i) {
+    if (seq_lens[i] < w) continue;
+    MmSeq q;
+    q.off = total; q.len = seq_lens[i]; q.seq_id = seq_ids[i]; q.first_chunk = 0; q.n_chunks = 0;
+    total += (seq_lens[i] + 63) / 64 * 64 + 64;
+    seqs.push_back(q);
+    src_index.push_back(i);
+  }
+  const int ns = (int)seqs.size();
+  if (ns == 0) return WFB_OK;
+  MmParams P;
+  P.k = k; P.w = w; P.s = s;
+  P.chunk = 4096; P.warm = 2 * w;
+  { const char* e = getenv("WFB_MM_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
+  { const char* e = getenv("WFB_MM_WARM"); if (e && atoi(e) >= w) P.warm = atoi(e); }
+  P.qcap = w + 2; P.heap_cap = 3 * w + 64; P.pool_cap = 4 * w + 64;
+  std::vector<MmChunk> chunks;
+  for (int q = 0; q < ns; ++q) {
+    const long long npos = seqs[q].len - k + 1;
+    seqs[q].first_chunk = (int)chunks.size();
+    for (long long cb = 0; cb < npos; cb += P.chunk) {
+      MmChunk c;
+      c.seq = q; c.body_begin = cb; c.body_end = std::min<long long>(cb + P.chunk, npos);
+      c.run_begin = std::max<long long>(0, cb - P.warm);
+      c.first_of_seq = cb == 0; c.last_of_seq = c.body_end == npos;
+      chunks.push_back(c);
+    }
+    seqs[q].n_chunks = (int)chunks.size() - seqs[q].first_chunk;
+  }
+  const int nchunks = (int)chunks.size();
+  const long long scratch_stride = ((long long)sizeof(MmKmer) * (P.qcap + P.heap_cap) + (long long)sizeof(MmNode) * P.pool_cap +
+                                    (long long)sizeof(MmWent) * (s + 2) + 255) / 256 * 256;
+  /* expected density ~0.0027*s windows per base; generous cap, overflow is detected */
+  long long rec_cap = (long long)((double)total * (0.01 * s + 0.05)) + 65536;
+#ifndef WFB_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    wfb_set_last_error_("no CUDA device (this library has no CPU path)");
+    return WFB_ENODEV;
+  }
+  uint8_t* d_seq = nullptr; MmSeq* d_seqs = nullptr; MmChunk* d_chunks = nullptr; unsigned char* d_scratch = nullptr;
+  MmRecord* d_rec = nullptr; MmEndEnt* d_end = nullptr; int* d_endcount = nullptr; MmCounters* d_cnt = nullptr;
+  int* d_pieces = nullptr; long long* d_offs = nullptr; MmFinal* d_fin = nullptr; unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+  int *d_perm = nullptr, *d_perm2 = nullptr, *d_keep = nullptr; wfb_minmer_t* d_out = nullptr; void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  uint8_t* h_seq = nullptr;
+  MmCounters hc;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  long long nrec = 0, nfin = 0, nout = 0;
+  const int TPB = 64;
+  std::vector<long long> tmpll(2);
+  MM_CHECK(cudaSetDevice(device));
+  MM_CHECK(cudaMallocHost(&h_seq, (size_t)total));
+  memset(h_seq, 'N', (size_t)total);
+  for (int q = 0; q < ns; ++q) memcpy(h_seq + seqs[q].off, seq_ptrs[src_index[q]], (size_t)seqs[q].len);
+  MM_CHECK(cudaMalloc(&d_seq, (size_t)total));
+  MM_CHECK(cudaMalloc(&d_seqs, sizeof(MmSeq) * ns));
+  MM_CHECK(cudaMalloc(&d_chunks, sizeof(MmChunk) * (size_t)nchunks));
+  MM_CHECK(cudaMalloc(&d_scratch, (size_t)scratch_stride * (size_t)nchunks));
+  MM_CHECK(cudaMalloc(&d_rec, sizeof(MmRecord) * (size_t)rec_cap));
+  MM_CHECK(cudaMalloc(&d_end, sizeof(MmEndEnt) * (size_t)nchunks * s));
+  MM_CHECK(cudaMalloc(&d_endcount, sizeof(int) * (size_t)nchunks));
+  MM_CHECK(cudaMalloc(&d_cnt, sizeof(MmCounters)));
+  MM_CHECK(cudaMemset(d_cnt, 0, sizeof(MmCounters)));
+  MM_CHECK(cudaEventCreate(&e0)); MM_CHECK(cudaEventCreate(&e1)); MM_CHECK(cudaEventCreate(&e2));
+  MM_CHECK(cudaMemcpy(d_seq, h_seq, (size_t)total, cudaMemcpyHostToDevice));
+  MM_CHECK(cudaMemcpy(d_seqs, seqs.data(), sizeof(MmSeq) * ns, cudaMemcpyHostToDevice));
+  MM_CHECK(cudaMemcpy(d_chunks, chunks.data(), sizeof(MmChunk) * (size_t)nchunks, cudaMemcpyHostToDevice));
+  MM_CHECK(cudaEventRecord(e0));
+  MM_LAUNCH(mm_clean_kernel, 148 * 8, 256, d_seq, total);
+  MM_LAUNCH(mm_stream_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, P, d_scratch, scratch_stride, d_rec,
+            rec_cap, d_end, d_endcount, d_cnt);
+  MM_CHECK(cudaEventRecord(e1));
+  MM_LAUNCH(mm_stitch_ends_kernel, (ns + 63) / 64, 64, d_seqs, ns, s, d_end, d_endcount, d_cnt);
+  MM_CHECK(cudaMemcpy(&hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (hc.overflow || (long long)hc.n_records > rec_cap) {
+    wfb_set_last_error_("minmer stream: capacity overflow (records / heap / pool)");
+    rc = WFB_ECAP;
+    goto done;
+  }
+  nrec = (long long)hc.n_records;
+  MM_LAUNCH(mm_stitch_records_kernel, 148 * 8, 256, d_rec, nrec, d_chunks, s, d_end, d_endcount, d_cnt);
+  /* post passes */
+  MM_CHECK(cudaMalloc(&d_pieces, sizeof(int) * (size_t)(nrec + 1)));
+  MM_CHECK(cudaMalloc(&d_offs, sizeof(long long) * (size_t)(nrec + 1)));
+  MM_LAUNCH(mm_pieces_kernel, 148 * 8, 256, d_rec, nrec, w, d_pieces);
+  MM_CHECK(cudaMemset(d_pieces + nrec, 0, sizeof(int)));
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_pieces, d_offs, nrec + 1);
+  MM_CHECK(cudaMalloc(&d_tmp, tmp_bytes + (size_t)nrec * 32 + (1 << 20)));
+  tmp_bytes += (size_t)nrec * 32 + (1 << 20);
+  {
+    size_t tb = tmp_bytes;
+    MM_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_pieces, d_offs, nrec + 1));
+  }
+  MM_CHECK(cudaMemcpy(&nfin, d_offs + nrec, sizeof(long long), cudaMemcpyDeviceToHost));
+  if (nfin > 0) {
+    MM_CHECK(cudaMalloc(&d_fin, sizeof(MmFinal) * (size_t)nfin));
+    MM_CHECK(cudaMalloc(&d_keys, 8 * (size_t)nfin)); MM_CHECK(cudaMalloc(&d_keys2, 8 * (size_t)nfin));
+    MM_CHECK(cudaMalloc(&d_perm, 4 * (size_t)nfin)); MM_CHECK(cudaMalloc(&d_perm2, 4 * (size_t)nfin));
+    MM_CHECK(cudaMalloc(&d_keep, 4 * (size_t)(nfin + 1)));
+    MM_LAUNCH(mm_expand_kernel, 148 * 8, 256, d_rec, nrec, w, d_pieces, d_offs, d_fin);
+    MM_LAUNCH(mm_iota_kernel, 148 * 8, 256, d_perm, nfin);
+    for (int pass = 0; pass < 3; ++pass) { /* stable LSD: hash, wpos_end, (seq,wpos) => order (seq,wpos,wpos_end,hash) */
+      MM_LAUNCH(mm_keys_kernel, 148 * 8, 256, d_fin, d_perm, nfin, pass, d_keys);
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys, d_keys2, d_perm, d_perm2, (int)nfin);
+      if (tb > tmp_bytes) { cudaFree(d_tmp); d_tmp = nullptr; MM_CHECK(cudaMalloc(&d_tmp, tb)); tmp_bytes = tb; }
+      tb = tmp_bytes;
+      MM_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys, d_keys2, d_perm, d_perm2, (int)nfin));
+      std::swap(d_perm, d_perm2);
+    }
+    MM_LAUNCH(mm_unique_flag_kernel, 148 * 8, 256, d_fin, d_perm, nfin, d_keep);
+    MM_CHECK(cudaMemset(d_keep + nfin, 0, 4));
+    cudaFree(d_offs); d_offs = nullptr;
+    MM_CHECK(cudaMalloc(&d_offs, sizeof(long long) * (size_t)(nfin + 1)));
+    {
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, d_keep, d_offs, nfin + 1);
+      if (tb > tmp_bytes) { cudaFree(d_tmp); d_tmp = nullptr; MM_CHECK(cudaMalloc(&d_tmp, tb)); tmp_bytes = tb; }
+      tb = tmp_bytes;
+      MM_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_keep, d_offs, nfin + 1));
+    }
+    MM_CHECK(cudaMemcpy(&nout, d_offs + nfin, sizeof(long long), cudaMemcpyDeviceToHost));
+    MM_CHECK(cudaMalloc(&d_out, sizeof(wfb_minmer_t) * (size_t)std::max<long long>(nout, 1)));
+    MM_LAUNCH(mm_gather_out_kernel, 148 * 8, 256, d_fin, d_perm, d_keep, d_offs, nfin, d_seqs, d_out);
+  }
+  MM_CHECK(cudaEventRecord(e2));
+  MM_CHECK(cudaEventSynchronize(e2));
+  MM_CHECK(cudaMemcpy(&hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost));
+  *out_count = nout;
+  if (stats) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1);
+    cudaEventElapsedTime(&b, e0, e2);
+    stats->stream_kernel_ms = a; stats->total_kernel_ms = b;
+    stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed;
+    stats->stitch_miss = hc.stitch_miss; stats->bases = 0;
+    for (int q = 0; q < ns; ++q) stats->bases += (uint64_t)seqs[q].len;
+  }
+  if (nout > out_cap) { wfb_set_last_error_("minmer output buffer too small"); rc = WFB_ECAP; goto done; }
+  if (nout > 0) MM_CHECK(cudaMemcpy(out, d_out, sizeof(wfb_minmer_t) * (size_t)nout, cudaMemcpyDeviceToHost));
+done:
+  if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2);
+  cudaFree(d_seq); cudaFree(d_seqs); cudaFree(d_chunks); cudaFree(d_scratch); cudaFree(d_rec); cudaFree(d_end); cudaFree(d_endcount);
+  cudaFree(d_cnt); cudaFree(d_pieces); cudaFree(d_offs); cudaFree(d_fin); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_perm);
+  cudaFree(d_perm2); cudaFree(d_keep); cudaFree(d_out); cudaFree(d_tmp);
+  if (h_seq) cudaFreeHost(h_seq);
+  return rc;
+#else
+  /* host emulation of the same kernels (tests/emu only): one thread per "CTA", serial sorts */
+  std::vector<uint8_t> buf((size_t)total, 'N');
+  for (int q = 0; q < ns; ++q) memcpy(buf.data() + seqs[q].off, seq_ptrs[src_index[q]], (size_t)seqs[q].len);
+  mm_clean_kernel(0, 1, buf.data(), total);
+  std::vector<unsigned char> scratch((size_t)scratch_stride);
+  std::vector<MmRecord> rec((size_t)rec_cap);
+  std::vector<MmEndEnt> endst((size_t)nchunks * s);
+  std::vector<int> endcount((size_t)nchunks);
+  MmCounters hc;
+  memset(&hc, 0, sizeof(hc));
+  for (int c = 0; c < nchunks; ++c) /* scratch reused: chunk c uses slot 0 */
+    mm_stream_kernel(c, nchunks, buf.data(), seqs.data(), chunks.data(), nchunks, P, scratch.data() - (long long)c * scratch_stride,
+                     scratch_stride, rec.data(), rec_cap, endst.data(), endcount.data(), &hc);
+  for (int q = 0; q < ns; ++q) mm_stitch_ends_kernel(q, ns, seqs.data(), ns, s, endst.data(), endcount.data(), &hc);
+  if (hc.overflow || (long long)hc.n_records > rec_cap) { wfb_set_last_error_("minmer stream: capacity overflow"); return WFB_ECAP; }
+  const long long nrec = (long long)hc.n_records;
+  mm_stitch_records_kernel(0, 1, rec.data(), nrec, chunks.data(), s, endst.data(), endcount.data(), &hc);
+  std::vector<int> pieces((size_t)nrec + 1, 0);
+  mm_pieces_kernel(0, 1, rec.data(), nrec, w, pieces.data());
+  std::vector<long long> offs((size_t)nrec + 1);
+  long long acc = 0;
+  for (long long i = 0; i <= nrec; ++i) { offs[i] = acc; if (i < nrec) acc += pieces[i]; }
+  const long long nfin = acc;
+  std::vector<MmFinal> fin((size_t)std::max<long long>(nfin, 1));
+  mm_expand_kernel(0, 1, rec.data(), nrec, w, pieces.data(), offs.data(), fin.data());
+  std::vector<int> perm((size_t)nfin);
+  for (long long i = 0; i < nfin; ++i) perm[i] = (int)i;
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+    const MmFinal &x = fin[a], &y = fin[b];
+    if (x.seq != y.seq) return x.seq < y.seq;
+    if (x.wpos != y.wpos) return x.wpos < y.wpos;
+    if (x.wpos_end != y.wpos_end) return x.wpos_end < y.wpos_end;
+    return x.hash < y.hash;
+  });
+  std::vector<int> keep((size_t)nfin + 1, 0);
+  if (nfin) mm_unique_flag_kernel(0, 1, fin.data(), perm.data(), nfin, keep.data());
+  std::vector<long long> offs2((size_t)nfin + 1);
+  acc = 0;
+  for (long long i = 0; i <= nfin; ++i) { offs2[i] = acc; if (i < nfin) acc += keep[i]; }
+  *out_count = acc;
+  if (stats) { stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed; stats->stitch_miss = hc.stitch_miss; }
+  if (acc > out_cap) { wfb_set_last_error_("minmer output buffer too small"); return WFB_ECAP; }
+  if (nfin) mm_gather_out_kernel(0, 1, fin.data(), perm.data(), keep.data(), offs2.data(), nfin, seqs.data(), out);
+  (void)device;
+  return rc;
+#endif
+}

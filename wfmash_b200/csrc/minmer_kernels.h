@@ -1,0 +1,404 @@
+// minmer_kernels.h — MashMap 3.5 reference-side windowed minmers on the GPU (sm_100a).
+//
+// Replaces skch::CommonFunc::addMinmers (src/map/include/commonFunc.hpp:439-708) as run per target
+// sequence by Sketch::buildHelper (src/map/include/winSketch.hpp:467-499).
+//
+// The reference is one sequential stream per sequence whose state (the window deque Q, the ordered
+// sketch `sortedWindow` with per-hash occurrence lists and strand tallies, and a lazily cleaned heap of
+// the window's other k-mers) depends on the last w positions. B200 mapping:
+//   * a sequence is cut into chunks of WFB_MM_CHUNK k-mer positions; ONE THREAD runs the reference's
+//     state machine over its chunk preceded by `warm` (>= w) warm-up positions, so tens of thousands of
+//     chunks advance concurrently (the stream itself has no intra-step parallelism worth a warp);
+//   * records closed inside the chunk body are appended to a global array through one atomic counter;
+//     a record whose interval was opened before the body carries an "inherited" start that the stitch
+//     pass replaces with the true start taken from the previous chunk's end state (same hash);
+//   * the post passes (:660-706: degenerate drop, strand sign, > w splitting, sort, unique) run as
+//     separate data-parallel kernels / library sorts (minmer_host.cu).
+// Exactness: the chunk state after >= w warm-up positions equals the reference's state restricted to
+// live entries; entries the reference keeps past their expiry ("stale" heap entries, :596-641) can make
+// the two differ. Every such absorption is counted (stale_absorbed) so callers can tell; the parity
+// tests compare whole sequences against the reference (LPA, yeast, synthetic repeats: identical).
+#pragma once
+#include "wfb_rt.h"
+
+struct MmKmer { /* KmerInfo, base_types.hpp:135-141 (pos relative to the sequence start) */
+  uint64_t hash;
+  int pos;
+  int strand;
+};
+struct MmNode { /* one entry of a sortedWindow occurrence list */
+  int pos;
+  int strand;
+  int next;
+};
+struct MmWent { /* sortedWindow value: (MinmerInfo, deque<KmerInfo>) keyed by hash */
+  uint64_t hash;
+  long long wpos; /* window id (i + k - w) when the interval was (re)opened; -1 = not open */
+  int strand;     /* running tally */
+  int head, tail, count;
+};
+struct MmRecord { /* raw MinmerInfo emitted by the stream (pre post-pass) */
+  uint64_t hash;
+  long long wpos, wpos_end;
+  int seq;    /* index of the sequence in the batch */
+  int strand; /* tally before the update, as the reference stores it */
+  int chunk;  /* global chunk id that emitted it */
+  int inherited; /* 1 = wpos comes from before the chunk body -> stitch */
+};
+struct MmChunk {
+  int seq;           /* sequence index */
+  long long body_begin, body_end; /* k-mer start positions [begin, end) */
+  long long run_begin;            /* body_begin - warm, clamped at 0 */
+  int first_of_seq, last_of_seq;
+};
+struct MmEndEnt { /* sortedWindow membership at the end of a chunk body */
+  uint64_t hash;
+  long long wpos;
+  int inherited, pad_;
+};
+struct MmSeq {
+  long long off; /* first base inside the cleaned sequence buffer */
+  long long len;
+  int seq_id;    /* MinmerInfo::seqId */
+  int first_chunk, n_chunks;
+};
+struct MmCounters {
+  unsigned long long n_records, stale_absorbed, overflow, stitch_miss;
+};
+
+WFB_DEV uint64_t mm_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+WFB_DEV uint64_t mm_fmix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return k;
+}
+/* MurmurHash3_x64_128 low 64 bits, seed 42, len <= 32 (murmur3.h:226-303; commonFunc.hpp:173-182) */
+WFB_DEV uint64_t mm_murmur3_lo64(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, int len) {
+  const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+  uint64_t h1 = 42, h2 = 42;
+  uint64_t t1 = w0, t2 = w1;
+  if (len >= 16) {
+    uint64_t k1 = w0, k2 = w1;
+    k1 *= c1; k1 = mm_rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    h1 = mm_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+    k2 *= c2; k2 = mm_rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    h2 = mm_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    t1 = w2; t2 = w3;
+  }
+  if (len == 32) { /* second full block, empty tail */
+    uint64_t k1 = w2, k2 = w3;
+    k1 *= c1; k1 = mm_rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    h1 = mm_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+    k2 *= c2; k2 = mm_rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    h2 = mm_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+  } else {
+    const int rem = len & 15;
+    if (rem > 8) { uint64_t k2 = t2; k2 *= c2; k2 = mm_rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    if (rem > 0) { uint64_t k1 = t1; k1 *= c1; k1 = mm_rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+  }
+  h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+  h1 += h2; h2 += h1;
+  h1 = mm_fmix64(h1); h2 = mm_fmix64(h2);
+  h1 += h2;
+  return h1;
+}
+WFB_DEV uint8_t mm_clean_base(uint8_t c) { /* makeUpperCaseAndValidDNA, commonFunc.hpp:110-142 */
+  if (c > 96 && c < 123) c -= 32;
+  return (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? c : (uint8_t)'N';
+}
+WFB_DEV uint8_t mm_comp(uint8_t c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+
+/* forward / reverse-complement hashes of the k-mer starting at s (ASCII, already cleaned) */
+WFB_DEV void mm_hash_pair(const uint8_t* s, int k, uint64_t& hf, uint64_t& hb) {
+  uint64_t f[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
+  for (int j = 0; j < k; ++j) {
+    const uint8_t b = s[j];
+    f[j >> 3] |= (uint64_t)b << ((j & 7) * 8);
+    const int jr = k - 1 - j;
+    r[jr >> 3] |= (uint64_t)mm_comp(b) << ((jr & 7) * 8);
+  }
+  hf = mm_murmur3_lo64(f[0], f[1], f[2], f[3], k);
+  hb = mm_murmur3_lo64(r[0], r[1], r[2], r[3], k);
+}
+
+/* ---- per-thread containers in global scratch ---- */
+struct MmHeap {
+  MmKmer* a;
+  int n, cap;
+};
+WFB_DEV bool mm_less(const MmKmer& x, const MmKmer& y) { return x.hash < y.hash || (x.hash == y.hash && x.pos < y.pos); }
+WFB_DEV bool mm_heap_push(MmHeap& h, const MmKmer& v) {
+  if (h.n >= h.cap) return false;
+  int i = h.n++;
+  while (i > 0) {
+    const int p = (i - 1) >> 1;
+    if (!mm_less(v, h.a[p])) break;
+    h.a[i] = h.a[p];
+    i = p;
+  }
+  h.a[i] = v;
+  return true;
+}
+WFB_DEV void mm_heap_sift_down(MmHeap& h, int i) {
+  const MmKmer v = h.a[i];
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= h.n) break;
+    if (c + 1 < h.n && mm_less(h.a[c + 1], h.a[c])) ++c;
+    if (!mm_less(h.a[c], v)) break;
+    h.a[i] = h.a[c];
+    i = c;
+  }
+  h.a[i] = v;
+}
+WFB_DEV void mm_heap_pop(MmHeap& h) { /* leaves the popped element readable in a[0] when the heap empties */
+  --h.n;
+  if (h.n > 0) {
+    h.a[0] = h.a[h.n];
+    mm_heap_sift_down(h, 0);
+  }
+}
+
+struct MmPool {
+  MmNode* nodes;
+  int free_head;
+};
+WFB_DEV int mm_pool_alloc(MmPool& p) {
+  const int i = p.free_head;
+  if (i >= 0) p.free_head = p.nodes[i].next;
+  return i;
+}
+WFB_DEV void mm_pool_free(MmPool& p, int i) { p.nodes[i].next = p.free_head; p.free_head = i; }
+WFB_DEV bool mm_went_push_back(MmPool& p, MmWent& e, int pos, int strand) {
+  const int n = mm_pool_alloc(p);
+  if (n < 0) return false;
+  p.nodes[n].pos = pos; p.nodes[n].strand = strand; p.nodes[n].next = -1;
+  if (e.tail >= 0) p.nodes[e.tail].next = n; else e.head = n;
+  e.tail = n;
+  e.count++;
+  return true;
+}
+WFB_DEV void mm_went_pop_front(MmPool& p, MmWent& e) {
+  const int n = e.head;
+  e.head = p.nodes[n].next;
+  if (e.head < 0) e.tail = -1;
+  e.count--;
+  mm_pool_free(p, n);
+}
+WFB_DEV void mm_went_clear(MmPool& p, MmWent& e) { while (e.head >= 0) mm_went_pop_front(p, e); }
+
+WFB_DEV int mm_lower_bound(const MmWent* W, int wn, uint64_t h) {
+  int lo = 0, hi = wn;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (W[mid].hash < h) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+struct MmParams {
+  int k, w, s;
+  int chunk, warm;
+  int qcap, heap_cap, pool_cap; /* per-thread capacities */
+};
+
+/* One thread = one chunk. scratch layout per thread: Q[qcap] | heap[heap_cap] | pool[pool_cap] | W[s+2]. */
+WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P,
+           unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
+           int* endcount, MmCounters* counters) {
+  WFB_KERNEL_PROLOGUE
+  const int c = bid * WFB_NT + WFB_TID;
+  if (c >= nchunks) return;
+  const MmChunk ch = chunks[c];
+  const MmSeq sq = seqs[ch.seq];
+  const uint8_t* seq = seqbuf + sq.off;
+  const long long len = sq.len;
+  const int k = P.k, w = P.w, s = P.s;
+  unsigned char* sp = scratch_all + (long long)c * scratch_stride;
+  MmKmer* Q = (MmKmer*)sp;
+  MmHeap H;
+  H.a = (MmKmer*)(sp + sizeof(MmKmer) * (size_t)P.qcap);
+  H.n = 0;
+  H.cap = P.heap_cap;
+  MmPool pool;
+  pool.nodes = (MmNode*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap));
+  MmWent* W = (MmWent*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) + sizeof(MmNode) * (size_t)P.pool_cap);
+  for (int i = 0; i < P.pool_cap; ++i) pool.nodes[i].next = (i + 1 < P.pool_cap) ? i + 1 : -1;
+  pool.free_head = 0;
+  int qh = 0, qn = 0, wn = 0;
+  unsigned long long stale = 0, overflow = 0;
+  const long long run_begin = ch.run_begin, run_end = ch.body_end, keep_from = ch.body_begin;
+  const long long body_win0 = keep_from + k - w; /* window id of the first body step */
+  int ambig = 0;
+  if (run_begin > 0) { /* the counter a run from position 0 holds here (only N at index >= k-1 arm it, :553-556) */
+    for (long long j = run_begin + k - 2; j >= run_begin && j >= k - 1; --j)
+      if (seq[j] == 'N') { ambig = (int)(j - run_begin + 1); break; }
+  }
+#define MM_EMIT(E, WEND)                                                                             \
+  {                                                                                                  \
+    if (i >= keep_from) {                                                                            \
+      const unsigned long long idx_ = (unsigned long long)atomicAdd_compat(&counters->n_records, 1ULL); \
+      if ((long long)idx_ < out_cap) {                                                               \
+        MmRecord r_;                                                                                 \
+        r_.hash = (E).hash; r_.wpos = (E).wpos; r_.wpos_end = (WEND); r_.seq = ch.seq; r_.strand = (E).strand; \
+        r_.chunk = c; r_.inherited = ((E).wpos < body_win0 && run_begin > 0) ? 1 : 0;                \
+        out[idx_] = r_;                                                                              \
+      } else overflow++;                                                                             \
+    }                                                                                                \
+  }
+  long long i = run_begin;
+  for (; i < run_end; ++i) {
+    const long long win = i + k - w; /* currentWindowId, :482 */
+    if (H.n > 2 * w) { /* :485-495 */
+      int m = 0;
+      for (int j = 0; j < H.n; ++j) if (!((long long)H.a[j].pos < win)) H.a[m++] = H.a[j];
+      H.n = m;
+      for (int j = H.n / 2 - 1; j >= 0; --j) mm_heap_sift_down(H, j);
+    }
+    uint64_t hf, hb;
+    mm_hash_pair(seq + i, k, hf, hb);
+    const uint64_t cur = hf < hb ? hf : hb;
+    const int cur_strand = hf < hb ? 1 : -1;
+    /* leaving k-mer, :517-551 */
+    if (qn > 0 && (long long)Q[qh].pos < win) {
+      const MmKmer lv = Q[qh];
+      if (wn > 0 && lv.hash <= W[wn - 1].hash) {
+        const int lo = mm_lower_bound(W, wn, lv.hash);
+        if (lo < wn && W[lo].hash == lv.hash) {
+          MmWent& e = W[lo];
+          if (e.count == 1) {
+            MM_EMIT(e, win)
+            mm_went_clear(pool, e);
+            for (int j = lo; j + 1 < wn; ++j) W[j] = W[j + 1];
+            --wn;
+          } else {
+            if (e.strand - lv.strand == 0 || e.strand == 0) {
+              MM_EMIT(e, win)
+              e.wpos = win;
+            }
+            e.strand -= lv.strand;
+            mm_went_pop_front(pool, e);
+          }
+        }
+      }
+      qh = (qh + 1) % P.qcap;
+      --qn;
+    }
+    if (seq[i + k - 1] == 'N') ambig = k;
+    if (hb != hf && ambig == 0) {
+      MmKmer kk;
+      kk.hash = cur; kk.pos = (int)i; kk.strand = cur_strand;
+      if (qn < P.qcap) { Q[(qh + qn) % P.qcap] = kk; ++qn; } else overflow++;
+      const int lo = mm_lower_bound(W, wn, cur);
+      if (lo < wn && W[lo].hash == cur) {
+        MmWent& e = W[lo];
+        if (!mm_went_push_back(pool, e, (int)i, cur_strand)) overflow++;
+        if (e.strand + cur_strand == 0 || e.strand == 0) {
+          MM_EMIT(e, win)
+          e.wpos = win;
+        }
+        e.strand += cur_strand;
+      } else {
+        if (!mm_heap_push(H, kk)) overflow++;
+      }
+    }
+    if (ambig > 0) --ambig;
+    if (win >= run_begin) { /* :593-643 (win >= 0 for a run from the sequence start) */
+      while (H.n > 0 && (long long)H.a[0].pos < win) mm_heap_pop(H);
+      if (wn > 0 && H.n > 0 && wn == s && H.a[0].hash < W[wn - 1].hash) {
+        MmWent& e = W[wn - 1];
+        MM_EMIT(e, win)
+        for (int n = e.head; n >= 0; n = pool.nodes[n].next)
+          if ((long long)pool.nodes[n].pos > win) {
+            MmKmer kk;
+            kk.hash = e.hash; kk.pos = pool.nodes[n].pos; kk.strand = pool.nodes[n].strand;
+            if (!mm_heap_push(H, kk)) overflow++;
+          }
+        mm_went_clear(pool, e);
+        --wn;
+      }
+      while (H.n > 0 && wn < s) {
+        if ((long long)H.a[0].pos < win) mm_heap_pop(H); /* may empty the heap; a[0] stays readable, see :627-633 */
+        const MmKmer nk = H.a[0];
+        const int lo = mm_lower_bound(W, wn, nk.hash);
+        if (!(lo < wn && W[lo].hash == nk.hash)) {
+          for (int j = wn; j > lo; --j) W[j] = W[j - 1];
+          ++wn;
+          W[lo].head = W[lo].tail = -1;
+          W[lo].count = 0;
+        }
+        W[lo].hash = nk.hash;
+        W[lo].wpos = win;
+        W[lo].strand = 0;
+        while (H.n > 0 && H.a[0].hash == nk.hash) {
+          if ((long long)H.a[0].pos < win) stale++; /* the reference absorbs expired entries too (:635-641) */
+          if (!mm_went_push_back(pool, W[lo], H.a[0].pos, H.a[0].strand)) overflow++;
+          W[lo].strand += H.a[0].strand;
+          mm_heap_pop(H);
+        }
+      }
+    }
+  }
+  /* membership at the end of the body, for the stitch of the next chunk */
+  {
+    MmEndEnt* es = endstate + (long long)c * s;
+    for (int j = 0; j < wn && j < s; ++j) {
+      es[j].hash = W[j].hash;
+      es[j].wpos = W[j].wpos;
+      es[j].inherited = (W[j].wpos < body_win0 && run_begin > 0) ? 1 : 0;
+      es[j].pad_ = 0;
+    }
+    endcount[c] = wn < s ? wn : s;
+  }
+  /* :646-658: still-open members are closed at len - k + 1 */
+  if (ch.last_of_seq) {
+    i = run_end; /* emissions of the flush count as body emissions */
+    for (int j = 0; j < wn && j < s; ++j)
+      if (W[j].wpos != -1) MM_EMIT(W[j], len - k + 1)
+  }
+#undef MM_EMIT
+  if (stale) atomicAdd_compat(&counters->stale_absorbed, stale);
+  if (overflow) atomicAdd_compat(&counters->overflow, overflow);
+}
+
+/* Stitch 1: resolve the true interval starts of the chunk end states, one thread per sequence walking its
+ * chunks in order (each end state has <= s entries sorted by hash). */
+WFB_KERNEL(mm_stitch_ends_kernel, const MmSeq* seqs, int nseqs, int s, MmEndEnt* endstate, const int* endcount,
+           MmCounters* counters) {
+  WFB_KERNEL_PROLOGUE
+  const int q = bid * WFB_NT + WFB_TID;
+  if (q >= nseqs) return;
+  const MmSeq sq = seqs[q];
+  unsigned long long miss = 0;
+  for (int ci = 1; ci < sq.n_chunks; ++ci) {
+    const int c = sq.first_chunk + ci;
+    MmEndEnt* cur = endstate + (long long)c * s;
+    const MmEndEnt* prev = endstate + (long long)(c - 1) * s;
+    const int np = endcount[c - 1], nc = endcount[c];
+    for (int j = 0; j < nc; ++j) {
+      if (!cur[j].inherited) continue;
+      int lo = 0, hi = np;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (prev[mid].hash < cur[j].hash) lo = mid + 1; else hi = mid; }
+      if (lo < np && prev[lo].hash == cur[j].hash) { cur[j].wpos = prev[lo].wpos; cur[j].inherited = 0; }
+      else miss++;
+    }
+  }
+  if (miss) atomicAdd_compat(&counters->stitch_miss, miss);
+}
+
+/* Stitch 2: records that inherited their start take it from the previous chunk's (resolved) end state. */
+WFB_KERNEL(mm_stitch_records_kernel, MmRecord* recs, long long nrec, const MmChunk* chunks, int s, const MmEndEnt* endstate,
+           const int* endcount, MmCounters* counters) {
+  WFB_KERNEL_PROLOGUE
+  for (long long r = (long long)bid * WFB_NT + WFB_TID; r < nrec; r += (long long)nblocks * WFB_NT) {
+    if (!recs[r].inherited) continue;
+    const int c = recs[r].chunk;
+    if (chunks[c].first_of_seq) continue;
+    const MmEndEnt* prev = endstate + (long long)(c - 1) * s;
+    const int np = endcount[c - 1];
+    const uint64_t h = recs[r].hash;
+    int lo = 0, hi = np;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (prev[mid].hash < h) lo = mid + 1; else hi = mid; }
+    if (lo < np && prev[lo].hash == h) { recs[r].wpos = prev[lo].wpos; recs[r].inherited = 0; }
+    else atomicAdd_compat(&counters->stitch_miss, 1ULL);
+  }
+}

@@ -30,6 +30,7 @@ WFB_DEV void wfb_smem_min(int* p, int v) { atomicMin(p, v); }
 WFB_DEV void wfb_smem_max(int* p, int v) { atomicMax(p, v); }
 WFB_DEV int wfb_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 WFB_DEV void wfb_atomic_add64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+WFB_DEV unsigned long long atomicAdd_compat(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 WFB_DEV uint32_t wfb_ldg32(const uint32_t* p) { return __ldg(p); }
 WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { return __ldg(p); }
 #else
@@ -52,6 +53,7 @@ WFB_DEV void wfb_smem_min(int* p, int v) { if (v < *p) *p = v; }
 WFB_DEV void wfb_smem_max(int* p, int v) { if (v > *p) *p = v; }
 WFB_DEV int wfb_atomic_add(int* p, int v) { const int o = *p; *p = o + v; return o; }
 WFB_DEV void wfb_atomic_add64(unsigned long long* p, unsigned long long v) { *p += v; }
+WFB_DEV unsigned long long atomicAdd_compat(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 WFB_DEV uint32_t wfb_ldg32(const uint32_t* p) { return *p; }
 WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }

@@ -401,3 +401,205 @@ int64_t orc_add_minmers_raw(const char* seq, int64_t len, int k, int w, int s, i
   free(raw.v);
   return n;
 }
+
+/* =================================================================================================
+ * Index build (Sketch::build, winSketch.hpp:266-429) over the concatenated per-sequence minmers.
+ * ================================================================================================= */
+static int cmp_u64(const void* a, const void* b) {
+  const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return x < y ? -1 : (x > y);
+}
+typedef struct { uint64_t hash; int64_t idx; } orc_hidx_t;
+static int cmp_hidx(const void* a, const void* b) {
+  const orc_hidx_t* x = (const orc_hidx_t*)a; const orc_hidx_t* y = (const orc_hidx_t*)b;
+  if (x->hash != y->hash) return x->hash < y->hash ? -1 : 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+/* count_threshold of winSketch.hpp:298-349 given all hash frequencies (any order). */
+uint64_t orc_count_threshold(const uint64_t* freqs, int64_t nuniq, uint64_t total_windows, double max_kmer_freq) {
+  const uint64_t min_occ = 10;
+  uint64_t thr;
+  if (max_kmer_freq <= 1.0) { const uint64_t t = (uint64_t)(total_windows * max_kmer_freq); thr = t > min_occ ? t : min_occ; }
+  else { const uint64_t t = (uint64_t)max_kmer_freq; thr = t > min_occ ? t : min_occ; }
+  uint64_t wpos = 0, wuniq = 0;
+  for (int64_t i = 0; i < nuniq; ++i) if (freqs[i] > thr && freqs[i] > min_occ) { wuniq++; wpos += freqs[i]; }
+  if (wpos > total_windows / 2 || wuniq > nuniq * 0.7) {
+    uint64_t* all = (uint64_t*)malloc((size_t)nuniq * sizeof(uint64_t));
+    memcpy(all, freqs, (size_t)nuniq * sizeof(uint64_t));
+    qsort(all, (size_t)nuniq, sizeof(uint64_t), cmp_u64);
+    size_t keep = (size_t)(nuniq * 0.999);
+    if ((int64_t)keep >= nuniq) keep = (size_t)nuniq - 1;
+    if (all[keep] > thr) thr = all[keep];
+    free(all);
+  }
+  return thr;
+}
+
+/* Builds the kept minmerIndex and the interval points grouped by hash (ascending hash; inside a hash the
+ * reference's push order). partition_of_seq[seqId] = index of the worker thread whose contiguous range of
+ * sequences holds seqId (winSketch.hpp:271-277,358-362): abutting intervals merge only inside a partition.
+ * Outputs (caller-allocated, sizes n / 2n): kept[], points[], and per unique kept hash uhash/ustart/ucount.
+ * Returns the number of kept minmers; *npoints, *nuniq, *threshold are set. */
+int64_t orc_index_build(const orc_minmer_t* mi, int64_t n, const int32_t* partition_of_seq, double max_kmer_freq,
+                        orc_minmer_t* kept, orc_ipoint_t* points, int64_t* npoints, uint64_t* uhash, int64_t* ustart,
+                        int64_t* ucount, int64_t* nuniq_out, uint64_t* threshold) {
+  orc_hidx_t* hs = (orc_hidx_t*)malloc((size_t)(n ? n : 1) * sizeof(orc_hidx_t));
+  for (int64_t i = 0; i < n; ++i) { hs[i].hash = mi[i].hash; hs[i].idx = i; }
+  qsort(hs, (size_t)n, sizeof(orc_hidx_t), cmp_hidx);
+  /* frequencies */
+  uint64_t* freqs = (uint64_t*)malloc((size_t)(n ? n : 1) * sizeof(uint64_t));
+  int64_t nu = 0;
+  for (int64_t i = 0; i < n;) { int64_t j = i; while (j < n && hs[j].hash == hs[i].hash) ++j; freqs[nu++] = (uint64_t)(j - i); i = j; }
+  const uint64_t thr = orc_count_threshold(freqs, nu, (uint64_t)n, max_kmer_freq);
+  *threshold = thr;
+  /* kept flags in index order */
+  char* keepf = (char*)calloc((size_t)(n ? n : 1), 1);
+  { int64_t u = 0; for (int64_t i = 0; i < n;) { int64_t j = i; while (j < n && hs[j].hash == hs[i].hash) ++j;
+      const int kp = !(freqs[u] > thr && freqs[u] > 10); for (int64_t t = i; t < j; ++t) keepf[hs[t].idx] = (char)kp; ++u; i = j; } }
+  int64_t nk = 0;
+  for (int64_t i = 0; i < n; ++i) if (keepf[i]) kept[nk++] = mi[i];
+  /* postings, :379-387 */
+  int64_t np = 0, nuq = 0;
+  for (int64_t i = 0; i < n;) {
+    int64_t j = i;
+    while (j < n && hs[j].hash == hs[i].hash) ++j;
+    if (keepf[hs[i].idx]) {
+      uhash[nuq] = hs[i].hash; ustart[nuq] = np;
+      int cur_part = -1; int64_t list_begin = np;
+      for (int64_t t = i; t < j; ++t) {
+        const orc_minmer_t* m = &mi[hs[t].idx];
+        const int part = partition_of_seq ? partition_of_seq[m->seqId] : 0;
+        if (part != cur_part) { cur_part = part; list_begin = np; } /* a new thread-local list starts */
+        if (np == list_begin || points[np - 1].pos != m->wpos) {
+          points[np].pos = m->wpos; points[np].hash = m->hash; points[np].seqId = m->seqId; points[np].side = 1; ++np;
+          points[np].pos = m->wpos_end; points[np].hash = m->hash; points[np].seqId = m->seqId; points[np].side = -1; ++np;
+        } else {
+          points[np - 1].pos = m->wpos_end;
+        }
+      }
+      ucount[nuq] = np - ustart[nuq];
+      ++nuq;
+    }
+    i = j;
+  }
+  *npoints = np; *nuniq_out = nuq;
+  free(hs); free(freqs); free(keepf);
+  return nk;
+}
+
+/* =================================================================================================
+ * L1: getSeedIntervalPoints (mappingCore.hpp:81-131) + computeL1CandidateRegions (:136-301) as driven by
+ * Map::doL1Mapping (computeMap.hpp:945-983), for fragments of length == windowLength (windowLen = 0),
+ * stage1_topANI_filter = stage2_full_scan = true (parse_args.hpp:701-702).
+ * ================================================================================================= */
+static int cmp_ipoint(const void* a, const void* b) {
+  const orc_ipoint_t* x = (const orc_ipoint_t*)a; const orc_ipoint_t* y = (const orc_ipoint_t*)b;
+  if (x->seqId != y->seqId) return x->seqId < y->seqId ? -1 : 1;
+  if (x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+  return x->side < y->side ? -1 : (x->side > y->side);
+}
+
+static void l1_regions(const orc_ipoint_t* ip, int64_t n, int minimumHits, int q_sketch, int param_sketch, const int* cutoffs,
+                       int ncut, int window_len_param, orc_l1_locus_t* out, int* nout, int cap) {
+  if (n == 0) return;
+  int overlap = 0, best = 0;
+  int64_t tr = 0, ld = 0;
+  while (ld < n) { /* pass 1, :160-187 */
+    while (tr < n && ((ip[tr].seqId == ip[ld].seqId && ip[tr].pos <= ip[ld].pos) || ip[tr].seqId < ip[ld].seqId)) {
+      if (ip[tr].side == -1) overlap--;
+      tr++;
+    }
+    const int64_t cur = ip[ld].pos;
+    while (ld < n && ip[ld].pos == cur) { if (ip[ld].side == 1) overlap++; ld++; }
+    if (overlap > best) best = overlap;
+  }
+  if (best < minimumHits) return;
+  {
+    const double div = param_sketch / 1000.0 > 1.0 ? param_sketch / 1000.0 : 1.0; /* skch::fixed::ss_table_max */
+    int idx = (int)((best < q_sketch ? best : q_sketch) / div);
+    if (idx >= ncut) idx = ncut - 1;
+    if (cutoffs[idx] > minimumHits) minimumHits = cutoffs[idx];
+  }
+  /* pass 2, :203-284 */
+  int in_cand = 0;
+  orc_l1_locus_t cur_out; memset(&cur_out, 0, sizeof(cur_out));
+  orc_l1_locus_t* local = (orc_l1_locus_t*)malloc((size_t)(n + 1) * sizeof(orc_l1_locus_t));
+  int nlocal = 0;
+  tr = 0; ld = 0; overlap = 0;
+  int prevOverlap = 0;
+  int32_t prev_seq = 0; int64_t prev_pos = 0; /* SeqCoord prevPos (uninitialised in the reference until first change) */
+  int32_t cur_seq = ip[0].seqId; int64_t cur_pos = ip[0].pos;
+  while (ld < n) {
+    prevOverlap = overlap;
+    while (tr < n && ((ip[tr].seqId == ip[ld].seqId && ip[tr].pos <= ip[ld].pos) || ip[tr].seqId < ip[ld].seqId)) {
+      if (ip[tr].side == -1) overlap--;
+      tr++;
+    }
+    if (ip[ld].pos != cur_pos) { prev_seq = cur_seq; prev_pos = cur_pos; cur_seq = ip[ld].seqId; cur_pos = ip[ld].pos; }
+    while (ld < n && ip[ld].pos == cur_pos) { if (ip[ld].side == 1) overlap++; ld++; }
+    if (prevOverlap >= minimumHits) {
+      if (cur_out.seqId != prev_seq && in_cand) { local[nlocal++] = cur_out; memset(&cur_out, 0, sizeof(cur_out)); in_cand = 0; }
+      if (!in_cand) {
+        cur_out.rangeStartPos = prev_pos; cur_out.rangeEndPos = prev_pos; cur_out.seqId = prev_seq; cur_out.intersectionSize = prevOverlap;
+        in_cand = 1;
+      } else { /* stage2_full_scan */
+        if (prevOverlap > cur_out.intersectionSize) cur_out.intersectionSize = prevOverlap;
+        cur_out.rangeEndPos = prev_pos;
+      }
+    } else {
+      if (in_cand) { local[nlocal++] = cur_out; memset(&cur_out, 0, sizeof(cur_out)); }
+      in_cand = 0;
+    }
+  }
+  if (in_cand) local[nlocal++] = cur_out;
+  for (int i = 0; i < nlocal; ++i) { /* :287-300 */
+    if (*nout == 0 || local[i].seqId != out[*nout - 1].seqId || local[i].rangeStartPos > out[*nout - 1].rangeEndPos + window_len_param) {
+      if (*nout < cap) out[*nout] = local[i];
+      (*nout)++;
+    } else {
+      out[*nout - 1].rangeEndPos = local[i].rangeEndPos;
+      if (local[i].intersectionSize > out[*nout - 1].intersectionSize) out[*nout - 1].intersectionSize = local[i].intersectionSize;
+    }
+  }
+  free(local);
+}
+
+int orc_l1_fragment(const uint64_t* uhash, const int64_t* ustart, const int64_t* ucount, int64_t nuniq, const orc_ipoint_t* points,
+                    const uint64_t* q_hashes, int q_n, int32_t q_seq_id, int q_group, const int32_t* ref_group, int skip_self,
+                    int skip_prefix, int lower_triangular, int minimum_hits, int param_sketch_size, int window_len,
+                    const int* cutoffs, int ncut, orc_l1_locus_t* out, int cap) {
+  int64_t total = 0;
+  for (int i = 0; i < q_n; ++i) {
+    int64_t lo = 0, hi = nuniq;
+    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (uhash[mid] < q_hashes[i]) lo = mid + 1; else hi = mid; }
+    if (lo < nuniq && uhash[lo] == q_hashes[i]) total += ucount[lo];
+  }
+  orc_ipoint_t* ip = (orc_ipoint_t*)malloc((size_t)(total + 1) * sizeof(orc_ipoint_t));
+  int64_t n = 0;
+  for (int i = 0; i < q_n; ++i) {
+    int64_t lo = 0, hi = nuniq;
+    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (uhash[mid] < q_hashes[i]) lo = mid + 1; else hi = mid; }
+    if (!(lo < nuniq && uhash[lo] == q_hashes[i])) continue;
+    for (int64_t t = 0; t < ucount[lo]; ++t) {
+      const orc_ipoint_t p = points[ustart[lo] + t];
+      const int tg = ref_group[p.seqId];
+      int skip = 0;
+      if (skip_self && q_group == tg) skip = 1;
+      if (skip_prefix && q_group == tg) skip = 1;
+      if (lower_triangular && q_seq_id <= p.seqId) skip = 1;
+      if (!skip) ip[n++] = p;
+    }
+  }
+  qsort(ip, (size_t)n, sizeof(orc_ipoint_t), cmp_ipoint); /* = the heap merge order up to ties of equal keys */
+  int nout = 0;
+  int64_t b = 0;
+  while (b < n) { /* per PanSN group slice, computeMap.hpp:964-982 */
+    int64_t e = n;
+    if (skip_prefix) { e = b; const int g = ref_group[ip[b].seqId]; while (e < n && ref_group[ip[e].seqId] == g) ++e; }
+    l1_regions(ip + b, e - b, minimum_hits, q_n, param_sketch_size, cutoffs, ncut, window_len, out, &nout, cap);
+    b = e;
+  }
+  free(ip);
+  return nout;
+}

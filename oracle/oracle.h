@@ -86,6 +86,34 @@ int orc_sketch_fragment(const char* seq, int len, int k, int s, int32_t seqId, o
  * upper-cased / N-masked). Returns the number of records (may exceed cap; only cap are written). */
 int64_t orc_add_minmers(const char* seq, int64_t len, int k, int w, int s, int32_t seqId, orc_minmer_t* out, int64_t cap);
 
+/* IntervalPoint, base_types.hpp:63-76 (24 bytes). side: OPEN = 1, CLOSE = -1. */
+typedef struct {
+  int64_t pos;
+  uint64_t hash;
+  int32_t seqId;
+  int8_t side;
+  int8_t pad_[3];
+} orc_ipoint_t;
+
+/* L1_candidateLocus_t, mappingCore.hpp:24-30 */
+typedef struct {
+  int32_t seqId;
+  int32_t pad_;
+  int64_t rangeStartPos;
+  int64_t rangeEndPos;
+  int32_t intersectionSize;
+  int32_t pad2_;
+} orc_l1_locus_t;
+
+uint64_t orc_count_threshold(const uint64_t* freqs, int64_t nuniq, uint64_t total_windows, double max_kmer_freq);
+int64_t orc_index_build(const orc_minmer_t* mi, int64_t n, const int32_t* partition_of_seq, double max_kmer_freq,
+                        orc_minmer_t* kept, orc_ipoint_t* points, int64_t* npoints, uint64_t* uhash, int64_t* ustart,
+                        int64_t* ucount, int64_t* nuniq_out, uint64_t* threshold);
+int orc_l1_fragment(const uint64_t* uhash, const int64_t* ustart, const int64_t* ucount, int64_t nuniq, const orc_ipoint_t* points,
+                    const uint64_t* q_hashes, int q_n, int32_t q_seq_id, int q_group, const int32_t* ref_group, int skip_self,
+                    int skip_prefix, int lower_triangular, int minimum_hits, int param_sketch_size, int window_len,
+                    const int* cutoffs, int ncut, orc_l1_locus_t* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

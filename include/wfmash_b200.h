@@ -171,6 +171,81 @@ int wfb_minmers_build(int device, const char* const* seq_ptrs, const int64_t* se
                       int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
                       int64_t* out_count, wfb_minmer_stats_t* stats);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 1 — GPU-resident reference index and the batched L1 stage.
+ * wfb_index_build replaces skch::Sketch::Sketch(...)/Sketch::build (src/map/include/winSketch.hpp:141-154,
+ * 175-457): minmerIndex (kept minmers, reference order) and minmerPosLookupIndex (hash -> interval points)
+ * live in HBM; wfb_index_export returns them for the host L2 stage and for parity dumps.
+ * wfb_l1_batch replaces MappingCore::getSeedHits / getSeedIntervalPoints / computeL1CandidateRegions as
+ * driven by Map::doL1Mapping (src/map/include/mappingCore.hpp:61-301; src/map/include/computeMap.hpp:945-983)
+ * for a batch of query fragments of length == window_size.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t kmer_size;      /* param.kmerSize     */
+  int32_t window_size;    /* param.windowLength */
+  int32_t sketch_size;    /* param.sketchSize   */
+  int32_t index_threads;  /* the reference's -t: abutting intervals of one hash merge only inside one worker's
+                             contiguous range of sequences (winSketch.hpp:271-277,379-387) */
+  double max_kmer_freq;   /* param.max_kmer_freq (-F, default 0.0002) */
+} wfb_index_params_t;
+
+typedef struct {
+  wfb_minmer_stats_t minmer;
+  double index_kernel_ms;
+  uint64_t total_windows, kept_minmers, interval_points, unique_hashes, count_threshold, table_buckets;
+} wfb_index_stats_t;
+
+typedef struct wfb_index wfb_index_t;
+
+wfb_index_t* wfb_index_build(int device, const wfb_index_params_t* params, const char* const* seq_ptrs, const int64_t* seq_lens,
+                             const int32_t* seq_ids, int32_t nseq, wfb_index_stats_t* stats);
+void wfb_index_free(wfb_index_t*);
+int wfb_index_sizes(const wfb_index_t*, int64_t* n_minmers, int64_t* n_unique_hashes, int64_t* n_points, uint64_t* count_threshold);
+/* Interval points come back packed as sort keys: seqId << 41 | pos << 1 | (side == OPEN), grouped by hash:
+ * points[ustart[u] .. ustart[u]+ucount[u]) belong to uhash[u] (ascending), in the reference's push order. */
+int wfb_index_export(const wfb_index_t*, wfb_minmer_t* minmers, int64_t minmers_cap, uint64_t* uhash, uint32_t* ustart,
+                     uint32_t* ucount, int64_t uniq_cap, uint64_t* points, int64_t points_cap);
+
+typedef struct { /* QueryMetaData (src/map/include/base_types.hpp:336-349) of the sequence a fragment comes from */
+  int32_t q_seq_id;
+  int32_t q_group; /* idManager.getRefGroup(Q.seqId) */
+} wfb_frag_query_t;
+
+typedef struct {
+  int32_t minimum_hits;           /* Map::cached_minimum_hits (computeMap.hpp:160): computed by the host from
+                                     Stat::estimateMinimumHitsRelaxed, max'ed with -H */
+  const int32_t* sketch_cutoffs;  /* Map::sketchCutoffs from setProbs() (computeMap.hpp:234-293) */
+  int32_t n_cutoffs;
+  const int32_t* ref_group;       /* idManager.getRefGroup(seqId) for every target seqId */
+  int32_t n_ref_group;
+  int32_t skip_self, skip_prefix, lower_triangular; /* map_parameters.hpp:59-61 */
+  float kmer_complexity_threshold; /* param.kmerComplexityThreshold (0 on the CLI path) */
+} wfb_l1_params_t;
+
+typedef struct { /* L1_candidateLocus_t (src/map/include/mappingCore.hpp:24-30) */
+  int32_t seqId;
+  int32_t intersectionSize; /* the L1 hit count */
+  int64_t rangeStartPos, rangeEndPos;
+} wfb_l1_locus_t;
+
+typedef struct {
+  /* caller-allocated outputs */
+  wfb_minmer_t* q_minmers;   /* [n * sketch_size] Q.minmerTableQuery per fragment (may be NULL) */
+  int32_t* q_count;          /* [n] Q.sketchSize (may be NULL) */
+  float* q_complexity;       /* [n] Q.kmerComplexity (may be NULL) */
+  wfb_l1_locus_t* loci;      /* [loci_cap] */
+  int64_t loci_cap;
+  int64_t* frag_loci_offset; /* [n] */
+  int32_t* frag_loci_count;  /* [n] */
+  int32_t* frag_status;      /* [n] 0 or WFB_ECAP (fragment exceeded an internal capacity) */
+  /* set by the call */
+  int64_t n_loci;
+  double kernel_ms;
+} wfb_l1_out_t;
+
+int wfb_l1_batch(const wfb_index_t*, const wfb_l1_params_t*, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
+                 const wfb_frag_query_t* frag_queries, int32_t n, wfb_l1_out_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,6 +199,109 @@ def minmers_build(seqs, seq_ids, kmer_size: int, window_size: int, sketch_size: 
     return out[: cnt.value], st
 
 
+class _IndexParams(ctypes.Structure):
+    _fields_ = [("kmer_size", ctypes.c_int32), ("window_size", ctypes.c_int32), ("sketch_size", ctypes.c_int32),
+                ("index_threads", ctypes.c_int32), ("max_kmer_freq", ctypes.c_double)]
+
+
+class IndexStats(ctypes.Structure):
+    _fields_ = [("minmer", MinmerStats), ("index_kernel_ms", ctypes.c_double), ("total_windows", ctypes.c_uint64),
+                ("kept_minmers", ctypes.c_uint64), ("interval_points", ctypes.c_uint64), ("unique_hashes", ctypes.c_uint64),
+                ("count_threshold", ctypes.c_uint64), ("table_buckets", ctypes.c_uint64)]
+
+
+class _L1Params(ctypes.Structure):
+    _fields_ = [("minimum_hits", ctypes.c_int32), ("sketch_cutoffs", ctypes.c_void_p), ("n_cutoffs", ctypes.c_int32),
+                ("ref_group", ctypes.c_void_p), ("n_ref_group", ctypes.c_int32), ("skip_self", ctypes.c_int32),
+                ("skip_prefix", ctypes.c_int32), ("lower_triangular", ctypes.c_int32), ("kmer_complexity_threshold", ctypes.c_float)]
+
+
+class _L1Out(ctypes.Structure):
+    _fields_ = [("q_minmers", ctypes.c_void_p), ("q_count", ctypes.c_void_p), ("q_complexity", ctypes.c_void_p),
+                ("loci", ctypes.c_void_p), ("loci_cap", ctypes.c_int64), ("frag_loci_offset", ctypes.c_void_p),
+                ("frag_loci_count", ctypes.c_void_p), ("frag_status", ctypes.c_void_p), ("n_loci", ctypes.c_int64),
+                ("kernel_ms", ctypes.c_double)]
+
+
+L1_LOCUS_DTYPE = np.dtype([("seqId", "<i4"), ("intersectionSize", "<i4"), ("rangeStartPos", "<i8"), ("rangeEndPos", "<i8")])
+FRAG_QUERY_DTYPE = np.dtype([("q_seq_id", "<i4"), ("q_group", "<i4")])
+
+
+class Index:
+    """GPU-resident drop-in for skch::Sketch (src/map/include/winSketch.hpp:63-154,175-457): build() =
+    Sketch::build, export() = the public members minmerIndex / minmerPosLookupIndex, l1() =
+    Map::doL1Mapping (src/map/include/computeMap.hpp:945-983) for a batch of fragments."""
+
+    def __init__(self, seqs, seq_ids, kmer_size, window_size, sketch_size, max_kmer_freq=0.0002, index_threads=1, device=0):
+        L = lib()
+        L.wfb_index_build.restype = ctypes.c_void_p
+        L.wfb_index_free.argtypes = [ctypes.c_void_p]
+        self._L = L
+        n = len(seqs)
+        prm = _IndexParams(kmer_size, window_size, sketch_size, index_threads, max_kmer_freq)
+        ptrs = (ctypes.c_char_p * n)(*seqs)
+        lens = (ctypes.c_int64 * n)(*[len(s) for s in seqs])
+        ids = (ctypes.c_int32 * n)(*seq_ids)
+        self.stats = IndexStats()
+        self.k, self.w, self.s = kmer_size, window_size, sketch_size
+        self._h = L.wfb_index_build(device, ctypes.byref(prm), ptrs, lens, ids, n, ctypes.byref(self.stats))
+        if not self._h:
+            raise WfbError(L.wfb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.wfb_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def export(self):
+        """(kept minmers, uhash, ustart, ucount, packed points)."""
+        st = self.stats
+        mi = np.zeros(max(int(st.kept_minmers), 1), dtype=MINMER_DTYPE)
+        uh = np.zeros(max(int(st.unique_hashes), 1), dtype=np.uint64)
+        us = np.zeros_like(uh, dtype=np.uint32)
+        uc = np.zeros_like(uh, dtype=np.uint32)
+        pts = np.zeros(max(int(st.interval_points), 1), dtype=np.uint64)
+        rc = self._L.wfb_index_export(ctypes.c_void_p(self._h), ctypes.c_void_p(mi.ctypes.data), ctypes.c_int64(len(mi)),
+                                      ctypes.c_void_p(uh.ctypes.data), ctypes.c_void_p(us.ctypes.data), ctypes.c_void_p(uc.ctypes.data),
+                                      ctypes.c_int64(len(uh)), ctypes.c_void_p(pts.ctypes.data), ctypes.c_int64(len(pts)))
+        if rc != 0:
+            raise _err(rc)
+        return (mi[: int(st.kept_minmers)], uh[: int(st.unique_hashes)], us[: int(st.unique_hashes)], uc[: int(st.unique_hashes)],
+                pts[: int(st.interval_points)])
+
+    def l1(self, seq: bytes, frags, frag_queries, minimum_hits, sketch_cutoffs, ref_group, skip_self=True, skip_prefix=True,
+           lower_triangular=False, loci_cap=None):
+        fr = np.ascontiguousarray(frags, dtype=FRAG_DTYPE)
+        fq = np.ascontiguousarray(frag_queries, dtype=FRAG_QUERY_DTYPE)
+        n = int(fr.shape[0])
+        cut = np.ascontiguousarray(sketch_cutoffs, dtype=np.int32)
+        grp = np.ascontiguousarray(ref_group, dtype=np.int32)
+        lp = _L1Params(minimum_hits, cut.ctypes.data, len(cut), grp.ctypes.data, len(grp), int(skip_self), int(skip_prefix),
+                       int(lower_triangular), 0.0)
+        loci_cap = loci_cap or (64 * n + 1024)
+        qm = np.zeros((max(n, 1), self.s), dtype=MINMER_DTYPE)
+        qn = np.zeros(max(n, 1), dtype=np.int32)
+        kc = np.zeros(max(n, 1), dtype=np.float32)
+        loci = np.zeros(loci_cap, dtype=L1_LOCUS_DTYPE)
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        cnt = np.zeros(max(n, 1), dtype=np.int32)
+        stt = np.zeros(max(n, 1), dtype=np.int32)
+        out = _L1Out(qm.ctypes.data, qn.ctypes.data, kc.ctypes.data, loci.ctypes.data, loci_cap, off.ctypes.data, cnt.ctypes.data,
+                     stt.ctypes.data, 0, 0.0)
+        rc = self._L.wfb_l1_batch(ctypes.c_void_p(self._h), ctypes.byref(lp), seq, ctypes.c_int64(len(seq)),
+                                  ctypes.c_void_p(fr.ctypes.data), ctypes.c_void_p(fq.ctypes.data), n, ctypes.byref(out))
+        if rc != 0:
+            raise _err(rc)
+        return {"q_minmers": qm[:n], "q_count": qn[:n], "q_complexity": kc[:n], "loci": loci[: out.n_loci], "offset": off[:n],
+                "count": cnt[:n], "status": stt[:n], "kernel_ms": out.kernel_ms}
+
+
 def sketch_fragments(seq: bytes, frags, kmer_size: int, sketch_size: int, device: int = 0):
     """Batched CommonFunc::sketchSequence (src/map/include/commonFunc.hpp:217-323).
     frags: array-like of (seq_offset, len, seq_id). Returns (minmers[n, sketch_size], counts[n], kernel_ms)."""

@@ -1,0 +1,379 @@
+// index_host.cu — host side of the GPU-resident reference index and the batched L1 stage (C ABI:
+// wfb_index_build / wfb_index_export / wfb_index_free / wfb_l1_batch). Kernels: index_kernels.h,
+// minmer_kernels.h, sketch_kernels.h (hand-written); CUB is used for the sorts / scans between them.
+#include "index_kernels.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#ifndef WFB_EMU
+#include <cub/cub.cuh>
+#endif
+
+void wfb_set_last_error_(const std::string& s);
+void wfb_count_launch_();
+
+struct wfb_index {
+  int device = 0;
+  wfb_index_params_t params{};
+  long long n_minmers_all = 0, n_minmers = 0, n_points = 0, n_uniq = 0, n_buckets = 0;
+  unsigned long long threshold = 0;
+  wfb_minmer_t* d_minmers = nullptr; /* kept minmerIndex, reference order */
+  uint64_t* d_points = nullptr;      /* packed interval points, grouped by hash */
+  IxSlot* d_table = nullptr;
+  unsigned long long* d_uhash = nullptr;
+  uint32_t *d_ustart = nullptr, *d_ucount = nullptr;
+};
+
+#ifndef WFB_EMU
+#define IX_CHECK(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      wfb_set_last_error_(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+      rc = (e_ == cudaErrorMemoryAllocation) ? WFB_ENOMEM : WFB_ECUDA;                   \
+      goto done;                                                                         \
+    }                                                                                    \
+  } while (0)
+#define IX_LAUNCH(kernel, grid, block, smem, ...)                                        \
+  do {                                                                                   \
+    kernel<<<(grid), (block), (smem)>>>(__VA_ARGS__);                                    \
+    wfb_count_launch_();                                                                 \
+  } while (0)
+
+namespace {
+struct Tmp { /* grow-only CUB temp storage */
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t b) {
+    if (b <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, b + 256);
+    if (e == cudaSuccess) cap = b + 256;
+    return e;
+  }
+  ~Tmp() { if (p) cudaFree(p); }
+};
+cudaError_t incl_scan(Tmp& t, const int* in, long long* out, long long n) {
+  size_t b = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, b, in, out, (int)n);
+  cudaError_t e = t.ensure(b);
+  if (e != cudaSuccess) return e;
+  b = t.cap;
+  return cub::DeviceScan::InclusiveSum(t.p, b, in, out, (int)n);
+}
+cudaError_t excl_scan(Tmp& t, const int* in, long long* out, long long n) {
+  size_t b = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b, in, out, (int)n);
+  cudaError_t e = t.ensure(b);
+  if (e != cudaSuccess) return e;
+  b = t.cap;
+  return cub::DeviceScan::ExclusiveSum(t.p, b, in, out, (int)n);
+}
+}  // namespace
+#endif
+
+/* count_threshold of winSketch.hpp:298-349 */
+static unsigned long long count_threshold(const std::vector<unsigned long long>& freqs, unsigned long long total_windows, double F) {
+  const unsigned long long min_occ = 10;
+  unsigned long long thr = (F <= 1.0) ? std::max<unsigned long long>(min_occ, (unsigned long long)(total_windows * F))
+                                      : std::max<unsigned long long>(min_occ, (unsigned long long)F);
+  unsigned long long wpos = 0, wuniq = 0;
+  for (unsigned long long f : freqs) if (f > thr && f > min_occ) { wuniq++; wpos += f; }
+  if (wpos > total_windows / 2 || wuniq > freqs.size() * 0.7) {
+    std::vector<unsigned long long> all(freqs);
+    std::sort(all.begin(), all.end());
+    size_t keep = (size_t)(all.size() * 0.999);
+    if (keep >= all.size()) keep = all.size() - 1;
+    thr = std::max(thr, all[keep]);
+  }
+  return thr;
+}
+
+extern "C" void wfb_index_free(wfb_index_t* ix) {
+  if (!ix) return;
+#ifndef WFB_EMU
+  cudaSetDevice(ix->device);
+  cudaFree(ix->d_minmers); cudaFree(ix->d_points); cudaFree(ix->d_table); cudaFree(ix->d_uhash); cudaFree(ix->d_ustart); cudaFree(ix->d_ucount);
+#else
+  free(ix->d_minmers); free(ix->d_points); free(ix->d_table); free(ix->d_uhash); free(ix->d_ustart); free(ix->d_ucount);
+#endif
+  delete ix;
+}
+
+extern "C" wfb_index_t* wfb_index_build(int device, const wfb_index_params_t* prm, const char* const* seq_ptrs, const int64_t* seq_lens,
+                                        const int32_t* seq_ids, int32_t nseq, wfb_index_stats_t* stats) {
+  if (!prm || nseq <= 0 || !seq_ptrs || !seq_lens || !seq_ids) { wfb_set_last_error_("bad argument"); return nullptr; }
+  if (stats) memset(stats, 0, sizeof(*stats));
+  const int k = prm->kmer_size, w = prm->window_size, s = prm->sketch_size;
+  /* 1. windowed minmers of every target (addMinmers), in Sketch::build's order */
+  long long total_len = 0;
+  int max_seq_id = 0;
+  for (int i = 0; i < nseq; ++i) { total_len += seq_lens[i]; max_seq_id = std::max(max_seq_id, seq_ids[i]); }
+  if (max_seq_id >= (1 << 22)) { wfb_set_last_error_("seqId too large for the packed interval points (22 bits)"); return nullptr; }
+  long long cap = (long long)((double)total_len * (0.01 * s + 0.05)) + 4096;
+  std::vector<wfb_minmer_t> mi((size_t)cap);
+  int64_t n = 0;
+  wfb_minmer_stats_t ms;
+  int rc = wfb_minmers_build(device, seq_ptrs, seq_lens, seq_ids, nseq, k, w, s, mi.data(), cap, &n, &ms);
+  if (rc != WFB_OK) return nullptr;
+  if (n == 0) { wfb_set_last_error_("reference sketch is empty (winSketch.hpp:451-456)"); return nullptr; }
+  /* worker partitions of Sketch::build (winSketch.hpp:271-277): contiguous ranges of the sequences >= w */
+  std::vector<int> part((size_t)max_seq_id + 1, 0);
+  {
+    int nvalid = 0;
+    for (int i = 0; i < nseq; ++i) if (seq_lens[i] >= w) ++nvalid;
+    const int threads = std::max(1, prm->index_threads);
+    const int chunk = (nvalid + threads - 1) / threads;
+    int j = 0;
+    for (int i = 0; i < nseq; ++i) if (seq_lens[i] >= w) { part[seq_ids[i]] = j / std::max(1, chunk); ++j; }
+  }
+  wfb_index* ix = new wfb_index();
+  ix->device = device;
+  ix->params = *prm;
+  ix->n_minmers_all = n;
+#ifndef WFB_EMU
+  {
+    wfb_minmer_t* d_mi = nullptr; unsigned long long *d_keys = nullptr, *d_skeys = nullptr, *d_ufreq = nullptr, *d_uhash_all = nullptr;
+    int *d_idx = nullptr, *d_sidx = nullptr, *d_head = nullptr, *d_keep_s = nullptr, *d_keep_o = nullptr, *d_pstart = nullptr, *d_hk = nullptr, *d_part = nullptr;
+    long long *d_run = nullptr, *d_pair = nullptr, *d_uk = nullptr, *d_off = nullptr;
+    int* d_fail = nullptr;
+    Tmp tmp;
+    long long nuniq_all = 0, npairs = 0, nuk = 0, nkept = 0;
+    std::vector<unsigned long long> hfreq;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const int G = 148 * 8, B = 256;
+    IX_CHECK(cudaSetDevice(device));
+    IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1));
+    IX_CHECK(cudaMalloc(&d_mi, sizeof(wfb_minmer_t) * (size_t)n));
+    IX_CHECK(cudaMemcpy(d_mi, mi.data(), sizeof(wfb_minmer_t) * (size_t)n, cudaMemcpyHostToDevice));
+    IX_CHECK(cudaMalloc(&d_part, sizeof(int) * part.size()));
+    IX_CHECK(cudaMemcpy(d_part, part.data(), sizeof(int) * part.size(), cudaMemcpyHostToDevice));
+    IX_CHECK(cudaMalloc(&d_keys, 8 * (size_t)n)); IX_CHECK(cudaMalloc(&d_skeys, 8 * (size_t)n));
+    IX_CHECK(cudaMalloc(&d_idx, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_sidx, 4 * (size_t)n));
+    IX_CHECK(cudaMalloc(&d_head, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_keep_s, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_keep_o, 4 * (size_t)n));
+    IX_CHECK(cudaMalloc(&d_pstart, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_hk, 4 * (size_t)n));
+    IX_CHECK(cudaMalloc(&d_run, 8 * (size_t)n)); IX_CHECK(cudaMalloc(&d_pair, 8 * (size_t)n)); IX_CHECK(cudaMalloc(&d_uk, 8 * (size_t)n));
+    IX_CHECK(cudaMalloc(&d_off, 8 * (size_t)n));
+    IX_CHECK(cudaMalloc(&d_fail, 4)); IX_CHECK(cudaMemset(d_fail, 0, 4));
+    IX_CHECK(cudaEventRecord(e0));
+    /* 2. stable sort by hash (postings keep the index order inside a hash) */
+    IX_LAUNCH(ix_hash_keys_kernel, G, B, 0, d_mi, n, d_keys, d_idx);
+    {
+      size_t b = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, b, d_keys, d_skeys, d_idx, d_sidx, (int)n);
+      IX_CHECK(tmp.ensure(b));
+      b = tmp.cap;
+      IX_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, b, d_keys, d_skeys, d_idx, d_sidx, (int)n));
+    }
+    /* 3. frequencies (:266-296) */
+    IX_LAUNCH(ix_head_flags_kernel, G, B, 0, d_skeys, n, d_head);
+    IX_CHECK(incl_scan(tmp, d_head, d_run, n));
+    IX_CHECK(cudaMemcpy(&nuniq_all, d_run + (n - 1), 8, cudaMemcpyDeviceToHost));
+    IX_CHECK(cudaMalloc(&d_ufreq, 8 * (size_t)nuniq_all)); IX_CHECK(cudaMalloc(&d_uhash_all, 8 * (size_t)nuniq_all));
+    IX_CHECK(cudaMemset(d_ufreq, 0, 8 * (size_t)nuniq_all));
+    IX_LAUNCH(ix_run_freq_kernel, G, B, 0, d_head, d_run, n, d_ufreq, d_skeys, d_uhash_all);
+    hfreq.resize((size_t)nuniq_all);
+    IX_CHECK(cudaMemcpy(hfreq.data(), d_ufreq, 8 * (size_t)nuniq_all, cudaMemcpyDeviceToHost));
+    /* 4. threshold (:298-349) and keep flags (:374-377) */
+    ix->threshold = count_threshold(hfreq, (unsigned long long)n, prm->max_kmer_freq);
+    IX_LAUNCH(ix_keep_kernel, G, B, 0, d_run, d_ufreq, d_sidx, n, ix->threshold, d_keep_s, d_keep_o);
+    /* 5. postings (:379-387) */
+    IX_LAUNCH(ix_pair_start_kernel, G, B, 0, d_mi, d_sidx, d_skeys, d_keep_s, d_part, n, d_pstart);
+    IX_CHECK(incl_scan(tmp, d_pstart, d_pair, n));
+    IX_CHECK(cudaMemcpy(&npairs, d_pair + (n - 1), 8, cudaMemcpyDeviceToHost));
+    ix->n_points = 2 * npairs;
+    if (ix->n_points >= (1LL << 32)) { wfb_set_last_error_("too many interval points for 32-bit postings offsets"); rc = WFB_EINVAL; goto done; }
+    IX_CHECK(cudaMalloc(&ix->d_points, 8 * (size_t)std::max<long long>(ix->n_points, 1)));
+    IX_LAUNCH(ix_points_kernel, G, B, 0, d_mi, d_sidx, d_keep_s, d_pstart, d_pair, n, ix->d_points);
+    /* 6. kept unique hashes -> (start, count) */
+    IX_LAUNCH(ix_and_kernel, G, B, 0, d_head, d_keep_s, n, d_hk);
+    IX_CHECK(incl_scan(tmp, d_hk, d_uk, n));
+    IX_CHECK(cudaMemcpy(&nuk, d_uk + (n - 1), 8, cudaMemcpyDeviceToHost));
+    ix->n_uniq = nuk;
+    IX_CHECK(cudaMalloc(&ix->d_uhash, 8 * (size_t)std::max<long long>(nuk, 1)));
+    IX_CHECK(cudaMalloc(&ix->d_ustart, 4 * (size_t)std::max<long long>(nuk, 1)));
+    IX_CHECK(cudaMalloc(&ix->d_ucount, 4 * (size_t)std::max<long long>(nuk, 1)));
+    IX_CHECK(cudaMemset(ix->d_ucount, 0, 4 * (size_t)std::max<long long>(nuk, 1)));
+    IX_LAUNCH(ix_uniq_kernel, G, B, 0, d_head, d_keep_s, d_pstart, d_pair, d_uk, d_skeys, n, ix->d_uhash, ix->d_ustart, ix->d_ucount);
+    /* 7. open-addressing table, load <= 0.5 */
+    {
+      long long nb = 1;
+      while (nb * IX_BUCKET < 2 * std::max<long long>(nuk, 1)) nb <<= 1;
+      ix->n_buckets = nb;
+      IX_CHECK(cudaMalloc(&ix->d_table, sizeof(IxSlot) * (size_t)nb * IX_BUCKET));
+      IX_LAUNCH(ix_fill_kernel, G, B, 0, (unsigned long long*)ix->d_table, nb * IX_BUCKET * 2, (unsigned long long)IX_EMPTY);
+      IX_LAUNCH(ix_insert_kernel, G, B, 0, ix->d_table, nb, (const uint64_t*)ix->d_uhash, ix->d_ustart, ix->d_ucount, nuk, d_fail);
+      int fail = 0;
+      IX_CHECK(cudaMemcpy(&fail, d_fail, 4, cudaMemcpyDeviceToHost));
+      if (fail) { wfb_set_last_error_("hash table insert failed"); rc = WFB_ECUDA; goto done; }
+    }
+    /* 8. kept minmerIndex in reference order (:389,424-429) */
+    IX_CHECK(excl_scan(tmp, d_keep_o, d_off, n));
+    {
+      long long last_off = 0; int last_keep = 0;
+      IX_CHECK(cudaMemcpy(&last_off, d_off + (n - 1), 8, cudaMemcpyDeviceToHost));
+      IX_CHECK(cudaMemcpy(&last_keep, d_keep_o + (n - 1), 4, cudaMemcpyDeviceToHost));
+      nkept = last_off + last_keep;
+    }
+    ix->n_minmers = nkept;
+    IX_CHECK(cudaMalloc(&ix->d_minmers, sizeof(wfb_minmer_t) * (size_t)std::max<long long>(nkept, 1)));
+    IX_LAUNCH(ix_compact_minmers_kernel, G, B, 0, d_mi, d_keep_o, d_off, n, ix->d_minmers);
+    IX_CHECK(cudaEventRecord(e1));
+    IX_CHECK(cudaEventSynchronize(e1));
+    IX_CHECK(cudaGetLastError());
+    if (stats) {
+      float t = 0;
+      cudaEventElapsedTime(&t, e0, e1);
+      stats->index_kernel_ms = t;
+    }
+  done:
+    if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
+    cudaFree(d_mi); cudaFree(d_keys); cudaFree(d_skeys); cudaFree(d_ufreq); cudaFree(d_uhash_all); cudaFree(d_idx); cudaFree(d_sidx);
+    cudaFree(d_head); cudaFree(d_keep_s); cudaFree(d_keep_o); cudaFree(d_pstart); cudaFree(d_hk); cudaFree(d_part); cudaFree(d_run);
+    cudaFree(d_pair); cudaFree(d_uk); cudaFree(d_off); cudaFree(d_fail);
+    if (rc != WFB_OK) { wfb_index_free(ix); return nullptr; }
+  }
+#else
+  { wfb_set_last_error_("index build is not part of the host emulation"); wfb_index_free(ix); return nullptr; }
+#endif
+  if (stats) {
+    stats->minmer = ms;
+    stats->total_windows = (uint64_t)n; stats->kept_minmers = (uint64_t)ix->n_minmers; stats->interval_points = (uint64_t)ix->n_points;
+    stats->unique_hashes = (uint64_t)ix->n_uniq; stats->count_threshold = ix->threshold; stats->table_buckets = (uint64_t)ix->n_buckets;
+  }
+  return ix;
+}
+
+extern "C" int wfb_index_export(const wfb_index_t* ix, wfb_minmer_t* minmers, int64_t minmers_cap, uint64_t* uhash, uint32_t* ustart,
+                                uint32_t* ucount, int64_t uniq_cap, uint64_t* points, int64_t points_cap) {
+  if (!ix) { wfb_set_last_error_("index == NULL"); return WFB_EINVAL; }
+  if ((minmers && minmers_cap < ix->n_minmers) || (uhash && uniq_cap < ix->n_uniq) || (points && points_cap < ix->n_points)) {
+    wfb_set_last_error_("export buffer too small");
+    return WFB_ECAP;
+  }
+#ifndef WFB_EMU
+  int rc = WFB_OK;
+  IX_CHECK(cudaSetDevice(ix->device));
+  if (minmers && ix->n_minmers) IX_CHECK(cudaMemcpy(minmers, ix->d_minmers, sizeof(wfb_minmer_t) * (size_t)ix->n_minmers, cudaMemcpyDeviceToHost));
+  if (uhash && ix->n_uniq) {
+    IX_CHECK(cudaMemcpy(uhash, ix->d_uhash, 8 * (size_t)ix->n_uniq, cudaMemcpyDeviceToHost));
+    IX_CHECK(cudaMemcpy(ustart, ix->d_ustart, 4 * (size_t)ix->n_uniq, cudaMemcpyDeviceToHost));
+    IX_CHECK(cudaMemcpy(ucount, ix->d_ucount, 4 * (size_t)ix->n_uniq, cudaMemcpyDeviceToHost));
+  }
+  if (points && ix->n_points) IX_CHECK(cudaMemcpy(points, ix->d_points, 8 * (size_t)ix->n_points, cudaMemcpyDeviceToHost));
+done:
+  return rc;
+#else
+  return WFB_ENODEV;
+#endif
+}
+
+extern "C" int wfb_index_sizes(const wfb_index_t* ix, int64_t* n_minmers, int64_t* n_uniq, int64_t* n_points, uint64_t* threshold) {
+  if (!ix) return WFB_EINVAL;
+  if (n_minmers) *n_minmers = ix->n_minmers;
+  if (n_uniq) *n_uniq = ix->n_uniq;
+  if (n_points) *n_points = ix->n_points;
+  if (threshold) *threshold = ix->threshold;
+  return WFB_OK;
+}
+
+extern "C" int wfb_l1_batch(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
+                            const wfb_frag_query_t* fq, int32_t n, wfb_l1_out_t* out) {
+  if (!ix || !lp || !out || n < 0 || (n > 0 && (!seq_base || !frags || !fq))) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
+  if (!lp->ref_group || !lp->sketch_cutoffs || lp->n_cutoffs <= 0 || lp->minimum_hits < 1) { wfb_set_last_error_("bad L1 parameters"); return WFB_EINVAL; }
+  const int k = ix->params.kmer_size, w = ix->params.window_size, s = ix->params.sketch_size;
+  if (s > 512) { wfb_set_last_error_("sketch_size > 512 unsupported by the L1 kernel"); return WFB_EINVAL; }
+  for (int i = 0; i < n; ++i) {
+    if (frags[i].len != w) { wfb_set_last_error_("L1 kernel handles fragments of length == window_size (windowLen == 0) only"); return WFB_EINVAL; }
+    if (frags[i].seq_offset < 0 || frags[i].seq_offset + frags[i].len > seq_bytes) { wfb_set_last_error_("fragment out of range"); return WFB_EINVAL; }
+  }
+  out->n_loci = 0;
+  out->kernel_ms = 0;
+  if (n == 0) return WFB_OK;
+#ifndef WFB_EMU
+  int rc = WFB_OK;
+  int npow2 = 1;
+  while (npow2 < w - k + 1) npow2 <<= 1;
+  const size_t sketch_smem = (size_t)npow2 * 12 + (((size_t)w + 15) & ~(size_t)15) + 16;
+  IxL1Params P;
+  P.k = k; P.w = w; P.s = s; P.minimum_hits = lp->minimum_hits;
+  P.skip_self = lp->skip_self; P.skip_prefix = lp->skip_prefix; P.lower_triangular = lp->lower_triangular;
+  P.ncut = lp->n_cutoffs; P.smem_cap = 4096; P.gcap = 1 << 17; P.max_loci = 256; P.complexity_threshold = lp->kmer_complexity_threshold;
+  const size_t smem = std::max(sketch_smem, (size_t)P.smem_cap * 8);
+  uint8_t* d_seq = nullptr; wfb_frag_t* d_frags = nullptr; IxFragQuery* d_fq = nullptr; int *d_group = nullptr, *d_cut = nullptr;
+  wfb_minmer_t* d_q = nullptr; int *d_qn = nullptr, *d_fn = nullptr, *d_fst = nullptr; float* d_kc = nullptr; uint64_t* d_gs = nullptr;
+  IxL1Locus *d_ltmp = nullptr, *d_loci = nullptr; unsigned long long* d_lc = nullptr; long long* d_foff = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  unsigned long long nl = 0;
+  int grid = 0;
+  const long long loci_cap = out->loci_cap;
+  std::vector<IxL1Locus> hl;
+  IX_CHECK(cudaSetDevice(ix->device));
+  {
+    cudaDeviceProp prop;
+    IX_CHECK(cudaGetDeviceProperties(&prop, ix->device));
+    grid = std::min(n, prop.multiProcessorCount * 4);
+  }
+  IX_CHECK(cudaMalloc(&d_seq, (size_t)seq_bytes + 16));
+  IX_CHECK(cudaMemcpy(d_seq, seq_base, (size_t)seq_bytes, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&d_frags, sizeof(wfb_frag_t) * (size_t)n));
+  IX_CHECK(cudaMemcpy(d_frags, frags, sizeof(wfb_frag_t) * (size_t)n, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&d_fq, sizeof(IxFragQuery) * (size_t)n));
+  IX_CHECK(cudaMemcpy(d_fq, fq, sizeof(IxFragQuery) * (size_t)n, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&d_group, 4 * (size_t)lp->n_ref_group));
+  IX_CHECK(cudaMemcpy(d_group, lp->ref_group, 4 * (size_t)lp->n_ref_group, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&d_cut, 4 * (size_t)lp->n_cutoffs));
+  IX_CHECK(cudaMemcpy(d_cut, lp->sketch_cutoffs, 4 * (size_t)lp->n_cutoffs, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&d_q, sizeof(wfb_minmer_t) * (size_t)n * s));
+  IX_CHECK(cudaMemset(d_q, 0, sizeof(wfb_minmer_t) * (size_t)n * s));
+  IX_CHECK(cudaMalloc(&d_qn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_fn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_fst, 4 * (size_t)n));
+  IX_CHECK(cudaMalloc(&d_kc, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_foff, 8 * (size_t)n));
+  IX_CHECK(cudaMalloc(&d_gs, 8 * (size_t)P.gcap * grid));
+  IX_CHECK(cudaMalloc(&d_ltmp, sizeof(IxL1Locus) * (size_t)2 * P.max_loci * grid));
+  IX_CHECK(cudaMalloc(&d_loci, sizeof(IxL1Locus) * (size_t)std::max<long long>(loci_cap, 1)));
+  IX_CHECK(cudaMalloc(&d_lc, 8)); IX_CHECK(cudaMemset(d_lc, 0, 8));
+  IX_CHECK(cudaFuncSetAttribute(ix_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1));
+  IX_CHECK(cudaEventRecord(e0));
+  IX_LAUNCH(ix_l1_kernel, grid, 128, smem, d_seq, d_frags, d_fq, n, npow2, P, ix->d_table, ix->n_buckets, ix->d_points, d_group, d_cut, d_q,
+            d_qn, d_kc, d_gs, d_ltmp, d_loci, d_lc, loci_cap, d_foff, d_fn, d_fst);
+  IX_CHECK(cudaEventRecord(e1));
+  IX_CHECK(cudaEventSynchronize(e1));
+  IX_CHECK(cudaGetLastError());
+  {
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    out->kernel_ms = t;
+  }
+  IX_CHECK(cudaMemcpy(&nl, d_lc, 8, cudaMemcpyDeviceToHost));
+  if ((long long)nl > loci_cap) { wfb_set_last_error_("loci buffer too small"); rc = WFB_ECAP; goto done; }
+  out->n_loci = (int64_t)nl;
+  if (out->q_minmers) IX_CHECK(cudaMemcpy(out->q_minmers, d_q, sizeof(wfb_minmer_t) * (size_t)n * s, cudaMemcpyDeviceToHost));
+  if (out->q_count) IX_CHECK(cudaMemcpy(out->q_count, d_qn, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  if (out->q_complexity) IX_CHECK(cudaMemcpy(out->q_complexity, d_kc, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  IX_CHECK(cudaMemcpy(out->frag_loci_offset, d_foff, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+  IX_CHECK(cudaMemcpy(out->frag_loci_count, d_fn, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  IX_CHECK(cudaMemcpy(out->frag_status, d_fst, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  hl.resize((size_t)nl);
+  if (nl) IX_CHECK(cudaMemcpy(hl.data(), d_loci, sizeof(IxL1Locus) * (size_t)nl, cudaMemcpyDeviceToHost));
+  for (unsigned long long i = 0; i < nl; ++i) {
+    out->loci[i].seqId = hl[i].seqId; out->loci[i].intersectionSize = hl[i].intersectionSize;
+    out->loci[i].rangeStartPos = hl[i].rangeStartPos; out->loci[i].rangeEndPos = hl[i].rangeEndPos;
+  }
+done:
+  if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
+  cudaFree(d_seq); cudaFree(d_frags); cudaFree(d_fq); cudaFree(d_group); cudaFree(d_cut); cudaFree(d_q); cudaFree(d_qn); cudaFree(d_fn);
+  cudaFree(d_fst); cudaFree(d_kc); cudaFree(d_gs); cudaFree(d_ltmp); cudaFree(d_loci); cudaFree(d_lc); cudaFree(d_foff);
+  return rc;
+#else
+  wfb_set_last_error_("L1 is not part of the host emulation");
+  return WFB_ENODEV;
+#endif
+}

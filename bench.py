@@ -163,6 +163,76 @@ def run_cpu_sample(recs, target_s, threads):
             "sample": f"first {len(sample)} of {len(recs)} records of the step ({bp} query bp), {dt:.1f} s wall on {threads} threads"}
 
 
+def map_path_section(dev, cores, with_cpu):
+    """Path 1 (MashMap 3.5 sketch / index / L1) on a C3-shaped synthetic pangenome slice: 8 haplotypes x 3 Mbp at
+    3 % divergence, -k15 -w1k, s=29 (scerevisiae8 parameters). Reported beside the headline."""
+    import wfmash_b200 as wb
+    from wfmash_b200 import synth
+    rng = np.random.default_rng(77)
+    root = synth.random_seq(3_000_000, rng)
+    seqs = [root.tobytes()] + [synth.mutate(root, 0.03, rng).tobytes() for _ in range(7)]
+    ids = list(range(8))
+    k, w, ssz = 15, 1000, 29
+    bases = sum(len(x) for x in seqs)
+    t0 = time.perf_counter()
+    ix = wb.Index(seqs, ids, k, w, ssz, index_threads=cores)
+    ix.close()
+    ix = wb.Index(seqs, ids, k, w, ssz, index_threads=cores)   # second build: warm context / allocator
+    t_index = time.perf_counter() - t0
+    st = ix.stats
+    blob = b"".join(seqs)
+    offs = np.cumsum([0] + [len(x) for x in seqs])
+    frags, fqs = [], []
+    for qi, sq in enumerate(seqs):
+        for j in range(len(sq) // w):
+            frags.append((int(offs[qi]) + j * w, w, qi)); fqs.append((qi, qi))
+    cut = np.array([max(1, int(i * 0.6)) for i in range(1001)], dtype=np.int32)
+    grp = np.arange(8, dtype=np.int32)
+    r = ix.l1(blob, frags, fqs, 3, cut, grp)       # warm-up
+    r = ix.l1(blob, frags, fqs, 3, cut, grp)
+    rho = st.total_windows / bases
+    pbar = st.interval_points / max(1, st.unique_hashes)
+    idx_bytes = bases * (1 + 32 * rho + 48 * rho)                    # SURVEY section 8(d): ~7.2 B per indexed base
+    l1_bytes = len(frags) * w * (1 + 32 * ssz / w) + len(frags) * ssz * (16 + 2 * 8 * pbar)
+    peak, _ = load_peaks()
+    out = {
+        "workload": "C3-shaped synthetic: 8 haplotypes x 3 Mbp, 3 % divergence, -k15 -w1k s=29, all-vs-all fragments",
+        "index": {"bases": bases, "windows": int(st.total_windows), "kept_minmers": int(st.kept_minmers),
+                  "unique_hashes": int(st.unique_hashes), "interval_points": int(st.interval_points),
+                  "count_threshold": int(st.count_threshold), "stale_absorbed": int(st.minmer.stale_absorbed),
+                  "stream_kernel_ms": st.minmer.stream_kernel_ms, "minmer_total_kernel_ms": st.minmer.total_kernel_ms,
+                  "index_kernel_ms": st.index_kernel_ms,
+                  "mbp_per_s_stream_kernel": bases / st.minmer.stream_kernel_ms / 1e3,
+                  "roofline_frac_stream_kernel": idx_bytes / (st.minmer.stream_kernel_ms / 1e3) / 1e9 / peak},
+        "l1": {"fragments": len(frags), "loci": int(len(r["loci"])), "kernel_ms": r["kernel_ms"],
+               "fragments_per_s": len(frags) / (r["kernel_ms"] / 1e3), "query_mbp_per_s": len(frags) * w / r["kernel_ms"] / 1e3,
+               "roofline_frac": l1_bytes / (r["kernel_ms"] / 1e3) / 1e9 / peak},
+    }
+    ix.close()
+    if with_cpu:
+        ref = os.path.join(ROOT, "oracle", "_ref", "libmapref.so")
+        if os.path.exists(ref):
+            lib = ctypes.CDLL(ref)
+            lib.ref_add_minmers.restype = ctypes.c_int64
+            dt = np.dtype([("hash", "<u8"), ("wpos", "<i8"), ("wpos_end", "<i8"), ("seqId", "<i4"), ("strand", "<i2"), ("pad_", "<i2")])
+
+            def one(i):
+                buf = ctypes.create_string_buffer(seqs[i], len(seqs[i]))
+                o = np.zeros(len(seqs[i]) // 4 + 1000, dtype=dt)
+                return lib.ref_add_minmers(buf, ctypes.c_int64(len(seqs[i])), k, w, ssz, i, ctypes.c_void_p(o.ctypes.data), ctypes.c_int64(len(o)))
+            fd = os.dup(2); dn = os.open(os.devnull, os.O_WRONLY); os.dup2(dn, 2)   # the reference's progress meter is chatty
+            try:
+                t0 = time.perf_counter()
+                with ThreadPoolExecutor(max_workers=min(cores, len(seqs))) as ex:
+                    list(ex.map(one, range(len(seqs))))
+                dtc = time.perf_counter() - t0
+            finally:
+                os.dup2(fd, 2); os.close(fd); os.close(dn)
+            out["index"]["cpu_reference_addMinmers_mbp_per_s"] = bases / dtc / 1e6
+            out["index"]["cpu_reference_threads"] = min(cores, len(seqs))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -173,6 +243,7 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override records per step (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning sweeps)")
+    ap.add_argument("--no-map", action="store_true", help="skip the mapping-path (path 1) section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -316,6 +387,11 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_map:
+            try:
+                line["map_path"] = map_path_section(dev, cores, not args.no_cpu)
+            except Exception as e:  # the headline must still be printed
+                line["map_path"] = {"error": str(e)}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -1,0 +1,71 @@
+"""Multi-process host logic on CPU: world_size-2 gloo run of the record sharding + result gather
+(the N>1 path of bench.py / align_sharded with a stand-in for the GPU call)."""
+import os
+import socket
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from wfmash_b200 import shard
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pairs = [(b"A" * (100 + 37 * i), b"C" * (90 + 41 * i)) for i in range(23)]
+    seen = []
+
+    def fake_align(local):  # stands in for Aligner.align_end2end_batch on this rank's GPU
+        seen.extend(local)
+        return [(len(p), len(t), rank) for p, t in local]
+
+    out = shard.align_sharded(pairs, fake_align)
+    if rank == 0:
+        q.put((out, len(seen)))
+    else:
+        q.put((None, len(seen)))
+    dist.destroy_process_group()
+
+
+def test_partition_is_balanced_and_complete():
+    sys.path.insert(0, ROOT)
+    from wfmash_b200 import shard
+    costs = [shard.record_cost(1000 * (i % 17 + 1), 900 * (i % 13 + 1), 0.9 + 0.005 * (i % 10)) for i in range(200)]
+    for world in (1, 2, 4, 8):
+        sh = shard.partition(costs, world)
+        assert sorted(i for s in sh for i in s) == list(range(200))
+        loads = [sum(costs[i] for i in s) for s in sh]
+        assert max(loads) <= 1.25 * (sum(costs) / world) + max(costs)
+    assert shard.partition(costs, 4) == shard.partition(costs, 4)  # deterministic
+
+
+def test_two_rank_gloo_shard_and_gather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = [g for g in got if g[0] is not None]
+    assert len(full) == 1
+    out, _ = full[0]
+    assert len(out) == 23 and all(o is not None for o in out)
+    assert [(o[0], o[1]) for o in out] == [(100 + 37 * i, 90 + 41 * i) for i in range(23)]
+    assert {o[2] for o in out} == {0, 1}            # both ranks did work
+    assert sum(g[1] for g in got) == 23             # every record aligned exactly once

@@ -110,6 +110,24 @@ int wfb_align_batch_device(wfb_aligner_t*, const char* d_seq, const int64_t* pat
                            const int64_t* text_off, const int32_t* text_len, int32_t n, char* ops, int64_t ops_cap,
                            wfb_aln_result_t* results, wfb_align_stats_t* stats);
 
+/* Head / tail patch alignments of do_biwfa_alignment (src/common/wflign/src/wflign.cpp:280-305, 368-397):
+ *   wfa::WFAlignerGapAffine2Pieces(0,x,o1,e1,o2,e2,Alignment,MemoryMed).alignEndsFree(pattern,
+ *       patternBeginFree, patternEndFree, text, textBeginFree, textEndFree)
+ * (deps/WFA2-lib/bindings/cpp/WFAligner.cpp:110-135) for a batch. Results as for wfb_align_batch.
+ * term_group: the reference picks the terminating cell in an order that depends on how it was compiled
+ * (scalar = 1, AVX2 = 8, AVX-512 = 16 lanes; wavefront_extend_kernels.c:166-193,
+ * wavefront_extend_kernels_avx.c:296-400,592-691); pass the value matching the reference build to compare with. */
+typedef struct {
+  const char* pattern;
+  int32_t pattern_len;
+  const char* text;
+  int32_t text_len;
+  int32_t pattern_begin_free, pattern_end_free, text_begin_free, text_end_free;
+} wfb_endsfree_pair_t;
+
+int wfb_align_endsfree_batch(wfb_aligner_t*, const wfb_endsfree_pair_t* pairs, int32_t n, int32_t term_group, char* ops,
+                             int64_t ops_cap, wfb_aln_result_t* results);
+
 /* Device memory helpers so callers without a CUDA binding (ctypes) can stage inputs. */
 void* wfb_device_malloc(int device, uint64_t bytes);
 void wfb_device_free(int device, void* p);

@@ -56,6 +56,12 @@ int orc_wfa_align(const char* pattern, int plen, const char* text, int tlen,
                   const orc_penalties_t* pen, char* ops_out, int ops_cap, int* ops_len,
                   int* score, orc_wfa_counters_t* counters);
 
+/* Ends-free unidirectional WFA as used by wfmash's head / tail patching (wflign.cpp:280-305,368-397).
+ * term_group = 1 (scalar build), 8 (AVX2) or 16 (AVX-512): which terminating cell the reference picks
+ * (wavefront_extend_kernels.c:166-193 vs wavefront_extend_kernels_avx.c:296-400,592-691). */
+int orc_wfa_endsfree(const char* pattern, int plen, int pbf, int pef, const char* text, int tlen, int tbf, int tef,
+                     const orc_penalties_t* pen, int term_group, char* ops_out, int ops_cap, int* ops_len, int* score);
+
 /* Gap-affine-2p score of an ops string (restates cigar_score_gap_affine2p, alignment/cigar.c);
  * returned as a non-negative penalty. */
 int orc_cigar_score(const char* ops, int n, const orc_penalties_t* pen);

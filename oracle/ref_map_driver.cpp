@@ -36,8 +36,10 @@ int ref_sketch_fragment(char* seq, int64_t len, int k, int s, int32_t seqId, ref
 /* commonFunc.hpp:440 */
 int64_t ref_add_minmers(char* seq, int64_t len, int k, int w, int s, int32_t seqId, ref_minmer_t* out, int64_t cap) {
   std::vector<skch::MinmerInfo> v;
-  progress_meter::ProgressMeter pm(0, "", true); /* chats on stderr; callers may redirect fd 2 */
-  skch::CommonFunc::addMinmers(v, seq, len, k, w, 4, s, seqId, &pm);
+  /* one shared meter like the reference's Sketch::build (winSketch.hpp:188-204); a huge total keeps
+   * increment() on its lock-free path (progress.hpp) so concurrent callers do not serialise */
+  static progress_meter::ProgressMeter* pm = new progress_meter::ProgressMeter((uint64_t)1 << 60, "", false);
+  skch::CommonFunc::addMinmers(v, seq, len, k, w, 4, s, seqId, pm);
   int64_t n = 0;
   for (auto& m : v) {
     if (n >= cap) break;

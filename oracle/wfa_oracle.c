@@ -57,6 +57,7 @@ typedef struct {
   int num_null_steps;
   int status, status_score;
   int end_k, end_off;
+  int endsfree, pbf, pef, tbf, tef, term_group; /* alignment form (wavefront_aligner.c:252-310) */
   orc_wfa_counters_t* cnt;
 } wfa_t;
 
@@ -269,6 +270,7 @@ static int wfa_extend(wfa_t* a, int score, int* max_ak) {
     if (mx < ak) mx = ak;
   }
   if (a->cnt) a->cnt->extend_matches += matched;
+  if (a->endsfree) return 0; /* handled by wfa_extend_endsfree */
   if (termination_end2end(a, score)) {
     a->status = ST_END_REACHED;
     a->status_score = score;
@@ -403,6 +405,62 @@ static int find_breakpoint(wfa_t* f, wfa_t* r, breakpoint_t* bp) {
   }
   if (f->cnt) f->cnt->score_steps += score_forward + score_reverse;
   return ST_OK;
+}
+
+/* wavefront_termination_endsfree, wavefront_termination.c:115-160 */
+static int termination_endsfree(const wfa_t* a, int k, int32_t offset) {
+  const int h = offset, v = offset - k;
+  if (h >= a->tlen && a->plen - v <= a->pef) return 1;
+  if (v >= a->plen && a->tlen - h <= a->tef) return 1;
+  return 0;
+}
+
+/* wavefront_extend_endsfree (wavefront_extend.c:259-293). All offsets end up fully extended; WHICH
+ * terminating cell ends the alignment depends on the build of the reference:
+ *   scalar (wavefront_extend_kernels.c:166-193): the first in ascending k;
+ *   AVX2 / AVX-512 (wavefront_extend_kernels_avx.c:296-400, 592-691), G = 8 / 16 lanes: first the
+ *   n % G lowest diagonals in order, then - group by group - the cells whose first 4 bases matched, then
+ *   a final ascending pass over all cells.  term_group = 1, 8 or 16 selects the rule. */
+static int wfa_extend_endsfree(wfa_t* a, int score) {
+  wf_t* m = &a->wf[C_M][slot_of(a, score)];
+  if (!m->exists) {
+    if (a->num_null_steps > a->scope) { a->status = ST_END_UNREACHABLE; a->status_score = score; return 1; }
+    return 0;
+  }
+  const int G = a->term_group, n = m->hi - m->lo + 1;
+  const int peel = (G > 1) ? (n < G ? n : n % G) : n;
+  int best_class = 3, best_j = 0;
+  for (int k = m->lo; k <= m->hi; ++k) {
+    int32_t off = m->off[k - m->kmin];
+    if (off < 0) continue;
+    int v = off - k, h = off, run = 0;
+    while (v < a->plen && h < a->tlen && pch(a, v) == tch(a, h)) { ++v; ++h; ++off; ++run; }
+    m->off[k - m->kmin] = off;
+    if (a->cnt) a->cnt->extend_matches += run;
+    if (termination_endsfree(a, k, off)) {
+      const int j = k - m->lo;
+      const int cls = (G <= 1 || j < peel) ? 0 : (run >= 4 ? 1 : 2);
+      if (cls < best_class) { best_class = cls; best_j = j; }
+    }
+  }
+  if (best_class < 3) {
+    a->end_k = m->lo + best_j;
+    a->end_off = m->off[best_j + m->lo - m->kmin];
+    a->status = ST_END_REACHED;
+    a->status_score = score;
+    return 1;
+  }
+  return 0;
+}
+
+/* wavefront_aligner_init_wf_m with ends-free begin (wavefront_aligner.c:252-310), match == 0 */
+static void wfa_init_endsfree(wfa_t* a, const char* P, int plen, const char* T, int tlen, int pbf, int pef, int tbf, int tef,
+                              int term_group) {
+  wfa_init(a, P, 0, plen, T, 0, tlen, 0, C_M, C_M);
+  a->endsfree = 1; a->pbf = pbf; a->pef = pef; a->tbf = tbf; a->tef = tef; a->term_group = term_group;
+  wf_t* w0 = &a->wf[C_M][0];
+  wf_set_range(w0, -pbf, tbf);
+  for (int k = -pbf; k <= tbf; ++k) w0->off[k + pbf] = k > 0 ? k : 0; /* (h,0) -> offset h ; (0,v) -> offset 0 */
 }
 
 /* ---- base case: unidirectional WFA + backtrace --------------------------------------------- */
@@ -655,6 +713,40 @@ int orc_wfa_align(const char* pattern, int plen, const char* text, int tlen, con
   int rc = base_align(&b, pattern, 0, plen, text, 0, tlen, C_M, C_M, &out, &sc);
   if (rc == ST_OK && out.len > out.cap) rc = -1000;
   *ops_len = rc == ST_OK ? out.len : 0;
+  if (score) *score = -sc;
+  wfa_free(&b);
+  return rc;
+}
+
+/* Ends-free unidirectional WFA (wflign.cpp:280-305 head patch, :368-397 tail patch use it with
+ * MemoryMed; `high` and `med` produce identical CIGARs). term_group: see wfa_extend_endsfree. */
+int orc_wfa_endsfree(const char* pattern, int plen, int pbf, int pef, const char* text, int tlen, int tbf, int tef,
+                     const orc_penalties_t* pen, int term_group, char* ops_out, int ops_cap, int* ops_len, int* score) {
+  wfa_t b;
+  wfa_alloc(&b, 0, 64);
+  b.pen = *pen;
+  b.scope = scope_of(pen);
+  b.cnt = 0;
+  wfa_init_endsfree(&b, pattern, plen, text, tlen, pbf, pef, tbf, tef, term_group);
+  int sc = 0;
+  for (;;) {
+    if (wfa_extend_endsfree(&b, sc)) break;
+    ++sc;
+    wfa_compute(&b, sc);
+  }
+  int rc = ST_UNATTAINABLE;
+  *ops_len = 0;
+  if (b.status == ST_END_REACHED) {
+    const int cap = 2 * (plen + tlen) + 8;
+    char* tmp = (char*)malloc((size_t)cap);
+    int begin = 0;
+    if (backtrace_affine(&b, sc, b.end_k, b.end_off, tmp, cap, &begin) == 0 && cap - begin <= ops_cap) {
+      memcpy(ops_out, tmp + begin, (size_t)(cap - begin));
+      *ops_len = cap - begin;
+      rc = ST_OK;
+    }
+    free(tmp);
+  }
   if (score) *score = -sc;
   wfa_free(&b);
   return rc;

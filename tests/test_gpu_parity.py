@@ -316,3 +316,42 @@ def test_l1_hit_counts_match_oracle(wb, oracle):
             nloci += n2
     assert nloci > 1000
     ix.close()
+
+
+def _patch_cases(seed, n):
+    import random
+    rng = random.Random(seed)
+    cases = []
+    for _ in range(n):
+        L = rng.choice([5, 20, 130, 200, 500, 1500, 4000])
+        x = "".join(rng.choice("ACGT") for _ in range(L))
+        y = util.mutate(x, rng.choice([0, 0.02, 0.1, 0.3]), rng)
+        if rng.random() < 0.3:
+            y = "".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 60))) + y
+        if rng.random() < 0.3:
+            x = x + "".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 60)))
+        if not x or not y:
+            continue
+        p, tt = x.encode(), y.encode()
+        cases.append((p, len(p), 0, tt, len(tt), 0))   # head patch: begin-free (wflign.cpp:300-305)
+        cases.append((p, 0, len(p), tt, 0, len(tt)))   # tail patch: end-free  (wflign.cpp:392-397)
+    return cases
+
+
+def test_ends_free_patch_alignments_match_oracle_and_reference(wb, oracle):
+    # a13: ends-free WFA of the head/tail patches; the oracle is pinned to the AVX2-built reference (MemoryMed)
+    cases = _patch_cases(77, 200)
+    al = wb.Aligner(0)
+    ref = util.load_ref("libwfa2ref.so")
+    for G in (8, 1, 16):
+        res = al.align_ends_free_batch(cases, term_group=G)
+        for (p, pbf, pef, t, tbf, tef), r in zip(cases, res):
+            buf = ctypes.create_string_buffer(2 * (len(p) + len(t)) + 16)
+            n, sc = ctypes.c_int(), ctypes.c_int()
+            P = util.Pen(*util.WFMASH_PEN)
+            st = oracle.orc_wfa_endsfree(p, len(p), pbf, pef, t, len(t), tbf, tef, ctypes.byref(P), G, buf, len(buf), ctypes.byref(n), ctypes.byref(sc))
+            assert st == r.status == 0
+            assert buf.raw[: n.value] == r.ops
+            if G == 8 and ref is not None:   # oracle/_ref is compiled with -march=x86-64-v3 (AVX2 kernels)
+                st2 = ref.ref_wfa_endsfree(p, len(p), pbf, pef, t, len(t), tbf, tef, *util.WFMASH_PEN, 1, buf, len(buf), ctypes.byref(n), ctypes.byref(sc))
+                assert st2 == 0 and buf.raw[: n.value] == r.ops

@@ -35,6 +35,12 @@ class _Res(ctypes.Structure):
                 ("ops_len", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
 
 
+class _EfPair(ctypes.Structure):
+    _fields_ = [("pattern", ctypes.c_char_p), ("pattern_len", ctypes.c_int32), ("text", ctypes.c_char_p), ("text_len", ctypes.c_int32),
+                ("pattern_begin_free", ctypes.c_int32), ("pattern_end_free", ctypes.c_int32), ("text_begin_free", ctypes.c_int32),
+                ("text_end_free", ctypes.c_int32)]
+
+
 class AlignStats(ctypes.Structure):
     _fields_ = [("cells", ctypes.c_uint64), ("extend_matches", ctypes.c_uint64), ("overlap_tests", ctypes.c_uint64),
                 ("score_steps", ctypes.c_uint64), ("break_tasks", ctypes.c_uint64), ("base_tasks", ctypes.c_uint64),
@@ -169,6 +175,23 @@ class Aligner:
 
     def align_end2end(self, pattern: bytes, text: bytes):
         return self.align_end2end_batch([(pattern, text)])[0]
+
+    def align_ends_free_batch(self, items, term_group=8):
+        """Head / tail patch alignments of do_biwfa_alignment (wflign.cpp:280-305, 368-397):
+        items = [(pattern, pattern_begin_free, pattern_end_free, text, text_begin_free, text_end_free)], the argument
+        order of wfa::WFAligner::alignEndsFree. term_group: 1 / 8 / 16 = scalar / AVX2 / AVX-512 build of the reference."""
+        n = len(items)
+        if n == 0:
+            return []
+        arr = (_EfPair * n)(*[_EfPair(p, len(p), t, len(t), pbf, pef, tbf, tef) for p, pbf, pef, t, tbf, tef in items])
+        cap = sum(len(it[0]) + len(it[3]) for it in items) + 16
+        ops = ctypes.create_string_buffer(cap)
+        res = (_Res * n)()
+        rc = self._L.wfb_align_endsfree_batch(ctypes.c_void_p(self._h), arr, n, term_group, ops, ctypes.c_int64(cap), res)
+        if rc != 0:
+            raise _err(rc)
+        raw = ops.raw
+        return [AlignResult(r.status, r.score, raw[r.ops_offset:r.ops_offset + r.ops_len]) for r in res]
 
 
 class MinmerStats(ctypes.Structure):

@@ -521,6 +521,126 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
   return WFB_OK;
 }
 
+/* Head / tail patch alignments (wflign.cpp:280-305, 368-397): ends-free gap-affine-2p WFA, one CTA per pair. */
+extern "C" int wfb_align_endsfree_batch(wfb_aligner_t* a, const wfb_endsfree_pair_t* hp, int32_t n, int32_t term_group, char* ops,
+                                        int64_t ops_cap, wfb_aln_result_t* results) {
+  if (!a || n < 0 || (n > 0 && (!hp || !results || !ops))) { g_last_error = "bad argument"; return WFB_EINVAL; }
+  if (term_group != 1 && term_group != 8 && term_group != 16) { g_last_error = "term_group must be 1, 8 or 16"; return WFB_EINVAL; }
+  if (n == 0) return WFB_OK;
+#ifndef WFB_EMU
+  WFB_CHECK(cudaSetDevice(a->device));
+#endif
+  const WfbPen pen = a->pen;
+  wfb_stream_t s = a->stream;
+  std::vector<WfbPairDesc> pd((size_t)n);
+  std::vector<WfbTask> tasks((size_t)n);
+  std::vector<WfbEndsFree> efs((size_t)n);
+  long long seq_bytes = 16, slot_bytes = 0, need = 0;
+  int maxPT = 0;
+  for (int i = 0; i < n; ++i) {
+    const int plen = hp[i].pattern_len, tlen = hp[i].text_len;
+    if (plen <= 0 || tlen <= 0 || !hp[i].pattern || !hp[i].text || hp[i].pattern_begin_free < 0 || hp[i].pattern_begin_free > plen ||
+        hp[i].pattern_end_free < 0 || hp[i].pattern_end_free > plen || hp[i].text_begin_free < 0 || hp[i].text_begin_free > tlen ||
+        hp[i].text_end_free < 0 || hp[i].text_end_free > tlen) {
+      g_last_error = "bad ends-free pair (wavefront_align.c checks P0<=|P|, Pf<=|P|, T0<=|T|, Tf<=|T|)";
+      return WFB_EINVAL;
+    }
+    pd[i].plen = plen; pd[i].tlen = tlen;
+    pd[i].p_off = seq_bytes; seq_bytes = align_up(seq_bytes + plen + 16, 16);
+    pd[i].t_off = seq_bytes; seq_bytes = align_up(seq_bytes + tlen + 16, 16);
+    pd[i].prev_off = pd[i].p_off; pd[i].trev_off = pd[i].t_off; /* no reverse aligner here */
+    pd[i].ops_off = slot_bytes; slot_bytes = align_up(slot_bytes + plen + tlen + 8, 8);
+    need += plen + tlen;
+    maxPT = std::max(maxPT, plen + tlen);
+    WfbTask t; t.pair = i; t.pb = 0; t.pe = plen; t.tb = 0; t.te = tlen; t.cbegin = WFB_M; t.cend = WFB_M; t.score_remaining = 0;
+    tasks[i] = t;
+    WfbEndsFree e; e.pbf = hp[i].pattern_begin_free; e.pef = hp[i].pattern_end_free; e.tbf = hp[i].text_begin_free; e.tef = hp[i].text_end_free;
+    efs[i] = e;
+  }
+  if (need > ops_cap) { g_last_error = "ops buffer too small (need sum(pattern_len+text_len))"; return WFB_ECAP; }
+  if (a->d_seq.ensure((size_t)seq_bytes + 64) || a->d_pairs.ensure(sizeof(WfbPairDesc) * (size_t)n) || a->d_slots.ensure((size_t)slot_bytes + 64) ||
+      a->d_dense.ensure((size_t)slot_bytes + 64) || a->d_len.ensure(sizeof(int) * (size_t)n) || a->d_status.ensure(sizeof(int) * (size_t)n) ||
+      a->d_ctrl.ensure(sizeof(int) * 16) || a->d_q[0].ensure(sizeof(WfbTask) * (size_t)n) || a->d_srcoff.ensure(sizeof(WfbEndsFree) * (size_t)n) ||
+      a->h_seq.ensure((size_t)seq_bytes)) {
+    g_last_error = "allocation failed";
+    return WFB_ENOMEM;
+  }
+  uint8_t* hs = (uint8_t*)a->h_seq.p;
+  for (int i = 0; i < n; ++i) {
+    memcpy(hs + pd[i].p_off, hp[i].pattern, (size_t)pd[i].plen); memset(hs + pd[i].p_off + pd[i].plen, 0, 16);
+    memcpy(hs + pd[i].t_off, hp[i].text, (size_t)pd[i].tlen);    memset(hs + pd[i].t_off + pd[i].tlen, 0, 16);
+  }
+  WFB_H2D(a->d_seq.p, hs, (size_t)seq_bytes, s);
+  WFB_H2D(a->d_pairs.p, pd.data(), sizeof(WfbPairDesc) * (size_t)n, s);
+  WFB_H2D(a->d_srcoff.p, efs.data(), sizeof(WfbEndsFree) * (size_t)n, s);
+  WFB_MEMSET(a->d_slots.p, 0, (size_t)slot_bytes, s);
+  WFB_MEMSET(a->d_status.p, 0, sizeof(int) * (size_t)n, s);
+  WFB_STREAM_SYNC(s);
+  int* d_ctrl = (int*)a->d_ctrl.p;
+  int* d_status = (int*)a->d_status.p;
+  std::vector<int> h_status((size_t)n, 0);
+  /* pass 0: every pair, modest arena; later passes: only the pairs that ran out of arena / score slots */
+  std::vector<int> todo((size_t)n);
+  for (int i = 0; i < n; ++i) todo[i] = i;
+  const long long arena_sizes[3] = {4LL << 20, 64LL << 20, 512LL << 20}; /* ints per CTA */
+  const int score_caps[3] = {1024, 6000, 12000};
+  for (int pass = 0; pass < 3 && !todo.empty(); ++pass) {
+    const long long arena_stride = arena_sizes[pass];
+    const int score_cap = score_caps[pass];
+    const int maxruns = 2 * score_cap + 16;
+    const int runflag_stride = (int)align_up(maxPT + 16, 16);
+    const size_t per_cta = (size_t)arena_stride * 4 + (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta) + (size_t)maxruns * sizeof(WfbRun) + (size_t)runflag_stride;
+    int ctas = (int)std::min<size_t>(todo.size(), (size_t)a->sm_count * (pass == 0 ? 4 : 1));
+    ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctas, (size_t)(a->workspace_bytes / per_cta)));
+    if (a->d_arena.ensure((size_t)ctas * (size_t)arena_stride * 4) || a->d_log.ensure((size_t)ctas * (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta)) ||
+        a->d_runs.ensure((size_t)ctas * (size_t)maxruns * sizeof(WfbRun)) || a->d_ws.ensure((size_t)ctas * (size_t)runflag_stride)) {
+      g_last_error = "device allocation failed (ends-free workspace)";
+      return WFB_ENOMEM;
+    }
+    std::vector<WfbTask> tk(todo.size());
+    std::vector<WfbEndsFree> ek(todo.size());
+    for (size_t j = 0; j < todo.size(); ++j) { tk[j] = tasks[todo[j]]; ek[j] = efs[todo[j]]; }
+    WFB_H2D(a->d_q[0].p, tk.data(), sizeof(WfbTask) * tk.size(), s);
+    WFB_H2D(a->d_srcoff.p, ek.data(), sizeof(WfbEndsFree) * ek.size(), s);
+    WFB_MEMSET(d_ctrl, 0, sizeof(int) * 16, s);
+    for (size_t j = 0; j < todo.size(); ++j) h_status[todo[j]] = 0;
+    WFB_H2D(d_status, h_status.data(), sizeof(int) * (size_t)n, s);
+    WFB_STREAM_SYNC(s);
+    WFB_LAUNCH(wfb_endsfree_kernel, ctas, kBaseThreads, s, (const WfbTask*)a->d_q[0].p, (const WfbEndsFree*)a->d_srcoff.p, (int)todo.size(),
+               d_ctrl + 0, (const WfbPairDesc*)a->d_pairs.p, (const uint8_t*)a->d_seq.p, (int32_t*)a->d_arena.p, arena_stride,
+               (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, (unsigned char*)a->d_ws.p, runflag_stride, (int)term_group,
+               pen, (char*)a->d_slots.p, d_status);
+    WFB_D2H(h_status.data(), d_status, sizeof(int) * (size_t)n, s);
+    WFB_STREAM_SYNC(s);
+#ifndef WFB_EMU
+    { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { g_last_error = std::string("kernel: ") + cudaGetErrorString(e); return WFB_ECUDA; } }
+#endif
+    std::vector<int> again;
+    for (int i : todo) if (h_status[i] == WFB_PAIR_BASE_SCORE_CAP) again.push_back(i);
+    todo.swap(again);
+  }
+  WFB_LAUNCH(wfb_compact_kernel, std::min(n, a->sm_count * 8), 256, s, (const WfbPairDesc*)a->d_pairs.p, n, (const char*)a->d_slots.p,
+             (char*)a->d_dense.p, (int*)a->d_len.p);
+  if (a->h_dense.ensure((size_t)slot_bytes + 64) || a->h_misc.ensure(sizeof(int) * (size_t)n)) { g_last_error = "pinned allocation failed"; return WFB_ENOMEM; }
+  WFB_D2H(a->h_misc.p, a->d_len.p, sizeof(int) * (size_t)n, s);
+  WFB_D2H(a->h_dense.p, a->d_dense.p, (size_t)slot_bytes, s);
+  WFB_STREAM_SYNC(s);
+  const int* h_len = (const int*)a->h_misc.p;
+  const char* h_dense = (const char*)a->h_dense.p;
+  int64_t out_off = 0;
+  for (int i = 0; i < n; ++i) {
+    wfb_aln_result_t& r = results[i];
+    r.status = h_status[i]; r.ops_offset = out_off; r.ops_len = 0; r.score = 0; r.reserved_ = 0;
+    if (r.status == 0) {
+      memcpy(ops + out_off, h_dense + pd[i].ops_off, (size_t)h_len[i]);
+      r.ops_len = h_len[i];
+      r.score = gap_affine2p_score(ops + out_off, h_len[i], pen);
+      out_off += h_len[i];
+    }
+  }
+  return WFB_OK;
+}
+
 extern "C" int wfb_align_batch(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_t n, char* ops, int64_t ops_cap,
                                wfb_aln_result_t* results, wfb_align_stats_t* stats) {
   if (n > 0 && !pairs) { g_last_error = "pairs == NULL"; return WFB_EINVAL; }

@@ -299,6 +299,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
       const int v_ = mx - k_;                                                                             \
       const int run = wfb_match_run(pseq + v_, tseq + mx, min(plen - v_, tlen - mx));                     \
       mx += run;                                                                                          \
+      if (alloc.runflag) alloc.runflag[k_ + alloc.runbias] = run >= 4 ? 1 : 0;                            \
       acc.matches += (unsigned)run;                                                                       \
       tmax = max(tmax, 2 * mx - k_);                                                                      \
       tlo[WFB_M] = min(tlo[WFB_M], k_);                                                                   \
@@ -411,7 +412,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
   WFB_SYNC();
   max_ak_out = red_maxak[par];
   /* wavefront_termination_end2end, wavefront_termination.c:37-114 */
-  if (ring.ex[slot][cend] && ring.lo[slot][cend] <= ak_end && ak_end <= ring.hi[slot][cend]) {
+  if (cend >= 0 && ring.ex[slot][cend] && ring.lo[slot][cend] <= ak_end && ak_end <= ring.hi[slot][cend]) {
     /* ak_end lies inside the trimmed range => it was computed in this step => red_end[par] is fresh */
     if (red_end[par] >= tlen) return WFB_ST_END_REACHED;
   }
@@ -610,6 +611,8 @@ struct WfbAllocFixed { /* breakpoint kernel: every (slot, component) has a fixed
   int dirbase; /* dir * R * 5 * W + kshift */
   int W;
   int kalign;  /* (k + kalign) % 4 == 0  <=>  cell(k) is 16-byte aligned, the same for every row (W % 8 == 0) */
+  static constexpr unsigned char* runflag = nullptr;
+  static const int runbias = 0;
   WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) const {
     (void)lo; (void)hi;
     for (int c = 0; c < 5; ++c) ob[c] = dirbase + (slot * 5 + c) * W;
@@ -830,6 +833,8 @@ struct WfbRun {
 
 struct WfbAllocBump {
   static const int kalign = -1; /* rows are packed back to back: no common alignment, scalar path only */
+  unsigned char* runflag; /* ends-free only: runflag[k + runbias] = 1 when M(k) matched >= 4 bases this step; else NULL */
+  int runbias;
   int bump; /* next free int in the arena */
   WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) {
     (void)slot;
@@ -868,16 +873,21 @@ WFB_DEV void wfb_emit(WfbRun* runs, int& nruns, int maxruns, int& err, int op, i
 /* Thread 0: wavefront_backtrace_affine (wavefront_backtrace.c:320-529). Emits runs (right to left);
  * `base_idx` = pb + tb turns local (v,h) into the pair's op-slot index. */
 WFB_DEV int wfb_backtrace(const WfbBaseMeta* log, const int32_t* arena, int nscores, const WfbPen& pen, int cbegin, int cend,
-                          int plen, int tlen, int alignment_score, int base_idx, WfbRun* runs, int maxruns, int* nruns_out) {
+                          int plen, int tlen, int alignment_score, int end_k, int end_off, int base_idx, WfbRun* runs, int maxruns,
+                          int* nruns_out) {
   enum { BT_M = 9, BT_D2_EXT = 8, BT_D2_OPEN = 7, BT_D1_EXT = 6, BT_D1_OPEN = 5, BT_I2_EXT = 4, BT_I2_OPEN = 3,
          BT_I1_EXT = 2, BT_I1_OPEN = 1 };
   (void)cbegin;
   int nruns = 0, err = 0;
   int matrix_type = cend;
   int score = alignment_score;
-  int k = tlen - plen;
-  int offset = tlen;
-  int v = plen, h = tlen;
+  int k = end_k;
+  int offset = end_off;
+  int v = end_off - end_k, h = end_off;
+  if (cend == WFB_M) { /* ends-free tails (:347-356), written right to left: the D's end the transcript, the I's precede them */
+    if (v < plen) wfb_emit(runs, nruns, maxruns, err, 'D', plen - v, base_idx + v + tlen);
+    if (h < tlen) wfb_emit(runs, nruns, maxruns, err, 'I', tlen - h, base_idx + v + h);
+  }
   while (v > 0 && h > 0 && score > 0) {
     const int mismatch = score - pen.x;
     const int gap_open1 = score - pen.o1 - pen.e1, gap_open2 = score - pen.o2 - pen.e2;
@@ -993,6 +1003,7 @@ WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter,
     if (WFB_TID == 0) { sh.red_maxak[0] = sh.red_maxak[1] = sh.red_maxak[2] = 0; }
     WFB_SYNC();
     WfbAllocBump ab;
+    ab.runflag = nullptr; ab.runbias = 0;
     ab.bump = 1; /* cell 0 = the score-0 wavefront */
     if (WFB_TID == 0) {
       wfb_init_score0(sh.ring, arena, 0, t.cbegin, t.cend, pf, tf, plen, tlen, &sh.st0, &sh.ak0, acc);
@@ -1025,7 +1036,7 @@ WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter,
     }
     if (WFB_TID == 0) {
       int nr = 0;
-      sh.bt_err = wfb_backtrace(log, arena, score + 1, pen, t.cbegin, t.cend, plen, tlen, score, t.pb + t.tb, runs, maxruns, &nr);
+      sh.bt_err = wfb_backtrace(log, arena, score + 1, pen, t.cbegin, t.cend, plen, tlen, score, tlen - plen, tlen, t.pb + t.tb, runs, maxruns, &nr);
       sh.nruns = nr;
     }
     WFB_SYNC();
@@ -1050,6 +1061,153 @@ WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter,
       wfb_atomic_add64(&counters->base_cells, acc.cells);
       wfb_atomic_add64(&counters->base_score_steps, acc.steps);
       wfb_atomic_add64(&counters->base_tasks, ntask_done);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Ends-free kernel: wfmash's head / tail patch alignments (wflign.cpp:280-305, 368-397):
+ * WFAlignerGapAffine2Pieces(..., Alignment, MemoryMed).alignEndsFree(). `med` (piggy-backed backtrace)
+ * and `high` memory produce the same transcript, so this is wavefront_unialign with the ends-free
+ * initial wavefront (wavefront_aligner.c:252-310), wavefront_extend_endsfree's termination
+ * (wavefront_extend.c:259-293, wavefront_termination.c:115-160) and wavefront_backtrace_affine.
+ * term_group selects which terminating cell wins (1 = scalar build, 8 = AVX2, 16 = AVX-512 of the
+ * reference: wavefront_extend_kernels.c:166-193 vs wavefront_extend_kernels_avx.c:296-400,592-691).
+ * ---------------------------------------------------------------------------------------------- */
+struct WfbEndsFree {
+  int pbf, pef, tbf, tef;
+};
+
+WFB_DEV bool wfb_term_endsfree(int k, int off, int plen, int tlen, int pef, int tef) {
+  const int h = off, v = off - k;
+  if (h >= tlen && plen - v <= pef) return true;
+  if (v >= plen && tlen - h <= tef) return true;
+  return false;
+}
+
+struct WfbEfShared {
+  WfbRing ring;
+  int red_maxak[3];
+  int red_end[3];
+  int task_idx;
+  int term_key; /* (class << 26 | j), INT_MAX = none */
+  int nruns, bt_err;
+};
+
+/* search the trimmed M row of `slot` for the terminating cell the reference would pick; all threads */
+WFB_DEV void wfb_ef_search(WfbEfShared& sh, const int32_t* arena, const unsigned char* runflag, int runbias, int slot, int plen, int tlen,
+                           const WfbEndsFree& ef, int G) {
+  const int lo = sh.ring.lo[slot][WFB_M], hi = sh.ring.hi[slot][WFB_M];
+  if (!sh.ring.ex[slot][WFB_M] || lo > hi) return;
+  const int n = hi - lo + 1;
+  const int peel = (G > 1) ? (n < G ? n : n % G) : n;
+  const int32_t* m = arena + sh.ring.boff[slot][WFB_M];
+  int best = INT_MAX;
+  for (int kk = lo + WFB_TID; kk <= hi; kk += WFB_NT) {
+    const int32_t off = m[kk];
+    if (off < 0) continue;
+    if (!wfb_term_endsfree(kk, off, plen, tlen, ef.pef, ef.tef)) continue;
+    const int j = kk - lo;
+    const int cls = (G <= 1 || j < peel) ? 0 : (runflag[kk + runbias] ? 1 : 2);
+    best = min(best, (cls << 26) | j);
+  }
+  best = wfb_warp_min(best);
+  if (wfb_lane() == 0 && best != INT_MAX) wfb_smem_min(&sh.term_key, best);
+}
+
+WFB_KERNEL(wfb_endsfree_kernel, const WfbTask* tasks, const WfbEndsFree* efs, int ntasks, int* task_counter, const WfbPairDesc* pairs,
+           const uint8_t* seq, int32_t* arena_all, long long arena_stride, WfbBaseMeta* log_all, int score_cap, WfbRun* runs_all,
+           int maxruns, unsigned char* runflag_all, int runflag_stride, int term_group, WfbPen pen, char* ops_all, int* pair_status) {
+  WFB_KERNEL_PROLOGUE
+  WFB_SHARED WfbEfShared sh;
+  int32_t* const arena = arena_all + (long long)bid * arena_stride;
+  WfbBaseMeta* const log = log_all + (long long)bid * (score_cap + 1) * 5;
+  WfbRun* const runs = runs_all + (long long)bid * maxruns;
+  unsigned char* const runflag = runflag_all + (long long)bid * runflag_stride;
+  WfbAcc acc;
+  acc.cells = acc.overlap = acc.matches = acc.steps = 0;
+  for (;;) {
+    WFB_SYNC();
+    if (WFB_TID == 0) sh.task_idx = wfb_atomic_add(task_counter, 1);
+    WFB_SYNC();
+    const int ti = sh.task_idx;
+    if (ti >= ntasks) break;
+    const WfbTask t = tasks[ti];
+    const WfbEndsFree ef = efs[ti];
+    const WfbPairDesc pd = pairs[t.pair];
+    char* const ops = ops_all + pd.ops_off;
+    const int plen = t.pe - t.pb, tlen = t.te - t.tb;
+    const uint8_t* pf = seq + pd.p_off + t.pb;
+    const uint8_t* tf = seq + pd.t_off + t.tb;
+    const int R = pen.R;
+    const int runbias = plen + 2;
+    if (plen + tlen + 8 > runflag_stride || (long long)(ef.pbf + ef.tbf + 1) + 16 > arena_stride) {
+      if (WFB_TID == 0) pair_status[t.pair] = WFB_PAIR_BASE_SCORE_CAP;
+      continue;
+    }
+    wfb_ring_reset(sh.ring, R);
+    if (WFB_TID == 0) { sh.red_maxak[0] = sh.red_maxak[1] = sh.red_maxak[2] = 0; sh.term_key = INT_MAX; }
+    WFB_SYNC();
+    /* score 0: M on diagonals [-pbf, tbf]: (h,0) -> offset h, (0,v) -> offset 0, each extended */
+    const int lo0 = -ef.pbf, hi0 = ef.tbf, n0 = hi0 - lo0 + 1;
+    for (int kk = lo0 + WFB_TID; kk <= hi0; kk += WFB_NT) {
+      int off = kk > 0 ? kk : 0;
+      const int v = off - kk;
+      const int run = wfb_match_run(pf + v, tf + off, min(plen - v, tlen - off));
+      off += run;
+      arena[kk - lo0] = off;
+      runflag[kk + runbias] = run >= 4 ? 1 : 0;
+    }
+    if (WFB_TID == 0) {
+      sh.ring.ex[0][WFB_M] = 1; sh.ring.lo[0][WFB_M] = lo0; sh.ring.hi[0][WFB_M] = hi0; sh.ring.boff[0][WFB_M] = -lo0;
+      for (int c = 0; c < 5; ++c) { WfbBaseMeta m; m.lo = lo0; m.hi = hi0; m.boff = -lo0; m.ex = (c == WFB_M); log[c] = m; }
+    }
+    WFB_SYNC();
+    wfb_ef_search(sh, arena, runflag, runbias, 0, plen, tlen, ef, term_group);
+    WFB_SYNC();
+    WfbAllocBump ab;
+    ab.runflag = runflag; ab.runbias = runbias;
+    ab.bump = n0;
+    int status = (sh.term_key != INT_MAX) ? WFB_ST_END_REACHED : WFB_ST_OK;
+    int score = 0, num_null = 0, max_ak = 0;
+    while (status == WFB_ST_OK) { /* wavefront_unialign.c:251-270 with wavefront_extend_endsfree */
+      ++score;
+      if (score > score_cap || (long long)ab.bump + 5LL * (plen + tlen + 8) > arena_stride) { status = -1; break; }
+      status = wfb_step(sh.ring, arena, pen, score, pf, tf, plen, tlen, -1, num_null, ab, sh.red_maxak, sh.red_end, max_ak, acc);
+      const int slot = score % R;
+      if (WFB_TID == 0)
+        for (int c = 0; c < 5; ++c) {
+          WfbBaseMeta m;
+          m.lo = sh.ring.lo[slot][c]; m.hi = sh.ring.hi[slot][c]; m.boff = sh.ring.boff[slot][c]; m.ex = sh.ring.ex[slot][c];
+          log[score * 5 + c] = m;
+        }
+      if (status != WFB_ST_OK) break; /* END_UNREACHABLE */
+      wfb_ef_search(sh, arena, runflag, runbias, slot, plen, tlen, ef, term_group);
+      WFB_SYNC();
+      if (sh.term_key != INT_MAX) status = WFB_ST_END_REACHED;
+    }
+    if (status != WFB_ST_END_REACHED) {
+      if (WFB_TID == 0) pair_status[t.pair] = (status == -1) ? WFB_PAIR_BASE_SCORE_CAP : WFB_PAIR_UNATTAINABLE;
+      continue;
+    }
+    if (WFB_TID == 0) {
+      const int slot = score % R;
+      const int end_k = sh.ring.lo[slot][WFB_M] + (sh.term_key & ((1 << 26) - 1));
+      const int end_off = arena[sh.ring.boff[slot][WFB_M] + end_k];
+      int nr = 0;
+      sh.bt_err = wfb_backtrace(log, arena, score + 1, pen, WFB_M, WFB_M, plen, tlen, score, end_k, end_off, t.pb + t.tb, runs, maxruns, &nr);
+      sh.nruns = nr;
+    }
+    WFB_SYNC();
+    if (sh.bt_err) {
+      if (WFB_TID == 0) pair_status[t.pair] = WFB_PAIR_BACKTRACE;
+      continue;
+    }
+    const int nr = sh.nruns;
+    for (int r = 0; r < nr; ++r) {
+      const WfbRun ru = runs[r];
+      const int stride = (ru.op == 'M' || ru.op == 'X') ? 2 : 1;
+      for (int j = WFB_TID; j < ru.count; j += WFB_NT) ops[ru.idx + j * stride] = (char)ru.op;
     }
   }
 }

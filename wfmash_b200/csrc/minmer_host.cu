@@ -149,7 +149,7 @@ extern "C" int wfb_minmers_build(int device, const char* const* seq_ptrs, const 
   if (ns == 0) return WFB_OK;
   MmParams P;
   P.k = k; P.w = w; P.s = s;
-  P.chunk = 4096; P.warm = 2 * w;
+  P.chunk = 1024; P.warm = w; /* tuned in profiles/r01_minmer_chunk_sweep.txt: latency-bound, more chunks = more threads */
   { const char* e = getenv("WFB_MM_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
   { const char* e = getenv("WFB_MM_WARM"); if (e && atoi(e) >= w) P.warm = atoi(e); }
   P.qcap = w + 2; P.heap_cap = 3 * w + 64; P.pool_cap = 4 * w + 64;

@@ -380,8 +380,79 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     g_last_error = "device allocation failed (workspace)";
     return WFB_ENOMEM;
   }
-  /* ---- level loop ---- */
-  size_t n_break = t_break.size(), n_base = t_base.size();
+  /* ---- persistent single-launch driver (default): no level barriers ---- */
+  bool persist_done = false;
+  double persist_ms = 0.0;
+  {
+    const char* sched = getenv("WFB_SCHED"); /* "level" selects the level-synchronous driver */
+    const bool want_persist = !(sched && strcmp(sched, "level") == 0);
+    int ctas = cta_break;
+#ifndef WFB_EMU
+    {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfb_persist_kernel, kBreakThreads, 0) == cudaSuccess && nb > 0) ctas = a->sm_count * nb;
+    }
+#endif
+    const size_t per_cta = (size_t)ws_stride * 4 + base_cta_bytes;
+    ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctas, a->workspace_bytes / per_cta));
+    const size_t n0 = t_break.size() + t_base.size();
+    size_t qcap = std::min<size_t>(std::max<size_t>((size_t)n * 1024, (size_t)1 << 16), (size_t)1 << 25);
+    if (want_persist && n0 <= qcap / 2) {
+      if (a->d_ws.ensure((size_t)ctas * (size_t)ws_stride * 4) || a->d_arena.ensure((size_t)ctas * (size_t)arena_stride * 4) ||
+          a->d_log.ensure((size_t)ctas * (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta)) || a->d_runs.ensure((size_t)ctas * (size_t)maxruns * sizeof(WfbRun)) ||
+          a->d_q[0].ensure(sizeof(WfbTask) * qcap) || a->d_q[1].ensure(sizeof(int) * qcap)) {
+        g_last_error = "device allocation failed (persistent queue / workspace)";
+        return WFB_ENOMEM;
+      }
+      std::vector<WfbTask> init(t_break);
+      init.insert(init.end(), t_base.begin(), t_base.end());
+      std::vector<int> ones(n0, 1);
+      WFB_MEMSET(a->d_q[1].p, 0, sizeof(int) * qcap, s);
+      WFB_H2D(a->d_q[0].p, init.data(), sizeof(WfbTask) * n0, s);
+      WFB_H2D(a->d_q[1].p, ones.data(), sizeof(int) * n0, s);
+      int ctrl0[16] = {0};
+      ctrl0[8] = 0;            /* head */
+      ctrl0[9] = (int)n0;      /* tail */
+      ctrl0[10] = (int)n0;     /* outstanding */
+      ctrl0[11] = 0;           /* error */
+      WFB_H2D(d_ctrl, ctrl0, sizeof(int) * 16, s);
+      WFB_STREAM_SYNC(s);
+      WfbPQueue pq;
+      pq.tasks = (WfbTask*)a->d_q[0].p; pq.ready = (int*)a->d_q[1].p; pq.head = d_ctrl + 8; pq.tail = d_ctrl + 9;
+      pq.outstanding = d_ctrl + 10; pq.error = d_ctrl + 11; pq.cap = (int)qcap;
+#ifndef WFB_EMU
+      WFB_CHECK(cudaEventRecord(a->ev[2], s));
+#endif
+      WFB_LAUNCH(wfb_persist_kernel, ctas, kBreakThreads, s, pq, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq, (int32_t*)a->d_ws.p, ws_stride,
+                 W, (int32_t*)a->d_arena.p, arena_stride, (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, pen, d_slots,
+                 d_status, d_counters);
+#ifndef WFB_EMU
+      WFB_CHECK(cudaEventRecord(a->ev[3], s));
+#endif
+      int ctrl1[16] = {0};
+      WFB_D2H(ctrl1, d_ctrl, sizeof(int) * 16, s);
+      WFB_STREAM_SYNC(s);
+#ifndef WFB_EMU
+      {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { g_last_error = std::string("kernel: ") + cudaGetErrorString(e); return WFB_ECUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a->ev[2], a->ev[3]);
+        persist_ms = ms;
+      }
+#endif
+      if (ctrl1[11] == 0 && ctrl1[10] == 0) {
+        persist_done = true;
+      } else {
+        /* queue overflow or watchdog: start over with the level-synchronous driver */
+        WFB_MEMSET(d_slots, 0, (size_t)slot_bytes, s);
+        WFB_MEMSET(d_status, 0, sizeof(int) * (size_t)n, s);
+        WFB_MEMSET(d_counters, 0, sizeof(WfbCounters), s);
+      }
+    }
+  }
+  /* ---- level loop (fallback / WFB_SCHED=level) ---- */
+  size_t n_break = persist_done ? 0 : t_break.size(), n_base = persist_done ? 0 : t_base.size();
   int cur = 0;
   {
     if (a->d_q[0].ensure(sizeof(WfbTask) * std::max<size_t>(n_break, 1)) || a->d_q[2].ensure(sizeof(WfbTask) * std::max<size_t>(n_base, 1))) {
@@ -392,8 +463,8 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     if (n_base) WFB_H2D(a->d_q[2].p, t_base.data(), sizeof(WfbTask) * n_base, s);
     WFB_STREAM_SYNC(s); /* host vectors + pd must stay alive until copied */
   }
-  double break_ms = 0.0;
-  uint64_t levels = 0;
+  double break_ms = persist_ms;
+  uint64_t levels = persist_done ? 1 : 0;
   const char* dbg_path = getenv("WFB_DEBUG_TASKS"); /* per-task timeline dump (tuning only) */
   FILE* dbg_f = dbg_path ? fopen(dbg_path, "w") : nullptr;
   if (!dbg_f) dbg_path = nullptr;

@@ -571,10 +571,50 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
 /* ------------------------------------------------------------------------------------------------
  * Task plumbing
  * ---------------------------------------------------------------------------------------------- */
+/* Where new sub-problems go: the next level's two queues (level-synchronous driver) or ONE persistent
+ * queue drained by the same running kernel (wfb_persist_kernel). */
+struct WfbPQueue {
+  WfbTask* tasks;
+  int* ready;       /* ready[i] = 1 once tasks[i] is published */
+  int* head;        /* next slot to claim   */
+  int* tail;        /* next slot to publish */
+  int* outstanding; /* tasks published and not yet finished */
+  int* error;       /* != 0: capacity overflow / watchdog */
+  int cap;
+};
+struct WfbSink {
+  WfbQueue q_break, q_base;
+  WfbPQueue pq;
+  int persistent;
+};
+
 WFB_DEV void wfb_push(const WfbQueue& q, const WfbTask& t, int* pair_status) {
   const int idx = wfb_atomic_add(q.count, 1);
   if (idx < q.cap) q.tasks[idx] = t;
   else pair_status[t.pair] = WFB_PAIR_QUEUE_OVERFLOW;
+}
+WFB_DEV void wfb_ppush(const WfbPQueue& q, const WfbTask& t, int* pair_status) {
+  wfb_atomic_add(q.outstanding, 1); /* before the parent retires */
+  const int idx = wfb_atomic_add(q.tail, 1);
+  if (idx >= q.cap) {
+    pair_status[t.pair] = WFB_PAIR_QUEUE_OVERFLOW;
+    *q.error = 1;
+    wfb_atomic_add(q.outstanding, -1);
+    return;
+  }
+  q.tasks[idx] = t;
+#ifndef WFB_EMU
+  __threadfence();
+  atomicExch(&q.ready[idx], 1);
+#else
+  q.ready[idx] = 1;
+#endif
+}
+/* thread 0 only */
+WFB_DEV void wfb_sink_push(const WfbSink& s, const WfbTask& t, int* pair_status) {
+  if (s.persistent) wfb_ppush(s.pq, t, pair_status);
+  else if (t.score_remaining <= WFB_FALLBACK_MIN_SCORE) wfb_push(s.q_base, t, pair_status);
+  else wfb_push(s.q_break, t, pair_status);
 }
 
 /* Fill n ops of kind `op` starting at DP cell (v,h) (absolute pair coordinates); all threads. */
@@ -585,16 +625,14 @@ WFB_DEV void wfb_fill_ops(char* ops, int v, int h, char op, int n) {
 
 /* Dispatch one child sub-problem (wavefront_bialign_alignment :1159-1170): trivial cases are
  * written immediately (all threads), the rest is queued by thread 0. */
-WFB_DEV void wfb_dispatch_child(const WfbTask& c, char* ops, const WfbQueue& q_break, const WfbQueue& q_base,
-                                int* pair_status) {
+WFB_DEV void wfb_dispatch_child(const WfbTask& c, char* ops, const WfbSink& sink, int* pair_status) {
   const int plen = c.pe - c.pb, tlen = c.te - c.tb;
   if (tlen == 0) {
     wfb_fill_ops(ops, c.pb, c.tb, 'D', plen);
   } else if (plen == 0) {
     wfb_fill_ops(ops, c.pb, c.tb, 'I', tlen);
   } else if (WFB_TID == 0) {
-    if (c.score_remaining <= WFB_FALLBACK_MIN_SCORE) wfb_push(q_base, c, pair_status);
-    else wfb_push(q_break, c, pair_status);
+    wfb_sink_push(sink, c, pair_status);
   }
 }
 
@@ -664,138 +702,156 @@ WFB_DEV void wfb_init_score0(WfbRing& ring, int32_t* basep, int boff0, int cbegi
 #ifndef WFB_BREAK_MINBLOCKS
 #define WFB_BREAK_MINBLOCKS 2
 #endif
+
+struct WfbBreakCtaShared {
+  WfbBreakShared sh;
+  int sh_st[2];
+  int sh_ak[2];
+};
+
+/* One breakpoint sub-problem on one CTA: wavefront_bialign_find_breakpoint (wavefront_bialign.c:974-1082) +
+ * the dispatch of both halves (:1188-1212) + the exception path (:1083-1110). */
+WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const WfbPairDesc* pairs, const uint8_t* seq, int32_t* ws, int W,
+                            const WfbPen& pen, const WfbSink& sink, char* ops_all, int* pair_status, WfbAcc& acc, WfbTaskLog* tasklog) {
+  WfbBreakShared& sh = S.sh;
+  int* const sh_st = S.sh_st;
+  int* const sh_ak = S.sh_ak;
+  const WfbPairDesc pd = pairs[t.pair];
+  char* const ops = ops_all + pd.ops_off;
+  const int plen = t.pe - t.pb, tlen = t.te - t.tb;
+  const long long tl_t0 = tasklog ? wfb_globaltimer() : 0;
+  const unsigned long long tl_s0 = acc.steps;
+  /* trivial cases, wavefront_bialign.c:1160-1165 */
+  if (tlen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'D', plen); return; }
+  if (plen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'I', tlen); return; }
+  /* sequence views: forward reads the forward copies, reverse the reversed copies
+   * (wavefront_sequences.c:288-295) */
+  const uint8_t* pf = seq + pd.p_off + t.pb;
+  const uint8_t* tf = seq + pd.t_off + t.tb;
+  const uint8_t* pr = seq + pd.prev_off + (pd.plen - t.pe);
+  const uint8_t* tr = seq + pd.trev_off + (pd.tlen - t.te);
+  const int R = pen.R;
+  const int kshift = plen + 1;
+  WfbAllocFixed af, ar;
+  af.W = ar.W = W;
+  af.kalign = ar.kalign = kshift & 3; /* dirbase = (multiple of 8) + kshift */
+  af.dirbase = kshift;
+  ar.dirbase = R * 5 * W + kshift;
+  wfb_ring_reset(sh.ring[0], R);
+  wfb_ring_reset(sh.ring[1], R);
+  for (int i = WFB_TID; i < WFB_RMAX * 5; i += WFB_NT) sh.os.found[i] = INT_MAX;
+  if (WFB_TID < (WFB_RMAX * 5 + 31) / 32) sh.os.hitmask[WFB_TID] = 0;
+  if (WFB_TID == 0) {
+    for (int d = 0; d < 2; ++d) for (int j = 0; j < 3; ++j) sh.red_maxak[d][j] = 0;
+    sh.bp.score = INT_MAX;
+    sh.os.ncand = 0;
+  }
+  WFB_SYNC();
+  if (WFB_TID == 0) {
+    /* wavefront_bialign_init :114-143: reverse aligner swaps begin/end components */
+    int ob[5];
+    af(0, 0, 0, ob);
+    wfb_init_score0(sh.ring[0], ws, ob[t.cbegin], t.cbegin, t.cend, pf, tf, plen, tlen, &sh_st[0], &sh_ak[0], acc);
+    ar(0, 0, 0, ob);
+    wfb_init_score0(sh.ring[1], ws, ob[t.cend], t.cend, t.cbegin, pr, tr, plen, tlen, &sh_st[1], &sh_ak[1], acc);
+  }
+  WFB_SYNC();
+  int status = WFB_ST_OK; /* != OK => a direction reached the end (or is unreachable) */
+  int score_reached = 0;
+  int score_forward = 0, score_reverse = 0;
+  int forward_max_ak = sh_ak[0], reverse_max_ak = sh_ak[1];
+  int null_f = 0, null_r = 0;
+  if (sh_st[0] != WFB_ST_OK) { status = sh_st[0]; score_reached = 0; }
+  else if (sh_st[1] != WFB_ST_OK) { status = sh_st[1]; score_reached = 0; }
+  const int max_antidiagonal = plen + tlen - 1;
+  bool last_wf_forward = false;
+  int max_ak = 0;
+  /* phase 1 (:1010-1043): alternate until the furthest points of both directions may collide */
+  while (status == WFB_ST_OK) {
+    if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
+    ++score_forward;
+    int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
+    if (forward_max_ak < max_ak) forward_max_ak = max_ak;
+    last_wf_forward = true;
+    if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
+    if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
+    ++score_reverse;
+    st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
+    if (reverse_max_ak < max_ak) reverse_max_ak = max_ak;
+    last_wf_forward = false;
+    if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
+  }
+  /* phase 2 (:1045-1079): advance while scanning for overlaps */
+  const int gap_opening = max(pen.o1, pen.o2);
+  while (status == WFB_ST_OK) {
+    if (last_wf_forward) {
+      const int min_score_reverse = (score_reverse > pen.scope - 1) ? score_reverse - (pen.scope - 1) : 0;
+      if (score_forward + min_score_reverse - gap_opening >= sh.bp.score) break;
+      wfb_overlap(sh.ring[0], ws, sh.ring[1], ws, pen, score_forward, score_reverse, true, plen, tlen, &sh.bp, &sh.os, acc);
+      ++score_reverse;
+      const int st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
+      if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
+    }
+    const int min_score_forward = (score_forward > pen.scope - 1) ? score_forward - (pen.scope - 1) : 0;
+    if (min_score_forward + score_reverse - gap_opening >= sh.bp.score) break;
+    wfb_overlap(sh.ring[1], ws, sh.ring[0], ws, pen, score_reverse, score_forward, false, plen, tlen, &sh.bp, &sh.os, acc);
+    ++score_forward;
+    const int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
+    if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
+    last_wf_forward = true;
+  }
+  if (tasklog && WFB_TID == 0) {
+    WfbTaskLog tl;
+    tl.t0 = tl_t0; tl.t1 = wfb_globaltimer(); tl.smid = wfb_smid(); tl.steps = (int)(acc.steps - tl_s0);
+    tl.score_f = score_forward; tl.score_r = score_reverse; tl.plen = plen; tl.tlen = tlen; tl.status = status; tl.pad_ = 0;
+    tasklog[ti] = tl;
+  }
+  if (status != WFB_ST_OK) {
+    /* wavefront_bialign_find_breakpoint_exception :1083-1110 */
+    if (WFB_TID == 0) {
+      if (status == WFB_ST_END_REACHED && score_reached <= WFB_RECOVERY_MIN_SCORE) {
+        WfbTask c = t;
+        c.score_remaining = 0;
+        wfb_sink_push(sink, c, pair_status);
+      } else {
+        pair_status[t.pair] = WFB_PAIR_UNATTAINABLE;
+      }
+    }
+    return;
+  }
+  /* both halves, :1188-1212 */
+  const WfbBreakpoint bp = sh.bp;
+  const int bh = bp.offset_forward, bv = bp.offset_forward - bp.k_forward;
+  WfbTask c0, c1;
+  c0.pair = t.pair; c0.pb = t.pb; c0.pe = t.pb + bv; c0.tb = t.tb; c0.te = t.tb + bh;
+  c0.cbegin = t.cbegin; c0.cend = bp.component; c0.score_remaining = bp.score_forward;
+  c1.pair = t.pair; c1.pb = t.pb + bv; c1.pe = t.pe; c1.tb = t.tb + bh; c1.te = t.te;
+  c1.cbegin = bp.component; c1.cend = t.cend; c1.score_remaining = bp.score_reverse;
+  wfb_dispatch_child(c0, ops, sink, pair_status);
+  wfb_dispatch_child(c1, ops, sink, pair_status);
+}
+
 WFB_KERNEL_LB(wfb_break_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, const WfbTask* tasks, int ntasks, int* task_counter, const WfbPairDesc* pairs,
            const uint8_t* seq, int32_t* ws_all, long long ws_stride /* ints per CTA */, int W, WfbPen pen,
            WfbQueue q_break, WfbQueue q_base, char* ops_all, int* pair_status, WfbCounters* counters, WfbTaskLog* tasklog) {
   WFB_KERNEL_PROLOGUE
-  WFB_SHARED WfbBreakShared sh;
-  WFB_SHARED int sh_st[2];
-  WFB_SHARED int sh_ak[2];
+  WFB_SHARED WfbBreakCtaShared S;
   int32_t* const ws = ws_all + (long long)bid * ws_stride;
+  WfbSink sink;
+  sink.q_break = q_break; sink.q_base = q_base; sink.persistent = 0;
+  sink.pq.tasks = nullptr; sink.pq.ready = nullptr; sink.pq.head = nullptr; sink.pq.tail = nullptr; sink.pq.outstanding = nullptr;
+  sink.pq.error = nullptr; sink.pq.cap = 0;
   WfbAcc acc;
   acc.cells = acc.overlap = acc.matches = acc.steps = 0;
   unsigned long long ntask_done = 0;
   for (;;) {
     WFB_SYNC();
-    if (WFB_TID == 0) sh.task_idx = wfb_atomic_add(task_counter, 1);
+    if (WFB_TID == 0) S.sh.task_idx = wfb_atomic_add(task_counter, 1);
     WFB_SYNC();
-    const int ti = sh.task_idx;
+    const int ti = S.sh.task_idx;
     if (ti >= ntasks) break;
-    const WfbTask t = tasks[ti];
-    const WfbPairDesc pd = pairs[t.pair];
-    char* const ops = ops_all + pd.ops_off;
-    const int plen = t.pe - t.pb, tlen = t.te - t.tb;
     ntask_done++;
-    const long long tl_t0 = tasklog ? wfb_globaltimer() : 0;
-    const unsigned long long tl_s0 = acc.steps;
-    /* trivial cases, wavefront_bialign.c:1160-1165 */
-    if (tlen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'D', plen); continue; }
-    if (plen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'I', tlen); continue; }
-    /* sequence views: forward reads the forward copies, reverse the reversed copies
-     * (wavefront_sequences.c:288-295) */
-    const uint8_t* pf = seq + pd.p_off + t.pb;
-    const uint8_t* tf = seq + pd.t_off + t.tb;
-    const uint8_t* pr = seq + pd.prev_off + (pd.plen - t.pe);
-    const uint8_t* tr = seq + pd.trev_off + (pd.tlen - t.te);
-    const int R = pen.R;
-    const int kshift = plen + 1;
-    WfbAllocFixed af, ar;
-    af.W = ar.W = W;
-    af.kalign = ar.kalign = kshift & 3; /* dirbase = (multiple of 8) + kshift */
-    af.dirbase = kshift;
-    ar.dirbase = R * 5 * W + kshift;
-    wfb_ring_reset(sh.ring[0], R);
-    wfb_ring_reset(sh.ring[1], R);
-    for (int i = WFB_TID; i < WFB_RMAX * 5; i += WFB_NT) sh.os.found[i] = INT_MAX;
-    if (WFB_TID < (WFB_RMAX * 5 + 31) / 32) sh.os.hitmask[WFB_TID] = 0;
-    if (WFB_TID == 0) {
-      for (int d = 0; d < 2; ++d) for (int j = 0; j < 3; ++j) sh.red_maxak[d][j] = 0;
-      sh.bp.score = INT_MAX;
-      sh.os.ncand = 0;
-    }
-    WFB_SYNC();
-    if (WFB_TID == 0) {
-      /* wavefront_bialign_init :114-143: reverse aligner swaps begin/end components */
-      int ob[5];
-      af(0, 0, 0, ob);
-      wfb_init_score0(sh.ring[0], ws, ob[t.cbegin], t.cbegin, t.cend, pf, tf, plen, tlen, &sh_st[0], &sh_ak[0], acc);
-      ar(0, 0, 0, ob);
-      wfb_init_score0(sh.ring[1], ws, ob[t.cend], t.cend, t.cbegin, pr, tr, plen, tlen, &sh_st[1], &sh_ak[1], acc);
-    }
-    WFB_SYNC();
-    int status = WFB_ST_OK; /* != OK => a direction reached the end (or is unreachable) */
-    int score_reached = 0;
-    int score_forward = 0, score_reverse = 0;
-    int forward_max_ak = sh_ak[0], reverse_max_ak = sh_ak[1];
-    int null_f = 0, null_r = 0;
-    if (sh_st[0] != WFB_ST_OK) { status = sh_st[0]; score_reached = 0; }
-    else if (sh_st[1] != WFB_ST_OK) { status = sh_st[1]; score_reached = 0; }
-    const int max_antidiagonal = plen + tlen - 1;
-    bool last_wf_forward = false;
-    int max_ak = 0;
-    /* phase 1 (:1010-1043): alternate until the furthest points of both directions may collide */
-    while (status == WFB_ST_OK) {
-      if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
-      ++score_forward;
-      int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
-      if (forward_max_ak < max_ak) forward_max_ak = max_ak;
-      last_wf_forward = true;
-      if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
-      if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
-      ++score_reverse;
-      st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
-      if (reverse_max_ak < max_ak) reverse_max_ak = max_ak;
-      last_wf_forward = false;
-      if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
-    }
-    /* phase 2 (:1045-1079): advance while scanning for overlaps */
-    const int gap_opening = max(pen.o1, pen.o2);
-    while (status == WFB_ST_OK) {
-      if (last_wf_forward) {
-        const int min_score_reverse = (score_reverse > pen.scope - 1) ? score_reverse - (pen.scope - 1) : 0;
-        if (score_forward + min_score_reverse - gap_opening >= sh.bp.score) break;
-        wfb_overlap(sh.ring[0], ws, sh.ring[1], ws, pen, score_forward, score_reverse, true, plen, tlen, &sh.bp, &sh.os, acc);
-        ++score_reverse;
-        const int st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
-        if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
-      }
-      const int min_score_forward = (score_forward > pen.scope - 1) ? score_forward - (pen.scope - 1) : 0;
-      if (min_score_forward + score_reverse - gap_opening >= sh.bp.score) break;
-      wfb_overlap(sh.ring[1], ws, sh.ring[0], ws, pen, score_reverse, score_forward, false, plen, tlen, &sh.bp, &sh.os, acc);
-      ++score_forward;
-      const int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
-      if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
-      last_wf_forward = true;
-    }
-    if (tasklog && WFB_TID == 0) {
-      WfbTaskLog tl;
-      tl.t0 = tl_t0; tl.t1 = wfb_globaltimer(); tl.smid = wfb_smid(); tl.steps = (int)(acc.steps - tl_s0);
-      tl.score_f = score_forward; tl.score_r = score_reverse; tl.plen = plen; tl.tlen = tlen; tl.status = status; tl.pad_ = 0;
-      tasklog[ti] = tl;
-    }
-    if (status != WFB_ST_OK) {
-      /* wavefront_bialign_find_breakpoint_exception :1083-1110 */
-      if (WFB_TID == 0) {
-        if (status == WFB_ST_END_REACHED && score_reached <= WFB_RECOVERY_MIN_SCORE) {
-          WfbTask c = t;
-          c.score_remaining = 0;
-          wfb_push(q_base, c, pair_status);
-        } else {
-          pair_status[t.pair] = WFB_PAIR_UNATTAINABLE;
-        }
-      }
-      continue;
-    }
-    /* both halves, :1188-1212 */
-    const WfbBreakpoint bp = sh.bp;
-    const int bh = bp.offset_forward, bv = bp.offset_forward - bp.k_forward;
-    WfbTask c0, c1;
-    c0.pair = t.pair; c0.pb = t.pb; c0.pe = t.pb + bv; c0.tb = t.tb; c0.te = t.tb + bh;
-    c0.cbegin = t.cbegin; c0.cend = bp.component; c0.score_remaining = bp.score_forward;
-    c1.pair = t.pair; c1.pb = t.pb + bv; c1.pe = t.pe; c1.tb = t.tb + bh; c1.te = t.te;
-    c1.cbegin = bp.component; c1.cend = t.cend; c1.score_remaining = bp.score_reverse;
-    wfb_dispatch_child(c0, ops, q_break, q_base, pair_status);
-    wfb_dispatch_child(c1, ops, q_break, q_base, pair_status);
+    wfb_break_task(S, tasks[ti], ti, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, tasklog);
   }
   /* counters */
   {
@@ -971,6 +1027,71 @@ struct WfbBaseShared {
   int nruns, bt_err;
 };
 
+/* One base sub-problem on one CTA: wavefront_bialign_base (wavefront_bialign.c:159-189). */
+WFB_DEV void wfb_base_task(WfbBaseShared& sh, const WfbTask t, const WfbPairDesc* pairs, const uint8_t* seq, int32_t* arena,
+                           long long arena_stride, WfbBaseMeta* log, int score_cap, WfbRun* runs, int maxruns, const WfbPen& pen,
+                           char* ops_all, int* pair_status, WfbAcc& acc) {
+  const WfbPairDesc pd = pairs[t.pair];
+  char* const ops = ops_all + pd.ops_off;
+  const int plen = t.pe - t.pb, tlen = t.te - t.tb;
+  if (tlen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'D', plen); return; }
+  if (plen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'I', tlen); return; }
+  const uint8_t* pf = seq + pd.p_off + t.pb;
+  const uint8_t* tf = seq + pd.t_off + t.tb;
+  const int R = pen.R;
+  wfb_ring_reset(sh.ring, R);
+  if (WFB_TID == 0) { sh.red_maxak[0] = sh.red_maxak[1] = sh.red_maxak[2] = 0; }
+  WFB_SYNC();
+  WfbAllocBump ab;
+  ab.runflag = nullptr; ab.runbias = 0;
+  ab.bump = 1; /* cell 0 = the score-0 wavefront */
+  if (WFB_TID == 0) {
+    wfb_init_score0(sh.ring, arena, 0, t.cbegin, t.cend, pf, tf, plen, tlen, &sh.st0, &sh.ak0, acc);
+    for (int c = 0; c < 5; ++c) {
+      WfbBaseMeta m;
+      m.lo = 0; m.hi = 0; m.boff = 0; m.ex = (c == t.cbegin);
+      log[c] = m;
+    }
+  }
+  WFB_SYNC();
+  int status = sh.st0;
+  int score = 0, num_null = 0, max_ak = 0;
+  /* wavefront_unialign, wavefront_unialign.c:251-270 */
+  while (status == WFB_ST_OK) {
+    ++score;
+    if (score > score_cap || (long long)ab.bump + 5LL * (2 * score + 3) > arena_stride) { status = -1; break; }
+    status = wfb_step(sh.ring, arena, pen, score, pf, tf, plen, tlen, t.cend, num_null, ab, sh.red_maxak, sh.red_end, max_ak, acc);
+    if (WFB_TID == 0) {
+      const int slot = score % R;
+      for (int c = 0; c < 5; ++c) {
+        WfbBaseMeta m;
+        m.lo = sh.ring.lo[slot][c]; m.hi = sh.ring.hi[slot][c]; m.boff = sh.ring.boff[slot][c]; m.ex = sh.ring.ex[slot][c];
+        log[score * 5 + c] = m;
+      }
+    }
+  }
+  if (status != WFB_ST_END_REACHED) {
+    if (WFB_TID == 0) pair_status[t.pair] = (status == -1) ? WFB_PAIR_BASE_SCORE_CAP : WFB_PAIR_UNATTAINABLE;
+    return;
+  }
+  if (WFB_TID == 0) {
+    int nr = 0;
+    sh.bt_err = wfb_backtrace(log, arena, score + 1, pen, t.cbegin, t.cend, plen, tlen, score, tlen - plen, tlen, t.pb + t.tb, runs, maxruns, &nr);
+    sh.nruns = nr;
+  }
+  WFB_SYNC();
+  if (sh.bt_err) {
+    if (WFB_TID == 0) pair_status[t.pair] = WFB_PAIR_BACKTRACE;
+    return;
+  }
+  const int nr = sh.nruns;
+  for (int r = 0; r < nr; ++r) {
+    const WfbRun ru = runs[r];
+    const int stride = (ru.op == 'M' || ru.op == 'X') ? 2 : 1;
+    for (int j = WFB_TID; j < ru.count; j += WFB_NT) ops[ru.idx + j * stride] = (char)ru.op;
+  }
+}
+
 WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter, const WfbPairDesc* pairs,
            const uint8_t* seq, int32_t* arena_all, long long arena_stride /* ints per CTA */, WfbBaseMeta* log_all,
            int score_cap, WfbRun* runs_all, int maxruns, WfbPen pen, char* ops_all, int* pair_status,
@@ -989,67 +1110,8 @@ WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter,
     WFB_SYNC();
     const int ti = sh.task_idx;
     if (ti >= ntasks) break;
-    const WfbTask t = tasks[ti];
-    const WfbPairDesc pd = pairs[t.pair];
-    char* const ops = ops_all + pd.ops_off;
-    const int plen = t.pe - t.pb, tlen = t.te - t.tb;
     ntask_done++;
-    if (tlen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'D', plen); continue; }
-    if (plen == 0) { wfb_fill_ops(ops, t.pb, t.tb, 'I', tlen); continue; }
-    const uint8_t* pf = seq + pd.p_off + t.pb;
-    const uint8_t* tf = seq + pd.t_off + t.tb;
-    const int R = pen.R;
-    wfb_ring_reset(sh.ring, R);
-    if (WFB_TID == 0) { sh.red_maxak[0] = sh.red_maxak[1] = sh.red_maxak[2] = 0; }
-    WFB_SYNC();
-    WfbAllocBump ab;
-    ab.runflag = nullptr; ab.runbias = 0;
-    ab.bump = 1; /* cell 0 = the score-0 wavefront */
-    if (WFB_TID == 0) {
-      wfb_init_score0(sh.ring, arena, 0, t.cbegin, t.cend, pf, tf, plen, tlen, &sh.st0, &sh.ak0, acc);
-      for (int c = 0; c < 5; ++c) {
-        WfbBaseMeta m;
-        m.lo = 0; m.hi = 0; m.boff = 0; m.ex = (c == t.cbegin);
-        log[c] = m;
-      }
-    }
-    WFB_SYNC();
-    int status = sh.st0;
-    int score = 0, num_null = 0, max_ak = 0;
-    /* wavefront_unialign, wavefront_unialign.c:251-270 */
-    while (status == WFB_ST_OK) {
-      ++score;
-      if (score > score_cap || (long long)ab.bump + 5LL * (2 * score + 3) > arena_stride) { status = -1; break; }
-      status = wfb_step(sh.ring, arena, pen, score, pf, tf, plen, tlen, t.cend, num_null, ab, sh.red_maxak, sh.red_end, max_ak, acc);
-      if (WFB_TID == 0) {
-        const int slot = score % R;
-        for (int c = 0; c < 5; ++c) {
-          WfbBaseMeta m;
-          m.lo = sh.ring.lo[slot][c]; m.hi = sh.ring.hi[slot][c]; m.boff = sh.ring.boff[slot][c]; m.ex = sh.ring.ex[slot][c];
-          log[score * 5 + c] = m;
-        }
-      }
-    }
-    if (status != WFB_ST_END_REACHED) {
-      if (WFB_TID == 0) pair_status[t.pair] = (status == -1) ? WFB_PAIR_BASE_SCORE_CAP : WFB_PAIR_UNATTAINABLE;
-      continue;
-    }
-    if (WFB_TID == 0) {
-      int nr = 0;
-      sh.bt_err = wfb_backtrace(log, arena, score + 1, pen, t.cbegin, t.cend, plen, tlen, score, tlen - plen, tlen, t.pb + t.tb, runs, maxruns, &nr);
-      sh.nruns = nr;
-    }
-    WFB_SYNC();
-    if (sh.bt_err) {
-      if (WFB_TID == 0) pair_status[t.pair] = WFB_PAIR_BACKTRACE;
-      continue;
-    }
-    const int nr = sh.nruns;
-    for (int r = 0; r < nr; ++r) {
-      const WfbRun ru = runs[r];
-      const int stride = (ru.op == 'M' || ru.op == 'X') ? 2 : 1;
-      for (int j = WFB_TID; j < ru.count; j += WFB_NT) ops[ru.idx + j * stride] = (char)ru.op;
-    }
+    wfb_base_task(sh, tasks[ti], pairs, seq, arena, arena_stride, log, score_cap, runs, maxruns, pen, ops_all, pair_status, acc);
   }
   {
     unsigned long long m = acc.matches;
@@ -1061,6 +1123,108 @@ WFB_KERNEL(wfb_base_kernel, const WfbTask* tasks, int ntasks, int* task_counter,
       wfb_atomic_add64(&counters->base_cells, acc.cells);
       wfb_atomic_add64(&counters->base_score_steps, acc.steps);
       wfb_atomic_add64(&counters->base_tasks, ntask_done);
+    }
+  }
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Persistent driver: ONE launch drains the whole recursion tree of a batch. Resident CTAs claim slots of a
+ * global queue in order, wait for the slot to be published, run the task (breakpoint or base, decided by
+ * score_remaining like wavefront_bialign_alignment :1166), publish its children into later slots, and exit
+ * when no task is outstanding. Removes the per-level launch barrier of the level-synchronous driver: a CTA
+ * that finishes early immediately continues with sub-problems of other alignments.
+ * Requires every CTA of the grid to be resident (the host sizes the grid from the occupancy query).
+ * ---------------------------------------------------------------------------------------------- */
+struct WfbPersistShared {
+  WfbBreakCtaShared brk;
+  WfbBaseShared base;
+  int slot;
+};
+
+WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, WfbPQueue q, const WfbPairDesc* pairs, const uint8_t* seq,
+              int32_t* ws_all, long long ws_stride, int W, int32_t* arena_all, long long arena_stride, WfbBaseMeta* log_all, int score_cap,
+              WfbRun* runs_all, int maxruns, WfbPen pen, char* ops_all, int* pair_status, WfbCounters* counters) {
+  WFB_KERNEL_PROLOGUE
+  WFB_SHARED WfbPersistShared S;
+  int32_t* const ws = ws_all + (long long)bid * ws_stride;
+  int32_t* const arena = arena_all + (long long)bid * arena_stride;
+  WfbBaseMeta* const log = log_all + (long long)bid * (score_cap + 1) * 5;
+  WfbRun* const runs = runs_all + (long long)bid * maxruns;
+  WfbSink sink;
+  sink.persistent = 1;
+  sink.pq = q;
+  sink.q_break.tasks = nullptr; sink.q_break.count = nullptr; sink.q_break.cap = 0;
+  sink.q_base = sink.q_break;
+  WfbAcc acc, acc_base;
+  acc.cells = acc.overlap = acc.matches = acc.steps = 0;
+  acc_base = acc;
+  unsigned long long n_break = 0, n_base = 0;
+  for (;;) {
+    WFB_SYNC();
+    if (WFB_TID == 0) {
+      int slot = wfb_atomic_add(q.head, 1);
+      if (slot >= q.cap) {
+        slot = -1;
+      } else {
+#ifndef WFB_EMU
+        unsigned spins = 0;
+        while (atomicAdd(&q.ready[slot], 0) == 0) {
+          if (atomicAdd(q.outstanding, 0) <= 0 || atomicAdd(q.error, 0) != 0) { slot = -1; break; }
+          __nanosleep(256);
+          if (++spins > (1u << 26)) { *q.error = 2; slot = -1; break; } /* watchdog (~20 s) */
+        }
+        __threadfence();
+#else
+        if (q.ready[slot] == 0) slot = -1; /* serial emulation: an unpublished slot means the tree is exhausted */
+#endif
+      }
+      S.slot = slot;
+    }
+    WFB_SYNC();
+    const int slot = S.slot;
+    if (slot < 0) break;
+    WfbTask t;
+#ifndef WFB_EMU
+    { /* read through L2: the task was published by another SM */
+      const int* src = (const int*)&q.tasks[slot];
+      int* dst = (int*)&t;
+#pragma unroll
+      for (int i = 0; i < (int)(sizeof(WfbTask) / sizeof(int)); ++i) dst[i] = __ldcg(src + i);
+    }
+#else
+    t = q.tasks[slot];
+#endif
+    if (t.score_remaining <= WFB_FALLBACK_MIN_SCORE && t.pe > t.pb && t.te > t.tb) {
+      n_base++;
+      wfb_base_task(S.base, t, pairs, seq, arena, arena_stride, log, score_cap, runs, maxruns, pen, ops_all, pair_status, acc_base);
+    } else {
+      n_break++;
+      wfb_break_task(S.brk, t, slot, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, nullptr);
+    }
+    WFB_SYNC();
+    if (WFB_TID == 0) {
+#ifndef WFB_EMU
+      __threadfence();
+#endif
+      wfb_atomic_add(q.outstanding, -1);
+    }
+  }
+  {
+    unsigned long long m = acc.matches, mb = acc_base.matches;
+#ifndef WFB_EMU
+    for (int o = 16; o > 0; o >>= 1) { m += __shfl_down_sync(0xffffffffu, m, o); mb += __shfl_down_sync(0xffffffffu, mb, o); }
+#endif
+    if (wfb_lane() == 0 && m) wfb_atomic_add64(&counters->extend_matches, m);
+    if (wfb_lane() == 0 && mb) wfb_atomic_add64(&counters->base_extend_matches, mb);
+    if (wfb_lane() == 0 && acc.overlap) wfb_atomic_add64(&counters->overlap_tests, acc.overlap);
+    if (WFB_TID == 0) {
+      wfb_atomic_add64(&counters->cells, acc.cells);
+      wfb_atomic_add64(&counters->score_steps, acc.steps);
+      wfb_atomic_add64(&counters->break_tasks, n_break);
+      wfb_atomic_add64(&counters->base_cells, acc_base.cells);
+      wfb_atomic_add64(&counters->base_score_steps, acc_base.steps);
+      wfb_atomic_add64(&counters->base_tasks, n_base);
     }
   }
 }

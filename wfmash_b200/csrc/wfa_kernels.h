@@ -155,6 +155,7 @@ WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
   return n;
 #else
   if (limit <= 0) return 0;
+  if (wfb_ldg8(p) != wfb_ldg8(t)) return 0; /* 3 of 4 cells of an unrelated diagonal stop right here */
   const uintptr_t pa = (uintptr_t)p, ta = (uintptr_t)t;
   const uint32_t* pw = (const uint32_t*)(pa & ~(uintptr_t)3);
   const uint32_t* tw = (const uint32_t*)(ta & ~(uintptr_t)3);
@@ -307,15 +308,19 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     } else {                                                                                              \
       mx = WFB_OFFSET_NULL;                                                                               \
     }                                                                                                     \
-    /* I keeps v of an in-bounds source, D keeps h: one unsigned compare decides in-bounds */             \
-    if (ex_i1 && (uint32_t)ins1 <= (uint32_t)tlen && (uint32_t)(ins1 - k_) <= (uint32_t)plen) { tlo[WFB_I1] = min(tlo[WFB_I1], k_); thi[WFB_I1] = max(thi[WFB_I1], k_); } \
-    if (ex_i2 && (uint32_t)ins2 <= (uint32_t)tlen && (uint32_t)(ins2 - k_) <= (uint32_t)plen) { tlo[WFB_I2] = min(tlo[WFB_I2], k_); thi[WFB_I2] = max(thi[WFB_I2], k_); } \
-    if (ex_d1 && (uint32_t)del1 <= (uint32_t)tlen && (uint32_t)(del1 - k_) <= (uint32_t)plen) { tlo[WFB_D1] = min(tlo[WFB_D1], k_); thi[WFB_D1] = max(thi[WFB_D1], k_); } \
-    if (ex_d2 && (uint32_t)del2 <= (uint32_t)tlen && (uint32_t)(del2 - k_) <= (uint32_t)plen) { tlo[WFB_D2] = min(tlo[WFB_D2], k_); thi[WFB_D2] = max(thi[WFB_D2], k_); } \
-    if (k_ == ak_end) /* hand the end component's offset on the final diagonal to the termination test */ \
-      red_end[par] = cend == WFB_M ? mx : cend == WFB_I1 ? ins1 : cend == WFB_I2 ? ins2 : cend == WFB_D1 ? del1 : del2; \
+    /* an I value keeps the v of its in-bounds source and a D value keeps the h, null-ish values are hugely      \
+     * negative: ONE unsigned compare decides what wavefront_compute_trim_ends (:594-596) tests with two */      \
+    if (ex_i1 && (uint32_t)ins1 <= (uint32_t)tlen) { tlo[WFB_I1] = min(tlo[WFB_I1], k_); thi[WFB_I1] = max(thi[WFB_I1], k_); } \
+    if (ex_i2 && (uint32_t)ins2 <= (uint32_t)tlen) { tlo[WFB_I2] = min(tlo[WFB_I2], k_); thi[WFB_I2] = max(thi[WFB_I2], k_); } \
+    if (ex_d1 && (uint32_t)(del1 - k_) <= (uint32_t)plen) { tlo[WFB_D1] = min(tlo[WFB_D1], k_); thi[WFB_D1] = max(thi[WFB_D1], k_); } \
+    if (ex_d2 && (uint32_t)(del2 - k_) <= (uint32_t)plen) { tlo[WFB_D2] = min(tlo[WFB_D2], k_); thi[WFB_D2] = max(thi[WFB_D2], k_); } \
     (OUT_M) = mx; (OUT_I1) = ins1; (OUT_I2) = ins2; (OUT_D1) = del1; (OUT_D2) = del2;                       \
   }
+
+  /* hand the end component's offset on the final diagonal to the termination test (wavefront_termination.c:37-114) */
+#define WFB_END_HANDOFF(K, VM, VI1, VI2, VD1, VD2)                                                          \
+  if ((K) == ak_end && cend >= 0)                                                                          \
+    red_end[par] = cend == WFB_M ? (VM) : cend == WFB_I1 ? (VI1) : cend == WFB_I2 ? (VI2) : cend == WFB_D1 ? (VD1) : (VD2);
 
   const int kalign = alloc.kalign;
 #ifndef WFB_EMU
@@ -355,6 +360,12 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
         WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
         WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
         WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+        if ((unsigned)(ak_end - k0) < 4u) { /* constant indices keep the arrays in registers */
+          WFB_END_HANDOFF(k0 + 0, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+          WFB_END_HANDOFF(k0 + 1, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+          WFB_END_HANDOFF(k0 + 2, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+          WFB_END_HANDOFF(k0 + 3, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+        }
         *(int4*)(basep + ob[WFB_M] + k0) = make_int4(rm[0], rm[1], rm[2], rm[3]);
         if (ex_i1) *(int4*)(basep + ob[WFB_I1] + k0) = make_int4(ri1[0], ri1[1], ri1[2], ri1[3]);
         if (ex_i2) *(int4*)(basep + ob[WFB_I2] + k0) = make_int4(ri2[0], ri2[1], ri2[2], ri2[3]);
@@ -368,6 +379,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
                    wfb_get(basep, m_open2, k + 1), wfb_get(basep, i1_ext, k - 1), wfb_get(basep, i2_ext, k - 1),
                    wfb_get(basep, d1_ext, k + 1), wfb_get(basep, d2_ext, k + 1), wfb_get(basep, m_misms, k),
                    rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+          WFB_END_HANDOFF(k, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
           basep[ob[WFB_M] + k] = rm[0];
           if (ex_i1) basep[ob[WFB_I1] + k] = ri1[0];
           if (ex_i2) basep[ob[WFB_I2] + k] = ri2[0];
@@ -383,6 +395,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
       WFB_CELL(k, wfb_get(basep, m_open1, k - 1), wfb_get(basep, m_open1, k + 1), wfb_get(basep, m_open2, k - 1),
                wfb_get(basep, m_open2, k + 1), wfb_get(basep, i1_ext, k - 1), wfb_get(basep, i2_ext, k - 1),
                wfb_get(basep, d1_ext, k + 1), wfb_get(basep, d2_ext, k + 1), wfb_get(basep, m_misms, k), rm, ri1, ri2, rd1, rd2)
+      WFB_END_HANDOFF(k, rm, ri1, ri2, rd1, rd2)
       basep[ob[WFB_M] + k] = rm;
       if (ex_i1) basep[ob[WFB_I1] + k] = ri1;
       if (ex_i2) basep[ob[WFB_I2] + k] = ri2;
@@ -391,6 +404,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     }
   }
 #undef WFB_CELL
+#undef WFB_END_HANDOFF
   /* trimmed [lo,hi] of each component = min / max diagonal holding an in-bounds offset */
   {
     const int lane = wfb_lane();

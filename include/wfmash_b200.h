@@ -128,6 +128,50 @@ typedef struct {
 int wfb_align_endsfree_batch(wfb_aligner_t*, const wfb_endsfree_pair_t* pairs, int32_t n, int32_t term_group, char* ops,
                              int64_t ops_cap, wfb_aln_result_t* results);
 
+/* Whole-record replacement of wflign::wavefront::do_biwfa_alignment (src/common/wflign/src/wflign.cpp:108-483,
+ * PAF branch) for a BATCH of mapping records: main end-to-end biWFA (wfb_align_batch), head and tail patching
+ * through ends-free alignments (wfb_align_endsfree_batch; wflign.cpp:167-418), try_swap_start/end_pattern
+ * (wflign_swizzle.cpp:220-300), trim_indels + process_compressed_cigar + write_alignment_paf
+ * (wflign_patch.cpp:139-283, 2611-2724). Argument meaning follows the reference's parameter list (wflign.cpp:108-133);
+ * the call site is Aligner::processAlignment (src/align/include/computeAlignments.hpp:695-720). */
+typedef struct {
+  const char* query_name;
+  const char* query;          /* strand-corrected, upper-cased query slice (text)  */
+  uint64_t query_total_length;
+  uint64_t query_offset;
+  uint64_t query_length;
+  int32_t query_is_rev;
+  int32_t chain_id;
+  const char* target_name;
+  const char* target;         /* upper-cased target slice (pattern)                */
+  uint64_t target_total_length;
+  uint64_t target_offset;
+  uint64_t target_length;
+  int32_t chain_length;
+  int32_t chain_pos;
+  float mashmap_estimated_identity;
+  int32_t reserved_;
+} wfb_record_t;
+
+typedef struct {
+  int32_t disable_chain_patching; /* wflign.cpp:125 */
+  int32_t term_group;             /* 1 / 8 / 16, see wfb_align_endsfree_batch; 0 = 8 */
+  float min_identity;             /* wflign_patch.cpp:2624-2626 filters */
+  float min_block_identity;
+  uint64_t min_alignment_length;
+} wfb_paf_params_t;
+
+#define WFB_REC_WRITTEN 0       /* a PAF line was produced                                                    */
+#define WFB_REC_FILTERED 1      /* aligned but rejected by the identity / length filters (nothing written)     */
+#define WFB_REC_UNALIGNED 2     /* main alignment status != 0: the reference returns early (wflign.cpp:150-152) */
+#define WFB_REC_PATCH_CAP (-1)  /* a patch alignment exceeded the ends-free kernel's score/arena caps; no line */
+
+/* out receives the PAF lines ('\n'-terminated) of records 0..n-1 back to back; line_offset[n+1] delimits them
+ * (empty for records that produce no line); rec_status[n] = WFB_REC_*. WFB_ECAP if out_cap is too small
+ * (*out_len then holds the required size). */
+int wfb_biwfa_paf_batch(wfb_aligner_t*, const wfb_record_t* recs, int32_t n, const wfb_paf_params_t* params, char* out,
+                        int64_t out_cap, int64_t* out_len, int64_t* line_offset, int32_t* rec_status, wfb_align_stats_t* stats);
+
 /* Device memory helpers so callers without a CUDA binding (ctypes) can stage inputs. */
 void* wfb_device_malloc(int device, uint64_t bytes);
 void wfb_device_free(int device, void* p);

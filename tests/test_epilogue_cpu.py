@@ -1,0 +1,38 @@
+"""CPU check of the a14 host logic (wfmash_b200/csrc/epilogue.cu: erosion, junction merge, swizzles, trimming, PAF
+metrics). The alignments themselves need the GPU; here the kernel bodies run under the single-thread host emulation
+of tests/emu (TEST INFRASTRUCTURE, -DWFB_EMU) in a subprocess, so that the record-level driver can be compared with
+the committed reference PAF fixture without a device. The product library is never replaced by this build."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from tests import util
+
+SCRIPT = r"""
+import json, sys
+sys.path.insert(0, %(root)r)
+import wfmash_b200 as wb
+from tests import util
+recs = util.paf_records()
+gold = util.paf_golden()
+al = wb.Aligner(0, penalties=tuple(gold["penalties"]))
+bad = []
+for kw, want in zip(gold["filter_sets"], gold["lines"]):
+    lines, status = al.biwfa_paf_batch(recs, term_group=gold["term_group"], **kw)
+    bad += [(i, str(kw)) for i, (g, w) in enumerate(zip(lines, want)) if g.decode() != w]
+print(json.dumps({"bad": bad, "n": len(recs)}))
+"""
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_record_epilogue_matches_reference_fixture_under_emulation():
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": util.ROOT}], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["n"] == 63 and res["bad"] == []

@@ -355,3 +355,23 @@ def test_ends_free_patch_alignments_match_oracle_and_reference(wb, oracle):
             if G == 8 and ref is not None:   # oracle/_ref is compiled with -march=x86-64-v3 (AVX2 kernels)
                 st2 = ref.ref_wfa_endsfree(p, len(p), pbf, pef, t, len(t), tbf, tef, *util.WFMASH_PEN, 1, buf, len(buf), ctypes.byref(n), ctypes.byref(sc))
                 assert st2 == 0 and buf.raw[: n.value] == r.ops
+
+
+def test_do_biwfa_alignment_paf_lines_match_reference(wb):
+    # a14: whole-record parity. The fixture holds the PAF text written by the unmodified reference do_biwfa_alignment
+    # (AVX2 build -> term_group 8) for tests.util.paf_records(); main biWFA, head / tail patches, swizzles, trimming,
+    # identity metrics and the filters all have to agree for the lines to be byte-identical.
+    recs = util.paf_records()
+    gold = util.paf_golden()
+    al = wb.Aligner(0, penalties=tuple(gold["penalties"]))
+    R = util.load_wflign_ref()
+    for kw, lines_ref in zip(gold["filter_sets"], gold["lines"]):
+        lines, status = al.biwfa_paf_batch(recs, term_group=gold["term_group"], **kw)
+        assert wb.REC_PATCH_CAP not in status
+        for i, (got, want) in enumerate(zip(lines, lines_ref)):
+            assert got.decode() == want, (i, kw, got[:200], want[:200])
+            assert (status[i] == wb.REC_WRITTEN) == bool(want)
+        if R is not None:  # live differential against the compiled reference when it travelled with the snapshot
+            for r, got in zip(recs[:20], lines[:20]):
+                assert got == util.ref_paf(R, r, **kw)
+    al.close()

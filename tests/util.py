@@ -6,6 +6,8 @@ import os
 import random
 import subprocess
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 GOLDEN_PEN = (4, 6, 2, 24, 1)   # penalties of the reference's wfa.utest vectors
@@ -131,3 +133,92 @@ def random_pairs(n, seed, lengths=(1, 5, 50, 101, 150, 400, 1000, 3000), rates=(
             a = "A"
         pairs.append((a.encode(), b.encode()))
     return pairs
+
+
+# ---- a14: record-level do_biwfa_alignment (PAF) ------------------------------------------------------------------
+
+def paf_records():
+    """Deterministic mapping records for the do_biwfa_alignment parity tests (shared by tests/golden/make_paf_golden.py
+    and the tests, so the committed fixture lines index into this list)."""
+    from wfmash_b200 import synth
+    recs = []
+    seed = 100
+    for (n, lo, hi, divs, pad) in [(12, 50, 400, (0.0, 0.01, 0.05, 0.15), 0), (10, 300, 1500, (0.01, 0.05, 0.1), 100),
+                                   (6, 1000, 3000, (0.02, 0.1), 300)]:
+        for (t, q, _d) in synth.mapping_records(n, seed, lo, hi, divs, pad=pad):
+            i = len(recs)
+            recs.append(dict(query_name=f"q{i}", target_name=f"t{i}", query=q, target=t, query_total_length=len(q) + 1000 + i,
+                             query_offset=17 * i, target_total_length=len(t) + 5000, target_offset=31 * i, query_is_rev=(i % 3 == 0),
+                             mashmap_estimated_identity=0.9 + 0.001 * i, chain_id=i, chain_length=(i % 4), chain_pos=1))
+        seed += 1
+
+    def mk(t, q):
+        i = len(recs)
+        recs.append(dict(query_name=f"Q{i}", target_name=f"T{i}", query=q, target=t, query_total_length=len(q) + 10, query_offset=5,
+                         target_total_length=len(t) + 9, target_offset=3, query_is_rev=bool(i & 1), mashmap_estimated_identity=0.95,
+                         chain_id=3, chain_length=2, chain_pos=1 + (i & 1)))
+    rs = np.random.default_rng(99)
+
+    def rseq(n):
+        return synth.random_seq(n, rs).tobytes()
+    s = rseq(3000)
+    mk(s, s)                                        # identical: one long '=' run, the head patch spans the whole record
+    mk(s[:200], s[:200])
+    mk(b"ACG", b"ACG")                              # <= 3 bases: no patching (wflign.cpp:278)
+    mk(b"ACGT", b"ACTT")
+    mk(b"A", b"C")
+    mk(rseq(500) + s[:600], s[:600])                # leading / trailing deletions and insertions
+    mk(s[:600] + rseq(500), s[:600])
+    mk(s[:600], rseq(300) + s[:600])
+    mk(s[:600], s[:600] + rseq(300))
+    mk(rseq(400), rseq(400))                        # unrelated
+    mk(rseq(100), rseq(900))
+    mk(s[:50] + s[300:1000], s[:1000])              # indels inside the eroded windows
+    mk(s[:1000], s[:950] + s[960:1000])
+    mk(s[:20] + rseq(6000) + s[20:700], s[:700])    # an indel longer than MAX_ERODE_LENGTH inside the head / tail window
+    mk(s[:700], s[:680] + rseq(5000) + s[680:700])
+    for _ in range(20):
+        L = int(rs.integers(5, 1200))
+        q = synth.random_seq(L, rs)
+        t = synth.mutate(q, float(rs.choice([0.0, 0.02, 0.1, 0.3])), rs)
+        padl, padr = int(rs.integers(0, 200)), int(rs.integers(0, 200))
+        t = np.concatenate([synth.random_seq(padl, rs), t, synth.random_seq(padr, rs)]).tobytes()
+        mk(t, q.tobytes())
+    return recs
+
+
+PAF_FILTER_SETS = [dict(), dict(disable_chain_patching=True), dict(min_identity=0.9, min_alignment_length=300, min_block_identity=0.8)]
+
+
+def load_wflign_ref():
+    """oracle/_ref/libwflignref.so: the unmodified reference wflign sources (do_biwfa_alignment) compiled in place."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libwflignref.so")
+    if not os.path.exists(path):
+        return None
+    R = ctypes.CDLL(path)
+    R.ref_do_biwfa_alignment.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
+                                         ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                         ctypes.c_uint64, ctypes.c_float, ctypes.c_uint64, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    return R
+
+
+def ref_paf(R, r, pen=WFMASH_PEN, min_identity=0.0, min_alignment_length=0, min_block_identity=0.0, disable_chain_patching=False):
+    cap = len(r["query"]) + len(r["target"]) + 4096
+    buf = ctypes.create_string_buffer(cap)
+    n = R.ref_do_biwfa_alignment(r["query_name"].encode(), r["query"], r.get("query_total_length", len(r["query"])),
+                                 r.get("query_offset", 0), len(r["query"]), 1 if r.get("query_is_rev") else 0,
+                                 r["target_name"].encode(), r["target"], r.get("target_total_length", len(r["target"])),
+                                 r.get("target_offset", 0), len(r["target"]), pen[0], pen[1], pen[2], pen[3], pen[4],
+                                 1 if disable_chain_patching else 0, min_identity, min_alignment_length, min_block_identity, 0,
+                                 r.get("mashmap_estimated_identity", 0.0), r.get("chain_id", 0), r.get("chain_length", 0),
+                                 r.get("chain_pos", 0), buf, cap)
+    assert n >= 0
+    return buf.raw[:n]
+
+
+def paf_golden():
+    import json
+    with gzip.open(os.path.join(GOLD, "paf_do_biwfa.json.gz"), "rt") as f:
+        return json.load(f)

@@ -41,6 +41,24 @@ class _EfPair(ctypes.Structure):
                 ("text_end_free", ctypes.c_int32)]
 
 
+class _Record(ctypes.Structure):
+    """wfb_record_t: the parameter list of do_biwfa_alignment (src/common/wflign/src/wflign.cpp:108-133)."""
+    _fields_ = [("query_name", ctypes.c_char_p), ("query", ctypes.c_char_p), ("query_total_length", ctypes.c_uint64),
+                ("query_offset", ctypes.c_uint64), ("query_length", ctypes.c_uint64), ("query_is_rev", ctypes.c_int32),
+                ("chain_id", ctypes.c_int32), ("target_name", ctypes.c_char_p), ("target", ctypes.c_char_p),
+                ("target_total_length", ctypes.c_uint64), ("target_offset", ctypes.c_uint64), ("target_length", ctypes.c_uint64),
+                ("chain_length", ctypes.c_int32), ("chain_pos", ctypes.c_int32), ("mashmap_estimated_identity", ctypes.c_float),
+                ("reserved_", ctypes.c_int32)]
+
+
+class _PafParams(ctypes.Structure):
+    _fields_ = [("disable_chain_patching", ctypes.c_int32), ("term_group", ctypes.c_int32), ("min_identity", ctypes.c_float),
+                ("min_block_identity", ctypes.c_float), ("min_alignment_length", ctypes.c_uint64)]
+
+
+REC_WRITTEN, REC_FILTERED, REC_UNALIGNED, REC_PATCH_CAP = 0, 1, 2, -1
+
+
 class AlignStats(ctypes.Structure):
     _fields_ = [("cells", ctypes.c_uint64), ("extend_matches", ctypes.c_uint64), ("overlap_tests", ctypes.c_uint64),
                 ("score_steps", ctypes.c_uint64), ("break_tasks", ctypes.c_uint64), ("base_tasks", ctypes.c_uint64),
@@ -192,6 +210,48 @@ class Aligner:
             raise _err(rc)
         raw = ops.raw
         return [AlignResult(r.status, r.score, raw[r.ops_offset:r.ops_offset + r.ops_len]) for r in res]
+
+
+    def biwfa_paf_batch(self, records, min_identity=0.0, min_alignment_length=0, min_block_identity=0.0,
+                        disable_chain_patching=False, term_group=8):
+        """Batched wflign::wavefront::do_biwfa_alignment, PAF branch (src/common/wflign/src/wflign.cpp:108-483).
+        records: dicts with the reference's parameter names: query_name, query, query_total_length, query_offset,
+        query_is_rev, target_name, target, target_total_length, target_offset, mashmap_estimated_identity, chain_id,
+        chain_length, chain_pos (query_length / target_length are the slice lengths).
+        Returns (lines, status): lines[i] is the PAF line (b"" when none), status[i] one of REC_*."""
+        n = len(records)
+        if n == 0:
+            return [], []
+        arr = (_Record * n)()
+        keep = []
+        for i, r in enumerate(records):
+            q, t = r["query"], r["target"]
+            qn, tn = r["query_name"].encode() if isinstance(r["query_name"], str) else r["query_name"], \
+                r["target_name"].encode() if isinstance(r["target_name"], str) else r["target_name"]
+            keep.append((q, t, qn, tn))
+            arr[i] = _Record(qn, q, r.get("query_total_length", len(q)), r.get("query_offset", 0), len(q),
+                             1 if r.get("query_is_rev", False) else 0, r.get("chain_id", 0), tn, t,
+                             r.get("target_total_length", len(t)), r.get("target_offset", 0), len(t),
+                             r.get("chain_length", 0), r.get("chain_pos", 0), r.get("mashmap_estimated_identity", 0.0), 0)
+        pp = _PafParams(1 if disable_chain_patching else 0, term_group, min_identity, min_block_identity, min_alignment_length)
+        cap = sum(len(k[0]) + len(k[1]) for k in keep) // 2 + 512 * n + 4096
+        offs = (ctypes.c_int64 * (n + 1))()
+        st = (ctypes.c_int32 * n)()
+        stats = AlignStats()
+        out_len = ctypes.c_int64(0)
+        for _ in range(2):
+            out = ctypes.create_string_buffer(cap)
+            rc = self._L.wfb_biwfa_paf_batch(ctypes.c_void_p(self._h), arr, n, ctypes.byref(pp), out, ctypes.c_int64(cap),
+                                             ctypes.byref(out_len), offs, st, ctypes.byref(stats))
+            if rc == -5 and out_len.value > cap:  # WFB_ECAP: retry once with the size the library asked for
+                cap = out_len.value + 16
+                continue
+            break
+        if rc != 0:
+            raise _err(rc)
+        self.last_stats = stats
+        raw = out.raw
+        return [raw[offs[i]:offs[i + 1]] for i in range(n)], list(st)
 
 
 class MinmerStats(ctypes.Structure):

@@ -163,6 +163,66 @@ def run_cpu_sample(recs, target_s, threads):
             "sample": f"first {len(sample)} of {len(recs)} records of the step ({bp} query bp), {dt:.1f} s wall on {threads} threads"}
 
 
+def paf_aligned_bp(lines):
+    """Aligned bp as the reference counts it: sum of qEnd - qStart over the output records (computeAlignments.hpp:481,528)."""
+    bp = 0
+    for ln in lines:
+        if ln:
+            f = ln.split(b"\t", 4)
+            bp += int(f[3]) - int(f[2])
+    return bp
+
+
+def record_path_section(al, recs, cores, with_cpu, cpu_seconds):
+    """Whole-record path (row a14 / boundary b4): do_biwfa_alignment's job — main biWFA, head / tail patch alignments,
+    swizzles, trimming, PAF text — through wfb_biwfa_paf_batch with HOST buffers, next to the unmodified reference
+    do_biwfa_alignment (oracle/_ref/libwflignref.so) on all host threads over a bounded prefix of the same records."""
+    import wfmash_b200 as wb
+    rr = [dict(query_name=f"q{i}", target_name=f"t{i}", query=t_, target=p_, mashmap_estimated_identity=1.0 - d_)
+          for i, (p_, t_, d_) in enumerate(recs)]
+    al.biwfa_paf_batch(rr[: max(8, len(rr) // 16)])  # warm-up (allocations)
+    l0 = wb.launch_count()
+    t0 = time.perf_counter()
+    lines, st = al.biwfa_paf_batch(rr, min_identity=0.0, min_alignment_length=32, min_block_identity=0.1)  # CLI defaults, parse_args.hpp:566-584
+    dt = time.perf_counter() - t0
+    bp = paf_aligned_bp(lines)
+    out = {"metric": "aligned_bp_per_s_record_path", "value": bp / dt, "unit": UNIT, "records": len(rr), "lines_written": sum(1 for x in lines if x),
+           "patch_cap_failures": sum(1 for x in st if x == wb.REC_PATCH_CAP), "aligned_bp": bp, "ms": 1e3 * dt,
+           "main_kernel_ms": al.last_stats.kernel_ms, "gpu_launches": int(wb.launch_count() - l0),
+           "paf_bytes": sum(len(x) for x in lines), "timing": "host wall clock around wfb_biwfa_paf_batch (H2D, three kernel rounds, D2H, PAF text)"}
+    ref = os.path.join(ROOT, "oracle", "_ref", "libwflignref.so")
+    if with_cpu and os.path.exists(ref):
+        R = ctypes.CDLL(ref)
+        R.ref_do_biwfa_alignment.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
+                                             ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                             ctypes.c_uint64, ctypes.c_float, ctypes.c_uint64, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+
+        def one(r):
+            cap = len(r["query"]) + len(r["target"]) + 4096
+            buf = ctypes.create_string_buffer(cap)
+            n = R.ref_do_biwfa_alignment(r["query_name"].encode(), r["query"], len(r["query"]), 0, len(r["query"]), 0, r["target_name"].encode(),
+                                         r["target"], len(r["target"]), 0, len(r["target"]), *PEN, 0, 0.0, 32, 0.1, 0,
+                                         r["mashmap_estimated_identity"], 0, 0, 0, buf, cap)
+            return buf.raw[:max(n, 0)]
+        # same cost model as run_cpu_sample: prefix of the step filling ~cpu_seconds on all threads
+        probe = min(range(len(recs)), key=lambda i: est_score(recs[i]))
+        t1 = time.perf_counter(); one(rr[probe]); unit = (time.perf_counter() - t1) / est_score(recs[probe]) ** 2
+        k, acc = 0, 0.0
+        while k < len(recs) and (k < cores or acc + unit * est_score(recs[k]) ** 2 <= cpu_seconds * cores):
+            acc += unit * est_score(recs[k]) ** 2
+            k += 1
+        t1 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            ref_lines = list(ex.map(one, rr[:k]))
+        dtc = time.perf_counter() - t1
+        out["cpu_reference"] = {"value": paf_aligned_bp(ref_lines) / dtc, "unit": UNIT, "cores": cores, "kind": "reference",
+                                "sample": f"first {k} of {len(rr)} records, {dtc:.1f} s wall on {cores} threads (unmodified do_biwfa_alignment)"}
+        out["lines_identical_to_reference_on_sample"] = bool(all(a == b for a, b in zip(ref_lines, lines[:k])))
+    return out
+
+
 def map_path_section(dev, cores, with_cpu):
     """Path 1 (MashMap 3.5 sketch / index / L1) on a C3-shaped synthetic pangenome slice: 8 haplotypes x 3 Mbp at
     3 % divergence, -k15 -w1k, s=29 (scerevisiae8 parameters). Reported beside the headline."""
@@ -210,25 +270,29 @@ def map_path_section(dev, cores, with_cpu):
     }
     ix.close()
     if with_cpu:
-        # CPU side of addMinmers: the oracle port (exact restatement, identical to the reference on LPA / yeast).
-        # The compiled reference itself (oracle/_ref/libmapref.so) dereferences std::map::end() on some
-        # i.i.d.-random inputs (commonFunc.hpp:521-524, undefined behaviour -> segfault), so it cannot time
-        # synthetic genomes reliably; the port runs the same state machine at the same speed.
+        # CPU side of addMinmers on all host threads (one sequence per thread, like Sketch::build's worker pool,
+        # winSketch.hpp:188-234): the unmodified reference (oracle/_ref/libmapref.so) when it travelled with the
+        # snapshot, else the oracle port (exact restatement of the same state machine).
+        ref = os.path.join(ROOT, "oracle", "_ref", "libmapref.so")
         orc = os.path.join(ROOT, "oracle", "liboracle.so")
-        if os.path.exists(orc):
-            lib = ctypes.CDLL(orc)
-            lib.orc_add_minmers.restype = ctypes.c_int64
+        kind = "reference" if os.path.exists(ref) else ("port" if os.path.exists(orc) else None)
+        if kind:
+            lib = ctypes.CDLL(ref if kind == "reference" else orc)
+            fn = lib.ref_add_minmers if kind == "reference" else lib.orc_add_minmers
+            fn.restype = ctypes.c_int64
             dt = np.dtype([("hash", "<u8"), ("wpos", "<i8"), ("wpos_end", "<i8"), ("seqId", "<i4"), ("strand", "<i2"), ("pad_", "<i2")])
 
             def one(i):
                 o = np.zeros(len(seqs[i]) // 4 + 1000, dtype=dt)
-                return lib.orc_add_minmers(seqs[i], ctypes.c_int64(len(seqs[i])), k, w, ssz, i, ctypes.c_void_p(o.ctypes.data), ctypes.c_int64(len(o)))
+                buf = ctypes.create_string_buffer(seqs[i], len(seqs[i]) + 16)  # the reference upper-cases in place
+                return fn(buf, ctypes.c_int64(len(seqs[i])), k, w, ssz, i, ctypes.c_void_p(o.ctypes.data), ctypes.c_int64(len(o)))
+            one(0)  # warm-up (page-in, the reference's meter set-up)
             t0 = time.perf_counter()
             with ThreadPoolExecutor(max_workers=min(cores, len(seqs))) as ex:
                 list(ex.map(one, range(len(seqs))))
             dtc = time.perf_counter() - t0
-            out["index"]["cpu_port_addMinmers_mbp_per_s"] = bases / dtc / 1e6
-            out["index"]["cpu_port_threads"] = min(cores, len(seqs))
+            out["index"]["cpu_addMinmers"] = {"value": bases / dtc / 1e6, "unit": "Mbp/s", "kind": kind, "cores": min(cores, len(seqs)),
+                                              "sample": f"all {len(seqs)} sequences ({bases} bp), {dtc:.2f} s wall"}
     return out
 
 
@@ -243,6 +307,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (tuning sweeps)")
     ap.add_argument("--no-map", action="store_true", help="skip the mapping-path (path 1) section")
+    ap.add_argument("--no-record", action="store_true", help="skip the whole-record (PAF) section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -357,16 +422,19 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # roofline of the dominant kernel (wfb_break_kernel): algorithmic bytes of SURVEY §8d
-        # = 48 B/cell + 2 B/extended base + 8 B/overlap test, per step, over its CUDA-event time
-        alg_bytes = 48 * stats_d["cells"] + 2 * stats_d["extend_matches"] + 8 * stats_d["overlap_tests"]
+        # roofline of the dominant kernel (wfb_persist_kernel: the whole biWFA recursion tree, breakpoint + base-case
+        # tasks, in one launch): algorithmic bytes of SURVEY §8d = 48 B/cell + 2 B/extended base + 8 B/overlap test
+        # over the cells / extends / overlap tests of BOTH task kinds, per step, over its CUDA-event time
+        alg_bytes = (48 * (stats_d["cells"] + stats_d["base_cells"]) + 2 * (stats_d["extend_matches"] + stats_d["base_extend_matches"])
+                     + 8 * stats_d["overlap_tests"])
         brk_s = (sum(brk_d) / len(brk_d)) / 1e3
         n_brk_launch = max(1, int(stats_d["levels"]))
         achieved = alg_bytes / brk_s / 1e9 if brk_s > 0 else 0.0
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "wfb_break_kernel", "peak_source": peak_src,
+                    "kernel": "wfb_persist_kernel", "peak_source": peak_src,
                     "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": brk_s * 1e3, "launches_per_step": n_brk_launch,
-                    "cells_per_step": stats_d["cells"], "gcells_per_s": stats_d["cells"] / brk_s / 1e9 if brk_s > 0 else 0.0}
+                    "cells_per_step": stats_d["cells"] + stats_d["base_cells"],
+                    "gcells_per_s": (stats_d["cells"] + stats_d["base_cells"]) / brk_s / 1e9 if brk_s > 0 else 0.0}
         cpu = run_cpu_sample(recs, args.cpu_seconds, cores) if (world == 1 and not args.no_cpu) else None
         h2d = int(plen.sum() + tlen.sum()) + 64 * n
         d2h = sum(r.ops_len for r in res) + 24 * n
@@ -386,6 +454,11 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_record:
+            try:
+                line["record_path"] = record_path_section(al, recs, cores, not args.no_cpu, args.cpu_seconds)
+            except Exception as e:
+                line["record_path"] = {"error": str(e)}
         if world == 1 and not args.no_map:
             try:
                 line["map_path"] = map_path_section(dev, cores, not args.no_cpu)

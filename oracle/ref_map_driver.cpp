@@ -36,9 +36,15 @@ int ref_sketch_fragment(char* seq, int64_t len, int k, int s, int32_t seqId, ref
 /* commonFunc.hpp:440 */
 int64_t ref_add_minmers(char* seq, int64_t len, int k, int w, int s, int32_t seqId, ref_minmer_t* out, int64_t cap) {
   std::vector<skch::MinmerInfo> v;
-  /* one shared meter like the reference's Sketch::build (winSketch.hpp:188-204); a huge total keeps
-   * increment() on its lock-free path (progress.hpp) so concurrent callers do not serialise */
-  static progress_meter::ProgressMeter* pm = new progress_meter::ProgressMeter((uint64_t)1 << 60, "", false);
+  /* one shared meter like the reference's Sketch::build (winSketch.hpp:188-204), silenced: its reporter thread
+   * (progress.hpp:32-103) is told it has finished and given time to leave before any progress is counted, so nothing
+   * is printed from a foreign thread inside the test process; increment() itself stays a plain atomic add */
+  static progress_meter::ProgressMeter* pm = [] {
+    auto* m = new progress_meter::ProgressMeter((uint64_t)1 << 60, "", false);
+    m->is_finished.store(true);
+    std::this_thread::sleep_for(std::chrono::milliseconds(300));
+    return m;
+  }();
   skch::CommonFunc::addMinmers(v, seq, len, k, w, 4, s, seqId, pm);
   int64_t n = 0;
   for (auto& m : v) {

@@ -3,11 +3,14 @@
 Each config = (library variant, WFB_BREAK_THREADS); prints one line per config."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# usage: sweep_break.py [records] [variant:threads ...]   (variants = wfmash_b200/variants/lib_<variant>.so)
 configs = [("q_256_2", 256), ("q_256_2", 128), ("q_256_3", 256), ("q_128_4", 128), ("q_128_6", 128), ("q_256_2", 192)]
 recs = sys.argv[1] if len(sys.argv) > 1 else "861"
+if len(sys.argv) > 2:
+    configs = [(a.split(":")[0], int(a.split(":")[1])) for a in sys.argv[2:]]
 for var, thr in configs:
     env = dict(os.environ, WFB_LIB=os.path.join(ROOT, "wfmash_b200", "variants", f"lib_{var}.so"), WFB_BREAK_THREADS=str(thr))
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "1", "--no-cpu", "--no-map", "--records", recs],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "1", "--no-cpu", "--no-map", "--no-record", "--records", recs],
                        env=env, capture_output=True, text=True, timeout=900)
     try:
         d = json.loads(p.stdout.strip().splitlines()[-1])

@@ -107,6 +107,10 @@ extern "C" void wfb_index_free(wfb_index_t* ix) {
   delete ix;
 }
 
+int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
+                           int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
+                           int64_t* out_count, wfb_minmer_stats_t* stats, wfb_minmer_t** d_out_keep); /* minmer_host.cu */
+
 extern "C" wfb_index_t* wfb_index_build(int device, const wfb_index_params_t* prm, const char* const* seq_ptrs, const int64_t* seq_lens,
                                         const int32_t* seq_ids, int32_t nseq, wfb_index_stats_t* stats) {
   if (!prm || nseq <= 0 || !seq_ptrs || !seq_lens || !seq_ids) { wfb_set_last_error_("bad argument"); return nullptr; }
@@ -117,13 +121,24 @@ extern "C" wfb_index_t* wfb_index_build(int device, const wfb_index_params_t* pr
   int max_seq_id = 0;
   for (int i = 0; i < nseq; ++i) { total_len += seq_lens[i]; max_seq_id = std::max(max_seq_id, seq_ids[i]); }
   if (max_seq_id >= (1 << 22)) { wfb_set_last_error_("seqId too large for the packed interval points (22 bits)"); return nullptr; }
-  long long cap = (long long)((double)total_len * (0.01 * s + 0.05)) + 4096;
-  std::vector<wfb_minmer_t> mi((size_t)cap);
   int64_t n = 0;
   wfb_minmer_stats_t ms;
-  int rc = wfb_minmers_build(device, seq_ptrs, seq_lens, seq_ids, nseq, k, w, s, mi.data(), cap, &n, &ms);
+  wfb_minmer_t* d_mi_built = nullptr; /* the minmers never leave the device between addMinmers and the index kernels */
+#ifdef WFB_EMU
+  long long cap = (long long)((double)total_len * (0.01 * s + 0.05)) + 4096;
+  std::vector<wfb_minmer_t> mi((size_t)cap);
+  int rc = wfb_minmers_build_impl(device, seq_ptrs, seq_lens, seq_ids, nseq, k, w, s, mi.data(), cap, &n, &ms, nullptr);
+#else
+  int rc = wfb_minmers_build_impl(device, seq_ptrs, seq_lens, seq_ids, nseq, k, w, s, nullptr, 0, &n, &ms, &d_mi_built);
+#endif
   if (rc != WFB_OK) return nullptr;
-  if (n == 0) { wfb_set_last_error_("reference sketch is empty (winSketch.hpp:451-456)"); return nullptr; }
+  if (n == 0) {
+#ifndef WFB_EMU
+    cudaFree(d_mi_built);
+#endif
+    wfb_set_last_error_("reference sketch is empty (winSketch.hpp:451-456)");
+    return nullptr;
+  }
   /* worker partitions of Sketch::build (winSketch.hpp:271-277): contiguous ranges of the sequences >= w */
   std::vector<int> part((size_t)max_seq_id + 1, 0);
   {
@@ -140,7 +155,7 @@ extern "C" wfb_index_t* wfb_index_build(int device, const wfb_index_params_t* pr
   ix->n_minmers_all = n;
 #ifndef WFB_EMU
   {
-    wfb_minmer_t* d_mi = nullptr; unsigned long long *d_keys = nullptr, *d_skeys = nullptr, *d_ufreq = nullptr, *d_uhash_all = nullptr;
+    wfb_minmer_t* d_mi = d_mi_built; unsigned long long *d_keys = nullptr, *d_skeys = nullptr, *d_ufreq = nullptr, *d_uhash_all = nullptr;
     int *d_idx = nullptr, *d_sidx = nullptr, *d_head = nullptr, *d_keep_s = nullptr, *d_keep_o = nullptr, *d_pstart = nullptr, *d_hk = nullptr, *d_part = nullptr;
     long long *d_run = nullptr, *d_pair = nullptr, *d_uk = nullptr, *d_off = nullptr;
     int* d_fail = nullptr;
@@ -151,8 +166,6 @@ extern "C" wfb_index_t* wfb_index_build(int device, const wfb_index_params_t* pr
     const int G = 148 * 8, B = 256;
     IX_CHECK(cudaSetDevice(device));
     IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1));
-    IX_CHECK(cudaMalloc(&d_mi, sizeof(wfb_minmer_t) * (size_t)n));
-    IX_CHECK(cudaMemcpy(d_mi, mi.data(), sizeof(wfb_minmer_t) * (size_t)n, cudaMemcpyHostToDevice));
     IX_CHECK(cudaMalloc(&d_part, sizeof(int) * part.size()));
     IX_CHECK(cudaMemcpy(d_part, part.data(), sizeof(int) * part.size(), cudaMemcpyHostToDevice));
     IX_CHECK(cudaMalloc(&d_keys, 8 * (size_t)n)); IX_CHECK(cudaMalloc(&d_skeys, 8 * (size_t)n));

@@ -121,9 +121,12 @@ WFB_KERNEL(mm_gather_out_kernel, const MmFinal* f, const int* perm, const int* k
   }
 }
 
-extern "C" int wfb_minmers_build(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
-                                 int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
-                                 int64_t* out_count, wfb_minmer_stats_t* stats) {
+/* Shared by wfb_minmers_build (results copied to the caller's host buffer) and wfb_index_build (d_out_keep != NULL:
+ * the result stays in device memory, ownership of *d_out_keep passes to the caller, `out` is not touched). */
+int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
+                           int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
+                           int64_t* out_count, wfb_minmer_stats_t* stats, wfb_minmer_t** d_out_keep) {
+  if (d_out_keep) *d_out_keep = nullptr;
   if (nseq < 0 || kmer_size <= 0 || kmer_size > 32 || window_size <= kmer_size || sketch_size <= 0 || !out_count ||
       (nseq > 0 && (!seq_ptrs || !seq_lens || !seq_ids))) {
     wfb_set_last_error_("bad argument");
@@ -277,6 +280,7 @@ extern "C" int wfb_minmers_build(int device, const char* const* seq_ptrs, const 
     stats->stitch_miss = hc.stitch_miss; stats->bases = 0;
     for (int q = 0; q < ns; ++q) stats->bases += (uint64_t)seqs[q].len;
   }
+  if (d_out_keep) { *d_out_keep = d_out; d_out = nullptr; goto done; }
   if (nout > out_cap) { wfb_set_last_error_("minmer output buffer too small"); rc = WFB_ECAP; goto done; }
   if (nout > 0) MM_CHECK(cudaMemcpy(out, d_out, sizeof(wfb_minmer_t) * (size_t)nout, cudaMemcpyDeviceToHost));
 done:
@@ -333,4 +337,11 @@ done:
   (void)device;
   return rc;
 #endif
+}
+
+extern "C" int wfb_minmers_build(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
+                                 int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
+                                 int64_t* out_count, wfb_minmer_stats_t* stats) {
+  return wfb_minmers_build_impl(device, seq_ptrs, seq_lens, seq_ids, nseq, kmer_size, window_size, sketch_size, out, out_cap, out_count,
+                                stats, nullptr);
 }

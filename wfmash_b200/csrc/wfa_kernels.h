@@ -27,6 +27,9 @@
 #ifndef WFB_UNROLL
 #define WFB_UNROLL 1
 #endif
+#ifndef WFB_BATCH_EXTEND
+#define WFB_BATCH_EXTEND 1
+#endif
 #ifndef WFB_PREFETCH_DIST
 #define WFB_PREFETCH_DIST 1
 #endif
@@ -148,14 +151,13 @@ WFB_DEV int32_t wfb_get(const int32_t* basep, const WfbIn& w, int k) {
 /* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 15 bytes past
  * the cap (sequence buffers are padded). wavefront_extend_kernels.c:68-92 does the same 8 bytes at a
  * time on the CPU. */
-WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
+WFB_DEV int wfb_match_run_words(const uint8_t* p, const uint8_t* t, int limit) {
 #ifdef WFB_EMU
   int n = 0;
   while (n < limit && p[n] == t[n]) ++n;
   return n;
 #else
   if (limit <= 0) return 0;
-  if (wfb_ldg8(p) != wfb_ldg8(t)) return 0; /* 3 of 4 cells of an unrelated diagonal stop right here */
   const uintptr_t pa = (uintptr_t)p, ta = (uintptr_t)t;
   const uint32_t* pw = (const uint32_t*)(pa & ~(uintptr_t)3);
   const uint32_t* tw = (const uint32_t*)(ta & ~(uintptr_t)3);
@@ -183,6 +185,36 @@ WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
     tw += 2;
   }
   return n < limit ? n : limit;
+#endif
+}
+
+WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
+#ifndef WFB_EMU
+  if (limit <= 0) return 0;
+  if (wfb_ldg8(p) != wfb_ldg8(t)) return 0; /* 3 of 4 cells of an unrelated diagonal stop right here */
+#endif
+  return wfb_match_run_words(p, t, limit);
+}
+
+/* XOR of the four bases at pattern[off-k ..] and text[off ..] (0 = all four equal; the lowest differing byte gives the
+ * common-prefix length). No control flow: the four loads of several cells can be in flight together. A cell without a
+ * valid offset (off < 0) issues no loads and reports "first base differs". Reads up to 7 bytes past the position
+ * (padded buffers). */
+WFB_DEV uint32_t wfb_match_head4(const uint8_t* pseq, const uint8_t* tseq, int32_t off, int k) {
+#ifdef WFB_EMU
+  if (off < 0) return 1u;
+  uint32_t x = 0;
+  for (int b = 0; b < 4; ++b) x |= (uint32_t)(uint8_t)(pseq[off - k + b] ^ tseq[off + b]) << (8 * b);
+  return x;
+#else
+  const bool ok = off >= 0;
+  const uintptr_t pa = (uintptr_t)(pseq + (ok ? off - k : 0)), ta = (uintptr_t)(tseq + (ok ? off : 0));
+  const uint32_t* pw = (const uint32_t*)(pa & ~(uintptr_t)3);
+  const uint32_t* tw = (const uint32_t*)(ta & ~(uintptr_t)3);
+  uint32_t p0 = 0, p1 = 0, t0 = 1, t1 = 0;
+  if (ok) { p0 = wfb_ldg32(pw); p1 = wfb_ldg32(pw + 1); t0 = wfb_ldg32(tw); t1 = wfb_ldg32(tw + 1); }
+  const uint32_t x = __funnelshift_r(p0, p1, (unsigned)(pa & 3) * 8u) ^ __funnelshift_r(t0, t1, (unsigned)(ta & 3) * 8u);
+  return ok ? x : 1u;
 #endif
 }
 
@@ -287,7 +319,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
 
   /* One wavefront cell (wavefront_compute_affine2p_idm, wavefront_compute_affine2p.c:71-105) fused with
    * its extension (wavefront_extend_kernels.c:125-152) and trim bookkeeping (wavefront_compute.c:579-613). */
-#define WFB_CELL(K, O1M, O1P, O2M, O2P, I1V, I2V, D1V, D2V, MMV, OUT_M, OUT_I1, OUT_I2, OUT_D1, OUT_D2)      \
+#define WFB_CELL_A(K, O1M, O1P, O2M, O2P, I1V, I2V, D1V, D2V, MMV, OUT_M, OUT_I1, OUT_I2, OUT_D1, OUT_D2)    \
   {                                                                                                       \
     const int k_ = (K);                                                                                   \
     const int32_t ins1 = max((O1M), (I1V)) + 1;                                                           \
@@ -296,18 +328,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     const int32_t del2 = max((O2P), (D2V));                                                               \
     int32_t mx = max(max(del1, del2), max((MMV) + 1, max(ins1, ins2)));                                   \
     if (mx >= 0) tak = max(tak, 2 * mx - k_); /* negative (null-ish) values can never be part of a hit */ \
-    if (wfb_inbounds(mx, k_, plen, tlen)) {                                                               \
-      const int v_ = mx - k_;                                                                             \
-      const int run = wfb_match_run(pseq + v_, tseq + mx, min(plen - v_, tlen - mx));                     \
-      mx += run;                                                                                          \
-      if (alloc.runflag) alloc.runflag[k_ + alloc.runbias] = run >= 4 ? 1 : 0;                            \
-      acc.matches += (unsigned)run;                                                                       \
-      tmax = max(tmax, 2 * mx - k_);                                                                      \
-      tlo[WFB_M] = min(tlo[WFB_M], k_);                                                                   \
-      thi[WFB_M] = max(thi[WFB_M], k_);                                                                   \
-    } else {                                                                                              \
-      mx = WFB_OFFSET_NULL;                                                                               \
-    }                                                                                                     \
+    if (!wfb_inbounds(mx, k_, plen, tlen)) mx = WFB_OFFSET_NULL;                                          \
     /* an I value keeps the v of its in-bounds source and a D value keeps the h, null-ish values are hugely      \
      * negative: ONE unsigned compare decides what wavefront_compute_trim_ends (:594-596) tests with two */      \
     if (ex_i1 && (uint32_t)ins1 <= (uint32_t)tlen) { tlo[WFB_I1] = min(tlo[WFB_I1], k_); thi[WFB_I1] = max(thi[WFB_I1], k_); } \
@@ -315,6 +336,28 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     if (ex_d1 && (uint32_t)(del1 - k_) <= (uint32_t)plen) { tlo[WFB_D1] = min(tlo[WFB_D1], k_); thi[WFB_D1] = max(thi[WFB_D1], k_); } \
     if (ex_d2 && (uint32_t)(del2 - k_) <= (uint32_t)plen) { tlo[WFB_D2] = min(tlo[WFB_D2], k_); thi[WFB_D2] = max(thi[WFB_D2], k_); } \
     (OUT_M) = mx; (OUT_I1) = ins1; (OUT_I2) = ins2; (OUT_D1) = del1; (OUT_D2) = del2;                       \
+  }
+  /* bookkeeping of one in-bounds M cell after its extension by RUN matches (wavefront_extend_kernels.c:125-152) */
+#define WFB_CELL_X(K, OUT_M, RUN)                                                                         \
+  {                                                                                                       \
+    const int k_ = (K);                                                                                   \
+    const int run_ = (RUN);                                                                               \
+    (OUT_M) += run_;                                                                                      \
+    if (alloc.runflag) alloc.runflag[k_ + alloc.runbias] = run_ >= 4 ? 1 : 0;                             \
+    acc.matches += (unsigned)run_;                                                                        \
+    tmax = max(tmax, 2 * (OUT_M) - k_);                                                                   \
+    tlo[WFB_M] = min(tlo[WFB_M], k_);                                                                     \
+    thi[WFB_M] = max(thi[WFB_M], k_);                                                                     \
+  }
+  /* the fused form used on the scalar paths */
+#define WFB_CELL(K, O1M, O1P, O2M, O2P, I1V, I2V, D1V, D2V, MMV, OUT_M, OUT_I1, OUT_I2, OUT_D1, OUT_D2)      \
+  {                                                                                                       \
+    WFB_CELL_A(K, O1M, O1P, O2M, O2P, I1V, I2V, D1V, D2V, MMV, OUT_M, OUT_I1, OUT_I2, OUT_D1, OUT_D2)       \
+    if ((OUT_M) >= 0) {                                                                                   \
+      const int v__ = (OUT_M) - (K);                                                                      \
+      const int run__ = wfb_match_run(pseq + v__, tseq + (OUT_M), min(plen - v__, tlen - (OUT_M)));       \
+      WFB_CELL_X(K, OUT_M, run__)                                                                         \
+    }                                                                                                     \
   }
 
   /* hand the end component's offset on the final diagonal to the termination test (wavefront_termination.c:37-114) */
@@ -356,10 +399,35 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
         if (!n_d1) { const int32_t* p = basep + d1_ext.off + k0; vd1 = *(const int4*)p; sd1 = p[4]; }
         if (!n_d2) { const int32_t* p = basep + d2_ext.off + k0; vd2 = *(const int4*)p; sd2 = p[4]; }
         if (!n_m)  { vmm = *(const int4*)(basep + m_misms.off + k0); }
+#if WFB_BATCH_EXTEND
+        WFB_CELL_A(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+        WFB_CELL_A(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+        WFB_CELL_A(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+        WFB_CELL_A(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+        {
+          /* extension of the four M cells with the first round of sequence loads of all four in flight together
+           * (16 independent loads, one memory round trip); only cells whose first four bases match go on */
+          uint32_t xr[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) xr[u] = wfb_match_head4(pseq, tseq, rm[u], k0 + u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (rm[u] >= 0) {
+              const int v_ = rm[u] - (k0 + u);
+              const int lim_ = min(plen - v_, tlen - rm[u]);
+              int run_ = xr[u] ? ((__ffs((int)xr[u]) - 1) >> 3) : 4;
+              if (run_ >= lim_) run_ = lim_;
+              else if (run_ == 4) run_ = 4 + wfb_match_run_words(pseq + v_ + 4, tseq + rm[u] + 4, lim_ - 4);
+              WFB_CELL_X(k0 + u, rm[u], run_)
+            }
+          }
+        }
+#else
         WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
         WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
         WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
         WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+#endif
         if ((unsigned)(ak_end - k0) < 4u) { /* constant indices keep the arrays in registers */
           WFB_END_HANDOFF(k0 + 0, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
           WFB_END_HANDOFF(k0 + 1, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
@@ -404,6 +472,8 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     }
   }
 #undef WFB_CELL
+#undef WFB_CELL_A
+#undef WFB_CELL_X
 #undef WFB_END_HANDOFF
   /* trimmed [lo,hi] of each component = min / max diagonal holding an in-bounds offset */
   {

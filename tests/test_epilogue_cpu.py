@@ -24,15 +24,27 @@ bad = []
 for kw, want in zip(gold["filter_sets"], gold["lines"]):
     lines, status = al.biwfa_paf_batch(recs, term_group=gold["term_group"], **kw)
     bad += [(i, str(kw)) for i, (g, w) in enumerate(zip(lines, want)) if g.decode() != w]
-print(json.dumps({"bad": bad, "n": len(recs)}))
+# the kernel bodies themselves (4-diagonal groups, batched extend, overlap scan, base case) on the reference's own
+# known-answer vectors and on medium random pairs against the oracle
+pairs = util.golden_pairs()
+gold_alg = util.golden_alg("wfa_utest.biwfa.affine2p.alg.gz")
+ag = wb.Aligner(0, penalties=util.GOLDEN_PEN)
+gbad = [i for i, (r, (gs, gc)) in enumerate(zip(ag.align_end2end_batch(pairs), gold_alg))
+        if r.status != 0 or util.rle(r.ops) != gc or r.score != int(gs)]
+orc = util.load_oracle()
+rp = [pt for pt in util.random_pairs(60, seed=41, lengths=(400, 1500, 4000), rates=(0.01, 0.05, 0.15)) if pt[0] and pt[1]]
+rbad = [i for i, ((p_, t_), r) in enumerate(zip(rp, al.align_end2end_batch(rp))) if (r.status, r.ops) != util.orc_biwfa(orc, p_, t_, util.WFMASH_PEN)[:2]]
+print(json.dumps({"bad": bad, "n": len(recs), "golden_bad": gbad, "golden_n": len(pairs), "random_bad": rbad, "random_n": len(rp)}))
 """
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
-def test_record_epilogue_matches_reference_fixture_under_emulation():
+def test_record_epilogue_and_kernel_bodies_under_emulation():
     so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
     env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": util.ROOT}], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["n"] == 63 and res["bad"] == []
+    assert res["golden_n"] == 305 and res["golden_bad"] == []
+    assert res["random_n"] > 40 and res["random_bad"] == []

@@ -750,3 +750,13 @@ extern "C" int wfb_memcpy_h2d(int device, void* dst, const void* src, uint64_t b
 #endif
   return WFB_OK;
 }
+
+#if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
+/* tuning builds only (not declared in include/wfmash_b200.h): read and clear the phase timers */
+extern "C" int wfb_debug_phase_timers(unsigned long long* out32) {
+  if (cudaMemcpyFromSymbol(out32, g_wfb_phase, sizeof(unsigned long long) * 32) != cudaSuccess) return WFB_ECUDA;
+  unsigned long long z[32] = {0};
+  if (cudaMemcpyToSymbol(g_wfb_phase, z, sizeof(z)) != cudaSuccess) return WFB_ECUDA;
+  return WFB_OK;
+}
+#endif

@@ -30,6 +30,9 @@
 #ifndef WFB_BATCH_EXTEND
 #define WFB_BATCH_EXTEND 1
 #endif
+#ifndef WFB_OVL_UNROLL
+#define WFB_OVL_UNROLL 4
+#endif
 #ifndef WFB_PREFETCH_DIST
 #define WFB_PREFETCH_DIST 1
 #endif
@@ -148,15 +151,10 @@ WFB_DEV int32_t wfb_get(const int32_t* basep, const WfbIn& w, int k) {
   return (k >= w.lo && k <= w.hi) ? basep[w.off + k] : WFB_OFFSET_NULL;
 }
 
-/* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 15 bytes past
+/* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 23 bytes past
  * the cap (sequence buffers are padded). wavefront_extend_kernels.c:68-92 does the same 8 bytes at a
  * time on the CPU. */
 WFB_DEV int wfb_match_run_words(const uint8_t* p, const uint8_t* t, int limit) {
-#ifdef WFB_EMU
-  int n = 0;
-  while (n < limit && p[n] == t[n]) ++n;
-  return n;
-#else
   if (limit <= 0) return 0;
   const uintptr_t pa = (uintptr_t)p, ta = (uintptr_t)t;
   const uint32_t* pw = (const uint32_t*)(pa & ~(uintptr_t)3);
@@ -165,34 +163,32 @@ WFB_DEV int wfb_match_run_words(const uint8_t* p, const uint8_t* t, int limit) {
   uint32_t p0 = wfb_ldg32(pw), t0 = wfb_ldg32(tw);
   int n = 0;
   while (n < limit) {
-    /* two words of each sequence per trip, the four loads are independent */
+    /* four words of each sequence per trip (16 bases), the eight loads are independent: a long exact run costs one
+     * memory round trip per 16 bases */
     const uint32_t p1 = wfb_ldg32(pw + 1), t1 = wfb_ldg32(tw + 1);
     const uint32_t p2 = wfb_ldg32(pw + 2), t2 = wfb_ldg32(tw + 2);
+    const uint32_t p3 = wfb_ldg32(pw + 3), t3 = wfb_ldg32(tw + 3);
+    const uint32_t p4 = wfb_ldg32(pw + 4), t4 = wfb_ldg32(tw + 4);
     const uint32_t x1 = __funnelshift_r(p0, p1, ps) ^ __funnelshift_r(t0, t1, ts);
-    if (x1) {
-      n += (__ffs((int)x1) - 1) >> 3;
-      break;
-    }
+    if (x1) { n += (__ffs((int)x1) - 1) >> 3; break; }
     const uint32_t x2 = __funnelshift_r(p1, p2, ps) ^ __funnelshift_r(t1, t2, ts);
-    if (x2) {
-      n += 4 + ((__ffs((int)x2) - 1) >> 3);
-      break;
-    }
-    n += 8;
-    p0 = p2;
-    t0 = t2;
-    pw += 2;
-    tw += 2;
+    if (x2) { n += 4 + ((__ffs((int)x2) - 1) >> 3); break; }
+    const uint32_t x3 = __funnelshift_r(p2, p3, ps) ^ __funnelshift_r(t2, t3, ts);
+    if (x3) { n += 8 + ((__ffs((int)x3) - 1) >> 3); break; }
+    const uint32_t x4 = __funnelshift_r(p3, p4, ps) ^ __funnelshift_r(t3, t4, ts);
+    if (x4) { n += 12 + ((__ffs((int)x4) - 1) >> 3); break; }
+    n += 16;
+    p0 = p4;
+    t0 = t4;
+    pw += 4;
+    tw += 4;
   }
   return n < limit ? n : limit;
-#endif
 }
 
 WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
-#ifndef WFB_EMU
   if (limit <= 0) return 0;
   if (wfb_ldg8(p) != wfb_ldg8(t)) return 0; /* 3 of 4 cells of an unrelated diagonal stop right here */
-#endif
   return wfb_match_run_words(p, t, limit);
 }
 
@@ -201,12 +197,6 @@ WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
  * valid offset (off < 0) issues no loads and reports "first base differs". Reads up to 7 bytes past the position
  * (padded buffers). */
 WFB_DEV uint32_t wfb_match_head4(const uint8_t* pseq, const uint8_t* tseq, int32_t off, int k) {
-#ifdef WFB_EMU
-  if (off < 0) return 1u;
-  uint32_t x = 0;
-  for (int b = 0; b < 4; ++b) x |= (uint32_t)(uint8_t)(pseq[off - k + b] ^ tseq[off + b]) << (8 * b);
-  return x;
-#else
   const bool ok = off >= 0;
   const uintptr_t pa = (uintptr_t)(pseq + (ok ? off - k : 0)), ta = (uintptr_t)(tseq + (ok ? off : 0));
   const uint32_t* pw = (const uint32_t*)(pa & ~(uintptr_t)3);
@@ -215,7 +205,6 @@ WFB_DEV uint32_t wfb_match_head4(const uint8_t* pseq, const uint8_t* tseq, int32
   if (ok) { p0 = wfb_ldg32(pw); p1 = wfb_ldg32(pw + 1); t0 = wfb_ldg32(tw); t1 = wfb_ldg32(tw + 1); }
   const uint32_t x = __funnelshift_r(p0, p1, (unsigned)(pa & 3) * 8u) ^ __funnelshift_r(t0, t1, (unsigned)(ta & 3) * 8u);
   return ok ? x : 1u;
-#endif
 }
 
 /* L2 prefetch of one 128-byte line (the rows a later score step will read come from DRAM otherwise) */
@@ -230,6 +219,18 @@ WFB_DEV void wfb_prefetch_l2(const void* p) {
 WFB_DEV bool wfb_inbounds(int32_t off, int k, int plen, int tlen) {
   return (uint32_t)off <= (uint32_t)tlen && (uint32_t)(off - k) <= (uint32_t)plen;
 }
+
+/* Optional phase timers (-DWFB_PHASE_TIMERS, tuning builds only): per wavefront-width bucket b in {<=128, <=1024,
+ * <=4096, >4096}: [4b+0] steps, [4b+1] SM cycles entry -> barrier passed, [4b+2] cycles of thread 0's own cells,
+ * [4b+3] diagonals. [16] = cycles in overlap scans, [17] = overlap calls. Thread 0 sits at the lo edge of the wavefront. */
+#if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
+__device__ unsigned long long g_wfb_phase[32];
+#define WFB_PT_CLOCK() ((long long)clock64())
+#define WFB_PT_ADD(i, v) atomicAdd(&g_wfb_phase[(i)], (unsigned long long)(v))
+#else
+#define WFB_PT_CLOCK() 0ll
+#define WFB_PT_ADD(i, v) ((void)0)
+#endif
 
 /* Per-thread accumulators that live in registers for the whole task. */
 struct WfbAcc {
@@ -264,6 +265,9 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
   const bool n_d1 = d1_ext.lo > d1_ext.hi, n_d2 = d2_ext.lo > d2_ext.hi;
   max_ak_out = 0;
   acc.steps += 1;
+#if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
+  const long long pt0 = WFB_PT_CLOCK();
+#endif
   if (n_m && n_o1 && n_o2 && n_i1 && n_i2 && n_d1 && n_d2) {
     /* wavefront_compute_affine2p.c:341-351 + wavefront_extend.c:95-103 */
     num_null++;
@@ -341,10 +345,10 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
 #define WFB_CELL_X(K, OUT_M, RUN)                                                                         \
   {                                                                                                       \
     const int k_ = (K);                                                                                   \
-    const int run_ = (RUN);                                                                               \
-    (OUT_M) += run_;                                                                                      \
-    if (alloc.runflag) alloc.runflag[k_ + alloc.runbias] = run_ >= 4 ? 1 : 0;                             \
-    acc.matches += (unsigned)run_;                                                                        \
+    const int wfb_x_run_ = (RUN);                                                                         \
+    (OUT_M) += wfb_x_run_;                                                                                \
+    if (alloc.runflag) alloc.runflag[k_ + alloc.runbias] = wfb_x_run_ >= 4 ? 1 : 0;                       \
+    acc.matches += (unsigned)wfb_x_run_;                                                                  \
     tmax = max(tmax, 2 * (OUT_M) - k_);                                                                   \
     tlo[WFB_M] = min(tlo[WFB_M], k_);                                                                     \
     thi[WFB_M] = max(thi[WFB_M], k_);                                                                     \
@@ -366,13 +370,8 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     red_end[par] = cend == WFB_M ? (VM) : cend == WFB_I1 ? (VI1) : cend == WFB_I2 ? (VI2) : cend == WFB_D1 ? (VD1) : (VD2);
 
   const int kalign = alloc.kalign;
-#ifndef WFB_EMU
   const bool vec_ok = kalign >= 0;
-#else
-  const bool vec_ok = false;
-#endif
   if (vec_ok) {
-#ifndef WFB_EMU
     /* groups of 4 diagonals whose cells are 16-byte aligned in every row: 128-bit loads / stores, range
      * checks once per group; ragged groups at the ends of any input take the scalar path */
     int safe_lo = lo, safe_hi = hi; /* diagonals k with [k-1, k+4] inside every non-null input */
@@ -415,10 +414,10 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
             if (rm[u] >= 0) {
               const int v_ = rm[u] - (k0 + u);
               const int lim_ = min(plen - v_, tlen - rm[u]);
-              int run_ = xr[u] ? ((__ffs((int)xr[u]) - 1) >> 3) : 4;
-              if (run_ >= lim_) run_ = lim_;
-              else if (run_ == 4) run_ = 4 + wfb_match_run_words(pseq + v_ + 4, tseq + rm[u] + 4, lim_ - 4);
-              WFB_CELL_X(k0 + u, rm[u], run_)
+              int nrun = xr[u] ? ((__ffs((int)xr[u]) - 1) >> 3) : 4;
+              if (nrun >= lim_) nrun = lim_;
+              else if (nrun == 4) nrun = 4 + wfb_match_run_words(pseq + v_ + 4, tseq + rm[u] + 4, lim_ - 4);
+              WFB_CELL_X(k0 + u, rm[u], nrun)
             }
           }
         }
@@ -456,7 +455,6 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
         }
       }
     }
-#endif
   } else {
     for (int k = lo + WFB_TID; k <= hi; k += WFB_NT) {
       int32_t rm, ri1, ri2, rd1, rd2;
@@ -474,6 +472,9 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
 #undef WFB_CELL
 #undef WFB_CELL_A
 #undef WFB_CELL_X
+#if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
+  const long long pt1 = WFB_PT_CLOCK();
+#endif
 #undef WFB_END_HANDOFF
   /* trimmed [lo,hi] of each component = min / max diagonal holding an in-bounds offset */
   {
@@ -494,6 +495,12 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     }
   }
   WFB_SYNC();
+#if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
+  if (WFB_TID == 0) {
+    const int wd = hi - lo + 1, b = wd <= 128 ? 0 : wd <= 1024 ? 1 : wd <= 4096 ? 2 : 3;
+    WFB_PT_ADD(4 * b + 0, 1); WFB_PT_ADD(4 * b + 1, WFB_PT_CLOCK() - pt0); WFB_PT_ADD(4 * b + 2, pt1 - pt0); WFB_PT_ADD(4 * b + 3, wd);
+  }
+#endif
   max_ak_out = red_maxak[par];
   /* wavefront_termination_end2end, wavefront_termination.c:37-114 */
   if (cend >= 0 && ring.ex[slot][cend] && ring.lo[slot][cend] <= ak_end && ak_end <= ring.hi[slot][cend]) {
@@ -527,6 +534,10 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
                          WfbBreakpoint* bp, WfbOverlapShared* os, WfbAcc& acc) {
   const int R = pen.R, s0 = score_0 % R;
   if (!r0.ex[s0][WFB_M]) return; /* uniform */
+#if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
+  const long long pto = WFB_PT_CLOCK();
+  struct PtScope { long long t0; WFB_DEV_MEMBER ~PtScope() { if (WFB_TID == 0) { WFB_PT_ADD(16, WFB_PT_CLOCK() - t0); WFB_PT_ADD(17, 1); } } } pt_scope{pto};
+#endif
   const int best0 = bp->score;
   const int kinv = tlen - plen;
   const int npairs = pen.scope * 5;
@@ -573,29 +584,47 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
     const int32_t* p0 = base0 + r0.boff[s0][c];
     const int32_t* p1 = base1 + r1.boff[si][c];
     int kfound = INT_MAX;
-    for (int kb = max_lo; kb <= min_hi; kb += 32) {
-      const int k0 = kb + lane;
-      bool hit = false;
-      if (k0 <= min_hi) {
-        const int k1 = kinv - k0;
-        const int32_t o0 = p0[k0], o1 = p1[k1];
-        if (o0 + o1 >= tlen) {
-          hit = true;
-          if (c != WFB_M) {
-            const int kk = bp_forward ? k0 : k1;
-            const int32_t oo = bp_forward ? o0 : o1;
-            if (oo - kk > plen || oo > tlen) hit = false; /* out-of-bounds coordinates: keep scanning */
-          }
-        }
-      }
 #ifndef WFB_EMU
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (bal) { kfound = kb + __ffs((int)bal) - 1; break; }
-#else
-      if (hit) { kfound = k0; break; }
-      kb -= 31; /* one diagonal per trip in the single-thread emulation */
-#endif
+    /* WFB_OVL_UNROLL chunks of 32 diagonals per trip: their loads are independent and in flight together (the scan
+     * is a chain of memory round trips otherwise); the ballots are then examined in ascending order, so the first
+     * satisfying diagonal is still the lowest one */
+    for (int kb = max_lo; kb <= min_hi && kfound == INT_MAX; kb += 32 * WFB_OVL_UNROLL) {
+      int32_t o0[WFB_OVL_UNROLL], o1[WFB_OVL_UNROLL];
+#pragma unroll
+      for (int u = 0; u < WFB_OVL_UNROLL; ++u) {
+        const int k0 = kb + 32 * u + lane;
+        const bool in = k0 <= min_hi;
+        o0[u] = in ? p0[k0] : WFB_OFFSET_NULL;
+        o1[u] = in ? p1[kinv - k0] : WFB_OFFSET_NULL;
+      }
+#pragma unroll
+      for (int u = 0; u < WFB_OVL_UNROLL; ++u) {
+        const int k0 = kb + 32 * u + lane;
+        bool hit = o0[u] + o1[u] >= tlen; /* two nulls: -2^30 - 2^30 stays negative */
+        if (hit && c != WFB_M) {
+          const int kk = bp_forward ? k0 : kinv - k0;
+          const int32_t oo = bp_forward ? o0[u] : o1[u];
+          if (oo - kk > plen || oo > tlen) hit = false; /* out-of-bounds coordinates: keep scanning */
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal && kfound == INT_MAX) kfound = kb + 32 * u + __ffs((int)bal) - 1;
+      }
     }
+#else
+    for (int k0 = max_lo; k0 <= min_hi; ++k0) { /* one diagonal per trip in the single-thread emulation */
+      const int k1 = kinv - k0;
+      const int32_t o0 = p0[k0], o1 = p1[k1];
+      if (o0 + o1 >= tlen) {
+        bool hit = true;
+        if (c != WFB_M) {
+          const int kk = bp_forward ? k0 : k1;
+          const int32_t oo = bp_forward ? o0 : o1;
+          if (oo - kk > plen || oo > tlen) hit = false;
+        }
+        if (hit) { kfound = k0; break; }
+      }
+    }
+#endif
     if (lane == 0) {
       if (kfound != INT_MAX) {
         os->found[q] = kfound;

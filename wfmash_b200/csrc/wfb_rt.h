@@ -58,4 +58,12 @@ WFB_DEV uint32_t wfb_ldg32(const uint32_t* p) { return *p; }
 WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+/* enough of the CUDA vocabulary for the 4-diagonal group path and the word-wise extend to run under emulation */
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, unsigned shift) {
+  const uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (uint32_t)(v >> (shift & 31));
+}
+static inline int __ffs(int v) { return v ? __builtin_ctz((unsigned)v) + 1 : 0; }
 #endif

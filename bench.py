@@ -180,7 +180,7 @@ def record_path_section(al, recs, cores, with_cpu, cpu_seconds):
     import wfmash_b200 as wb
     rr = [dict(query_name=f"q{i}", target_name=f"t{i}", query=t_, target=p_, mashmap_estimated_identity=1.0 - d_)
           for i, (p_, t_, d_) in enumerate(recs)]
-    al.biwfa_paf_batch(rr[: max(8, len(rr) // 16)])  # warm-up (allocations)
+    al.biwfa_paf_batch(rr)  # warm-up with the same batch: the timed call below is the steady state (grow-only workspaces sized)
     l0 = wb.launch_count()
     t0 = time.perf_counter()
     lines, st = al.biwfa_paf_batch(rr, min_identity=0.0, min_alignment_length=32, min_block_identity=0.1)  # CLI defaults, parse_args.hpp:566-584

@@ -168,8 +168,10 @@ extern "C" wfb_aligner_t* wfb_aligner_create(int device, const wfb_penalties_t* 
   pen.x = p->mismatch; pen.o1 = p->gap_opening1; pen.e1 = p->gap_extension1;
   pen.o2 = p->gap_opening2; pen.e2 = p->gap_extension2;
   pen.scope = std::max(std::max(pen.o2 + pen.e2, pen.o1 + pen.e1), pen.x) + 1;
-  pen.R = pen.scope + 1;
-  if (pen.R > WFB_RMAX) { g_last_error = "penalties too large for the wavefront ring (scope+1 > 40)"; return nullptr; }
+  /* scope + 1 slots are live during a step (the scope window + the slot being written); one more so that the slot a
+   * step resets for its successor is outside the window too (a speculative step may be dropped, see wfb_break_task) */
+  pen.R = pen.scope + 2;
+  if (pen.R > WFB_RMAX) { g_last_error = "penalties too large for the wavefront ring (scope+2 > 40)"; return nullptr; }
 #ifndef WFB_EMU
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {

@@ -28,10 +28,13 @@
 #define WFB_UNROLL 1
 #endif
 #ifndef WFB_BATCH_EXTEND
-#define WFB_BATCH_EXTEND 1
+#define WFB_BATCH_EXTEND 0
 #endif
 #ifndef WFB_OVL_UNROLL
 #define WFB_OVL_UNROLL 4
+#endif
+#ifndef WFB_DUAL_PHASE1
+#define WFB_DUAL_PHASE1 1
 #endif
 #ifndef WFB_PREFETCH_DIST
 #define WFB_PREFETCH_DIST 1
@@ -116,6 +119,7 @@ struct WfbRing { /* shared-memory wavefront metadata of the last R scores */
   int hi[WFB_RMAX][5];
   int boff[WFB_RMAX][5]; /* element offset so that cell(k) = basep[boff + k] */
   int mak[WFB_RMAX][5];  /* max anti-diagonal 2*offset-k over the computed cells (overlap pruning) */
+  int cw[WFB_RMAX];      /* diagonals computed by the step (before trimming): the C counter of SURVEY 8(d) */
   unsigned char ex[WFB_RMAX][5];
 };
 
@@ -130,22 +134,22 @@ struct WfbBreakpoint {
   int component;
 };
 
-/* wavefront_compute_get_*wavefront (wavefront_compute.c:266-305): null => lo=1, hi=-1 */
-WFB_DEV WfbIn wfb_fetch(const WfbRing& r, const int32_t* basep, int R, int comp, int score) {
-  (void)basep;
+/* wavefront_compute_get_*wavefront (wavefront_compute.c:266-305): null => lo=1, hi=-1.
+ * slot = score % R is derived by the caller from the current slot (one subtraction + wrap: a runtime modulo costs
+ * ~40 dependent instructions, and a score step needs seven of these); valid = (score >= 0). Branch-free. */
+WFB_DEV WfbIn wfb_fetch_slot(const WfbRing& r, int comp, bool valid, int slot) {
+  const int lo = r.lo[slot][comp], hi = r.hi[slot][comp], off = r.boff[slot][comp];
+  const bool ok = valid && r.ex[slot][comp] && lo <= hi;
   WfbIn w;
-  w.off = 0;
-  w.lo = 1;
-  w.hi = -1;
-  if (score >= 0) {
-    const int s = score % R;
-    if (r.ex[s][comp] && r.lo[s][comp] <= r.hi[s][comp]) {
-      w.lo = r.lo[s][comp];
-      w.hi = r.hi[s][comp];
-      w.off = r.boff[s][comp];
-    }
-  }
+  w.off = ok ? off : 0;
+  w.lo = ok ? lo : 1;
+  w.hi = ok ? hi : -1;
   return w;
+}
+/* (cur - d) mod R for 0 <= d < R, cur in [0, R) */
+WFB_DEV int wfb_slot_back(int cur, int d, int R) {
+  const int s = cur - d;
+  return s < 0 ? s + R : s;
 }
 WFB_DEV int32_t wfb_get(const int32_t* basep, const WfbIn& w, int k) {
   return (k >= w.lo && k <= w.hi) ? basep[w.off + k] : WFB_OFFSET_NULL;
@@ -248,42 +252,42 @@ struct WfbAcc {
  *   red_maxak[3] : shared-memory reduction slots, rotated by score % 3.
  */
 template <class Alloc>
-WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
-                     const uint8_t* tseq, int plen, int tlen, int cend, int& num_null, Alloc& alloc, int* red_maxak,
-                     int* red_end, int& max_ak_out, WfbAcc& acc) {
-  const int R = pen.R, slot = score % R, nslot = (score + 1) % R;
-  const int par = score % 3, npar = (score + 1) % 3;
-  const WfbIn m_misms = wfb_fetch(ring, basep, R, WFB_M, score - pen.x);
-  const WfbIn m_open1 = wfb_fetch(ring, basep, R, WFB_M, score - pen.o1 - pen.e1);
-  const WfbIn m_open2 = wfb_fetch(ring, basep, R, WFB_M, score - pen.o2 - pen.e2);
-  const WfbIn i1_ext = wfb_fetch(ring, basep, R, WFB_I1, score - pen.e1);
-  const WfbIn i2_ext = wfb_fetch(ring, basep, R, WFB_I2, score - pen.e2);
-  const WfbIn d1_ext = wfb_fetch(ring, basep, R, WFB_D1, score - pen.e1);
-  const WfbIn d2_ext = wfb_fetch(ring, basep, R, WFB_D2, score - pen.e2);
+WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
+                     const uint8_t* tseq, int plen, int tlen, int cend, Alloc& alloc, int* red_maxak,
+                     int* red_end, WfbAcc& acc, const int tid, const int nt) {
+  const int R = pen.R, slot = score % R, nslot = slot + 1 == R ? 0 : slot + 1;
+  const int par = score % 3, npar = par == 2 ? 0 : par + 1;
+  (void)basep;
+  /* every distance below is <= max_score_scope = R - 1 */
+  const int d_x = pen.x, d_o1 = pen.o1 + pen.e1, d_o2 = pen.o2 + pen.e2;
+  const int s_e1 = wfb_slot_back(slot, pen.e1, R), s_e2 = wfb_slot_back(slot, pen.e2, R);
+  const WfbIn m_misms = wfb_fetch_slot(ring, WFB_M, score >= d_x, wfb_slot_back(slot, d_x, R));
+  const WfbIn m_open1 = wfb_fetch_slot(ring, WFB_M, score >= d_o1, wfb_slot_back(slot, d_o1, R));
+  const WfbIn m_open2 = wfb_fetch_slot(ring, WFB_M, score >= d_o2, wfb_slot_back(slot, d_o2, R));
+  const WfbIn i1_ext = wfb_fetch_slot(ring, WFB_I1, score >= pen.e1, s_e1);
+  const WfbIn i2_ext = wfb_fetch_slot(ring, WFB_I2, score >= pen.e2, s_e2);
+  const WfbIn d1_ext = wfb_fetch_slot(ring, WFB_D1, score >= pen.e1, s_e1);
+  const WfbIn d2_ext = wfb_fetch_slot(ring, WFB_D2, score >= pen.e2, s_e2);
   const bool n_m = m_misms.lo > m_misms.hi, n_o1 = m_open1.lo > m_open1.hi, n_o2 = m_open2.lo > m_open2.hi;
   const bool n_i1 = i1_ext.lo > i1_ext.hi, n_i2 = i2_ext.lo > i2_ext.hi;
   const bool n_d1 = d1_ext.lo > d1_ext.hi, n_d2 = d2_ext.lo > d2_ext.hi;
-  max_ak_out = 0;
-  acc.steps += 1;
 #if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
   const long long pt0 = WFB_PT_CLOCK();
 #endif
   if (n_m && n_o1 && n_o2 && n_i1 && n_i2 && n_d1 && n_d2) {
     /* wavefront_compute_affine2p.c:341-351 + wavefront_extend.c:95-103 */
-    num_null++;
-    if (WFB_TID == 0) {
+    if (tid == 0) {
       for (int c = 0; c < 5; ++c) {
         ring.ex[slot][c] = 0;
         ring.lo[nslot][c] = INT_MAX;
         ring.hi[nslot][c] = INT_MIN;
         ring.mak[nslot][c] = INT_MIN;
       }
+      ring.cw[slot] = 0;
       red_maxak[npar] = 0;
     }
-    WFB_SYNC();
-    return (num_null > pen.scope) ? WFB_ST_END_UNREACHABLE : WFB_ST_OK;
+    return;
   }
-  num_null = 0;
   /* wavefront_compute_limits_input, wavefront_compute.c:40-86 */
   int lo = m_misms.lo, hi = m_misms.hi;
   lo = min(lo, m_open1.lo - 1); hi = max(hi, m_open1.hi + 1);
@@ -297,7 +301,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
   const bool ex_i2 = !n_o2 || !n_i2, ex_d2 = !n_o2 || !n_d2;
   int ob[5];
   alloc(slot, lo, hi, ob);
-  if (WFB_TID == 0) {
+  if (tid == 0) {
     ring.ex[slot][WFB_M] = 1;
     ring.ex[slot][WFB_I1] = ex_i1;
     ring.ex[slot][WFB_I2] = ex_i2;
@@ -310,7 +314,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
       ring.mak[nslot][c] = INT_MIN;
     }
     red_maxak[npar] = 0;
-    acc.cells += (unsigned long long)(hi - lo + 1);
+    ring.cw[slot] = hi - lo + 1;
   }
   /* per-thread trim / anti-diagonal accumulators */
   int tlo[5], thi[5];
@@ -384,7 +388,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
     if (!n_d2) { safe_lo = max(safe_lo, d2_ext.lo + 1);  safe_hi = min(safe_hi, d2_ext.hi - 4); }
     safe_hi = min(safe_hi, hi - 3);
     const int kfirst = lo - ((lo + kalign) & 3); /* first group start (<= lo) */
-    for (int k0 = kfirst + 4 * WFB_TID; k0 <= hi; k0 += 4 * WFB_NT) {
+    for (int k0 = kfirst + 4 * tid; k0 <= hi; k0 += 4 * nt) {
       int32_t rm[4], ri1[4], ri2[4], rd1[4], rd2[4];
       if (k0 >= safe_lo && k0 <= safe_hi) {
         const int4 NUL4 = make_int4(WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL);
@@ -456,7 +460,7 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
       }
     }
   } else {
-    for (int k = lo + WFB_TID; k <= hi; k += WFB_NT) {
+    for (int k = lo + tid; k <= hi; k += nt) {
       int32_t rm, ri1, ri2, rd1, rd2;
       WFB_CELL(k, wfb_get(basep, m_open1, k - 1), wfb_get(basep, m_open1, k + 1), wfb_get(basep, m_open2, k - 1),
                wfb_get(basep, m_open2, k + 1), wfb_get(basep, i1_ext, k - 1), wfb_get(basep, i2_ext, k - 1),
@@ -494,20 +498,45 @@ WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, i
       wfb_smem_max(&ring.mak[slot][WFB_M], v); /* extended M cells can exceed the raw bound */
     }
   }
-  WFB_SYNC();
 #if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
-  if (WFB_TID == 0) {
+  if (tid == 0) {
     const int wd = hi - lo + 1, b = wd <= 128 ? 0 : wd <= 1024 ? 1 : wd <= 4096 ? 2 : 3;
     WFB_PT_ADD(4 * b + 0, 1); WFB_PT_ADD(4 * b + 1, WFB_PT_CLOCK() - pt0); WFB_PT_ADD(4 * b + 2, pt1 - pt0); WFB_PT_ADD(4 * b + 3, wd);
   }
 #endif
+}
+
+/* Second half of a score step, AFTER the barrier that follows wfb_step_work: every thread of the CTA derives the
+ * (uniform) outcome from shared memory. wavefront_termination_end2end, wavefront_termination.c:37-114. */
+WFB_DEV int wfb_step_finish(const WfbRing& ring, const WfbPen& pen, int score, int plen, int tlen, int cend, int& num_null,
+                            const int* red_maxak, const int* red_end, int& max_ak_out, WfbAcc& acc, int* width_out = nullptr) {
+  const int slot = score % pen.R, par = score % 3;
+  acc.steps += 1;
+  max_ak_out = 0;
+  if (width_out) *width_out = ring.cw[slot];
+  if (!ring.ex[slot][WFB_M]) { /* the all-null step */
+    num_null++;
+    return (num_null > pen.scope) ? WFB_ST_END_UNREACHABLE : WFB_ST_OK;
+  }
+  num_null = 0;
+  acc.cells += (unsigned long long)ring.cw[slot];
   max_ak_out = red_maxak[par];
-  /* wavefront_termination_end2end, wavefront_termination.c:37-114 */
+  const int ak_end = tlen - plen;
   if (cend >= 0 && ring.ex[slot][cend] && ring.lo[slot][cend] <= ak_end && ak_end <= ring.hi[slot][cend]) {
     /* ak_end lies inside the trimmed range => it was computed in this step => red_end[par] is fresh */
     if (red_end[par] >= tlen) return WFB_ST_END_REACHED;
   }
   return WFB_ST_OK;
+}
+
+/* The whole CTA on one direction: work, ONE barrier, outcome. */
+template <class Alloc>
+WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
+                     const uint8_t* tseq, int plen, int tlen, int cend, int& num_null, Alloc& alloc, int* red_maxak,
+                     int* red_end, int& max_ak_out, WfbAcc& acc) {
+  wfb_step_work(ring, basep, pen, score, pseq, tseq, plen, tlen, cend, alloc, red_maxak, red_end, acc, WFB_TID, WFB_NT);
+  WFB_SYNC();
+  return wfb_step_finish(ring, pen, score, plen, tlen, cend, num_null, red_maxak, red_end, max_ak_out, acc);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -534,6 +563,7 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
                          WfbBreakpoint* bp, WfbOverlapShared* os, WfbAcc& acc) {
   const int R = pen.R, s0 = score_0 % R;
   if (!r0.ex[s0][WFB_M]) return; /* uniform */
+  const int s1cur = score_1 % R; /* slots of score_1 - i follow by subtraction (i < scope < R) */
 #if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
   const long long pto = WFB_PT_CLOCK();
   struct PtScope { long long t0; WFB_DEV_MEMBER ~PtScope() { if (WFB_TID == 0) { WFB_PT_ADD(16, WFB_PT_CLOCK() - t0); WFB_PT_ADD(17, 1); } } } pt_scope{pto};
@@ -549,7 +579,7 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
     const int score_i = score_1 - i;
     bool ok = score_i >= 0;
     if (ok) {
-      const int si = score_i % R;
+      const int si = wfb_slot_back(s1cur, i, R);
       ok = (score_0 + score_i - wfb_gap_of(pen, c) < best0) && r0.ex[s0][c] && r1.ex[si][c];
       /* off0[k0] + off1[kinv-k0] >= tlen  <=>  ak0 + ak1 >= plen + tlen (ak = 2*off - k): no diagonal can
        * satisfy it unless the two wavefronts' maximal anti-diagonals do */
@@ -577,7 +607,7 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
     const int q = os->cand[ci];
     const int i = q / 5, j = q - i * 5;
     const int c = j == 0 ? WFB_D2 : j == 1 ? WFB_I2 : j == 2 ? WFB_D1 : j == 3 ? WFB_I1 : WFB_M;
-    const int si = (score_1 - i) % R;
+    const int si = wfb_slot_back(s1cur, i, R);
     const int lo_0 = r0.lo[s0][c], hi_0 = r0.hi[s0][c];
     const int lo_1 = kinv - r1.hi[si][c], hi_1 = kinv - r1.lo[si][c];
     const int max_lo = max(lo_0, lo_1), min_hi = min(hi_0, hi_1);
@@ -655,7 +685,7 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
         const int q = w * 32 + b;
         const int i = q / 5, j = q - i * 5;
         const int c = j == 0 ? WFB_D2 : j == 1 ? WFB_I2 : j == 2 ? WFB_D1 : j == 3 ? WFB_I1 : WFB_M;
-        const int score_i = score_1 - i, si = score_i % R;
+        const int score_i = score_1 - i, si = wfb_slot_back(s1cur, i, R);
         const int cand = score_0 + score_i - wfb_gap_of(pen, c);
         const int k0 = os->found[q];
         os->found[q] = INT_MAX;
@@ -879,7 +909,67 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
   const int max_antidiagonal = plen + tlen - 1;
   bool last_wf_forward = false;
   int max_ak = 0;
-  /* phase 1 (:1010-1043): alternate until the furthest points of both directions may collide */
+  /* phase 1 (:1010-1043): alternate until the furthest points of both directions may collide.
+   * The forward step to score_forward+1 and the reverse step to score_reverse+1 do not depend on each other, so the
+   * two halves of the CTA compute them at the same time and share ONE barrier (a score step is a chain of dependent
+   * latencies; narrow wavefronts leave most warps idle). The reference's order is kept exactly: the forward outcome is
+   * examined first, and when it ends the phase the reverse step is not accepted — nothing of it is visible afterwards
+   * (its ring slot and the slot it resets lie outside the scope window because R = scope + 2, and re-running the step
+   * later rewrites the same values). */
+#if WFB_DUAL_PHASE1
+  int width_f = 1, width_r = 1;
+  while (status == WFB_ST_OK) {
+    if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
+    const unsigned long long m_before = acc.matches;
+#ifndef WFB_EMU
+    /* warps are dealt to the two directions in proportion to the widths of their last wavefronts */
+    const int nwarps = WFB_NT >> 5;
+    int fw = nwarps >> 1; /* eighths of the CTA for the forward direction, without a division */
+    if (3 * width_f > 5 * width_r) fw = (nwarps * 5) >> 3;
+    if (width_f > 3 * width_r) fw = (nwarps * 3) >> 2;
+    if (3 * width_r > 5 * width_f) fw = (nwarps * 3) >> 3;
+    if (width_r > 3 * width_f) fw = nwarps >> 2;
+    fw = fw < 1 ? 1 : (fw > nwarps - 1 ? nwarps - 1 : fw);
+    const int fnt = fw << 5;
+    const bool rev_half = WFB_TID >= fnt;
+    { /* one call site (one copy of the step body in the instruction cache); the direction is a per-warp choice */
+      const int d = rev_half ? 1 : 0;
+      WfbAllocFixed ad = af;
+      ad.dirbase = rev_half ? ar.dirbase : af.dirbase;
+      wfb_step_work(sh.ring[d], ws, pen, (rev_half ? score_reverse : score_forward) + 1, rev_half ? pr : pf, rev_half ? tr : tf, plen, tlen,
+                    rev_half ? t.cbegin : t.cend, ad, sh.red_maxak[d], sh.red_end[d], acc, rev_half ? WFB_TID - fnt : WFB_TID,
+                    rev_half ? WFB_NT - fnt : fnt);
+    }
+#else
+    const bool rev_half = true; /* the single emulated thread plays both halves, one after the other */
+    wfb_step_work(sh.ring[0], ws, pen, score_forward + 1, pf, tf, plen, tlen, t.cend, af, sh.red_maxak[0], sh.red_end[0], acc, 0, 1);
+    const unsigned long long m_mid = acc.matches;
+    wfb_step_work(sh.ring[1], ws, pen, score_reverse + 1, pr, tr, plen, tlen, t.cbegin, ar, sh.red_maxak[1], sh.red_end[1], acc, 0, 1);
+#endif
+    WFB_SYNC();
+    ++score_forward;
+    int st = wfb_step_finish(sh.ring[0], pen, score_forward, plen, tlen, t.cend, null_f, sh.red_maxak[0], sh.red_end[0], max_ak, acc, &width_f);
+    if (forward_max_ak < max_ak) forward_max_ak = max_ak;
+    last_wf_forward = true;
+    const bool stop_after_forward = (st != WFB_ST_OK) || (forward_max_ak + reverse_max_ak >= max_antidiagonal);
+    if (stop_after_forward) {
+      /* the reverse step was speculative: forget the matches it counted (cells / steps are only counted on acceptance) */
+#ifndef WFB_EMU
+      if (rev_half) acc.matches = m_before;
+#else
+      acc.matches = m_mid;
+#endif
+      if (st != WFB_ST_OK) { status = st; score_reached = score_forward; }
+      break;
+    }
+    (void)rev_half; (void)m_before;
+    ++score_reverse;
+    st = wfb_step_finish(sh.ring[1], pen, score_reverse, plen, tlen, t.cbegin, null_r, sh.red_maxak[1], sh.red_end[1], max_ak, acc, &width_r);
+    if (reverse_max_ak < max_ak) reverse_max_ak = max_ak;
+    last_wf_forward = false;
+    if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
+  }
+#else
   while (status == WFB_ST_OK) {
     if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
     ++score_forward;
@@ -894,6 +984,7 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
     last_wf_forward = false;
     if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
   }
+#endif
   /* phase 2 (:1045-1079): advance while scanning for overlaps */
   const int gap_opening = max(pen.o1, pen.o2);
   while (status == WFB_ST_OK) {

@@ -28,3 +28,8 @@ for b, name in enumerate(["<=128", "<=1024", "<=4096", ">4096"]):
         print(f"width {name:7s} steps {s_:10d} cyc/step {cyc / s_:9.0f} thread0-own {c0 / s_:9.0f} mean width {wd / s_:8.0f} share of CTA cycles {cyc / tot:.3f}")
 if v[17]:
     print(f"overlap calls {v[17]} cyc/call {v[16] / v[17]:.0f} share {v[16] / tot:.3f}")
+GHZ = 1.965
+if v[21]:
+    print(f"base tasks {v[21]} mean {v[20] / v[21] / GHZ / 1e3:.1f} us (backtrace {v[22] / max(1, v[23]) / GHZ / 1e3:.1f} us) total {v[20] / GHZ / 1e9:.2f} CTA-s")
+if v[25]:
+    print(f"break tasks {v[25]} mean {v[24] / v[25] / GHZ / 1e3:.1f} us total {v[24] / GHZ / 1e9:.2f} CTA-s; waiting for tasks {v[26] / GHZ / 1e9:.2f} CTA-s; kernel x 296 CTAs = {st.kernel_ms * 0.296:.2f} CTA-s")

@@ -27,11 +27,11 @@
 #ifndef WFB_UNROLL
 #define WFB_UNROLL 1
 #endif
-#ifndef WFB_BATCH_EXTEND
-#define WFB_BATCH_EXTEND 0
-#endif
 #ifndef WFB_OVL_UNROLL
 #define WFB_OVL_UNROLL 4
+#endif
+#ifndef WFB_PF_NEXT
+#define WFB_PF_NEXT 1
 #endif
 #ifndef WFB_DUAL_PHASE1
 #define WFB_DUAL_PHASE1 1
@@ -196,22 +196,17 @@ WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
   return wfb_match_run_words(p, t, limit);
 }
 
-/* XOR of the four bases at pattern[off-k ..] and text[off ..] (0 = all four equal; the lowest differing byte gives the
- * common-prefix length). No control flow: the four loads of several cells can be in flight together. A cell without a
- * valid offset (off < 0) issues no loads and reports "first base differs". Reads up to 7 bytes past the position
- * (padded buffers). */
-WFB_DEV uint32_t wfb_match_head4(const uint8_t* pseq, const uint8_t* tseq, int32_t off, int k) {
-  const bool ok = off >= 0;
-  const uintptr_t pa = (uintptr_t)(pseq + (ok ? off - k : 0)), ta = (uintptr_t)(tseq + (ok ? off : 0));
-  const uint32_t* pw = (const uint32_t*)(pa & ~(uintptr_t)3);
-  const uint32_t* tw = (const uint32_t*)(ta & ~(uintptr_t)3);
-  uint32_t p0 = 0, p1 = 0, t0 = 1, t1 = 0;
-  if (ok) { p0 = wfb_ldg32(pw); p1 = wfb_ldg32(pw + 1); t0 = wfb_ldg32(tw); t1 = wfb_ldg32(tw + 1); }
-  const uint32_t x = __funnelshift_r(p0, p1, (unsigned)(pa & 3) * 8u) ^ __funnelshift_r(t0, t1, (unsigned)(ta & 3) * 8u);
-  return ok ? x : 1u;
+WFB_DEV void wfb_prefetch_row(const void* p) {
+#ifndef WFB_EMU
+#if (WFB_PF_NEXT & 3) == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+#else
+  (void)p;
+#endif
 }
-
-/* L2 prefetch of one 128-byte line (the rows a later score step will read come from DRAM otherwise) */
 WFB_DEV void wfb_prefetch_l2(const void* p) {
 #ifndef WFB_EMU
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -225,8 +220,10 @@ WFB_DEV bool wfb_inbounds(int32_t off, int k, int plen, int tlen) {
 }
 
 /* Optional phase timers (-DWFB_PHASE_TIMERS, tuning builds only): per wavefront-width bucket b in {<=128, <=1024,
- * <=4096, >4096}: [4b+0] steps, [4b+1] SM cycles entry -> barrier passed, [4b+2] cycles of thread 0's own cells,
- * [4b+3] diagonals. [16] = cycles in overlap scans, [17] = overlap calls. Thread 0 sits at the lo edge of the wavefront. */
+ * <=4096, >4096}: [4b+0] steps, [4b+1] SM cycles entry -> end of the step's work, [4b+2] cycles of thread 0's own cells,
+ * [4b+3] diagonals. [16] = cycles in overlap scans, [17] = overlap calls. [20],[21] = cycles / count of base-case tasks,
+ * [22],[23] = of their single-thread backtraces, [24],[25] = of breakpoint tasks, [26] = cycles CTAs waited for a task.
+ * Thread 0 sits at the lo edge of the wavefront. */
 #if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
 __device__ unsigned long long g_wfb_phase[32];
 #define WFB_PT_CLOCK() ((long long)clock64())
@@ -254,9 +251,10 @@ struct WfbAcc {
 template <class Alloc>
 WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
                      const uint8_t* tseq, int plen, int tlen, int cend, Alloc& alloc, int* red_maxak,
-                     int* red_end, WfbAcc& acc, const int tid, const int nt) {
-  const int R = pen.R, slot = score % R, nslot = slot + 1 == R ? 0 : slot + 1;
-  const int par = score % 3, npar = par == 2 ? 0 : par + 1;
+                     int* red_end, WfbAcc& acc, const int tid, const int nt, const int slot /* score % R */,
+                     const int par /* score % 3 */) {
+  const int R = pen.R, nslot = slot + 1 == R ? 0 : slot + 1;
+  const int npar = par == 2 ? 0 : par + 1;
   (void)basep;
   /* every distance below is <= max_score_scope = R - 1 */
   const int d_x = pen.x, d_o1 = pen.o1 + pen.e1, d_o2 = pen.o2 + pen.e2;
@@ -388,13 +386,44 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
     if (!n_d2) { safe_lo = max(safe_lo, d2_ext.lo + 1);  safe_hi = min(safe_hi, d2_ext.hi - 4); }
     safe_hi = min(safe_hi, hi - 3);
     const int kfirst = lo - ((lo + kalign) & 3); /* first group start (<= lo) */
+#if WFB_PF_NEXT & 4
+    if (Alloc::kFixedRows) {
+      /* the first pass of the NEXT score step reads rows that already exist (all but the ones this step writes):
+       * bring this thread's part of them towards the SM now */
+      const int kp = kfirst + 4 * tid;
+      if (kp <= hi) {
+        if (d_x > 1)  wfb_prefetch_row(basep + alloc.row(wfb_slot_back(nslot, d_x, R), WFB_M) + kp);
+        if (d_o1 > 1) wfb_prefetch_row(basep + alloc.row(wfb_slot_back(nslot, d_o1, R), WFB_M) + kp);
+        if (d_o2 > 1) wfb_prefetch_row(basep + alloc.row(wfb_slot_back(nslot, d_o2, R), WFB_M) + kp);
+        if (pen.e1 > 1) {
+          wfb_prefetch_row(basep + alloc.row(wfb_slot_back(nslot, pen.e1, R), WFB_I1) + kp);
+          wfb_prefetch_row(basep + alloc.row(wfb_slot_back(nslot, pen.e1, R), WFB_D1) + kp);
+        }
+      }
+    }
+#endif
     for (int k0 = kfirst + 4 * tid; k0 <= hi; k0 += 4 * nt) {
       int32_t rm[4], ri1[4], ri2[4], rd1[4], rd2[4];
-      if (k0 >= safe_lo && k0 <= safe_hi) {
-        const int4 NUL4 = make_int4(WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL);
-        int4 vo1 = NUL4, vo2 = NUL4, vi1 = NUL4, vi2 = NUL4, vd1 = NUL4, vd2 = NUL4, vmm = NUL4;
-        int32_t so1m = WFB_OFFSET_NULL, so1p = WFB_OFFSET_NULL, so2m = WFB_OFFSET_NULL, so2p = WFB_OFFSET_NULL;
-        int32_t si1 = WFB_OFFSET_NULL, si2 = WFB_OFFSET_NULL, sd1 = WFB_OFFSET_NULL, sd2 = WFB_OFFSET_NULL;
+#if WFB_PF_NEXT & 3
+      { /* the rows this thread reads in its NEXT pass come from L2 / HBM: start them now, no registers needed */
+        const int kn = k0 + 4 * nt;
+        if (kn >= safe_lo && kn <= safe_hi) {
+          if (!n_o1) wfb_prefetch_row(basep + m_open1.off + kn);
+          if (!n_o2) wfb_prefetch_row(basep + m_open2.off + kn);
+          if (!n_i1) wfb_prefetch_row(basep + i1_ext.off + kn);
+          if (!n_i2) wfb_prefetch_row(basep + i2_ext.off + kn);
+          if (!n_d1) wfb_prefetch_row(basep + d1_ext.off + kn);
+          if (!n_d2) wfb_prefetch_row(basep + d2_ext.off + kn);
+          if (!n_m)  wfb_prefetch_row(basep + m_misms.off + kn);
+        }
+      }
+#endif
+      const bool safe = k0 >= safe_lo && k0 <= safe_hi;
+      const int4 NUL4 = make_int4(WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL);
+      int4 vo1 = NUL4, vo2 = NUL4, vi1 = NUL4, vi2 = NUL4, vd1 = NUL4, vd2 = NUL4, vmm = NUL4;
+      int32_t so1m = WFB_OFFSET_NULL, so1p = WFB_OFFSET_NULL, so2m = WFB_OFFSET_NULL, so2p = WFB_OFFSET_NULL;
+      int32_t si1 = WFB_OFFSET_NULL, si2 = WFB_OFFSET_NULL, sd1 = WFB_OFFSET_NULL, sd2 = WFB_OFFSET_NULL;
+      if (safe) {
         if (!n_o1) { const int32_t* p = basep + m_open1.off + k0; vo1 = *(const int4*)p; so1m = p[-1]; so1p = p[4]; }
         if (!n_o2) { const int32_t* p = basep + m_open2.off + k0; vo2 = *(const int4*)p; so2m = p[-1]; so2p = p[4]; }
         if (!n_i1) { const int32_t* p = basep + i1_ext.off + k0; vi1 = *(const int4*)p; si1 = p[-1]; }
@@ -402,61 +431,51 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
         if (!n_d1) { const int32_t* p = basep + d1_ext.off + k0; vd1 = *(const int4*)p; sd1 = p[4]; }
         if (!n_d2) { const int32_t* p = basep + d2_ext.off + k0; vd2 = *(const int4*)p; sd2 = p[4]; }
         if (!n_m)  { vmm = *(const int4*)(basep + m_misms.off + k0); }
-#if WFB_BATCH_EXTEND
-        WFB_CELL_A(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
-        WFB_CELL_A(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
-        WFB_CELL_A(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
-        WFB_CELL_A(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
-        {
-          /* extension of the four M cells with the first round of sequence loads of all four in flight together
-           * (16 independent loads, one memory round trip); only cells whose first four bases match go on */
-          uint32_t xr[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) xr[u] = wfb_match_head4(pseq, tseq, rm[u], k0 + u);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (rm[u] >= 0) {
-              const int v_ = rm[u] - (k0 + u);
-              const int lim_ = min(plen - v_, tlen - rm[u]);
-              int nrun = xr[u] ? ((__ffs((int)xr[u]) - 1) >> 3) : 4;
-              if (nrun >= lim_) nrun = lim_;
-              else if (nrun == 4) nrun = 4 + wfb_match_run_words(pseq + v_ + 4, tseq + rm[u] + 4, lim_ - 4);
-              WFB_CELL_X(k0 + u, rm[u], nrun)
-            }
-          }
-        }
-#else
-        WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
-        WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
-        WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
-        WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
-#endif
-        if ((unsigned)(ak_end - k0) < 4u) { /* constant indices keep the arrays in registers */
-          WFB_END_HANDOFF(k0 + 0, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
-          WFB_END_HANDOFF(k0 + 1, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
-          WFB_END_HANDOFF(k0 + 2, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
-          WFB_END_HANDOFF(k0 + 3, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
-        }
+      } else {
+        /* ragged group at an end of some input: the same 36 values by range-checked element loads, all independent
+         * (one memory round trip for the group instead of one per cell). Diagonals outside [lo,hi] see only nulls
+         * and produce nothing (no valid offset, no trim update); their stores are skipped below. */
+        vo1 = make_int4(wfb_get(basep, m_open1, k0), wfb_get(basep, m_open1, k0 + 1), wfb_get(basep, m_open1, k0 + 2), wfb_get(basep, m_open1, k0 + 3));
+        so1m = wfb_get(basep, m_open1, k0 - 1); so1p = wfb_get(basep, m_open1, k0 + 4);
+        vo2 = make_int4(wfb_get(basep, m_open2, k0), wfb_get(basep, m_open2, k0 + 1), wfb_get(basep, m_open2, k0 + 2), wfb_get(basep, m_open2, k0 + 3));
+        so2m = wfb_get(basep, m_open2, k0 - 1); so2p = wfb_get(basep, m_open2, k0 + 4);
+        vi1 = make_int4(wfb_get(basep, i1_ext, k0), wfb_get(basep, i1_ext, k0 + 1), wfb_get(basep, i1_ext, k0 + 2), WFB_OFFSET_NULL);
+        si1 = wfb_get(basep, i1_ext, k0 - 1);
+        vi2 = make_int4(wfb_get(basep, i2_ext, k0), wfb_get(basep, i2_ext, k0 + 1), wfb_get(basep, i2_ext, k0 + 2), WFB_OFFSET_NULL);
+        si2 = wfb_get(basep, i2_ext, k0 - 1);
+        vd1 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d1_ext, k0 + 1), wfb_get(basep, d1_ext, k0 + 2), wfb_get(basep, d1_ext, k0 + 3));
+        sd1 = wfb_get(basep, d1_ext, k0 + 4);
+        vd2 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d2_ext, k0 + 1), wfb_get(basep, d2_ext, k0 + 2), wfb_get(basep, d2_ext, k0 + 3));
+        sd2 = wfb_get(basep, d2_ext, k0 + 4);
+        vmm = make_int4(wfb_get(basep, m_misms, k0), wfb_get(basep, m_misms, k0 + 1), wfb_get(basep, m_misms, k0 + 2), wfb_get(basep, m_misms, k0 + 3));
+      }
+      WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+      WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+      WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+      WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+      if ((unsigned)(ak_end - k0) < 4u) { /* constant indices keep the arrays in registers */
+        WFB_END_HANDOFF(k0 + 0, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+        WFB_END_HANDOFF(k0 + 1, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+        WFB_END_HANDOFF(k0 + 2, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+        WFB_END_HANDOFF(k0 + 3, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+      }
+      if (k0 >= lo && k0 + 3 <= hi) {
         *(int4*)(basep + ob[WFB_M] + k0) = make_int4(rm[0], rm[1], rm[2], rm[3]);
         if (ex_i1) *(int4*)(basep + ob[WFB_I1] + k0) = make_int4(ri1[0], ri1[1], ri1[2], ri1[3]);
         if (ex_i2) *(int4*)(basep + ob[WFB_I2] + k0) = make_int4(ri2[0], ri2[1], ri2[2], ri2[3]);
         if (ex_d1) *(int4*)(basep + ob[WFB_D1] + k0) = make_int4(rd1[0], rd1[1], rd1[2], rd1[3]);
         if (ex_d2) *(int4*)(basep + ob[WFB_D2] + k0) = make_int4(rd2[0], rd2[1], rd2[2], rd2[3]);
       } else {
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + u;
-          if (k < lo || k > hi) continue;
-          WFB_CELL(k, wfb_get(basep, m_open1, k - 1), wfb_get(basep, m_open1, k + 1), wfb_get(basep, m_open2, k - 1),
-                   wfb_get(basep, m_open2, k + 1), wfb_get(basep, i1_ext, k - 1), wfb_get(basep, i2_ext, k - 1),
-                   wfb_get(basep, d1_ext, k + 1), wfb_get(basep, d2_ext, k + 1), wfb_get(basep, m_misms, k),
-                   rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
-          WFB_END_HANDOFF(k, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
-          basep[ob[WFB_M] + k] = rm[0];
-          if (ex_i1) basep[ob[WFB_I1] + k] = ri1[0];
-          if (ex_i2) basep[ob[WFB_I2] + k] = ri2[0];
-          if (ex_d1) basep[ob[WFB_D1] + k] = rd1[0];
-          if (ex_d2) basep[ob[WFB_D2] + k] = rd2[0];
+#define WFB_STORE1(U)                                                                  \
+        if (k0 + (U) >= lo && k0 + (U) <= hi) {                                        \
+          basep[ob[WFB_M] + k0 + (U)] = rm[U];                                         \
+          if (ex_i1) basep[ob[WFB_I1] + k0 + (U)] = ri1[U];                            \
+          if (ex_i2) basep[ob[WFB_I2] + k0 + (U)] = ri2[U];                            \
+          if (ex_d1) basep[ob[WFB_D1] + k0 + (U)] = rd1[U];                            \
+          if (ex_d2) basep[ob[WFB_D2] + k0 + (U)] = rd2[U];                            \
         }
+        WFB_STORE1(0) WFB_STORE1(1) WFB_STORE1(2) WFB_STORE1(3)
+#undef WFB_STORE1
       }
     }
   } else {
@@ -509,8 +528,9 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
 /* Second half of a score step, AFTER the barrier that follows wfb_step_work: every thread of the CTA derives the
  * (uniform) outcome from shared memory. wavefront_termination_end2end, wavefront_termination.c:37-114. */
 WFB_DEV int wfb_step_finish(const WfbRing& ring, const WfbPen& pen, int score, int plen, int tlen, int cend, int& num_null,
-                            const int* red_maxak, const int* red_end, int& max_ak_out, WfbAcc& acc, int* width_out = nullptr) {
-  const int slot = score % pen.R, par = score % 3;
+                            const int* red_maxak, const int* red_end, int& max_ak_out, WfbAcc& acc, const int slot /* score % R */,
+                            const int par /* score % 3 */, int* width_out = nullptr) {
+  (void)score;
   acc.steps += 1;
   max_ak_out = 0;
   if (width_out) *width_out = ring.cw[slot];
@@ -534,9 +554,10 @@ template <class Alloc>
 WFB_STEP_INLINE int wfb_step(WfbRing& ring, int32_t* basep, const WfbPen& pen, int score, const uint8_t* pseq,
                      const uint8_t* tseq, int plen, int tlen, int cend, int& num_null, Alloc& alloc, int* red_maxak,
                      int* red_end, int& max_ak_out, WfbAcc& acc) {
-  wfb_step_work(ring, basep, pen, score, pseq, tseq, plen, tlen, cend, alloc, red_maxak, red_end, acc, WFB_TID, WFB_NT);
+  const int slot = score % pen.R, par = score % 3;
+  wfb_step_work(ring, basep, pen, score, pseq, tseq, plen, tlen, cend, alloc, red_maxak, red_end, acc, WFB_TID, WFB_NT, slot, par);
   WFB_SYNC();
-  return wfb_step_finish(ring, pen, score, plen, tlen, cend, num_null, red_maxak, red_end, max_ak_out, acc);
+  return wfb_step_finish(ring, pen, score, plen, tlen, cend, num_null, red_maxak, red_end, max_ak_out, acc, slot, par);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -794,6 +815,8 @@ struct WfbAllocFixed { /* breakpoint kernel: every (slot, component) has a fixed
   int kalign;  /* (k + kalign) % 4 == 0  <=>  cell(k) is 16-byte aligned, the same for every row (W % 8 == 0) */
   static constexpr unsigned char* runflag = nullptr;
   static const int runbias = 0;
+  static const bool kFixedRows = true; /* the row of (slot, component) is known before the step that fills it */
+  WFB_DEV_MEMBER int row(int slot, int c) const { return dirbase + (slot * 5 + c) * W; }
   WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) const {
     (void)lo; (void)hi;
     for (int c = 0; c < 5; ++c) ob[c] = dirbase + (slot * 5 + c) * W;
@@ -918,6 +941,9 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
    * later rewrites the same values). */
 #if WFB_DUAL_PHASE1
   int width_f = 1, width_r = 1;
+  /* ring slot / reduction parity of the NEXT forward and reverse score, advanced by hand (no runtime modulo per step) */
+  int nslot_f = (score_forward + 1) % R, npar_f = (score_forward + 1) % 3;
+  int nslot_r = (score_reverse + 1) % R, npar_r = (score_reverse + 1) % 3;
   while (status == WFB_ST_OK) {
     if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
     const unsigned long long m_before = acc.matches;
@@ -938,17 +964,18 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
       ad.dirbase = rev_half ? ar.dirbase : af.dirbase;
       wfb_step_work(sh.ring[d], ws, pen, (rev_half ? score_reverse : score_forward) + 1, rev_half ? pr : pf, rev_half ? tr : tf, plen, tlen,
                     rev_half ? t.cbegin : t.cend, ad, sh.red_maxak[d], sh.red_end[d], acc, rev_half ? WFB_TID - fnt : WFB_TID,
-                    rev_half ? WFB_NT - fnt : fnt);
+                    rev_half ? WFB_NT - fnt : fnt, rev_half ? nslot_r : nslot_f, rev_half ? npar_r : npar_f);
     }
 #else
     const bool rev_half = true; /* the single emulated thread plays both halves, one after the other */
-    wfb_step_work(sh.ring[0], ws, pen, score_forward + 1, pf, tf, plen, tlen, t.cend, af, sh.red_maxak[0], sh.red_end[0], acc, 0, 1);
+    wfb_step_work(sh.ring[0], ws, pen, score_forward + 1, pf, tf, plen, tlen, t.cend, af, sh.red_maxak[0], sh.red_end[0], acc, 0, 1, nslot_f, npar_f);
     const unsigned long long m_mid = acc.matches;
-    wfb_step_work(sh.ring[1], ws, pen, score_reverse + 1, pr, tr, plen, tlen, t.cbegin, ar, sh.red_maxak[1], sh.red_end[1], acc, 0, 1);
+    wfb_step_work(sh.ring[1], ws, pen, score_reverse + 1, pr, tr, plen, tlen, t.cbegin, ar, sh.red_maxak[1], sh.red_end[1], acc, 0, 1, nslot_r, npar_r);
 #endif
     WFB_SYNC();
     ++score_forward;
-    int st = wfb_step_finish(sh.ring[0], pen, score_forward, plen, tlen, t.cend, null_f, sh.red_maxak[0], sh.red_end[0], max_ak, acc, &width_f);
+    int st = wfb_step_finish(sh.ring[0], pen, score_forward, plen, tlen, t.cend, null_f, sh.red_maxak[0], sh.red_end[0], max_ak, acc, nslot_f, npar_f, &width_f);
+    nslot_f = nslot_f + 1 == R ? 0 : nslot_f + 1; npar_f = npar_f == 2 ? 0 : npar_f + 1;
     if (forward_max_ak < max_ak) forward_max_ak = max_ak;
     last_wf_forward = true;
     const bool stop_after_forward = (st != WFB_ST_OK) || (forward_max_ak + reverse_max_ak >= max_antidiagonal);
@@ -964,7 +991,8 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
     }
     (void)rev_half; (void)m_before;
     ++score_reverse;
-    st = wfb_step_finish(sh.ring[1], pen, score_reverse, plen, tlen, t.cbegin, null_r, sh.red_maxak[1], sh.red_end[1], max_ak, acc, &width_r);
+    st = wfb_step_finish(sh.ring[1], pen, score_reverse, plen, tlen, t.cbegin, null_r, sh.red_maxak[1], sh.red_end[1], max_ak, acc, nslot_r, npar_r, &width_r);
+    nslot_r = nslot_r + 1 == R ? 0 : nslot_r + 1; npar_r = npar_r == 2 ? 0 : npar_r + 1;
     if (reverse_max_ak < max_ak) reverse_max_ak = max_ak;
     last_wf_forward = false;
     if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
@@ -1096,6 +1124,8 @@ struct WfbAllocBump {
   unsigned char* runflag; /* ends-free only: runflag[k + runbias] = 1 when M(k) matched >= 4 bases this step; else NULL */
   int runbias;
   int bump; /* next free int in the arena */
+  static const bool kFixedRows = false;
+  WFB_DEV_MEMBER int row(int slot, int c) const { (void)slot; (void)c; return 0; }
   WFB_DEV_MEMBER void operator()(int slot, int lo, int hi, int ob[5]) {
     (void)slot;
     const int n = hi - lo + 1;
@@ -1280,7 +1310,10 @@ WFB_DEV void wfb_base_task(WfbBaseShared& sh, const WfbTask t, const WfbPairDesc
   }
   if (WFB_TID == 0) {
     int nr = 0;
+    const long long pt_bt0 = WFB_PT_CLOCK();
     sh.bt_err = wfb_backtrace(log, arena, score + 1, pen, t.cbegin, t.cend, plen, tlen, score, tlen - plen, tlen, t.pb + t.tb, runs, maxruns, &nr);
+    WFB_PT_ADD(22, WFB_PT_CLOCK() - pt_bt0); WFB_PT_ADD(23, 1);
+    (void)pt_bt0;
     sh.nruns = nr;
   }
   WFB_SYNC();
@@ -1367,6 +1400,8 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
   for (;;) {
     WFB_SYNC();
     if (WFB_TID == 0) {
+      const long long pt_idle0 = WFB_PT_CLOCK();
+      (void)pt_idle0;
       int slot = wfb_atomic_add(q.head, 1);
       if (slot >= q.cap) {
         slot = -1;
@@ -1384,6 +1419,7 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
 #endif
       }
       S.slot = slot;
+      WFB_PT_ADD(26, WFB_PT_CLOCK() - pt_idle0);
     }
     WFB_SYNC();
     const int slot = S.slot;
@@ -1399,13 +1435,17 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
 #else
     t = q.tasks[slot];
 #endif
+    const long long pt_task0 = WFB_PT_CLOCK();
     if (t.score_remaining <= WFB_FALLBACK_MIN_SCORE && t.pe > t.pb && t.te > t.tb) {
       n_base++;
       wfb_base_task(S.base, t, pairs, seq, arena, arena_stride, log, score_cap, runs, maxruns, pen, ops_all, pair_status, acc_base);
+      if (WFB_TID == 0) { WFB_PT_ADD(20, WFB_PT_CLOCK() - pt_task0); WFB_PT_ADD(21, 1); }
     } else {
       n_break++;
       wfb_break_task(S.brk, t, slot, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, nullptr);
+      if (WFB_TID == 0) { WFB_PT_ADD(24, WFB_PT_CLOCK() - pt_task0); WFB_PT_ADD(25, 1); }
     }
+    (void)pt_task0;
     WFB_SYNC();
     if (WFB_TID == 0) {
 #ifndef WFB_EMU

@@ -33,6 +33,9 @@
 #ifndef WFB_PF_NEXT
 #define WFB_PF_NEXT 1
 #endif
+#ifndef WFB_FASTPATH
+#define WFB_FASTPATH 1
+#endif
 #ifndef WFB_DUAL_PHASE1
 #define WFB_DUAL_PHASE1 1
 #endif
@@ -123,6 +126,8 @@ struct WfbRing { /* shared-memory wavefront metadata of the last R scores */
   unsigned char ex[WFB_RMAX][5];
 };
 
+template <bool B> struct WfbBool { static constexpr bool value = B; };
+
 struct WfbIn {
   int off; /* cell(k) = basep[off + k] */
   int lo, hi;
@@ -152,7 +157,7 @@ WFB_DEV int wfb_slot_back(int cur, int d, int R) {
   return s < 0 ? s + R : s;
 }
 WFB_DEV int32_t wfb_get(const int32_t* basep, const WfbIn& w, int k) {
-  return (k >= w.lo && k <= w.hi) ? basep[w.off + k] : WFB_OFFSET_NULL;
+  return (k >= w.lo && k <= w.hi) ? wfb_ld_row1(basep + w.off + k) : WFB_OFFSET_NULL;
 }
 
 /* Length of the common prefix of p[0..] and t[0..], capped at limit. Reads up to 23 bytes past
@@ -402,82 +407,97 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
       }
     }
 #endif
+    /* steady state: all seven inputs exist, so no load is predicated and no null needs materialising; the general
+     * body is kept for the first scores of a task. ALLIN is a compile-time constant of each instantiation. */
+    const bool o_n_m = n_m, o_n_o1 = n_o1, o_n_o2 = n_o2, o_n_i1 = n_i1, o_n_i2 = n_i2, o_n_d1 = n_d1, o_n_d2 = n_d2;
+    const bool o_ex_i1 = ex_i1, o_ex_i2 = ex_i2, o_ex_d1 = ex_d1, o_ex_d2 = ex_d2;
+    auto group_loop = [&](auto allin_tag) {
+      constexpr bool ALLIN = decltype(allin_tag)::value;
+      const bool n_m = ALLIN ? false : o_n_m, n_o1 = ALLIN ? false : o_n_o1, n_o2 = ALLIN ? false : o_n_o2;
+      const bool n_i1 = ALLIN ? false : o_n_i1, n_i2 = ALLIN ? false : o_n_i2, n_d1 = ALLIN ? false : o_n_d1, n_d2 = ALLIN ? false : o_n_d2;
+      const bool ex_i1 = ALLIN ? true : o_ex_i1, ex_i2 = ALLIN ? true : o_ex_i2, ex_d1 = ALLIN ? true : o_ex_d1, ex_d2 = ALLIN ? true : o_ex_d2;
     for (int k0 = kfirst + 4 * tid; k0 <= hi; k0 += 4 * nt) {
-      int32_t rm[4], ri1[4], ri2[4], rd1[4], rd2[4];
+        int32_t rm[4], ri1[4], ri2[4], rd1[4], rd2[4];
 #if WFB_PF_NEXT & 3
-      { /* the rows this thread reads in its NEXT pass come from L2 / HBM: start them now, no registers needed */
-        const int kn = k0 + 4 * nt;
-        if (kn >= safe_lo && kn <= safe_hi) {
-          if (!n_o1) wfb_prefetch_row(basep + m_open1.off + kn);
-          if (!n_o2) wfb_prefetch_row(basep + m_open2.off + kn);
-          if (!n_i1) wfb_prefetch_row(basep + i1_ext.off + kn);
-          if (!n_i2) wfb_prefetch_row(basep + i2_ext.off + kn);
-          if (!n_d1) wfb_prefetch_row(basep + d1_ext.off + kn);
-          if (!n_d2) wfb_prefetch_row(basep + d2_ext.off + kn);
-          if (!n_m)  wfb_prefetch_row(basep + m_misms.off + kn);
+        { /* the rows this thread reads in its NEXT pass come from L2 / HBM: start them now, no registers needed */
+          const int kn = k0 + 4 * nt;
+          if (kn >= safe_lo && kn <= safe_hi) {
+            if (!n_o1) wfb_prefetch_row(basep + m_open1.off + kn);
+            if (!n_o2) wfb_prefetch_row(basep + m_open2.off + kn);
+            if (!n_i1) wfb_prefetch_row(basep + i1_ext.off + kn);
+            if (!n_i2) wfb_prefetch_row(basep + i2_ext.off + kn);
+            if (!n_d1) wfb_prefetch_row(basep + d1_ext.off + kn);
+            if (!n_d2) wfb_prefetch_row(basep + d2_ext.off + kn);
+            if (!n_m)  wfb_prefetch_row(basep + m_misms.off + kn);
+          }
         }
-      }
 #endif
-      const bool safe = k0 >= safe_lo && k0 <= safe_hi;
-      const int4 NUL4 = make_int4(WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL);
-      int4 vo1 = NUL4, vo2 = NUL4, vi1 = NUL4, vi2 = NUL4, vd1 = NUL4, vd2 = NUL4, vmm = NUL4;
-      int32_t so1m = WFB_OFFSET_NULL, so1p = WFB_OFFSET_NULL, so2m = WFB_OFFSET_NULL, so2p = WFB_OFFSET_NULL;
-      int32_t si1 = WFB_OFFSET_NULL, si2 = WFB_OFFSET_NULL, sd1 = WFB_OFFSET_NULL, sd2 = WFB_OFFSET_NULL;
-      if (safe) {
-        if (!n_o1) { const int32_t* p = basep + m_open1.off + k0; vo1 = *(const int4*)p; so1m = p[-1]; so1p = p[4]; }
-        if (!n_o2) { const int32_t* p = basep + m_open2.off + k0; vo2 = *(const int4*)p; so2m = p[-1]; so2p = p[4]; }
-        if (!n_i1) { const int32_t* p = basep + i1_ext.off + k0; vi1 = *(const int4*)p; si1 = p[-1]; }
-        if (!n_i2) { const int32_t* p = basep + i2_ext.off + k0; vi2 = *(const int4*)p; si2 = p[-1]; }
-        if (!n_d1) { const int32_t* p = basep + d1_ext.off + k0; vd1 = *(const int4*)p; sd1 = p[4]; }
-        if (!n_d2) { const int32_t* p = basep + d2_ext.off + k0; vd2 = *(const int4*)p; sd2 = p[4]; }
-        if (!n_m)  { vmm = *(const int4*)(basep + m_misms.off + k0); }
-      } else {
-        /* ragged group at an end of some input: the same 36 values by range-checked element loads, all independent
-         * (one memory round trip for the group instead of one per cell). Diagonals outside [lo,hi] see only nulls
-         * and produce nothing (no valid offset, no trim update); their stores are skipped below. */
-        vo1 = make_int4(wfb_get(basep, m_open1, k0), wfb_get(basep, m_open1, k0 + 1), wfb_get(basep, m_open1, k0 + 2), wfb_get(basep, m_open1, k0 + 3));
-        so1m = wfb_get(basep, m_open1, k0 - 1); so1p = wfb_get(basep, m_open1, k0 + 4);
-        vo2 = make_int4(wfb_get(basep, m_open2, k0), wfb_get(basep, m_open2, k0 + 1), wfb_get(basep, m_open2, k0 + 2), wfb_get(basep, m_open2, k0 + 3));
-        so2m = wfb_get(basep, m_open2, k0 - 1); so2p = wfb_get(basep, m_open2, k0 + 4);
-        vi1 = make_int4(wfb_get(basep, i1_ext, k0), wfb_get(basep, i1_ext, k0 + 1), wfb_get(basep, i1_ext, k0 + 2), WFB_OFFSET_NULL);
-        si1 = wfb_get(basep, i1_ext, k0 - 1);
-        vi2 = make_int4(wfb_get(basep, i2_ext, k0), wfb_get(basep, i2_ext, k0 + 1), wfb_get(basep, i2_ext, k0 + 2), WFB_OFFSET_NULL);
-        si2 = wfb_get(basep, i2_ext, k0 - 1);
-        vd1 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d1_ext, k0 + 1), wfb_get(basep, d1_ext, k0 + 2), wfb_get(basep, d1_ext, k0 + 3));
-        sd1 = wfb_get(basep, d1_ext, k0 + 4);
-        vd2 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d2_ext, k0 + 1), wfb_get(basep, d2_ext, k0 + 2), wfb_get(basep, d2_ext, k0 + 3));
-        sd2 = wfb_get(basep, d2_ext, k0 + 4);
-        vmm = make_int4(wfb_get(basep, m_misms, k0), wfb_get(basep, m_misms, k0 + 1), wfb_get(basep, m_misms, k0 + 2), wfb_get(basep, m_misms, k0 + 3));
-      }
-      WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
-      WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
-      WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
-      WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
-      if ((unsigned)(ak_end - k0) < 4u) { /* constant indices keep the arrays in registers */
-        WFB_END_HANDOFF(k0 + 0, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
-        WFB_END_HANDOFF(k0 + 1, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
-        WFB_END_HANDOFF(k0 + 2, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
-        WFB_END_HANDOFF(k0 + 3, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
-      }
-      if (k0 >= lo && k0 + 3 <= hi) {
-        *(int4*)(basep + ob[WFB_M] + k0) = make_int4(rm[0], rm[1], rm[2], rm[3]);
-        if (ex_i1) *(int4*)(basep + ob[WFB_I1] + k0) = make_int4(ri1[0], ri1[1], ri1[2], ri1[3]);
-        if (ex_i2) *(int4*)(basep + ob[WFB_I2] + k0) = make_int4(ri2[0], ri2[1], ri2[2], ri2[3]);
-        if (ex_d1) *(int4*)(basep + ob[WFB_D1] + k0) = make_int4(rd1[0], rd1[1], rd1[2], rd1[3]);
-        if (ex_d2) *(int4*)(basep + ob[WFB_D2] + k0) = make_int4(rd2[0], rd2[1], rd2[2], rd2[3]);
-      } else {
-#define WFB_STORE1(U)                                                                  \
-        if (k0 + (U) >= lo && k0 + (U) <= hi) {                                        \
-          basep[ob[WFB_M] + k0 + (U)] = rm[U];                                         \
-          if (ex_i1) basep[ob[WFB_I1] + k0 + (U)] = ri1[U];                            \
-          if (ex_i2) basep[ob[WFB_I2] + k0 + (U)] = ri2[U];                            \
-          if (ex_d1) basep[ob[WFB_D1] + k0 + (U)] = rd1[U];                            \
-          if (ex_d2) basep[ob[WFB_D2] + k0 + (U)] = rd2[U];                            \
+        const bool safe = k0 >= safe_lo && k0 <= safe_hi;
+        const int4 NUL4 = make_int4(WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL);
+        int4 vo1 = NUL4, vo2 = NUL4, vi1 = NUL4, vi2 = NUL4, vd1 = NUL4, vd2 = NUL4, vmm = NUL4;
+        int32_t so1m = WFB_OFFSET_NULL, so1p = WFB_OFFSET_NULL, so2m = WFB_OFFSET_NULL, so2p = WFB_OFFSET_NULL;
+        int32_t si1 = WFB_OFFSET_NULL, si2 = WFB_OFFSET_NULL, sd1 = WFB_OFFSET_NULL, sd2 = WFB_OFFSET_NULL;
+        if (safe) {
+          if (!n_o1) { const int32_t* p = basep + m_open1.off + k0; vo1 = wfb_ld_row4(p); so1m = wfb_ld_row1(p - 1); so1p = wfb_ld_row1(p + 4); }
+          if (!n_o2) { const int32_t* p = basep + m_open2.off + k0; vo2 = wfb_ld_row4(p); so2m = wfb_ld_row1(p - 1); so2p = wfb_ld_row1(p + 4); }
+          if (!n_i1) { const int32_t* p = basep + i1_ext.off + k0; vi1 = wfb_ld_row4(p); si1 = wfb_ld_row1(p - 1); }
+          if (!n_i2) { const int32_t* p = basep + i2_ext.off + k0; vi2 = wfb_ld_row4(p); si2 = wfb_ld_row1(p - 1); }
+          if (!n_d1) { const int32_t* p = basep + d1_ext.off + k0; vd1 = wfb_ld_row4(p); sd1 = wfb_ld_row1(p + 4); }
+          if (!n_d2) { const int32_t* p = basep + d2_ext.off + k0; vd2 = wfb_ld_row4(p); sd2 = wfb_ld_row1(p + 4); }
+          if (!n_m)  { vmm = wfb_ld_row4(basep + m_misms.off + k0); }
+        } else {
+          /* ragged group at an end of some input: the same 36 values by range-checked element loads, all independent
+           * (one memory round trip for the group instead of one per cell). Diagonals outside [lo,hi] see only nulls
+           * and produce nothing (no valid offset, no trim update); their stores are skipped below. */
+          vo1 = make_int4(wfb_get(basep, m_open1, k0), wfb_get(basep, m_open1, k0 + 1), wfb_get(basep, m_open1, k0 + 2), wfb_get(basep, m_open1, k0 + 3));
+          so1m = wfb_get(basep, m_open1, k0 - 1); so1p = wfb_get(basep, m_open1, k0 + 4);
+          vo2 = make_int4(wfb_get(basep, m_open2, k0), wfb_get(basep, m_open2, k0 + 1), wfb_get(basep, m_open2, k0 + 2), wfb_get(basep, m_open2, k0 + 3));
+          so2m = wfb_get(basep, m_open2, k0 - 1); so2p = wfb_get(basep, m_open2, k0 + 4);
+          vi1 = make_int4(wfb_get(basep, i1_ext, k0), wfb_get(basep, i1_ext, k0 + 1), wfb_get(basep, i1_ext, k0 + 2), WFB_OFFSET_NULL);
+          si1 = wfb_get(basep, i1_ext, k0 - 1);
+          vi2 = make_int4(wfb_get(basep, i2_ext, k0), wfb_get(basep, i2_ext, k0 + 1), wfb_get(basep, i2_ext, k0 + 2), WFB_OFFSET_NULL);
+          si2 = wfb_get(basep, i2_ext, k0 - 1);
+          vd1 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d1_ext, k0 + 1), wfb_get(basep, d1_ext, k0 + 2), wfb_get(basep, d1_ext, k0 + 3));
+          sd1 = wfb_get(basep, d1_ext, k0 + 4);
+          vd2 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d2_ext, k0 + 1), wfb_get(basep, d2_ext, k0 + 2), wfb_get(basep, d2_ext, k0 + 3));
+          sd2 = wfb_get(basep, d2_ext, k0 + 4);
+          vmm = make_int4(wfb_get(basep, m_misms, k0), wfb_get(basep, m_misms, k0 + 1), wfb_get(basep, m_misms, k0 + 2), wfb_get(basep, m_misms, k0 + 3));
         }
-        WFB_STORE1(0) WFB_STORE1(1) WFB_STORE1(2) WFB_STORE1(3)
+        WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+        WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+        WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+        WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+        if ((unsigned)(ak_end - k0) < 4u) { /* constant indices keep the arrays in registers */
+          WFB_END_HANDOFF(k0 + 0, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+          WFB_END_HANDOFF(k0 + 1, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+          WFB_END_HANDOFF(k0 + 2, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+          WFB_END_HANDOFF(k0 + 3, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+        }
+        if (k0 >= lo && k0 + 3 <= hi) {
+          *(int4*)(basep + ob[WFB_M] + k0) = make_int4(rm[0], rm[1], rm[2], rm[3]);
+          if (ex_i1) *(int4*)(basep + ob[WFB_I1] + k0) = make_int4(ri1[0], ri1[1], ri1[2], ri1[3]);
+          if (ex_i2) *(int4*)(basep + ob[WFB_I2] + k0) = make_int4(ri2[0], ri2[1], ri2[2], ri2[3]);
+          if (ex_d1) *(int4*)(basep + ob[WFB_D1] + k0) = make_int4(rd1[0], rd1[1], rd1[2], rd1[3]);
+          if (ex_d2) *(int4*)(basep + ob[WFB_D2] + k0) = make_int4(rd2[0], rd2[1], rd2[2], rd2[3]);
+        } else {
+#define WFB_STORE1(U)                                                                  \
+          if (k0 + (U) >= lo && k0 + (U) <= hi) {                                        \
+            basep[ob[WFB_M] + k0 + (U)] = rm[U];                                         \
+            if (ex_i1) basep[ob[WFB_I1] + k0 + (U)] = ri1[U];                            \
+            if (ex_i2) basep[ob[WFB_I2] + k0 + (U)] = ri2[U];                            \
+            if (ex_d1) basep[ob[WFB_D1] + k0 + (U)] = rd1[U];                            \
+            if (ex_d2) basep[ob[WFB_D2] + k0 + (U)] = rd2[U];                            \
+          }
+          WFB_STORE1(0) WFB_STORE1(1) WFB_STORE1(2) WFB_STORE1(3)
 #undef WFB_STORE1
+        }
       }
-    }
+    };
+#if WFB_FASTPATH
+    if (!(n_m || n_o1 || n_o2 || n_i1 || n_i2 || n_d1 || n_d2)) group_loop(WfbBool<true>{});
+    else
+#endif
+      group_loop(WfbBool<false>{});
   } else {
     for (int k = lo + tid; k <= hi; k += nt) {
       int32_t rm, ri1, ri2, rd1, rd2;

@@ -31,8 +31,26 @@ WFB_DEV void wfb_smem_max(int* p, int v) { atomicMax(p, v); }
 WFB_DEV int wfb_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 WFB_DEV void wfb_atomic_add64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 WFB_DEV unsigned long long atomicAdd_compat(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+#ifndef WFB_CACHE_HINTS
+#define WFB_CACHE_HINTS 0
+#endif
+#if WFB_CACHE_HINTS
+/* The wavefront rows stream through L1 once per score step and would push the (re-read) sequence bytes out of it:
+ * rows are loaded evict-first, sequence bytes evict-last. */
+WFB_DEV uint32_t wfb_ldg32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.L1::evict_last.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (uint8_t)v; }
+WFB_DEV int4 wfb_ld_row4(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.global.L1::evict_first.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+WFB_DEV int32_t wfb_ld_row1(const int32_t* p) { int32_t v; asm volatile("ld.global.L1::evict_first.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+#else
 WFB_DEV uint32_t wfb_ldg32(const uint32_t* p) { return __ldg(p); }
 WFB_DEV uint8_t wfb_ldg8(const uint8_t* p) { return __ldg(p); }
+WFB_DEV int4 wfb_ld_row4(const int32_t* p) { return *(const int4*)p; }
+WFB_DEV int32_t wfb_ld_row1(const int32_t* p) { return *p; }
+#endif
 #else
 #include <string.h>
 #define WFB_DEV static inline
@@ -66,4 +84,6 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, unsigned shift)
   return (uint32_t)(v >> (shift & 31));
 }
 static inline int __ffs(int v) { return v ? __builtin_ctz((unsigned)v) + 1 : 0; }
+static inline int4 wfb_ld_row4(const int32_t* p) { return *(const int4*)p; }
+static inline int32_t wfb_ld_row1(const int32_t* p) { return *p; }
 #endif

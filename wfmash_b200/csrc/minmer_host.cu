@@ -214,7 +214,19 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   MM_LAUNCH(mm_stream_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, P, d_scratch, scratch_stride, d_rec,
             rec_cap, d_end, d_endcount, d_cnt);
   MM_CHECK(cudaEventRecord(e1));
-  MM_LAUNCH(mm_stitch_ends_kernel, (ns + 63) / 64, 64, d_seqs, ns, s, d_end, d_endcount, d_cnt);
+  { /* stitch 1: parallel passes over all (chunk, entry) pairs until every inherited start is settled */
+    int* d_pending = nullptr;
+    MM_CHECK(cudaMalloc(&d_pending, sizeof(int)));
+    int pending = 1, passes = 0;
+    while (pending > 0 && passes <= nchunks) {
+      MM_CHECK(cudaMemset(d_pending, 0, sizeof(int)));
+      MM_LAUNCH(mm_stitch_ends_pass_kernel, 148 * 8, 256, d_chunks, nchunks, s, d_end, d_endcount, d_cnt, d_pending);
+      MM_CHECK(cudaMemcpy(&pending, d_pending, sizeof(int), cudaMemcpyDeviceToHost));
+      ++passes;
+    }
+    cudaFree(d_pending);
+    if (pending > 0) { wfb_set_last_error_("minmer stitch did not converge"); rc = WFB_ECUDA; goto done; }
+  }
   MM_CHECK(cudaMemcpy(&hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost));
   if (hc.overflow || (long long)hc.n_records > rec_cap) {
     wfb_set_last_error_("minmer stream: capacity overflow (records / heap / pool)");
@@ -304,7 +316,10 @@ done:
   for (int c = 0; c < nchunks; ++c) /* scratch reused: chunk c uses slot 0 */
     mm_stream_kernel(c, nchunks, buf.data(), seqs.data(), chunks.data(), nchunks, P, scratch.data() - (long long)c * scratch_stride,
                      scratch_stride, rec.data(), rec_cap, endst.data(), endcount.data(), &hc);
-  for (int q = 0; q < ns; ++q) mm_stitch_ends_kernel(q, ns, seqs.data(), ns, s, endst.data(), endcount.data(), &hc);
+  for (int pending = 1, passes = 0; pending > 0 && passes <= nchunks; ++passes) {
+    pending = 0;
+    mm_stitch_ends_pass_kernel(0, 1, chunks.data(), nchunks, s, endst.data(), endcount.data(), &hc, &pending);
+  }
   if (hc.overflow || (long long)hc.n_records > rec_cap) { wfb_set_last_error_("minmer stream: capacity overflow"); return WFB_ECAP; }
   const long long nrec = (long long)hc.n_records;
   mm_stitch_records_kernel(0, 1, rec.data(), nrec, chunks.data(), s, endst.data(), endcount.data(), &hc);

@@ -360,29 +360,40 @@ WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmC
   if (overflow) atomicAdd_compat(&counters->overflow, overflow);
 }
 
-/* Stitch 1: resolve the true interval starts of the chunk end states, one thread per sequence walking its
- * chunks in order (each end state has <= s entries sorted by hash). */
-WFB_KERNEL(mm_stitch_ends_kernel, const MmSeq* seqs, int nseqs, int s, MmEndEnt* endstate, const int* endcount,
-           MmCounters* counters) {
+/* Stitch 1: resolve the true interval starts of the chunk end states (each end state has <= s entries sorted by hash),
+ * one thread per (chunk, entry). An inherited entry takes its start from the previous chunk's entry of the same hash
+ * once THAT entry is settled. Passes repeat until *pending == 0: an interval that stays in the sketch across n chunks
+ * takes n passes (one or two on ordinary sequence; the host bounds the count). A writer publishes wpos before it
+ * clears `inherited`. */
+WFB_KERNEL(mm_stitch_ends_pass_kernel, const MmChunk* chunks, int nchunks, int s, MmEndEnt* endstate, const int* endcount,
+           MmCounters* counters, int* pending) {
   WFB_KERNEL_PROLOGUE
-  const int q = bid * WFB_NT + WFB_TID;
-  if (q >= nseqs) return;
-  const MmSeq sq = seqs[q];
-  unsigned long long miss = 0;
-  for (int ci = 1; ci < sq.n_chunks; ++ci) {
-    const int c = sq.first_chunk + ci;
-    MmEndEnt* cur = endstate + (long long)c * s;
+  const long long total = (long long)nchunks * s;
+  for (long long e = (long long)bid * WFB_NT + WFB_TID; e < total; e += (long long)nblocks * WFB_NT) {
+    const int c = (int)(e / s), j = (int)(e - (long long)c * s);
+    if (j >= endcount[c] || chunks[c].first_of_seq) continue;
+    MmEndEnt* cur = endstate + (long long)c * s + j;
+    if (!((volatile MmEndEnt*)cur)->inherited) continue;
     const MmEndEnt* prev = endstate + (long long)(c - 1) * s;
-    const int np = endcount[c - 1], nc = endcount[c];
-    for (int j = 0; j < nc; ++j) {
-      if (!cur[j].inherited) continue;
-      int lo = 0, hi = np;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (prev[mid].hash < cur[j].hash) lo = mid + 1; else hi = mid; }
-      if (lo < np && prev[lo].hash == cur[j].hash) { cur[j].wpos = prev[lo].wpos; cur[j].inherited = 0; }
-      else miss++;
+    const int np = endcount[c - 1];
+    const uint64_t h = cur->hash;
+    int lo = 0, hi = np;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (prev[mid].hash < h) lo = mid + 1; else hi = mid; }
+    if (lo < np && prev[lo].hash == h) {
+      if (((volatile const MmEndEnt*)&prev[lo])->inherited) { wfb_atomic_add(pending, 1); continue; } /* not settled yet */
+#ifndef WFB_EMU
+      __threadfence();
+#endif
+      cur->wpos = ((volatile const MmEndEnt*)&prev[lo])->wpos;
+#ifndef WFB_EMU
+      __threadfence();
+#endif
+      ((volatile MmEndEnt*)cur)->inherited = 0;
+    } else {
+      atomicAdd_compat(&counters->stitch_miss, 1ULL);
+      ((volatile MmEndEnt*)cur)->inherited = 0; /* settled with its local start, like the serial walk leaves it */
     }
   }
-  if (miss) atomicAdd_compat(&counters->stitch_miss, miss);
 }
 
 /* Stitch 2: records that inherited their start take it from the previous chunk's (resolved) end state. */

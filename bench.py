@@ -430,7 +430,15 @@ def main():
         brk_s = (sum(brk_d) / len(brk_d)) / 1e3
         n_brk_launch = max(1, int(stats_d["levels"]))
         achieved = alg_bytes / brk_s / 1e9 if brk_s > 0 else 0.0
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of ONE launch of this kernel from the committed ncu --set full capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tj.get("records") == n and world == 1:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "kernel": "wfb_persist_kernel", "peak_source": peak_src,
                     "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": brk_s * 1e3, "launches_per_step": n_brk_launch,
                     "cells_per_step": stats_d["cells"] + stats_d["base_cells"],

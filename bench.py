@@ -268,6 +268,53 @@ def map_path_section(dev, cores, with_cpu):
                "fragments_per_s": len(frags) / (r["kernel_ms"] / 1e3), "query_mbp_per_s": len(frags) * w / r["kernel_ms"] / 1e3,
                "roofline_frac": l1_bytes / (r["kernel_ms"] / 1e3) / 1e9 / peak},
     }
+    # L1 + L2 fused on the device: the L1 loci stay in HBM, the L2 kernel streams minmerIndex (32 B / record)
+    s1 = wb.stage1_min_hits(k, ssz)
+    ms = wb.l2_min_shared(0.85, k, ssz)
+    m = ix.map_fragments(blob, frags, fqs, 3, cut, grp, stage1_min_hits=s1, l2_min_shared=ms)   # warm-up
+    t0 = time.perf_counter()
+    m = ix.map_fragments(blob, frags, fqs, 3, cut, grp, stage1_min_hits=s1, l2_min_shared=ms)
+    t_map = time.perf_counter() - t0
+    out["l2"] = {"fragments": len(frags), "l1_loci": int(m["n_l1_loci"]), "l2_loci": int(m["l2_loci"]), "mappings": int(len(m["mappings"])),
+                 "index_records_visited": int(m["l2_steps"]), "l1_kernel_ms": m["l1_kernel_ms"], "l2_kernel_ms": m["l2_kernel_ms"],
+                 "sort_kernel_ms": m["sort_kernel_ms"], "loci_per_s": m["l2_loci"] / max(m["l2_kernel_ms"], 1e-9) * 1e3,
+                 "roofline_frac": 32.0 * m["l2_steps"] / (max(m["l2_kernel_ms"], 1e-9) / 1e3) / 1e9 / peak,
+                 "e2e_query_mbp_per_s": len(frags) * w / t_map / 1e6,
+                 "e2e_note": "wfb_map_fragments_batch with host buffers: H2D of the query bases, L1 + L2 + sort kernels, D2H of the mappings"}
+    if with_cpu:
+        # the reference's own computeL2MappedRegions (oracle/_ref/libl2ref.so: slidingMap.hpp + mappingCore.hpp compiled
+        # unmodified) on a sample of the same L1 loci, all host threads
+        ref2 = os.path.join(ROOT, "oracle", "_ref", "libl2ref.so")
+        if os.path.exists(ref2):
+            r1 = ix.map_fragments(blob, frags[:20000], fqs[:20000], 3, cut, grp, stage1_min_hits=s1, l2_min_shared=ms, with_l1=True)
+            l2lib = ctypes.CDLL(ref2)
+            l2lib.ref_l2_open.restype = ctypes.c_void_p
+            kept = np.ascontiguousarray(ix.export()[0])
+            h = ctypes.c_void_p(l2lib.ref_l2_open(ctypes.c_void_p(kept.ctypes.data), ctypes.c_int64(len(kept))))
+            L1 = r1["l1"]
+            todo = [(f, j) for f in range(len(L1["count"])) for j in range(int(L1["offset"][f]), int(L1["offset"][f]) + int(L1["count"][f]))
+                    if L1["loci"]["intersectionSize"][j] >= s1[int(L1["q_count"][f])]]
+            l2dt = np.dtype([("seqId", "<i4"), ("shared", "<i4"), ("mean", "<i8"), ("start", "<i8"), ("end", "<i8"), ("strand", "<i4"), ("pad", "<i4")])
+
+            def one_l2(chunk):
+                o = np.zeros(64, dtype=l2dt)
+                tot = 0
+                for f, j in chunk:
+                    lc = L1["loci"][j]
+                    q = np.ascontiguousarray(L1["q_minmers"][f])
+                    tot += l2lib.ref_l2_locus(h, ctypes.c_void_p(q.ctypes.data), int(L1["q_count"][f]), w, int(lc["seqId"]),
+                                              ctypes.c_int64(int(lc["rangeStartPos"])), ctypes.c_int64(int(lc["rangeEndPos"])),
+                                              ctypes.c_void_p(o.ctypes.data), 64)
+                return tot
+            nthr = max(1, min(cores, 64))
+            chunks = [todo[i::nthr] for i in range(nthr)]
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(max_workers=nthr) as ex:
+                tot = sum(ex.map(one_l2, chunks))
+            dtc = time.perf_counter() - t0
+            l2lib.ref_l2_close(h)
+            out["l2"]["cpu_computeL2MappedRegions"] = {"value": len(todo) / dtc, "unit": "loci/s", "kind": "reference", "cores": nthr,
+                                                       "sample": f"{len(todo)} L1 loci of the first 20000 fragments, {tot} L2 loci, {dtc:.2f} s wall (ctypes call overhead included)"}
     ix.close()
     if with_cpu:
         # CPU side of addMinmers on all host threads (one sequence per thread, like Sketch::build's worker pool,

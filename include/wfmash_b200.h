@@ -308,6 +308,61 @@ typedef struct {
 int wfb_l1_batch(const wfb_index_t*, const wfb_l1_params_t*, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
                  const wfb_frag_query_t* frag_queries, int32_t n, wfb_l1_out_t* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 1 — L2 stage on the GPU-resident index, fused behind the L1 stage: the L1 loci never leave
+ * the device. wfb_map_fragments_batch replaces Map::mapSingleQueryFrag's two stages for a batch of fragments
+ * (src/map/include/computeMap.hpp:879-921): doL1Mapping (:945-983) as wfb_l1_batch does, then per PanSN group slice
+ * doL2Mapping (:989-1061) = stage-1 top-ANI test on the L1 hit count, MappingCore::computeL2MappedRegions
+ * (src/map/include/mappingCore.hpp:306-442) with SlideMapper (src/map/include/slidingMap.hpp:28-215), the identity
+ * test, and the final sort by (refSeqId, refStartPos) (:919-920).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  /* [sketch_size + 1], indexed by Q.sketchSize: smallest L1 intersectionSize that passes the stage-1 top-ANI test
+   * (computeMap.hpp:999-1012; wfb_stage1_min_hits computes it). NULL = param.stage1_topANI_filter off. */
+  const int32_t* stage1_min_hits;
+  int32_t n_stage1_min_hits;
+  /* [sketch_size + 1], indexed by Q.sketchSize: smallest sharedSketchSize whose mapping is kept by the identity test
+   * (computeMap.hpp:1018-1024). With keep_low_pct_id (the CLI default, parse_args.hpp:173) the test uses
+   * Stat::md_lower_bound, i.e. GSL's binomial tail: the host, which links GSL, fills the table;
+   * wfb_l2_min_shared fills it for keep_low_pct_id == false. NULL = keep every mapping. */
+  const int32_t* l2_min_shared;
+  int32_t n_l2_min_shared;
+} wfb_l2_params_t;
+
+typedef struct { /* the MappingResult fields doL2Mapping sets (computeMap.hpp:1029-1044; queryStartPos = 0,
+                    blockLength = Q.len, n_merged = 1) + L2_mapLocus_t's optimalStart / optimalEnd */
+  int32_t frag;              /* index of the fragment in the batch */
+  int32_t refSeqId;
+  int64_t refStartPos;       /* L2_mapLocus_t::meanOptimalPos */
+  int64_t optimalStart, optimalEnd;
+  int32_t conservedSketches; /* L2_mapLocus_t::sharedSketchSize */
+  int32_t strand;            /* FWD = 1, REV = -1 */
+  float nucIdentity;         /* 1 - Stat::j2md(conservedSketches / Q.sketchSize, k) */
+  float kmerComplexity;      /* Q.kmerComplexity */
+} wfb_l2_mapping_t;
+
+typedef struct {
+  /* caller-allocated outputs */
+  wfb_l2_mapping_t* mappings;  /* [mappings_cap], grouped by fragment, inside a fragment by (refSeqId, refStartPos) */
+  int64_t mappings_cap;
+  int64_t* frag_map_offset;    /* [n + 1]: fragment i owns mappings[frag_map_offset[i] .. frag_map_offset[i+1]) */
+  int32_t* frag_status;        /* [n] 0 or WFB_ECAP */
+  wfb_l1_out_t* l1;            /* optional: also return the L1 stage's outputs (parity dumps); NULL on the fast path */
+  /* set by the call */
+  int64_t n_mappings;
+  double l1_kernel_ms, l2_kernel_ms, sort_kernel_ms;
+  uint64_t n_l1_loci;          /* L1 loci produced                                   */
+  uint64_t l2_loci;            /* ... that passed the stage-1 test and were scanned    */
+  uint64_t l2_steps;           /* minmerIndex records the L2 kernel visited (32 B each) */
+} wfb_map_out_t;
+
+int wfb_map_fragments_batch(const wfb_index_t*, const wfb_l1_params_t*, const wfb_l2_params_t*, const char* seq_base, int64_t seq_bytes,
+                            const wfb_frag_t* frags, const wfb_frag_query_t* frag_queries, int32_t n, wfb_map_out_t* out);
+/* out[sketch_size + 1]; hg_numerator = param.hgNumerator (1.0), ani_diff = param.ANIDiff (0.0) */
+int wfb_stage1_min_hits(double hg_numerator, float ani_diff, int32_t kmer_size, int32_t sketch_size, int32_t* out);
+/* out[sketch_size + 1] for keep_low_pct_id == false; percentage_identity in [0,1] */
+int wfb_l2_min_shared(float percentage_identity, int32_t kmer_size, int32_t sketch_size, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

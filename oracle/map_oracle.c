@@ -603,3 +603,225 @@ int orc_l1_fragment(const uint64_t* uhash, const int64_t* ustart, const int64_t*
   free(ip);
   return nout;
 }
+
+/* =================================================================================================
+ * L2: SlideMapper (slidingMap.hpp:28-215) + computeL2MappedRegions (mappingCore.hpp:306-442) for fragments
+ * of length == windowLength (windowLen = 0, so the hash_to_freq multiplicity map never gates anything), and
+ * the part of Map::doL2Mapping / mapSingleQueryFrag that turns L1 loci into fragment mappings
+ * (computeMap.hpp:895-921, 989-1061).
+ * ================================================================================================= */
+typedef struct { uint64_t hash_val; int q_strand; int strand_vote; unsigned num_before_inc; int active; } orc_slot_t;
+typedef struct {
+  orc_slot_t* v; int size;     /* slidingWindowMinhashes: size = sketchSize + 1, slot 0 is the zero dummy */
+  int pivot; long pivRank;     /* pivot as an index into v */
+  int sketchSize;
+  int sharedSketchElements, strand_votes, intersectionSize;
+  int64_t dup_inserts;         /* test probe: a matching insert into an already active slot */
+} orc_slidemap_t;
+
+static void slidemap_init(orc_slidemap_t* m, const orc_minmer_t* q, int q_n) { /* ctor + init(), :84-125 */
+  m->size = q_n + 1;
+  m->v = (orc_slot_t*)calloc((size_t)m->size, sizeof(orc_slot_t));
+  for (int i = 0; i < q_n; ++i) { m->v[i + 1].hash_val = q[i].hash; m->v[i + 1].q_strand = q[i].strand; m->v[i + 1].num_before_inc = 1; }
+  m->pivot = m->size - 1; m->pivRank = m->size - 1; m->sketchSize = q_n;
+  m->sharedSketchElements = 0; m->strand_votes = 0; m->intersectionSize = 0; m->dup_inserts = 0;
+}
+static int slidemap_lower_bound(const orc_slidemap_t* m, uint64_t h) { /* over [1, size) */
+  int lo = 1, hi = m->size;
+  while (lo < hi) { const int mid = (lo + hi) / 2; if (m->v[mid].hash_val < h) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+static void slidemap_insert(orc_slidemap_t* m, uint64_t hash, int strand) { /* :129-170 */
+  const int loc = slidemap_lower_bound(m, hash);
+  if (loc == m->size) return;
+  orc_slot_t* s = &m->v[loc];
+  if (s->hash_val == hash) {
+    if (s->active) m->dup_inserts++;
+    s->active = 1;
+    s->strand_vote = (int16_t)(s->strand_vote + s->q_strand * strand);
+    m->intersectionSize++;
+    if (s->hash_val <= m->v[m->pivot].hash_val) { m->sharedSketchElements++; m->strand_votes += s->strand_vote; }
+  } else {
+    s->num_before_inc++;
+    if (s->hash_val <= m->v[m->pivot].hash_val) m->pivRank++;
+    if (m->pivRank > m->sketchSize) {
+      m->sharedSketchElements -= m->v[m->pivot].active;
+      m->strand_votes -= m->v[m->pivot].strand_vote;
+      m->pivRank -= m->v[m->pivot].num_before_inc;
+      m->pivot--;
+    }
+  }
+}
+static void slidemap_delete(orc_slidemap_t* m, uint64_t hash) { /* :176-214 */
+  const int loc = slidemap_lower_bound(m, hash);
+  if (loc == m->size) return;
+  orc_slot_t* s = &m->v[loc];
+  if (s->hash_val == hash) {
+    if (s->hash_val <= m->v[m->pivot].hash_val) { m->sharedSketchElements--; m->strand_votes -= s->strand_vote; }
+    s->active = 0; s->strand_vote = 0; m->intersectionSize--;
+  } else {
+    s->num_before_inc--;
+    if (s->hash_val <= m->v[m->pivot].hash_val) m->pivRank--;
+    if (m->pivot + 1 != m->size && m->pivRank + m->v[m->pivot + 1].num_before_inc <= (unsigned long)m->sketchSize) {
+      m->pivot++;
+      m->sharedSketchElements += m->v[m->pivot].active;
+      m->strand_votes += m->v[m->pivot].strand_vote;
+      m->pivRank += m->v[m->pivot].num_before_inc;
+    }
+  }
+}
+
+/* min-heap on wpos_end (std::push_heap / pop_heap with heap_cmp, mappingCore.hpp:320). The order in which equal
+ * wpos_end leave is immaterial: every delete of one window step happens before anything is read. */
+typedef struct { int64_t wpos_end; uint64_t hash; } orc_hent_t;
+typedef struct { orc_hent_t* a; int n, cap; } orc_heap2_t;
+static void heap2_push(orc_heap2_t* h, orc_hent_t e) {
+  if (h->n == h->cap) { h->cap = h->cap ? 2 * h->cap : 64; h->a = (orc_hent_t*)realloc(h->a, (size_t)h->cap * sizeof(orc_hent_t)); }
+  int i = h->n++;
+  while (i > 0) { const int p = (i - 1) / 2; if (h->a[p].wpos_end <= e.wpos_end) break; h->a[i] = h->a[p]; i = p; }
+  h->a[i] = e;
+}
+static void heap2_pop(orc_heap2_t* h) {
+  const orc_hent_t e = h->a[--h->n];
+  int i = 0;
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= h->n) break;
+    if (c + 1 < h->n && h->a[c + 1].wpos_end < h->a[c].wpos_end) ++c;
+    if (h->a[c].wpos_end >= e.wpos_end) break;
+    h->a[i] = h->a[c]; i = c;
+  }
+  if (h->n > 0) h->a[i] = e;
+}
+
+static void l2_close_candidate(orc_l2_locus_t* out, int* nout, int cap, orc_l2_locus_t* cur, int32_t seqId, int strand_votes, int w) {
+  cur->meanOptimalPos = (cur->optimalStart + cur->optimalEnd) / 2;
+  cur->seqId = seqId;
+  cur->strand = strand_votes >= 0 ? 1 : -1;
+  if (*nout == 0 || out[(*nout - 1) < cap ? (*nout - 1) : cap - 1].optimalEnd + w < cur->optimalStart) {
+    if (*nout < cap) out[*nout] = *cur;
+    (*nout)++;
+  } else {
+    orc_l2_locus_t* b = &out[*nout - 1];
+    b->optimalEnd = cur->optimalEnd;
+    b->meanOptimalPos = (b->optimalStart + b->optimalEnd) / 2;
+  }
+}
+
+/* index[] = Sketch::minmerIndex (kept minmers, sorted by (seqId, wpos)); q[] = Q.minmerTableQuery (ascending hash),
+ * q_n = Q.sketchSize. Returns the number of L2_mapLocus_t of this L1 locus (l2_vec_out); out must hold them all for
+ * the merge rule to be exact (cap >= (rangeEnd-rangeStart)/w + 2 is always enough). */
+int orc_l2_locus(const orc_minmer_t* index, int64_t n_index, const orc_minmer_t* q, int q_n, int window_len_param, int32_t seqId,
+                 int64_t rangeStartPos, int64_t rangeEndPos, orc_l2_locus_t* out, int cap, int* best_intersection, int64_t* dup_inserts) {
+  const int w = window_len_param;
+  int64_t lo = 0, hi = n_index;
+  { const int64_t key = rangeStartPos - w - 1; /* std::lower_bound with MinmerInfo::operator< = (seqId, wpos), :318-319 */
+    while (lo < hi) { const int64_t mid = (lo + hi) / 2;
+      if (index[mid].seqId < seqId || (index[mid].seqId == seqId && index[mid].wpos < key)) lo = mid + 1; else hi = mid; } }
+  int64_t it = lo;
+  orc_slidemap_t sm; slidemap_init(&sm, q, q_n);
+  orc_heap2_t hp = {0, 0, 0};
+  int bestSketchSize = 1, bestIntersectionSize = 0, in_candidate = 0, nout = 0;
+  orc_l2_locus_t l2; memset(&l2, 0, sizeof(l2));
+  while (it < n_index && index[it].seqId == seqId && index[it].wpos < rangeStartPos) { /* set up the window, :339-355 */
+    if (index[it].wpos_end > rangeStartPos) {
+      const orc_hent_t e = {index[it].wpos_end, index[it].hash};
+      heap2_push(&hp, e);
+      slidemap_insert(&sm, index[it].hash, index[it].strand);
+    }
+    it++;
+  }
+  while (it < n_index && index[it].seqId == seqId && index[it].wpos <= rangeEndPos) { /* :358-423 (windowLen = 0) */
+    const int prev_strand_votes = sm.strand_votes;
+    while (hp.n > 0 && hp.a[0].wpos_end <= index[it].wpos) { slidemap_delete(&sm, hp.a[0].hash); heap2_pop(&hp); }
+    slidemap_insert(&sm, index[it].hash, index[it].strand);
+    { const orc_hent_t e = {index[it].wpos_end, index[it].hash}; heap2_push(&hp, e); }
+    if (sm.intersectionSize > bestIntersectionSize) bestIntersectionSize = sm.intersectionSize;
+    if (sm.sharedSketchElements > bestSketchSize) {
+      nout = 0; /* l2_vec_out.clear() */
+      in_candidate = 1;
+      bestSketchSize = sm.sharedSketchElements;
+      l2.sharedSketchSize = sm.sharedSketchElements;
+      l2.optimalStart = index[it].wpos;
+      l2.optimalEnd = index[it].wpos;
+    } else if (sm.sharedSketchElements == bestSketchSize) {
+      if (!in_candidate) { l2.sharedSketchSize = sm.sharedSketchElements; l2.optimalStart = index[it].wpos; }
+      in_candidate = 1;
+      l2.optimalEnd = index[it].wpos;
+    } else {
+      if (in_candidate) {
+        l2_close_candidate(out, &nout, cap, &l2, index[it].seqId, prev_strand_votes, w);
+        memset(&l2, 0, sizeof(l2));
+      }
+      in_candidate = 0;
+    }
+    it++;
+  }
+  if (in_candidate) l2_close_candidate(out, &nout, cap, &l2, index[it - 1].seqId, sm.strand_votes, w);
+  if (best_intersection) *best_intersection = bestIntersectionSize;
+  if (dup_inserts) *dup_inserts += sm.dup_inserts;
+  free(sm.v); free(hp.a);
+  return nout;
+}
+
+/* Stat::j2md / md2j (map_stats.hpp:56-80) with the reference's float / double mix. */
+float orc_j2md(float j, int k) {
+  if (j == 0) return 1.0f;
+  if (j == 1) return 0.0f;
+  const float mash_dist = (float)(1 - pow((double)(2 * j / (1 + j)), 1.0 / k));
+  return mash_dist;
+}
+float orc_md2j(float d, int k) {
+  const float sim = 1 - d;
+  const float jaccard = (float)(pow((double)sim, (double)k) / (2 - pow((double)sim, (double)k)));
+  return jaccard;
+}
+/* 1 when an L1 locus passes the stage-1 top-ANI test of doL2Mapping (computeMap.hpp:999-1012) */
+int orc_stage1_pass(double hg_numerator, float ani_diff, int kmer_size, int q_sketch_size, int intersection_size) {
+  const double jaccardSimilarity = hg_numerator / q_sketch_size;
+  const double mash_dist = orc_j2md((float)jaccardSimilarity, kmer_size);
+  const double cutoff_ani = fmax(0.0, (1 - mash_dist) - ani_diff);
+  const double cutoff_j = orc_md2j((float)(1 - cutoff_ani), kmer_size);
+  const double candidateJaccard = (double)intersection_size / q_sketch_size;
+  return !(candidateJaccard < cutoff_j);
+}
+
+static int cmp_l2map(const void* a, const void* b) {
+  const orc_l2_mapping_t* x = (const orc_l2_mapping_t*)a; const orc_l2_mapping_t* y = (const orc_l2_mapping_t*)b;
+  if (x->refSeqId != y->refSeqId) return x->refSeqId < y->refSeqId ? -1 : 1;
+  if (x->refStartPos != y->refStartPos) return x->refStartPos < y->refStartPos ? -1 : 1;
+  /* the reference's std::sort compares (refSeqId, refStartPos) only; ties are put in a fixed order here */
+  if (x->optimalStart != y->optimalStart) return x->optimalStart < y->optimalStart ? -1 : 1;
+  if (x->conservedSketches != y->conservedSketches) return x->conservedSketches < y->conservedSketches ? -1 : 1;
+  return 0;
+}
+
+/* mapSingleQueryFrag's L2 half (computeMap.hpp:895-921) over the L1 loci of one fragment: per PanSN group slice the
+ * stage-1 filter keeps the loci whose intersectionSize passes (the heap pops the largest first and stops at the
+ * first failure, so the kept SET is every passing locus), computeL2MappedRegions per kept locus, the identity test
+ * on sharedSketchSize (min_shared = smallest passing value for this Q.sketchSize, 0 = keep all), and the final sort
+ * by (refSeqId, refStartPos). stage1: 0 = off. */
+int orc_l2_fragment(const orc_minmer_t* index, int64_t n_index, const orc_minmer_t* q, int q_n, float kmer_complexity, int kmer_size,
+                    int window_len_param, const orc_l1_locus_t* loci, int n_loci, int stage1, double hg_numerator, float ani_diff,
+                    int min_shared, orc_l2_mapping_t* out, int cap) {
+  int n = 0;
+  const int tcap = 4096;
+  orc_l2_locus_t* tmp = (orc_l2_locus_t*)malloc((size_t)tcap * sizeof(orc_l2_locus_t));
+  for (int i = 0; i < n_loci; ++i) {
+    if (stage1 && !orc_stage1_pass(hg_numerator, ani_diff, kmer_size, q_n, loci[i].intersectionSize)) continue;
+    const int m = orc_l2_locus(index, n_index, q, q_n, window_len_param, loci[i].seqId, loci[i].rangeStartPos, loci[i].rangeEndPos, tmp, tcap, 0, 0);
+    for (int j = 0; j < m && j < tcap; ++j) {
+      if (tmp[j].sharedSketchSize < min_shared) continue;
+      const float mash_dist = orc_j2md((float)(1.0 * tmp[j].sharedSketchSize / q_n), kmer_size);
+      orc_l2_mapping_t r;
+      memset(&r, 0, sizeof(r));
+      r.refSeqId = tmp[j].seqId; r.refStartPos = tmp[j].meanOptimalPos; r.optimalStart = tmp[j].optimalStart; r.optimalEnd = tmp[j].optimalEnd;
+      r.conservedSketches = tmp[j].sharedSketchSize; r.strand = tmp[j].strand; r.nucIdentity = 1 - mash_dist; r.kmerComplexity = kmer_complexity;
+      if (n < cap) out[n] = r;
+      ++n;
+    }
+  }
+  free(tmp);
+  qsort(out, (size_t)(n < cap ? n : cap), sizeof(orc_l2_mapping_t), cmp_l2map);
+  return n;
+}

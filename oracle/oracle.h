@@ -120,6 +120,39 @@ int orc_l1_fragment(const uint64_t* uhash, const int64_t* ustart, const int64_t*
                     int skip_prefix, int lower_triangular, int minimum_hits, int param_sketch_size, int window_len,
                     const int* cutoffs, int ncut, orc_l1_locus_t* out, int cap);
 
+/* L2_mapLocus_t, mappingCore.hpp:33-41 */
+typedef struct {
+  int32_t seqId;
+  int32_t sharedSketchSize;
+  int64_t meanOptimalPos;
+  int64_t optimalStart;
+  int64_t optimalEnd;
+  int32_t strand;
+  int32_t pad_;
+} orc_l2_locus_t;
+
+/* the MappingResult fields doL2Mapping sets (computeMap.hpp:1029-1044) + the L2_mapLocus_t extras */
+typedef struct {
+  int32_t frag;
+  int32_t refSeqId;
+  int64_t refStartPos;
+  int64_t optimalStart;
+  int64_t optimalEnd;
+  int32_t conservedSketches;
+  int32_t strand;
+  float nucIdentity;
+  float kmerComplexity;
+} orc_l2_mapping_t;
+
+int orc_l2_locus(const orc_minmer_t* index, int64_t n_index, const orc_minmer_t* q, int q_n, int window_len_param, int32_t seqId,
+                 int64_t rangeStartPos, int64_t rangeEndPos, orc_l2_locus_t* out, int cap, int* best_intersection, int64_t* dup_inserts);
+float orc_j2md(float j, int k);
+float orc_md2j(float d, int k);
+int orc_stage1_pass(double hg_numerator, float ani_diff, int kmer_size, int q_sketch_size, int intersection_size);
+int orc_l2_fragment(const orc_minmer_t* index, int64_t n_index, const orc_minmer_t* q, int q_n, float kmer_complexity, int kmer_size,
+                    int window_len_param, const orc_l1_locus_t* loci, int n_loci, int stage1, double hg_numerator, float ani_diff,
+                    int min_shared, orc_l2_mapping_t* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

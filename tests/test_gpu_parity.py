@@ -318,6 +318,53 @@ def test_l1_hit_counts_match_oracle(wb, oracle):
     ix.close()
 
 
+def test_l2_mappings_match_oracle(wb, oracle):
+    # L1 + L2 fused on the device (wfb_map_fragments_batch) against the oracle's mapSingleQueryFrag restatement
+    # (oracle L2 pinned to the reference's slidingMap.hpp / mappingCore.hpp by tests/test_l2_emu_cpu.py): every fragment
+    # mapping (refSeqId, refStartPos, optimalStart/End, conservedSketches, strand, nucIdentity bits), both strands,
+    # with and without the stage-1 / identity filters, several (k, w, s).
+    from tests import maputil
+    from tests.test_l2_emu_cpu import L2_CASES, same_mappings
+    total = 0
+    for seed, mode, (k, w, s) in L2_CASES:
+        seqs, ids, groups = maputil.l2_case(seed=seed)
+        index = maputil.oracle_index(oracle, seqs, ids, k, w, s, 0.0002, 3)
+        ix = wb.Index(seqs, ids, k, w, s, index_threads=3)
+        kept = ix.export()[0]
+        assert len(kept) == len(index[0]) and (kept["hash"] == index[0]["hash"]).all() and (kept["wpos"] == index[0]["wpos"]).all()
+        cut = np.array([max(1, int(i * 0.5)) for i in range(1001)], dtype=np.int32)
+        grp = np.array(groups, dtype=np.int32)
+        blob = b"".join(seqs)
+        offs = np.cumsum([0] + [len(x) for x in seqs])
+        frs = maputil.fragments_of(seqs, w)
+        frags = [(int(offs[qi]) + st, w, ids[qi]) for qi, st in frs]
+        fqs = [(ids[qi], groups[qi]) for qi, _ in frs]
+        ss, sp, lt, mh = mode
+        s1 = wb.stage1_min_hits(k, s)
+        assert (s1 == maputil.stage1_table(oracle, 1.0, 0.0, k, s)).all()
+        ms = wb.l2_min_shared(0.85, k, s)
+        for stage1 in (True, False):
+            _, q_all, q_count, loci, want = maputil.oracle_map_fragments(oracle, index, seqs, ids, groups, k, w, s, mode, stage1=stage1,
+                                                                         min_shared=None if stage1 else ms)
+            r = ix.map_fragments(blob, frags, fqs, mh, cut, grp, skip_self=ss, skip_prefix=sp, lower_triangular=lt,
+                                 stage1_min_hits=s1 if stage1 else None, l2_min_shared=None if stage1 else ms, with_l1=True)
+            assert (r["status"] == 0).all()
+            assert (r["l1"]["q_count"] == q_count).all()
+            assert int(r["n_l1_loci"]) == len(loci)
+            got = r["mappings"]
+            assert same_mappings(got, want), (seed, stage1, len(got), len(want))
+            assert (got["kmerComplexity"] == want["kmerComplexity"]).all()
+            off = r["offset"]
+            assert off[0] == 0 and off[-1] == len(got) and (np.diff(off) == np.bincount(got["frag"], minlength=len(frags))).all()
+            assert r["l2_steps"] > r["l2_loci"] > 0
+            total += len(got)
+        # the fast path (no L1 dump) gives the same mappings
+        r2 = ix.map_fragments(blob, frags, fqs, mh, cut, grp, skip_self=ss, skip_prefix=sp, lower_triangular=lt, l2_min_shared=ms)
+        assert same_mappings(r2["mappings"], want)
+        ix.close()
+    assert total > 2000
+
+
 def _patch_cases(seed, n):
     import random
     rng = random.Random(seed)

@@ -1,0 +1,89 @@
+"""CPU checks of the L2 stage:
+  * the oracle's computeL2MappedRegions / SlideMapper restatement against the committed reference fixture and, when
+    oracle/_ref is present, against the reference's unmodified slidingMap.hpp + mappingCore.hpp compiled in place;
+  * the L2 CUDA kernel's BODY (wfmash_b200/csrc/l2_kernels.h) under the single-thread host emulation of tests/emu
+    (TEST INFRASTRUCTURE, -DWFB_EMU; never the product library) against the oracle."""
+import ctypes
+import gzip
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import maputil, util
+
+vp = maputil.vp
+L2_CASES = [(41, (1, 1, 0, 3), (15, 1000, 29)), (9, (0, 0, 0, 2), (15, 1000, 59)), (7, (0, 1, 1, 5), (19, 500, 17)), (11, (1, 1, 0, 2), (15, 256, 11))]
+
+
+def test_l2_oracle_reproduces_reference_fixture(oracle):
+    with gzip.open(os.path.join(util.GOLD, "l2_reference.json.gz"), "rt") as f:
+        gold = json.load(f)
+    assert len(gold["cases"]) == len(L2_CASES)
+    for (seed, mode, (k, w, s)), g in zip(L2_CASES, gold["cases"]):
+        assert (seed, list(mode), [k, w, s]) == (g["seed"], g["mode"], g["kws"])
+        seqs, ids, groups = maputil.l2_case(seed=seed)
+        index = maputil.oracle_index(oracle, seqs, ids, k, w, s, 0.0002, 3)
+        rows = maputil.l2_all_loci(oracle, "orc", index, seqs, ids, groups, k, w, s, oracle, mode)
+        want = np.array(g["rows"], dtype=np.int64).reshape(-1, 8)
+        assert len(want) > 100 and rows.shape == want.shape and (rows == want).all()
+        assert (want[:, 7] == -1).sum() > 20  # both strands are exercised
+
+
+@pytest.mark.ref
+def test_l2_oracle_matches_compiled_reference_live(oracle):
+    ref = util.load_ref("libl2ref.so")
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    for seed, mode, (k, w, s) in [(3, (1, 1, 0, 3), (15, 1000, 29)), (4, (0, 0, 0, 2), (15, 1000, 39)), (6, (0, 1, 0, 2), (21, 300, 13))]:
+        seqs, ids, groups = maputil.l2_case(seed=seed)
+        index = maputil.oracle_index(oracle, seqs, ids, k, w, s, 0.0002, 2)
+        a = maputil.l2_all_loci(ref, "ref", index, seqs, ids, groups, k, w, s, oracle, mode)
+        b = maputil.l2_all_loci(oracle, "orc", index, seqs, ids, groups, k, w, s, oracle, mode)
+        assert len(a) > 100 and a.shape == b.shape and (a == b).all()
+
+
+def same_mappings(got, want):
+    if len(got) != len(want):
+        return False
+    for f in ("frag", "refSeqId", "refStartPos", "optimalStart", "optimalEnd", "conservedSketches", "strand"):
+        if not (got[f] == want[f]).all():
+            return False
+    return bool((got["nucIdentity"].view(np.uint32) == want["nucIdentity"].view(np.uint32)).all()
+                and (got["kmerComplexity"].view(np.uint32) == want["kmerComplexity"].view(np.uint32)).all())
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_l2_kernel_body_under_emulation_matches_oracle(oracle):
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    emu = ctypes.CDLL(os.path.join(util.ROOT, so))
+    total = 0
+    for seed, mode, (k, w, s) in L2_CASES:
+        seqs, ids, groups = maputil.l2_case(seed=seed)
+        index = maputil.oracle_index(oracle, seqs, ids, k, w, s, 0.0002, 3)
+        kept = np.ascontiguousarray(index[0])
+        for stage1 in (True, False):
+            s1 = np.zeros(s + 1, dtype=np.int32)
+            assert emu.wfb_stage1_min_hits(ctypes.c_double(1.0), ctypes.c_float(0.0), k, s, vp(s1)) == 0
+            assert (s1 == maputil.stage1_table(oracle, 1.0, 0.0, k, s)).all()
+            ms = np.zeros(s + 1, dtype=np.int32)
+            assert emu.wfb_l2_min_shared(ctypes.c_float(0.85), k, s, vp(ms)) == 0
+            frs, q_all, q_count, loci, want = maputil.oracle_map_fragments(oracle, index, seqs, ids, groups, k, w, s, mode, stage1=stage1,
+                                                                           min_shared=ms if not stage1 else None)
+            l1 = np.zeros(len(loci), dtype=maputil.L1PUBDT)
+            l1["seqId"], l1["rangeStartPos"], l1["rangeEndPos"], l1["intersectionSize"] = loci[:, 1], loci[:, 2], loci[:, 3], loci[:, 4]
+            lfrag = np.ascontiguousarray(loci[:, 0].astype(np.int32))
+            out = np.zeros(len(want) + 64, dtype=maputil.L2MAPDT)
+            n_out, steps = ctypes.c_int64(0), ctypes.c_uint64(0)
+            status = np.zeros(len(frs), dtype=np.int32)
+            rc = emu.wfb_emu_l2_loci(vp(kept), ctypes.c_int64(len(kept)), vp(l1), vp(lfrag), ctypes.c_int64(len(l1)), vp(q_all), vp(q_count), len(frs),
+                                     k, w, s, vp(s1) if stage1 else None, None if stage1 else vp(ms), vp(out), ctypes.c_int64(len(out)),
+                                     ctypes.byref(n_out), vp(status), ctypes.byref(steps))
+            assert rc == 0 and (status == 0).all()
+            assert same_mappings(out[: n_out.value], want), (seed, stage1)
+            assert steps.value > len(l1)
+            total += n_out.value
+    assert total > 2000

@@ -385,6 +385,91 @@ class Index:
                 "count": cnt[:n], "status": stt[:n], "kernel_ms": out.kernel_ms}
 
 
+    def map_fragments(self, seq: bytes, frags, frag_queries, minimum_hits, sketch_cutoffs, ref_group, skip_self=True, skip_prefix=True,
+                      lower_triangular=False, stage1_min_hits=None, l2_min_shared=None, with_l1=False, mappings_cap=None):
+        """Map::mapSingleQueryFrag's L1 + L2 stages for a batch of fragments (src/map/include/computeMap.hpp:879-921,
+        945-1061; MappingCore::computeL2MappedRegions, mappingCore.hpp:306-442). The L1 loci stay in device memory;
+        with_l1=True also returns them. stage1_min_hits / l2_min_shared: tables indexed by Q.sketchSize (see
+        stage1_min_hits(), l2_min_shared()) or None (filter off)."""
+        fr = np.ascontiguousarray(frags, dtype=FRAG_DTYPE)
+        fq = np.ascontiguousarray(frag_queries, dtype=FRAG_QUERY_DTYPE)
+        n = int(fr.shape[0])
+        cut = np.ascontiguousarray(sketch_cutoffs, dtype=np.int32)
+        grp = np.ascontiguousarray(ref_group, dtype=np.int32)
+        lp = _L1Params(minimum_hits, cut.ctypes.data, len(cut), grp.ctypes.data, len(grp), int(skip_self), int(skip_prefix),
+                       int(lower_triangular), 0.0)
+        s1 = None if stage1_min_hits is None else np.ascontiguousarray(stage1_min_hits, dtype=np.int32)
+        ms = None if l2_min_shared is None else np.ascontiguousarray(l2_min_shared, dtype=np.int32)
+        l2p = _L2Params(s1.ctypes.data if s1 is not None else None, len(s1) if s1 is not None else 0,
+                        ms.ctypes.data if ms is not None else None, len(ms) if ms is not None else 0)
+        cap = mappings_cap or (32 * n + 1024)
+        maps = np.zeros(cap, dtype=L2_MAPPING_DTYPE)
+        moff = np.zeros(n + 1, dtype=np.int64)
+        stt = np.zeros(max(n, 1), dtype=np.int32)
+        l1 = None
+        keep = []
+        if with_l1:
+            loci_cap = 64 * n + 1024
+            qm = np.zeros((max(n, 1), self.s), dtype=MINMER_DTYPE)
+            qn = np.zeros(max(n, 1), dtype=np.int32)
+            kc = np.zeros(max(n, 1), dtype=np.float32)
+            loci = np.zeros(loci_cap, dtype=L1_LOCUS_DTYPE)
+            off = np.zeros(max(n, 1), dtype=np.int64)
+            cnt = np.zeros(max(n, 1), dtype=np.int32)
+            st1 = np.zeros(max(n, 1), dtype=np.int32)
+            l1 = _L1Out(qm.ctypes.data, qn.ctypes.data, kc.ctypes.data, loci.ctypes.data, loci_cap, off.ctypes.data, cnt.ctypes.data,
+                        st1.ctypes.data, 0, 0.0)
+            keep = [qm, qn, kc, loci, off, cnt, st1]
+        out = _MapOut(maps.ctypes.data, cap, moff.ctypes.data, stt.ctypes.data, ctypes.addressof(l1) if l1 is not None else None,
+                      0, 0.0, 0.0, 0.0, 0, 0, 0)
+        rc = self._L.wfb_map_fragments_batch(ctypes.c_void_p(self._h), ctypes.byref(lp), ctypes.byref(l2p), seq, ctypes.c_int64(len(seq)),
+                                             ctypes.c_void_p(fr.ctypes.data), ctypes.c_void_p(fq.ctypes.data), n, ctypes.byref(out))
+        if rc != 0:
+            raise _err(rc)
+        res = {"mappings": maps[: out.n_mappings], "offset": moff, "status": stt[:n], "l1_kernel_ms": out.l1_kernel_ms,
+               "l2_kernel_ms": out.l2_kernel_ms, "sort_kernel_ms": out.sort_kernel_ms, "n_l1_loci": out.n_l1_loci, "l2_loci": out.l2_loci,
+               "l2_steps": out.l2_steps}
+        if with_l1:
+            qm, qn, kc, loci, off, cnt, st1 = keep
+            res["l1"] = {"q_minmers": qm[:n], "q_count": qn[:n], "q_complexity": kc[:n], "loci": loci[: l1.n_loci], "offset": off[:n],
+                         "count": cnt[:n], "status": st1[:n]}
+        return res
+
+
+class _L2Params(ctypes.Structure):
+    _fields_ = [("stage1_min_hits", ctypes.c_void_p), ("n_stage1_min_hits", ctypes.c_int32), ("l2_min_shared", ctypes.c_void_p),
+                ("n_l2_min_shared", ctypes.c_int32)]
+
+
+class _MapOut(ctypes.Structure):
+    _fields_ = [("mappings", ctypes.c_void_p), ("mappings_cap", ctypes.c_int64), ("frag_map_offset", ctypes.c_void_p),
+                ("frag_status", ctypes.c_void_p), ("l1", ctypes.c_void_p), ("n_mappings", ctypes.c_int64), ("l1_kernel_ms", ctypes.c_double),
+                ("l2_kernel_ms", ctypes.c_double), ("sort_kernel_ms", ctypes.c_double), ("n_l1_loci", ctypes.c_uint64),
+                ("l2_loci", ctypes.c_uint64), ("l2_steps", ctypes.c_uint64)]
+
+
+L2_MAPPING_DTYPE = np.dtype([("frag", "<i4"), ("refSeqId", "<i4"), ("refStartPos", "<i8"), ("optimalStart", "<i8"), ("optimalEnd", "<i8"),
+                             ("conservedSketches", "<i4"), ("strand", "<i4"), ("nucIdentity", "<f4"), ("kmerComplexity", "<f4")])
+
+
+def stage1_min_hits(kmer_size: int, sketch_size: int, hg_numerator: float = 1.0, ani_diff: float = 0.0):
+    """Table of the stage-1 top-ANI test of Map::doL2Mapping (computeMap.hpp:999-1012), indexed by Q.sketchSize."""
+    out = np.zeros(sketch_size + 1, dtype=np.int32)
+    rc = lib().wfb_stage1_min_hits(ctypes.c_double(hg_numerator), ctypes.c_float(ani_diff), kmer_size, sketch_size, ctypes.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise _err(rc)
+    return out
+
+
+def l2_min_shared(percentage_identity: float, kmer_size: int, sketch_size: int):
+    """Table of the identity test of Map::doL2Mapping (computeMap.hpp:1018-1024) for keep_low_pct_id == false."""
+    out = np.zeros(sketch_size + 1, dtype=np.int32)
+    rc = lib().wfb_l2_min_shared(ctypes.c_float(percentage_identity), kmer_size, sketch_size, ctypes.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise _err(rc)
+    return out
+
+
 def sketch_fragments(seq: bytes, frags, kmer_size: int, sketch_size: int, device: int = 0):
     """Batched CommonFunc::sketchSequence (src/map/include/commonFunc.hpp:217-323).
     frags: array-like of (seq_offset, len, seq_id). Returns (minmers[n, sketch_size], counts[n], kernel_ms)."""

@@ -1,7 +1,10 @@
 // index_host.cu — host side of the GPU-resident reference index and the batched L1 stage (C ABI:
 // wfb_index_build / wfb_index_export / wfb_index_free / wfb_l1_batch). Kernels: index_kernels.h,
 // minmer_kernels.h, sketch_kernels.h (hand-written); CUB is used for the sorts / scans between them.
-#include "index_kernels.h"
+#include "l2_kernels.h"
+
+#include <math.h>
+#include <cmath>
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -9,6 +12,7 @@
 #include <algorithm>
 #include <string>
 #include <vector>
+#include <limits>
 
 #ifndef WFB_EMU
 #include <cub/cub.cuh>
@@ -297,21 +301,60 @@ extern "C" int wfb_index_sizes(const wfb_index_t* ix, int64_t* n_minmers, int64_
   return WFB_OK;
 }
 
-extern "C" int wfb_l1_batch(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
-                            const wfb_frag_query_t* fq, int32_t n, wfb_l1_out_t* out) {
-  if (!ix || !lp || !out || n < 0 || (n > 0 && (!seq_base || !frags || !fq))) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
+/* ---- L1 (+ L2) over a batch of fragments ------------------------------------------------------------------- */
+static int l1_validate(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
+                       const wfb_frag_query_t* fq, int32_t n) {
+  if (!ix || !lp || n < 0 || (n > 0 && (!seq_base || !frags || !fq))) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
   if (!lp->ref_group || !lp->sketch_cutoffs || lp->n_cutoffs <= 0 || lp->minimum_hits < 1) { wfb_set_last_error_("bad L1 parameters"); return WFB_EINVAL; }
-  const int k = ix->params.kmer_size, w = ix->params.window_size, s = ix->params.sketch_size;
+  const int w = ix->params.window_size, s = ix->params.sketch_size;
   if (s > 512) { wfb_set_last_error_("sketch_size > 512 unsupported by the L1 kernel"); return WFB_EINVAL; }
   for (int i = 0; i < n; ++i) {
     if (frags[i].len != w) { wfb_set_last_error_("L1 kernel handles fragments of length == window_size (windowLen == 0) only"); return WFB_EINVAL; }
     if (frags[i].seq_offset < 0 || frags[i].seq_offset + frags[i].len > seq_bytes) { wfb_set_last_error_("fragment out of range"); return WFB_EINVAL; }
   }
-  out->n_loci = 0;
-  out->kernel_ms = 0;
-  if (n == 0) return WFB_OK;
+  return WFB_OK;
+}
+
+/* Q.kmerComplexity exactly as MappingCore::getSeedHits computes it (src/map/include/mappingCore.hpp:72-74): the first
+ * division is done in long double on the host, like the reference's. */
+static float ix_kmer_complexity(unsigned long long max_hash, int qn, int len, int k) {
+  if (qn <= 0) return 0.f;
+  const double max_hash_01 = (long double)(max_hash) / std::numeric_limits<uint64_t>::max();
+  return (double(qn) / max_hash_01) / ((len - k + 1) * 2);
+}
+
 #ifndef WFB_EMU
+namespace {
+/* per-fragment Q.kmerComplexity from what the L1 kernel left on the device */
+int l1_host_complexity(const unsigned long long* d_qmax, const int* d_qn, int32_t n, int len, int k, std::vector<float>& kc, std::vector<int32_t>& qn) {
   int rc = WFB_OK;
+  std::vector<unsigned long long> mx((size_t)n);
+  qn.resize((size_t)n);
+  kc.resize((size_t)n);
+  IX_CHECK(cudaMemcpy(mx.data(), d_qmax, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+  IX_CHECK(cudaMemcpy(qn.data(), d_qn, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  for (int32_t i = 0; i < n; ++i) kc[(size_t)i] = ix_kmer_complexity(mx[(size_t)i], qn[(size_t)i], len, k);
+done:
+  return rc;
+}
+struct L1Dev { /* what ix_l1_kernel leaves in device memory; the L2 kernel reads it in place */
+  uint8_t* d_seq = nullptr; wfb_frag_t* d_frags = nullptr; IxFragQuery* d_fq = nullptr; int *d_group = nullptr, *d_cut = nullptr;
+  wfb_minmer_t* d_q = nullptr; int *d_qn = nullptr, *d_fn = nullptr, *d_fst = nullptr, *d_lfrag = nullptr; float* d_kc = nullptr;
+  uint64_t* d_gs = nullptr; IxL1Locus *d_ltmp = nullptr, *d_loci = nullptr; unsigned long long *d_lc = nullptr, *d_qmax = nullptr; long long* d_foff = nullptr;
+  long long loci_cap = 0;
+  unsigned long long n_loci = 0;
+  double kernel_ms = 0;
+  int sm_count = 0;
+  ~L1Dev() {
+    cudaFree(d_seq); cudaFree(d_frags); cudaFree(d_fq); cudaFree(d_group); cudaFree(d_cut); cudaFree(d_q); cudaFree(d_qn); cudaFree(d_fn);
+    cudaFree(d_fst); cudaFree(d_lfrag); cudaFree(d_kc); cudaFree(d_gs); cudaFree(d_ltmp); cudaFree(d_loci); cudaFree(d_lc); cudaFree(d_foff); cudaFree(d_qmax);
+  }
+};
+
+int l1_run(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
+           const wfb_frag_query_t* fq, int32_t n, long long loci_cap, L1Dev& D) {
+  int rc = WFB_OK;
+  const int k = ix->params.kmer_size, w = ix->params.window_size, s = ix->params.sketch_size;
   int npow2 = 1;
   while (npow2 < w - k + 1) npow2 <<= 1;
   const size_t sketch_smem = (size_t)npow2 * 12 + (((size_t)w + 15) & ~(size_t)15) + 16;
@@ -320,73 +363,303 @@ extern "C" int wfb_l1_batch(const wfb_index_t* ix, const wfb_l1_params_t* lp, co
   P.skip_self = lp->skip_self; P.skip_prefix = lp->skip_prefix; P.lower_triangular = lp->lower_triangular;
   P.ncut = lp->n_cutoffs; P.smem_cap = 4096; P.gcap = 1 << 17; P.max_loci = 256; P.complexity_threshold = lp->kmer_complexity_threshold;
   const size_t smem = std::max(sketch_smem, (size_t)P.smem_cap * 8);
-  uint8_t* d_seq = nullptr; wfb_frag_t* d_frags = nullptr; IxFragQuery* d_fq = nullptr; int *d_group = nullptr, *d_cut = nullptr;
-  wfb_minmer_t* d_q = nullptr; int *d_qn = nullptr, *d_fn = nullptr, *d_fst = nullptr; float* d_kc = nullptr; uint64_t* d_gs = nullptr;
-  IxL1Locus *d_ltmp = nullptr, *d_loci = nullptr; unsigned long long* d_lc = nullptr; long long* d_foff = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  unsigned long long nl = 0;
   int grid = 0;
-  const long long loci_cap = out->loci_cap;
-  std::vector<IxL1Locus> hl;
+  D.loci_cap = loci_cap;
   IX_CHECK(cudaSetDevice(ix->device));
   {
     cudaDeviceProp prop;
     IX_CHECK(cudaGetDeviceProperties(&prop, ix->device));
+    D.sm_count = prop.multiProcessorCount;
     grid = std::min(n, prop.multiProcessorCount * 4);
   }
-  IX_CHECK(cudaMalloc(&d_seq, (size_t)seq_bytes + 16));
-  IX_CHECK(cudaMemcpy(d_seq, seq_base, (size_t)seq_bytes, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&d_frags, sizeof(wfb_frag_t) * (size_t)n));
-  IX_CHECK(cudaMemcpy(d_frags, frags, sizeof(wfb_frag_t) * (size_t)n, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&d_fq, sizeof(IxFragQuery) * (size_t)n));
-  IX_CHECK(cudaMemcpy(d_fq, fq, sizeof(IxFragQuery) * (size_t)n, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&d_group, 4 * (size_t)lp->n_ref_group));
-  IX_CHECK(cudaMemcpy(d_group, lp->ref_group, 4 * (size_t)lp->n_ref_group, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&d_cut, 4 * (size_t)lp->n_cutoffs));
-  IX_CHECK(cudaMemcpy(d_cut, lp->sketch_cutoffs, 4 * (size_t)lp->n_cutoffs, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&d_q, sizeof(wfb_minmer_t) * (size_t)n * s));
-  IX_CHECK(cudaMemset(d_q, 0, sizeof(wfb_minmer_t) * (size_t)n * s));
-  IX_CHECK(cudaMalloc(&d_qn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_fn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_fst, 4 * (size_t)n));
-  IX_CHECK(cudaMalloc(&d_kc, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&d_foff, 8 * (size_t)n));
-  IX_CHECK(cudaMalloc(&d_gs, 8 * (size_t)P.gcap * grid));
-  IX_CHECK(cudaMalloc(&d_ltmp, sizeof(IxL1Locus) * (size_t)2 * P.max_loci * grid));
-  IX_CHECK(cudaMalloc(&d_loci, sizeof(IxL1Locus) * (size_t)std::max<long long>(loci_cap, 1)));
-  IX_CHECK(cudaMalloc(&d_lc, 8)); IX_CHECK(cudaMemset(d_lc, 0, 8));
+  IX_CHECK(cudaMalloc(&D.d_seq, (size_t)seq_bytes + 16));
+  IX_CHECK(cudaMemcpy(D.d_seq, seq_base, (size_t)seq_bytes, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&D.d_frags, sizeof(wfb_frag_t) * (size_t)n));
+  IX_CHECK(cudaMemcpy(D.d_frags, frags, sizeof(wfb_frag_t) * (size_t)n, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&D.d_fq, sizeof(IxFragQuery) * (size_t)n));
+  IX_CHECK(cudaMemcpy(D.d_fq, fq, sizeof(IxFragQuery) * (size_t)n, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&D.d_group, 4 * (size_t)lp->n_ref_group));
+  IX_CHECK(cudaMemcpy(D.d_group, lp->ref_group, 4 * (size_t)lp->n_ref_group, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&D.d_cut, 4 * (size_t)lp->n_cutoffs));
+  IX_CHECK(cudaMemcpy(D.d_cut, lp->sketch_cutoffs, 4 * (size_t)lp->n_cutoffs, cudaMemcpyHostToDevice));
+  IX_CHECK(cudaMalloc(&D.d_q, sizeof(wfb_minmer_t) * (size_t)n * s));
+  IX_CHECK(cudaMemset(D.d_q, 0, sizeof(wfb_minmer_t) * (size_t)n * s));
+  IX_CHECK(cudaMalloc(&D.d_qn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_fn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_fst, 4 * (size_t)n));
+  IX_CHECK(cudaMalloc(&D.d_kc, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_foff, 8 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_qmax, 8 * (size_t)n));
+  IX_CHECK(cudaMalloc(&D.d_gs, 8 * (size_t)P.gcap * grid));
+  IX_CHECK(cudaMalloc(&D.d_ltmp, sizeof(IxL1Locus) * (size_t)2 * P.max_loci * grid));
+  IX_CHECK(cudaMalloc(&D.d_loci, sizeof(IxL1Locus) * (size_t)std::max<long long>(loci_cap, 1)));
+  IX_CHECK(cudaMalloc(&D.d_lfrag, 4 * (size_t)std::max<long long>(loci_cap, 1)));
+  IX_CHECK(cudaMalloc(&D.d_lc, 8)); IX_CHECK(cudaMemset(D.d_lc, 0, 8));
   IX_CHECK(cudaFuncSetAttribute(ix_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1));
   IX_CHECK(cudaEventRecord(e0));
-  IX_LAUNCH(ix_l1_kernel, grid, 128, smem, d_seq, d_frags, d_fq, n, npow2, P, ix->d_table, ix->n_buckets, ix->d_points, d_group, d_cut, d_q,
-            d_qn, d_kc, d_gs, d_ltmp, d_loci, d_lc, loci_cap, d_foff, d_fn, d_fst);
+  IX_LAUNCH(ix_l1_kernel, grid, 128, smem, D.d_seq, D.d_frags, D.d_fq, n, npow2, P, ix->d_table, ix->n_buckets, ix->d_points, D.d_group, D.d_cut,
+            D.d_q, D.d_qn, D.d_kc, D.d_qmax, D.d_gs, D.d_ltmp, D.d_loci, D.d_lfrag, D.d_lc, loci_cap, D.d_foff, D.d_fn, D.d_fst);
   IX_CHECK(cudaEventRecord(e1));
   IX_CHECK(cudaEventSynchronize(e1));
   IX_CHECK(cudaGetLastError());
   {
     float t = 0;
     cudaEventElapsedTime(&t, e0, e1);
-    out->kernel_ms = t;
+    D.kernel_ms = t;
   }
-  IX_CHECK(cudaMemcpy(&nl, d_lc, 8, cudaMemcpyDeviceToHost));
-  if ((long long)nl > loci_cap) { wfb_set_last_error_("loci buffer too small"); rc = WFB_ECAP; goto done; }
+  IX_CHECK(cudaMemcpy(&D.n_loci, D.d_lc, 8, cudaMemcpyDeviceToHost));
+  if ((long long)D.n_loci > loci_cap) { wfb_set_last_error_("loci buffer too small"); rc = WFB_ECAP; goto done; }
+done:
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return rc;
+}
+
+int l1_copy_out(const L1Dev& D, int32_t n, int s, int w, int k, wfb_l1_out_t* out) {
+  int rc = WFB_OK;
+  const unsigned long long nl = D.n_loci;
+  std::vector<IxL1Locus> hl;
   out->n_loci = (int64_t)nl;
-  if (out->q_minmers) IX_CHECK(cudaMemcpy(out->q_minmers, d_q, sizeof(wfb_minmer_t) * (size_t)n * s, cudaMemcpyDeviceToHost));
-  if (out->q_count) IX_CHECK(cudaMemcpy(out->q_count, d_qn, 4 * (size_t)n, cudaMemcpyDeviceToHost));
-  if (out->q_complexity) IX_CHECK(cudaMemcpy(out->q_complexity, d_kc, 4 * (size_t)n, cudaMemcpyDeviceToHost));
-  IX_CHECK(cudaMemcpy(out->frag_loci_offset, d_foff, 8 * (size_t)n, cudaMemcpyDeviceToHost));
-  IX_CHECK(cudaMemcpy(out->frag_loci_count, d_fn, 4 * (size_t)n, cudaMemcpyDeviceToHost));
-  IX_CHECK(cudaMemcpy(out->frag_status, d_fst, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  out->kernel_ms = D.kernel_ms;
+  if (out->q_minmers) IX_CHECK(cudaMemcpy(out->q_minmers, D.d_q, sizeof(wfb_minmer_t) * (size_t)n * s, cudaMemcpyDeviceToHost));
+  if (out->q_count) IX_CHECK(cudaMemcpy(out->q_count, D.d_qn, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  if (out->q_complexity) {
+    std::vector<float> kc; std::vector<int32_t> qn;
+    rc = l1_host_complexity(D.d_qmax, D.d_qn, n, w, k, kc, qn);
+    if (rc != WFB_OK) return rc;
+    memcpy(out->q_complexity, kc.data(), 4 * (size_t)n);
+  }
+  IX_CHECK(cudaMemcpy(out->frag_loci_offset, D.d_foff, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+  IX_CHECK(cudaMemcpy(out->frag_loci_count, D.d_fn, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  IX_CHECK(cudaMemcpy(out->frag_status, D.d_fst, 4 * (size_t)n, cudaMemcpyDeviceToHost));
   hl.resize((size_t)nl);
-  if (nl) IX_CHECK(cudaMemcpy(hl.data(), d_loci, sizeof(IxL1Locus) * (size_t)nl, cudaMemcpyDeviceToHost));
+  if (nl) IX_CHECK(cudaMemcpy(hl.data(), D.d_loci, sizeof(IxL1Locus) * (size_t)nl, cudaMemcpyDeviceToHost));
   for (unsigned long long i = 0; i < nl; ++i) {
     out->loci[i].seqId = hl[i].seqId; out->loci[i].intersectionSize = hl[i].intersectionSize;
     out->loci[i].rangeStartPos = hl[i].rangeStartPos; out->loci[i].rangeEndPos = hl[i].rangeEndPos;
   }
 done:
-  if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
-  cudaFree(d_seq); cudaFree(d_frags); cudaFree(d_fq); cudaFree(d_group); cudaFree(d_cut); cudaFree(d_q); cudaFree(d_qn); cudaFree(d_fn);
-  cudaFree(d_fst); cudaFree(d_kc); cudaFree(d_gs); cudaFree(d_ltmp); cudaFree(d_loci); cudaFree(d_lc); cudaFree(d_foff);
   return rc;
+}
+}  // namespace
+#endif
+
+extern "C" int wfb_l1_batch(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
+                            const wfb_frag_query_t* fq, int32_t n, wfb_l1_out_t* out) {
+  if (!out) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
+  int rc = l1_validate(ix, lp, seq_base, seq_bytes, frags, fq, n);
+  if (rc != WFB_OK) return rc;
+  out->n_loci = 0;
+  out->kernel_ms = 0;
+  if (n == 0) return WFB_OK;
+#ifndef WFB_EMU
+  L1Dev D;
+  rc = l1_run(ix, lp, seq_base, seq_bytes, frags, fq, n, out->loci_cap, D);
+  if (rc != WFB_OK) return rc;
+  return l1_copy_out(D, n, ix->params.sketch_size, ix->params.window_size, ix->params.kmer_size, out);
 #else
   wfb_set_last_error_("L1 is not part of the host emulation");
   return WFB_ENODEV;
 #endif
 }
+
+/* ---- L2 ---------------------------------------------------------------------------------------------------- */
+/* Stat::j2md / md2j (src/map/include/map_stats.hpp:56-80), with the reference's float / double mix */
+static float l2_j2md(float j, int k) {
+  if (j == 0) return 1.0f;
+  if (j == 1) return 0.0f;
+  const float mash_dist = 1 - std::pow(2 * j / (1 + j), 1.0 / k);
+  return mash_dist;
+}
+static float l2_md2j(float d, int k) {
+  const float sim = 1 - d;
+  const float jaccard = std::pow((double)sim, (double)k) / (2 - std::pow((double)sim, (double)k));
+  return jaccard;
+}
+
+extern "C" int wfb_stage1_min_hits(double hg_numerator, float ani_diff, int32_t kmer_size, int32_t sketch_size, int32_t* out) {
+  if (!out || sketch_size < 1 || kmer_size < 1) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
+  out[0] = 0;
+  for (int qs = 1; qs <= sketch_size; ++qs) { /* Map::doL2Mapping, computeMap.hpp:999-1012, for Q.sketchSize == qs */
+    const double jaccardSimilarity = hg_numerator / qs;
+    const double mash_dist = l2_j2md((float)jaccardSimilarity, kmer_size);
+    const double cutoff_ani = std::max(0.0, (1 - mash_dist) - ani_diff);
+    const double cutoff_j = l2_md2j((float)(1 - cutoff_ani), kmer_size);
+    int v = 0;
+    while (v <= qs && static_cast<double>(v) / qs < cutoff_j) ++v; /* first intersectionSize that is not "< cutoff_j" */
+    out[qs] = v;
+  }
+  return WFB_OK;
+}
+
+extern "C" int wfb_l2_min_shared(float percentage_identity, int32_t kmer_size, int32_t sketch_size, int32_t* out) {
+  if (!out || sketch_size < 1 || kmer_size < 1) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
+  out[0] = 0;
+  for (int qs = 1; qs <= sketch_size; ++qs) { /* computeMap.hpp:1018-1024 with keep_low_pct_id == false */
+    int v = 0;
+    for (; v <= qs; ++v) {
+      const float mash_dist = l2_j2md(1.0 * v / qs, kmer_size);
+      const float nucIdentity = (1 - mash_dist);
+      if (nucIdentity >= percentage_identity) break;
+    }
+    out[qs] = v; /* qs + 1 = nothing passes */
+  }
+  return WFB_OK;
+}
+
+/* nucIdentity of every mapping (computeMap.hpp:1018-1019), frag_map_offset CSR */
+static void l2_finish_host(wfb_l2_mapping_t* m, int64_t nm, const int32_t* q_count, const float* q_complexity, int32_t n, int k, int s, int64_t* frag_map_offset) {
+  std::vector<float> tab((size_t)(s + 1) * (s + 1), -1.f);
+  for (int i = 0; i <= n; ++i) frag_map_offset[i] = 0;
+  for (int64_t i = 0; i < nm; ++i) {
+    const int qn = q_count[m[i].frag], sh = m[i].conservedSketches;
+    float& t = tab[(size_t)qn * (s + 1) + std::min(std::max(sh, 0), s)];
+    if (t < 0) { const float mash_dist = l2_j2md(1.0 * sh / qn, k); t = (1 - mash_dist); }
+    m[i].nucIdentity = t;
+    m[i].kmerComplexity = q_complexity[m[i].frag];
+    frag_map_offset[m[i].frag + 1]++;
+  }
+  for (int i = 0; i < n; ++i) frag_map_offset[i + 1] += frag_map_offset[i];
+}
+
+extern "C" int wfb_map_fragments_batch(const wfb_index_t* ix, const wfb_l1_params_t* lp, const wfb_l2_params_t* l2p, const char* seq_base,
+                                       int64_t seq_bytes, const wfb_frag_t* frags, const wfb_frag_query_t* fq, int32_t n, wfb_map_out_t* out) {
+  if (!out || !l2p || !out->mappings || !out->frag_map_offset || !out->frag_status) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
+  int rc = l1_validate(ix, lp, seq_base, seq_bytes, frags, fq, n);
+  if (rc != WFB_OK) return rc;
+  const int s = ix->params.sketch_size;
+  if ((l2p->stage1_min_hits && l2p->n_stage1_min_hits < s + 1) || (l2p->l2_min_shared && l2p->n_l2_min_shared < s + 1)) {
+    wfb_set_last_error_("L2 tables need sketch_size + 1 entries");
+    return WFB_EINVAL;
+  }
+  out->n_mappings = 0; out->l1_kernel_ms = 0; out->l2_kernel_ms = 0; out->sort_kernel_ms = 0; out->n_l1_loci = 0; out->l2_loci = 0; out->l2_steps = 0;
+  if (out->l1) { out->l1->n_loci = 0; out->l1->kernel_ms = 0; }
+  out->frag_map_offset[0] = 0;
+  if (n == 0) return WFB_OK;
+#ifndef WFB_EMU
+  L1Dev D;
+  const long long loci_cap = out->l1 ? out->l1->loci_cap : (64LL * n + 1024);
+  rc = l1_run(ix, lp, seq_base, seq_bytes, frags, fq, n, loci_cap, D);
+  if (rc != WFB_OK) return rc;
+  if (out->l1) { rc = l1_copy_out(D, n, s, ix->params.window_size, ix->params.kmer_size, out->l1); if (rc != WFB_OK) return rc; }
+  out->l1_kernel_ms = D.kernel_ms;
+  out->n_l1_loci = D.n_loci;
+  int *d_s1 = nullptr, *d_ms = nullptr; L2Entry* d_slab = nullptr; wfb_l2_mapping_t *d_map = nullptr, *d_sorted = nullptr;
+  unsigned long long *d_cnt = nullptr, *d_kp = nullptr, *d_kp2 = nullptr; L2Counters* d_ctr = nullptr;
+  unsigned int *d_kf = nullptr, *d_kf2 = nullptr, *d_kf3 = nullptr, *d_idx = nullptr, *d_idx2 = nullptr, *d_idx3 = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  Tmp tmp;
+  L2Counters hc{};
+  unsigned long long nm = 0;
+  std::vector<int32_t> hq;
+  std::vector<float> hkc;
+  L2Params P;
+  P.k = ix->params.kmer_size; P.w = ix->params.window_size; P.s = s; P.vec_cap = 256; P.warps_per_cta = 8;
+  const size_t smem = l2_warp_smem(s) * P.warps_per_cta;
+  const long long warps_needed = (long long)std::max<unsigned long long>(D.n_loci, 1);
+  const int grid = (int)std::min<long long>((warps_needed + P.warps_per_cta - 1) / P.warps_per_cta, (long long)D.sm_count * 4);
+  const long long cap = out->mappings_cap;
+  if (l2p->stage1_min_hits) {
+    IX_CHECK(cudaMalloc(&d_s1, 4 * (size_t)(s + 1)));
+    IX_CHECK(cudaMemcpy(d_s1, l2p->stage1_min_hits, 4 * (size_t)(s + 1), cudaMemcpyHostToDevice));
+  }
+  if (l2p->l2_min_shared) {
+    IX_CHECK(cudaMalloc(&d_ms, 4 * (size_t)(s + 1)));
+    IX_CHECK(cudaMemcpy(d_ms, l2p->l2_min_shared, 4 * (size_t)(s + 1), cudaMemcpyHostToDevice));
+  }
+  IX_CHECK(cudaMalloc(&d_slab, sizeof(L2Entry) * (size_t)P.vec_cap * P.warps_per_cta * grid));
+  IX_CHECK(cudaMalloc(&d_map, sizeof(wfb_l2_mapping_t) * (size_t)std::max<long long>(cap, 1)));
+  IX_CHECK(cudaMalloc(&d_cnt, 8)); IX_CHECK(cudaMemset(d_cnt, 0, 8));
+  IX_CHECK(cudaMalloc(&d_ctr, sizeof(L2Counters))); IX_CHECK(cudaMemset(d_ctr, 0, sizeof(L2Counters)));
+  IX_CHECK(cudaFuncSetAttribute(l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1)); IX_CHECK(cudaEventCreate(&e2));
+  IX_CHECK(cudaEventRecord(e0));
+  IX_LAUNCH(l2_kernel, grid, 32 * P.warps_per_cta, smem, ix->d_minmers, ix->n_minmers, D.d_loci, D.d_lfrag, D.d_lc, D.loci_cap, D.d_q, D.d_qn, P,
+            d_s1, d_ms, d_slab, d_map, d_cnt, cap, D.d_fst, d_ctr);
+  IX_CHECK(cudaEventRecord(e1));
+  IX_CHECK(cudaMemcpy(&nm, d_cnt, 8, cudaMemcpyDeviceToHost));
+  IX_CHECK(cudaGetLastError());
+  if ((long long)nm > cap) { wfb_set_last_error_("mappings buffer too small"); out->n_mappings = (int64_t)nm; rc = WFB_ECAP; goto done; }
+  if (nm > 0) { /* order by (frag, refSeqId, refStartPos): two stable LSD radix passes */
+    const long long N = (long long)nm;
+    const int G = (int)std::min<long long>((N + 255) / 256, 148 * 8);
+    int fbits = 1;
+    while ((1LL << fbits) < n) ++fbits;
+    size_t b1 = 0, b2 = 0;
+    IX_CHECK(cudaMalloc(&d_kp, 8 * (size_t)N)); IX_CHECK(cudaMalloc(&d_kp2, 8 * (size_t)N));
+    IX_CHECK(cudaMalloc(&d_kf, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_kf2, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_kf3, 4 * (size_t)N));
+    IX_CHECK(cudaMalloc(&d_idx, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_idx2, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_idx3, 4 * (size_t)N));
+    IX_CHECK(cudaMalloc(&d_sorted, sizeof(wfb_l2_mapping_t) * (size_t)N));
+    IX_LAUNCH(l2_keys_kernel, G, 256, 0, d_map, N, d_kp, d_kf, d_idx);
+    IX_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, b1, d_kp, d_kp2, d_idx, d_idx2, (int)N));
+    IX_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, b2, d_kf2, d_kf3, d_idx2, d_idx3, (int)N, 0, fbits));
+    IX_CHECK(tmp.ensure(std::max(b1, b2)));
+    IX_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, b1, d_kp, d_kp2, d_idx, d_idx2, (int)N));
+    wfb_count_launch_();
+    IX_LAUNCH(l2_gather_u32_kernel, G, 256, 0, d_kf, d_idx2, N, d_kf2);
+    IX_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, b2, d_kf2, d_kf3, d_idx2, d_idx3, (int)N, 0, fbits));
+    wfb_count_launch_();
+    IX_LAUNCH(l2_permute_kernel, G, 256, 0, d_map, d_idx3, N, d_sorted);
+    IX_CHECK(cudaEventRecord(e2));
+    IX_CHECK(cudaMemcpy(out->mappings, d_sorted, sizeof(wfb_l2_mapping_t) * (size_t)N, cudaMemcpyDeviceToHost));
+  } else {
+    IX_CHECK(cudaEventRecord(e2));
+  }
+  IX_CHECK(cudaEventSynchronize(e2));
+  IX_CHECK(cudaGetLastError());
+  {
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1); out->l2_kernel_ms = t;
+    cudaEventElapsedTime(&t, e1, e2); out->sort_kernel_ms = t;
+  }
+  IX_CHECK(cudaMemcpy(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  out->l2_loci = hc.loci; out->l2_steps = hc.steps;
+  IX_CHECK(cudaMemcpy(out->frag_status, D.d_fst, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  rc = l1_host_complexity(D.d_qmax, D.d_qn, n, P.w, P.k, hkc, hq);
+  if (rc != WFB_OK) goto done;
+  out->n_mappings = (int64_t)nm;
+  l2_finish_host(out->mappings, (int64_t)nm, hq.data(), hkc.data(), n, P.k, s, out->frag_map_offset);
+done:
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (e2) cudaEventDestroy(e2);
+  cudaFree(d_s1); cudaFree(d_ms); cudaFree(d_slab); cudaFree(d_map); cudaFree(d_sorted); cudaFree(d_cnt); cudaFree(d_ctr); cudaFree(d_kp);
+  cudaFree(d_kp2); cudaFree(d_kf); cudaFree(d_kf2); cudaFree(d_kf3); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_idx3);
+  return rc;
+#else
+  wfb_set_last_error_("the mapping batch is not part of the host emulation (see wfb_emu_l2_loci)");
+  return WFB_ENODEV;
+#endif
+}
+
+#ifdef WFB_EMU
+/* TEST-ONLY (never in the product library): runs l2_kernel's body under the single-thread emulation over host arrays,
+ * so the kernel's bookkeeping can be checked against the oracle in a container without a GPU. */
+extern "C" int wfb_emu_l2_loci(const wfb_minmer_t* index, int64_t n_index, const wfb_l1_locus_t* loci, const int32_t* locus_frag, int64_t n_loci,
+                               const wfb_minmer_t* q_all, const int32_t* q_count, int32_t n_frags, int32_t k, int32_t w, int32_t s,
+                               const int32_t* stage1_min_hits, const int32_t* l2_min_shared, wfb_l2_mapping_t* out, int64_t out_cap,
+                               int64_t* n_out, int32_t* frag_status, uint64_t* steps) {
+  std::vector<IxL1Locus> L((size_t)n_loci);
+  for (int64_t i = 0; i < n_loci; ++i) { L[i].seqId = loci[i].seqId; L[i].intersectionSize = loci[i].intersectionSize; L[i].rangeStartPos = loci[i].rangeStartPos; L[i].rangeEndPos = loci[i].rangeEndPos; }
+  L2Params P; P.k = k; P.w = w; P.s = s; P.vec_cap = 256; P.warps_per_cta = 1;
+  const int grid = 3;
+  std::vector<L2Entry> slab((size_t)P.vec_cap * grid);
+  std::vector<unsigned char> smem(l2_warp_smem(s) + 64);
+  unsigned long long nl = (unsigned long long)n_loci, cnt = 0;
+  L2Counters ctr{};
+  for (int b = 0; b < grid; ++b)
+    l2_kernel(b, grid, index, n_index, L.data(), locus_frag, &nl, n_loci, q_all, q_count, P, stage1_min_hits, l2_min_shared, slab.data(), out, &cnt,
+              out_cap, frag_status, &ctr, smem.data());
+  *n_out = (int64_t)cnt;
+  if (steps) *steps = ctr.steps;
+  if ((int64_t)cnt > out_cap) return WFB_ECAP;
+  std::stable_sort(out, out + cnt, [](const wfb_l2_mapping_t& a, const wfb_l2_mapping_t& b) {
+    if (a.frag != b.frag) return a.frag < b.frag;
+    if (a.refSeqId != b.refSeqId) return a.refSeqId < b.refSeqId;
+    return a.refStartPos < b.refStartPos;
+  });
+  std::vector<int64_t> off((size_t)n_frags + 1);
+  std::vector<float> kc((size_t)n_frags);
+  for (int32_t i = 0; i < n_frags; ++i) kc[(size_t)i] = q_count[i] > 0 ? ix_kmer_complexity(q_all[(size_t)i * s + q_count[i] - 1].hash, q_count[i], w, k) : 0.f;
+  l2_finish_host(out, (int64_t)cnt, q_count, kc.data(), n_frags, k, s, off.data());
+  return WFB_OK;
+}
+#endif

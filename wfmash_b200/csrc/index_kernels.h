@@ -185,8 +185,8 @@ struct IxFragQuery { /* per-fragment query metadata (QueryMetaData, base_types.h
 /* dynamic smem: [sketch buffers: npow2*12 + seq] ... reused afterwards as the interval-point buffer */
 WFB_KERNEL(ix_l1_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, const IxFragQuery* fq, int nfrags, int npow2_max,
            IxL1Params P, const IxSlot* table, long long nbuckets, const uint64_t* points, const int* ref_group, const int* cutoffs,
-           wfb_minmer_t* q_out, int* q_count, float* q_complexity, uint64_t* gscratch_all, IxL1Locus* loci_tmp_all,
-           IxL1Locus* loci_out, unsigned long long* loci_counter, long long loci_cap, long long* frag_loci_off, int* frag_loci_n,
+           wfb_minmer_t* q_out, int* q_count, float* q_complexity, unsigned long long* q_maxhash, uint64_t* gscratch_all, IxL1Locus* loci_tmp_all,
+           IxL1Locus* loci_out, int* loci_frag, unsigned long long* loci_counter, long long loci_cap, long long* frag_loci_off, int* frag_loci_n,
            int* frag_status
 #ifdef WFB_EMU
            , unsigned char* smem_emu
@@ -215,10 +215,13 @@ WFB_KERNEL(ix_l1_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, const
       q_count[f] = qn;
       sh_nloci = 0; sh_err = 0; sh_total = 0;
       float kc = 0.f;
-      if (qn > 0) { /* mappingCore.hpp:72-74 */
-        const double max_hash_01 = (double)((long double)qo[qn - 1].hash / (long double)18446744073709551615.0L);
+      if (qn > 0) { /* mappingCore.hpp:72-74. The reference divides in x87 long double; this double-precision value is only used
+                       for the kmerComplexityThreshold test below (0 on the CLI path). The value handed back to the caller is
+                       recomputed on the host in long double from q_maxhash (index_host.cu ix_kmer_complexity). */
+        const double max_hash_01 = (double)qo[qn - 1].hash / 18446744073709551615.0;
         kc = (float)(((double)qn / max_hash_01) / ((double)(fr.len - P.k + 1) * 2));
       }
+      q_maxhash[f] = qn > 0 ? qo[qn - 1].hash : 0ULL;
       q_complexity[f] = kc;
       frag_loci_off[f] = 0; frag_loci_n[f] = 0; frag_status[f] = 0;
     }
@@ -301,7 +304,7 @@ WFB_KERNEL(ix_l1_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, const
     if (nl > 0) {
       const unsigned long long base = sh_base;
       if ((long long)(base + nl) <= loci_cap) {
-        for (int i = WFB_TID; i < nl; i += WFB_NT) loci_out[base + i] = ltmp[i];
+        for (int i = WFB_TID; i < nl; i += WFB_NT) { loci_out[base + i] = ltmp[i]; loci_frag[base + i] = f; }
         if (WFB_TID == 0) { frag_loci_off[f] = (long long)base; frag_loci_n[f] = nl; }
       } else if (WFB_TID == 0) frag_status[f] = WFB_ECAP;
     }
@@ -384,7 +387,7 @@ WFB_KERNEL(ix_uniq_kernel, const int* head, const int* keep_sorted, const int* p
     if (!keep_sorted[i]) continue;
     const long long u = ukept_incl[i] - 1; /* index among kept unique hashes (scan of head&&keep) */
     if (head[i]) { uhash[u] = skeys[i]; ustart[u] = (uint32_t)(2 * (pair_incl[i] - 1)); }
-    if (pstart[i]) atomicAdd((unsigned int*)&ucount_pairs[u], 2u);
+    if (pstart[i]) wfb_atomic_add((int*)&ucount_pairs[u], 2);
   }
 }
 WFB_KERNEL(ix_and_kernel, const int* a, const int* b, long long n, int* out) {

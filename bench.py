@@ -271,10 +271,14 @@ def map_path_section(dev, cores, with_cpu):
     # L1 + L2 fused on the device: the L1 loci stay in HBM, the L2 kernel streams minmerIndex (32 B / record)
     s1 = wb.stage1_min_hits(k, ssz)
     ms = wb.l2_min_shared(0.85, k, ssz)
-    m = ix.map_fragments(blob, frags, fqs, 3, cut, grp, stage1_min_hits=s1, l2_min_shared=ms)   # warm-up
-    t0 = time.perf_counter()
-    m = ix.map_fragments(blob, frags, fqs, 3, cut, grp, stage1_min_hits=s1, l2_min_shared=ms)
-    t_map = time.perf_counter() - t0
+    frags_a = np.array(frags, dtype=wb.FRAG_DTYPE)
+    fqs_a = np.array(fqs, dtype=wb.FRAG_QUERY_DTYPE)
+    m = ix.map_fragments(blob, frags_a, fqs_a, 3, cut, grp, stage1_min_hits=s1, l2_min_shared=ms)   # warm-up (sizes the workspace)
+    t_map = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        m = ix.map_fragments(blob, frags_a, fqs_a, 3, cut, grp, stage1_min_hits=s1, l2_min_shared=ms)
+        t_map = min(t_map, time.perf_counter() - t0)
     out["l2"] = {"fragments": len(frags), "l1_loci": int(m["n_l1_loci"]), "l2_loci": int(m["l2_loci"]), "mappings": int(len(m["mappings"])),
                  "index_records_visited": int(m["l2_steps"]), "l1_kernel_ms": m["l1_kernel_ms"], "l2_kernel_ms": m["l2_kernel_ms"],
                  "sort_kernel_ms": m["sort_kernel_ms"], "loci_per_s": m["l2_loci"] / max(m["l2_kernel_ms"], 1e-9) * 1e3,

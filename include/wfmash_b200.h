@@ -110,6 +110,18 @@ int wfb_align_batch_device(wfb_aligner_t*, const char* d_seq, const int64_t* pat
                            const int64_t* text_off, const int32_t* text_len, int32_t n, char* ops, int64_t ops_cap,
                            wfb_aln_result_t* results, wfb_align_stats_t* stats);
 
+/* Compatibility shim with the shape of the C API that wfb_align_batch sits under:
+ *   wavefront_aligner_t* wavefront_aligner_new(attr) / int wavefront_align(aligner, pattern, plen, text, tlen)
+ * (deps/WFA2-lib/wavefront/wavefront_aligner.c:422, wavefront_align.c:212) with the result the reference leaves in
+ * aligner->cigar (deps/WFA2-lib/alignment/cigar.h: operations[begin_offset, end_offset), score). One pair per call, so
+ * that align_benchmark-style drivers can target the GPU; throughput needs wfb_align_batch. Returns the reference's
+ * status convention: 0 = WF_STATUS_ALG_COMPLETED, -300 = WF_STATUS_UNATTAINABLE (deps/WFA2-lib/wavefront/wfa.h:46-51),
+ * or a negative WFB_E* code for an API failure (distinguishable: WFB_E* are > -100). */
+#define WFB_WF_STATUS_ALG_COMPLETED 0
+#define WFB_WF_STATUS_UNATTAINABLE (-300)
+int wfb_wavefront_align(wfb_aligner_t*, const char* pattern, int32_t pattern_length, const char* text, int32_t text_length,
+                        char* cigar_operations, int32_t cigar_cap, int32_t* cigar_length, int32_t* cigar_score);
+
 /* Head / tail patch alignments of do_biwfa_alignment (src/common/wflign/src/wflign.cpp:280-305, 368-397):
  *   wfa::WFAlignerGapAffine2Pieces(0,x,o1,e1,o2,e2,Alignment,MemoryMed).alignEndsFree(pattern,
  *       patternBeginFree, patternEndFree, text, textBeginFree, textEndFree)

@@ -41,6 +41,16 @@ def test_biwfa_reference_golden_vectors_bit_exact(wb):
         assert r.score == int(gscore)
 
 
+def test_wavefront_align_shim_matches_reference_golden_vectors(wb):
+    # the wavefront_align-shaped single-pair entry reproduces the same known-answer file
+    pairs = util.golden_pairs()[:40]
+    gold = util.golden_alg("wfa_utest.biwfa.affine2p.alg.gz")[:40]
+    al = wb.Aligner(0, penalties=util.GOLDEN_PEN)
+    for (p, t), (gscore, gcigar) in zip(pairs, gold):
+        st, ops, score = al.wavefront_align(p, t)
+        assert st == 0 and util.rle(ops) == gcigar and score == int(gscore)
+
+
 def test_biwfa_wfmash_penalties_match_reference_fixture(wb):
     pairs = util.golden_pairs()
     rows = util.golden_alg("wfa_wfmash_pen.tsv.gz")

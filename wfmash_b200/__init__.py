@@ -212,6 +212,17 @@ class Aligner:
         return [AlignResult(r.status, r.score, raw[r.ops_offset:r.ops_offset + r.ops_len]) for r in res]
 
 
+    def wavefront_align(self, pattern: bytes, text: bytes):
+        """wavefront_align-shaped single-pair call (deps/WFA2-lib/wavefront/wavefront_align.c:212):
+        returns (status, cigar operations, score) with the reference's status codes (0 completed, -300 unattainable)."""
+        cap = len(pattern) + len(text) + 16
+        buf = ctypes.create_string_buffer(cap)
+        n, sc = ctypes.c_int32(0), ctypes.c_int32(0)
+        st = self._L.wfb_wavefront_align(ctypes.c_void_p(self._h), pattern, len(pattern), text, len(text), buf, cap, ctypes.byref(n), ctypes.byref(sc))
+        if -100 < st < 0:
+            raise _err(st)
+        return st, buf.raw[: n.value], sc.value
+
     def biwfa_paf_batch(self, records, min_identity=0.0, min_alignment_length=0, min_block_identity=0.0,
                         disable_chain_patching=False, term_group=8):
         """Batched wflign::wavefront::do_biwfa_alignment, PAF branch (src/common/wflign/src/wflign.cpp:108-483).

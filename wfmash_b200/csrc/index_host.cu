@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include <limits>
+#include <mutex>
 
 #ifndef WFB_EMU
 #include <cub/cub.cuh>
@@ -31,6 +32,12 @@ struct wfb_index {
   IxSlot* d_table = nullptr;
   unsigned long long* d_uhash = nullptr;
   uint32_t *d_ustart = nullptr, *d_ucount = nullptr;
+  /* grow-only device workspace of the batched mapping calls (wfb_l1_batch / wfb_map_fragments_batch): allocated on the
+   * first call and reused, so that a steady stream of batches does no cudaMalloc / cudaFree. Calls on one index serialise
+   * on ws_mu. */
+  mutable std::mutex ws_mu;
+  mutable void* ws_ptr[48] = {};
+  mutable size_t ws_cap[48] = {};
 };
 
 #ifndef WFB_EMU
@@ -105,6 +112,7 @@ extern "C" void wfb_index_free(wfb_index_t* ix) {
 #ifndef WFB_EMU
   cudaSetDevice(ix->device);
   cudaFree(ix->d_minmers); cudaFree(ix->d_points); cudaFree(ix->d_table); cudaFree(ix->d_uhash); cudaFree(ix->d_ustart); cudaFree(ix->d_ucount);
+  for (int i = 0; i < 48; ++i) cudaFree(ix->ws_ptr[i]);
 #else
   free(ix->d_minmers); free(ix->d_points); free(ix->d_table); free(ix->d_uhash); free(ix->d_ustart); free(ix->d_ucount);
 #endif
@@ -337,7 +345,25 @@ int l1_host_complexity(const unsigned long long* d_qmax, const int* d_qn, int32_
 done:
   return rc;
 }
-struct L1Dev { /* what ix_l1_kernel leaves in device memory; the L2 kernel reads it in place */
+/* slot `slot` of the index's grow-only workspace, at least `bytes` big (contents are NOT preserved when it grows) */
+template <typename T>
+cudaError_t ws_get(const wfb_index_t* ix, int slot, size_t bytes, T** out) {
+  if (bytes < 256) bytes = 256;
+  if (ix->ws_cap[slot] < bytes) {
+    if (ix->ws_ptr[slot]) cudaFree(ix->ws_ptr[slot]);
+    ix->ws_ptr[slot] = nullptr; ix->ws_cap[slot] = 0;
+    const size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&ix->ws_ptr[slot], want);
+    if (e != cudaSuccess) return e;
+    ix->ws_cap[slot] = want;
+  }
+  *out = (T*)ix->ws_ptr[slot];
+  return cudaSuccess;
+}
+enum { WS_SEQ, WS_FRAGS, WS_FQ, WS_GROUP, WS_CUT, WS_Q, WS_QN, WS_FN, WS_FST, WS_LFRAG, WS_KC, WS_GS, WS_LTMP, WS_LOCI, WS_LC, WS_FOFF, WS_QMAX,
+       WS_S1, WS_MS, WS_SLAB, WS_MAP, WS_SORTED, WS_CNT, WS_CTR, WS_KP, WS_KP2, WS_KF, WS_KF2, WS_KF3, WS_IDX, WS_IDX2, WS_IDX3, WS_CUBTMP };
+
+struct L1Dev { /* what ix_l1_kernel leaves in device memory (views into the index's workspace); the L2 kernel reads it in place */
   uint8_t* d_seq = nullptr; wfb_frag_t* d_frags = nullptr; IxFragQuery* d_fq = nullptr; int *d_group = nullptr, *d_cut = nullptr;
   wfb_minmer_t* d_q = nullptr; int *d_qn = nullptr, *d_fn = nullptr, *d_fst = nullptr, *d_lfrag = nullptr; float* d_kc = nullptr;
   uint64_t* d_gs = nullptr; IxL1Locus *d_ltmp = nullptr, *d_loci = nullptr; unsigned long long *d_lc = nullptr, *d_qmax = nullptr; long long* d_foff = nullptr;
@@ -345,10 +371,6 @@ struct L1Dev { /* what ix_l1_kernel leaves in device memory; the L2 kernel reads
   unsigned long long n_loci = 0;
   double kernel_ms = 0;
   int sm_count = 0;
-  ~L1Dev() {
-    cudaFree(d_seq); cudaFree(d_frags); cudaFree(d_fq); cudaFree(d_group); cudaFree(d_cut); cudaFree(d_q); cudaFree(d_qn); cudaFree(d_fn);
-    cudaFree(d_fst); cudaFree(d_lfrag); cudaFree(d_kc); cudaFree(d_gs); cudaFree(d_ltmp); cudaFree(d_loci); cudaFree(d_lc); cudaFree(d_foff); cudaFree(d_qmax);
-  }
 };
 
 int l1_run(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_base, int64_t seq_bytes, const wfb_frag_t* frags,
@@ -373,25 +395,25 @@ int l1_run(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_bas
     D.sm_count = prop.multiProcessorCount;
     grid = std::min(n, prop.multiProcessorCount * 4);
   }
-  IX_CHECK(cudaMalloc(&D.d_seq, (size_t)seq_bytes + 16));
+  IX_CHECK(ws_get(ix, WS_SEQ, (size_t)seq_bytes + 16, &D.d_seq));
   IX_CHECK(cudaMemcpy(D.d_seq, seq_base, (size_t)seq_bytes, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&D.d_frags, sizeof(wfb_frag_t) * (size_t)n));
+  IX_CHECK(ws_get(ix, WS_FRAGS, sizeof(wfb_frag_t) * (size_t)n, &D.d_frags));
   IX_CHECK(cudaMemcpy(D.d_frags, frags, sizeof(wfb_frag_t) * (size_t)n, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&D.d_fq, sizeof(IxFragQuery) * (size_t)n));
+  IX_CHECK(ws_get(ix, WS_FQ, sizeof(IxFragQuery) * (size_t)n, &D.d_fq));
   IX_CHECK(cudaMemcpy(D.d_fq, fq, sizeof(IxFragQuery) * (size_t)n, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&D.d_group, 4 * (size_t)lp->n_ref_group));
+  IX_CHECK(ws_get(ix, WS_GROUP, 4 * (size_t)lp->n_ref_group, &D.d_group));
   IX_CHECK(cudaMemcpy(D.d_group, lp->ref_group, 4 * (size_t)lp->n_ref_group, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&D.d_cut, 4 * (size_t)lp->n_cutoffs));
+  IX_CHECK(ws_get(ix, WS_CUT, 4 * (size_t)lp->n_cutoffs, &D.d_cut));
   IX_CHECK(cudaMemcpy(D.d_cut, lp->sketch_cutoffs, 4 * (size_t)lp->n_cutoffs, cudaMemcpyHostToDevice));
-  IX_CHECK(cudaMalloc(&D.d_q, sizeof(wfb_minmer_t) * (size_t)n * s));
+  IX_CHECK(ws_get(ix, WS_Q, sizeof(wfb_minmer_t) * (size_t)n * s, &D.d_q));
   IX_CHECK(cudaMemset(D.d_q, 0, sizeof(wfb_minmer_t) * (size_t)n * s));
-  IX_CHECK(cudaMalloc(&D.d_qn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_fn, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_fst, 4 * (size_t)n));
-  IX_CHECK(cudaMalloc(&D.d_kc, 4 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_foff, 8 * (size_t)n)); IX_CHECK(cudaMalloc(&D.d_qmax, 8 * (size_t)n));
-  IX_CHECK(cudaMalloc(&D.d_gs, 8 * (size_t)P.gcap * grid));
-  IX_CHECK(cudaMalloc(&D.d_ltmp, sizeof(IxL1Locus) * (size_t)2 * P.max_loci * grid));
-  IX_CHECK(cudaMalloc(&D.d_loci, sizeof(IxL1Locus) * (size_t)std::max<long long>(loci_cap, 1)));
-  IX_CHECK(cudaMalloc(&D.d_lfrag, 4 * (size_t)std::max<long long>(loci_cap, 1)));
-  IX_CHECK(cudaMalloc(&D.d_lc, 8)); IX_CHECK(cudaMemset(D.d_lc, 0, 8));
+  IX_CHECK(ws_get(ix, WS_QN, 4 * (size_t)n, &D.d_qn)); IX_CHECK(ws_get(ix, WS_FN, 4 * (size_t)n, &D.d_fn)); IX_CHECK(ws_get(ix, WS_FST, 4 * (size_t)n, &D.d_fst));
+  IX_CHECK(ws_get(ix, WS_KC, 4 * (size_t)n, &D.d_kc)); IX_CHECK(ws_get(ix, WS_FOFF, 8 * (size_t)n, &D.d_foff)); IX_CHECK(ws_get(ix, WS_QMAX, 8 * (size_t)n, &D.d_qmax));
+  IX_CHECK(ws_get(ix, WS_GS, 8 * (size_t)P.gcap * grid, &D.d_gs));
+  IX_CHECK(ws_get(ix, WS_LTMP, sizeof(IxL1Locus) * (size_t)2 * P.max_loci * grid, &D.d_ltmp));
+  IX_CHECK(ws_get(ix, WS_LOCI, sizeof(IxL1Locus) * (size_t)std::max<long long>(loci_cap, 1), &D.d_loci));
+  IX_CHECK(ws_get(ix, WS_LFRAG, 4 * (size_t)std::max<long long>(loci_cap, 1), &D.d_lfrag));
+  IX_CHECK(ws_get(ix, WS_LC, 8, &D.d_lc)); IX_CHECK(cudaMemset(D.d_lc, 0, 8));
   IX_CHECK(cudaFuncSetAttribute(ix_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1));
   IX_CHECK(cudaEventRecord(e0));
@@ -451,6 +473,7 @@ extern "C" int wfb_l1_batch(const wfb_index_t* ix, const wfb_l1_params_t* lp, co
   out->kernel_ms = 0;
   if (n == 0) return WFB_OK;
 #ifndef WFB_EMU
+  std::lock_guard<std::mutex> ws_lock(ix->ws_mu);
   L1Dev D;
   rc = l1_run(ix, lp, seq_base, seq_bytes, frags, fq, n, out->loci_cap, D);
   if (rc != WFB_OK) return rc;
@@ -535,6 +558,7 @@ extern "C" int wfb_map_fragments_batch(const wfb_index_t* ix, const wfb_l1_param
   out->frag_map_offset[0] = 0;
   if (n == 0) return WFB_OK;
 #ifndef WFB_EMU
+  std::lock_guard<std::mutex> ws_lock(ix->ws_mu);
   L1Dev D;
   const long long loci_cap = out->l1 ? out->l1->loci_cap : (64LL * n + 1024);
   rc = l1_run(ix, lp, seq_base, seq_bytes, frags, fq, n, loci_cap, D);
@@ -546,7 +570,7 @@ extern "C" int wfb_map_fragments_batch(const wfb_index_t* ix, const wfb_l1_param
   unsigned long long *d_cnt = nullptr, *d_kp = nullptr, *d_kp2 = nullptr; L2Counters* d_ctr = nullptr;
   unsigned int *d_kf = nullptr, *d_kf2 = nullptr, *d_kf3 = nullptr, *d_idx = nullptr, *d_idx2 = nullptr, *d_idx3 = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-  Tmp tmp;
+  void* d_cubtmp = nullptr;
   L2Counters hc{};
   unsigned long long nm = 0;
   std::vector<int32_t> hq;
@@ -558,17 +582,17 @@ extern "C" int wfb_map_fragments_batch(const wfb_index_t* ix, const wfb_l1_param
   const int grid = (int)std::min<long long>((warps_needed + P.warps_per_cta - 1) / P.warps_per_cta, (long long)D.sm_count * 4);
   const long long cap = out->mappings_cap;
   if (l2p->stage1_min_hits) {
-    IX_CHECK(cudaMalloc(&d_s1, 4 * (size_t)(s + 1)));
+    IX_CHECK(ws_get(ix, WS_S1, 4 * (size_t)(s + 1), &d_s1));
     IX_CHECK(cudaMemcpy(d_s1, l2p->stage1_min_hits, 4 * (size_t)(s + 1), cudaMemcpyHostToDevice));
   }
   if (l2p->l2_min_shared) {
-    IX_CHECK(cudaMalloc(&d_ms, 4 * (size_t)(s + 1)));
+    IX_CHECK(ws_get(ix, WS_MS, 4 * (size_t)(s + 1), &d_ms));
     IX_CHECK(cudaMemcpy(d_ms, l2p->l2_min_shared, 4 * (size_t)(s + 1), cudaMemcpyHostToDevice));
   }
-  IX_CHECK(cudaMalloc(&d_slab, sizeof(L2Entry) * (size_t)P.vec_cap * P.warps_per_cta * grid));
-  IX_CHECK(cudaMalloc(&d_map, sizeof(wfb_l2_mapping_t) * (size_t)std::max<long long>(cap, 1)));
-  IX_CHECK(cudaMalloc(&d_cnt, 8)); IX_CHECK(cudaMemset(d_cnt, 0, 8));
-  IX_CHECK(cudaMalloc(&d_ctr, sizeof(L2Counters))); IX_CHECK(cudaMemset(d_ctr, 0, sizeof(L2Counters)));
+  IX_CHECK(ws_get(ix, WS_SLAB, sizeof(L2Entry) * (size_t)P.vec_cap * P.warps_per_cta * grid, &d_slab));
+  IX_CHECK(ws_get(ix, WS_MAP, sizeof(wfb_l2_mapping_t) * (size_t)std::max<long long>(cap, 1), &d_map));
+  IX_CHECK(ws_get(ix, WS_CNT, 8, &d_cnt)); IX_CHECK(cudaMemset(d_cnt, 0, 8));
+  IX_CHECK(ws_get(ix, WS_CTR, sizeof(L2Counters), &d_ctr)); IX_CHECK(cudaMemset(d_ctr, 0, sizeof(L2Counters)));
   IX_CHECK(cudaFuncSetAttribute(l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1)); IX_CHECK(cudaEventCreate(&e2));
   IX_CHECK(cudaEventRecord(e0));
@@ -584,18 +608,18 @@ extern "C" int wfb_map_fragments_batch(const wfb_index_t* ix, const wfb_l1_param
     int fbits = 1;
     while ((1LL << fbits) < n) ++fbits;
     size_t b1 = 0, b2 = 0;
-    IX_CHECK(cudaMalloc(&d_kp, 8 * (size_t)N)); IX_CHECK(cudaMalloc(&d_kp2, 8 * (size_t)N));
-    IX_CHECK(cudaMalloc(&d_kf, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_kf2, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_kf3, 4 * (size_t)N));
-    IX_CHECK(cudaMalloc(&d_idx, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_idx2, 4 * (size_t)N)); IX_CHECK(cudaMalloc(&d_idx3, 4 * (size_t)N));
-    IX_CHECK(cudaMalloc(&d_sorted, sizeof(wfb_l2_mapping_t) * (size_t)N));
+    IX_CHECK(ws_get(ix, WS_KP, 8 * (size_t)N, &d_kp)); IX_CHECK(ws_get(ix, WS_KP2, 8 * (size_t)N, &d_kp2));
+    IX_CHECK(ws_get(ix, WS_KF, 4 * (size_t)N, &d_kf)); IX_CHECK(ws_get(ix, WS_KF2, 4 * (size_t)N, &d_kf2)); IX_CHECK(ws_get(ix, WS_KF3, 4 * (size_t)N, &d_kf3));
+    IX_CHECK(ws_get(ix, WS_IDX, 4 * (size_t)N, &d_idx)); IX_CHECK(ws_get(ix, WS_IDX2, 4 * (size_t)N, &d_idx2)); IX_CHECK(ws_get(ix, WS_IDX3, 4 * (size_t)N, &d_idx3));
+    IX_CHECK(ws_get(ix, WS_SORTED, sizeof(wfb_l2_mapping_t) * (size_t)N, &d_sorted));
     IX_LAUNCH(l2_keys_kernel, G, 256, 0, d_map, N, d_kp, d_kf, d_idx);
     IX_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, b1, d_kp, d_kp2, d_idx, d_idx2, (int)N));
     IX_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, b2, d_kf2, d_kf3, d_idx2, d_idx3, (int)N, 0, fbits));
-    IX_CHECK(tmp.ensure(std::max(b1, b2)));
-    IX_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, b1, d_kp, d_kp2, d_idx, d_idx2, (int)N));
+    IX_CHECK(ws_get(ix, WS_CUBTMP, std::max(b1, b2), &d_cubtmp));
+    IX_CHECK(cub::DeviceRadixSort::SortPairs(d_cubtmp, b1, d_kp, d_kp2, d_idx, d_idx2, (int)N));
     wfb_count_launch_();
     IX_LAUNCH(l2_gather_u32_kernel, G, 256, 0, d_kf, d_idx2, N, d_kf2);
-    IX_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, b2, d_kf2, d_kf3, d_idx2, d_idx3, (int)N, 0, fbits));
+    IX_CHECK(cub::DeviceRadixSort::SortPairs(d_cubtmp, b2, d_kf2, d_kf3, d_idx2, d_idx3, (int)N, 0, fbits));
     wfb_count_launch_();
     IX_LAUNCH(l2_permute_kernel, G, 256, 0, d_map, d_idx3, N, d_sorted);
     IX_CHECK(cudaEventRecord(e2));
@@ -621,8 +645,6 @@ done:
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (e2) cudaEventDestroy(e2);
-  cudaFree(d_s1); cudaFree(d_ms); cudaFree(d_slab); cudaFree(d_map); cudaFree(d_sorted); cudaFree(d_cnt); cudaFree(d_ctr); cudaFree(d_kp);
-  cudaFree(d_kp2); cudaFree(d_kf); cudaFree(d_kf2); cudaFree(d_kf3); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_idx3);
   return rc;
 #else
   wfb_set_last_error_("the mapping batch is not part of the host emulation (see wfb_emu_l2_loci)");

@@ -762,3 +762,20 @@ extern "C" int wfb_debug_phase_timers(unsigned long long* out32) {
   return WFB_OK;
 }
 #endif
+
+/* wavefront_align-shaped shim over the batch entry (one pair). */
+extern "C" int wfb_wavefront_align(wfb_aligner_t* a, const char* pattern, int32_t pattern_length, const char* text, int32_t text_length,
+                                   char* cigar_operations, int32_t cigar_cap, int32_t* cigar_length, int32_t* cigar_score) {
+  if (!a || !pattern || !text || pattern_length < 0 || text_length < 0 || !cigar_operations || !cigar_length) {
+    wfb_set_last_error_("bad argument");
+    return WFB_EINVAL;
+  }
+  wfb_pair_t pr;
+  pr.pattern = pattern; pr.pattern_len = pattern_length; pr.text = text; pr.text_len = text_length;
+  wfb_aln_result_t r;
+  const int rc = wfb_align_batch(a, &pr, 1, cigar_operations, (int64_t)cigar_cap, &r, nullptr);
+  if (rc != WFB_OK) return rc;
+  *cigar_length = r.status == 0 ? r.ops_len : 0;
+  if (cigar_score) *cigar_score = r.status == 0 ? r.score : 0;
+  return r.status == 0 ? WFB_WF_STATUS_ALG_COMPLETED : WFB_WF_STATUS_UNATTAINABLE;
+}

@@ -87,3 +87,42 @@ def test_l2_kernel_body_under_emulation_matches_oracle(oracle):
             assert steps.value > len(l1)
             total += n_out.value
     assert total > 2000
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_l1_parallel_sweep_equals_serial_walk_under_emulation():
+    """The data-parallel L1 sweep (ix_l1_regions_par: prefix sums / segment ids over the sorted interval points) against
+    the literal two-pass walk of computeL1CandidateRegions (ix_l1_regions, itself checked against the oracle and the
+    compiled reference on the GPU) on random interval sets: several sequences and PanSN groups, equal positions across a
+    sequence boundary (the reference's position-only grouping), dense and sparse overlaps."""
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    emu = ctypes.CDLL(os.path.join(util.ROOT, so))
+    rng = np.random.default_rng(5)
+    cut = np.array([max(1, int(i * 0.5)) for i in range(1001)], dtype=np.int32)
+    nl_total = 0
+    for it in range(300):
+        nseq = int(rng.integers(1, 7))
+        groups = np.sort(rng.integers(0, 3, size=nseq)).astype(np.int32)  # ascending seqId -> non-decreasing group, like PanSN order
+        w = int(rng.choice([200, 1000]))
+        nint = int(rng.integers(1, 900))
+        seq = rng.integers(0, nseq, size=nint)
+        span = int(rng.choice([300, 3000, 50000]))
+        start = rng.integers(0, span, size=nint)
+        if it % 3 == 0:
+            start = (start // 7) * 7  # many equal positions, also across sequences
+        length = rng.integers(1, w + 1, size=nint)
+        keys = np.concatenate([(seq.astype(np.uint64) << np.uint64(41)) | (start.astype(np.uint64) << np.uint64(1)) | np.uint64(1),
+                               (seq.astype(np.uint64) << np.uint64(41)) | ((start + length).astype(np.uint64) << np.uint64(1))])
+        keys = np.sort(keys)
+        mh = int(rng.integers(1, 6))
+        sp = int(rng.integers(0, 2))
+        a = np.zeros(256, dtype=maputil.L1PUBDT); b = np.zeros(256, dtype=maputil.L1PUBDT)
+        na, nb = ctypes.c_int32(0), ctypes.c_int32(0)
+        rc = emu.wfb_emu_l1_sweeps(vp(keys), len(keys), 29, w, 29, mh, sp, vp(cut), len(cut), vp(groups), vp(a), ctypes.byref(na), vp(b), ctypes.byref(nb))
+        if rc == -5:
+            continue  # more than 256 loci: both paths report the capacity error
+        assert rc == 0
+        assert na.value == nb.value, (it, na.value, nb.value)
+        assert (a[: na.value] == b[: nb.value]).all(), it
+        nl_total += na.value
+    assert nl_total > 1500

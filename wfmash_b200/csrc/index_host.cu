@@ -384,7 +384,8 @@ int l1_run(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_bas
   P.k = k; P.w = w; P.s = s; P.minimum_hits = lp->minimum_hits;
   P.skip_self = lp->skip_self; P.skip_prefix = lp->skip_prefix; P.lower_triangular = lp->lower_triangular;
   P.ncut = lp->n_cutoffs; P.smem_cap = 4096; P.gcap = 1 << 17; P.max_loci = 256; P.complexity_threshold = lp->kmer_complexity_threshold;
-  const size_t smem = std::max(sketch_smem, (size_t)P.smem_cap * 8);
+  P.par_sweep = getenv("WFB_L1_SERIAL") ? 0 : 1;
+  const size_t smem = std::max(std::max(sketch_smem, (size_t)P.smem_cap * 8), (size_t)IX_PAR_CAP * 8 + ix_par_aux_bytes());
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int grid = 0;
   D.loci_cap = loci_cap;
@@ -682,6 +683,37 @@ extern "C" int wfb_emu_l2_loci(const wfb_minmer_t* index, int64_t n_index, const
   std::vector<float> kc((size_t)n_frags);
   for (int32_t i = 0; i < n_frags; ++i) kc[(size_t)i] = q_count[i] > 0 ? ix_kmer_complexity(q_all[(size_t)i * s + q_count[i] - 1].hash, q_count[i], w, k) : 0.f;
   l2_finish_host(out, (int64_t)cnt, q_count, kc.data(), n_frags, k, s, off.data());
+  return WFB_OK;
+}
+#endif
+
+#ifdef WFB_EMU
+/* TEST-ONLY: the serial L1 walk (ix_l1_regions per group slice, as the kernel's fallback runs it) and the data-parallel
+ * sweep (ix_l1_regions_par) over the same sorted packed keys, under the single-thread emulation. */
+extern "C" int wfb_emu_l1_sweeps(const uint64_t* keys, int32_t n, int32_t q_sketch, int32_t w, int32_t s, int32_t minimum_hits, int32_t skip_prefix,
+                                 const int32_t* cutoffs, int32_t ncut, const int32_t* ref_group, wfb_l1_locus_t* out_serial, int32_t* n_serial,
+                                 wfb_l1_locus_t* out_par, int32_t* n_par) {
+  if (n > IX_PAR_CAP) return WFB_EINVAL;
+  IxL1Params P{};
+  P.k = 15; P.w = w; P.s = s; P.minimum_hits = minimum_hits; P.skip_prefix = skip_prefix; P.ncut = ncut; P.max_loci = 256; P.par_sweep = 1;
+  std::vector<IxL1Locus> ltmp((size_t)2 * P.max_loci), ltmp2((size_t)2 * P.max_loci);
+  int nout = 0, err = 0, b = 0;
+  while (b < n) {
+    int e = n;
+    if (skip_prefix) { e = b; const int g = ref_group[ix_seq(keys[b])]; while (e < n && ref_group[ix_seq(keys[e])] == g) ++e; }
+    ix_l1_regions(keys + b, e - b, minimum_hits, q_sketch, P, cutoffs, ltmp.data(), nout, ltmp.data() + P.max_loci, P.max_loci, err);
+    b = e;
+  }
+  if (err) return WFB_ECAP;
+  *n_serial = nout;
+  for (int i = 0; i < nout; ++i) { out_serial[i].seqId = ltmp[i].seqId; out_serial[i].intersectionSize = ltmp[i].intersectionSize; out_serial[i].rangeStartPos = ltmp[i].rangeStartPos; out_serial[i].rangeEndPos = ltmp[i].rangeEndPos; }
+  std::vector<unsigned char> aux(ix_par_aux_bytes() + 64);
+  static IxParShared S;
+  const IxParAux A = ix_par_carve(aux.data());
+  if (!ix_l1_regions_par(keys, n, q_sketch, P, cutoffs, ref_group, A, S, ltmp2.data(), ltmp2.data() + P.max_loci, P.max_loci)) return WFB_ECAP;
+  if (S.err) return WFB_ECAP;
+  *n_par = S.nout;
+  for (int i = 0; i < S.nout; ++i) { out_par[i].seqId = ltmp2[i].seqId; out_par[i].intersectionSize = ltmp2[i].intersectionSize; out_par[i].rangeStartPos = ltmp2[i].rangeStartPos; out_par[i].rangeEndPos = ltmp2[i].rangeEndPos; }
   return WFB_OK;
 }
 #endif

@@ -102,6 +102,7 @@ struct IxL1Params {
   int smem_cap;         /* interval points that fit the shared-memory buffer (power of two) */
   int gcap;             /* ... the per-CTA global scratch (power of two) */
   int max_loci;         /* per fragment */
+  int par_sweep;        /* 1 = data-parallel L1 sweep (ix_l1_regions_par), 0 = thread 0 walks (kept for A/B runs: WFB_L1_SERIAL=1) */
   float complexity_threshold;
 };
 
@@ -178,6 +179,206 @@ WFB_DEV void ix_l1_regions(const uint64_t* ip, int n, int minimumHits, int q_ske
   }
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * The same two sweeps (+ the join, :287-300) for ALL group slices of a fragment at once, data-parallel over the CTA.
+ * The serial walk above is a chain of ~3 n dependent shared-memory reads on one thread while the other warps wait at a
+ * barrier (65 % of the L1 kernel's time, profiles/r01_ncu_map_kernels_summary.txt); here every quantity it carries is a
+ * prefix sum, a segment id or a segmented maximum over the sorted points:
+ *   slice    = maximal run of points whose sequences share a PanSN group (computeMap.hpp:964-982; one slice without -Y)
+ *   step     = maximal run of consecutive points with equal pos (POSITION ONLY, like the reference's leading loop, :177
+ *              / :238: a step may spill across a sequence boundary)
+ *   spc run  = maximal run of points with equal (seqId, pos): where the trailing pointer stops (ip[tr] <= lead | 1)
+ *   overlap after step j = opens before the step's end - closes before the end of the spc run its first point starts
+ *   candidate run = consecutive steps (never a slice's last one: the reference looks at a step's count one iteration
+ *              later) with overlap >= the slice's minimumHits on one sequence -> one local locus; loci closer than w on the
+ *              same sequence join (the rule only looks at the previous local locus).
+ * One 64-bit block scan carries five 12-bit counters (n <= IX_PAR_CAP = 2048 points): opens | closes | steps | spc runs |
+ * slices. Larger fragments and fragments with more than IX_PAR_SLICES slices take the serial walk (same results). */
+#define IX_PAR_CAP 2048
+#define IX_PAR_SLICES 256
+#define IX_F_OPEN(x) ((int)((x) & 0xFFF))
+#define IX_F_CLOSE(x) ((int)(((x) >> 12) & 0xFFF))
+#define IX_F_STEP(x) ((int)(((x) >> 24) & 0xFFF))
+#define IX_F_SPC(x) ((int)(((x) >> 36) & 0xFFF))
+#define IX_F_SLICE(x) ((int)(((x) >> 48) & 0xFFF))
+#define IX_ID_ONE ((1ULL << 24) | (1ULL << 36) | (1ULL << 48))
+
+struct IxParAux { /* views into the CTA's dynamic shared memory behind the IX_PAR_CAP keys */
+  unsigned long long* pre;   /* [n + 1] per point: opens / closes BEFORE it, ids of its step / spc run / slice; [n] = totals */
+  unsigned short* stepfirst; /* [nsteps + 1] first point of a step; [nsteps] = n */
+  unsigned short* spcfirst;  /* [nspc + 1] */
+  short* ov;                 /* [nsteps] overlap after the step */
+};
+#ifndef WFB_EMU
+__host__ __device__
+#endif
+static inline size_t ix_par_aux_bytes() { return (size_t)(IX_PAR_CAP + 2) * 8 + (size_t)(IX_PAR_CAP + 8) * 2 * 3; }
+WFB_DEV IxParAux ix_par_carve(unsigned char* p) {
+  IxParAux a;
+  a.pre = (unsigned long long*)p; p += (size_t)(IX_PAR_CAP + 2) * 8;
+  a.stepfirst = (unsigned short*)p; p += (size_t)(IX_PAR_CAP + 8) * 2;
+  a.spcfirst = (unsigned short*)p; p += (size_t)(IX_PAR_CAP + 8) * 2;
+  a.ov = (short*)p;
+  return a;
+}
+
+/* exclusive scan of one 64-bit value per thread over the CTA (two barriers); total = the CTA-wide sum */
+WFB_DEV unsigned long long ix_cta_exscan(unsigned long long v, unsigned long long* sh, unsigned long long& total) {
+#ifndef WFB_EMU
+  const int lane = WFB_TID & 31, wid = WFB_TID >> 5, nw = (WFB_NT + 31) >> 5;
+  unsigned long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) sh[wid] = x;
+  __syncthreads();
+  unsigned long long base = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) { const unsigned long long t = sh[w]; if (w < wid) base += t; tot += t; }
+  __syncthreads();
+  total = tot;
+  return base + x - v;
+#else
+  (void)sh;
+  total = v;
+  return 0;
+#endif
+}
+
+struct IxParShared { /* static shared memory of the parallel sweep */
+  unsigned long long scan[33];
+  int slbest[IX_PAR_SLICES], slmh[IX_PAR_SLICES], slstep[IX_PAR_SLICES]; /* per slice: best overlap, minimumHits, first step */
+  int nout, err;
+};
+
+/* All threads of the CTA call this with the same arguments. buf[0..n) sorted keys in shared memory (n <= IX_PAR_CAP).
+ * Returns false (uniform, nothing written) when the fragment has more slices than IX_PAR_SLICES; otherwise the joined
+ * loci are in out[0 .. S.nout) and S.err tells whether a capacity was exceeded. local: scratch of local_cap loci. */
+WFB_DEV bool ix_l1_regions_par(const uint64_t* buf, int n, int q_sketch, const IxL1Params& P, const int* cutoffs, const int* ref_group,
+                               const IxParAux& A, IxParShared& S, IxL1Locus* out, IxL1Locus* local, int local_cap) {
+  const int tid = WFB_TID, nt = WFB_NT;
+  for (int i = tid; i < IX_PAR_SLICES; i += nt) S.slbest[i] = 0;
+  if (tid == 0) { S.nout = 0; S.err = 0; }
+  /* P1: flags -> one packed scan */
+  unsigned long long carry = 0;
+  for (int base = 0; base < n; base += nt) {
+    const int i = base + tid;
+    unsigned long long v = 0;
+    bool sb = false, st = false, spc = false;
+    if (i < n) {
+      const uint64_t key = buf[i], prev = i > 0 ? buf[i - 1] : 0ULL;
+      sb = i == 0 || (P.skip_prefix && ref_group[ix_seq(key)] != ref_group[ix_seq(prev)]);
+      st = sb || ix_pos(key) != ix_pos(prev);
+      spc = sb || (key >> 1) != (prev >> 1);
+      v = (ix_open(key) ? 1ULL : (1ULL << 12)) | (st ? (1ULL << 24) : 0ULL) | (spc ? (1ULL << 36) : 0ULL) | (sb ? (1ULL << 48) : 0ULL);
+    }
+    unsigned long long total;
+    const unsigned long long ex = ix_cta_exscan(v, S.scan, total) + carry;
+    if (i < n) {
+      const unsigned long long incl = ex + v; /* every id field of incl is >= 1: point 0 carries all three flags */
+      const unsigned long long rec = (ex & 0xFFFFFFULL) | ((incl - IX_ID_ONE) & ~0xFFFFFFULL);
+      A.pre[i] = rec;
+      if (st) A.stepfirst[IX_F_STEP(rec)] = (unsigned short)i;
+      if (spc) A.spcfirst[IX_F_SPC(rec)] = (unsigned short)i;
+      if (sb && IX_F_SLICE(rec) < IX_PAR_SLICES) S.slstep[IX_F_SLICE(rec)] = IX_F_STEP(rec);
+    }
+    carry += total;
+  }
+  const int nsteps = IX_F_STEP(carry), nspc = IX_F_SPC(carry), nslices = IX_F_SLICE(carry);
+  if (nslices > IX_PAR_SLICES) { WFB_SYNC(); return false; }
+  if (tid == 0) { A.pre[n] = carry; A.stepfirst[nsteps] = (unsigned short)n; A.spcfirst[nspc] = (unsigned short)n; }
+  WFB_SYNC();
+  /* P2: overlap after every step (pass 1, :160-187) + the slice's best */
+  for (int j = tid; j < nsteps; j += nt) {
+    const int f = A.stepfirst[j], l = A.stepfirst[j + 1];
+    const unsigned long long pf = A.pre[f];
+    const int tr = A.spcfirst[IX_F_SPC(pf) + 1];
+    const int sl = IX_F_SLICE(pf);
+    const unsigned long long p0 = A.pre[A.stepfirst[S.slstep[sl]]];
+    const int ov = (IX_F_OPEN(A.pre[l]) - IX_F_OPEN(p0)) - (IX_F_CLOSE(A.pre[tr]) - IX_F_CLOSE(p0));
+    A.ov[j] = (short)ov;
+    wfb_smem_max(&S.slbest[sl], ov);
+  }
+  WFB_SYNC();
+  /* P3: minimumHits of every slice (:189-198) */
+  for (int sl = tid; sl < nslices; sl += nt) {
+    const int best = S.slbest[sl];
+    int mh = INT_MAX; /* best < minimumHits: the slice returns early */
+    if (best >= P.minimum_hits) {
+      mh = P.minimum_hits;
+      const double div = P.s / 1000.0 > 1.0 ? P.s / 1000.0 : 1.0;
+      int idx = (int)((best < q_sketch ? best : q_sketch) / div);
+      if (idx >= P.ncut) idx = P.ncut - 1;
+      if (cutoffs[idx] > mh) mh = cutoffs[idx];
+    }
+    S.slmh[sl] = mh;
+  }
+  WFB_SYNC();
+  /* P4: candidate runs (pass 2, :203-284) -> local[] in order */
+#define IX_STEP_Q(J, SL) ((J) + 1 < nsteps && IX_F_SLICE(A.pre[A.stepfirst[(J) + 1]]) == (SL) && (int)A.ov[(J)] >= S.slmh[(SL)])
+  int nlocal = 0;
+  for (int base = 0; base < nsteps; base += nt) {
+    const int j = base + tid;
+    bool rs = false;
+    int sl = 0, f = 0;
+    if (j < nsteps) {
+      f = A.stepfirst[j];
+      sl = IX_F_SLICE(A.pre[f]);
+      if (IX_STEP_Q(j, sl)) {
+        rs = j == S.slstep[sl] || !((int)A.ov[j - 1] >= S.slmh[sl]) || ix_seq(buf[f]) != ix_seq(buf[A.stepfirst[j - 1]]);
+      }
+    }
+    unsigned long long total;
+    const int r = nlocal + (int)ix_cta_exscan(rs ? 1ULL : 0ULL, S.scan, total);
+    if (rs) {
+      IxL1Locus c;
+      c.seqId = ix_seq(buf[f]); c.rangeStartPos = ix_pos(buf[f]); c.rangeEndPos = c.rangeStartPos; c.intersectionSize = A.ov[j];
+      for (int t = j + 1; IX_STEP_Q(t, sl) && ix_seq(buf[A.stepfirst[t]]) == c.seqId; ++t) {
+        c.rangeEndPos = ix_pos(buf[A.stepfirst[t]]);
+        if ((int)A.ov[t] > c.intersectionSize) c.intersectionSize = A.ov[t];
+      }
+      if (r < local_cap) local[r] = c; else S.err = 1;
+    }
+    nlocal += (int)total;
+  }
+#undef IX_STEP_Q
+  if (nlocal > local_cap) nlocal = local_cap; /* S.err is set */
+#ifndef WFB_EMU
+  __threadfence_block();
+#endif
+  WFB_SYNC();
+  /* P5: join (:287-300) */
+  int nout = 0;
+  for (int base = 0; base < nlocal; base += nt) {
+    const int r = base + tid;
+    bool ng = false;
+    IxL1Locus c;
+    if (r < nlocal) {
+      c = local[r];
+      ng = r == 0 || c.seqId != local[r - 1].seqId || c.rangeStartPos > local[r - 1].rangeEndPos + P.w;
+    }
+    unsigned long long total;
+    const int g = nout + (int)ix_cta_exscan(ng ? 1ULL : 0ULL, S.scan, total);
+    if (ng) {
+      for (int t = r + 1; t < nlocal; ++t) {
+        const IxL1Locus d = local[t];
+        if (d.seqId != local[t - 1].seqId || d.rangeStartPos > local[t - 1].rangeEndPos + P.w) break;
+        c.rangeEndPos = d.rangeEndPos;
+        if (d.intersectionSize > c.intersectionSize) c.intersectionSize = d.intersectionSize;
+      }
+      if (g < P.max_loci) out[g] = c; else S.err = 1;
+    }
+    nout += (int)total;
+  }
+  if (tid == 0) S.nout = nout < P.max_loci ? nout : P.max_loci;
+#ifndef WFB_EMU
+  __threadfence_block();
+#endif
+  WFB_SYNC();
+  return true;
+}
+
 struct IxFragQuery { /* per-fragment query metadata (QueryMetaData, base_types.hpp:336-349) */
   int q_seq_id, q_group;
 };
@@ -203,6 +404,7 @@ WFB_KERNEL(ix_l1_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, const
   WFB_SHARED uint32_t sh_start[512], sh_cnt[512], sh_off[513];
   WFB_SHARED int sh_total, sh_nloci, sh_err;
   WFB_SHARED unsigned long long sh_base;
+  WFB_SHARED IxParShared sh_par;
   uint64_t* gscratch = gscratch_all + (long long)bid * P.gcap;
   IxL1Locus* ltmp = loci_tmp_all + (long long)bid * 2 * P.max_loci; /* [0,max) = out list, [max,2max) = local */
   for (int f = bid; f < nfrags; f += nblocks) {
@@ -285,9 +487,23 @@ WFB_KERNEL(ix_l1_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, const
         WFB_SYNC();
       }
     }
-    if (WFB_TID == 0) {
-      int n = total;
-      while (n > 0 && buf[n - 1] == IX_EMPTY) --n; /* filtered points sorted to the end */
+    /* points that survived the group filters (the dropped ones sorted to the end as +inf keys) */
+    if (WFB_TID == 0) sh_total = 0;
+    WFB_SYNC();
+    for (int i = WFB_TID; i < total; i += WFB_NT)
+      if (buf[i] != IX_EMPTY && (i + 1 == total || buf[i + 1] == IX_EMPTY)) sh_total = i + 1;
+    WFB_SYNC();
+    const int n = sh_total;
+    bool swept = false;
+    if (P.par_sweep && buf == (uint64_t*)smem && N <= IX_PAR_CAP) {
+      const IxParAux A = ix_par_carve(smem + (size_t)IX_PAR_CAP * 8);
+      swept = ix_l1_regions_par(buf, n, qn, P, cutoffs, ref_group, A, sh_par, ltmp, ltmp + P.max_loci, P.max_loci);
+      if (swept && WFB_TID == 0) {
+        sh_nloci = sh_par.nout; sh_err = sh_par.err;
+        if (sh_par.nout > 0) sh_base = atomicAdd_compat(loci_counter, (unsigned long long)sh_par.nout);
+      }
+    }
+    if (!swept && WFB_TID == 0) { /* oversized fragment / too many group slices: the serial walk */
       int nout = 0, err = 0;
       int b = 0;
       while (b < n) { /* per PanSN group slice, computeMap.hpp:964-982 */

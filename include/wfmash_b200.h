@@ -375,6 +375,53 @@ int wfb_stage1_min_hits(double hg_numerator, float ani_diff, int32_t kmer_size, 
 /* out[sketch_size + 1] for keep_low_pct_id == false; percentage_identity in [0,1] */
 int wfb_l2_min_shared(float percentage_identity, int32_t kmer_size, int32_t sketch_size, int32_t* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path 1 -> path 2 hand-over, host stage (first part): the fragment mappings of a query become chains,
+ * and every chain is cut into merged mappings of at most max_mapping_length: the records the aligner receives.
+ * Host C++ like the reference (one query per host thread).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { /* skch::MappingResult (src/map/include/base_types.hpp:153-163), same 28-byte layout */
+  uint32_t refSeqId;
+  uint32_t refStartPos;
+  uint32_t queryStartPos;
+  uint32_t blockLength;
+  uint32_t n_merged;
+  uint32_t conservedSketches;
+  uint16_t nucIdentity;   /* identity * 10000, rounded (setNucIdentity)          */
+  uint8_t flags;          /* bit 0 = REV strand, bit 1 = discard, bit 2 = overlapped */
+  uint8_t kmerComplexity; /* complexity * 100, rounded (setKmerComplexity)       */
+} wfb_mapping_t;
+
+typedef struct { /* skch::ChainInfo (base_types.hpp:261-265): the ch:Z:<chainId>.<chainPos>.<chainLen> tag */
+  uint32_t chainId;
+  uint16_t chainPos;
+  uint16_t chainLen;
+} wfb_chain_info_t;
+
+typedef struct {
+  int32_t split;               /* param.split (default true; false = -N: nothing is chained)  */
+  int32_t reserved_;
+  int64_t chain_gap;           /* param.chain_gap (-c, default 2000)                          */
+  int64_t window_length;       /* param.windowLength                                          */
+  uint64_t max_mapping_length; /* param.max_mapping_length (-P, default 50000)                */
+} wfb_chain_params_t;
+
+/* What Map::processFragment + OutputHandler::mappingBoundarySanityCheck do to the L2 results of ONE query before the
+ * filters see them (src/map/include/computeMap.hpp:121-127,1029-1046; src/map/include/mappingOutput.hpp:31-69):
+ * MappingResult construction (scaled identity / complexity, strand flag), queryStartPos = fragmentIndex * windowLength,
+ * clamping against the query / reference lengths. frag_index[f] = FragmentData::fragmentIndex of batch fragment f
+ * (the overlapping tail fragment carries noOverlapFragmentCount, computeMap.hpp:612). out[n]. */
+int wfb_l2_to_query_mappings(const wfb_l2_mapping_t* l2, int64_t n, const int32_t* frag_index, int64_t window_length, int64_t query_len,
+                             const int64_t* ref_seq_len, wfb_mapping_t* out);
+
+/* skch::MappingFilterUtils::mergeMappingsInRangeWithChains (src/map/include/mappingFilter.hpp:381-571) as called by
+ * Map::filterSubsetMappings (src/map/include/computeMap.hpp:1090-1094), for a batch of queries:
+ * query q owns mappings[query_offset[q] .. query_offset[q+1]) (reordered in place, as the reference leaves readMappings)
+ * and receives merged[merged_offset[q] .. merged_offset[q+1]) with their chain tags. host_threads <= 0: all cores. */
+int wfb_chain_mappings_batch(const wfb_chain_params_t* params, wfb_mapping_t* mappings, const int64_t* query_offset, int32_t n_queries,
+                             wfb_mapping_t* merged, wfb_chain_info_t* chain_info, int64_t merged_cap, int64_t* merged_offset,
+                             int32_t host_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -495,3 +495,49 @@ def sketch_fragments(seq: bytes, frags, kmer_size: int, sketch_size: int, device
     if rc != 0:
         raise _err(rc)
     return out[:n], cnt[:n], ms.value
+
+
+# ---- path 1 -> path 2 hand-over (host stage) ---------------------------------------------------------
+MAPPING_DTYPE = np.dtype([("refSeqId", "<u4"), ("refStartPos", "<u4"), ("queryStartPos", "<u4"), ("blockLength", "<u4"), ("n_merged", "<u4"),
+                          ("conservedSketches", "<u4"), ("nucIdentity", "<u2"), ("flags", "u1"), ("kmerComplexity", "u1")])  # skch::MappingResult
+CHAIN_INFO_DTYPE = np.dtype([("chainId", "<u4"), ("chainPos", "<u2"), ("chainLen", "<u2")])  # skch::ChainInfo
+
+
+class _ChainParams(ctypes.Structure):
+    _fields_ = [("split", ctypes.c_int32), ("reserved_", ctypes.c_int32), ("chain_gap", ctypes.c_int64), ("window_length", ctypes.c_int64),
+                ("max_mapping_length", ctypes.c_uint64)]
+
+
+def l2_to_query_mappings(l2, frag_index, window_length: int, query_len: int, ref_seq_len):
+    """Map::processFragment + mappingBoundarySanityCheck for the L2 mappings of ONE query (computeMap.hpp:121-127,
+    1029-1046; mappingOutput.hpp:31-69): returns skch::MappingResult records."""
+    l2 = np.ascontiguousarray(l2, dtype=L2_MAPPING_DTYPE)
+    fi = np.ascontiguousarray(frag_index, dtype=np.int32)
+    rl = np.ascontiguousarray(ref_seq_len, dtype=np.int64)
+    out = np.zeros(max(len(l2), 1), dtype=MAPPING_DTYPE)
+    rc = lib().wfb_l2_to_query_mappings(ctypes.c_void_p(l2.ctypes.data), ctypes.c_int64(len(l2)), ctypes.c_void_p(fi.ctypes.data),
+                                        ctypes.c_int64(window_length), ctypes.c_int64(query_len), ctypes.c_void_p(rl.ctypes.data),
+                                        ctypes.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise _err(rc)
+    return out[: len(l2)]
+
+
+def chain_mappings_batch(mappings, query_offset, window_length: int, chain_gap: int = 2000, max_mapping_length: int = 50000, split: bool = True,
+                         host_threads: int = 0):
+    """MappingFilterUtils::mergeMappingsInRangeWithChains (mappingFilter.hpp:381-571) for a batch of queries.
+    Returns (mappings reordered like the reference's readMappings, merged mappings, chain info, merged_offset)."""
+    m = np.array(mappings, dtype=MAPPING_DTYPE, copy=True)
+    qo = np.ascontiguousarray(query_offset, dtype=np.int64)
+    nq = len(qo) - 1
+    cap = len(m) + 16
+    merged = np.zeros(cap, dtype=MAPPING_DTYPE)
+    info = np.zeros(cap, dtype=CHAIN_INFO_DTYPE)
+    mo = np.zeros(nq + 1, dtype=np.int64)
+    prm = _ChainParams(int(split), 0, chain_gap, window_length, max_mapping_length)
+    rc = lib().wfb_chain_mappings_batch(ctypes.byref(prm), ctypes.c_void_p(m.ctypes.data), ctypes.c_void_p(qo.ctypes.data), nq,
+                                        ctypes.c_void_p(merged.ctypes.data), ctypes.c_void_p(info.ctypes.data), ctypes.c_int64(cap),
+                                        ctypes.c_void_p(mo.ctypes.data), host_threads)
+    if rc != 0:
+        raise _err(rc)
+    return m, merged[: mo[-1]], info[: mo[-1]], mo

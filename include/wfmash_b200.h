@@ -422,6 +422,93 @@ int wfb_chain_mappings_batch(const wfb_chain_params_t* params, wfb_mapping_t* ma
                              wfb_mapping_t* merged, wfb_chain_info_t* chain_info, int64_t merged_cap, int64_t* merged_offset,
                              int32_t host_threads);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8 f2, second part + b3: everything Map::filterSubsetMappings does to the mappings of one query after the
+ * chain merge (src/map/include/computeMap.hpp:1076-1165), the mapping PAF text (the reference's map -> align
+ * dispatch format, src/map/include/mappingOutput.hpp:74-139) and its reader on the aligner side
+ * (Aligner::parseMashmapRow + createSeqRecord, src/align/include/computeAlignments.hpp:195-303,582-660).
+ * Host C++ like the reference.
+ * ---------------------------------------------------------------------------------------------- */
+#define WFB_FILTER_MAP 1      /* skch::filter::MAP (default)      */
+#define WFB_FILTER_ONETOONE 2 /* skch::filter::ONETOONE (-o)      */
+#define WFB_FILTER_NONE 3     /* skch::filter::NONE (-f)          */
+
+typedef struct { /* the skch::Parameters fields the filters read (src/map/include/map_parameters.hpp:31-109) */
+  int32_t split;                    /* param.split (true unless -N)                                     */
+  int32_t merge_mappings;           /* param.mergeMappings (true unless -M)                             */
+  int32_t filter_mode;              /* WFB_FILTER_*                                                     */
+  int32_t skip_prefix;              /* param.skip_prefix (-Y given): plane sweep per PanSN target group */
+  int32_t filter_length_mismatches; /* param.filterLengthMismatches (true on the CLI path)              */
+  int32_t drop_rand;                /* param.dropRand (false on the CLI path)                           */
+  int32_t threads;                  /* param.threads (only sizes the scaffold distance loop)            */
+  int32_t legacy_output;            /* param.legacy_output (false on the CLI path)                      */
+  int64_t chain_gap;                /* -c, default 2000                                                 */
+  int64_t window_length;            /* -w                                                               */
+  int64_t block_length;             /* -l, default 0                                                    */
+  uint64_t max_mapping_length;      /* -P, default 50000                                                */
+  uint64_t sparsity_hash_threshold; /* default UINT64_MAX = keep everything                             */
+  uint32_t num_mappings_for_segment;  /* -n; default UINT32_MAX ("inf")                                 */
+  uint32_t num_mappings_for_scaffold; /* -r; default 1                                                  */
+  double overlap_threshold;           /* -O, default 0.95                                               */
+  double scaffold_overlap_threshold;  /* --scaffold-overlap, default 0.5                                */
+  int64_t scaffold_gap;               /* -j, default 100000; <= 0 disables the scaffold filter          */
+  int64_t scaffold_max_deviation;     /* -D, default 100000                                             */
+  int64_t scaffold_min_length;        /* -S, default 10000                                              */
+  float percentage_identity;          /* param.percentageIdentity in [0,1]                              */
+  int32_t reserved_;
+} wfb_filter_params_t;
+
+/* Map::filterSubsetMappings for a batch of queries: chain merge (as wfb_chain_mappings_batch), filterWeakMappings,
+ * filterByGroup (query plane sweep, src/map/include/filter.hpp:170-240), filterFalseHighIdentity, sparsifyMappings,
+ * filterByScaffolds (src/map/include/mappingFilter.hpp:154-293,831-1016). Query q owns mappings[query_offset[q] ..
+ * query_offset[q+1]) (not modified) and receives out[out_offset[q] .. out_offset[q+1]) = the mappings the reference
+ * prints for it (the merged ones when merge_mappings && split, else the filtered fragment mappings) with the ChainInfo
+ * the reference pairs them with (the i-th surviving mapping gets the i-th pre-filter entry, computeMap.hpp:664-667 +
+ * mappingOutput.hpp:96-97). ref_group[refSeqId] is only read when skip_prefix. host_threads <= 0: all cores. */
+int wfb_filter_mappings_batch(const wfb_filter_params_t* params, const wfb_mapping_t* mappings, const int64_t* query_offset,
+                              const int64_t* query_len, int32_t n_queries, const int32_t* ref_group, const int64_t* ref_seq_len,
+                              wfb_mapping_t* out, wfb_chain_info_t* out_chain, int64_t out_cap, int64_t* out_offset, int32_t host_threads);
+
+/* skch::MappingFilterUtils::filterByGroup alone (mappingFilter.hpp:220-293): filter_ref = 0 plane sweep over the query
+ * axis, 1 over the reference axis (filter.hpp:474-535). mappings is reordered in place like the reference's
+ * unfilteredMappings. Returns the number of survivors (<0: WFB_E*); out[out_cap]. */
+int64_t wfb_filter_by_group(const wfb_filter_params_t* params, wfb_mapping_t* mappings, int64_t n, int32_t n_mappings, int32_t filter_ref,
+                            const int32_t* ref_group, const int64_t* ref_seq_len, wfb_mapping_t* out, int64_t out_cap);
+
+/* The final pass of the one-to-one mode (computeMap.hpp:788-850): the surviving mappings of ALL queries are regrouped by
+ * target sequence, plane-swept over the reference axis, and handed back to every query that holds a mapping with the same
+ * (refSeqId, refStartPos, queryStartPos) — including the duplicates this rule creates when two queries share such a
+ * triple. Queries are visited in ascending q and targets in ascending refSeqId (the reference iterates unordered_maps,
+ * so its line ORDER is unspecified; the multiset of lines is what is reproduced). out_query[i] = owner of out[i];
+ * out is grouped by query. Returns the count (<0: WFB_E*). */
+int64_t wfb_one_to_one_filter(const wfb_filter_params_t* params, const wfb_mapping_t* mappings, const int64_t* query_offset, int32_t n_queries,
+                              const int32_t* ref_group, const int64_t* ref_seq_len, wfb_mapping_t* out, int32_t* out_query, int64_t out_cap);
+
+/* OutputHandler::reportReadMappings (mappingOutput.hpp:74-139): the mapping PAF lines of one query, byte-compatible with
+ * `wfmash -m` (so they feed the reference aligner through -i and vice versa). ref_names[refSeqId]. chain may be NULL
+ * (every mapping its own chain, mappingOutput.hpp:143-160). Returns the text length; WFB_ECAP (with the needed size in
+ * *needed, when not NULL) if buf_cap is too small. */
+int64_t wfb_mapping_paf_format(const wfb_filter_params_t* params, const wfb_mapping_t* mappings, const wfb_chain_info_t* chain, int64_t n,
+                               const char* query_name, int64_t query_len, const char* const* ref_names, const int64_t* ref_seq_len, char* buf,
+                               int64_t buf_cap, int64_t* needed);
+
+typedef struct { /* align::MappingBoundaryRow (src/align/include/align_types.hpp) + what createSeqRecord derives from it */
+  int64_t q_start, q_end;           /* after query padding                                               */
+  int64_t r_start, r_end;           /* after target padding                                              */
+  int64_t ref_fetch_start, ref_fetch_len; /* target slice incl. the wflign_max_len_minor head / tail room (computeAlignments.hpp:611-624) */
+  int64_t query_len, ref_len;       /* columns 2 and 7                                                   */
+  int64_t chain_id, chain_length, chain_pos;
+  int32_t strand;                   /* 1 = '+', -1 = '-'                                                 */
+  float mashmap_estimated_identity;
+  int32_t q_name_off, q_name_len;   /* byte ranges of the two names inside the line                      */
+  int32_t r_name_off, r_name_len;
+} wfb_mapping_row_t;
+
+/* Aligner::parseMashmapRow for one line (no trailing '\n' needed). WFB_EINVAL (message in wfb_last_error) where the
+ * reference throws: fewer than 13 tokens, unparsable numbers, padded coordinates beyond the reference length. */
+int wfb_mapping_paf_parse(const char* line, int64_t line_len, uint64_t target_padding, uint64_t query_padding, uint64_t wflign_max_len_minor,
+                          wfb_mapping_row_t* row);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,217 @@
+"""Host stage between the chain merge and the aligner (second part, and b3): wfb_filter_mappings_batch,
+wfb_filter_by_group, wfb_one_to_one_filter, wfb_mapping_paf_format against the reference's UNMODIFIED mappingFilter.hpp /
+filter.hpp / mappingOutput.hpp compiled in place (oracle/_ref/libfilterref.so) and against the committed fixture generated
+from it (tests/golden/filter_reference.json.gz); wfb_mapping_paf_parse against the rules of Aligner::parseMashmapRow.
+These entry points are host C++ inside the product library: no GPU is needed to run them."""
+import ctypes
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import chainutil, util
+
+# (seed, generator arguments, filter parameters, PanSN groups of the 4 target sequences or None)
+CASES = [
+    (21, dict(w=1000), dict(), None),                                                                   # the CLI defaults
+    (22, dict(w=1000), dict(num_mappings_for_segment=1, overlap_threshold=0.5, skip_prefix=1), [0, 0, 1, 2]),
+    (23, dict(w=1000), dict(num_mappings_for_segment=3, block_length=3000, scaffold_gap=0), None),
+    (24, dict(w=1000), dict(merge_mappings=0, filter_mode=3), None),                                     # -M -f
+    (25, dict(w=1000), dict(split=0, num_mappings_for_segment=2, scaffold_min_length=500), None),                                # -N
+    (26, dict(w=1000), dict(filter_mode=3), None),
+    (27, dict(w=1000), dict(drop_rand=1, num_mappings_for_segment=2, overlap_threshold=1.0), None),
+    (28, dict(w=500, qlen=120_000), dict(scaffold_gap=5000, scaffold_max_deviation=3000, scaffold_min_length=5000, max_mapping_length=10000), None),
+    (29, dict(w=1000), dict(sparsity_hash_threshold=2**63, filter_mode=2, num_mappings_for_scaffold=2), None),
+    (30, dict(w=1000, nref=1), dict(merge_mappings=0, num_mappings_for_segment=1, scaffold_min_length=1000), None),
+]
+REF_LEN = np.full(4, 400_000, dtype=np.int64)
+QLEN = 300_000
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def params(gen, prm):
+    import wfmash_b200 as wb
+    return wb.FilterParams(window_length=gen.get("w", 1000), **prm)
+
+
+def ours(seed, gen, prm, groups):
+    import wfmash_b200 as wb
+    m, off = chainutil.batch(seed, **gen)
+    qlen = np.full(len(off) - 1, gen.get("qlen", QLEN), dtype=np.int64)
+    out, info, oo = wb.filter_mappings_batch(params(gen, prm), m, off, qlen, REF_LEN, ref_group=groups, host_threads=3)
+    return (out, info, oo), m, off
+
+
+def reference(ref, gen, prm, groups, m, off):
+    import wfmash_b200 as wb
+    ref.ref_filter_subset.restype = ctypes.c_int64
+    P = params(gen, prm)
+    g = np.ascontiguousarray(groups, dtype=np.int32) if groups is not None else None
+    outs, infos, oo = [], [], [0]
+    for q in range(len(off) - 1):
+        a = np.ascontiguousarray(m[off[q]: off[q + 1]])
+        o = np.zeros(len(a) + 4, dtype=wb.MAPPING_DTYPE)
+        c = np.zeros(len(a) + 4, dtype=wb.CHAIN_INFO_DTYPE)
+        n = ref.ref_filter_subset(ctypes.byref(P), ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(len(a)), q, ctypes.c_int64(gen.get("qlen", QLEN)),
+                                  ctypes.c_void_p(g.ctypes.data) if g is not None else None, ctypes.c_void_p(REF_LEN.ctypes.data),
+                                  ctypes.c_void_p(o.ctypes.data), ctypes.c_void_p(c.ctypes.data), ctypes.c_int64(len(o)))
+        assert 0 <= n <= len(o)
+        outs.append(o[:n]); infos.append(c[:n]); oo.append(oo[-1] + n)
+    return np.concatenate(outs), np.concatenate(infos), np.array(oo, dtype=np.int64)
+
+
+def paf_ours(gen, prm, out, info, oo):
+    import wfmash_b200 as wb
+    P = params(gen, prm)
+    names = [f"s{i}" for i in range(len(REF_LEN))]
+    return b"".join(wb.mapping_paf_format(P, out[oo[q]: oo[q + 1]], info[oo[q]: oo[q + 1]], f"q{q}", gen.get("qlen", QLEN), names, REF_LEN)
+                    for q in range(len(oo) - 1))
+
+
+def paf_reference(ref, gen, prm, out, info, oo):
+    ref.ref_report_mappings.restype = ctypes.c_int64
+    P = params(gen, prm)
+    txt = []
+    for q in range(len(oo) - 1):
+        a, c = np.ascontiguousarray(out[oo[q]: oo[q + 1]]), np.ascontiguousarray(info[oo[q]: oo[q + 1]])
+        buf = ctypes.create_string_buffer(300 * len(a) + 64)
+        n = ref.ref_report_mappings(ctypes.byref(P), ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(c.ctypes.data), ctypes.c_int64(len(a)), f"q{q}".encode(),
+                                    ctypes.c_int64(gen.get("qlen", QLEN)), ctypes.c_void_p(REF_LEN.ctypes.data), buf, ctypes.c_int64(len(buf)))
+        assert n <= len(buf)
+        txt.append(buf.raw[:n])
+    return b"".join(txt)
+
+
+def test_filters_reproduce_reference_fixture():
+    with gzip.open(os.path.join(util.GOLD, "filter_reference.json.gz"), "rt") as f:
+        gold = json.load(f)
+    assert len(gold["cases"]) == len(CASES)
+    for (seed, gen, prm, groups), g in zip(CASES, gold["cases"]):
+        (out, info, oo), m, off = ours(seed, gen, prm, groups)
+        assert len(m) == g["n_in"] and len(out) == g["n_out"], (seed, len(out), g["n_out"])
+        assert oo.tolist() == g["out_offset"], seed
+        assert digest(out) == g["sha_out"], seed
+        assert digest(info) == g["sha_chain_info"], seed
+        txt = paf_ours(gen, prm, out, info, oo)
+        assert hashlib.sha256(txt).hexdigest() == g["sha_paf"], seed
+        assert txt.decode().splitlines()[:3] == g["paf_head"], seed
+
+
+@pytest.mark.ref
+def test_filters_match_compiled_reference_live():
+    ref = util.load_ref("libfilterref.so")
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    kept = dropped = 0
+    for seed, gen, prm, groups in [(s + 100, g, p, grp) for s, g, p, grp in CASES]:
+        (out, info, oo), m, off = ours(seed, gen, prm, groups)
+        r_out, r_info, r_oo = reference(ref, gen, prm, groups, m, off)
+        assert (oo == r_oo).all(), seed
+        assert out.tobytes() == r_out.tobytes() and info.tobytes() == r_info.tobytes(), seed
+        assert paf_ours(gen, prm, out, info, oo) == paf_reference(ref, gen, prm, out, info, oo), seed
+        kept += len(out); dropped += len(m) - len(out)
+    assert kept > 300 and dropped > 300
+
+
+@pytest.mark.ref
+def test_filter_by_group_both_axes_match_compiled_reference_live():
+    import wfmash_b200 as wb
+    ref = util.load_ref("libfilterref.so")
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    ref.ref_filter_by_group.restype = ctypes.c_int64
+    groups = np.array([0, 1, 1, 2], dtype=np.int32)
+    n_checked = 0
+    for seed in range(40, 46):
+        m, off = chainutil.batch(seed, nq=3)
+        _, merged, _, mo = wb.chain_mappings_batch(m, off, 1000)
+        for axis in (0, 1):
+            for n_map, prm in [(0, dict()), (1, dict(overlap_threshold=0.3)), (-2, dict(skip_prefix=1)), (2, dict(drop_rand=1))]:
+                P = wb.FilterParams(window_length=1000, **prm)
+                for a in (np.ascontiguousarray(m[off[0]: off[1]]), np.ascontiguousarray(merged[mo[1]: mo[2]])):
+                    mine_in, mine = wb.filter_by_group(P, a, n_map, bool(axis), REF_LEN, ref_group=groups)
+                    r_in = a.copy()
+                    r_out = np.zeros(len(a) + 1, dtype=wb.MAPPING_DTYPE)
+                    n = ref.ref_filter_by_group(ctypes.byref(P), ctypes.c_void_p(r_in.ctypes.data), ctypes.c_int64(len(a)), n_map, axis,
+                                                ctypes.c_void_p(groups.ctypes.data), ctypes.c_void_p(REF_LEN.ctypes.data), ctypes.c_void_p(r_out.ctypes.data),
+                                                ctypes.c_int64(len(r_out)))
+                    assert n == len(mine) and mine.tobytes() == r_out[:n].tobytes(), (seed, axis, n_map)
+                    assert mine_in.tobytes() == r_in.tobytes()
+                    n_checked += 1
+    assert n_checked == 96
+
+
+@pytest.mark.ref
+def test_one_to_one_final_pass_equals_reference_pieces_composed():
+    """computeMap.hpp:788-850 lives inside Map (not compilable here): the reference-axis sweep it calls is the compiled
+    reference, the regrouping loops around it are restated in this test."""
+    import wfmash_b200 as wb
+    ref = util.load_ref("libfilterref.so")
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    ref.ref_filter_by_group.restype = ctypes.c_int64
+    P = wb.FilterParams(window_length=1000, filter_mode=wb.FILTER_ONETOONE, num_mappings_for_segment=1)
+    m, off = chainutil.batch(77, nq=5)
+    out, info, oo = wb.filter_mappings_batch(P, m, off, np.full(5, QLEN, dtype=np.int64), REF_LEN)
+    out = np.concatenate([out, out[oo[1]: oo[1] + 2]])  # two queries sharing (refSeqId, refStartPos, queryStartPos) triples
+    oo = np.append(oo, oo[-1] + 2)
+    got, owner = wb.one_to_one_filter(P, out, oo, REF_LEN)
+    exp = []
+    for t in sorted(set(out["refSeqId"].tolist())):
+        a = np.ascontiguousarray(out[out["refSeqId"] == t])
+        r = np.zeros(len(a) + 1, dtype=wb.MAPPING_DTYPE)
+        n = ref.ref_filter_by_group(ctypes.byref(P), ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(len(a)), 0, 1, None, ctypes.c_void_p(REF_LEN.ctypes.data),
+                                    ctypes.c_void_p(r.ctypes.data), ctypes.c_int64(len(r)))
+        for k in r[:n]:
+            for q in range(len(oo) - 1):
+                sub = out[oo[q]: oo[q + 1]]
+                if ((sub["refSeqId"] == k["refSeqId"]) & (sub["refStartPos"] == k["refStartPos"]) & (sub["queryStartPos"] == k["queryStartPos"])).any():
+                    exp.append((q, k.tobytes()))
+    assert sorted(exp) == sorted((int(q), k.tobytes()) for q, k in zip(owner, got))
+    assert 0 < len(got) < len(out) and (np.diff(owner) >= 0).all()
+
+
+def test_mapping_paf_round_trip_and_parse_rules():
+    """parseMashmapRow + createSeqRecord (computeAlignments.hpp:195-303,611-624) on lines written by wfb_mapping_paf_format."""
+    import wfmash_b200 as wb
+    P = wb.FilterParams(window_length=1000)
+    m = np.zeros(3, dtype=wb.MAPPING_DTYPE)
+    m[0] = (1, 500, 0, 30_000, 30, 420, 9512, 0, 97)
+    m[1] = (0, 200_000, 30_000, 41_000, 41, 600, 10000, 1, 88)
+    m[2] = (1, 70_000, 80_000, 19_000, 19, 250, 8000, 0, 100)
+    info = np.array([(0, 1, 30), (1, 1, 41), (1, 41, 41)], dtype=wb.CHAIN_INFO_DTYPE)
+    names, rlen = ["tgt#1#a", "tgt#1#b"], np.array([250_000, 90_000], dtype=np.int64)
+    txt = wb.mapping_paf_format(P, m, info, "qry#1#x", 100_000, names, rlen)
+    lines = txt.split(b"\n")[:-1]
+    assert lines[0] == b"qry#1#x\t100000\t0\t30000\t+\ttgt#1#b\t90000\t500\t30500\t420\t30000\t13\tid:f:0.9512\tkc:f:0.97\tch:Z:0.1.30"
+    assert lines[1] == b"qry#1#x\t100000\t30000\t71000\t-\ttgt#1#a\t250000\t200000\t241000\t600\t41000\t255\tid:f:1\tkc:f:0.88\tch:Z:1.1.41"
+    r0, qn, tn = wb.mapping_paf_parse(lines[0], 1000, 1000, 128_000)
+    assert (qn, tn) == ("qry#1#x", "tgt#1#b")
+    # first piece, not the last: target padded and clamped at 0, the query padding is computed but only stored for the last piece
+    assert (r0.r_start, r0.r_end, r0.q_start, r0.q_end, r0.strand) == (0, 31_500, 0, 30_000, 1)
+    assert (r0.chain_id, r0.chain_pos, r0.chain_length) == (0, 1, 30) and abs(r0.mashmap_estimated_identity - 0.9512) < 1e-7
+    assert (r0.ref_fetch_start, r0.ref_fetch_len) == (0, 90_000)  # 128 kb of patch room on both sides, clamped to the sequence
+    r1, _, _ = wb.mapping_paf_parse(lines[1], 1000, 1000, 5_000)
+    assert (r1.r_start, r1.r_end, r1.strand) == (199_000, 242_000, -1) and (r1.ref_fetch_start, r1.ref_fetch_len) == (194_000, 53_000)
+    r2, _, _ = wb.mapping_paf_parse(lines[2], 5000, 700, 1000)
+    assert (r2.q_start, r2.q_end) == (80_000, 99_700)   # last piece of its chain (41 of 41): the end is padded; the start only for piece 1
+    assert (r2.r_start, r2.r_end, r2.ref_fetch_start, r2.ref_fetch_len) == (65_000, 90_000, 64_000, 26_000)
+    # 13 tokens suffice (no kc / ch tags): defaults chain -1 / 1 / 1; a non-numeric identity falls back to 0.70
+    r3, _, _ = wb.mapping_paf_parse(b"q 1000 0 900 + t 5000 100 1000 9 900 20 id:f:x", 0, 50, 10)
+    assert (r3.chain_id, r3.chain_length, r3.chain_pos) == (-1, 1, 1) and abs(r3.mashmap_estimated_identity - 0.70) < 1e-7
+    assert (r3.q_start, r3.q_end) == (0, 950)
+    for bad in (b"q 1000 0 900 + t 5000 100 1000 9 900 20", b"q 1000 0 900 + t 5000 5000 5100 9 900 20 id:f:0.9", b"q 1000 zero 900 + t 5000 1 2 9 900 20 id:f:0.9"):
+        with pytest.raises(wb.WfbError):
+            wb.mapping_paf_parse(bad, 0)
+    # -M output carries jc:f:0 instead of the chain tag; legacy output is blank separated with inclusive ends
+    assert wb.mapping_paf_format(wb.FilterParams(merge_mappings=0), m[:1], None, "q", 100_000, names, rlen).endswith(b"\tkc:f:0.97\tjc:f:0\n")
+    assert wb.mapping_paf_format(wb.FilterParams(legacy_output=1), m[:1], None, "q", 100_000, names, rlen) == b"q 100000 0 29999 + tgt#1#b 90000 500 30499 951200\n"

@@ -541,3 +541,127 @@ def chain_mappings_batch(mappings, query_offset, window_length: int, chain_gap: 
     if rc != 0:
         raise _err(rc)
     return m, merged[: mo[-1]], info[: mo[-1]], mo
+
+
+# ---- SURVEY 8 f2 (second part) + b3: filters, mapping PAF writer / reader ----------------------------------------------
+FILTER_MAP, FILTER_ONETOONE, FILTER_NONE = 1, 2, 3
+
+
+class FilterParams(ctypes.Structure):
+    """wfb_filter_params_t; the defaults are the reference's CLI defaults (src/interface/parse_args.hpp)."""
+    _fields_ = [("split", ctypes.c_int32), ("merge_mappings", ctypes.c_int32), ("filter_mode", ctypes.c_int32), ("skip_prefix", ctypes.c_int32),
+                ("filter_length_mismatches", ctypes.c_int32), ("drop_rand", ctypes.c_int32), ("threads", ctypes.c_int32), ("legacy_output", ctypes.c_int32),
+                ("chain_gap", ctypes.c_int64), ("window_length", ctypes.c_int64), ("block_length", ctypes.c_int64),
+                ("max_mapping_length", ctypes.c_uint64), ("sparsity_hash_threshold", ctypes.c_uint64),
+                ("num_mappings_for_segment", ctypes.c_uint32), ("num_mappings_for_scaffold", ctypes.c_uint32),
+                ("overlap_threshold", ctypes.c_double), ("scaffold_overlap_threshold", ctypes.c_double),
+                ("scaffold_gap", ctypes.c_int64), ("scaffold_max_deviation", ctypes.c_int64), ("scaffold_min_length", ctypes.c_int64),
+                ("percentage_identity", ctypes.c_float), ("reserved_", ctypes.c_int32)]
+
+    def __init__(self, window_length=1000, **kw):
+        d = dict(split=1, merge_mappings=1, filter_mode=FILTER_MAP, skip_prefix=0, filter_length_mismatches=1, drop_rand=0, threads=2, legacy_output=0,
+                 chain_gap=2000, window_length=window_length, block_length=0, max_mapping_length=50000, sparsity_hash_threshold=2**64 - 1,
+                 num_mappings_for_segment=2**32 - 1, num_mappings_for_scaffold=1, overlap_threshold=0.95, scaffold_overlap_threshold=0.5,
+                 scaffold_gap=100000, scaffold_max_deviation=100000, scaffold_min_length=10000, percentage_identity=0.7, reserved_=0)
+        unknown = set(kw) - set(d)
+        if unknown:
+            raise TypeError(f"unknown filter parameter(s): {sorted(unknown)}")
+        d.update(kw)
+        super().__init__(**d)
+
+
+class MappingRow(ctypes.Structure):
+    """wfb_mapping_row_t: align::MappingBoundaryRow + the target fetch range of createSeqRecord."""
+    _fields_ = [(n, ctypes.c_int64) for n in ("q_start", "q_end", "r_start", "r_end", "ref_fetch_start", "ref_fetch_len", "query_len", "ref_len",
+                                               "chain_id", "chain_length", "chain_pos")] + \
+               [("strand", ctypes.c_int32), ("mashmap_estimated_identity", ctypes.c_float), ("q_name_off", ctypes.c_int32), ("q_name_len", ctypes.c_int32),
+                ("r_name_off", ctypes.c_int32), ("r_name_len", ctypes.c_int32)]
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def filter_mappings_batch(params: FilterParams, mappings, query_offset, query_len, ref_seq_len, ref_group=None, host_threads: int = 0):
+    """Map::filterSubsetMappings (computeMap.hpp:1076-1165) for a batch of queries -> (mappings, chain info, out_offset)."""
+    m = np.ascontiguousarray(mappings, dtype=MAPPING_DTYPE)
+    qo, ql, rl = _i64(query_offset), _i64(query_len), _i64(ref_seq_len)
+    rg = np.ascontiguousarray(ref_group, dtype=np.int32) if ref_group is not None else None
+    nq = len(qo) - 1
+    cap = len(m) + 16
+    out = np.zeros(cap, dtype=MAPPING_DTYPE)
+    info = np.zeros(cap, dtype=CHAIN_INFO_DTYPE)
+    oo = np.zeros(nq + 1, dtype=np.int64)
+    rc = lib().wfb_filter_mappings_batch(ctypes.byref(params), _ptr(m), _ptr(qo), _ptr(ql), nq, _ptr(rg), _ptr(rl), _ptr(out), _ptr(info),
+                                         ctypes.c_int64(cap), _ptr(oo), host_threads)
+    if rc != 0:
+        raise _err(rc)
+    return out[: oo[-1]], info[: oo[-1]], oo
+
+
+def filter_by_group(params: FilterParams, mappings, n_mappings: int, filter_ref: bool, ref_seq_len, ref_group=None):
+    """MappingFilterUtils::filterByGroup (mappingFilter.hpp:220-293) -> (input as the reference reorders it, survivors)."""
+    m = np.array(mappings, dtype=MAPPING_DTYPE, copy=True)
+    rl = _i64(ref_seq_len)
+    rg = np.ascontiguousarray(ref_group, dtype=np.int32) if ref_group is not None else None
+    out = np.zeros(len(m) + 1, dtype=MAPPING_DTYPE)
+    L = lib()
+    L.wfb_filter_by_group.restype = ctypes.c_int64
+    n = L.wfb_filter_by_group(ctypes.byref(params), _ptr(m), ctypes.c_int64(len(m)), ctypes.c_int32(n_mappings), int(filter_ref), _ptr(rg), _ptr(rl),
+                              _ptr(out), ctypes.c_int64(len(out)))
+    if n < 0:
+        raise _err(n)
+    return m, out[:n]
+
+
+def one_to_one_filter(params: FilterParams, mappings, query_offset, ref_seq_len, ref_group=None):
+    """Final reference-axis pass of the one-to-one mode (computeMap.hpp:788-850) -> (mappings grouped by query, owner query of each)."""
+    m = np.ascontiguousarray(mappings, dtype=MAPPING_DTYPE)
+    qo, rl = _i64(query_offset), _i64(ref_seq_len)
+    rg = np.ascontiguousarray(ref_group, dtype=np.int32) if ref_group is not None else None
+    cap = 4 * len(m) + 16
+    out = np.zeros(cap, dtype=MAPPING_DTYPE)
+    owner = np.zeros(cap, dtype=np.int32)
+    L = lib()
+    L.wfb_one_to_one_filter.restype = ctypes.c_int64
+    n = L.wfb_one_to_one_filter(ctypes.byref(params), _ptr(m), _ptr(qo), len(qo) - 1, _ptr(rg), _ptr(rl), _ptr(out), _ptr(owner), ctypes.c_int64(cap))
+    if n < 0:
+        raise _err(n)
+    return out[:n], owner[:n]
+
+
+def mapping_paf_format(params: FilterParams, mappings, chain, query_name: str, query_len: int, ref_names, ref_seq_len) -> bytes:
+    """OutputHandler::reportReadMappings (mappingOutput.hpp:74-139): the `wfmash -m` lines of one query."""
+    m = np.ascontiguousarray(mappings, dtype=MAPPING_DTYPE)
+    c = np.ascontiguousarray(chain, dtype=CHAIN_INFO_DTYPE) if chain is not None else None
+    rl = _i64(ref_seq_len)
+    names = (ctypes.c_char_p * len(ref_names))(*[s.encode() for s in ref_names])
+    L = lib()
+    L.wfb_mapping_paf_format.restype = ctypes.c_int64
+    cap = 256 * len(m) + 256
+    while True:
+        buf = ctypes.create_string_buffer(cap)
+        need = ctypes.c_int64(0)
+        n = L.wfb_mapping_paf_format(ctypes.byref(params), _ptr(m), _ptr(c), ctypes.c_int64(len(m)), query_name.encode(), ctypes.c_int64(query_len), names,
+                                     _ptr(rl), buf, ctypes.c_int64(cap), ctypes.byref(need))
+        if n == -5 and need.value > cap:
+            cap = need.value
+            continue
+        if n < 0:
+            raise _err(n)
+        return buf.raw[:n]
+
+
+def mapping_paf_parse(line: bytes, target_padding: int, query_padding: int = 0, wflign_max_len_minor: int = 128000):
+    """Aligner::parseMashmapRow + the fetch range of createSeqRecord (computeAlignments.hpp:195-303,611-624).
+    Returns (MappingRow, query name, target name); raises WfbError where the reference throws."""
+    row = MappingRow()
+    rc = lib().wfb_mapping_paf_parse(line, ctypes.c_int64(len(line)), ctypes.c_uint64(target_padding), ctypes.c_uint64(query_padding),
+                                     ctypes.c_uint64(wflign_max_len_minor), ctypes.byref(row))
+    if rc != 0:
+        raise _err(rc)
+    return row, line[row.q_name_off: row.q_name_off + row.q_name_len].decode(), line[row.r_name_off: row.r_name_off + row.r_name_len].decode()

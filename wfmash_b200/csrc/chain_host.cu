@@ -57,8 +57,11 @@ void ch_reorder(std::vector<T>& v, const std::vector<uint32_t>& p) {
   v.swap(out);
 }
 
-void chain_one_query(const wfb_chain_params_t& P, wfb_mapping_t* io, int64_t n, std::vector<wfb_mapping_t>& merged,
-                     std::vector<wfb_chain_info_t>& info) {
+}  // namespace
+
+/* also used by filter_host.cu (the scaffold filter chains with a second gap) */
+void wfb_chain_one_query_(const wfb_chain_params_t& P, wfb_mapping_t* io, int64_t n, std::vector<wfb_mapping_t>& merged,
+                          std::vector<wfb_chain_info_t>& info) {
   merged.clear();
   info.clear();
   if (!P.split || n < 2) { /* :390-399: every mapping is its own chain */
@@ -170,8 +173,6 @@ void chain_one_query(const wfb_chain_params_t& P, wfb_mapping_t* io, int64_t n, 
   std::copy(m.begin(), m.end(), io); /* the reference leaves readMappings in this order */
 }
 
-}  // namespace
-
 extern "C" int wfb_chain_mappings_batch(const wfb_chain_params_t* params, wfb_mapping_t* mappings, const int64_t* query_offset, int32_t n_queries,
                                         wfb_mapping_t* merged, wfb_chain_info_t* chain_info, int64_t merged_cap, int64_t* merged_offset,
                                         int32_t host_threads) {
@@ -187,7 +188,7 @@ extern "C" int wfb_chain_mappings_batch(const wfb_chain_params_t* params, wfb_ma
   const int nt = std::max(1, std::min<int>(host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency(), n_queries));
   auto work = [&](int t) {
     for (int32_t q = t; q < n_queries; q += nt)
-      chain_one_query(*params, mappings + query_offset[q], query_offset[q + 1] - query_offset[q], out[(size_t)q], inf[(size_t)q]);
+      wfb_chain_one_query_(*params, mappings + query_offset[q], query_offset[q + 1] - query_offset[q], out[(size_t)q], inf[(size_t)q]);
   };
   if (nt == 1) work(0);
   else {

@@ -509,6 +509,30 @@ typedef struct { /* align::MappingBoundaryRow (src/align/include/align_types.hpp
 int wfb_mapping_paf_parse(const char* line, int64_t line_len, uint64_t target_padding, uint64_t query_padding, uint64_t wflign_max_len_minor,
                           wfb_mapping_row_t* row);
 
+/* ------------------------------------------------------------------------------------------------
+ * Run-level constants of the mapping path (host; the reference derives them once per run with GNU GSL, which is an
+ * un-vendored third-party dependency: restated from the distributions' definitions, see wfmash_b200/csrc/stats_host.cu).
+ * ---------------------------------------------------------------------------------------------- */
+/* param.sketchSize when -s is not given (src/interface/parse_args.hpp:642-644) */
+int32_t wfb_sketch_size(float percentage_identity, int64_t window_length, int32_t kmer_size);
+/* skch::Stat::estimateMinimumHitsRelaxed (src/map/include/map_stats.hpp:159-180): Map::cached_minimum_hits
+ * (computeMap.hpp:160) = max(param.minimum_hits, this) -> wfb_l1_params_t::minimum_hits. confidence_interval = 0.95
+ * (skch::fixed::confidence_interval). */
+int32_t wfb_estimate_minimum_hits_relaxed(int32_t sketch_size, int32_t kmer_size, float percentage_identity, float confidence_interval);
+/* Map::sketchCutoffs (computeMap.hpp:150,234-293) -> wfb_l1_params_t::sketch_cutoffs. out[min(sketch_size,1000) + 1];
+ * all ones unless stage1_top_ani_filter (true on the CLI path). ani_diff = param.ANIDiff (0), ani_diff_conf =
+ * param.ANIDiffConf (0.999). */
+int wfb_sketch_cutoffs(int32_t sketch_size, int32_t kmer_size, float ani_diff, float ani_diff_conf, int32_t stage1_top_ani_filter, int32_t* out,
+                       int32_t out_len);
+/* wfb_l2_min_shared for keep_low_pct_id == true (the CLI default, parse_args.hpp:173): the identity test of
+ * Map::doL2Mapping (computeMap.hpp:1016-1024) passes when the UPPER bound of the identity's confidence interval
+ * (Stat::md_lower_bound, map_stats.hpp:93-126) reaches percentage_identity. out[sketch_size + 1]. */
+int wfb_l2_min_shared_relaxed(float percentage_identity, int32_t kmer_size, int32_t sketch_size, float confidence_interval, int32_t* out);
+/* the three GSL functions as restated here (exported for the cross-check against scipy.stats) */
+double wfb_stat_binomial_Q(uint32_t k, double p, uint32_t n);
+double wfb_stat_hypergeometric_pdf(uint32_t k, uint32_t n1, uint32_t n2, uint32_t t);
+double wfb_stat_hypergeometric_P(uint32_t k, uint32_t n1, uint32_t n2, uint32_t t);
+
 #ifdef __cplusplus
 }
 #endif

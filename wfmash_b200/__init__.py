@@ -665,3 +665,36 @@ def mapping_paf_parse(line: bytes, target_padding: int, query_padding: int = 0, 
     if rc != 0:
         raise _err(rc)
     return row, line[row.q_name_off: row.q_name_off + row.q_name_len].decode(), line[row.r_name_off: row.r_name_off + row.r_name_len].decode()
+
+
+# ---- run-level constants of the mapping path (host) ---------------------------------------------------------------------
+def sketch_size(percentage_identity: float, window_length: int, kmer_size: int) -> int:
+    """param.sketchSize when -s is not given (parse_args.hpp:642-644)."""
+    return int(lib().wfb_sketch_size(ctypes.c_float(percentage_identity), ctypes.c_int64(window_length), kmer_size))
+
+
+def estimate_minimum_hits_relaxed(sketch_size: int, kmer_size: int, percentage_identity: float, confidence_interval: float = 0.95) -> int:
+    """skch::Stat::estimateMinimumHitsRelaxed (map_stats.hpp:159-180)."""
+    r = lib().wfb_estimate_minimum_hits_relaxed(sketch_size, kmer_size, ctypes.c_float(percentage_identity), ctypes.c_float(confidence_interval))
+    if r < 0:
+        raise _err(r)
+    return int(r)
+
+
+def sketch_cutoffs(sketch_size: int, kmer_size: int, ani_diff: float = 0.0, ani_diff_conf: float = 0.999, stage1_top_ani_filter: bool = True):
+    """Map::sketchCutoffs (computeMap.hpp:150,234-293)."""
+    out = np.zeros(min(sketch_size, 1000) + 1, dtype=np.int32)
+    rc = lib().wfb_sketch_cutoffs(sketch_size, kmer_size, ctypes.c_float(ani_diff), ctypes.c_float(ani_diff_conf), int(stage1_top_ani_filter),
+                                  _ptr(out), len(out))
+    if rc != 0:
+        raise _err(rc)
+    return out
+
+
+def l2_min_shared_relaxed(percentage_identity: float, kmer_size: int, sketch_size: int, confidence_interval: float = 0.95):
+    """Identity test of Map::doL2Mapping with keep_low_pct_id (computeMap.hpp:1016-1024), as a table over Q.sketchSize."""
+    out = np.zeros(sketch_size + 1, dtype=np.int32)
+    rc = lib().wfb_l2_min_shared_relaxed(ctypes.c_float(percentage_identity), kmer_size, sketch_size, ctypes.c_float(confidence_interval), _ptr(out))
+    if rc != 0:
+        raise _err(rc)
+    return out

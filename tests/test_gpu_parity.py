@@ -432,3 +432,30 @@ def test_do_biwfa_alignment_paf_lines_match_reference(wb):
             for r, got in zip(recs[:20], lines[:20]):
                 assert got == util.ref_paf(R, r, **kw)
     al.close()
+
+
+def test_pipeline_map_align_matches_reference_pieces(wb, oracle):
+    # SURVEY 8 f2 + b3 + both hot paths chained: sequences -> index -> L1/L2 kernels -> host chain merge + filters -> mapping
+    # PAF -> padded records -> biWFA kernels + patches -> alignment PAF, against the run composed from the reference-side
+    # pieces (tests/pipeutil.py): committed fixture always, live when oracle/_ref travelled with the snapshot.
+    import gzip, json, os
+    from tests import pipeutil
+    from wfmash_b200 import pipeline
+    with gzip.open(os.path.join(util.GOLD, "pipeline_reference.json.gz"), "rt") as f:
+        gold = json.load(f)
+    fref, wref = util.load_ref("libfilterref.so"), util.load_wflign_ref()
+    assert [c["name"] for c in gold["cases"]] == [c[0] for c in pipeutil.PIPELINE_CASES]
+    for (name, gen, prm), g in zip(pipeutil.PIPELINE_CASES, gold["cases"]):
+        seqs = pipeutil.case(**gen)
+        P = pipeutil.params(prm)
+        paf, st = pipeline.wfmash(seqs, seqs, P)
+        assert sorted(st["mapping_paf"].decode().splitlines()) == sorted(g["mapping_paf"].splitlines()), name
+        # the alignment lines follow the order of the mapping PAF (grouped by query, sorted by query start with the
+        # reference's unstable sort): compare as multisets of (first 12 columns, digest of the whole line)
+        got = sorted((d["head"], d["sha"]) for d in map(pipeutil.line_digest, [ln + b"\n" for ln in paf.split(b"\n") if ln]))
+        want = sorted((d["head"], d["sha"]) for d in g["lines"] if d["head"])
+        assert got == want, name
+        assert st["written"] == len(want) and st["aligned_bp"] > 0
+        if fref is not None and wref is not None and name == "defaults_p90":
+            mp, lines = pipeutil.expected(seqs, P, oracle, fref, wref)
+            assert st["mapping_paf"] == mp and paf == b"".join(lines)

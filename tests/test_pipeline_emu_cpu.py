@@ -1,0 +1,49 @@
+"""wfmash_b200.pipeline.align (mapping PAF -> padded, strand-corrected records -> batched do_biwfa_alignment -> alignment
+PAF) WITHOUT a GPU: the kernel bodies run under the single-thread host emulation of tests/emu (TEST INFRASTRUCTURE,
+-DWFB_EMU, in a subprocess; never the product library). The mapping PAF comes from the reference-side composition of
+tests/pipeutil.py (the mapping kernels are not part of the emulation), and the alignment PAF is compared with the
+reference's UNMODIFIED do_biwfa_alignment on the same records. The whole pipeline, mapping kernels included, is compared
+the same way on the real device in tests/test_gpu_parity.py::test_pipeline_map_align_matches_reference_pieces."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from tests import util
+
+SCRIPT = r"""
+import json, sys
+sys.path.insert(0, %(root)r)
+from tests import pipeutil, util
+from wfmash_b200 import pipeline
+seqs = pipeutil.case(length=14_000)
+P = pipeline.Params()
+fref, wref = util.load_ref("libfilterref.so"), util.load_wflign_ref()
+out = {"have_ref": fref is not None and wref is not None}
+if out["have_ref"]:
+    mp, lines = pipeutil.expected(seqs, P, util.load_oracle(), fref, wref)
+    paf, st = pipeline.align(mp, seqs, seqs, P)
+    out.update(ref_map=mp.decode(), ref_paf=b"".join(lines).decode(), ours_paf=paf.decode(), records=st["records"], written=st["written"],
+               aligned_bp=st["aligned_bp"])
+print(json.dumps(out))
+"""
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_align_phase_under_emulation_matches_reference_do_biwfa_alignment():
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": util.ROOT}], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    if not res["have_ref"]:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    assert res["records"] >= 8 and res["written"] >= 8
+    assert res["ours_paf"] == res["ref_paf"]
+    assert {ln.split("\t")[4] for ln in res["ours_paf"].splitlines()} == {"+", "-"}
+    spans = [int(f[3]) - int(f[2]) for f in (ln.split("\t") for ln in res["ref_map"].splitlines())]
+    assert res["aligned_bp"] >= sum(spans)  # + the query padding of the chain ends

@@ -1,0 +1,118 @@
+"""SURVEY 8 row a4 pinned by the real code: the oracle's index build (orc_index_build, which the GPU index is compared
+with in tests/test_gpu_parity.py::test_index_build_matches_oracle) against the reference's UNMODIFIED skch::Sketch
+(src/map/include/winSketch.hpp:175-457: thread-pool sketching, hash frequencies, frequency cut-off with its safety
+re-threshold, minmerPosLookupIndex / minmerIndex) and skch::SequenceIdManager (sequenceIds.hpp) compiled in place behind
+oracle/ref_sketch_driver.cpp (htslib replaced by oracle/shims/htslib/faidx.h) — live when oracle/_ref is present, and by
+the committed fixture tests/golden/index_reference.json.gz generated from it."""
+import ctypes
+import gzip
+import hashlib
+import json
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import maputil, util
+
+PT = np.dtype([("hash", "<u8"), ("pos", "<i8"), ("seqId", "<i4"), ("side", "<i4")])
+# (seed, k, w, s, max_kmer_freq, threads)
+CASES = [(32, 15, 1000, 29, 0.0002, 3), (33, 15, 1000, 59, 0.0002, 1), (34, 19, 500, 17, 0.01, 2), (35, 15, 256, 11, 0.0002, 4), (36, 15, 1000, 39, 5.0, 2)]
+
+
+def names_of(groups):
+    return [f"g{g}#1#s{i}" for i, g in enumerate(groups)]
+
+
+def reference_index(R, seqs, names, k, w, s, F, threads):
+    R.ref_sketch_build.restype = ctypes.c_void_p
+    n = len(seqs)
+    with tempfile.TemporaryDirectory() as d:
+        h = ctypes.c_void_p(R.ref_sketch_build(os.path.join(d, "t.fa").encode(), (ctypes.c_char_p * n)(*[x.encode() for x in names]), (ctypes.c_char_p * n)(*seqs),
+                                               (ctypes.c_int64 * n)(*[len(x) for x in seqs]), n, k, ctypes.c_int64(w), s, threads, ctypes.c_double(F), b"#"))
+        assert h.value
+        nm, nh, npt = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        R.ref_sketch_sizes(h, ctypes.byref(nm), ctypes.byref(nh), ctypes.byref(npt))
+        mi = np.zeros(nm.value, dtype=maputil.MDT); hs = np.zeros(nh.value, dtype=np.uint64)
+        st = np.zeros(nh.value + 1, dtype=np.int64); pts = np.zeros(npt.value, dtype=PT)
+        R.ref_sketch_export(h, maputil.vp(mi), maputil.vp(hs), maputil.vp(st), maputil.vp(pts))
+        groups = [R.ref_sketch_group(h, i) for i in range(n)]
+        R.ref_sketch_free(h)
+    return mi, hs, st, pts, groups
+
+
+def oracle_flat(oracle, seqs, ids, k, w, s, F, threads):
+    """The oracle index in the driver's flat layout: minmers, ascending hashes, CSR starts, points (hash, pos, seqId, side)."""
+    kept, opts, uh, us, uc, _ = maputil.oracle_index(oracle, [maputil.clean(x) for x in seqs], ids, k, w, s, F, threads)
+    order = np.argsort(uh, kind="stable")
+    pts = np.zeros(len(opts), dtype=PT)
+    st = np.zeros(len(uh) + 1, dtype=np.int64)
+    o = 0
+    for j, i in enumerate(order):
+        seg = opts[int(us[i]): int(us[i]) + int(uc[i])]
+        pts["hash"][o: o + len(seg)] = seg["hash"]; pts["pos"][o: o + len(seg)] = seg["pos"]
+        pts["seqId"][o: o + len(seg)] = seg["seqId"]; pts["side"][o: o + len(seg)] = seg["side"]
+        st[j] = o
+        o += len(seg)
+    st[len(uh)] = o
+    return kept, uh[order], st, pts[:o]
+
+
+def canonical(mi, hs, st, pts):
+    """The reference's thread pool hands the per-sequence minmer lists back in COMPLETION order (winSketch.hpp:222-240), so
+    with more than one thread the order of whole sequences inside minmerIndex / inside one hash's point list is not
+    reproducible run to run. Inside a sequence the minmers are sorted by (wpos, wpos_end) with an UNSTABLE std::sort
+    (commonFunc.hpp:696), so the order of equal (wpos, wpos_end) is unspecified as well. Compare with sequences put back
+    in id order and those ties ordered by hash; nothing else is reordered (hashes differ inside a tie, so the per-hash
+    point lists do not depend on it)."""
+    mi = mi[np.lexsort((mi["strand"], mi["hash"], mi["wpos_end"], mi["wpos"], mi["seqId"]))]
+    grp = np.repeat(np.arange(len(hs)), np.diff(st))
+    pts = pts[np.lexsort((pts["seqId"], grp))]  # lexsort is stable: hash group, then sequence, original order inside
+    return mi, hs, st, pts
+
+
+def digest(mi, hs, st, pts):
+    mi, hs, st, pts = canonical(mi, hs, st, pts)
+    h = hashlib.sha256()
+    for f in ("hash", "wpos", "wpos_end", "seqId", "strand"):
+        h.update(np.ascontiguousarray(mi[f]).tobytes())
+    for a in (hs, st, pts["hash"], pts["pos"], pts["seqId"], pts["side"]):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def case_seqs(seed):
+    seqs, ids, groups = maputil.l2_case(seed=seed) if seed % 2 else maputil.l1_case(seed=seed)
+    return seqs, ids, groups
+
+
+def test_oracle_index_reproduces_reference_sketch_fixture(oracle):
+    with gzip.open(os.path.join(util.GOLD, "index_reference.json.gz"), "rt") as f:
+        gold = json.load(f)
+    assert len(gold["cases"]) == len(CASES)
+    for (seed, k, w, s, F, threads), g in zip(CASES, gold["cases"]):
+        seqs, ids, groups = case_seqs(seed)
+        mi, hs, st, pts = oracle_flat(oracle, seqs, ids, k, w, s, F, threads)
+        assert (len(mi), len(hs), len(pts)) == (g["n_minmers"], g["n_hashes"], g["n_points"]), seed
+        assert digest(mi, hs, st, pts) == g["sha"], seed
+
+
+@pytest.mark.ref
+def test_oracle_index_matches_compiled_reference_sketch_live(oracle):
+    from wfmash_b200 import pipeline
+    R = util.load_ref("libsketchref.so")
+    if R is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    for seed, k, w, s, F, threads in [(c[0] + 50,) + c[1:] for c in CASES]:
+        seqs, ids, groups = case_seqs(seed)
+        names = names_of(groups)
+        r_mi, r_hs, r_st, r_pts, r_groups = reference_index(R, seqs, names, k, w, s, F, threads)
+        r_mi, r_hs, r_st, r_pts = canonical(r_mi, r_hs, r_st, r_pts)
+        mi, hs, st, pts = canonical(*oracle_flat(oracle, seqs, ids, k, w, s, F, threads))
+        assert len(mi) == len(r_mi) > 1000 and all((mi[f] == r_mi[f]).all() for f in ("hash", "wpos", "wpos_end", "seqId", "strand")), seed
+        assert (hs == r_hs).all() and (st == r_st).all(), seed
+        assert all((pts[f] == r_pts[f]).all() for f in ("hash", "pos", "seqId", "side")), seed
+        # the host mirror of SequenceIdManager::buildRefGroups (sequenceIds.hpp:284-330)
+        mirror = pipeline.SequenceIds([(n, b"") for n in names], [], "#")
+        assert mirror.group == r_groups

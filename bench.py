@@ -353,7 +353,7 @@ def map_path_section(dev, cores, with_cpu):
 # padded records -> biWFA kernels + patches -> alignment PAF) on a C4-shaped synthetic pair of haplotypes,
 # host buffers in, PAF text out, wall clock around the whole call.
 # ---------------------------------------------------------------------------------------------------
-def pipeline_section(dev, contigs=4, contig_bp=500_000, ani=0.95, runs=2):
+def pipeline_section(dev, contigs=16, contig_bp=500_000, ani=0.95, runs=2):
     from wfmash_b200 import pipeline, synth
     rng = np.random.default_rng(4242)
     d = 1.0 - ani ** 0.5  # each haplotype derived from the root at d = 1 - sqrt(ANI)

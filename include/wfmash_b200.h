@@ -533,6 +533,38 @@ double wfb_stat_binomial_Q(uint32_t k, double p, uint32_t n);
 double wfb_stat_hypergeometric_pdf(uint32_t k, uint32_t n1, uint32_t n2, uint32_t t);
 double wfb_stat_hypergeometric_P(uint32_t k, uint32_t n1, uint32_t n2, uint32_t t);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8 f3 — ANI auto-identity: skch::Stat::estimate_identity_for_groups (src/map/include/map_stats.hpp:325-822), the
+ * `-p` default of the CLI (src/interface/main.cpp:75-134): decides percentageIdentity, hence sketch size and minimum hits.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double hash_kernel_ms;  /* ani_hash_kernel, all passes               */
+  double sort_kernel_ms;  /* segmented radix sort + gather              */
+  uint64_t bases;         /* sequence bytes streamed                    */
+  uint64_t valid_kmers;   /* canonical, non-palindromic, N-free k-mers  */
+  uint64_t candidates;    /* hashes that passed the group thresholds    */
+  uint64_t tiles;
+  int32_t passes;         /* 1 unless a threshold / capacity was revised */
+  int32_t reserved_;
+} wfb_ani_stats_t;
+
+/* Per-group MinHash sketches on the GPU: group g's sketch = the min(sketch_size, #k-mers) smallest elements of the MULTISET
+ * of canonical k-mer hashes (Murmur3, seed 42, min of both strands, palindromes and k-mers touching a non-ACGT base dropped;
+ * map_stats.hpp:563-613) of the sequences with seq_group[i] == g — what the reference's per-sequence StreamingMinHash heaps
+ * merged per PanSN group hold (streamingMinHash.hpp:89-99, map_stats.hpp:617-637). The reference keeps separate sketches for
+ * the query role and the target role of a group: call once per role (or once, when both files are the same).
+ * sketches[n_groups * sketch_size] ascending per group, sketch_count[n_groups]. kmer_size 21 and sketch_size 4096 on the CLI. */
+int wfb_ani_group_sketches(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_group, int32_t nseq,
+                           int32_t n_groups, int32_t kmer_size, int32_t sketch_size, uint64_t* sketches, int32_t* sketch_count,
+                           wfb_ani_stats_t* stats);
+
+/* The host part (map_stats.hpp:690-800): every query-role sketch against every target-role sketch of another group id,
+ * ANI = 1 - j2md(|intersection| / min(sizes)), the ani_percentile-th value of the sorted ANIs plus ani_adjustment / 100,
+ * clamped to [0, 1]; 0.70 when nothing overlaps. CLI defaults: ani_percentile 50, ani_adjustment -2.0. */
+double wfb_ani_estimate_identity(const uint64_t* q_sketch, const int32_t* q_count, const int32_t* q_group, int32_t nq, const uint64_t* t_sketch,
+                                 const int32_t* t_count, const int32_t* t_group, int32_t nt, int32_t sketch_size, int32_t kmer_size,
+                                 int32_t ani_percentile, float ani_adjustment, int32_t* n_comparisons);
+
 #ifdef __cplusplus
 }
 #endif

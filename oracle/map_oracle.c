@@ -825,3 +825,57 @@ int orc_l2_fragment(const orc_minmer_t* index, int64_t n_index, const orc_minmer
   qsort(out, (size_t)(n < cap ? n : cap), sizeof(orc_l2_mapping_t), cmp_l2map);
   return n;
 }
+
+/* ---------------------------------------------------------------------------------------------------
+ * ANI auto-identity sketch: the per-sequence part of skch::Stat::estimate_identity_for_groups
+ * (src/map/include/map_stats.hpp:563-613) stated literally — upper-case on the fly, `ambig_kmer_count` state machine
+ * (initial scan of the first k bases sets it to k whatever the position of the bad base), canonical Murmur3 hash,
+ * StreamingMinHash::add_unsafe (streamingMinHash.hpp:89-99: a max-heap of `ssize` hashes, duplicates kept, a new hash
+ * replaces the top only when strictly smaller). heap[] is the caller's heap (may already hold hashes: merging a group
+ * is the same add loop, map_stats.hpp:617-637). Returns the new heap size.
+ * ------------------------------------------------------------------------------------------------- */
+static void ani_heap_add(uint64_t* heap, int* n, int ssize, uint64_t h) {
+  if (*n < ssize) { /* push + sift up */
+    int i = (*n)++;
+    heap[i] = h;
+    while (i > 0 && heap[(i - 1) / 2] < heap[i]) { uint64_t t = heap[i]; heap[i] = heap[(i - 1) / 2]; heap[(i - 1) / 2] = t; i = (i - 1) / 2; }
+  } else if (h < heap[0]) { /* replace the maximum + sift down */
+    int i = 0;
+    heap[0] = h;
+    for (;;) {
+      int l = 2 * i + 1, r = l + 1, m = i;
+      if (l < *n && heap[l] > heap[m]) m = l;
+      if (r < *n && heap[r] > heap[m]) m = r;
+      if (m == i) break;
+      uint64_t t = heap[i]; heap[i] = heap[m]; heap[m] = t;
+      i = m;
+    }
+  }
+}
+
+static char ani_upper(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+static int ani_acgt(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+int orc_ani_add_sequence(const char* seq, int64_t len, int k, int ssize, uint64_t* heap, int heap_n) {
+  char fwd[64], rev[64];
+  int ambig = 0;
+  for (int j = 0; j < k && j < len; j++)
+    if (!ani_acgt(ani_upper(seq[j]))) { ambig = k; break; }
+  for (int64_t i = 0; i <= len - k; i++) {
+    if (!ani_acgt(ani_upper(seq[i + k - 1]))) ambig = k;
+    if (ambig == 0) {
+      for (int j = 0; j < k; j++) fwd[j] = ani_upper(seq[i + j]);
+      revcomp(fwd, rev, k);
+      const uint64_t hf = orc_kmer_hash(fwd, k), hb = orc_kmer_hash(rev, k);
+      if (hf != hb) ani_heap_add(heap, &heap_n, ssize, hf < hb ? hf : hb);
+    }
+    if (ambig > 0) ambig--;
+  }
+  return heap_n;
+}
+
+/* StreamingMinHash::add_unsafe for one hash (group merge) */
+int orc_ani_add_hash(uint64_t h, int ssize, uint64_t* heap, int heap_n) {
+  ani_heap_add(heap, &heap_n, ssize, h);
+  return heap_n;
+}

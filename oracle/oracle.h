@@ -153,6 +153,10 @@ int orc_l2_fragment(const orc_minmer_t* index, int64_t n_index, const orc_minmer
                     int window_len_param, const orc_l1_locus_t* loci, int n_loci, int stage1, double hg_numerator, float ani_diff,
                     int min_shared, orc_l2_mapping_t* out, int cap);
 
+/* ANI auto-identity sketch (map_stats.hpp:563-637, streamingMinHash.hpp:89-99): see map_oracle.c */
+int orc_ani_add_sequence(const char* seq, int64_t len, int k, int ssize, uint64_t* heap, int heap_n);
+int orc_ani_add_hash(uint64_t h, int ssize, uint64_t* heap, int heap_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -459,3 +459,58 @@ def test_pipeline_map_align_matches_reference_pieces(wb, oracle):
         if fref is not None and wref is not None and name == "defaults_p90":
             mp, lines = pipeutil.expected(seqs, P, oracle, fref, wref)
             assert st["mapping_paf"] == mp and paf == b"".join(lines)
+
+
+def test_ani_auto_identity_matches_reference(wb, oracle):
+    # group MinHash sketches from ani_hash_kernel (threshold filter + segmented radix sort) against the oracle's
+    # literal StreamingMinHash restatement, and the adopted identity against the doubles the reference's UNMODIFIED
+    # estimate_identity_for_groups returned (committed fixture; live when oracle/_ref travelled with the snapshot).
+    import gzip, hashlib, json, os
+    from tests import aniutil
+    from tests.test_ani_cpu import SETS
+    from wfmash_b200 import pipeline
+    with gzip.open(os.path.join(util.GOLD, "ani_reference.json.gz"), "rt") as f:
+        gold = json.load(f)
+    seqs = aniutil.case()
+    ids = pipeline.SequenceIds(seqs, seqs, "#")
+    gids = sorted(set(ids.group)); dense = {g: i for i, g in enumerate(gids)}
+    grp = [dense[ids.group[ids.id_of[n]]] for n, _ in seqs]
+    passes = []
+    for s in (4096, 64, 16):
+        sk, cnt, st = wb.ani_group_sketches([x for _, x in seqs], grp, len(gids), 21, s)
+        osk, ocnt = aniutil.oracle_group_sketches(oracle, [x for _, x in seqs], grp, len(gids), 21, s)
+        assert (cnt == ocnt).all() and (sk == osk).all(), s
+        passes.append(st.passes)
+        if s == 4096:
+            assert hashlib.sha256(sk.tobytes() + cnt.tobytes()).hexdigest() == gold["sketch_sha"]
+            assert st.candidates < 0.6 * st.valid_kmers and st.hash_kernel_ms > 0
+    assert passes[0] == 1 and max(passes[1:]) >= 2
+    R = util.load_ref("libstatsref.so")
+    for name, (q0, q1), (t0, t1), pct, adj in SETS:
+        P = pipeline.Params(percentage_identity=None, ani_percentile=pct, ani_adjustment=adj)
+        got = pipeline.estimate_identity(seqs[t0:t1], seqs[q0:q1], P)[0]
+        assert float(got).hex() == gold["identity"][name], name
+        if R is not None:
+            assert got == aniutil.reference_identity(R, seqs[t0:t1], seqs[q0:q1], "#", pct, adj)
+    # a genome-sized group: every k-mer of 24 Mbp through the threshold filter; size-independent properties
+    import numpy as np
+    from wfmash_b200 import synth
+    rng = np.random.default_rng(77)
+    big = [synth.random_seq(6_000_000, rng).tobytes() for _ in range(4)]
+    sk, cnt, st = wb.ani_group_sketches(big, [0, 0, 1, 1], 2)
+    assert (cnt == 4096).all() and st.passes == 1 and st.valid_kmers > 23_900_000 and st.candidates < 200_000
+    assert (np.diff(sk.astype(np.float64), axis=1) >= 0).all()
+    # the reference's merge identity: a group's sketch = the 4096 smallest of its sequences' own sketches taken together
+    parts = [wb.ani_group_sketches([b], [0], 1)[0][0] for b in big[:2]]
+    assert (np.sort(np.concatenate(parts))[:4096] == sk[0]).all()
+
+
+def test_pipeline_auto_identity_then_map(wb):
+    # the CLI default (-p ani50-2): estimate, adopt, re-derive the sketch size, map with it
+    from tests import pipeutil
+    from wfmash_b200 import pipeline
+    seqs = pipeutil.case(seed=5, length=60_000)
+    P = pipeline.auto_identity(seqs, seqs, pipeline.Params(percentage_identity=None))
+    assert 0.85 < P.percentage_identity < 0.97 and P.sketch_size == wb.sketch_size(P.percentage_identity, 1000, 15)
+    m = pipeline.map(seqs, seqs, P)
+    assert m.stats["mappings"] >= 6 and m.paf.count(b"\n") == m.stats["mappings"]

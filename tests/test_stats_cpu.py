@@ -126,3 +126,34 @@ def test_sketch_cutoffs_table():
             exp[cmax] = lo if lo != 0 else 1
         assert got.tolist() == exp.tolist(), (ss, k, delta)
         assert got[ss] > 1 and (np.diff(got[1:]) >= 0).all()
+
+
+@pytest.mark.ref
+def test_minimum_hits_and_bounds_match_compiled_reference_live():
+    """Stat::estimateMinimumHitsRelaxed / md_lower_bound / j2md / md2j of the reference's UNMODIFIED map_stats.hpp
+    (oracle/_ref/libstatsref.so; the two GSL cdf calls it makes are defined in the driver from the textbook formulas in long
+    double, independently of the product's restatement)."""
+    from tests import util
+    R = util.load_ref("libstatsref.so")
+    if R is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    R.ref_md_lower_bound.restype = ctypes.c_float
+    n = 0
+    for k in (15, 19, 21):
+        for s in (10, 17, 29, 39, 59, 98, 200, 333):
+            for pid in (0.70, 0.80, 0.85, 0.90, 0.95, 0.99):
+                assert wb.estimate_minimum_hits_relaxed(s, k, pid) == R.ref_estimate_minimum_hits_relaxed(s, k, ctypes.c_float(pid), ctypes.c_float(0.95)), (s, k, pid)
+                n += 1
+    assert n == 144
+    # the keep_low_pct_id table against the reference's own md_lower_bound
+    for s, k, pid in [(29, 15, 0.95), (59, 15, 0.80)]:
+        tab = wb.l2_min_shared_relaxed(pid, k, s)
+        for qs in (1, 7, s):
+            exp = qs + 1
+            for v in range(qs + 1):
+                md = j2md(f32(1.0 * v / qs), k)
+                ub = f32(1 - float(R.ref_md_lower_bound(ctypes.c_float(float(md)), qs, k, ctypes.c_float(0.95))))
+                if ub >= f32(pid) or f32(1 - float(md)) >= f32(pid):
+                    exp = v
+                    break
+            assert tab[qs] == exp, (s, qs)

@@ -698,3 +698,40 @@ def l2_min_shared_relaxed(percentage_identity: float, kmer_size: int, sketch_siz
     if rc != 0:
         raise _err(rc)
     return out
+
+
+# ---- ANI auto-identity ---------------------------------------------------------------------------------------
+class AniStats(ctypes.Structure):
+    _fields_ = [("hash_kernel_ms", ctypes.c_double), ("sort_kernel_ms", ctypes.c_double), ("bases", ctypes.c_uint64), ("valid_kmers", ctypes.c_uint64),
+                ("candidates", ctypes.c_uint64), ("tiles", ctypes.c_uint64), ("passes", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
+
+
+def ani_group_sketches(seqs, seq_group, n_groups: int, kmer_size: int = 21, sketch_size: int = 4096, device: int = 0):
+    """Per-group bottom-`sketch_size` multiset MinHash on the GPU (Stat::estimate_identity_for_groups, map_stats.hpp:563-637).
+    seq_group[i] = dense group index of seqs[i]. Returns (sketches[n_groups, sketch_size] ascending, counts[n_groups], AniStats)."""
+    n = len(seqs)
+    ptrs = (ctypes.c_char_p * max(n, 1))(*seqs)
+    lens = (ctypes.c_int64 * max(n, 1))(*[len(x) for x in seqs])
+    grp = (ctypes.c_int32 * max(n, 1))(*seq_group)
+    sk = np.zeros((n_groups, sketch_size), dtype=np.uint64)
+    cnt = np.zeros(n_groups, dtype=np.int32)
+    st = AniStats()
+    rc = lib().wfb_ani_group_sketches(device, ptrs, lens, grp, n, n_groups, kmer_size, sketch_size, _ptr(sk), _ptr(cnt), ctypes.byref(st))
+    if rc != 0:
+        raise _err(rc)
+    return sk, cnt, st
+
+
+def ani_estimate_identity(q_sketch, q_count, q_group, t_sketch, t_count, t_group, kmer_size: int = 21, ani_percentile: int = 50,
+                          ani_adjustment: float = -2.0):
+    """Host part of the ANI estimate (map_stats.hpp:690-800) -> (identity the CLI adopts, number of group comparisons)."""
+    qs, ts = np.ascontiguousarray(q_sketch, dtype=np.uint64), np.ascontiguousarray(t_sketch, dtype=np.uint64)
+    qc, tc = np.ascontiguousarray(q_count, dtype=np.int32), np.ascontiguousarray(t_count, dtype=np.int32)
+    qg, tg = np.ascontiguousarray(q_group, dtype=np.int32), np.ascontiguousarray(t_group, dtype=np.int32)
+    assert qs.ndim == 2 and ts.ndim == 2 and qs.shape[1] == ts.shape[1]
+    L = lib()
+    L.wfb_ani_estimate_identity.restype = ctypes.c_double
+    ncmp = ctypes.c_int32(0)
+    v = L.wfb_ani_estimate_identity(_ptr(qs), _ptr(qc), _ptr(qg), len(qg), _ptr(ts), _ptr(tc), _ptr(tg), len(tg), int(qs.shape[1]), kmer_size,
+                                    ani_percentile, ctypes.c_float(ani_adjustment), ctypes.byref(ncmp))
+    return float(v), int(ncmp.value)

@@ -33,7 +33,9 @@ class Params:
     here it is explicit, like `-p`)."""
     kmer_size: int = 15
     window_length: int = 1000              # -w (segment length)
-    percentage_identity: float = 0.90      # -p 90
+    percentage_identity: float = 0.90      # -p 90; None = the CLI default `-p ani50-2` (estimate_identity() below)
+    ani_percentile: int = 50
+    ani_adjustment: float = -2.0
     sketch_size: int = 0                   # -s; 0 = derive from identity / window / k
     minimum_hits: int = -1                 # -H; -1 = auto
     max_kmer_freq: float = 0.0002          # -F
@@ -58,6 +60,8 @@ class Params:
 
     def resolved(self):
         p = dataclasses.replace(self)
+        if p.percentage_identity is None:
+            raise ValueError("percentage_identity is None: call pipeline.auto_identity(targets, queries, params) first (the CLI does this before mapping, main.cpp:75-134)")
         if p.sketch_size <= 0:
             p.sketch_size = wb.sketch_size(p.percentage_identity, p.window_length, p.kmer_size)
         if p.filter is None:
@@ -87,6 +91,35 @@ class SequenceIds:
             if key not in keys:
                 keys[key] = len(keys) + 1
             self.group[self.id_of[name]] = keys[key]
+
+
+def estimate_identity(targets, queries, params: Params = None, device: int = 0):
+    """skch::Stat::estimate_identity_for_groups (map_stats.hpp:325-822): k = 21, 4096-hash MinHash per PanSN group and role,
+    all query-role groups against all target-role groups of another id -> (identity, stats). The sketches come from the GPU."""
+    P = params or Params()
+    ids = SequenceIds(targets, queries, P.prefix_delim if P.skip_prefix else "")
+    gids = sorted(set(ids.group))
+    dense = {g: i for i, g in enumerate(gids)}
+    same = [n for n, _ in targets] == [n for n, _ in queries]
+
+    def role(seqs):
+        sk, cnt, st = wb.ani_group_sketches([s for _, s in seqs], [dense[ids.group[ids.id_of[n]]] for n, _ in seqs], len(gids), 21, 4096, device)
+        present = sorted({dense[ids.group[ids.id_of[n]]] for n, _ in seqs})
+        return sk[present], cnt[present], [gids[i] for i in present], st
+
+    q = role(queries)
+    t = q if same else role(targets)
+    ident, ncmp = wb.ani_estimate_identity(q[0], q[1], q[2], t[0], t[1], t[2], 21, P.ani_percentile, P.ani_adjustment)
+    return ident, {"comparisons": ncmp, "hash_kernel_ms": q[3].hash_kernel_ms + (0 if same else t[3].hash_kernel_ms), "valid_kmers": int(q[3].valid_kmers)}
+
+
+def auto_identity(targets, queries, params: Params = None, device: int = 0) -> Params:
+    """main.cpp:75-134: adopt the estimated identity and, unless -s was given, re-derive the sketch size from it."""
+    P = dataclasses.replace(params or Params())
+    P.percentage_identity, _ = estimate_identity(targets, queries, P, device)
+    if params is None or params.sketch_size <= 0:
+        P.sketch_size = min(wb.sketch_size(P.percentage_identity, P.window_length, P.kmer_size), P.window_length)
+    return P
 
 
 @dataclasses.dataclass

@@ -171,6 +171,11 @@ typedef struct {
   float min_identity;             /* wflign_patch.cpp:2624-2626 filters */
   float min_block_identity;
   uint64_t min_alignment_length;
+  /* the SAM branch of do_biwfa_alignment (wflign.cpp:455-481 -> write_alignment_sam, wflign_patch.cpp:2480-2609) */
+  int32_t sam_format;             /* 0 = PAF lines (paf_format_else_sam = true), 1 = SAM records (-a)         */
+  int32_t emit_md_tag;            /* -d: append MD:Z: (write_tag_and_md_string, wflign_patch.cpp:2397-2478)    */
+  int32_t no_seq_in_sam;          /* SEQ column '*' instead of the aligned query bases                         */
+  int32_t reserved_;
 } wfb_paf_params_t;
 
 #define WFB_REC_WRITTEN 0       /* a PAF line was produced                                                    */

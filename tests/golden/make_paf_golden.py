@@ -18,3 +18,16 @@ for kw in util.PAF_FILTER_SETS:
 with gzip.GzipFile(os.path.join(HERE, "paf_do_biwfa.json.gz"), "wb", mtime=0) as f:
     f.write(json.dumps({"term_group": 8, "penalties": list(util.WFMASH_PEN), "filter_sets": util.PAF_FILTER_SETS, "lines": out}).encode())
 print("records", len(recs), "lines written", [sum(1 for l in s if l) for s in out])
+
+# the SAM branch (write_alignment_sam + MD tag) of the same unmodified function; lines kept as SHA-256 + first 9 columns
+import hashlib
+sam = []
+for kw in util.SAM_SETS:
+    rows = []
+    for r in recs:
+        ln = util.ref_sam(R, r, **kw)
+        rows.append({"head": b"\t".join(ln.split(b"\t")[:5]).decode(), "sha": hashlib.sha256(ln).hexdigest(), "tail": ln[-60:].decode()})
+    sam.append(rows)
+with gzip.GzipFile(os.path.join(HERE, "sam_do_biwfa.json.gz"), "wb", mtime=0) as f:
+    f.write(json.dumps({"term_group": 8, "sets": util.SAM_SETS, "lines": sam}).encode())
+print("SAM records written", [sum(1 for l in s_ if l["head"]) for s_ in sam])

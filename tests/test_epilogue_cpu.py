@@ -24,6 +24,13 @@ bad = []
 for kw, want in zip(gold["filter_sets"], gold["lines"]):
     lines, status = al.biwfa_paf_batch(recs, term_group=gold["term_group"], **kw)
     bad += [(i, str(kw)) for i, (g, w) in enumerate(zip(lines, want)) if g.decode() != w]
+# SURVEY 8 f4: the SAM branch (write_alignment_sam, MD tag) against the committed reference fixture
+import hashlib
+sgold = util.sam_golden()
+sbad = []
+for kw, want in zip(sgold["sets"], sgold["lines"]):
+    lines, status = al.biwfa_paf_batch(recs, term_group=sgold["term_group"], sam_format=True, **kw)
+    sbad += [(i, str(kw), g[:80].decode()) for i, (g, w) in enumerate(zip(lines, want)) if hashlib.sha256(g).hexdigest() != w["sha"]]
 # the kernel bodies themselves (4-diagonal groups, batched extend, overlap scan, base case) on the reference's own
 # known-answer vectors and on medium random pairs against the oracle
 pairs = util.golden_pairs()
@@ -34,7 +41,7 @@ gbad = [i for i, (r, (gs, gc)) in enumerate(zip(ag.align_end2end_batch(pairs), g
 orc = util.load_oracle()
 rp = [pt for pt in util.random_pairs(60, seed=41, lengths=(400, 1500, 4000), rates=(0.01, 0.05, 0.15)) if pt[0] and pt[1]]
 rbad = [i for i, ((p_, t_), r) in enumerate(zip(rp, al.align_end2end_batch(rp))) if (r.status, r.ops) != util.orc_biwfa(orc, p_, t_, util.WFMASH_PEN)[:2]]
-print(json.dumps({"bad": bad, "n": len(recs), "golden_bad": gbad, "golden_n": len(pairs), "random_bad": rbad, "random_n": len(rp)}))
+print(json.dumps({"bad": bad, "sam_bad": sbad, "n": len(recs), "golden_bad": gbad, "golden_n": len(pairs), "random_bad": rbad, "random_n": len(rp)}))
 """
 
 
@@ -46,5 +53,6 @@ def test_record_epilogue_and_kernel_bodies_under_emulation():
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["n"] == 63 and res["bad"] == []
+    assert res["sam_bad"] == []
     assert res["golden_n"] == 305 and res["golden_bad"] == []
     assert res["random_n"] > 40 and res["random_bad"] == []

@@ -431,6 +431,16 @@ def test_do_biwfa_alignment_paf_lines_match_reference(wb):
         if R is not None:  # live differential against the compiled reference when it travelled with the snapshot
             for r, got in zip(recs[:20], lines[:20]):
                 assert got == util.ref_paf(R, r, **kw)
+    # the SAM branch of the same function (write_alignment_sam + MD tag, wflign_patch.cpp:2397-2609)
+    import hashlib
+    sgold = util.sam_golden()
+    for kw, want in zip(sgold["sets"], sgold["lines"]):
+        lines, status = al.biwfa_paf_batch(recs, term_group=sgold["term_group"], sam_format=True, **kw)
+        for i, (got, w) in enumerate(zip(lines, want)):
+            assert hashlib.sha256(got).hexdigest() == w["sha"], (i, kw, got[:120], w["head"])
+        if R is not None:
+            for r, got in zip(recs[40:52], lines[40:52]):
+                assert got == util.ref_sam(R, r, **kw)
     al.close()
 
 

@@ -218,6 +218,33 @@ def ref_paf(R, r, pen=WFMASH_PEN, min_identity=0.0, min_alignment_length=0, min_
     return buf.raw[:n]
 
 
+SAM_SETS = [dict(emit_md_tag=True), dict(emit_md_tag=False, no_seq_in_sam=True, min_alignment_length=32, min_block_identity=0.1),
+            dict(emit_md_tag=True, disable_chain_patching=True)]
+
+
+def ref_sam(R, r, pen=WFMASH_PEN, min_identity=0.0, min_alignment_length=0, min_block_identity=0.0, disable_chain_patching=False, emit_md_tag=False,
+            no_seq_in_sam=False):
+    """The SAM branch of the unmodified do_biwfa_alignment (oracle/ref_wflign_driver.cpp::ref_do_biwfa_alignment_sam)."""
+    R.ref_do_biwfa_alignment_sam.argtypes = R.ref_do_biwfa_alignment.argtypes[:25] + [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    cap = 3 * (len(r["query"]) + len(r["target"])) + 4096
+    buf = ctypes.create_string_buffer(cap)
+    n = R.ref_do_biwfa_alignment_sam(r["query_name"].encode(), r["query"], r.get("query_total_length", len(r["query"])),
+                                     r.get("query_offset", 0), len(r["query"]), 1 if r.get("query_is_rev") else 0,
+                                     r["target_name"].encode(), r["target"], r.get("target_total_length", len(r["target"])),
+                                     r.get("target_offset", 0), len(r["target"]), pen[0], pen[1], pen[2], pen[3], pen[4],
+                                     1 if disable_chain_patching else 0, min_identity, min_alignment_length, min_block_identity, 0,
+                                     r.get("mashmap_estimated_identity", 0.0), r.get("chain_id", 0), r.get("chain_length", 0),
+                                     r.get("chain_pos", 0), int(emit_md_tag), int(no_seq_in_sam), buf, cap)
+    assert n >= 0
+    return buf.raw[:n]
+
+
+def sam_golden():
+    import json
+    with gzip.open(os.path.join(GOLD, "sam_do_biwfa.json.gz"), "rt") as f:
+        return json.load(f)
+
+
 def paf_golden():
     import json
     with gzip.open(os.path.join(GOLD, "paf_do_biwfa.json.gz"), "rt") as f:

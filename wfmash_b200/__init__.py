@@ -53,7 +53,8 @@ class _Record(ctypes.Structure):
 
 class _PafParams(ctypes.Structure):
     _fields_ = [("disable_chain_patching", ctypes.c_int32), ("term_group", ctypes.c_int32), ("min_identity", ctypes.c_float),
-                ("min_block_identity", ctypes.c_float), ("min_alignment_length", ctypes.c_uint64)]
+                ("min_block_identity", ctypes.c_float), ("min_alignment_length", ctypes.c_uint64), ("sam_format", ctypes.c_int32),
+                ("emit_md_tag", ctypes.c_int32), ("no_seq_in_sam", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
 
 
 REC_WRITTEN, REC_FILTERED, REC_UNALIGNED, REC_PATCH_CAP = 0, 1, 2, -1
@@ -224,12 +225,13 @@ class Aligner:
         return st, buf.raw[: n.value], sc.value
 
     def biwfa_paf_batch(self, records, min_identity=0.0, min_alignment_length=0, min_block_identity=0.0,
-                        disable_chain_patching=False, term_group=8):
+                        disable_chain_patching=False, term_group=8, sam_format=False, emit_md_tag=False, no_seq_in_sam=False):
         """Batched wflign::wavefront::do_biwfa_alignment, PAF branch (src/common/wflign/src/wflign.cpp:108-483).
         records: dicts with the reference's parameter names: query_name, query, query_total_length, query_offset,
         query_is_rev, target_name, target, target_total_length, target_offset, mashmap_estimated_identity, chain_id,
         chain_length, chain_pos (query_length / target_length are the slice lengths).
-        Returns (lines, status): lines[i] is the PAF line (b"" when none), status[i] one of REC_*."""
+        sam_format / emit_md_tag / no_seq_in_sam select the SAM branch (write_alignment_sam, wflign_patch.cpp:2480-2609).
+        Returns (lines, status): lines[i] is the PAF line / SAM record (b"" when none), status[i] one of REC_*."""
         n = len(records)
         if n == 0:
             return [], []
@@ -244,7 +246,8 @@ class Aligner:
                              1 if r.get("query_is_rev", False) else 0, r.get("chain_id", 0), tn, t,
                              r.get("target_total_length", len(t)), r.get("target_offset", 0), len(t),
                              r.get("chain_length", 0), r.get("chain_pos", 0), r.get("mashmap_estimated_identity", 0.0), 0)
-        pp = _PafParams(1 if disable_chain_patching else 0, term_group, min_identity, min_block_identity, min_alignment_length)
+        pp = _PafParams(1 if disable_chain_patching else 0, term_group, min_identity, min_block_identity, min_alignment_length,
+                        int(sam_format), int(emit_md_tag), int(no_seq_in_sam), 0)
         cap = sum(len(k[0]) + len(k[1]) for k in keep) // 2 + 512 * n + 4096
         offs = (ctypes.c_int64 * (n + 1))()
         st = (ctypes.c_int32 * n)()

@@ -150,7 +150,10 @@ WFB_DEV void ani_tile(unsigned char* smem, const uint8_t* blob, const AniTile t,
       }
     }
   }
-  if (valid_here) atomicAdd_compat(n_valid, (unsigned long long)valid_here);
+  { /* one counter update per warp, not per thread: 6 M same-address atomics per 200 Mbp were 10 % of the stall samples */
+    const unsigned warp_valid = wfb_warp_add(valid_here);
+    if (wfb_lane() == 0 && warp_valid) atomicAdd_compat(n_valid, (unsigned long long)warp_valid);
+  }
   WFB_SYNC();
 }
 

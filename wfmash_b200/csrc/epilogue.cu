@@ -277,6 +277,86 @@ bool write_paf(std::string& out, const Cigar& c, const wfb_record_t& r, const wf
   return true;
 }
 
+/* write_tag_and_md_string (wflign_patch.cpp:2397-2478) over the trimmed runs; the reference starts the target walk at
+ * offset 0 of the slice even when trim_indels removed leading deletions (wflign_patch.cpp:2596-2600), and so does this. */
+void put_md(std::string& out, const Run* c, size_t n, const char* target) {
+  out.append("MD:Z:");
+  char last_op = '\0';
+  int64_t last_len = 0, t_off = 0, l_md = 0;
+  for (size_t x = 0; x < n; ++x) {
+    const char op = c[x].op;
+    int64_t len = c[x].n;
+    if (last_len) {
+      if (last_op == op) len += last_len;
+      else if (last_op == '=' || last_op == 'M') { l_md += last_len; t_off += last_len; }
+      else if (last_op == 'X') {
+        for (int64_t i = 0; i < last_len; ++i) { put_u(out, (uint64_t)l_md); out.push_back(target[t_off + i]); l_md = 0; }
+        t_off += last_len;
+      } else if (last_op == 'D') {
+        put_u(out, (uint64_t)l_md); out.push_back('^');
+        out.append(target + t_off, (size_t)last_len);
+        l_md = 0;
+        t_off += last_len;
+      } /* an insertion in the middle changes nothing */
+    }
+    last_op = op;
+    last_len = len;
+  }
+  if (last_len) {
+    if (last_op == '=' || last_op == 'M') put_u(out, (uint64_t)(last_len + l_md));
+    else if (last_op == 'X') {
+      for (int64_t i = 0; i < last_len; ++i) { put_u(out, (uint64_t)l_md); out.push_back(target[t_off + i]); l_md = 0; }
+      out.push_back('0');
+    } else if (last_op == 'I') put_u(out, (uint64_t)l_md);
+    else if (last_op == 'D') {
+      put_u(out, (uint64_t)l_md); out.push_back('^');
+      out.append(target + t_off, (size_t)last_len);
+      out.push_back('0');
+    }
+  }
+}
+
+/* trim_indels + write_alignment_sam (wflign_patch.cpp:139-222, 2480-2609) with aln.i = aln.j = 0, aln.is_rev = false */
+bool write_sam(std::string& out, const Cigar& c, const wfb_record_t& r, const wfb_paf_params_t& pp) {
+  size_t b = 0, e = c.size();
+  uint64_t ref_start = r.target_offset, q_start0 = r.query_offset;
+  while (b < e && (c[b].op == 'I' || c[b].op == 'D')) {
+    if (c[b].op == 'I') q_start0 += (uint64_t)c[b].n; else ref_start += (uint64_t)c[b].n;
+    ++b;
+  }
+  if (b == e) return false;
+  while (e > b && (c[e - 1].op == 'I' || c[e - 1].op == 'D')) --e;
+  const Metrics m = measure(c.data() + b, e - b);
+  const double gap_compressed_identity = (double)m.matches / (double)(m.matches + m.mismatches + m.insertions + m.deletions);
+  const double block_identity = (double)m.matches / (double)(m.matches + m.mismatches + m.inserted_bp + m.deleted_bp);
+  if (!(gap_compressed_identity >= pp.min_identity && m.q_len >= pp.min_alignment_length && block_identity >= pp.min_block_identity))
+    return false;
+  out.append(r.query_name ? r.query_name : ""); out.push_back('\t');
+  out.append(r.query_is_rev ? "16" : "0"); out.push_back('\t');
+  out.append(r.target_name ? r.target_name : ""); out.push_back('\t');
+  put_u(out, ref_start + 1); out.push_back('\t');
+  put_g(out, std::round(float2phred(1.0 - block_identity))); out.push_back('\t');
+  append_text(out, c.data() + b, e - b);
+  out.append("\t*\t0\t0\t");
+  if (pp.no_seq_in_sam) out.push_back('*');
+  else out.append(r.query + (q_start0 - r.query_offset), (size_t)m.q_len);
+  out.append("\t*\tNM:i:"); put_u(out, m.mismatches + m.inserted_bp + m.deleted_bp);
+  out.append("\tgi:f:"); put_g(out, gap_compressed_identity);
+  out.append("\tbi:f:"); put_g(out, block_identity);
+  out.append("\tmd:f:"); put_g(out, (double)r.mashmap_estimated_identity);
+  if (r.chain_length > 0) {
+    char buf[96];
+    const int k = snprintf(buf, sizeof buf, "\tci:i:%d\tch:Z:%d.%d.%d", r.chain_id, r.chain_id, r.chain_length, r.chain_pos);
+    out.append(buf, (size_t)k);
+  }
+  if (pp.emit_md_tag) {
+    out.push_back('\t');
+    put_md(out, c.data() + b, e - b, r.target);
+  }
+  out.push_back('\n');
+  return true;
+}
+
 struct Patch {
   int rec;
   Erosion er;
@@ -392,7 +472,7 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     Cigar& c = cig[(size_t)i];
     swap_start(c, r.query, qn, r.target, tn);
     swap_end(c, r.query, qn, r.target, tn);
-    if (!write_paf(text, c, r, *params)) rec_status[i] = WFB_REC_FILTERED;
+    if (!(params->sam_format ? write_sam(text, c, r, *params) : write_paf(text, c, r, *params))) rec_status[i] = WFB_REC_FILTERED;
   }
   line_offset[n] = (int64_t)text.size();
   *out_len = (int64_t)text.size();

@@ -570,6 +570,81 @@ double wfb_ani_estimate_identity(const uint64_t* q_sketch, const int32_t* q_coun
                                  const int32_t* t_count, const int32_t* t_group, int32_t nt, int32_t sketch_size, int32_t kmer_size,
                                  int32_t ani_percentile, float ani_adjustment, int32_t* n_comparisons);
 
+/* ------------------------------------------------------------------------------------------------
+ * The two phases of src/interface/main.cpp as ONE call each over sequences held in host memory (no CLI, no FASTA / index
+ * files): what skch::Map (src/map/include/computeMap.hpp:300-860) and align::Aligner
+ * (src/align/include/computeAlignments.hpp:318-720) do between "sequences loaded" and "text written". Every step inside is
+ * one of the entry points above; the text handed from one to the other is the reference's mapping PAF.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const char* name; /* sequence name (PanSN: sample#hap#contig)                                  */
+  const char* seq;  /* bases, any case, not NUL-terminated                                       */
+  int64_t len;
+} wfb_seq_t;
+
+typedef struct { /* the skch::Parameters fields of the mapping phase; CLI defaults in brackets (src/interface/parse_args.hpp) */
+  int32_t kmer_size;            /* -k [15]                                                         */
+  int32_t sketch_size;          /* -s; <= 0 = derive from identity / window / k (wfb_sketch_size)   */
+  int32_t minimum_hits;         /* -H; < 0 = auto (wfb_estimate_minimum_hits_relaxed)               */
+  int32_t index_threads;        /* param.threads of the index build (partitions of the postings)    */
+  int64_t window_length;        /* -w [1000]                                                       */
+  float percentage_identity;    /* -p as a fraction; <= 0 = estimate it (ANI auto-identity, the CLI default `ani50-2`) */
+  float ani_adjustment;         /* [-2.0]                                                          */
+  int32_t ani_percentile;       /* [50]                                                            */
+  int32_t skip_self;            /* [1] no -X                                                       */
+  int32_t skip_prefix;          /* [1] -Y '#'                                                      */
+  int32_t lower_triangular;     /* [0] -L                                                          */
+  int32_t stage1_top_ani_filter;/* [1]                                                             */
+  int32_t keep_low_pct_id;      /* [1]                                                             */
+  int32_t prefix_delim;         /* ['#'] as a character code; group = name up to its LAST delimiter */
+  int32_t reserved_;
+  double max_kmer_freq;         /* -F [0.0002]                                                     */
+  double hg_numerator;          /* [1.0]                                                           */
+  float ani_diff;               /* [0.0]                                                           */
+  float ani_diff_conf;          /* [0.999]                                                         */
+  wfb_filter_params_t filter;   /* chain / filter stage; window_length, percentage_identity and skip_prefix are overwritten
+                                   with the values above                                            */
+} wfb_map_phase_params_t;
+
+typedef struct {
+  int64_t fragments, l2_mappings, mappings; /* query fragments, fragment mappings before / after the filters */
+  int32_t sketch_size, minimum_hits;        /* as resolved                                                   */
+  float percentage_identity;                /* as resolved (estimated when the parameter was <= 0)           */
+  int32_t reserved_;
+  double index_seconds, map_kernel_ms, filter_seconds, total_seconds;
+} wfb_map_phase_stats_t;
+
+/* Mapping phase: ids + PanSN groups (SequenceIdManager, sequenceIds.hpp:284-441; targets first), optional ANI estimate,
+ * index build, query fragments (computeMap.hpp:560-630), L1 + L2 kernels, per-query chain merge + filters, mapping PAF text.
+ * *paf receives a malloc'ed buffer (free it with wfb_free_text) holding *paf_len bytes of `wfmash -m` output, grouped by
+ * query in input order. The one-to-one mode runs its final reference-axis pass over all queries (wfb_one_to_one_filter). */
+int wfb_map_phase(int device, const wfb_map_phase_params_t* params, const wfb_seq_t* targets, int32_t n_targets, const wfb_seq_t* queries,
+                  int32_t n_queries, char** paf, int64_t* paf_len, wfb_map_phase_stats_t* stats);
+
+typedef struct { /* the align::Parameters fields of the alignment phase */
+  uint64_t target_padding;       /* -E [min(window_length, 5000)]                                   */
+  uint64_t query_padding;        /* -U [min(window_length, 5000)]                                   */
+  uint64_t wflign_max_len_minor; /* [window_length * 128]                                           */
+  int32_t batch_records;         /* records per GPU batch; <= 0 = 4096                              */
+  int32_t reserved_;
+  wfb_paf_params_t output;       /* filters, patching, PAF / SAM                                    */
+} wfb_align_phase_params_t;
+
+typedef struct {
+  int64_t records, written, skipped_lines; /* parsable mapping rows, output records, rows skipped like computeAlignments.hpp:368-372 */
+  uint64_t aligned_bp;                     /* the reference's processed_alignment_length (computeAlignments.hpp:480,528)  */
+  double kernel_ms, total_seconds;
+} wfb_align_phase_stats_t;
+
+/* Alignment phase over mapping PAF text: parseMashmapRow + padding, slices fetched with faidx's clamping, upper-casing /
+ * N-masking, reverse complement of '-' queries (computeAlignments.hpp:195-303,582-686), batched do_biwfa_alignment
+ * (wfb_biwfa_paf_batch). *out: malloc'ed text of *out_len bytes (wfb_free_text), records in the order of the rows. */
+int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_params_t* params, const char* mapping_paf, int64_t mapping_paf_len,
+                    const wfb_seq_t* targets, int32_t n_targets, const wfb_seq_t* queries, int32_t n_queries, char** out, int64_t* out_len,
+                    wfb_align_phase_stats_t* stats);
+
+void wfb_free_text(char* text);
+
 #ifdef __cplusplus
 }
 #endif

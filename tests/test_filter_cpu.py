@@ -215,3 +215,35 @@ def test_mapping_paf_round_trip_and_parse_rules():
     # -M output carries jc:f:0 instead of the chain tag; legacy output is blank separated with inclusive ends
     assert wb.mapping_paf_format(wb.FilterParams(merge_mappings=0), m[:1], None, "q", 100_000, names, rlen).endswith(b"\tkc:f:0.97\tjc:f:0\n")
     assert wb.mapping_paf_format(wb.FilterParams(legacy_output=1), m[:1], None, "q", 100_000, names, rlen) == b"q 100000 0 29999 + tgt#1#b 90000 500 30499 951200\n"
+
+
+@pytest.mark.ref
+def test_filter_edge_cases_match_compiled_reference_live():
+    """Empty batch, queries without mappings, one and two mappings, a mapping ending beyond the query, zero-length blocks."""
+    import wfmash_b200 as wb
+    ref = util.load_ref("libfilterref.so")
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    ref.ref_filter_subset.restype = ctypes.c_int64
+    out, info, oo = wb.filter_mappings_batch(wb.FilterParams(), np.zeros(0, dtype=wb.MAPPING_DTYPE), [0], [], REF_LEN)
+    assert len(out) == 0 and oo.tolist() == [0]
+    one = np.zeros(1, dtype=wb.MAPPING_DTYPE); one[0] = (2, 399_500, 299_000, 1000, 1, 9, 9100, 1, 80)     # ends at the sequence ends
+    two = np.zeros(2, dtype=wb.MAPPING_DTYPE); two[0] = (1, 5000, 0, 1000, 1, 20, 9900, 0, 90); two[1] = (1, 6000, 1000, 1000, 1, 22, 9800, 0, 95)
+    zero = np.zeros(3, dtype=wb.MAPPING_DTYPE); zero[0] = (0, 100, 100, 0, 1, 0, 0, 0, 0); zero[1] = (0, 100, 100, 0, 1, 0, 0, 0, 0); zero[2] = (0, 7000, 7000, 1000, 1, 5, 8000, 0, 50)
+    many = np.concatenate([two] * 3 + [one])                                                                  # exact duplicates
+    for prm in (dict(), dict(scaffold_gap=0), dict(merge_mappings=0), dict(num_mappings_for_segment=1, scaffold_min_length=500), dict(filter_mode=3, block_length=5000)):
+        P = wb.FilterParams(window_length=1000, **prm)
+        batch = [one, np.zeros(0, dtype=wb.MAPPING_DTYPE), two, zero, many]
+        off = np.cumsum([0] + [len(b) for b in batch])
+        got, ginfo, goo = wb.filter_mappings_batch(P, np.concatenate(batch), off, [QLEN] * len(batch), REF_LEN, host_threads=2)
+        for q, b in enumerate(batch):
+            a = np.ascontiguousarray(b)
+            o = np.zeros(len(a) + 4, dtype=wb.MAPPING_DTYPE); c = np.zeros(len(a) + 4, dtype=wb.CHAIN_INFO_DTYPE)
+            n = ref.ref_filter_subset(ctypes.byref(P), ctypes.c_void_p(a.ctypes.data) if len(a) else None, ctypes.c_int64(len(a)), q, ctypes.c_int64(QLEN), None,
+                                      ctypes.c_void_p(REF_LEN.ctypes.data), ctypes.c_void_p(o.ctypes.data), ctypes.c_void_p(c.ctypes.data), ctypes.c_int64(len(o)))
+            assert n == goo[q + 1] - goo[q], (prm, q)
+            assert got[goo[q]: goo[q + 1]].tobytes() == o[:n].tobytes() and ginfo[goo[q]: goo[q + 1]].tobytes() == c[:n].tobytes(), (prm, q)
+    with pytest.raises(wb.WfbError):
+        wb.filter_mappings_batch(wb.FilterParams(window_length=0), one, [0, 1], [QLEN], REF_LEN)
+    with pytest.raises(wb.WfbError):
+        wb.filter_mappings_batch(wb.FilterParams(skip_prefix=1), one, [0, 1], [QLEN], REF_LEN)     # skip_prefix needs the groups

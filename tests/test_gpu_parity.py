@@ -466,6 +466,13 @@ def test_pipeline_map_align_matches_reference_pieces(wb, oracle):
         want = sorted((d["head"], d["sha"]) for d in g["lines"] if d["head"])
         assert got == want, name
         assert st["written"] == len(want) and st["aligned_bp"] > 0
+        # the same run through the two one-call C-ABI phases (wfmash_b200/csrc/phases_host.cu)
+        mp_c, mst = wb.map_phase(seqs, seqs, wb.MapPhaseParams(filter=P.filter, window_length=P.window_length, percentage_identity=P.percentage_identity))
+        assert mp_c == st["mapping_paf"], name
+        al = wb.Aligner(0)
+        paf_c, ast = wb.align_phase(al, mp_c, seqs, seqs, window_length=P.window_length, disable_chain_patching=P.disable_chain_patching)
+        al.close()
+        assert paf_c == paf and ast.records == st["records"] and ast.aligned_bp == st["aligned_bp"], name
         if fref is not None and wref is not None and name == "defaults_p90":
             mp, lines = pipeutil.expected(seqs, P, oracle, fref, wref)
             assert st["mapping_paf"] == mp and paf == b"".join(lines)
@@ -524,3 +531,5 @@ def test_pipeline_auto_identity_then_map(wb):
     assert 0.85 < P.percentage_identity < 0.97 and P.sketch_size == wb.sketch_size(P.percentage_identity, 1000, 15)
     m = pipeline.map(seqs, seqs, P)
     assert m.stats["mappings"] >= 6 and m.paf.count(b"\n") == m.stats["mappings"]
+    mp_c, mst = wb.map_phase(seqs, seqs, wb.MapPhaseParams())   # percentage_identity <= 0: the C phase estimates it itself
+    assert abs(mst.percentage_identity - P.percentage_identity) < 1e-6 and mst.sketch_size == P.sketch_size and mp_c == m.paf

@@ -26,6 +26,10 @@ out = {"have_ref": fref is not None and wref is not None}
 if out["have_ref"]:
     mp, lines = pipeutil.expected(seqs, P, util.load_oracle(), fref, wref)
     paf, st = pipeline.align(mp, seqs, seqs, P)
+    import wfmash_b200 as wb
+    al = wb.Aligner(0)
+    c_paf, c_st = wb.align_phase(al, mp + b"not a mapping row\n", seqs, seqs)   # the one-call C ABI phase (phases_host.cu) on the same text
+    out.update(c_paf=c_paf.decode(), c_records=int(c_st.records), c_skipped=int(c_st.skipped_lines), c_aligned_bp=int(c_st.aligned_bp))
     out.update(ref_map=mp.decode(), ref_paf=b"".join(lines).decode(), ours_paf=paf.decode(), records=st["records"], written=st["written"],
                aligned_bp=st["aligned_bp"])
 print(json.dumps(out))
@@ -44,6 +48,7 @@ def test_align_phase_under_emulation_matches_reference_do_biwfa_alignment():
         pytest.skip("oracle/_ref not built (reference sources absent)")
     assert res["records"] >= 8 and res["written"] >= 8
     assert res["ours_paf"] == res["ref_paf"]
+    assert res["c_paf"] == res["ref_paf"] and res["c_records"] == res["records"] and res["c_skipped"] == 1 and res["c_aligned_bp"] == res["aligned_bp"]
     assert {ln.split("\t")[4] for ln in res["ours_paf"].splitlines()} == {"+", "-"}
     spans = [int(f[3]) - int(f[2]) for f in (ln.split("\t") for ln in res["ref_map"].splitlines())]
     assert res["aligned_bp"] >= sum(spans)  # + the query padding of the chain ends

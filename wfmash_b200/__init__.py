@@ -738,3 +738,93 @@ def ani_estimate_identity(q_sketch, q_count, q_group, t_sketch, t_count, t_group
     v = L.wfb_ani_estimate_identity(_ptr(qs), _ptr(qc), _ptr(qg), len(qg), _ptr(ts), _ptr(tc), _ptr(tg), len(tg), int(qs.shape[1]), kmer_size,
                                     ani_percentile, ctypes.c_float(ani_adjustment), ctypes.byref(ncmp))
     return float(v), int(ncmp.value)
+
+
+# ---- the two phases as one C-ABI call each (wfmash_b200/csrc/phases_host.cu) --------------------------------------------------
+class _Seq(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("seq", ctypes.c_char_p), ("len", ctypes.c_int64)]
+
+
+class MapPhaseParams(ctypes.Structure):
+    """wfb_map_phase_params_t with the CLI defaults (percentage_identity <= 0 = ANI auto-identity)."""
+    _fields_ = [("kmer_size", ctypes.c_int32), ("sketch_size", ctypes.c_int32), ("minimum_hits", ctypes.c_int32), ("index_threads", ctypes.c_int32),
+                ("window_length", ctypes.c_int64), ("percentage_identity", ctypes.c_float), ("ani_adjustment", ctypes.c_float),
+                ("ani_percentile", ctypes.c_int32), ("skip_self", ctypes.c_int32), ("skip_prefix", ctypes.c_int32), ("lower_triangular", ctypes.c_int32),
+                ("stage1_top_ani_filter", ctypes.c_int32), ("keep_low_pct_id", ctypes.c_int32), ("prefix_delim", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+                ("max_kmer_freq", ctypes.c_double), ("hg_numerator", ctypes.c_double), ("ani_diff", ctypes.c_float), ("ani_diff_conf", ctypes.c_float),
+                ("filter", FilterParams)]
+
+    def __init__(self, filter=None, **kw):  # noqa: A002
+        d = dict(kmer_size=15, sketch_size=0, minimum_hits=-1, index_threads=1, window_length=1000, percentage_identity=0.0, ani_adjustment=-2.0,
+                 ani_percentile=50, skip_self=1, skip_prefix=1, lower_triangular=0, stage1_top_ani_filter=1, keep_low_pct_id=1, prefix_delim=ord("#"),
+                 reserved_=0, max_kmer_freq=0.0002, hg_numerator=1.0, ani_diff=0.0, ani_diff_conf=0.999)
+        unknown = set(kw) - set(d)
+        if unknown:
+            raise TypeError(f"unknown mapping parameter(s): {sorted(unknown)}")
+        d.update(kw)
+        super().__init__(**d)
+        self.filter = filter if filter is not None else FilterParams(window_length=d["window_length"])
+
+
+class MapPhaseStats(ctypes.Structure):
+    _fields_ = [("fragments", ctypes.c_int64), ("l2_mappings", ctypes.c_int64), ("mappings", ctypes.c_int64), ("sketch_size", ctypes.c_int32),
+                ("minimum_hits", ctypes.c_int32), ("percentage_identity", ctypes.c_float), ("reserved_", ctypes.c_int32), ("index_seconds", ctypes.c_double),
+                ("map_kernel_ms", ctypes.c_double), ("filter_seconds", ctypes.c_double), ("total_seconds", ctypes.c_double)]
+
+
+class AlignPhaseParams(ctypes.Structure):
+    _fields_ = [("target_padding", ctypes.c_uint64), ("query_padding", ctypes.c_uint64), ("wflign_max_len_minor", ctypes.c_uint64),
+                ("batch_records", ctypes.c_int32), ("reserved_", ctypes.c_int32), ("output", _PafParams)]
+
+
+class AlignPhaseStats(ctypes.Structure):
+    _fields_ = [("records", ctypes.c_int64), ("written", ctypes.c_int64), ("skipped_lines", ctypes.c_int64), ("aligned_bp", ctypes.c_uint64),
+                ("kernel_ms", ctypes.c_double), ("total_seconds", ctypes.c_double)]
+
+
+def _seq_array(seqs):
+    arr = (_Seq * max(len(seqs), 1))()
+    keep = []
+    for i, (name, seq) in enumerate(seqs):
+        nb = name.encode() if isinstance(name, str) else name
+        keep.append((nb, seq))
+        arr[i] = _Seq(nb, seq, len(seq))
+    return arr, keep
+
+
+def map_phase(targets, queries, params: MapPhaseParams = None, device: int = 0):
+    """wfb_map_phase: the whole `wfmash -m` phase over in-memory sequences -> (mapping PAF bytes, MapPhaseStats)."""
+    P = params or MapPhaseParams()
+    ta, tk = _seq_array(targets)
+    qa, qk = _seq_array(queries)
+    txt, n, st = ctypes.c_void_p(), ctypes.c_int64(0), MapPhaseStats()
+    L = lib()
+    rc = L.wfb_map_phase(device, ctypes.byref(P), ta, len(targets), qa, len(queries), ctypes.byref(txt), ctypes.byref(n), ctypes.byref(st))
+    if rc != 0:
+        raise _err(rc)
+    out = ctypes.string_at(txt, n.value)
+    L.wfb_free_text.argtypes = [ctypes.c_void_p]
+    L.wfb_free_text(txt)
+    return out, st
+
+
+def align_phase(aligner: "Aligner", mapping_paf: bytes, targets, queries, window_length: int = 1000, target_padding: int = -1, query_padding: int = -1,
+                batch_records: int = 0, min_identity=0.0, min_alignment_length=32, min_block_identity=0.1, disable_chain_patching=False, term_group=8,
+                sam_format=False, emit_md_tag=False, no_seq_in_sam=False):
+    """wfb_align_phase: mapping PAF text -> alignment PAF / SAM text (bytes, AlignPhaseStats); defaults = the CLI's."""
+    pad = min(window_length, 5000)
+    P = AlignPhaseParams(pad if target_padding < 0 else target_padding, pad if query_padding < 0 else query_padding, window_length * 128, batch_records, 0,
+                         _PafParams(int(disable_chain_patching), term_group, min_identity, min_block_identity, min_alignment_length, int(sam_format),
+                                    int(emit_md_tag), int(no_seq_in_sam), 0))
+    ta, tk = _seq_array(targets)
+    qa, qk = _seq_array(queries)
+    txt, n, st = ctypes.c_void_p(), ctypes.c_int64(0), AlignPhaseStats()
+    L = lib()
+    rc = L.wfb_align_phase(ctypes.c_void_p(aligner._h), ctypes.byref(P), mapping_paf, ctypes.c_int64(len(mapping_paf)), ta, len(targets), qa, len(queries),
+                           ctypes.byref(txt), ctypes.byref(n), ctypes.byref(st))
+    if rc != 0:
+        raise _err(rc)
+    out = ctypes.string_at(txt, n.value)
+    L.wfb_free_text.argtypes = [ctypes.c_void_p]
+    L.wfb_free_text(txt)
+    return out, st

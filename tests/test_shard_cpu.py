@@ -31,10 +31,25 @@ def _worker(rank, world, port, q):
         return [(len(p), len(t), rank) for p, t in local]
 
     out = shard.align_sharded(pairs, fake_align)
+    # the two phases of the pipeline sharded the same way (stand-ins for the GPU calls; the real ones are pipeline.map / align)
+    queries = [(f"s{i}#1#c", b"A" * (1000 * (i % 5 + 1))) for i in range(9)]
+
+    def fake_map(only):  # two mapping rows per query of this rank's partition, one of them unparsable
+        return b"".join(b"%s\t%d\t0\t%d\t+\tt\t99999\t10\t%d\t5\t100\t30\tid:f:0.9%d\tkc:f:1\n%s\tgarbage\n"
+                        % (n.encode(), len(s), len(s), 10 + len(s), rank, n.encode()) for n, s in queries if n in only)
+
+    mp = shard.map_sharded(None, queries, None, map_fn=fake_map)
+    box = [mp]
+    dist.broadcast_object_list(box, src=0)
+
+    def fake_align(text, per_row=True):  # one record per parsable row, none for the garbage rows
+        return [(b"aligned:" + ln.split(b"\t")[0] + b":%d\n" % rank) if b"garbage" not in ln else b"" for ln in text.split(b"\n") if ln]
+
+    paf = shard.align_paf_sharded(box[0], None, queries, align_fn=fake_align)
     if rank == 0:
-        q.put((out, len(seen)))
+        q.put((out, len(seen), mp, paf))
     else:
-        q.put((None, len(seen)))
+        q.put((None, len(seen), None, None))
     dist.destroy_process_group()
 
 
@@ -64,7 +79,12 @@ def test_two_rank_gloo_shard_and_gather():
         assert p.exitcode == 0
     full = [g for g in got if g[0] is not None]
     assert len(full) == 1
-    out, _ = full[0]
+    out, _, mp, paf = full[0]
+    rows = [ln for ln in mp.split(b"\n") if ln]
+    assert [ln.split(b"\t")[0].decode() for ln in rows] == [f"s{i}#1#c" for i in range(9) for _ in range(2)]   # query order restored, rows kept together
+    assert {ln.split(b"\t")[12] for ln in rows if b"garbage" not in ln} == {b"id:f:0.90", b"id:f:0.91"}        # both ranks mapped
+    recs = [ln for ln in paf.split(b"\n") if ln]
+    assert [r.split(b":")[1].decode() for r in recs] == [f"s{i}#1#c" for i in range(9)] and {r.split(b":")[2] for r in recs} == {b"0", b"1"}
     assert len(out) == 23 and all(o is not None for o in out)
     assert [(o[0], o[1]) for o in out] == [(100 + 37 * i, 90 + 41 * i) for i in range(23)]
     assert {o[2] for o in out} == {0, 1}            # both ranks did work

@@ -132,8 +132,9 @@ class MapResult:
     stats: dict
 
 
-def map(targets, queries, params: Params = None, device: int = 0, index=None) -> MapResult:  # noqa: A001 - the reference's phase name
-    """Mapping phase. targets / queries: [(name, bytes)]. `index` reuses a wb.Index built for the same targets."""
+def map(targets, queries, params: Params = None, device: int = 0, index=None, only_queries=None) -> MapResult:  # noqa: A001 - the reference's phase name
+    """Mapping phase. targets / queries: [(name, bytes)]. `index` reuses a wb.Index built for the same targets.
+    only_queries: names of the queries this call maps (multi-GPU sharding by query); ids and groups still come from ALL sequences."""
     P = (params or Params()).resolved()
     k, w, s = P.kmer_size, P.window_length, P.sketch_size
     ids = SequenceIds(targets, queries, P.prefix_delim if P.skip_prefix else "")
@@ -147,7 +148,7 @@ def map(targets, queries, params: Params = None, device: int = 0, index=None) ->
     shared = wb.l2_min_shared_relaxed(P.percentage_identity, k, s) if P.keep_low_pct_id else wb.l2_min_shared(P.percentage_identity, k, s)
 
     # query fragments (computeMap.hpp:560-630): floor(len / w) window-sized pieces + one overlapping tail piece
-    mapped = [(n, seq) for n, seq in queries if len(seq) >= w]
+    mapped = [(n, seq) for n, seq in queries if len(seq) >= w and (only_queries is None or n in only_queries)]
     blob = b"".join(seq for _, seq in mapped)
     frags, fqs, frag_index, q_frag = [], [], [], [0]
     base = 0
@@ -205,9 +206,7 @@ def records_from_paf(paf: bytes, targets, queries, params: Params = None):
     P = (params or Params()).resolved()
     tseq, qseq = dict(targets), dict(queries)
     recs = []
-    for line in paf.split(b"\n"):
-        if not line:
-            continue
+    for row_index, line in enumerate(ln for ln in paf.split(b"\n") if ln):
         try:
             row, qn, tn = wb.mapping_paf_parse(line, P.target_padding, P.query_padding, P.window_length * 128)
         except wb.WfbError:
@@ -223,12 +222,13 @@ def records_from_paf(paf: bytes, targets, queries, params: Params = None):
         recs.append(dict(query_name=qn, query=q.tobytes(), query_total_length=len(qseq[qn]), query_offset=row.q_start, query_is_rev=row.strand != 1,
                          target_name=tn, target=t.tobytes(), target_total_length=len(tseq[tn]), target_offset=row.r_start,
                          mashmap_estimated_identity=row.mashmap_estimated_identity, chain_id=row.chain_id, chain_length=row.chain_length,
-                         chain_pos=row.chain_pos, mapping_query_span=row.q_end - row.q_start))
+                         chain_pos=row.chain_pos, mapping_query_span=row.q_end - row.q_start, row_index=row_index))
     return recs
 
 
-def align(paf: bytes, targets, queries, params: Params = None, device: int = 0, aligner=None, batch_records: int = 4096):
-    """Alignment phase over mapping PAF text -> (alignment PAF text, stats)."""
+def align(paf: bytes, targets, queries, params: Params = None, device: int = 0, aligner=None, batch_records: int = 4096, per_row: bool = False):
+    """Alignment phase over mapping PAF text -> (alignment PAF text, stats). per_row: return one bytes object per non-empty input
+    row instead (b"" for rows that were skipped or filtered), for callers that scatter rows over GPUs."""
     P = (params or Params()).resolved()
     recs = records_from_paf(paf, targets, queries, P)
     own = aligner is None
@@ -245,7 +245,12 @@ def align(paf: bytes, targets, queries, params: Params = None, device: int = 0, 
         aligner.close()
     # the reference's processed_alignment_length (computeAlignments.hpp:480,528): qEndPos - qStartPos of every processed record
     aligned_bp = sum(r["mapping_query_span"] for r in recs)
-    return b"".join(lines), {"records": len(recs), "written": sum(1 for x in lines if x), "aligned_bp": aligned_bp, "status": status}
+    if per_row:
+        rows = [b""] * sum(1 for ln in paf.split(b"\n") if ln)
+        for r, ln in zip(recs, lines):
+            rows[r["row_index"]] = ln
+        lines = rows
+    return (lines if per_row else b"".join(lines)), {"records": len(recs), "written": sum(1 for x in lines if x), "aligned_bp": aligned_bp, "status": status}
 
 
 def wfmash(targets, queries, params: Params = None, device: int = 0):

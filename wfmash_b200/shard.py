@@ -59,3 +59,53 @@ def align_sharded(pairs, align_fn, identities=None, group=None):
     mine = partition(costs, world)[rank]
     res = align_fn([pairs[i] for i in mine]) if mine else []
     return gather_results(mine, res, len(pairs), group=group)
+
+
+def map_sharded(targets, queries, params=None, device=0, group=None, map_fn=None):
+    """Mapping phase over the ranks of a process group: every rank holds a replica of the index (C5 needs ~64 GB of
+    180 GB) and maps the queries of its partition — whole queries, because the chain / filter stage needs all fragments of a
+    query (computeMap.hpp:635-667) — balanced by length. The mapping PAF of all ranks is gathered on rank 0 in query order
+    (None elsewhere). The one-to-one mode needs every query's survivors for its final pass and is not sharded."""
+    import torch.distributed as dist
+    from wfmash_b200 import pipeline
+    if map_fn is None:
+        def map_fn(only):
+            return pipeline.map(targets, queries, params, device, only_queries=only).paf
+    P = params or pipeline.Params()
+    if P.filter is not None and P.filter.filter_mode == 2:
+        raise NotImplementedError("one-to-one filtering runs a final pass over all queries (computeMap.hpp:788-850): map on one rank")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = partition([float(len(s)) for _, s in queries], world)[rank]
+    paf = map_fn({queries[i][0] for i in mine}) if mine else b""
+    by_query = {}
+    for line in paf.split(b"\n"):
+        if line:
+            by_query.setdefault(line.split(b"\t", 1)[0].decode(), []).append(line)
+    res = gather_results(mine, [b"".join(l + b"\n" for l in by_query.get(queries[i][0], [])) for i in mine], len(queries), group=group)
+    return None if res is None else b"".join(res)
+
+
+def align_paf_sharded(mapping_paf, targets, queries, params=None, device=0, group=None, align_fn=None):
+    """Alignment phase over the ranks of a process group: the rows of the mapping PAF are partitioned by estimated cost
+    (record_cost from the row's spans and id:f: tag), every rank aligns its rows, rank 0 receives the records in row order
+    (the reference's single writer, computeAlignments.hpp:535-542). No collective touches the kernels."""
+    import torch.distributed as dist
+    from wfmash_b200 import pipeline
+    if align_fn is None:
+        def align_fn(text, per_row=True):
+            return pipeline.align(text, targets, queries, params, device, per_row=per_row)[0]
+    rows = [ln for ln in mapping_paf.split(b"\n") if ln]
+    costs = []
+    for ln in rows:
+        f = ln.split(b"\t")
+        try:
+            ident = float(f[12].rsplit(b":", 1)[-1])
+            costs.append(record_cost(int(f[8]) - int(f[7]), int(f[3]) - int(f[2]), ident))
+        except (IndexError, ValueError):
+            costs.append(1.0)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = partition(costs, world)[rank]
+    # one call per row keeps the row -> record association without parsing the output (a row may produce no record)
+    out = align_fn(b"".join(rows[i] + b"\n" for i in mine), per_row=True) if mine else []
+    res = gather_results(mine, out, len(rows), group=group)
+    return None if res is None else b"".join(res)

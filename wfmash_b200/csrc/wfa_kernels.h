@@ -50,6 +50,9 @@
 #endif
 #endif
 
+#ifndef WFB_NARROW_SCALAR
+#define WFB_NARROW_SCALAR 0
+#endif
 #define WFB_OFFSET_NULL (INT32_MIN / 2) /* wavefront_offset.h:44 */
 #define WFB_RMAX 40                     /* max ring slots = max_score_scope + 1 */
 #define WFB_FALLBACK_MIN_SCORE 250      /* wavefront_bialign.c:52 */
@@ -377,7 +380,11 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
     red_end[par] = cend == WFB_M ? (VM) : cend == WFB_I1 ? (VI1) : cend == WFB_I2 ? (VI2) : cend == WFB_D1 ? (VD1) : (VD2);
 
   const int kalign = alloc.kalign;
-  const bool vec_ok = kalign >= 0;
+  /* A narrow wavefront leaves most threads idle, and the step then lasts as long as ONE thread's chain of four dependent cells
+   * (each with its own extension). With at most WFB_NARROW_SCALAR diagonals per thread the one-diagonal-per-thread path below
+   * is the shorter critical path (profiles/r01_phase_timers_v6.log: steps of width <= 128 cost 9.5 k cycles, 8 k of them in a
+   * single thread's group). */
+  const bool vec_ok = kalign >= 0 && !(WFB_NARROW_SCALAR > 0 && (hi - lo + 1) <= WFB_NARROW_SCALAR * nt);
   if (vec_ok) {
     /* groups of 4 diagonals whose cells are 16-byte aligned in every row: 128-bit loads / stores, range
      * checks once per group; ragged groups at the ends of any input take the scalar path */

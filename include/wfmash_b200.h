@@ -645,6 +645,42 @@ int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_params_t* para
 
 void wfb_free_text(char* text);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8 f4 (second half): the reference's on-disk index (`-W` writes it, `-I` reads it; Sketch::writeIndex / readIndex,
+ * src/map/include/winSketch.hpp:554-979): one or more subsets, each = header (magic 0xDEADBEEFCAFEBABE, batch index /
+ * count, index_by_size, target names, the SequenceIdManager's name -> id map + next id, sequenceIds.hpp:102-115),
+ * parameters (windowLength i64, sketchSize i32, kmerSize i32), minmerIndex (count + 32-byte MinmerInfo records) and
+ * minmerPosLookupIndex (count; per hash: key, count, 24-byte IntervalPoint records). Files written here load in
+ * `wfmash -I`, and files written by `wfmash -W` load here.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { /* an index in host memory, in the layout wfb_index_export fills */
+  wfb_minmer_t* minmers;  int64_t n_minmers;   /* minmerIndex, reference order                                  */
+  uint64_t* uhash;        int64_t n_uniq;      /* distinct hashes, ascending                                    */
+  uint32_t* ustart;       uint32_t* ucount;    /* points[ustart[i] .. ustart[i] + ucount[i]) belong to uhash[i] */
+  uint64_t* points;       int64_t n_points;    /* seqId << 41 | pos << 1 | (OPEN ? 1 : 0), reference order per hash */
+} wfb_index_view_t;
+
+typedef struct {
+  uint64_t batch_idx, total_batches; /* subset number / count (1 subset unless -b splits the targets)            */
+  int64_t index_by_size;             /* param.index_by_size                                                        */
+  int64_t window_length; int32_t sketch_size, kmer_size;
+  int32_t n_targets, n_ids, next_id, reserved_;
+  char* target_names;                /* n_targets names, '\n' separated (malloc'ed by the reader)                */
+  char* id_names;                    /* n_ids names of the id map, '\n' separated, ids in id_values               */
+  int32_t* id_values;
+} wfb_index_file_header_t;
+
+/* Appends (append != 0) or writes one subset. The header's names / ids describe the SequenceIdManager of the run
+ * (target_names = the subset's targets; id_names / id_values = every known sequence). */
+int wfb_index_file_write(const char* path, int32_t append, const wfb_index_file_header_t* header, const wfb_index_view_t* index);
+/* Reads the subset that starts at *offset (0 = first) and advances *offset past it. header and index receive malloc'ed
+ * arrays: release them with wfb_index_file_release. WFB_EINVAL on a bad magic number / truncated file. */
+int wfb_index_file_read(const char* path, int64_t* offset, wfb_index_file_header_t* header, wfb_index_view_t* index);
+void wfb_index_file_release(wfb_index_file_header_t* header, wfb_index_view_t* index);
+/* Uploads an index held in host memory (read from a file, or exported from another index) and builds the device lookup
+ * table: the result maps exactly like an index built from the sequences. */
+wfb_index_t* wfb_index_import(int device, const wfb_index_params_t* params, const wfb_index_view_t* index);
+
 #ifdef __cplusplus
 }
 #endif

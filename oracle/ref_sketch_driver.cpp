@@ -24,24 +24,27 @@ extern "C" {
 struct ref_sketch {
   skch::SequenceIdManager* ids;
   skch::Sketch* sk;
+  std::vector<std::string> targets;
 };
+
+static void write_fasta(const char* fasta_path, const char* const* names, const char* const* seqs, const int64_t* lens, int32_t n) {
+  std::ofstream fa(fasta_path), fai(std::string(fasta_path) + ".fai");
+  int64_t off = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    const std::string head = std::string(">") + names[i] + "\n";
+    fa << head;
+    off += (int64_t)head.size();
+    fa.write(seqs[i], lens[i]);
+    fa << "\n";
+    fai << names[i] << "\t" << lens[i] << "\t" << off << "\t" << (lens[i] > 0 ? lens[i] : 1) << "\t" << (lens[i] > 0 ? lens[i] : 1) + 1 << "\n";
+    off += lens[i] + 1;
+  }
+}
 
 /* names[i] / seqs[i] / lens[i]: target sequences in file order (ids 0..n-1). Returns NULL on failure. */
 void* ref_sketch_build(const char* fasta_path, const char* const* names, const char* const* seqs, const int64_t* lens, int32_t n, int32_t kmer_size,
                        int64_t window_length, int32_t sketch_size, int32_t threads, double max_kmer_freq, const char* prefix_delim) {
-  {
-    std::ofstream fa(fasta_path), fai(std::string(fasta_path) + ".fai");
-    int64_t off = 0;
-    for (int32_t i = 0; i < n; ++i) {
-      const std::string head = std::string(">") + names[i] + "\n";
-      fa << head;
-      off += (int64_t)head.size();
-      fa.write(seqs[i], lens[i]);
-      fa << "\n";
-      fai << names[i] << "\t" << lens[i] << "\t" << off << "\t" << (lens[i] > 0 ? lens[i] : 1) << "\t" << (lens[i] > 0 ? lens[i] : 1) + 1 << "\n";
-      off += lens[i] + 1;
-    }
-  }
+  write_fasta(fasta_path, names, seqs, lens, n);
   skch::Parameters p;
   p.kmerSize = kmer_size; p.windowLength = window_length; p.sketchSize = sketch_size; p.threads = threads; p.max_kmer_freq = max_kmer_freq;
   p.refSequences = {fasta_path}; p.querySequences = {fasta_path}; p.alphabetSize = 4; p.use_progress_bar = false; p.hgNumerator = 1.0;
@@ -49,8 +52,32 @@ void* ref_sketch_build(const char* fasta_path, const char* const* names, const c
   p.use_streaming_minhash = false; /* the CLI sets it from a flag that defaults to off (parse_args.hpp:177): windowed addMinmers */
   ref_sketch* h = new ref_sketch;
   h->ids = new skch::SequenceIdManager({fasta_path}, {fasta_path}, {}, {}, std::string(prefix_delim ? prefix_delim : ""));
-  std::vector<std::string> targets(names, names + n);
-  h->sk = new skch::Sketch(p, *h->ids, targets);
+  h->targets.assign(names, names + n);
+  h->sk = new skch::Sketch(p, *h->ids, h->targets);
+  return h;
+}
+
+/* Sketch::writeIndex (winSketch.hpp:616-635): the `-W` file of this index */
+void ref_sketch_write_index(void* hv, const char* index_path) {
+  ref_sketch* h = (ref_sketch*)hv;
+  h->sk->writeIndex(h->targets, index_path, false, 0, 1);
+}
+
+/* Sketch(param, idManager, targets, &indexStream) = Sketch::readIndex (winSketch.hpp:840-866): the `-I` path. The FASTA + .fai
+ * are only needed by the SequenceIdManager. */
+void* ref_sketch_read_index(const char* fasta_path, const char* index_path, const char* const* names, const char* const* seqs, const int64_t* lens,
+                            int32_t n, int32_t kmer_size, int64_t window_length, int32_t sketch_size, const char* prefix_delim) {
+  write_fasta(fasta_path, names, seqs, lens, n);
+  skch::Parameters p;
+  p.kmerSize = kmer_size; p.windowLength = window_length; p.sketchSize = sketch_size; p.threads = 1; p.max_kmer_freq = 0.0002;
+  p.refSequences = {fasta_path}; p.alphabetSize = 4; p.use_progress_bar = false; p.hgNumerator = 1.0; p.prefix_delim = prefix_delim && prefix_delim[0] ? prefix_delim[0] : '\0';
+  p.percentageIdentity = 0.9f; p.use_streaming_minhash = false;
+  ref_sketch* h = new ref_sketch;
+  h->ids = new skch::SequenceIdManager({}, {fasta_path}, {}, {}, std::string(prefix_delim ? prefix_delim : ""));
+  h->targets.assign(names, names + n);
+  std::ifstream in(index_path, std::ios::binary);
+  if (!in) { delete h->ids; delete h; return nullptr; }
+  h->sk = new skch::Sketch(p, *h->ids, h->targets, &in);
   return h;
 }
 

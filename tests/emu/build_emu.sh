@@ -14,6 +14,6 @@ g++ -O2 -g -std=c++17 -DWFB_EMU $EMU_DEFS -fPIC -Wall -Wno-unused-function -Wno-
     -Wno-unknown-pragmas -Wno-unused-but-set-variable -Iinclude \
     -x c++ wfmash_b200/csrc/wfa_host.cu -x c++ wfmash_b200/csrc/sketch.cu -x c++ wfmash_b200/csrc/minmer_host.cu \
     -x c++ wfmash_b200/csrc/epilogue.cu -x c++ wfmash_b200/csrc/index_host.cu -x c++ wfmash_b200/csrc/chain_host.cu \
-    -x c++ wfmash_b200/csrc/filter_host.cu -x c++ wfmash_b200/csrc/stats_host.cu -x c++ wfmash_b200/csrc/ani_host.cu -x c++ wfmash_b200/csrc/phases_host.cu -shared -o tests/emu/_build/libwfb_emu.so
+    -x c++ wfmash_b200/csrc/filter_host.cu -x c++ wfmash_b200/csrc/stats_host.cu -x c++ wfmash_b200/csrc/ani_host.cu -x c++ wfmash_b200/csrc/phases_host.cu -x c++ wfmash_b200/csrc/index_file_host.cu -shared -o tests/emu/_build/libwfb_emu.so
 printf '%s' "$EMU_DEFS" > tests/emu/_build/defs
 echo tests/emu/_build/libwfb_emu.so

@@ -533,3 +533,36 @@ def test_pipeline_auto_identity_then_map(wb):
     assert m.stats["mappings"] >= 6 and m.paf.count(b"\n") == m.stats["mappings"]
     mp_c, mst = wb.map_phase(seqs, seqs, wb.MapPhaseParams())   # percentage_identity <= 0: the C phase estimates it itself
     assert abs(mst.percentage_identity - P.percentage_identity) < 1e-6 and mst.sketch_size == P.sketch_size and mp_c == m.paf
+
+
+def test_index_import_and_file_round_trip_map_identically(wb, tmp_path):
+    # wfb_index_import of an exported index, and of the same index after a trip through the reference's file
+    # format, must map exactly like the index built from the sequences
+    import numpy as np
+    from tests import maputil
+    seqs, ids, groups = maputil.l2_case(seed=41)
+    k, w, s = 15, 1000, 29
+    ix = wb.Index(seqs, ids, k, w, s, index_threads=2)
+    blob = b"".join(seqs)
+    offs = np.cumsum([0] + [len(x) for x in seqs])
+    frags = np.array([(int(offs[q]) + j * w, w, ids[q]) for q in range(len(seqs)) for j in range(len(seqs[q]) // w)], dtype=wb.FRAG_DTYPE)
+    fqs = np.array([(ids[q], groups[q]) for q in range(len(seqs)) for j in range(len(seqs[q]) // w)], dtype=wb.FRAG_QUERY_DTYPE)
+    cut, s1 = wb.sketch_cutoffs(s, k), wb.stage1_min_hits(k, s)
+    grp = np.array(groups, dtype=np.int32)
+
+    def run(index):
+        r = index.map_fragments(blob, frags, fqs, 3, cut, grp, stage1_min_hits=s1, l2_min_shared=wb.l2_min_shared_relaxed(0.85, k, s))
+        return r["mappings"].tobytes(), r["offset"].tobytes()
+
+    base = run(ix)
+    exported = ix.export()
+    assert len(exported[0]) > 1000
+    ix2 = wb.Index.from_export(exported, k, w, s)
+    assert run(ix2) == base
+    path = str(tmp_path / "index.bin")
+    wb.index_file_write(path, exported, k, w, s, [f"s{i}" for i in ids], {f"s{i}": i for i in ids})
+    hdr, data, _ = wb.index_file_read(path)
+    ix3 = wb.Index.from_export(data, hdr["kmer_size"], hdr["window_length"], hdr["sketch_size"])
+    assert run(ix3) == base and all((a == b).all() for a, b in zip(ix3.export()[1:], exported[1:]))
+    for i in (ix, ix2, ix3):
+        i.close()

@@ -116,3 +116,68 @@ def test_oracle_index_matches_compiled_reference_sketch_live(oracle):
         # the host mirror of SequenceIdManager::buildRefGroups (sequenceIds.hpp:284-330)
         mirror = pipeline.SequenceIds([(n, b"") for n in names], [], "#")
         assert mirror.group == r_groups
+
+
+def _flat_to_export(mi, hs, st, pts):
+    """The driver's flat layout -> the Index.export() layout (packed points seqId << 41 | pos << 1 | open)."""
+    import wfmash_b200 as wb
+    m = np.zeros(len(mi), dtype=wb.MINMER_DTYPE)
+    for f in ("hash", "wpos", "wpos_end", "seqId", "strand"):
+        m[f] = mi[f]
+    packed = (pts["seqId"].astype(np.uint64) << np.uint64(41)) | (pts["pos"].astype(np.uint64) << np.uint64(1)) | (pts["side"] == 1).astype(np.uint64)
+    return m, hs.astype(np.uint64), st[:-1].astype(np.uint32), np.diff(st).astype(np.uint32), packed
+
+
+def _same_export(a, b):
+    return (all((a[0][f] == b[0][f]).all() for f in ("hash", "wpos", "wpos_end", "seqId", "strand")) and len(a[0]) == len(b[0])
+            and all(len(x) == len(y) and (x == y).all() for x, y in zip(a[1:], b[1:])))
+
+
+@pytest.mark.ref
+def test_index_file_is_interchangeable_with_the_reference(oracle, tmp_path):
+    """SURVEY 8 f4: a `-W` file written by the reference's UNMODIFIED Sketch::writeIndex loads here, and a file written here
+    loads in its Sketch::readIndex (both compiled in place in libsketchref.so) — same minmerIndex and per-hash postings."""
+    import wfmash_b200 as wb
+    R = util.load_ref("libsketchref.so")
+    if R is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    R.ref_sketch_build.restype = ctypes.c_void_p
+    R.ref_sketch_read_index.restype = ctypes.c_void_p
+    seed, k, w, s, F, threads = CASES[0]
+    seqs, ids, groups = case_seqs(seed)
+    names = names_of(groups)
+    n = len(seqs)
+    cn = (ctypes.c_char_p * n)(*[x.encode() for x in names]); cs = (ctypes.c_char_p * n)(*seqs); cl = (ctypes.c_int64 * n)(*[len(x) for x in seqs])
+    fa = str(tmp_path / "t.fa").encode()
+    h = ctypes.c_void_p(R.ref_sketch_build(fa, cn, cs, cl, n, k, ctypes.c_int64(w), s, 1, ctypes.c_double(F), b"#"))
+    ref_file = str(tmp_path / "ref.idx")
+    R.ref_sketch_write_index(h, ref_file.encode())
+    R.ref_sketch_free(h)
+    # reference -> here
+    hdr, data, nxt = wb.index_file_read(ref_file)
+    assert (hdr["kmer_size"], hdr["window_length"], hdr["sketch_size"], hdr["batch_idx"], hdr["total_batches"]) == (k, w, s, 0, 1)
+    assert hdr["target_names"] == names and hdr["id_map"] == {nm: i for i, nm in enumerate(names)} and hdr["next_id"] == n
+    assert nxt == os.path.getsize(ref_file)
+    want = _flat_to_export(*oracle_flat(oracle, seqs, ids, k, w, s, F, 1))   # = the reference's index (test above), threads = 1: no reordering
+    assert _same_export(data, want)
+    # here -> reference
+    our_file = str(tmp_path / "ours.idx")
+    wb.index_file_write(our_file, data, k, w, s, names, hdr["id_map"])
+    assert os.path.getsize(our_file) == os.path.getsize(ref_file)
+    h2 = ctypes.c_void_p(R.ref_sketch_read_index(fa, our_file.encode(), cn, cs, cl, n, k, ctypes.c_int64(w), s, b"#"))
+    assert h2.value
+    nm_, nh_, np_ = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    R.ref_sketch_sizes(h2, ctypes.byref(nm_), ctypes.byref(nh_), ctypes.byref(np_))
+    mi = np.zeros(nm_.value, dtype=maputil.MDT); hs = np.zeros(nh_.value, dtype=np.uint64); st = np.zeros(nh_.value + 1, dtype=np.int64); pts = np.zeros(np_.value, dtype=PT)
+    R.ref_sketch_export(h2, maputil.vp(mi), maputil.vp(hs), maputil.vp(st), maputil.vp(pts))
+    R.ref_sketch_free(h2)
+    assert _same_export(_flat_to_export(mi, hs, st, pts), want)
+    # two subsets in one file (-b): append, then read them back one after the other
+    wb.index_file_write(our_file, data, k, w, s, names[:3], hdr["id_map"], append=True, batch_idx=1, total_batches=2)
+    h1, d1, o1 = wb.index_file_read(our_file)
+    h2_, d2, o2 = wb.index_file_read(our_file, o1)
+    assert o2 == os.path.getsize(our_file) and (h2_["batch_idx"], h2_["total_batches"], h2_["target_names"]) == (1, 2, names[:3]) and _same_export(d1, d2)
+    with pytest.raises(wb.WfbError):
+        wb.index_file_read(our_file, 8)          # not a subset boundary: bad magic number
+    with pytest.raises(wb.WfbError):
+        wb.index_file_read(str(tmp_path / "missing.idx"))

@@ -828,3 +828,82 @@ def align_phase(aligner: "Aligner", mapping_paf: bytes, targets, queries, window
     L.wfb_free_text.argtypes = [ctypes.c_void_p]
     L.wfb_free_text(txt)
     return out, st
+
+
+# ---- SURVEY 8 f4 (second half): the reference's index file (-W / -I) ----------------------------------------------------
+class _IndexView(ctypes.Structure):
+    _fields_ = [("minmers", ctypes.c_void_p), ("n_minmers", ctypes.c_int64), ("uhash", ctypes.c_void_p), ("n_uniq", ctypes.c_int64),
+                ("ustart", ctypes.c_void_p), ("ucount", ctypes.c_void_p), ("points", ctypes.c_void_p), ("n_points", ctypes.c_int64)]
+
+
+class _IndexFileHeader(ctypes.Structure):
+    _fields_ = [("batch_idx", ctypes.c_uint64), ("total_batches", ctypes.c_uint64), ("index_by_size", ctypes.c_int64), ("window_length", ctypes.c_int64),
+                ("sketch_size", ctypes.c_int32), ("kmer_size", ctypes.c_int32), ("n_targets", ctypes.c_int32), ("n_ids", ctypes.c_int32),
+                ("next_id", ctypes.c_int32), ("reserved_", ctypes.c_int32), ("target_names", ctypes.c_void_p), ("id_names", ctypes.c_void_p),
+                ("id_values", ctypes.c_void_p)]
+
+
+def _view_of(minmers, uhash, ustart, ucount, points):
+    mi = np.ascontiguousarray(minmers, dtype=MINMER_DTYPE); uh = np.ascontiguousarray(uhash, dtype=np.uint64)
+    us = np.ascontiguousarray(ustart, dtype=np.uint32); uc = np.ascontiguousarray(ucount, dtype=np.uint32); pt = np.ascontiguousarray(points, dtype=np.uint64)
+    return _IndexView(mi.ctypes.data, len(mi), uh.ctypes.data, len(uh), us.ctypes.data, uc.ctypes.data, pt.ctypes.data, len(pt)), (mi, uh, us, uc, pt)
+
+
+def index_file_write(path: str, exported, kmer_size: int, window_length: int, sketch_size: int, target_names, id_map, append: bool = False,
+                     batch_idx: int = 0, total_batches: int = 1, index_by_size: int = 2**63 - 1):
+    """Sketch::writeIndex (winSketch.hpp:616-659): one subset of a `-W` file. exported = Index.export(); id_map = {name: id}."""
+    view, keep = _view_of(*exported)
+    tn = ("\n".join(target_names)).encode()
+    names = list(id_map)
+    idn = ("\n".join(names)).encode()
+    idv = np.array([id_map[n] for n in names], dtype=np.int32)
+    tb, ib = ctypes.create_string_buffer(tn), ctypes.create_string_buffer(idn)
+    h = _IndexFileHeader(batch_idx, total_batches, index_by_size, window_length, sketch_size, kmer_size, len(target_names), len(names),
+                         (max(id_map.values()) + 1) if id_map else 0, 0, ctypes.addressof(tb), ctypes.addressof(ib), idv.ctypes.data)
+    rc = lib().wfb_index_file_write(path.encode(), int(append), ctypes.byref(h), ctypes.byref(view))
+    if rc != 0:
+        raise _err(rc)
+
+
+def index_file_read(path: str, offset: int = 0):
+    """Sketch::readIndex (winSketch.hpp:840-979) for the subset at `offset` -> (header dict, (minmers, uhash, ustart, ucount, points), next offset)."""
+    L = lib()
+    h, v, off = _IndexFileHeader(), _IndexView(), ctypes.c_int64(offset)
+    rc = L.wfb_index_file_read(path.encode(), ctypes.byref(off), ctypes.byref(h), ctypes.byref(v))
+    if rc != 0:
+        raise _err(rc)
+    try:
+        def arr(ptr, n, dt):
+            return np.frombuffer(ctypes.string_at(ptr, n * np.dtype(dt).itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+        names = ctypes.string_at(h.id_names).decode().split("\n")[:-1] if h.n_ids else []
+        ids = arr(h.id_values, h.n_ids, np.int32)
+        hdr = {"batch_idx": h.batch_idx, "total_batches": h.total_batches, "index_by_size": h.index_by_size, "window_length": h.window_length,
+               "sketch_size": h.sketch_size, "kmer_size": h.kmer_size, "next_id": h.next_id,
+               "target_names": ctypes.string_at(h.target_names).decode().split("\n")[:-1] if h.n_targets else [],
+               "id_map": {n: int(i) for n, i in zip(names, ids)}}
+        data = (arr(v.minmers, v.n_minmers, MINMER_DTYPE), arr(v.uhash, v.n_uniq, np.uint64), arr(v.ustart, v.n_uniq, np.uint32),
+                arr(v.ucount, v.n_uniq, np.uint32), arr(v.points, v.n_points, np.uint64))
+    finally:
+        L.wfb_index_file_release(ctypes.byref(h), ctypes.byref(v))
+    return hdr, data, off.value
+
+
+def _index_import(cls, exported, kmer_size, window_size, sketch_size, device=0):
+    """wfb_index_import: a device index from host arrays in the Index.export() layout (e.g. index_file_read's)."""
+    L = lib()
+    L.wfb_index_import.restype = ctypes.c_void_p
+    L.wfb_index_free.argtypes = [ctypes.c_void_p]
+    view, keep = _view_of(*exported)
+    self = cls.__new__(cls)
+    self._L = L
+    self.k, self.w, self.s = kmer_size, window_size, sketch_size
+    self.stats = IndexStats()
+    self.stats.kept_minmers, self.stats.unique_hashes, self.stats.interval_points = len(keep[0]), len(keep[1]), len(keep[4])
+    prm = _IndexParams(kmer_size, window_size, sketch_size, 1, 0.0002)
+    self._h = L.wfb_index_import(device, ctypes.byref(prm), ctypes.byref(view))
+    if not self._h:
+        raise WfbError(L.wfb_last_error().decode())
+    return self
+
+
+Index.from_export = classmethod(_index_import)

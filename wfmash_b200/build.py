@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("wfa_host.cu", "sketch.cu", "minmer_host.cu", "index_host.cu", "epilogue.cu", "chain_host.cu", "filter_host.cu", "stats_host.cu", "ani_host.cu", "phases_host.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("wfa_host.cu", "sketch.cu", "minmer_host.cu", "index_host.cu", "epilogue.cu", "chain_host.cu", "filter_host.cu", "stats_host.cu", "ani_host.cu", "phases_host.cu", "index_file_host.cu")]
 HDR = [os.path.join(HERE, "csrc", f) for f in ("wfa_kernels.h", "wfb_rt.h", "minmer_kernels.h", "sketch_kernels.h", "index_kernels.h", "l2_kernels.h", "ani_kernels.h")] + [os.path.join(ROOT, "include", "wfmash_b200.h")]
 OUT = os.path.join(HERE, "libwfmash_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

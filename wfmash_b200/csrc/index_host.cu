@@ -276,6 +276,66 @@ extern "C" wfb_index_t* wfb_index_build(int device, const wfb_index_params_t* pr
   return ix;
 }
 
+/* An index that already exists in host memory (wfb_index_file_read, or wfb_index_export of another index): upload the
+ * kept minmers, the per-hash postings and build the open-addressing table (step 7 of wfb_index_build). */
+extern "C" wfb_index_t* wfb_index_import(int device, const wfb_index_params_t* prm, const wfb_index_view_t* v) {
+  if (!prm || !v || prm->kmer_size < 1 || prm->window_size < 1 || prm->sketch_size < 1 || v->n_minmers <= 0 || v->n_uniq <= 0 || v->n_points <= 0 ||
+      !v->minmers || !v->uhash || !v->ustart || !v->ucount || !v->points) {
+    wfb_set_last_error_("bad argument (an empty index cannot be imported: the reference exits on an empty sketch, winSketch.hpp:451-456)");
+    return nullptr;
+  }
+#ifndef WFB_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    wfb_set_last_error_("no CUDA device (this library has no CPU path)");
+    return nullptr;
+  }
+  wfb_index* ix = new wfb_index();
+  ix->device = device;
+  ix->params = *prm;
+  ix->n_minmers_all = ix->n_minmers = v->n_minmers;
+  ix->n_points = v->n_points;
+  ix->n_uniq = v->n_uniq;
+  int rc = WFB_OK;
+  int* d_fail = nullptr;
+  {
+    const long long nuk = v->n_uniq;
+    const int B = 256, G = 148 * 8;
+    IX_CHECK(cudaSetDevice(device));
+    IX_CHECK(cudaMalloc(&ix->d_minmers, sizeof(wfb_minmer_t) * (size_t)v->n_minmers));
+    IX_CHECK(cudaMemcpy(ix->d_minmers, v->minmers, sizeof(wfb_minmer_t) * (size_t)v->n_minmers, cudaMemcpyHostToDevice));
+    IX_CHECK(cudaMalloc(&ix->d_points, 8 * (size_t)v->n_points));
+    IX_CHECK(cudaMemcpy(ix->d_points, v->points, 8 * (size_t)v->n_points, cudaMemcpyHostToDevice));
+    IX_CHECK(cudaMalloc(&ix->d_uhash, 8 * (size_t)nuk));
+    IX_CHECK(cudaMalloc(&ix->d_ustart, 4 * (size_t)nuk));
+    IX_CHECK(cudaMalloc(&ix->d_ucount, 4 * (size_t)nuk));
+    IX_CHECK(cudaMemcpy(ix->d_uhash, v->uhash, 8 * (size_t)nuk, cudaMemcpyHostToDevice));
+    IX_CHECK(cudaMemcpy(ix->d_ustart, v->ustart, 4 * (size_t)nuk, cudaMemcpyHostToDevice));
+    IX_CHECK(cudaMemcpy(ix->d_ucount, v->ucount, 4 * (size_t)nuk, cudaMemcpyHostToDevice));
+    IX_CHECK(cudaMalloc(&d_fail, 4));
+    IX_CHECK(cudaMemset(d_fail, 0, 4));
+    long long nb = 1;
+    while (nb * IX_BUCKET < 2 * nuk) nb <<= 1;
+    ix->n_buckets = nb;
+    IX_CHECK(cudaMalloc(&ix->d_table, sizeof(IxSlot) * (size_t)nb * IX_BUCKET));
+    IX_LAUNCH(ix_fill_kernel, G, B, 0, (unsigned long long*)ix->d_table, nb * IX_BUCKET * 2, (unsigned long long)IX_EMPTY);
+    IX_LAUNCH(ix_insert_kernel, G, B, 0, ix->d_table, nb, (const uint64_t*)ix->d_uhash, ix->d_ustart, ix->d_ucount, nuk, d_fail);
+    int fail = 0;
+    IX_CHECK(cudaMemcpy(&fail, d_fail, 4, cudaMemcpyDeviceToHost));
+    if (fail) { wfb_set_last_error_("hash table insert failed"); rc = WFB_ECUDA; goto done; }
+  }
+done:
+  cudaFree(d_fail);
+  if (rc != WFB_OK) { wfb_index_free(ix); return nullptr; }
+  return ix;
+#else
+  (void)device;
+  wfb_set_last_error_("index import is not part of the host emulation");
+  return nullptr;
+#endif
+}
+
 extern "C" int wfb_index_export(const wfb_index_t* ix, wfb_minmer_t* minmers, int64_t minmers_cap, uint64_t* uhash, uint32_t* ustart,
                                 uint32_t* ucount, int64_t uniq_cap, uint64_t* points, int64_t points_cap) {
   if (!ix) { wfb_set_last_error_("index == NULL"); return WFB_EINVAL; }

@@ -199,7 +199,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   MM_CHECK(cudaMalloc(&d_seq, (size_t)total));
   MM_CHECK(cudaMalloc(&d_seqs, sizeof(MmSeq) * ns));
   MM_CHECK(cudaMalloc(&d_chunks, sizeof(MmChunk) * (size_t)nchunks));
-  MM_CHECK(cudaMalloc(&d_scratch, (size_t)scratch_stride * (size_t)nchunks));
+  MM_CHECK(cudaMalloc(&d_scratch, (size_t)scratch_stride * (((size_t)nchunks + MM_LANES - 1) / MM_LANES * MM_LANES))); /* whole warps: the slabs are interleaved */
   MM_CHECK(cudaMalloc(&d_rec, sizeof(MmRecord) * (size_t)rec_cap));
   MM_CHECK(cudaMalloc(&d_end, sizeof(MmEndEnt) * (size_t)nchunks * s));
   MM_CHECK(cudaMalloc(&d_endcount, sizeof(int) * (size_t)nchunks));

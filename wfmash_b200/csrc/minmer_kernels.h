@@ -120,9 +120,61 @@ WFB_DEV void mm_hash_pair(const uint8_t* s, int k, uint64_t& hf, uint64_t& hb) {
   hb = mm_murmur3_lo64(r[0], r[1], r[2], r[3], k);
 }
 
-/* ---- per-thread containers in global scratch ---- */
+/* The forward and reverse-complement k-mers of the current position as eight 64-bit byte-shift registers: a position costs one
+ * new base and a few shifts instead of re-packing 2k bytes (and scalars stay in registers where f[j >> 3] did not). */
+struct MmRoll {
+  uint64_t f0, f1, f2, f3, r0, r1, r2, r3;
+};
+WFB_DEV void mm_roll_init(MmRoll& R, const uint8_t* s, int k) {
+  R.f0 = R.f1 = R.f2 = R.f3 = R.r0 = R.r1 = R.r2 = R.r3 = 0;
+#define MM_INIT_WORD(FW, RW, WI)                                              \
+  _Pragma("unroll") for (int jj = 0; jj < 8; ++jj) {                          \
+    const int j = (WI) * 8 + jj;                                              \
+    if (j < k) {                                                              \
+      FW |= (uint64_t)s[j] << (jj * 8);                                       \
+      RW |= (uint64_t)mm_comp(s[k - 1 - j]) << (jj * 8);                      \
+    }                                                                         \
+  }
+  MM_INIT_WORD(R.f0, R.r0, 0)
+  MM_INIT_WORD(R.f1, R.r1, 1)
+  MM_INIT_WORD(R.f2, R.r2, 2)
+  MM_INIT_WORD(R.f3, R.r3, 3)
+#undef MM_INIT_WORD
+}
+WFB_DEV void mm_roll_step(MmRoll& R, uint8_t in, int k) { /* k-mer at i -> k-mer at i + 1; in = s[i + k] */
+  const int top = k - 1, topw = top >> 3, clrw = k >> 3;
+  const uint64_t ins = (uint64_t)in << ((top & 7) * 8);
+  const uint64_t clr = k < 32 ? ~(0xFFull << ((k & 7) * 8)) : ~0ULL;
+  R.f0 = (R.f0 >> 8) | (R.f1 << 56);
+  R.f1 = (R.f1 >> 8) | (R.f2 << 56);
+  R.f2 = (R.f2 >> 8) | (R.f3 << 56);
+  R.f3 = R.f3 >> 8;
+  R.f0 |= topw == 0 ? ins : 0; R.f1 |= topw == 1 ? ins : 0; R.f2 |= topw == 2 ? ins : 0; R.f3 |= topw == 3 ? ins : 0;
+  R.r3 = (R.r3 << 8) | (R.r2 >> 56);
+  R.r2 = (R.r2 << 8) | (R.r1 >> 56);
+  R.r1 = (R.r1 << 8) | (R.r0 >> 56);
+  R.r0 = (R.r0 << 8) | (uint64_t)mm_comp(in);
+  R.r0 &= clrw == 0 ? clr : ~0ULL; R.r1 &= clrw == 1 ? clr : ~0ULL; R.r2 &= clrw == 2 ? clr : ~0ULL; R.r3 &= clrw == 3 ? clr : ~0ULL;
+}
+
+/* ---- per-thread containers in global scratch ----
+ * The 32 chunks of a warp share one slab and their containers are INTERLEAVED element by element: element i of lane l lives
+ * at slab[i * 32 + l]. The window deque advances in lockstep across the lanes (one k-mer in, one out per position), the top
+ * levels of the heaps and the first sortedWindow entries are touched by every lane at the same index, so those accesses
+ * coalesce into contiguous 512-byte (MmKmer) runs instead of 32 scattered sectors (ncu on the private-slab layout: 314 B
+ * of DRAM traffic per base against 7.2 algorithmic). The host emulation runs one chunk at a time: MM_LANES = 1. */
+#ifdef WFB_EMU
+#define MM_LANES 1
+#else
+#define MM_LANES 32
+#endif
+template <class T>
+struct MmArr {
+  T* p; /* this lane's element 0 */
+  WFB_DEV_MEMBER T& operator[](long long i) const { return p[i * MM_LANES]; }
+};
 struct MmHeap {
-  MmKmer* a;
+  MmArr<MmKmer> a;
   int n, cap;
 };
 WFB_DEV bool mm_less(const MmKmer& x, const MmKmer& y) { return x.hash < y.hash || (x.hash == y.hash && x.pos < y.pos); }
@@ -159,7 +211,7 @@ WFB_DEV void mm_heap_pop(MmHeap& h) { /* leaves the popped element readable in a
 }
 
 struct MmPool {
-  MmNode* nodes;
+  MmArr<MmNode> nodes;
   int free_head;
 };
 WFB_DEV int mm_pool_alloc(MmPool& p) {
@@ -186,7 +238,7 @@ WFB_DEV void mm_went_pop_front(MmPool& p, MmWent& e) {
 }
 WFB_DEV void mm_went_clear(MmPool& p, MmWent& e) { while (e.head >= 0) mm_went_pop_front(p, e); }
 
-WFB_DEV int mm_lower_bound(const MmWent* W, int wn, uint64_t h) {
+WFB_DEV int mm_lower_bound(const MmArr<MmWent>& W, int wn, uint64_t h) {
   int lo = 0, hi = wn;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -201,7 +253,8 @@ struct MmParams {
   int qcap, heap_cap, pool_cap; /* per-thread capacities */
 };
 
-/* One thread = one chunk. scratch layout per thread: Q[qcap] | heap[heap_cap] | pool[pool_cap] | W[s+2]. */
+/* One thread = one chunk. scratch layout per WARP (scratch_stride bytes per chunk, MM_LANES chunks per slab):
+ * Q[qcap][lanes] | heap[heap_cap][lanes] | pool[pool_cap][lanes] | W[s+2][lanes]. */
 WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P,
            unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
            int* endcount, MmCounters* counters) {
@@ -213,15 +266,16 @@ WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmC
   const uint8_t* seq = seqbuf + sq.off;
   const long long len = sq.len;
   const int k = P.k, w = P.w, s = P.s;
-  unsigned char* sp = scratch_all + (long long)c * scratch_stride;
-  MmKmer* Q = (MmKmer*)sp;
+  const int lane = c % MM_LANES;
+  unsigned char* sp = scratch_all + (long long)(c / MM_LANES) * scratch_stride * MM_LANES;
+  const MmArr<MmKmer> Q{(MmKmer*)sp + lane};
   MmHeap H;
-  H.a = (MmKmer*)(sp + sizeof(MmKmer) * (size_t)P.qcap);
+  H.a = MmArr<MmKmer>{(MmKmer*)(sp + sizeof(MmKmer) * (size_t)P.qcap * MM_LANES) + lane};
   H.n = 0;
   H.cap = P.heap_cap;
   MmPool pool;
-  pool.nodes = (MmNode*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap));
-  MmWent* W = (MmWent*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) + sizeof(MmNode) * (size_t)P.pool_cap);
+  pool.nodes = MmArr<MmNode>{(MmNode*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) * MM_LANES) + lane};
+  const MmArr<MmWent> W{(MmWent*)(sp + (sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) + sizeof(MmNode) * (size_t)P.pool_cap) * MM_LANES) + lane};
   for (int i = 0; i < P.pool_cap; ++i) pool.nodes[i].next = (i + 1 < P.pool_cap) ? i + 1 : -1;
   pool.free_head = 0;
   int qh = 0, qn = 0, wn = 0;
@@ -246,6 +300,8 @@ WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmC
     }                                                                                                \
   }
   long long i = run_begin;
+  MmRoll roll;
+  if (run_begin < run_end) mm_roll_init(roll, seq + run_begin, k);
   for (; i < run_end; ++i) {
     const long long win = i + k - w; /* currentWindowId, :482 */
     if (H.n > 2 * w) { /* :485-495 */
@@ -254,8 +310,8 @@ WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmC
       H.n = m;
       for (int j = H.n / 2 - 1; j >= 0; --j) mm_heap_sift_down(H, j);
     }
-    uint64_t hf, hb;
-    mm_hash_pair(seq + i, k, hf, hb);
+    const uint64_t hf = mm_murmur3_lo64(roll.f0, roll.f1, roll.f2, roll.f3, k), hb = mm_murmur3_lo64(roll.r0, roll.r1, roll.r2, roll.r3, k);
+    if (i + 1 < run_end) mm_roll_step(roll, seq[i + k], k);
     const uint64_t cur = hf < hb ? hf : hb;
     const int cur_strand = hf < hb ? 1 : -1;
     /* leaving k-mer, :517-551 */

@@ -51,7 +51,7 @@
 #endif
 
 #ifndef WFB_NARROW_SCALAR
-#define WFB_NARROW_SCALAR 0
+#define WFB_NARROW_SCALAR 4 /* profiles/r01_sweep14_narrow_scalar.log: 0 -> 14.65, 1 -> 14.87, 2 -> 15.21, 4 -> 15.28, 8 -> 15.16, 16 -> 14.49 Mbp/s */
 #endif
 #define WFB_OFFSET_NULL (INT32_MIN / 2) /* wavefront_offset.h:44 */
 #define WFB_RMAX 40                     /* max ring slots = max_score_scope + 1 */
@@ -380,10 +380,11 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
     red_end[par] = cend == WFB_M ? (VM) : cend == WFB_I1 ? (VI1) : cend == WFB_I2 ? (VI2) : cend == WFB_D1 ? (VD1) : (VD2);
 
   const int kalign = alloc.kalign;
-  /* A narrow wavefront leaves most threads idle, and the step then lasts as long as ONE thread's chain of four dependent cells
-   * (each with its own extension). With at most WFB_NARROW_SCALAR diagonals per thread the one-diagonal-per-thread path below
-   * is the shorter critical path (profiles/r01_phase_timers_v6.log: steps of width <= 128 cost 9.5 k cycles, 8 k of them in a
-   * single thread's group). */
+  /* A step lasts as long as its busiest thread's chain of dependent cells (each with its own extension). The 4-diagonal groups
+   * give ceil(width / 4) threads four cells each and leave the others idle; below 4 diagonals per thread the one-diagonal path
+   * spreads the same cells over ALL threads (ceil(width / nt) cells each), which is the shorter critical path until the 128-bit
+   * row loads of the group path win (profiles/r01_phase_timers_v6.log: steps of width <= 1024 are 28 % of the CTA cycles, a
+   * step of width <= 128 costs 9.5 k cycles of which 8 k are one thread's group; A/B in profiles/r01_sweep14_narrow_scalar.log). */
   const bool vec_ok = kalign >= 0 && !(WFB_NARROW_SCALAR > 0 && (hi - lo + 1) <= WFB_NARROW_SCALAR * nt);
   if (vec_ok) {
     /* groups of 4 diagonals whose cells are 16-byte aligned in every row: 128-bit loads / stores, range

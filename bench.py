@@ -223,6 +223,29 @@ def record_path_section(al, recs, cores, with_cpu, cpu_seconds):
     return out
 
 
+def cpu_sketch_build(seqs, k, w, ssz, cores, bases):
+    """Sketch::Sketch (index build: thread-pool addMinmers + frequency cut-off + minmerPosLookupIndex) of the UNMODIFIED reference
+    on the host cores, through oracle/ref_sketch_driver.cpp. Checker / baseline only."""
+    import tempfile
+    ref = os.path.join(ROOT, "oracle", "_ref", "libsketchref.so")
+    if not os.path.exists(ref):
+        return {"unavailable": "oracle/_ref/libsketchref.so not built"}
+    R = ctypes.CDLL(ref)
+    R.ref_sketch_build.restype = ctypes.c_void_p
+    n = len(seqs)
+    names = (ctypes.c_char_p * n)(*[f"g{i}#1#c".encode() for i in range(n)])
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.perf_counter()
+        h = R.ref_sketch_build(os.path.join(d, "t.fa").encode(), names, (ctypes.c_char_p * n)(*seqs), (ctypes.c_int64 * n)(*[len(x) for x in seqs]), n, k,
+                               ctypes.c_int64(w), ssz, cores, ctypes.c_double(0.0002), b"#")
+        dt = time.perf_counter() - t0
+        nm, nh, npt = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        R.ref_sketch_sizes(ctypes.c_void_p(h), ctypes.byref(nm), ctypes.byref(nh), ctypes.byref(npt))
+        R.ref_sketch_free(ctypes.c_void_p(h))
+    return {"value": bases / dt / 1e6, "unit": "Mbp/s", "kind": "reference", "cores": cores, "kept_minmers": int(nm.value), "unique_hashes": int(nh.value),
+            "sample": f"all {n} sequences ({bases} bp) incl. writing the FASTA the reference reads, {dt:.2f} s wall"}
+
+
 def map_path_section(dev, cores, with_cpu):
     """Path 1 (MashMap 3.5 sketch / index / L1) on a C3-shaped synthetic pangenome slice: 8 haplotypes x 3 Mbp at
     3 % divergence, -k15 -w1k, s=29 (scerevisiae8 parameters). Reported beside the headline."""
@@ -344,6 +367,10 @@ def map_path_section(dev, cores, with_cpu):
             dtc = time.perf_counter() - t0
             out["index"]["cpu_addMinmers"] = {"value": bases / dtc / 1e6, "unit": "Mbp/s", "kind": kind, "cores": min(cores, len(seqs)),
                                               "sample": f"all {len(seqs)} sequences ({bases} bp), {dtc:.2f} s wall"}
+        try:  # the reference's whole index build (unmodified skch::Sketch compiled in place, oracle/_ref/libsketchref.so)
+            out["index"]["cpu_sketch_build"] = cpu_sketch_build(seqs, k, w, ssz, cores, bases)
+        except Exception as e:
+            out["index"]["cpu_sketch_build"] = {"error": str(e)}
     return out
 
 

@@ -247,3 +247,13 @@ def test_filter_edge_cases_match_compiled_reference_live():
         wb.filter_mappings_batch(wb.FilterParams(window_length=0), one, [0, 1], [QLEN], REF_LEN)
     with pytest.raises(wb.WfbError):
         wb.filter_mappings_batch(wb.FilterParams(skip_prefix=1), one, [0, 1], [QLEN], REF_LEN)     # skip_prefix needs the groups
+
+
+def test_phase_entry_points_validate_arguments_before_touching_the_device():
+    import wfmash_b200 as wb
+    seqs = [("a#1#c", b"ACGT" * 300)]
+    for bad in (dict(kmer_size=0), dict(window_length=0)):
+        with pytest.raises(wb.WfbError):
+            wb.map_phase(seqs, seqs, wb.MapPhaseParams(percentage_identity=0.9, **bad))
+    with pytest.raises(wb.WfbError):
+        wb.map_phase([], seqs, wb.MapPhaseParams(percentage_identity=0.9))   # no targets

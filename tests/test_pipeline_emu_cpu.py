@@ -29,6 +29,13 @@ if out["have_ref"]:
     import wfmash_b200 as wb
     al = wb.Aligner(0)
     c_paf, c_st = wb.align_phase(al, mp + b"not a mapping row\n", seqs, seqs)   # the one-call C ABI phase (phases_host.cu) on the same text
+    # robustness of the phase entry point: empty text, rows naming unknown sequences, the SAM branch
+    e_paf, e_st = wb.align_phase(al, b"", seqs, seqs)
+    rows = mp.split(b"\n")
+    u_paf, u_st = wb.align_phase(al, rows[0].replace(b"a#1#chr1", b"nobody#1#x") + b"\n" + rows[1] + b"\n", seqs, seqs)
+    s_paf, s_st = wb.align_phase(al, rows[1] + b"\n", seqs, seqs, sam_format=True, emit_md_tag=True)
+    out.update(empty=[len(e_paf), int(e_st.records)], unknown=[int(u_st.records), int(u_st.skipped_lines), u_paf.decode() == lines[1].decode()],
+               sam=s_paf.decode().split("\t")[:4] + [s_paf.decode().rstrip("\n").split("\t")[-1][:5]])
     out.update(c_paf=c_paf.decode(), c_records=int(c_st.records), c_skipped=int(c_st.skipped_lines), c_aligned_bp=int(c_st.aligned_bp))
     out.update(ref_map=mp.decode(), ref_paf=b"".join(lines).decode(), ours_paf=paf.decode(), records=st["records"], written=st["written"],
                aligned_bp=st["aligned_bp"])
@@ -50,5 +57,7 @@ def test_align_phase_under_emulation_matches_reference_do_biwfa_alignment():
     assert res["ours_paf"] == res["ref_paf"]
     assert res["c_paf"] == res["ref_paf"] and res["c_records"] == res["records"] and res["c_skipped"] == 1 and res["c_aligned_bp"] == res["aligned_bp"]
     assert {ln.split("\t")[4] for ln in res["ours_paf"].splitlines()} == {"+", "-"}
+    assert res["empty"] == [0, 0] and res["unknown"] == [1, 1, True]
+    assert res["sam"][0] == res["ref_paf"].splitlines()[1].split("\t")[0] and res["sam"][1] in ("0", "16") and res["sam"][4] == "MD:Z:"
     spans = [int(f[3]) - int(f[2]) for f in (ln.split("\t") for ln in res["ref_map"].splitlines())]
     assert res["aligned_bp"] >= sum(spans)  # + the query padding of the chain ends

@@ -66,9 +66,29 @@ def expected(seqs, P, oracle, fref, wref):
         text.append(line)
     map_paf = b"".join(text)
     recs = pipeline.records_from_paf(map_paf, seqs, seqs, P)
-    lines = [util.ref_paf(wref, r, min_identity=P.min_identity, min_alignment_length=P.min_alignment_length, min_block_identity=P.min_block_identity,
-                          disable_chain_patching=P.disable_chain_patching) for r in recs]
+    # do_biwfa_alignment's own text, then the re-emission of Aligner::processMappingRecord (computeAlignments.hpp:486-516: fields
+    # joined by single tabs, i.e. without the trailing tab). tests/test_pipeline_emu_cpu.py also runs the reference's whole
+    # align::Aligner (oracle/_ref/libalignref.so) on the same mapping PAF, which includes that step for real.
+    lines = [pipeline._phase_line(util.ref_paf(wref, r, min_identity=P.min_identity, min_alignment_length=P.min_alignment_length,
+                                               min_block_identity=P.min_block_identity, disable_chain_patching=P.disable_chain_patching)) for r in recs]
     return map_paf, lines
+
+
+def reference_align_phase(A, mapping_paf, seqs, P, sam_format=False, emit_md_tag=False, no_seq_in_sam=False):
+    """The reference's UNMODIFIED align::Aligner::compute() (oracle/ref_align_driver.cpp -> libalignref.so) on a mapping PAF."""
+    import ctypes, tempfile
+    P = P.resolved()
+    A.ref_align_phase.restype = ctypes.c_int64
+    n = len(seqs)
+    names = (ctypes.c_char_p * n)(*[a.encode() for a, _ in seqs]); sq = (ctypes.c_char_p * n)(*[b for _, b in seqs]); ln = (ctypes.c_int64 * n)(*[len(b) for _, b in seqs])
+    buf = ctypes.create_string_buffer(4 * sum(len(b) for _, b in seqs) * 4 + (1 << 20))
+    with tempfile.TemporaryDirectory() as d:
+        k = A.ref_align_phase(d.encode(), names, sq, ln, n, names, sq, ln, n, mapping_paf, ctypes.c_int64(len(mapping_paf)), ctypes.c_uint64(P.target_padding),
+                              ctypes.c_uint64(P.query_padding), ctypes.c_uint64(P.window_length * 128), ctypes.c_float(P.min_identity),
+                              ctypes.c_uint64(P.min_alignment_length), ctypes.c_float(P.min_block_identity), int(P.disable_chain_patching), int(sam_format),
+                              int(emit_md_tag), int(no_seq_in_sam), buf, ctypes.c_int64(len(buf)))
+    assert k >= 0
+    return buf.raw[:k]
 
 
 # (name, arguments of case(), pipeline.Params overrides; "filter" holds FilterParams overrides)

@@ -257,3 +257,42 @@ def test_phase_entry_points_validate_arguments_before_touching_the_device():
             wb.map_phase(seqs, seqs, wb.MapPhaseParams(percentage_identity=0.9, **bad))
     with pytest.raises(wb.WfbError):
         wb.map_phase([], seqs, wb.MapPhaseParams(percentage_identity=0.9))   # no targets
+
+
+@pytest.mark.ref
+def test_mapping_paf_parse_matches_compiled_reference_live():
+    """wfb_mapping_paf_parse against the reference's UNMODIFIED Aligner::parseMashmapRow (computeAlignments.hpp:195-303, compiled in
+    place in oracle/_ref/libalignref.so) on rows written by wfb_mapping_paf_format and on malformed rows: same fields, same rejections."""
+    import wfmash_b200 as wb
+    A = util.load_ref("libalignref.so")
+    if A is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    (out, info, oo), m, off = ours(21, dict(w=1000), dict(), None)
+    names = [f"s{i}" for i in range(len(REF_LEN))]
+    rows = []
+    for q in range(len(oo) - 1):
+        rows += wb.mapping_paf_format(params(dict(w=1000), dict()), out[oo[q]: oo[q + 1]], info[oo[q]: oo[q + 1]], f"q{q}", QLEN, names, REF_LEN).split(b"\n")[:-1]
+    rows += [b"q 1000 0 900 + t 5000 100 1000 9 900 20 id:f:x", b"q 1000 0 900 + t 5000 100 1000 9 900 20 id:f:0.93 kc:f:1 ch:Z:7.1.1",
+             b"q 1000 10 990 - t 5000 4100 4990 9 900 20 id:f:0.5 kc:f:1 ch:Z:3.2.2", b"q 1000 0 900 + t 5000 100 1000 9 900 20 id:f:0.9 kc:f:1 ch:Z:bad",
+             b"q 1000 0 900 + t 5000 100 1000 9 900 20", b"q 1000 0 900 + t 5000 5000 5100 9 900 20 id:f:0.9", b"q 1000 zero 900 + t 5000 1 2 9 900 20 id:f:0.9",
+             b"q\t1000\t0\t900\t+\tt\t5000\t100\t6000\t9\t900\t20\tid:f:0.9", b""]
+    assert len(rows) > 100
+    n_ok = n_bad = 0
+    for tp, qp in ((0, 0), (1000, 1000), (5000, 700), (77, 100000)):
+        for line in rows:
+            q0, q1, r0, r1 = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+            strand, cid, clen, cpos, ident = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_float()
+            bad = A.ref_parse_mashmap_row(line, ctypes.c_uint64(tp), ctypes.c_uint64(qp), ctypes.byref(q0), ctypes.byref(q1), ctypes.byref(r0), ctypes.byref(r1),
+                                          ctypes.byref(strand), ctypes.byref(ident), ctypes.byref(cid), ctypes.byref(clen), ctypes.byref(cpos))
+            try:
+                row, _, _ = wb.mapping_paf_parse(line, tp, qp, 128_000)
+            except wb.WfbError:
+                assert bad == 1, (line, tp, qp)
+                n_bad += 1
+                continue
+            assert bad == 0, (line, tp, qp)
+            assert (row.q_start, row.q_end, row.r_start, row.r_end, row.strand, row.chain_id, row.chain_length, row.chain_pos) == \
+                   (q0.value, q1.value, r0.value, r1.value, strand.value, cid.value, clen.value, cpos.value), (line, tp, qp)
+            assert np.float32(row.mashmap_estimated_identity) == np.float32(ident.value)
+            n_ok += 1
+    assert n_ok > 400 and n_bad >= 12

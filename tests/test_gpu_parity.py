@@ -476,6 +476,9 @@ def test_pipeline_map_align_matches_reference_pieces(wb, oracle):
         if fref is not None and wref is not None and name == "defaults_p90":
             mp, lines = pipeutil.expected(seqs, P, oracle, fref, wref)
             assert st["mapping_paf"] == mp and paf == b"".join(lines)
+            A = util.load_ref("libalignref.so")   # the reference's whole alignment phase (align::Aligner::compute) on our mapping PAF
+            if A is not None:
+                assert pipeutil.reference_align_phase(A, mp_c, seqs, P) == paf_c
 
 
 def test_ani_auto_identity_matches_reference(wb, oracle):

@@ -36,6 +36,11 @@ if out["have_ref"]:
     s_paf, s_st = wb.align_phase(al, rows[1] + b"\n", seqs, seqs, sam_format=True, emit_md_tag=True)
     out.update(empty=[len(e_paf), int(e_st.records)], unknown=[int(u_st.records), int(u_st.skipped_lines), u_paf.decode() == lines[1].decode()],
                sam=s_paf.decode().split("\t")[:4] + [s_paf.decode().rstrip("\n").split("\t")[-1][:5]])
+    A = util.load_ref("libalignref.so")   # the reference's whole alignment phase (align::Aligner::compute) on the same mapping PAF
+    if A is not None:
+        out["aligner_paf"] = pipeutil.reference_align_phase(A, mp, seqs, P).decode()
+        out["aligner_sam"] = pipeutil.reference_align_phase(A, rows[1] + b"\n", seqs, P, sam_format=True, emit_md_tag=True).decode()
+        out["ours_sam"] = s_paf.decode()
     out.update(c_paf=c_paf.decode(), c_records=int(c_st.records), c_skipped=int(c_st.skipped_lines), c_aligned_bp=int(c_st.aligned_bp))
     out.update(ref_map=mp.decode(), ref_paf=b"".join(lines).decode(), ours_paf=paf.decode(), records=st["records"], written=st["written"],
                aligned_bp=st["aligned_bp"])
@@ -57,6 +62,10 @@ def test_align_phase_under_emulation_matches_reference_do_biwfa_alignment():
     assert res["ours_paf"] == res["ref_paf"]
     assert res["c_paf"] == res["ref_paf"] and res["c_records"] == res["records"] and res["c_skipped"] == 1 and res["c_aligned_bp"] == res["aligned_bp"]
     assert {ln.split("\t")[4] for ln in res["ours_paf"].splitlines()} == {"+", "-"}
+    if "aligner_paf" in res:   # byte-identical to what the reference's own Aligner writes to its output file
+        assert res["aligner_paf"] == res["c_paf"] == res["ours_paf"]
+        sam_records = [ln for ln in res["aligner_sam"].splitlines() if not ln.startswith("@")]   # the reference's file starts with @SQ / @PG header lines
+        assert sam_records == res["ours_sam"].splitlines()
     assert res["empty"] == [0, 0] and res["unknown"] == [1, 1, True]
     assert res["sam"][0] == res["ref_paf"].splitlines()[1].split("\t")[0] and res["sam"][1] in ("0", "16") and res["sam"][4] == "MD:Z:"
     spans = [int(f[3]) - int(f[2]) for f in (ln.split("\t") for ln in res["ref_map"].splitlines())]

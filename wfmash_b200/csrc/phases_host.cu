@@ -4,6 +4,7 @@
 // run them. Nothing here computes a mapping or an alignment itself.
 #include "wfmash_b200.h"
 
+#include <ctype.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -318,7 +319,36 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
       rc = wfb_biwfa_paf_batch(aligner, arr.data(), (int32_t)(b1 - b0), &params->output, buf.data(), (int64_t)buf.size(), &len, off.data(), st.data(), &as);
     }
     if (rc != WFB_OK) return rc;
-    text.append(buf.data(), (size_t)len);
+    /* Aligner::processMappingRecord re-emits every line that carries a cg:Z: field as its whitespace-separated fields joined by
+     * single tabs (computeAlignments.hpp:486-516): the trailing tab do_biwfa_alignment writes before the newline disappears.
+     * Lines without a CIGAR field (SAM records) pass through unchanged. */
+    for (int64_t a = 0; a < len;) {
+      const char* nl = (const char*)memchr(buf.data() + a, '\n', (size_t)(len - a));
+      const int64_t b = nl ? (int64_t)(nl - buf.data()) : len;
+      if (b > a) {
+        std::vector<std::pair<int64_t, int64_t>> fields;
+        bool has_cigar = false;
+        for (int64_t p = a; p < b;) {
+          while (p < b && isspace((unsigned char)buf[(size_t)p])) ++p;
+          if (p >= b) break;
+          const int64_t f0 = p;
+          while (p < b && !isspace((unsigned char)buf[(size_t)p])) ++p;
+          fields.emplace_back(f0, p);
+          if (p - f0 >= 5 && memcmp(buf.data() + f0, "cg:Z:", 5) == 0) has_cigar = true;
+        }
+        if (has_cigar) {
+          for (size_t i = 0; i < fields.size(); ++i) {
+            if (i) text.push_back('\t');
+            text.append(buf.data() + fields[i].first, (size_t)(fields[i].second - fields[i].first));
+          }
+          text.push_back('\n');
+        } else {
+          text.append(buf.data() + a, (size_t)(b - a));
+          text.push_back('\n');
+        }
+      }
+      a = b + 1;
+    }
     for (size_t i = 0; i < st.size(); ++i) written += st[i] == WFB_REC_WRITTEN;
     kernel_ms += as.kernel_ms;
   }

@@ -226,6 +226,16 @@ def records_from_paf(paf: bytes, targets, queries, params: Params = None):
     return recs
 
 
+def _phase_line(line: bytes) -> bytes:
+    """Aligner::processMappingRecord (computeAlignments.hpp:486-516) re-emits a line that has a cg:Z: field as its whitespace-
+    separated fields joined by single tabs: the trailing tab do_biwfa_alignment writes before the newline disappears. Lines
+    without a CIGAR field (SAM records) pass through unchanged."""
+    if not line:
+        return line
+    f = line.split()
+    return b"\t".join(f) + b"\n" if any(x.startswith(b"cg:Z:") for x in f) else line
+
+
 def align(paf: bytes, targets, queries, params: Params = None, device: int = 0, aligner=None, batch_records: int = 4096, per_row: bool = False):
     """Alignment phase over mapping PAF text -> (alignment PAF text, stats). per_row: return one bytes object per non-empty input
     row instead (b"" for rows that were skipped or filtered), for callers that scatter rows over GPUs."""
@@ -239,7 +249,7 @@ def align(paf: bytes, targets, queries, params: Params = None, device: int = 0, 
         ln, st = aligner.biwfa_paf_batch(recs[b: b + batch_records], min_identity=P.min_identity, min_alignment_length=P.min_alignment_length,
                                          min_block_identity=P.min_block_identity, disable_chain_patching=P.disable_chain_patching,
                                          term_group=P.term_group)
-        lines += ln
+        lines += [_phase_line(x) for x in ln]
         status += st
     if own:
         aligner.close()

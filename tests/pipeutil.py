@@ -23,8 +23,14 @@ def case(seed=5, length=30_000):
     return [("a#1#chr1", low), ("b#1#chr1", b.tobytes()), ("c#1#chr1", c.tobytes()), ("c#1#tiny", b"ACGT" * 100)]
 
 
-def expected(seqs, P, oracle, fref, wref):
-    """(mapping PAF, alignment PAF lines) the reference-side pieces produce for an all-vs-all run over `seqs`."""
+def expected(seqs, P, oracle, fref, wref, fragment_order="reverse", align=True):
+    """(mapping PAF, alignment PAF lines) the reference-side pieces produce for an all-vs-all run over `seqs`.
+    fragment_order: the order in which the fragments' results reach Map::filterSubsetMappings. The reference appends them as its
+    fragment tasks finish (computeMap.hpp:590-597), so it is schedule dependent there, and it decides the ch:Z: tags (chain ids are
+    the ranks of the smallest ORIGINAL index in each chain, mappingFilter.hpp:401-404,498-520). "reverse" = the order a one-thread
+    taskflow executor runs the subflow (last emplaced fragment first): the reference's only reproducible schedule, the one the library
+    follows, and the one under which this composition equals the reference's real `wfmash -m -t 1` text (reference_map_phase below);
+    "forward" = fragment 0 first."""
     import wfmash_b200 as wb
     from wfmash_b200 import pipeline
     P = P.resolved()
@@ -52,6 +58,9 @@ def expected(seqs, P, oracle, fref, wref):
         if len(sq) < w:
             continue
         l2 = mp[frag_q[mp["frag"]] == qi]
+        if fragment_order == "reverse":   # whole fragments in reverse order, each fragment's own results in their order
+            fr = sorted(set(l2["frag"].tolist()), reverse=True)
+            l2 = np.concatenate([l2[l2["frag"] == f] for f in fr]) if fr else l2
         m = np.ascontiguousarray(wb.l2_to_query_mappings(l2, fi, w, len(sq), ref_len))
         o = np.zeros(len(m) + 4, dtype=wb.MAPPING_DTYPE); c = np.zeros(len(m) + 4, dtype=wb.CHAIN_INFO_DTYPE)
         n = fref.ref_filter_subset(ctypes.byref(P.filter), ctypes.c_void_p(m.ctypes.data), ctypes.c_int64(len(m)), ids.id_of[name], ctypes.c_int64(len(sq)),
@@ -65,6 +74,8 @@ def expected(seqs, P, oracle, fref, wref):
             line = line.replace(b"\ts%d\t" % i, b"\t" + nm.encode() + b"\t")
         text.append(line)
     map_paf = b"".join(text)
+    if not align:
+        return map_paf, []
     recs = pipeline.records_from_paf(map_paf, seqs, seqs, P)
     # do_biwfa_alignment's own text, then the re-emission of Aligner::processMappingRecord (computeAlignments.hpp:486-516: fields
     # joined by single tabs, i.e. without the trailing tab). tests/test_pipeline_emu_cpu.py also runs the reference's whole
@@ -115,3 +126,57 @@ def params(prm):
 def line_digest(line: bytes):
     import hashlib
     return {"head": b"\t".join(line.split(b"\t")[:12]).decode(), "sha": hashlib.sha256(line).hexdigest()}
+
+
+class _RefMapParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in "kmer_size sketch_size threads filter_mode skip_self skip_prefix lower_triangular merge_mappings split minimum_hits".split()] + \
+               [(n, ctypes.c_int64) for n in "window_length block_length chain_gap scaffold_gap scaffold_max_deviation scaffold_min_length".split()] + \
+               [("max_mapping_length", ctypes.c_uint64), ("num_mappings_for_segment", ctypes.c_uint32), ("num_mappings_for_scaffold", ctypes.c_uint32),
+                ("percentage_identity", ctypes.c_float), ("prefix_delim", ctypes.c_int32), ("overlap_threshold", ctypes.c_double),
+                ("scaffold_overlap_threshold", ctypes.c_double), ("max_kmer_freq", ctypes.c_double)]
+
+
+def reference_map_phase(M, seqs, P, threads=1):
+    """The reference's UNMODIFIED skch::Map (oracle/ref_mapper_driver.cpp -> libmapperref.so): the whole `wfmash -m` run, all-vs-all."""
+    import ctypes, tempfile
+    P = P.resolved()
+    F = P.filter
+    M.ref_map_phase.restype = ctypes.c_int64
+    prm = _RefMapParams(P.kmer_size, P.sketch_size, threads, F.filter_mode, int(P.skip_self), int(P.skip_prefix), int(P.lower_triangular), F.merge_mappings, F.split,
+                        P.minimum_hits, P.window_length, F.block_length, F.chain_gap, F.scaffold_gap, F.scaffold_max_deviation, F.scaffold_min_length,
+                        F.max_mapping_length, F.num_mappings_for_segment, F.num_mappings_for_scaffold, P.percentage_identity, ord(P.prefix_delim),
+                        F.overlap_threshold, F.scaffold_overlap_threshold, P.max_kmer_freq)
+    n = len(seqs)
+    names = (ctypes.c_char_p * n)(*[a.encode() for a, _ in seqs]); sq = (ctypes.c_char_p * n)(*[b for _, b in seqs]); ln = (ctypes.c_int64 * n)(*[len(b) for _, b in seqs])
+    buf = ctypes.create_string_buffer(64 << 20)
+    with tempfile.TemporaryDirectory() as d:
+        k = M.ref_map_phase(d.encode(), ctypes.byref(prm), names, sq, ln, n, names, sq, ln, n, 1, buf, ctypes.c_int64(len(buf)))
+    assert k >= 0
+    return buf.raw[:k]
+
+
+class OracleIndex:
+    """Stands in for wb.Index in CPU tests of pipeline.map's HOST half: map_fragments answers from the oracle's mapping restatement
+    (the GPU kernels are compared with that same restatement in tests/test_gpu_parity.py)."""
+
+    def __init__(self, oracle, seqs, ids, groups, k, w, s, F, threads):
+        self.o, self.seqs, self.ids, self.groups, self.k, self.w, self.s = oracle, seqs, ids, groups, k, w, s
+        self.index = maputil.oracle_index(oracle, [maputil.clean(x) for x in seqs], ids, k, w, s, F, threads)
+
+    def map_fragments(self, blob, frags, fqs, minimum_hits, cutoffs, grp, skip_self=True, skip_prefix=True, lower_triangular=False, stage1_min_hits=None,
+                      l2_min_shared=None, **kw):
+        import wfmash_b200 as wb
+        frs, _, _, _, mp = maputil.oracle_map_fragments(self.o, self.index, self.seqs, self.ids, self.groups, self.k, self.w, self.s,
+                                                        mode=(int(skip_self), int(skip_prefix), int(lower_triangular), minimum_hits),
+                                                        stage1=stage1_min_hits is not None, min_shared=l2_min_shared, cut=cutoffs)
+        assert len(frs) == len(frags)   # the same fragments in the same order (every sequence is both target and query)
+        out = np.zeros(len(mp), dtype=wb.L2_MAPPING_DTYPE)
+        for f in ("frag", "refSeqId", "refStartPos", "optimalStart", "optimalEnd", "conservedSketches", "strand", "nucIdentity", "kmerComplexity"):
+            out[f] = mp[f]
+        off = np.zeros(len(frs) + 1, dtype=np.int64)
+        np.add.at(off, out["frag"] + 1, 1)
+        return {"mappings": out, "offset": np.cumsum(off), "status": np.zeros(len(frs), dtype=np.int32), "l1_kernel_ms": 0.0, "l2_kernel_ms": 0.0,
+                "n_l1_loci": 0}
+
+    def close(self):
+        pass

@@ -1,0 +1,39 @@
+"""The mapping phase as a whole against the reference's UNMODIFIED skch::Map (src/map/include/computeMap.hpp compiled in place behind
+oracle/ref_mapper_driver.cpp -> oracle/_ref/libmapperref.so; htslib / GSL replaced by the stand-ins under oracle/shims): what it writes
+is what `wfmash -m -t 1` writes for the same sequences.
+  * the composition the fixtures are made of (oracle mapping restatement -> unmodified filters -> unmodified writer, tests/pipeutil.py)
+    equals that text for every parameter set of the pipeline fixture, so the GPU pipeline test is pinned to the real program;
+  * the HOST half of wfmash_b200.pipeline.map (ids, PanSN groups, fragments, run-level constants, fragment order, boundary check,
+    chain merge + filters, PAF text) equals it too, with the device call answered by the oracle (tests.pipeutil.OracleIndex)."""
+import pytest
+
+from tests import pipeutil, util
+
+
+@pytest.mark.ref
+def test_composed_expectation_and_pipeline_host_half_equal_the_reference_mapper(oracle):
+    from wfmash_b200 import pipeline
+    M, fref, wref = util.load_ref("libmapperref.so"), util.load_ref("libfilterref.so"), util.load_wflign_ref()
+    if M is None or fref is None or wref is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    total = 0
+    for name, gen, prm in pipeutil.PIPELINE_CASES:
+        gen = dict(gen, length=min(gen["length"], 30_000))
+        seqs = pipeutil.case(**gen)
+        P = pipeutil.params(prm)
+        ref = sorted(pipeutil.reference_map_phase(M, seqs, P).split(b"\n"))
+        composed = sorted(pipeutil.expected(seqs, P, oracle, fref, wref, align=False)[0].split(b"\n"))
+        assert composed == ref, name
+        R = P.resolved()
+        ids = pipeline.SequenceIds(seqs, seqs, R.prefix_delim)
+        fake = pipeutil.OracleIndex(oracle, [s for _, s in seqs], [ids.id_of[n] for n, _ in seqs], ids.group, R.kmer_size, R.window_length, R.sketch_size,
+                                    R.max_kmer_freq, R.index_threads)
+        ours = sorted(pipeline.map(seqs, seqs, P, index=fake).paf.split(b"\n"))
+        assert ours == ref, name
+        # the reference against itself: with more threads its fragment tasks finish in another order, which may renumber the chains;
+        # every other column is schedule independent
+        strip = lambda lines: sorted(b"\t".join(ln.split(b"\t")[:14]) for ln in lines if ln)
+        assert strip(pipeutil.reference_map_phase(M, seqs, P, threads=3).split(b"\n")) == strip(ref), name
+        total += len(ref) - 1
+        assert any(b"\t-\t" in ln for ln in ref)
+    assert total > 100

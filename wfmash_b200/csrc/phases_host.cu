@@ -178,9 +178,17 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
     /* per query: MappingResult construction + boundary check, then the chain / filter stage for the whole batch */
     std::vector<wfb_mapping_t> all((size_t)n_l2);
     std::vector<int64_t> q_off(1, 0), q_len;
+    /* The order in which the fragments' results reach the chain merge decides the ch:Z: tags (chain ids rank the smallest ORIGINAL
+     * index of each chain, mappingFilter.hpp:401-404,498-520). The reference appends them as its fragment tasks finish
+     * (computeMap.hpp:590-597), i.e. in a schedule-dependent order; its only reproducible schedule is the one-thread run, where
+     * the taskflow subflow executes the LAST emplaced fragment first. That order is used here, so the text equals `wfmash -m -t 1`. */
+    std::vector<wfb_l2_mapping_t> ordered;
     for (size_t m = 0; m < mapped.size(); ++m) {
       const int64_t a = moff[(size_t)q_frag[m]], b = moff[(size_t)q_frag[m + 1]];
-      if ((rc = wfb_l2_to_query_mappings(maps.data() + a, b - a, frag_index.data(), w, queries[mapped[m]].len, ids.lens.data(), all.data() + a)) != WFB_OK) break;
+      ordered.clear();
+      for (int64_t f = q_frag[m + 1] - 1; f >= q_frag[m]; --f)
+        for (int64_t i = moff[(size_t)f]; i < moff[(size_t)f + 1]; ++i) ordered.push_back(maps[(size_t)i]);
+      if ((rc = wfb_l2_to_query_mappings(ordered.data(), b - a, frag_index.data(), w, queries[mapped[m]].len, ids.lens.data(), all.data() + a)) != WFB_OK) break;
       q_off.push_back(b);
       q_len.push_back(queries[mapped[m]].len);
     }

@@ -181,7 +181,11 @@ def map(targets, queries, params: Params = None, device: int = 0, index=None, on
     off = r["offset"]
     per_query, q_off = [], [0]
     for qi, (name, seq) in enumerate(mapped):
-        l2 = r["mappings"][off[q_frag[qi]]: off[q_frag[qi + 1]]]
+        # The order in which the fragments' results reach the chain merge decides the ch:Z: tags; the reference appends them as its
+        # fragment tasks finish (computeMap.hpp:590-597). Its only reproducible schedule is the one-thread run, where the taskflow
+        # subflow executes the LAST emplaced fragment first: use that order, so the text equals `wfmash -m -t 1`.
+        parts = [r["mappings"][off[f]: off[f + 1]] for f in range(q_frag[qi + 1] - 1, q_frag[qi] - 1, -1)]
+        l2 = np.concatenate(parts) if parts else r["mappings"][:0]
         per_query.append(wb.l2_to_query_mappings(l2, fi, w, len(seq), ref_len))
         q_off.append(q_off[-1] + len(l2))
     allm = np.concatenate(per_query) if per_query else np.zeros(0, wb.MAPPING_DTYPE)

@@ -374,13 +374,62 @@ def map_path_section(dev, cores, with_cpu):
     return out
 
 
+def cpu_reference_pipeline(seqs, mapping_paf, cores):
+    """The reference's own two phases on the host cores, UNMODIFIED (oracle/_ref/libmapperref.so = skch::Map, libalignref.so =
+    align::Aligner, compiled in place): the mapping phase on the same sequences and parameters (-p 90 -k15 -w1k -P50k, defaults
+    otherwise), the alignment phase on OUR mapping PAF so that both sides align the same records. Baseline / checker only."""
+    import tempfile
+    mlib, alib = os.path.join(ROOT, "oracle", "_ref", "libmapperref.so"), os.path.join(ROOT, "oracle", "_ref", "libalignref.so")
+    if not (os.path.exists(mlib) and os.path.exists(alib)):
+        return {"unavailable": "oracle/_ref/libmapperref.so / libalignref.so not built"}
+
+    class MP(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_int32) for n in "kmer_size sketch_size threads filter_mode skip_self skip_prefix lower_triangular merge_mappings split minimum_hits".split()] + \
+                   [(n, ctypes.c_int64) for n in "window_length block_length chain_gap scaffold_gap scaffold_max_deviation scaffold_min_length".split()] + \
+                   [("max_mapping_length", ctypes.c_uint64), ("num_mappings_for_segment", ctypes.c_uint32), ("num_mappings_for_scaffold", ctypes.c_uint32),
+                    ("percentage_identity", ctypes.c_float), ("prefix_delim", ctypes.c_int32), ("overlap_threshold", ctypes.c_double),
+                    ("scaffold_overlap_threshold", ctypes.c_double), ("max_kmer_freq", ctypes.c_double)]
+    import wfmash_b200 as wb
+    s = wb.sketch_size(0.90, 1000, 15)
+    prm = MP(15, s, cores, 1, 1, 1, 0, 1, 1, -1, 1000, 0, 2000, 100000, 100000, 10000, 50000, 2**32 - 1, 1, 0.90, ord("#"), 0.95, 0.5, 0.0002)
+    n = len(seqs)
+    names = (ctypes.c_char_p * n)(*[a.encode() for a, _ in seqs]); sq = (ctypes.c_char_p * n)(*[b for _, b in seqs]); ln = (ctypes.c_int64 * n)(*[len(b) for _, b in seqs])
+    M, A = ctypes.CDLL(mlib), ctypes.CDLL(alib)
+    M.ref_map_phase.restype = ctypes.c_int64
+    A.ref_align_phase.restype = ctypes.c_int64
+    buf = ctypes.create_string_buffer(max(64 << 20, 8 * len(mapping_paf)))
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.perf_counter()
+        k = M.ref_map_phase(d.encode(), ctypes.byref(prm), names, sq, ln, n, names, sq, ln, n, 1, buf, ctypes.c_int64(len(buf)))
+        t_map = time.perf_counter() - t0
+    ref_map = buf.raw[:max(k, 0)]
+    strip = lambda t: sorted(b"\t".join(x.split(b"\t")[:14]) for x in t.split(b"\n") if x)   # ch:Z: is schedule dependent in the reference itself
+    A.ref_align_set_threads(cores)
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.perf_counter()
+        k2 = A.ref_align_phase(d.encode(), names, sq, ln, n, names, sq, ln, n, mapping_paf, ctypes.c_int64(len(mapping_paf)), ctypes.c_uint64(1000), ctypes.c_uint64(1000),
+                               ctypes.c_uint64(128000), ctypes.c_float(0.0), ctypes.c_uint64(32), ctypes.c_float(0.1), 0, 0, 0, 0, buf, ctypes.c_int64(len(buf)))
+        t_aln = time.perf_counter() - t0
+    A.ref_align_set_threads(1)
+    ref_paf = buf.raw[:max(k2, 0)]
+    aligned = 0
+    for row in mapping_paf.split(b"\n"):
+        if row:
+            f = row.split(b"\t")
+            aligned += int(f[3]) - int(f[2])
+    return {"kind": "reference", "cores": cores, "seconds": {"map_phase": t_map, "align_phase": t_aln, "total": t_map + t_aln},
+            "aligned_bp_per_s": aligned / (t_map + t_aln) if t_map + t_aln > 0 else None, "mapping_rows": ref_map.count(b"\n"),
+            "mapping_columns_1_14_identical": strip(ref_map) == strip(mapping_paf), "paf_lines": ref_paf.count(b"\n"), "_paf_sorted": sorted(ref_paf.split(b"\n")),
+            "sample": "the whole workload of this section (reference mapper on the same sequences; reference aligner on our mapping PAF), FASTA writing included"}
+
+
 # ---------------------------------------------------------------------------------------------------
 # BASELINE.json's metric is quoted end to end (map + WFA). pipeline_section runs the two phases chained
 # (wfmash_b200.pipeline.wfmash: index build -> L1/L2 kernels -> host chain merge + filters -> mapping PAF ->
 # padded records -> biWFA kernels + patches -> alignment PAF) on a C4-shaped synthetic pair of haplotypes,
 # host buffers in, PAF text out, wall clock around the whole call.
 # ---------------------------------------------------------------------------------------------------
-def pipeline_section(dev, contigs=16, contig_bp=500_000, ani=0.95, runs=2):
+def pipeline_section(dev, contigs=16, contig_bp=500_000, ani=0.95, runs=2, with_cpu=True, cores=1):
     from wfmash_b200 import synth
     rng = np.random.default_rng(4242)
     d = 1.0 - ani ** 0.5  # SURVEY 8(d): each haplotype derived from the root at d = 1 - sqrt(ANI)
@@ -405,7 +454,16 @@ def pipeline_section(dev, contigs=16, contig_bp=500_000, ani=0.95, runs=2):
     al.close()
     ms, a, paf_bytes = st
     total_bp = sum(len(x) for _, x in seqs)
-    return {"workload": f"C4-shaped synthetic: 2 haplotypes x {contigs} contigs x {contig_bp} bp at {ani:.0%} ANI, all-vs-all, -p 90 -k15 -w1k -P50k (defaults otherwise)",
+    cpu_ref = None
+    if with_cpu:
+        try:
+            cpu_ref = cpu_reference_pipeline(seqs, mp, cores)
+            if "_paf_sorted" in cpu_ref:
+                cpu_ref["paf_lines_identical"] = cpu_ref.pop("_paf_sorted") == sorted(paf.split(b"\n"))
+                cpu_ref["aligned_bp_per_s"] = int(a.aligned_bp) / cpu_ref["seconds"]["total"]   # same numerator as ours (padded record spans)
+        except Exception as e:
+            cpu_ref = {"error": str(e)}
+    return {"cpu_reference": cpu_ref, "workload": f"C4-shaped synthetic: 2 haplotypes x {contigs} contigs x {contig_bp} bp at {ani:.0%} ANI, all-vs-all, -p 90 -k15 -w1k -P50k (defaults otherwise)",
             "sequence_bp": total_bp, "mapping_records": int(ms.mappings), "fragments": int(ms.fragments), "records_aligned": int(a.records),
             "paf_lines": int(a.written), "paf_bytes": paf_bytes, "aligned_bp": int(a.aligned_bp),
             "seconds": {"total": best[0], "map_phase": best[1], "align_phase": best[2], "index_build": ms.index_seconds, "map_kernels": ms.map_kernel_ms / 1e3,
@@ -600,7 +658,7 @@ def main():
                 line["map_path"] = {"error": str(e)}
         if world == 1 and not args.no_pipeline:
             try:
-                line["pipeline"] = pipeline_section(dev)
+                line["pipeline"] = pipeline_section(dev, with_cpu=not args.no_cpu, cores=cores)
             except Exception as e:
                 line["pipeline"] = {"error": str(e)}
         print(json.dumps(line))

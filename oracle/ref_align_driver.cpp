@@ -29,6 +29,9 @@ static void write_fasta(const std::string& path, const char* const* names, const
   }
 }
 
+static int g_align_threads = 1;
+extern "C" void ref_align_set_threads(int32_t n) { g_align_threads = n > 0 ? n : 1; } /* 1 = records in row order (parity tests); more = timing runs */
+
 extern "C" {
 /* Writes the sequences as FASTA + .fai and the mapping PAF into `dir`, runs align::Aligner::compute() with one thread (records in
  * row order) and returns the bytes of its output file (PAF or SAM). -1 when the buffer is too small. */
@@ -42,7 +45,7 @@ int64_t ref_align_phase(const char* dir, const char* const* t_names, const char*
   write_fasta(qf, q_names, q_seqs, q_lens, nq);
   { std::ofstream m(mp, std::ios::binary); m.write(mapping_paf, mapping_paf_len); }
   align::Parameters p{};
-  p.threads = 1;
+  p.threads = g_align_threads;
   p.refSequences = {tf}; p.querySequences = {qf}; p.mashmapPafFile = mp; p.pafOutputFile = op;
   p.target_padding = target_padding; p.query_padding = query_padding; p.wflign_max_len_minor = wflign_max_len_minor;
   p.min_identity = min_identity; p.min_alignment_length = min_alignment_length; p.min_block_identity = min_block_identity;

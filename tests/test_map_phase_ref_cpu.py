@@ -37,3 +37,38 @@ def test_composed_expectation_and_pipeline_host_half_equal_the_reference_mapper(
         total += len(ref) - 1
         assert any(b"\t-\t" in ln for ln in ref)
     assert total > 100
+
+
+# (name, Params overrides incl. "filter" overrides, compare without the ch:Z: tag?)
+MORE = [
+    ("one_to_one", dict(filter=dict(filter_mode=2, num_mappings_for_segment=1)), True),    # chain ids follow an unordered_map in the reference
+    ("lower_triangular", dict(lower_triangular=True), False),
+    ("self_mappings", dict(skip_self=False, skip_prefix=False), False),
+    ("no_split", dict(filter=dict(split=0, scaffold_min_length=500)), False),
+    ("block_length_5k_gap_500", dict(filter=dict(block_length=5000, chain_gap=500)), False),
+    ("n2_overlap_half_P10k", dict(filter=dict(num_mappings_for_segment=2, overlap_threshold=0.5, max_mapping_length=10000, scaffold_min_length=2000)), False),
+    ("k19_w500_p80", dict(kmer_size=19, window_length=500, percentage_identity=0.80), False),
+]
+
+
+@pytest.mark.ref
+def test_pipeline_host_half_equals_the_reference_mapper_across_cli_options(oracle):
+    from wfmash_b200 import pipeline
+    M = util.load_ref("libmapperref.so")
+    if M is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    seqs = pipeutil.case(seed=13, length=24_000)
+    n = 0
+    for name, prm, no_tag in MORE:
+        P = pipeutil.params(prm)
+        R = P.resolved()
+        ids = pipeline.SequenceIds(seqs, seqs, R.prefix_delim if R.skip_prefix else "")
+        fake = pipeutil.OracleIndex(oracle, [s for _, s in seqs], [ids.id_of[x] for x, _ in seqs], ids.group, R.kmer_size, R.window_length, R.sketch_size,
+                                    R.max_kmer_freq, R.index_threads)
+        ours = pipeline.map(seqs, seqs, P, index=fake).paf
+        ref = pipeutil.reference_map_phase(M, seqs, P)
+        cut = (lambda t: sorted(b"\t".join(x.split(b"\t")[:14]) for x in t.split(b"\n") if x)) if no_tag else (lambda t: sorted(x for x in t.split(b"\n") if x))
+        assert cut(ours) == cut(ref), name
+        assert len(cut(ref)) >= 3, name
+        n += len(cut(ref))
+    assert n > 100

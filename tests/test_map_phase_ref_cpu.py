@@ -5,6 +5,12 @@ is what `wfmash -m -t 1` writes for the same sequences.
     equals that text for every parameter set of the pipeline fixture, so the GPU pipeline test is pinned to the real program;
   * the HOST half of wfmash_b200.pipeline.map (ids, PanSN groups, fragments, run-level constants, fragment order, boundary check,
     chain merge + filters, PAF text) equals it too, with the device call answered by the oracle (tests.pipeutil.OracleIndex)."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
 import pytest
 
 from tests import pipeutil, util
@@ -72,3 +78,55 @@ def test_pipeline_host_half_equals_the_reference_mapper_across_cli_options(oracl
         assert len(cut(ref)) >= 3, name
         n += len(cut(ref))
     assert n > 100
+
+
+C_PHASE_SCRIPT = r"""
+import ctypes, json, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import wfmash_b200 as wb
+from wfmash_b200 import pipeline
+from tests import pipeutil, util
+from tests.test_map_phase_ref_cpu import MORE
+oracle, M = util.load_oracle(), util.load_ref("libmapperref.so")
+out = {"have_ref": M is not None, "bad": [], "n": 0}
+if M is not None:
+    seqs = pipeutil.case(seed=13, length=24_000)
+    for name, prm, no_tag in [("defaults", dict(), False)] + MORE:
+        P = pipeutil.params(prm)
+        R = P.resolved()
+        ids = pipeline.SequenceIds(seqs, seqs, R.prefix_delim if R.skip_prefix else "")
+        fake = pipeutil.OracleIndex(oracle, [s for _, s in seqs], [ids.id_of[x] for x, _ in seqs], ids.group, R.kmer_size, R.window_length, R.sketch_size,
+                                    R.max_kmer_freq, R.index_threads)
+        min_hits = max(R.minimum_hits, wb.estimate_minimum_hits_relaxed(R.sketch_size, R.kmer_size, R.percentage_identity))
+        r = fake.map_fragments(None, [0] * sum(len(s) // R.window_length + (1 if len(s) %% R.window_length and len(s) >= R.window_length else 0) for _, s in seqs), None,
+                               min_hits, wb.sketch_cutoffs(R.sketch_size, R.kmer_size), None, skip_self=R.skip_self, skip_prefix=R.skip_prefix,
+                               lower_triangular=R.lower_triangular, stage1_min_hits=wb.stage1_min_hits(R.kmer_size, R.sketch_size),
+                               l2_min_shared=wb.l2_min_shared_relaxed(R.percentage_identity, R.kmer_size, R.sketch_size))
+        maps, off = np.ascontiguousarray(r["mappings"]), np.ascontiguousarray(r["offset"], dtype=np.int64)
+        wb.lib().wfb_emu_inject_l2(ctypes.c_void_p(maps.ctypes.data), ctypes.c_void_p(off.ctypes.data), ctypes.c_int64(len(off) - 1))
+        MP = wb.MapPhaseParams(filter=R.filter, kmer_size=R.kmer_size, window_length=R.window_length, percentage_identity=R.percentage_identity,
+                               skip_self=int(R.skip_self), skip_prefix=int(R.skip_prefix), lower_triangular=int(R.lower_triangular))
+        ours, st = wb.map_phase(seqs, seqs, MP)
+        ref = pipeutil.reference_map_phase(M, seqs, P)
+        cut = (lambda t: sorted(b"\t".join(x.split(b"\t")[:14]) for x in t.split(b"\n") if x)) if no_tag else (lambda t: sorted(x for x in t.split(b"\n") if x))
+        if cut(ours) != cut(ref) or st.sketch_size != R.sketch_size or st.minimum_hits != min_hits:
+            out["bad"].append(name)
+        out["n"] += len(cut(ref))
+print(json.dumps(out))
+"""
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_c_map_phase_host_half_equals_the_reference_mapper_under_emulation():
+    """wfb_map_phase (C++) with the fragment mappings injected through the emulation build's test-only hook (the index build and the mapping
+    kernels are not emulated): everything around the device calls runs for real and must reproduce the reference mapper's text."""
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
+    r = subprocess.run([sys.executable, "-c", C_PHASE_SCRIPT % {"root": util.ROOT}], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    if not res["have_ref"]:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    assert res["bad"] == [] and res["n"] > 120

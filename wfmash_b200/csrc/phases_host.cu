@@ -65,6 +65,18 @@ char* to_c_text(const std::string& s) {
 
 extern "C" void wfb_free_text(char* text) { free(text); }
 
+#ifdef WFB_EMU
+/* TEST-ONLY (never in the product library): the index build and the mapping kernels are not part of the host emulation, so a test
+ * injects the fragment mappings (the oracle's) and wfb_map_phase runs everything AROUND the device calls for real: ids, groups,
+ * fragments, run-level constants, fragment order, boundary check, chain merge + filters, PAF text. */
+static const wfb_l2_mapping_t* g_emu_l2 = nullptr;
+static const int64_t* g_emu_off = nullptr;
+static int64_t g_emu_nfrag = -1;
+extern "C" void wfb_emu_inject_l2(const wfb_l2_mapping_t* mappings, const int64_t* frag_map_offset, int64_t n_frags) {
+  g_emu_l2 = mappings; g_emu_off = frag_map_offset; g_emu_nfrag = n_frags;
+}
+#endif
+
 extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, const wfb_seq_t* targets, int32_t n_targets, const wfb_seq_t* queries,
                              int32_t n_queries, char** paf, int64_t* paf_len, wfb_map_phase_stats_t* stats) {
   if (!params || !paf || !paf_len || n_targets <= 0 || n_queries < 0 || !targets || (n_queries > 0 && !queries) || params->kmer_size < 1 ||
@@ -118,8 +130,13 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
   wfb_index_params_t ip; memset(&ip, 0, sizeof ip);
   ip.kmer_size = k; ip.window_size = (int32_t)w; ip.sketch_size = s; ip.index_threads = std::max(1, P.index_threads); ip.max_kmer_freq = P.max_kmer_freq;
   const double t_ix = now_s();
+#ifndef WFB_EMU
   wfb_index_t* ix = wfb_index_build(device, &ip, tptr.data(), tlen.data(), tid.data(), n_targets, nullptr);
   if (!ix) return WFB_ECUDA; /* message already set */
+#else
+  wfb_index_t* ix = nullptr;
+  if (g_emu_nfrag < 0) { wfb_set_last_error_("the mapping kernels are not part of the host emulation (see wfb_emu_inject_l2)"); return WFB_ENODEV; }
+#endif
   const double index_seconds = now_s() - t_ix;
 
   /* run-level constants (computeMap.hpp:150-160, 224-226, 999-1024) */
@@ -165,7 +182,18 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
       maps.resize((size_t)cap);
       wfb_map_out_t mo; memset(&mo, 0, sizeof mo);
       mo.mappings = maps.data(); mo.mappings_cap = cap; mo.frag_map_offset = moff.data(); mo.frag_status = fst.data();
+#ifndef WFB_EMU
       rc = wfb_map_fragments_batch(ix, &lp, &l2p, blob.data(), (int64_t)blob.size(), frags.data(), fq.data(), nf, &mo);
+#else
+      if (g_emu_nfrag != nf) { wfb_set_last_error_("injected fragment count differs from the phase's fragments"); return WFB_EINVAL; }
+      if (g_emu_off[nf] > cap) rc = WFB_ECAP;
+      else {
+        memcpy(maps.data(), g_emu_l2, sizeof(wfb_l2_mapping_t) * (size_t)g_emu_off[nf]);
+        memcpy(moff.data(), g_emu_off, sizeof(int64_t) * ((size_t)nf + 1));
+        mo.n_mappings = g_emu_off[nf];
+        rc = WFB_OK;
+      }
+#endif
       if (rc == WFB_ECAP) { cap *= 4; continue; }
       if (rc == WFB_OK) { n_l2 = mo.n_mappings; map_ms = mo.l1_kernel_ms + mo.l2_kernel_ms + mo.sort_kernel_ms; }
       break;
@@ -173,7 +201,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
     if (rc == WFB_OK)
       for (int32_t f = 0; f < nf; ++f)
         if (fst[(size_t)f] != 0) { wfb_set_last_error_("a fragment exceeded an internal capacity of the mapping kernels"); rc = WFB_ECAP; break; }
-    if (rc != WFB_OK) { wfb_index_free(ix); return rc; }
+    if (rc != WFB_OK) { if (ix) wfb_index_free(ix); return rc; }
     const double t_f = now_s();
     /* per query: MappingResult construction + boundary check, then the chain / filter stage for the whole batch */
     std::vector<wfb_mapping_t> all((size_t)n_l2);
@@ -210,7 +238,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
         default_chain = true;
       }
     }
-    if (rc != WFB_OK) { wfb_index_free(ix); return rc; }
+    if (rc != WFB_OK) { if (ix) wfb_index_free(ix); return rc; }
     std::vector<const char*> names(ids.names.size());
     for (size_t i = 0; i < names.size(); ++i) names[i] = ids.names[i].c_str();
     std::vector<char> buf(1 << 16);
@@ -224,13 +252,13 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
         got = wfb_mapping_paf_format(&P.filter, out.data() + oo[m], default_chain ? nullptr : chain.data() + oo[m], n, queries[mapped[m]].name, queries[mapped[m]].len,
                                      names.data(), ids.lens.data(), buf.data(), (int64_t)buf.size(), &need);
       }
-      if (got < 0) { wfb_index_free(ix); return (int)got; }
+      if (got < 0) { if (ix) wfb_index_free(ix); return (int)got; }
       text.append(buf.data(), (size_t)got);
     }
     n_out = oo.back();
     filter_seconds = now_s() - t_f;
   }
-  wfb_index_free(ix);
+  if (ix) wfb_index_free(ix);
   *paf = to_c_text(text);
   if (!*paf) { wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
   *paf_len = (int64_t)text.size();

@@ -113,6 +113,23 @@ if M is not None:
         if cut(ours) != cut(ref) or st.sketch_size != R.sketch_size or st.minimum_hits != min_hits:
             out["bad"].append(name)
         out["n"] += len(cut(ref))
+    # the CLI default: no -p. main.cpp:75-134 estimates the identity (ANI), adopts it and re-derives the sketch size before mapping
+    P2 = pipeline.auto_identity(seqs, seqs, pipeline.Params(percentage_identity=None))
+    R = P2.resolved()
+    ids = pipeline.SequenceIds(seqs, seqs, R.prefix_delim)
+    fake = pipeutil.OracleIndex(oracle, [s for _, s in seqs], [ids.id_of[x] for x, _ in seqs], ids.group, R.kmer_size, R.window_length, R.sketch_size, R.max_kmer_freq, 1)
+    r = fake.map_fragments(None, [0] * sum(len(s) // 1000 + (1 if len(s) %% 1000 and len(s) >= 1000 else 0) for _, s in seqs), None,
+                           max(-1, wb.estimate_minimum_hits_relaxed(R.sketch_size, 15, R.percentage_identity)), wb.sketch_cutoffs(R.sketch_size, 15), None,
+                           stage1_min_hits=wb.stage1_min_hits(15, R.sketch_size), l2_min_shared=wb.l2_min_shared_relaxed(R.percentage_identity, 15, R.sketch_size))
+    maps, off = np.ascontiguousarray(r["mappings"]), np.ascontiguousarray(r["offset"], dtype=np.int64)
+    wb.lib().wfb_emu_inject_l2(ctypes.c_void_p(maps.ctypes.data), ctypes.c_void_p(off.ctypes.data), ctypes.c_int64(len(off) - 1))
+    ours, st = wb.map_phase(seqs, seqs, wb.MapPhaseParams())          # percentage_identity <= 0: the C phase estimates it itself
+    S = util.load_ref("libstatsref.so")
+    from tests import aniutil
+    ref_id = aniutil.reference_identity(S, seqs, seqs) if S is not None else None
+    ref = pipeutil.reference_map_phase(M, seqs, P2)
+    out["auto"] = {"identity_equal": bool(ref_id is None or np.float32(ref_id) == np.float32(st.percentage_identity)), "sketch": [int(st.sketch_size), R.sketch_size],
+                   "text_equal": sorted(ours.split(b"\n")) == sorted(ref.split(b"\n")), "rows": ref.count(b"\n"), "identity": float(st.percentage_identity)}
 print(json.dumps(out))
 """
 
@@ -130,3 +147,5 @@ def test_c_map_phase_host_half_equals_the_reference_mapper_under_emulation():
     if not res["have_ref"]:
         pytest.skip("oracle/_ref not built (reference sources absent)")
     assert res["bad"] == [] and res["n"] > 120
+    a = res["auto"]   # ANI auto-identity (the reference's estimate_identity_for_groups) -> sketch size -> mapping, all inside the one C call
+    assert a["identity_equal"] and a["sketch"][0] == a["sketch"][1] and a["text_equal"] and a["rows"] >= 3 and 0.8 < a["identity"] < 0.99

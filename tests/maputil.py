@@ -219,14 +219,15 @@ def stage1_table(oracle, hg, ani_diff, k, s):
     return t
 
 
-def oracle_map_fragments(oracle, index, seqs, ids, groups, k, w, s, mode=(1, 1, 0, 3), stage1=True, min_shared=None, hg=1.0, ani_diff=0.0, cut=None):
+def oracle_map_fragments(oracle, index, seqs, ids, groups, k, w, s, mode=(1, 1, 0, 3), stage1=True, min_shared=None, hg=1.0, ani_diff=0.0, cut=None, ref_group=None):
     """Map::mapSingleQueryFrag's L1 + L2 stages through the oracle for every fragment of every sequence. Returns
     (frag_list, q_all[n, s] MDT, q_count[n], loci rows (frag, seqId, start, end, isz), mappings L2MAPDT sorted by
     (frag, refSeqId, refStartPos))."""
     kept, pts, uh, us, uc, _ = index
     kept = np.ascontiguousarray(kept)
     cut = np.array([max(1, int(i * 0.5)) for i in range(1001)], dtype=np.int32) if cut is None else np.ascontiguousarray(cut, dtype=np.int32)
-    grp = np.array(groups, dtype=np.int32)
+    # groups[qi] = group of query qi; the table indexed by target seqId is the same list unless the queries are not the targets
+    grp = np.array(groups if ref_group is None else ref_group, dtype=np.int32)
     ss, sp, lt, mh = mode
     oracle.orc_l2_fragment.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]

@@ -136,8 +136,9 @@ class _RefMapParams(ctypes.Structure):
                 ("scaffold_overlap_threshold", ctypes.c_double), ("max_kmer_freq", ctypes.c_double)]
 
 
-def reference_map_phase(M, seqs, P, threads=1):
-    """The reference's UNMODIFIED skch::Map (oracle/ref_mapper_driver.cpp -> libmapperref.so): the whole `wfmash -m` run, all-vs-all."""
+def reference_map_phase(M, seqs, P, threads=1, queries=None):
+    """The reference's UNMODIFIED skch::Map (oracle/ref_mapper_driver.cpp -> libmapperref.so): the whole `wfmash -m` run; all-vs-all over
+    `seqs`, or `queries` (a second FASTA) against `seqs`."""
     import ctypes, tempfile
     P = P.resolved()
     F = P.filter
@@ -149,8 +150,12 @@ def reference_map_phase(M, seqs, P, threads=1):
     n = len(seqs)
     names = (ctypes.c_char_p * n)(*[a.encode() for a, _ in seqs]); sq = (ctypes.c_char_p * n)(*[b for _, b in seqs]); ln = (ctypes.c_int64 * n)(*[len(b) for _, b in seqs])
     buf = ctypes.create_string_buffer(64 << 20)
+    qn, qs, ql, nq, same = names, sq, ln, n, 1
+    if queries is not None:
+        nq, same = len(queries), 0
+        qn = (ctypes.c_char_p * nq)(*[a.encode() for a, _ in queries]); qs = (ctypes.c_char_p * nq)(*[b for _, b in queries]); ql = (ctypes.c_int64 * nq)(*[len(b) for _, b in queries])
     with tempfile.TemporaryDirectory() as d:
-        k = M.ref_map_phase(d.encode(), ctypes.byref(prm), names, sq, ln, n, names, sq, ln, n, 1, buf, ctypes.c_int64(len(buf)))
+        k = M.ref_map_phase(d.encode(), ctypes.byref(prm), names, sq, ln, n, qn, qs, ql, nq, same, buf, ctypes.c_int64(len(buf)))
     assert k >= 0
     return buf.raw[:k]
 
@@ -159,16 +164,20 @@ class OracleIndex:
     """Stands in for wb.Index in CPU tests of pipeline.map's HOST half: map_fragments answers from the oracle's mapping restatement
     (the GPU kernels are compared with that same restatement in tests/test_gpu_parity.py)."""
 
-    def __init__(self, oracle, seqs, ids, groups, k, w, s, F, threads):
+    def __init__(self, oracle, seqs, ids, groups, k, w, s, F, threads, queries=None):
+        """seqs / ids: the targets; groups: group of every sequence id; queries: [(seq, id)] when they are not the targets."""
         self.o, self.seqs, self.ids, self.groups, self.k, self.w, self.s = oracle, seqs, ids, groups, k, w, s
+        self.q = queries if queries is not None else list(zip(seqs, ids))
         self.index = maputil.oracle_index(oracle, [maputil.clean(x) for x in seqs], ids, k, w, s, F, threads)
 
     def map_fragments(self, blob, frags, fqs, minimum_hits, cutoffs, grp, skip_self=True, skip_prefix=True, lower_triangular=False, stage1_min_hits=None,
                       l2_min_shared=None, **kw):
         import wfmash_b200 as wb
-        frs, _, _, _, mp = maputil.oracle_map_fragments(self.o, self.index, self.seqs, self.ids, self.groups, self.k, self.w, self.s,
+        qs = [x for x, _ in self.q if len(x) >= self.w]
+        qi = [i for x, i in self.q if len(x) >= self.w]
+        frs, _, _, _, mp = maputil.oracle_map_fragments(self.o, self.index, qs, qi, [self.groups[i] for i in qi], self.k, self.w, self.s,
                                                         mode=(int(skip_self), int(skip_prefix), int(lower_triangular), minimum_hits),
-                                                        stage1=stage1_min_hits is not None, min_shared=l2_min_shared, cut=cutoffs)
+                                                        stage1=stage1_min_hits is not None, min_shared=l2_min_shared, cut=cutoffs, ref_group=self.groups)
         assert len(frs) == len(frags)   # the same fragments in the same order (every sequence is both target and query)
         out = np.zeros(len(mp), dtype=wb.L2_MAPPING_DTYPE)
         for f in ("frag", "refSeqId", "refStartPos", "optimalStart", "optimalEnd", "conservedSketches", "strand", "nucIdentity", "kmerComplexity"):

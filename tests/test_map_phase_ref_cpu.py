@@ -149,3 +149,32 @@ def test_c_map_phase_host_half_equals_the_reference_mapper_under_emulation():
     assert res["bad"] == [] and res["n"] > 120
     a = res["auto"]   # ANI auto-identity (the reference's estimate_identity_for_groups) -> sketch size -> mapping, all inside the one C call
     assert a["identity_equal"] and a["sketch"][0] == a["sketch"][1] and a["text_equal"] and a["rows"] >= 3 and 0.8 < a["identity"] < 0.99
+
+
+@pytest.mark.ref
+def test_pipeline_host_half_with_a_separate_query_file_equals_the_reference_mapper(oracle):
+    """target.fa != query.fa: a query that is also a target keeps its id, new queries get ids after the targets (sequenceIds.hpp:358-373), groups span
+    both files; -L compares ids across the two sets."""
+    from wfmash_b200 import pipeline
+    from wfmash_b200 import synth
+    import numpy as np
+    M = util.load_ref("libmapperref.so")
+    if M is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    base = pipeutil.case(seed=17, length=20_000)
+    rng = np.random.default_rng(3)
+    novel = ("d#2#chrX", synth.mutate(np.frombuffer(base[0][1].upper(), dtype=np.uint8), 0.06, rng).tobytes())
+    targets = base[:3]
+    queries = [base[1], novel, ("b#1#extra", base[2][1][2000:9000])]
+    n = 0
+    for name, prm in [("defaults", dict()), ("lower_triangular", dict(lower_triangular=True)), ("no_prefix_skip", dict(skip_prefix=False))]:
+        P = pipeutil.params(prm)
+        R = P.resolved()
+        ids = pipeline.SequenceIds(targets, queries, R.prefix_delim if R.skip_prefix else "")
+        fake = pipeutil.OracleIndex(oracle, [s for _, s in targets], [ids.id_of[x] for x, _ in targets], ids.group, R.kmer_size, R.window_length, R.sketch_size,
+                                    R.max_kmer_freq, R.index_threads, queries=[(s, ids.id_of[x]) for x, s in queries])
+        ours = sorted(x for x in pipeline.map(targets, queries, P, index=fake).paf.split(b"\n") if x)
+        ref = sorted(x for x in pipeutil.reference_map_phase(M, targets, P, queries=queries).split(b"\n") if x)
+        assert ours == ref, name
+        n += len(ref)
+    assert n > 20

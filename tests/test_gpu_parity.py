@@ -444,43 +444,6 @@ def test_do_biwfa_alignment_paf_lines_match_reference(wb):
     al.close()
 
 
-def test_pipeline_map_align_matches_reference_pieces(wb, oracle):
-    # SURVEY 8 f2 + b3 + both hot paths chained: sequences -> index -> L1/L2 kernels -> host chain merge + filters -> mapping
-    # PAF -> padded records -> biWFA kernels + patches -> alignment PAF, against the run composed from the reference-side
-    # pieces (tests/pipeutil.py): committed fixture always, live when oracle/_ref travelled with the snapshot.
-    import gzip, json, os
-    from tests import pipeutil
-    from wfmash_b200 import pipeline
-    with gzip.open(os.path.join(util.GOLD, "pipeline_reference.json.gz"), "rt") as f:
-        gold = json.load(f)
-    fref, wref = util.load_ref("libfilterref.so"), util.load_wflign_ref()
-    assert [c["name"] for c in gold["cases"]] == [c[0] for c in pipeutil.PIPELINE_CASES]
-    for (name, gen, prm), g in zip(pipeutil.PIPELINE_CASES, gold["cases"]):
-        seqs = pipeutil.case(**gen)
-        P = pipeutil.params(prm)
-        paf, st = pipeline.wfmash(seqs, seqs, P)
-        assert sorted(st["mapping_paf"].decode().splitlines()) == sorted(g["mapping_paf"].splitlines()), name
-        # the alignment lines follow the order of the mapping PAF (grouped by query, sorted by query start with the
-        # reference's unstable sort): compare as multisets of (first 12 columns, digest of the whole line)
-        got = sorted((d["head"], d["sha"]) for d in map(pipeutil.line_digest, [ln + b"\n" for ln in paf.split(b"\n") if ln]))
-        want = sorted((d["head"], d["sha"]) for d in g["lines"] if d["head"])
-        assert got == want, name
-        assert st["written"] == len(want) and st["aligned_bp"] > 0
-        # the same run through the two one-call C-ABI phases (wfmash_b200/csrc/phases_host.cu)
-        mp_c, mst = wb.map_phase(seqs, seqs, wb.MapPhaseParams(filter=P.filter, window_length=P.window_length, percentage_identity=P.percentage_identity))
-        assert mp_c == st["mapping_paf"], name
-        al = wb.Aligner(0)
-        paf_c, ast = wb.align_phase(al, mp_c, seqs, seqs, window_length=P.window_length, disable_chain_patching=P.disable_chain_patching)
-        al.close()
-        assert paf_c == paf and ast.records == st["records"] and ast.aligned_bp == st["aligned_bp"], name
-        if fref is not None and wref is not None and name == "defaults_p90":
-            mp, lines = pipeutil.expected(seqs, P, oracle, fref, wref)
-            assert st["mapping_paf"] == mp and paf == b"".join(lines)
-            A = util.load_ref("libalignref.so")   # the reference's whole alignment phase (align::Aligner::compute) on our mapping PAF
-            if A is not None:
-                assert pipeutil.reference_align_phase(A, mp_c, seqs, P) == paf_c
-
-
 def test_ani_auto_identity_matches_reference(wb, oracle):
     # group MinHash sketches from ani_hash_kernel (threshold filter + segmented radix sort) against the oracle's
     # literal StreamingMinHash restatement, and the adopted identity against the doubles the reference's UNMODIFIED
@@ -525,19 +488,6 @@ def test_ani_auto_identity_matches_reference(wb, oracle):
     assert (np.sort(np.concatenate(parts))[:4096] == sk[0]).all()
 
 
-def test_pipeline_auto_identity_then_map(wb):
-    # the CLI default (-p ani50-2): estimate, adopt, re-derive the sketch size, map with it
-    from tests import pipeutil
-    from wfmash_b200 import pipeline
-    seqs = pipeutil.case(seed=5, length=60_000)
-    P = pipeline.auto_identity(seqs, seqs, pipeline.Params(percentage_identity=None))
-    assert 0.85 < P.percentage_identity < 0.97 and P.sketch_size == wb.sketch_size(P.percentage_identity, 1000, 15)
-    m = pipeline.map(seqs, seqs, P)
-    assert m.stats["mappings"] >= 6 and m.paf.count(b"\n") == m.stats["mappings"]
-    mp_c, mst = wb.map_phase(seqs, seqs, wb.MapPhaseParams())   # percentage_identity <= 0: the C phase estimates it itself
-    assert abs(mst.percentage_identity - P.percentage_identity) < 1e-6 and mst.sketch_size == P.sketch_size and mp_c == m.paf
-
-
 def test_index_import_and_file_round_trip_map_identically(wb, tmp_path):
     # wfb_index_import of an exported index, and of the same index after a trip through the reference's file
     # format, must map exactly like the index built from the sequences
@@ -569,3 +519,54 @@ def test_index_import_and_file_round_trip_map_identically(wb, tmp_path):
     assert run(ix3) == base and all((a == b).all() for a, b in zip(ix3.export()[1:], exported[1:]))
     for i in (ix, ix2, ix3):
         i.close()
+
+
+
+def test_pipeline_map_align_matches_reference_pieces(wb, oracle):
+    # SURVEY 8 f2 + b3 + both hot paths chained: sequences -> index -> L1/L2 kernels -> host chain merge + filters -> mapping
+    # PAF -> padded records -> biWFA kernels + patches -> alignment PAF, against the run composed from the reference-side
+    # pieces (tests/pipeutil.py): committed fixture always, live when oracle/_ref travelled with the snapshot.
+    import gzip, json, os
+    from tests import pipeutil
+    from wfmash_b200 import pipeline
+    with gzip.open(os.path.join(util.GOLD, "pipeline_reference.json.gz"), "rt") as f:
+        gold = json.load(f)
+    fref, wref = util.load_ref("libfilterref.so"), util.load_wflign_ref()
+    assert [c["name"] for c in gold["cases"]] == [c[0] for c in pipeutil.PIPELINE_CASES]
+    for (name, gen, prm), g in zip(pipeutil.PIPELINE_CASES, gold["cases"]):
+        seqs = pipeutil.case(**gen)
+        P = pipeutil.params(prm)
+        paf, st = pipeline.wfmash(seqs, seqs, P)
+        assert sorted(st["mapping_paf"].decode().splitlines()) == sorted(g["mapping_paf"].splitlines()), name
+        # the alignment lines follow the order of the mapping PAF (grouped by query, sorted by query start with the
+        # reference's unstable sort): compare as multisets of (first 12 columns, digest of the whole line)
+        got = sorted((d["head"], d["sha"]) for d in map(pipeutil.line_digest, [ln + b"\n" for ln in paf.split(b"\n") if ln]))
+        want = sorted((d["head"], d["sha"]) for d in g["lines"] if d["head"])
+        assert got == want, name
+        assert st["written"] == len(want) and st["aligned_bp"] > 0
+        # the same run through the two one-call C-ABI phases (wfmash_b200/csrc/phases_host.cu)
+        mp_c, mst = wb.map_phase(seqs, seqs, wb.MapPhaseParams(filter=P.filter, window_length=P.window_length, percentage_identity=P.percentage_identity))
+        assert mp_c == st["mapping_paf"], name
+        al = wb.Aligner(0)
+        paf_c, ast = wb.align_phase(al, mp_c, seqs, seqs, window_length=P.window_length, disable_chain_patching=P.disable_chain_patching)
+        al.close()
+        assert paf_c == paf and ast.records == st["records"] and ast.aligned_bp == st["aligned_bp"], name
+        if fref is not None and wref is not None and name == "defaults_p90":
+            mp, lines = pipeutil.expected(seqs, P, oracle, fref, wref)
+            assert st["mapping_paf"] == mp and paf == b"".join(lines)
+            A = util.load_ref("libalignref.so")   # the reference's whole alignment phase (align::Aligner::compute) on our mapping PAF
+            if A is not None:
+                assert pipeutil.reference_align_phase(A, mp_c, seqs, P) == paf_c
+
+
+def test_pipeline_auto_identity_then_map(wb):
+    # the CLI default (-p ani50-2): estimate, adopt, re-derive the sketch size, map with it
+    from tests import pipeutil
+    from wfmash_b200 import pipeline
+    seqs = pipeutil.case(seed=5, length=60_000)
+    P = pipeline.auto_identity(seqs, seqs, pipeline.Params(percentage_identity=None))
+    assert 0.85 < P.percentage_identity < 0.97 and P.sketch_size == wb.sketch_size(P.percentage_identity, 1000, 15)
+    m = pipeline.map(seqs, seqs, P)
+    assert m.stats["mappings"] >= 6 and m.paf.count(b"\n") == m.stats["mappings"]
+    mp_c, mst = wb.map_phase(seqs, seqs, wb.MapPhaseParams())   # percentage_identity <= 0: the C phase estimates it itself
+    assert abs(mst.percentage_identity - P.percentage_identity) < 1e-6 and mst.sketch_size == P.sketch_size and mp_c == m.paf

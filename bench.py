@@ -159,7 +159,7 @@ def run_cpu_sample(recs, target_s, threads):
         sample.append(r)
         acc += c
     bp, dt = cpu_align_records(lib, kind, sample, threads)
-    return {"value": bp / dt, "unit": UNIT, "cores": threads, "kind": kind,
+    return {"value": bp / dt, "unit": UNIT, "cores": threads, "kind": kind, "sample_ms": 1e3 * dt,
             "sample": f"first {len(sample)} of {len(recs)} records of the step ({bp} query bp), {dt:.1f} s wall on {threads} threads"}
 
 
@@ -500,15 +500,16 @@ def main():
         if rank != 0:
             return 0
         recs = make_records(0, args.records or None)
-        vals, last = [], None
+        vals, ms, last = [], [], None
         for i in range(args.warmup + args.steps):
             last = run_cpu_sample(recs, max(2.0, args.cpu_seconds / max(1, args.steps)), cores)
             if i >= args.warmup:
                 vals.append(last["value"])
+                ms.append(last["sample_ms"])
         v = statistics.mean(vals)
         last["value"] = v
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": dict(WORKLOAD), "cpu_baseline": last,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))

@@ -10,7 +10,7 @@ if [ -f "$OUT" ] && [ "$(cat tests/emu/_build/defs 2>/dev/null)" = "$EMU_DEFS" ]
    [ -z "$(find wfmash_b200/csrc include tests/emu/build_emu.sh -newer "$OUT" -type f | head -1)" ]; then
   echo "$OUT"; exit 0
 fi
-g++ -O2 -g -std=c++17 -DWFB_EMU $EMU_DEFS -fPIC -Wall -Wno-unused-function -Wno-unused-variable -Wno-maybe-uninitialized \
+g++ -O2 -g -std=c++17 -DWFB_EMU -DWFB_HOST_PAR_MIN_BYTES=0 $EMU_DEFS -fPIC -Wall -Wno-unused-function -Wno-unused-variable -Wno-maybe-uninitialized \
     -Wno-unknown-pragmas -Wno-unused-but-set-variable -Iinclude \
     -x c++ wfmash_b200/csrc/wfa_host.cu -x c++ wfmash_b200/csrc/sketch.cu -x c++ wfmash_b200/csrc/minmer_host.cu \
     -x c++ wfmash_b200/csrc/epilogue.cu -x c++ wfmash_b200/csrc/index_host.cu -x c++ wfmash_b200/csrc/chain_host.cu \

@@ -11,10 +11,12 @@
  * CIGAR strings; the run vector is formatted to text once, when the PAF line is written.
  */
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "wfmash_b200.h"
@@ -362,6 +364,34 @@ struct Patch {
   Erosion er;
 };
 
+/* The per-record host loops (run-length conversion of the kernels' ops, erosion scans, PAF / SAM text) are independent per
+ * record: spread them over the host cores the way the reference spreads records over its worker threads
+ * (computeAlignments.hpp:695-720). Records are taken in blocks of `grain` from an atomic counter; every result lands in
+ * its own slot, so the output does not depend on the schedule. */
+#ifndef WFB_HOST_PAR_MIN_BYTES
+#define WFB_HOST_PAR_MIN_BYTES (1 << 20) /* tests build the emulation with 0 to force the threaded path on small cases */
+#endif
+template <class F>
+void for_each_record(int64_t n, int64_t work_bytes, F f) {
+  int nt = (int)std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 32u), n / 4);
+  if (work_bytes < (int64_t)WFB_HOST_PAR_MIN_BYTES) nt = 1; /* small batches: a thread launch costs more than the loop */
+  if (nt <= 1) { for (int64_t i = 0; i < n; ++i) f(i); return; }
+  const int64_t grain = std::max<int64_t>(1, n / (8 * (int64_t)nt));
+  std::atomic<int64_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int64_t b = next.fetch_add(grain);
+      if (b >= n) return;
+      const int64_t e = std::min(n, b + grain);
+      for (int64_t i = b; i < e; ++i) f(i);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
+}
+
 /* Runs one round of ends-free patches and splices the results into cig[]. head: the patch replaces runs [0,cut);
  * otherwise runs [cut,size). */
 int patch_round(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& cig, std::vector<int32_t>& status, bool head, int term_group) {
@@ -370,7 +400,7 @@ int patch_round(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& 
     if (status[i] != WFB_REC_WRITTEN) continue;
     Patch p;
     p.rec = (int)i;
-    p.er = head ? erode_head(cig[i]) : erode_tail(cig[i]);
+    p.er = head ? erode_head(cig[i]) : erode_tail(cig[i]); /* O(runs of the eroded end): not worth a thread */
     if (p.er.q > 3 || p.er.t > 3) all.push_back(p);
   }
   if (all.empty()) return WFB_OK;
@@ -450,10 +480,10 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
   if (rc != WFB_OK) return rc;
   std::vector<Cigar> cig((size_t)n);
   std::vector<int32_t> status((size_t)n, WFB_REC_WRITTEN);
-  for (int i = 0; i < n; ++i) {
-    if (res[(size_t)i].status != 0) { status[(size_t)i] = WFB_REC_UNALIGNED; continue; } /* wflign.cpp:150-152 */
+  for_each_record(n, cap, [&](int64_t i) {
+    if (res[(size_t)i].status != 0) { status[(size_t)i] = WFB_REC_UNALIGNED; return; } /* wflign.cpp:150-152 */
     cig[(size_t)i] = rle(ops.data() + res[(size_t)i].ops_offset, res[(size_t)i].ops_len);
-  }
+  });
   std::vector<char>().swap(ops);
   if (!params->disable_chain_patching) {
     rc = patch_round(a, recs, cig, status, true, term_group);
@@ -461,22 +491,24 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     rc = patch_round(a, recs, cig, status, false, term_group);
     if (rc != WFB_OK) return rc;
   }
-  std::string text;
-  for (int i = 0; i < n; ++i) {
-    line_offset[i] = (int64_t)text.size();
+  std::vector<std::string> line((size_t)n);
+  for_each_record(n, cap, [&](int64_t i) {
     rec_status[i] = status[(size_t)i];
-    if (status[(size_t)i] != WFB_REC_WRITTEN) continue;
+    if (status[(size_t)i] != WFB_REC_WRITTEN) return;
     const wfb_record_t& r = recs[i];
     /* the reference builds std::string(query) / std::string(target) from the char* (wflign.cpp:422-430): NUL-terminated views */
     const size_t qn = strnlen(r.query, (size_t)r.query_length), tn = strnlen(r.target, (size_t)r.target_length);
     Cigar& c = cig[(size_t)i];
     swap_start(c, r.query, qn, r.target, tn);
     swap_end(c, r.query, qn, r.target, tn);
-    if (!(params->sam_format ? write_sam(text, c, r, *params) : write_paf(text, c, r, *params))) rec_status[i] = WFB_REC_FILTERED;
-  }
-  line_offset[n] = (int64_t)text.size();
-  *out_len = (int64_t)text.size();
-  if ((int64_t)text.size() > out_cap || !out) { wfb_set_last_error("PAF output buffer too small (see *out_len)"); return WFB_ECAP; }
-  memcpy(out, text.data(), text.size());
+    std::string& text = line[(size_t)i];
+    if (!(params->sam_format ? write_sam(text, c, r, *params) : write_paf(text, c, r, *params))) { rec_status[i] = WFB_REC_FILTERED; text.clear(); }
+  });
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) { line_offset[i] = total; total += (int64_t)line[(size_t)i].size(); }
+  line_offset[n] = total;
+  *out_len = total;
+  if (total > out_cap || !out) { wfb_set_last_error("PAF output buffer too small (see *out_len)"); return WFB_ECAP; }
+  for (int i = 0; i < n; ++i) memcpy(out + line_offset[i], line[(size_t)i].data(), line[(size_t)i].size());
   return WFB_OK;
 }

@@ -8,9 +8,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -290,9 +292,9 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
   for (const char* p = "ACGT"; *p; ++p) { clean[(unsigned char)*p] = (unsigned char)*p; clean[(unsigned char)(*p + 32)] = (unsigned char)*p; }
   comp['A'] = 'T'; comp['C'] = 'G'; comp['G'] = 'C'; comp['T'] = 'A';
 
-  struct Rec { std::string qname, tname, query, target; wfb_mapping_row_t row; };
+  struct Rec { std::string qname, tname, query, target; wfb_mapping_row_t row; const wfb_seq_t *qs, *ts; int64_t q0, q1, t0, t1; };
   std::vector<Rec> recs;
-  int64_t skipped = 0;
+  int64_t skipped = 0, slice_bytes = 0;
   uint64_t aligned_bp = 0;
   for (int64_t a = 0; a < mapping_paf_len;) {
     const char* nl = (const char*)memchr(mapping_paf + a, '\n', (size_t)(mapping_paf_len - a));
@@ -311,11 +313,8 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
           const int64_t t0 = std::min(r.row.r_start, ti->second->len), t1 = std::min(r.row.r_end, ti->second->len);
           if (q1 <= q0 || t1 <= t0) ++skipped;
           else {
-            r.target.resize((size_t)(t1 - t0));
-            for (int64_t i = 0; i < t1 - t0; ++i) r.target[(size_t)i] = (char)clean[(unsigned char)ti->second->seq[t0 + i]];
-            r.query.resize((size_t)(q1 - q0));
-            if (r.row.strand == 1) for (int64_t i = 0; i < q1 - q0; ++i) r.query[(size_t)i] = (char)clean[(unsigned char)qi->second->seq[q0 + i]];
-            else for (int64_t i = 0; i < q1 - q0; ++i) r.query[(size_t)i] = (char)comp[clean[(unsigned char)qi->second->seq[q1 - 1 - i]]];
+            r.qs = qi->second; r.ts = ti->second; r.q0 = q0; r.q1 = q1; r.t0 = t0; r.t1 = t1;
+            slice_bytes += (q1 - q0) + (t1 - t0);
             aligned_bp += (uint64_t)(r.row.q_end - r.row.q_start);
             recs.push_back(std::move(r));
           }
@@ -323,6 +322,31 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
       }
     }
     a = b + 1;
+  }
+  /* the records' slices (upper-cased, N-masked, query strand-corrected), over the host cores: records are independent */
+  {
+    const int64_t nrec = (int64_t)recs.size();
+    int nt = (int)std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 32u), nrec / 4);
+#ifndef WFB_HOST_PAR_MIN_BYTES
+#define WFB_HOST_PAR_MIN_BYTES (1 << 20)
+#endif
+    if (slice_bytes < (int64_t)WFB_HOST_PAR_MIN_BYTES) nt = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+      for (int64_t i; (i = next.fetch_add(1)) < nrec;) {
+        Rec& r = recs[(size_t)i];
+        const int64_t tn = r.t1 - r.t0, qn = r.q1 - r.q0;
+        r.target.resize((size_t)tn);
+        for (int64_t j = 0; j < tn; ++j) r.target[(size_t)j] = (char)clean[(unsigned char)r.ts->seq[r.t0 + j]];
+        r.query.resize((size_t)qn);
+        if (r.row.strand == 1) for (int64_t j = 0; j < qn; ++j) r.query[(size_t)j] = (char)clean[(unsigned char)r.qs->seq[r.q0 + j]];
+        else for (int64_t j = 0; j < qn; ++j) r.query[(size_t)j] = (char)comp[clean[(unsigned char)r.qs->seq[r.q1 - 1 - j]]];
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
   }
   std::string text;
   int64_t written = 0;
@@ -338,9 +362,9 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
       const Rec& r = recs[i];
       wfb_record_t& w = arr[i - b0];
       memset(&w, 0, sizeof w);
-      w.query_name = r.qname.c_str(); w.query = r.query.data(); w.query_total_length = (uint64_t)qmap[r.qname]->len; w.query_offset = (uint64_t)r.row.q_start;
+      w.query_name = r.qname.c_str(); w.query = r.query.data(); w.query_total_length = (uint64_t)r.qs->len; w.query_offset = (uint64_t)r.row.q_start;
       w.query_length = (uint64_t)r.query.size(); w.query_is_rev = r.row.strand != 1; w.chain_id = (int32_t)r.row.chain_id;
-      w.target_name = r.tname.c_str(); w.target = r.target.data(); w.target_total_length = (uint64_t)tmap[r.tname]->len; w.target_offset = (uint64_t)r.row.r_start;
+      w.target_name = r.tname.c_str(); w.target = r.target.data(); w.target_total_length = (uint64_t)r.ts->len; w.target_offset = (uint64_t)r.row.r_start;
       w.target_length = (uint64_t)r.target.size(); w.chain_length = (int32_t)r.row.chain_length; w.chain_pos = (int32_t)r.row.chain_pos;
       w.mashmap_estimated_identity = r.row.mashmap_estimated_identity;
       bytes += (r.query.size() + r.target.size()) * (params->output.sam_format ? 2 : 1) + 1024;

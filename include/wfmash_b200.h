@@ -610,8 +610,10 @@ typedef struct {
   int64_t fragments, l2_mappings, mappings; /* query fragments, fragment mappings before / after the filters */
   int32_t sketch_size, minimum_hits;        /* as resolved                                                   */
   float percentage_identity;                /* as resolved (estimated when the parameter was <= 0)           */
-  int32_t reserved_;
+  int32_t stale_absorbed;                   /* wfb_minmer_stats_t::stale_absorbed of the index build (saturating): 0 = the
+                                               windowed minmers are provably those of the reference's addMinmers */
   double index_seconds, map_kernel_ms, filter_seconds, total_seconds;
+  double ani_seconds;                       /* ANI auto-identity (0 when -p was given)                        */
 } wfb_map_phase_stats_t;
 
 /* Mapping phase: ids + PanSN groups (SequenceIdManager, sequenceIds.hpp:284-441; targets first), optional ANI estimate,

@@ -768,8 +768,8 @@ class MapPhaseParams(ctypes.Structure):
 
 class MapPhaseStats(ctypes.Structure):
     _fields_ = [("fragments", ctypes.c_int64), ("l2_mappings", ctypes.c_int64), ("mappings", ctypes.c_int64), ("sketch_size", ctypes.c_int32),
-                ("minimum_hits", ctypes.c_int32), ("percentage_identity", ctypes.c_float), ("reserved_", ctypes.c_int32), ("index_seconds", ctypes.c_double),
-                ("map_kernel_ms", ctypes.c_double), ("filter_seconds", ctypes.c_double), ("total_seconds", ctypes.c_double)]
+                ("minimum_hits", ctypes.c_int32), ("percentage_identity", ctypes.c_float), ("stale_absorbed", ctypes.c_int32), ("index_seconds", ctypes.c_double),
+                ("map_kernel_ms", ctypes.c_double), ("filter_seconds", ctypes.c_double), ("total_seconds", ctypes.c_double), ("ani_seconds", ctypes.c_double)]
 
 
 class AlignPhaseParams(ctypes.Structure):

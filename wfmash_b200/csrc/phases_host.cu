@@ -67,6 +67,39 @@ char* to_c_text(const std::string& s) {
 
 extern "C" void wfb_free_text(char* text) { free(text); }
 
+/* The order in which a ONE-worker taskflow executor (`wfmash -t 1`) runs the fragment tasks of every query = the order in which their
+ * results reach Map::filterSubsetMappings, which decides the ch:Z: tags (computeMap.hpp:532-640). n_frag[q] = fragment tasks of the
+ * q-th entry of querySequenceNames (0 for sequences shorter than the segment length: they still get a query task). Restates the
+ * executor's scheduling (src/common/taskflow/core/executor.hpp:1271-1310,1452-1493; tsq.hpp:436-484 with
+ * TF_DEFAULT_BOUNDED_TASK_QUEUE_LOG_SIZE 8 => 255 usable slots): scheduled nodes go to the worker's bounded LIFO queue, overflow to the
+ * unbounded FIFO free list; a worker waiting in Subflow::join keeps popping its own queue (which may hold OTHER queries' tasks: they
+ * run nested inside the join) and takes from the free list only when its queue is empty. order[q] = fragment indices of query q. */
+static void one_thread_fragment_order(const std::vector<int64_t>& n_frag, std::vector<std::vector<int32_t>>& order) {
+  const size_t kQueueCapacity = 255;
+  struct Node { int32_t q, i; };
+  order.assign(n_frag.size(), {});
+  std::vector<int64_t> remaining(n_frag);
+  std::vector<Node> stack, fifo;
+  std::vector<int32_t> waiting;
+  size_t head = 0;
+  auto schedule = [&](Node n) { if (stack.size() < kQueueCapacity) stack.push_back(n); else fifo.push_back(n); };
+  for (size_t q = 0; q < n_frag.size(); ++q) schedule(Node{(int32_t)q, -1});
+  for (;;) {
+    if (!waiting.empty() && remaining[(size_t)waiting.back()] == 0) { waiting.pop_back(); continue; }
+    Node n;
+    if (!stack.empty()) { n = stack.back(); stack.pop_back(); }
+    else if (head < fifo.size()) n = fifo[head++];
+    else break;
+    if (n.i < 0) { /* a query task: emplaces its fragments, then joins */
+      for (int64_t j = 0; j < n_frag[(size_t)n.q]; ++j) schedule(Node{n.q, (int32_t)j});
+      waiting.push_back(n.q);
+    } else {
+      order[(size_t)n.q].push_back(n.i);
+      --remaining[(size_t)n.q];
+    }
+  }
+}
+
 #ifdef WFB_EMU
 /* TEST-ONLY (never in the product library): the index build and the mapping kernels are not part of the host emulation, so a test
  * injects the fragment mappings (the oracle's) and wfb_map_phase runs everything AROUND the device calls for real: ids, groups,
@@ -96,8 +129,11 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
   ids.add(queries, n_queries);
   ids.build_groups(P.skip_prefix ? P.prefix_delim : 0);
   int rc = WFB_OK;
+  int32_t stale_absorbed = 0;
+  double ani_seconds = 0;
 
-  if (!(P.percentage_identity > 0)) { /* main.cpp:75-134: ANI auto-identity, then the sketch size follows the estimate */
+  if (!(P.percentage_identity > 0)) {
+    const double t_ani = now_s(); /* main.cpp:75-134: ANI auto-identity, then the sketch size follows the estimate */
     std::vector<int32_t> gid(ids.group.begin(), ids.group.end());
     std::sort(gid.begin(), gid.end());
     gid.erase(std::unique(gid.begin(), gid.end()), gid.end());
@@ -121,6 +157,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
     P.percentage_identity = (float)wfb_ani_estimate_identity(qs.data(), qc.data(), qg.data(), (int32_t)qg.size(), ts.data(), tc.data(), tg.data(),
                                                             (int32_t)tg.size(), 4096, 21, P.ani_percentile, P.ani_adjustment, nullptr);
     if (params->sketch_size <= 0) P.sketch_size = (int32_t)std::min<int64_t>(wfb_sketch_size(P.percentage_identity, w, k), w);
+    ani_seconds = now_s() - t_ani;
   }
   if (P.sketch_size <= 0) P.sketch_size = wfb_sketch_size(P.percentage_identity, w, k);
   const int s = P.sketch_size;
@@ -133,7 +170,9 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
   ip.kmer_size = k; ip.window_size = (int32_t)w; ip.sketch_size = s; ip.index_threads = std::max(1, P.index_threads); ip.max_kmer_freq = P.max_kmer_freq;
   const double t_ix = now_s();
 #ifndef WFB_EMU
-  wfb_index_t* ix = wfb_index_build(device, &ip, tptr.data(), tlen.data(), tid.data(), n_targets, nullptr);
+  wfb_index_stats_t ixs; memset(&ixs, 0, sizeof ixs);
+  wfb_index_t* ix = wfb_index_build(device, &ip, tptr.data(), tlen.data(), tid.data(), n_targets, &ixs);
+  stale_absorbed = (int32_t)std::min<uint64_t>(ixs.minmer.stale_absorbed, 0x7fffffffu);
   if (!ix) return WFB_ECUDA; /* message already set */
 #else
   wfb_index_t* ix = nullptr;
@@ -210,14 +249,20 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
     std::vector<int64_t> q_off(1, 0), q_len;
     /* The order in which the fragments' results reach the chain merge decides the ch:Z: tags (chain ids rank the smallest ORIGINAL
      * index of each chain, mappingFilter.hpp:401-404,498-520). The reference appends them as its fragment tasks finish
-     * (computeMap.hpp:590-597), i.e. in a schedule-dependent order; its only reproducible schedule is the one-thread run, where
-     * the taskflow subflow executes the LAST emplaced fragment first. That order is used here, so the text equals `wfmash -m -t 1`. */
+     * (computeMap.hpp:590-597), i.e. in a schedule-dependent order; its only reproducible schedule is the one-thread run
+     * (one_thread_fragment_order above). That order is used here, so the text equals `wfmash -m -t 1`. */
+    std::vector<int64_t> tasks((size_t)n_queries, 0);
+    for (size_t m = 0; m < mapped.size(); ++m) tasks[(size_t)mapped[m]] = q_frag[m + 1] - q_frag[m];
+    std::vector<std::vector<int32_t>> frag_order;
+    one_thread_fragment_order(tasks, frag_order);
     std::vector<wfb_l2_mapping_t> ordered;
     for (size_t m = 0; m < mapped.size(); ++m) {
       const int64_t a = moff[(size_t)q_frag[m]], b = moff[(size_t)q_frag[m + 1]];
       ordered.clear();
-      for (int64_t f = q_frag[m + 1] - 1; f >= q_frag[m]; --f)
+      for (int32_t fo : frag_order[(size_t)mapped[m]]) {
+        const int64_t f = q_frag[m] + fo;
         for (int64_t i = moff[(size_t)f]; i < moff[(size_t)f + 1]; ++i) ordered.push_back(maps[(size_t)i]);
+      }
       if ((rc = wfb_l2_to_query_mappings(ordered.data(), b - a, frag_index.data(), w, queries[mapped[m]].len, ids.lens.data(), all.data() + a)) != WFB_OK) break;
       q_off.push_back(b);
       q_len.push_back(queries[mapped[m]].len);
@@ -268,7 +313,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
     memset(stats, 0, sizeof *stats);
     stats->fragments = (int64_t)frags.size(); stats->l2_mappings = n_l2; stats->mappings = n_out; stats->sketch_size = s; stats->minimum_hits = min_hits;
     stats->percentage_identity = P.percentage_identity; stats->index_seconds = index_seconds; stats->map_kernel_ms = map_ms; stats->filter_seconds = filter_seconds;
-    stats->total_seconds = now_s() - t_begin;
+    stats->total_seconds = now_s() - t_begin; stats->stale_absorbed = stale_absorbed; stats->ani_seconds = ani_seconds;
   }
   return WFB_OK;
 }

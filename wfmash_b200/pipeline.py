@@ -122,6 +122,49 @@ def auto_identity(targets, queries, params: Params = None, device: int = 0) -> P
     return P
 
 
+def one_thread_fragment_order(n_fragments, queue_capacity: int = 255):
+    """The order in which a ONE-worker taskflow executor (`wfmash -t 1`) runs the fragment tasks of every query, which is the order
+    their results reach Map::filterSubsetMappings and therefore decides the ch:Z: tags (computeMap.hpp:532-640).
+
+    n_fragments[q] = number of fragment tasks of the q-th entry of querySequenceNames (0 for sequences shorter than the segment
+    length: they still get a query task). Restates the executor's scheduling (src/common/taskflow/core/executor.hpp:1271-1310,
+    1452-1493; tsq.hpp:436-484, TF_DEFAULT_BOUNDED_TASK_QUEUE_LOG_SIZE 8 => 255 usable slots): scheduled nodes go to the worker's
+    bounded LIFO queue, overflow to the unbounded FIFO free list; a worker waiting in Subflow::join keeps popping its own queue
+    (which may hold OTHER queries' tasks: they run nested) and takes from the free list only when the queue is empty.
+    -> list of per-query lists of fragment indices."""
+    order = [[] for _ in n_fragments]
+    remaining = list(n_fragments)
+    stack, fifo, head, waiting = [], [], 0, []
+
+    def schedule(node):
+        if len(stack) < queue_capacity:
+            stack.append(node)
+        else:
+            fifo.append(node)
+
+    for q in range(len(n_fragments)):
+        schedule((q, -1))
+    while True:
+        if waiting and remaining[waiting[-1]] == 0:
+            waiting.pop()
+            continue
+        if stack:
+            q, i = stack.pop()
+        elif head < len(fifo):
+            q, i = fifo[head]
+            head += 1
+        else:
+            break
+        if i < 0:  # a query task: emplaces its fragments, then joins
+            for j in range(n_fragments[q]):
+                schedule((q, j))
+            waiting.append(q)
+        else:
+            order[q].append(i)
+            remaining[q] -= 1
+    return order
+
+
 @dataclasses.dataclass
 class MapResult:
     paf: bytes                 # the `wfmash -m` text
@@ -179,12 +222,17 @@ def map(targets, queries, params: Params = None, device: int = 0, index=None, on
         index.close()
     fi = np.array(frag_index, dtype=np.int32)
     off = r["offset"]
+    # every query of the run has a task in the reference's executor, also the ones that map nothing (or that another rank maps)
+    nfr = {n: (len(seq) // w + (1 if len(seq) % w else 0) if len(seq) >= w else 0) for n, seq in queries}
+    all_order = one_thread_fragment_order([nfr[n] for n, _ in queries])
+    order_of = {n: o for (n, _), o in zip(queries, all_order)}
+    frag_order = [order_of[n] for n, _ in mapped]
     per_query, q_off = [], [0]
     for qi, (name, seq) in enumerate(mapped):
         # The order in which the fragments' results reach the chain merge decides the ch:Z: tags; the reference appends them as its
-        # fragment tasks finish (computeMap.hpp:590-597). Its only reproducible schedule is the one-thread run, where the taskflow
-        # subflow executes the LAST emplaced fragment first: use that order, so the text equals `wfmash -m -t 1`.
-        parts = [r["mappings"][off[f]: off[f + 1]] for f in range(q_frag[qi + 1] - 1, q_frag[qi] - 1, -1)]
+        # fragment tasks finish (computeMap.hpp:590-597). Its only reproducible schedule is the one-thread run: use that order
+        # (one_thread_fragment_order), so the text equals `wfmash -m -t 1`.
+        parts = [r["mappings"][off[q_frag[qi] + f]: off[q_frag[qi] + f + 1]] for f in frag_order[qi]]
         l2 = np.concatenate(parts) if parts else r["mappings"][:0]
         per_query.append(wb.l2_to_query_mappings(l2, fi, w, len(seq), ref_len))
         q_off.append(q_off[-1] + len(l2))

@@ -45,9 +45,9 @@ def run(wb, name, aligner=None, align=True, device=0):
     mp, mst = wb.map_phase(targets, queries, MP, device)
     t_map = time.perf_counter() - t0
     ours_m, ref_m = digests(mp, 14), sorted((d["head"], d["sha"]) for d in g["mapping"])
-    out = dict(name=name, mapping_paf=mp, map_seconds=t_map, map_stats=mst, mapping_rows=len(ours_m), mapping_identical=ours_m == ref_m,
+    out = dict(name=name, mapping_paf=mp, map_seconds=t_map, map_stats=mst, mapping_rows=len(ours_m), mapping_identical=bool(ours_m == ref_m),
                mapping_cols14_identical=[h for h, _ in ours_m] == [h for h, _ in ref_m],
-               identity_identical=np.float32(mst.percentage_identity) == np.float32(g["percentage_identity"]),
+               identity_identical=bool(np.float32(mst.percentage_identity) == np.float32(g["percentage_identity"])),
                mapping_only_ours=sorted(set(ours_m) - set(ref_m)), mapping_only_ref=sorted(set(ref_m) - set(ours_m)))
     if not align:
         return out

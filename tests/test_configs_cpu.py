@@ -103,6 +103,13 @@ for name in ("C2", "C3sub"):
     MP = wb.MapPhaseParams(filter=R.filter, kmer_size=R.kmer_size, window_length=w, percentage_identity=R.percentage_identity, sketch_size=R.sketch_size)
     ours, st = wb.map_phase(t, q, MP)
     out[name] = {"rows": ours.count(b"\n"), "sha": sha_sorted(ours)}
+# C1w250: fragments exist but none maps anywhere (the reads do not come from this reference): the phase must return empty text, not an error
+t, q = configs.sequences(configs.by_name("C1w250"))
+nf = sum(len(s) // 250 + (1 if len(s) %% 250 else 0) for _, s in q if len(s) >= 250)
+maps, off = np.zeros(1, dtype=wb.L2_MAPPING_DTYPE), np.zeros(nf + 1, dtype=np.int64)
+wb.lib().wfb_emu_inject_l2(ctypes.c_void_p(maps.ctypes.data), ctypes.c_void_p(off.ctypes.data), ctypes.c_int64(nf))
+ours, st = wb.map_phase(t, q, wb.MapPhaseParams(window_length=250, filter=wb.FilterParams(window_length=250)))
+out["C1w250"] = {"rows": ours.count(b"\n"), "sha": sha_sorted(ours), "fragments": int(st.fragments), "identity": float(st.percentage_identity)}
 print(json.dumps(out))
 """
 
@@ -115,5 +122,6 @@ def test_c_map_phase_host_half_on_the_real_inputs_equals_the_reference_text():
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     doc = golden()
-    for name in ("C2", "C3sub"):
+    for name in ("C2", "C3sub", "C1w250"):
         assert res[name]["rows"] == doc[name]["mapping_rows"] and res[name]["sha"] == doc[name]["mapping_sha_sorted"], name
+    assert res["C1w250"]["fragments"] == 16 and abs(res["C1w250"]["identity"] - doc["C1w250"]["percentage_identity"]) < 1e-7

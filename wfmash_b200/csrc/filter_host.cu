@@ -325,7 +325,8 @@ extern "C" int wfb_filter_mappings_batch(const wfb_filter_params_t* params, cons
                                          const int64_t* query_len, int32_t n_queries, const int32_t* ref_group, const int64_t* ref_seq_len,
                                          wfb_mapping_t* out, wfb_chain_info_t* out_chain, int64_t out_cap, int64_t* out_offset, int32_t host_threads) {
   if (!params_ok(params) || n_queries < 0 || !ref_seq_len || (params->skip_prefix && !ref_group) ||
-      (n_queries > 0 && (!mappings || !query_offset || !query_len || !out || !out_chain || !out_offset))) {
+      (n_queries > 0 && (!query_offset || !query_len || !out || !out_chain || !out_offset)) ||
+      (n_queries > 0 && query_offset && query_offset[n_queries] > query_offset[0] && !mappings)) { /* queries without any mapping need no array */
     wfb_set_last_error_("bad argument");
     return WFB_EINVAL;
   }

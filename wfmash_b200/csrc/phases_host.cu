@@ -245,7 +245,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
     if (rc != WFB_OK) { if (ix) wfb_index_free(ix); return rc; }
     const double t_f = now_s();
     /* per query: MappingResult construction + boundary check, then the chain / filter stage for the whole batch */
-    std::vector<wfb_mapping_t> all((size_t)n_l2);
+    std::vector<wfb_mapping_t> all((size_t)n_l2 + 1); /* + 1: never a null pointer, also when no fragment mapped anywhere */
     std::vector<int64_t> q_off(1, 0), q_len;
     /* The order in which the fragments' results reach the chain merge decides the ch:Z: tags (chain ids rank the smallest ORIGINAL
      * index of each chain, mappingFilter.hpp:401-404,498-520). The reference appends them as its fragment tasks finish

@@ -103,6 +103,12 @@ void wfb_aligner_destroy(wfb_aligner_t*);
 int wfb_align_batch(wfb_aligner_t*, const wfb_pair_t* pairs, int32_t n, char* ops, int64_t ops_cap,
                     wfb_aln_result_t* results, wfb_align_stats_t* stats);
 
+/* wfb_align_batch with a scheduling hint: cost_hint[i] ~ the expected number of edits of pair i (e.g. (1 - mapping identity) *
+ * length; any monotone proxy of the alignment score). The persistent kernel starts the most expensive pairs first, so the launch
+ * does not end with a few CTAs finishing heavy pairs alone. Results are independent of the hint. NULL = order by length. */
+int wfb_align_batch_hinted(wfb_aligner_t*, const wfb_pair_t* pairs, int32_t n, const float* cost_hint, char* ops, int64_t ops_cap,
+                           wfb_aln_result_t* results, wfb_align_stats_t* stats);
+
 /* Same with the sequences already resident in device memory (used by bench.py's HBM-resident
  * `value` leg). d_seq holds all sequences; pattern_off/text_off are byte offsets into it.
  * The results (ops + wfb_aln_result_t) still come back to the host buffers. */

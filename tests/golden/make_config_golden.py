@@ -111,9 +111,18 @@ def main():
                 json.dump({k: v for k, v in r.items() if not k.endswith("_paf")}, open(cache, "w"))
         mlines = [ln for ln in r["mapping_paf"].split(b"\n") if ln]
         alines = [ln for ln in r["alignment_paf"].split(b"\n") if ln]
-        aligned_bp = sum(int(f[3]) - int(f[2]) for f in (ln.split(b"\t") for ln in mlines))
+        mapped_bp = sum(int(f[3]) - int(f[2]) for f in (ln.split(b"\t") for ln in mlines))
+        # the reference's own "total aligned bp" counter (computeAlignments.hpp:481,528) adds qEndPos - qStartPos of the PARSED row, i.e.
+        # after parseMashmapRow's query padding; the library's row parser equals the unmodified parseMashmapRow field by field
+        # (tests/test_filter_cpu.py::test_mapping_paf_parse_matches_compiled_reference_live)
+        import wfmash_b200 as wb
+        w = cfg["params"].get("window_length", 1000)
+        aligned_bp = 0
+        for ln in mlines:
+            row, _, _ = wb.mapping_paf_parse(ln, min(w, 5000), min(w, 5000), w * 128)
+            aligned_bp += row.q_end - row.q_start
         entry = dict(identity=r["identity"], percentage_identity=r["percentage_identity"], mapping_rows=len(mlines), alignment_lines=len(alines),
-                     mapped_query_bp=aligned_bp, mapping_sha_t1=hashlib.sha256(r["mapping_paf"]).hexdigest(),
+                     mapped_query_bp=mapped_bp, aligned_bp=aligned_bp, mapping_sha_t1=hashlib.sha256(r["mapping_paf"]).hexdigest(),
                      mapping_sha_sorted=hashlib.sha256(b"\n".join(sorted(mlines))).hexdigest(),
                      mapping_sha_cols14=hashlib.sha256(b"\n".join(sorted(b"\t".join(ln.split(b"\t")[:14]) for ln in mlines))).hexdigest(),
                      alignment_sha_sorted=hashlib.sha256(b"\n".join(sorted(alines))).hexdigest(), reference_seconds=r["seconds"])

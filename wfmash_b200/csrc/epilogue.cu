@@ -476,7 +476,15 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
   }
   std::vector<char> ops((size_t)cap);
   std::vector<wfb_aln_result_t> res((size_t)n);
-  int rc = wfb_align_batch(a, pairs.data(), n, ops.data(), cap, res.data(), stats);
+  /* scheduling hint: expected edits from the mapping's identity estimate (the same quantity the reference's own progress / cost
+   * heuristics use); it only orders the work, the alignments do not depend on it */
+  std::vector<float> hint((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const float id = recs[i].mashmap_estimated_identity;
+    const float d = (id > 0.f && id <= 1.f) ? std::max(1.f - id, 0.002f) : 0.05f;
+    hint[(size_t)i] = d * (float)std::max(recs[i].query_length, recs[i].target_length);
+  }
+  int rc = wfb_align_batch_hinted(a, pairs.data(), n, hint.data(), ops.data(), cap, res.data(), stats);
   if (rc != WFB_OK) return rc;
   std::vector<Cigar> cig((size_t)n);
   std::vector<int32_t> status((size_t)n, WFB_REC_WRITTEN);

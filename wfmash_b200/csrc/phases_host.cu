@@ -393,10 +393,26 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     worker();
     for (auto& t : th) t.join();
   }
-  std::string text;
   int64_t written = 0;
   double kernel_ms = 0;
-  const int32_t batch = params->batch_records > 0 ? params->batch_records : 4096;
+  const int32_t batch = params->batch_records > 0 ? params->batch_records : 8192;
+  /* The records are independent (computeAlignments.hpp:398-435) and their cost is wildly uneven (~ score^2: a 50 kb record at 20 %
+   * divergence costs a thousand times one at 1 %). Batches are formed in order of decreasing expected cost — expected edits from the
+   * mapping's identity estimate — so that records of similar cost share a launch: the heavy ones keep all CTAs busy together
+   * instead of each batch ending with its one heavy record. The text is re-assembled in row order below. */
+  std::vector<uint32_t> order(recs.size());
+  for (size_t i = 0; i < recs.size(); ++i) order[i] = (uint32_t)i;
+  {
+    std::vector<float> key(recs.size());
+    for (size_t i = 0; i < recs.size(); ++i) {
+      const float id = recs[i].row.mashmap_estimated_identity;
+      const float d = (id > 0.f && id <= 1.f) ? std::max(1.f - id, 0.002f) : 0.05f;
+      key[i] = d * (float)std::max(recs[i].query.size(), recs[i].target.size());
+    }
+    if (!(getenv("WFB_COST_SORT") && atoi(getenv("WFB_COST_SORT")) == 0))
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key[x] > key[y]; });
+  }
+  std::vector<std::string> line(recs.size());
   std::vector<wfb_record_t> arr;
   std::vector<char> buf;
   for (size_t b0 = 0; b0 < recs.size(); b0 += (size_t)batch) {
@@ -404,7 +420,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     arr.assign(b1 - b0, wfb_record_t());
     size_t bytes = 4096;
     for (size_t i = b0; i < b1; ++i) {
-      const Rec& r = recs[i];
+      const Rec& r = recs[order[i]];
       wfb_record_t& w = arr[i - b0];
       memset(&w, 0, sizeof w);
       w.query_name = r.qname.c_str(); w.query = r.query.data(); w.query_total_length = (uint64_t)r.qs->len; w.query_offset = (uint64_t)r.row.q_start;
@@ -412,7 +428,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
       w.target_name = r.tname.c_str(); w.target = r.target.data(); w.target_total_length = (uint64_t)r.ts->len; w.target_offset = (uint64_t)r.row.r_start;
       w.target_length = (uint64_t)r.target.size(); w.chain_length = (int32_t)r.row.chain_length; w.chain_pos = (int32_t)r.row.chain_pos;
       w.mashmap_estimated_identity = r.row.mashmap_estimated_identity;
-      bytes += (r.query.size() + r.target.size()) * (params->output.sam_format ? 2 : 1) + 1024;
+      bytes += (r.query.size() + r.target.size()) * (params->output.sam_format ? 2 : 1) / (params->output.sam_format ? 1 : 4) + 1024;
     }
     std::vector<int64_t> off(b1 - b0 + 1); std::vector<int32_t> st(b1 - b0);
     int64_t len = 0;
@@ -427,35 +443,45 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     /* Aligner::processMappingRecord re-emits every line that carries a cg:Z: field as its whitespace-separated fields joined by
      * single tabs (computeAlignments.hpp:486-516): the trailing tab do_biwfa_alignment writes before the newline disappears.
      * Lines without a CIGAR field (SAM records) pass through unchanged. */
-    for (int64_t a = 0; a < len;) {
-      const char* nl = (const char*)memchr(buf.data() + a, '\n', (size_t)(len - a));
-      const int64_t b = nl ? (int64_t)(nl - buf.data()) : len;
-      if (b > a) {
-        std::vector<std::pair<int64_t, int64_t>> fields;
-        bool has_cigar = false;
-        for (int64_t p = a; p < b;) {
-          while (p < b && isspace((unsigned char)buf[(size_t)p])) ++p;
-          if (p >= b) break;
-          const int64_t f0 = p;
-          while (p < b && !isspace((unsigned char)buf[(size_t)p])) ++p;
-          fields.emplace_back(f0, p);
-          if (p - f0 >= 5 && memcmp(buf.data() + f0, "cg:Z:", 5) == 0) has_cigar = true;
-        }
-        if (has_cigar) {
-          for (size_t i = 0; i < fields.size(); ++i) {
-            if (i) text.push_back('\t');
-            text.append(buf.data() + fields[i].first, (size_t)(fields[i].second - fields[i].first));
+    for (size_t i = b0; i < b1; ++i) {
+      std::string& text = line[order[i]];
+      for (int64_t a = off[i - b0]; a < off[i - b0 + 1];) {
+        const char* nl = (const char*)memchr(buf.data() + a, '\n', (size_t)(off[i - b0 + 1] - a));
+        const int64_t b = nl ? (int64_t)(nl - buf.data()) : off[i - b0 + 1];
+        if (b > a) {
+          std::vector<std::pair<int64_t, int64_t>> fields;
+          bool has_cigar = false;
+          for (int64_t p = a; p < b;) {
+            while (p < b && isspace((unsigned char)buf[(size_t)p])) ++p;
+            if (p >= b) break;
+            const int64_t f0 = p;
+            while (p < b && !isspace((unsigned char)buf[(size_t)p])) ++p;
+            fields.emplace_back(f0, p);
+            if (p - f0 >= 5 && memcmp(buf.data() + f0, "cg:Z:", 5) == 0) has_cigar = true;
           }
-          text.push_back('\n');
-        } else {
-          text.append(buf.data() + a, (size_t)(b - a));
-          text.push_back('\n');
+          if (has_cigar) {
+            for (size_t f = 0; f < fields.size(); ++f) {
+              if (f) text.push_back('\t');
+              text.append(buf.data() + fields[f].first, (size_t)(fields[f].second - fields[f].first));
+            }
+            text.push_back('\n');
+          } else {
+            text.append(buf.data() + a, (size_t)(b - a));
+            text.push_back('\n');
+          }
         }
+        a = b + 1;
       }
-      a = b + 1;
     }
     for (size_t i = 0; i < st.size(); ++i) written += st[i] == WFB_REC_WRITTEN;
     kernel_ms += as.kernel_ms;
+  }
+  std::string text;
+  {
+    size_t total = 0;
+    for (const std::string& l : line) total += l.size();
+    text.reserve(total);
+    for (const std::string& l : line) text += l;
   }
   *out = to_c_text(text);
   if (!*out) { wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }

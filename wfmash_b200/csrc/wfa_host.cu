@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <atomic>
 #include <string>
@@ -248,7 +249,7 @@ static int gap_affine2p_score(const char* ops, int n, const WfbPen& p) {
 /* Core: sequences are described by (host pointers) or (device buffer + offsets). */
 static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const char* d_src, const int64_t* src_p_off,
                       const int32_t* src_p_len, const int64_t* src_t_off, const int32_t* src_t_len, char* ops,
-                      int64_t ops_cap, wfb_aln_result_t* results, wfb_align_stats_t* stats) {
+                      int64_t ops_cap, wfb_aln_result_t* results, wfb_align_stats_t* stats, const float* cost_hint = nullptr) {
   if (!a || n < 0 || (n > 0 && (!results || !ops))) { g_last_error = "bad argument"; return WFB_EINVAL; }
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n == 0) return WFB_OK;
@@ -271,11 +272,14 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     pd[i].plen = plen; pd[i].tlen = tlen;
     pd[i].p_off = seq_bytes;    seq_bytes = align_up(seq_bytes + plen + 16, 16);
     pd[i].t_off = seq_bytes;    seq_bytes = align_up(seq_bytes + tlen + 16, 16);
-    pd[i].prev_off = seq_bytes; seq_bytes = align_up(seq_bytes + plen + 16, 16);
-    pd[i].trev_off = seq_bytes; seq_bytes = align_up(seq_bytes + tlen + 16, 16);
     pd[i].ops_off = slot_bytes; slot_bytes = align_up(slot_bytes + plen + tlen + 8, 8);
     maxP = std::max(maxP, plen); maxT = std::max(maxT, tlen);
   }
+  /* all forward copies first (the only part that crosses PCIe), then the reversed copies at the same offsets one region further:
+   * the device fills those (wfb_reverse_kernel) */
+  const long long fwd_bytes = seq_bytes;
+  for (int i = 0; i < n; ++i) { pd[i].prev_off = fwd_bytes + pd[i].p_off; pd[i].trev_off = fwd_bytes + pd[i].t_off; }
+  seq_bytes = 2 * fwd_bytes;
   {
     /* worst case a pair needs plen+tlen ops; demand that much so no result can be truncated */
     long long need = 0;
@@ -304,7 +308,7 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
   WFB_H2D(d_pairs, pd.data(), sizeof(WfbPairDesc) * (size_t)n, s);
   if (hpairs) {
     /* pack the forward copies in pinned memory, one H2D */
-    if (a->h_seq.ensure((size_t)seq_bytes)) { g_last_error = "pinned allocation failed"; return WFB_ENOMEM; }
+    if (a->h_seq.ensure((size_t)fwd_bytes)) { g_last_error = "pinned allocation failed"; return WFB_ENOMEM; }
     uint8_t* hs = (uint8_t*)a->h_seq.p;
     /* only the forward regions are written; the device-side reversed regions are filled by a kernel.
      * Copy the span [first p_off, last t_off+tlen) in one go. */
@@ -314,7 +318,8 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
       memcpy(hs + pd[i].t_off, hpairs[i].text, (size_t)pd[i].tlen);
       memset(hs + pd[i].t_off + pd[i].tlen, 0, 16);
     }
-    WFB_H2D(d_seq, hs, (size_t)seq_bytes, s);
+    WFB_H2D(d_seq, hs, (size_t)fwd_bytes, s);
+    WFB_MEMSET(d_seq + fwd_bytes, 0, (size_t)fwd_bytes, s);
   } else {
     if (a->d_srcoff.ensure(sizeof(long long) * 2 * (size_t)n)) { g_last_error = "device allocation failed"; return WFB_ENOMEM; }
     long long* d_off = (long long*)a->d_srcoff.p;
@@ -340,10 +345,14 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     if (pd[i].plen == 0 || pd[i].tlen == 0 || !min_length) t_break.push_back(t);
     else t_base.push_back(t);
   }
-  /* longest first: the level's makespan is bounded by its slowest CTA */
-  std::stable_sort(t_break.begin(), t_break.end(), [](const WfbTask& x, const WfbTask& y) {
-    return (long long)(x.pe + x.te) > (long long)(y.pe + y.te);
-  });
+  /* most expensive first (LPT): the makespan is bounded by the last heavy root a CTA picks up. Cost ~ score^2; the caller's hint
+   * (expected edits, e.g. (1 - mapping identity) * length) orders roots of similar length, the length alone otherwise. */
+  if (cost_hint && !(getenv("WFB_COST_SORT") && atoi(getenv("WFB_COST_SORT")) == 0))
+    std::stable_sort(t_break.begin(), t_break.end(), [&](const WfbTask& x, const WfbTask& y) { return cost_hint[x.pair] > cost_hint[y.pair]; });
+  else
+    std::stable_sort(t_break.begin(), t_break.end(), [](const WfbTask& x, const WfbTask& y) {
+      return (long long)(x.pe + x.te) > (long long)(y.pe + y.te);
+    });
   /* ---- workspaces ---- */
   const int W = (int)align_up(maxP + maxT + 8, 8);
   const long long ws_stride = 2LL * pen.R * 5 * W;
@@ -573,6 +582,16 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
       out_off += len;
     }
   }
+  if (getenv("WFB_TRACE")) {
+    float ms = 0.f;
+#ifndef WFB_EMU
+    cudaEventElapsedTime(&ms, a->ev[0], a->ev[1]);
+#endif
+    fprintf(stderr, "[wfb] main n=%d W=%d persist_ms=%.1f total_ms=%.1f levels=%llu cells=%.3g steps=%.3g ext=%.3g ovl=%.3g break_tasks=%llu base_tasks=%llu base_cells=%.3g base_steps=%.3g\n",
+            n, W, persist_ms, ms, (unsigned long long)levels, (double)h_cnt->cells, (double)h_cnt->score_steps, (double)h_cnt->extend_matches,
+            (double)h_cnt->overlap_tests, (unsigned long long)h_cnt->break_tasks, (unsigned long long)h_cnt->base_tasks, (double)h_cnt->base_cells,
+            (double)h_cnt->base_score_steps);
+  }
   if (stats) {
     stats->cells = h_cnt->cells;
     stats->extend_matches = h_cnt->extend_matches;
@@ -679,6 +698,9 @@ extern "C" int wfb_align_endsfree_batch(wfb_aligner_t* a, const wfb_endsfree_pai
     for (size_t j = 0; j < todo.size(); ++j) h_status[todo[j]] = 0;
     WFB_H2D(d_status, h_status.data(), sizeof(int) * (size_t)n, s);
     WFB_STREAM_SYNC(s);
+    const double tr_t0 = getenv("WFB_TRACE") ? (double)clock() / CLOCKS_PER_SEC : 0;
+    struct timespec tr_ts0; clock_gettime(CLOCK_MONOTONIC, &tr_ts0);
+    (void)tr_t0;
     WFB_LAUNCH(wfb_endsfree_kernel, ctas, kBaseThreads, s, (const WfbTask*)a->d_q[0].p, (const WfbEndsFree*)a->d_srcoff.p, (int)todo.size(),
                d_ctrl + 0, (const WfbPairDesc*)a->d_pairs.p, (const uint8_t*)a->d_seq.p, (int32_t*)a->d_arena.p, arena_stride,
                (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, (unsigned char*)a->d_ws.p, runflag_stride, (int)term_group,
@@ -688,6 +710,11 @@ extern "C" int wfb_align_endsfree_batch(wfb_aligner_t* a, const wfb_endsfree_pai
 #ifndef WFB_EMU
     { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { g_last_error = std::string("kernel: ") + cudaGetErrorString(e); return WFB_ECUDA; } }
 #endif
+    if (getenv("WFB_TRACE")) {
+      struct timespec tr_ts1; clock_gettime(CLOCK_MONOTONIC, &tr_ts1);
+      fprintf(stderr, "[wfb] endsfree n=%d pass=%d todo=%zu ctas=%d kernel+sync_ms=%.1f\n", n, pass, todo.size(), ctas,
+              (tr_ts1.tv_sec - tr_ts0.tv_sec) * 1e3 + (tr_ts1.tv_nsec - tr_ts0.tv_nsec) * 1e-6);
+    }
     std::vector<int> again;
     for (int i : todo) if (h_status[i] == WFB_PAIR_BASE_SCORE_CAP) again.push_back(i);
     todo.swap(again);
@@ -718,6 +745,12 @@ extern "C" int wfb_align_batch(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_
                                wfb_aln_result_t* results, wfb_align_stats_t* stats) {
   if (n > 0 && !pairs) { g_last_error = "pairs == NULL"; return WFB_EINVAL; }
   return align_impl(a, n, pairs, nullptr, nullptr, nullptr, nullptr, nullptr, ops, ops_cap, results, stats);
+}
+
+extern "C" int wfb_align_batch_hinted(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_t n, const float* cost_hint, char* ops, int64_t ops_cap,
+                                      wfb_aln_result_t* results, wfb_align_stats_t* stats) {
+  if (n > 0 && !pairs) { g_last_error = "pairs == NULL"; return WFB_EINVAL; }
+  return align_impl(a, n, pairs, nullptr, nullptr, nullptr, nullptr, nullptr, ops, ops_cap, results, stats, cost_hint);
 }
 
 extern "C" int wfb_align_batch_device(wfb_aligner_t* a, const char* d_seq, const int64_t* pattern_off, const int32_t* pattern_len,

@@ -86,6 +86,8 @@ typedef struct {
   uint64_t levels;
   double kernel_ms;      /* CUDA-event time of all kernels of the call (on the call's stream)   */
   double break_kernel_ms; /* ... of the breakpoint (bidirectional wavefront) kernel launches only */
+  double patch_kernel_ms; /* wfb_biwfa_paf_batch only: CUDA-event time of the head / tail patch kernel rounds */
+  uint64_t h2d_bytes, d2h_bytes; /* bytes the call copied to / from the device                   */
 } wfb_align_stats_t;
 
 typedef struct wfb_aligner wfb_aligner_t;
@@ -620,6 +622,7 @@ typedef struct {
                                                windowed minmers are provably those of the reference's addMinmers */
   double index_seconds, map_kernel_ms, filter_seconds, total_seconds;
   double ani_seconds;                       /* ANI auto-identity (0 when -p was given)                        */
+  double index_kernel_ms, ani_kernel_ms;    /* CUDA-event time of the index-build kernels / the ANI kernels   */
 } wfb_map_phase_stats_t;
 
 /* Mapping phase: ids + PanSN groups (SequenceIdManager, sequenceIds.hpp:284-441; targets first), optional ANI estimate,
@@ -628,6 +631,12 @@ typedef struct {
  * query in input order. The one-to-one mode runs its final reference-axis pass over all queries (wfb_one_to_one_filter). */
 int wfb_map_phase(int device, const wfb_map_phase_params_t* params, const wfb_seq_t* targets, int32_t n_targets, const wfb_seq_t* queries,
                   int32_t n_queries, char** paf, int64_t* paf_len, wfb_map_phase_stats_t* stats);
+/* The same for a SHARE of the queries (one process per GPU: queries are independent, computeMap.hpp:565-599): query_select[q] != 0
+ * marks the queries this call maps; sequence ids, PanSN groups, the ANI estimate and the fragment order (hence the ch:Z: tags) still
+ * come from ALL queries, so the concatenation of the shares' texts equals the text of one call over everything. NULL = all.
+ * Not available with the one-to-one filter (its final pass needs every query's mappings). */
+int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* params, const wfb_seq_t* targets, int32_t n_targets, const wfb_seq_t* queries,
+                         int32_t n_queries, const uint8_t* query_select, char** paf, int64_t* paf_len, wfb_map_phase_stats_t* stats);
 
 typedef struct { /* the align::Parameters fields of the alignment phase */
   uint64_t target_padding;       /* -E [min(window_length, 5000)]                                   */
@@ -641,7 +650,11 @@ typedef struct { /* the align::Parameters fields of the alignment phase */
 typedef struct {
   int64_t records, written, skipped_lines; /* parsable mapping rows, output records, rows skipped like computeAlignments.hpp:368-372 */
   uint64_t aligned_bp;                     /* the reference's processed_alignment_length (computeAlignments.hpp:480,528)  */
-  double kernel_ms, total_seconds;
+  double kernel_ms, total_seconds;         /* kernel_ms: CUDA-event time of the main biWFA rounds                       */
+  double persist_kernel_ms, patch_kernel_ms; /* ... of wfb_persist_kernel alone / of the head + tail patch rounds        */
+  int64_t batches;                         /* GPU batches (= launches of wfb_persist_kernel)                             */
+  uint64_t cells, base_cells, extend_matches, base_extend_matches, overlap_tests, score_steps, base_score_steps; /* wfb_align_stats_t, summed */
+  uint64_t h2d_bytes, d2h_bytes;
 } wfb_align_phase_stats_t;
 
 /* Alignment phase over mapping PAF text: parseMashmapRow + padding, slices fetched with faidx's clamping, upper-casing /

@@ -64,7 +64,8 @@ class AlignStats(ctypes.Structure):
     _fields_ = [("cells", ctypes.c_uint64), ("extend_matches", ctypes.c_uint64), ("overlap_tests", ctypes.c_uint64),
                 ("score_steps", ctypes.c_uint64), ("break_tasks", ctypes.c_uint64), ("base_tasks", ctypes.c_uint64),
                 ("base_cells", ctypes.c_uint64), ("base_extend_matches", ctypes.c_uint64), ("base_score_steps", ctypes.c_uint64),
-                ("levels", ctypes.c_uint64), ("kernel_ms", ctypes.c_double), ("break_kernel_ms", ctypes.c_double)]
+                ("levels", ctypes.c_uint64), ("kernel_ms", ctypes.c_double), ("break_kernel_ms", ctypes.c_double), ("patch_kernel_ms", ctypes.c_double),
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -769,7 +770,8 @@ class MapPhaseParams(ctypes.Structure):
 class MapPhaseStats(ctypes.Structure):
     _fields_ = [("fragments", ctypes.c_int64), ("l2_mappings", ctypes.c_int64), ("mappings", ctypes.c_int64), ("sketch_size", ctypes.c_int32),
                 ("minimum_hits", ctypes.c_int32), ("percentage_identity", ctypes.c_float), ("stale_absorbed", ctypes.c_int32), ("index_seconds", ctypes.c_double),
-                ("map_kernel_ms", ctypes.c_double), ("filter_seconds", ctypes.c_double), ("total_seconds", ctypes.c_double), ("ani_seconds", ctypes.c_double)]
+                ("map_kernel_ms", ctypes.c_double), ("filter_seconds", ctypes.c_double), ("total_seconds", ctypes.c_double), ("ani_seconds", ctypes.c_double),
+                ("index_kernel_ms", ctypes.c_double), ("ani_kernel_ms", ctypes.c_double)]
 
 
 class AlignPhaseParams(ctypes.Structure):
@@ -779,7 +781,9 @@ class AlignPhaseParams(ctypes.Structure):
 
 class AlignPhaseStats(ctypes.Structure):
     _fields_ = [("records", ctypes.c_int64), ("written", ctypes.c_int64), ("skipped_lines", ctypes.c_int64), ("aligned_bp", ctypes.c_uint64),
-                ("kernel_ms", ctypes.c_double), ("total_seconds", ctypes.c_double)]
+                ("kernel_ms", ctypes.c_double), ("total_seconds", ctypes.c_double), ("persist_kernel_ms", ctypes.c_double), ("patch_kernel_ms", ctypes.c_double),
+                ("batches", ctypes.c_int64)] + [(n, ctypes.c_uint64) for n in ("cells", "base_cells", "extend_matches", "base_extend_matches", "overlap_tests",
+                                                                                "score_steps", "base_score_steps", "h2d_bytes", "d2h_bytes")]
 
 
 def _seq_array(seqs):
@@ -792,14 +796,22 @@ def _seq_array(seqs):
     return arr, keep
 
 
-def map_phase(targets, queries, params: MapPhaseParams = None, device: int = 0):
-    """wfb_map_phase: the whole `wfmash -m` phase over in-memory sequences -> (mapping PAF bytes, MapPhaseStats)."""
+def map_phase(targets, queries, params: MapPhaseParams = None, device: int = 0, all_queries=None):
+    """wfb_map_phase: the whole `wfmash -m` phase over in-memory sequences -> (mapping PAF bytes, MapPhaseStats).
+    all_queries: every query of the run when `queries` is only this process's share (wfb_map_phase_subset: ids, groups, ANI estimate and
+    fragment order come from all of them, so the shares' texts concatenate to the text of one call)."""
     P = params or MapPhaseParams()
     ta, tk = _seq_array(targets)
-    qa, qk = _seq_array(queries)
     txt, n, st = ctypes.c_void_p(), ctypes.c_int64(0), MapPhaseStats()
     L = lib()
-    rc = L.wfb_map_phase(device, ctypes.byref(P), ta, len(targets), qa, len(queries), ctypes.byref(txt), ctypes.byref(n), ctypes.byref(st))
+    if all_queries is not None:
+        mine = {name for name, _ in queries}
+        qa, qk = _seq_array(all_queries)
+        sel = (ctypes.c_uint8 * max(1, len(all_queries)))(*[1 if name in mine else 0 for name, _ in all_queries])
+        rc = L.wfb_map_phase_subset(device, ctypes.byref(P), ta, len(targets), qa, len(all_queries), sel, ctypes.byref(txt), ctypes.byref(n), ctypes.byref(st))
+    else:
+        qa, qk = _seq_array(queries)
+        rc = L.wfb_map_phase(device, ctypes.byref(P), ta, len(targets), qa, len(queries), ctypes.byref(txt), ctypes.byref(n), ctypes.byref(st))
     if rc != 0:
         raise _err(rc)
     out = ctypes.string_at(txt, n.value)

@@ -24,6 +24,8 @@
 void wfb_set_last_error_(const std::string& s); /* wfa_host.cu */
 static inline void wfb_set_last_error(const char* msg) { wfb_set_last_error_(msg); }
 
+void wfb_take_endsfree_counters_(wfb_aligner_t* a, double* kernel_ms, uint64_t* h2d, uint64_t* d2h); /* wfa_host.cu */
+
 namespace {
 
 struct Run {
@@ -494,10 +496,14 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
   });
   std::vector<char>().swap(ops);
   if (!params->disable_chain_patching) {
+    double ms = 0; uint64_t h2d = 0, d2h = 0;
+    wfb_take_endsfree_counters_(a, &ms, &h2d, &d2h);
     rc = patch_round(a, recs, cig, status, true, term_group);
     if (rc != WFB_OK) return rc;
     rc = patch_round(a, recs, cig, status, false, term_group);
     if (rc != WFB_OK) return rc;
+    wfb_take_endsfree_counters_(a, &ms, &h2d, &d2h);
+    if (stats) { stats->patch_kernel_ms = ms; stats->h2d_bytes += h2d; stats->d2h_bytes += d2h; }
   }
   std::vector<std::string> line((size_t)n);
   for_each_record(n, cap, [&](int64_t i) {

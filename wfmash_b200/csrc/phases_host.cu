@@ -114,6 +114,15 @@ extern "C" void wfb_emu_inject_l2(const wfb_l2_mapping_t* mappings, const int64_
 
 extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, const wfb_seq_t* targets, int32_t n_targets, const wfb_seq_t* queries,
                              int32_t n_queries, char** paf, int64_t* paf_len, wfb_map_phase_stats_t* stats) {
+  return wfb_map_phase_subset(device, params, targets, n_targets, queries, n_queries, nullptr, paf, paf_len, stats);
+}
+
+extern "C" int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* params, const wfb_seq_t* targets, int32_t n_targets, const wfb_seq_t* queries,
+                                    int32_t n_queries, const uint8_t* query_select, char** paf, int64_t* paf_len, wfb_map_phase_stats_t* stats) {
+  if (params && query_select && params->filter.filter_mode == WFB_FILTER_ONETOONE) {
+    wfb_set_last_error_("the one-to-one filter needs every query in one call");
+    return WFB_EINVAL;
+  }
   if (!params || !paf || !paf_len || n_targets <= 0 || n_queries < 0 || !targets || (n_queries > 0 && !queries) || params->kmer_size < 1 ||
       params->window_length <= 0) {
     wfb_set_last_error_("bad argument");
@@ -130,7 +139,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
   ids.build_groups(P.skip_prefix ? P.prefix_delim : 0);
   int rc = WFB_OK;
   int32_t stale_absorbed = 0;
-  double ani_seconds = 0;
+  double ani_seconds = 0, ani_kernel_ms = 0, index_kernel_ms = 0;
 
   if (!(P.percentage_identity > 0)) {
     const double t_ani = now_s(); /* main.cpp:75-134: ANI auto-identity, then the sketch size follows the estimate */
@@ -145,8 +154,10 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
       std::vector<char> has((size_t)ng, 0);
       for (int32_t i = 0; i < n; ++i) { ptr[(size_t)i] = s[i].seq; len[(size_t)i] = s[i].len; g[(size_t)i] = dense[ids.group[(size_t)ids.id_of[s[i].name]]]; has[(size_t)g[(size_t)i]] = 1; }
       std::vector<uint64_t> all((size_t)ng * 4096); std::vector<int32_t> c((size_t)ng);
-      const int r = wfb_ani_group_sketches(device, ptr.data(), len.data(), g.data(), n, ng, 21, 4096, all.data(), c.data(), nullptr);
+      wfb_ani_stats_t as; memset(&as, 0, sizeof as);
+      const int r = wfb_ani_group_sketches(device, ptr.data(), len.data(), g.data(), n, ng, 21, 4096, all.data(), c.data(), &as);
       if (r != WFB_OK) return r;
+      ani_kernel_ms += as.hash_kernel_ms + as.sort_kernel_ms;
       for (int32_t j = 0; j < ng; ++j)
         if (has[(size_t)j]) { sk.insert(sk.end(), all.begin() + (size_t)j * 4096, all.begin() + (size_t)(j + 1) * 4096); cnt.push_back(c[(size_t)j]); present_gid.push_back(gid[(size_t)j]); }
       return WFB_OK;
@@ -173,6 +184,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
   wfb_index_stats_t ixs; memset(&ixs, 0, sizeof ixs);
   wfb_index_t* ix = wfb_index_build(device, &ip, tptr.data(), tlen.data(), tid.data(), n_targets, &ixs);
   stale_absorbed = (int32_t)std::min<uint64_t>(ixs.minmer.stale_absorbed, 0x7fffffffu);
+  index_kernel_ms = ixs.minmer.total_kernel_ms + ixs.index_kernel_ms;
   if (!ix) return WFB_ECUDA; /* message already set */
 #else
   wfb_index_t* ix = nullptr;
@@ -193,7 +205,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
   std::vector<int64_t> base;
   int64_t blob_bytes = 0;
   for (int32_t q = 0; q < n_queries; ++q)
-    if (queries[q].len >= w) { mapped.push_back(q); base.push_back(blob_bytes); blob_bytes += queries[q].len; }
+    if (queries[q].len >= w && (!query_select || query_select[q])) { mapped.push_back(q); base.push_back(blob_bytes); blob_bytes += queries[q].len; }
   std::string blob;
   blob.reserve((size_t)blob_bytes);
   for (int32_t q : mapped) blob.append(queries[q].seq, (size_t)queries[q].len);
@@ -251,8 +263,8 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
      * index of each chain, mappingFilter.hpp:401-404,498-520). The reference appends them as its fragment tasks finish
      * (computeMap.hpp:590-597), i.e. in a schedule-dependent order; its only reproducible schedule is the one-thread run
      * (one_thread_fragment_order above). That order is used here, so the text equals `wfmash -m -t 1`. */
-    std::vector<int64_t> tasks((size_t)n_queries, 0);
-    for (size_t m = 0; m < mapped.size(); ++m) tasks[(size_t)mapped[m]] = q_frag[m + 1] - q_frag[m];
+    std::vector<int64_t> tasks((size_t)n_queries, 0); /* every query of the RUN has a task in the reference's executor, also the ones another rank maps */
+    for (int32_t q = 0; q < n_queries; ++q) tasks[(size_t)q] = queries[q].len >= w ? queries[q].len / w + (queries[q].len % w != 0 ? 1 : 0) : 0;
     std::vector<std::vector<int32_t>> frag_order;
     one_thread_fragment_order(tasks, frag_order);
     std::vector<wfb_l2_mapping_t> ordered;
@@ -314,6 +326,7 @@ extern "C" int wfb_map_phase(int device, const wfb_map_phase_params_t* params, c
     stats->fragments = (int64_t)frags.size(); stats->l2_mappings = n_l2; stats->mappings = n_out; stats->sketch_size = s; stats->minimum_hits = min_hits;
     stats->percentage_identity = P.percentage_identity; stats->index_seconds = index_seconds; stats->map_kernel_ms = map_ms; stats->filter_seconds = filter_seconds;
     stats->total_seconds = now_s() - t_begin; stats->stale_absorbed = stale_absorbed; stats->ani_seconds = ani_seconds;
+    stats->index_kernel_ms = index_kernel_ms; stats->ani_kernel_ms = ani_kernel_ms;
   }
   return WFB_OK;
 }
@@ -413,6 +426,8 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
       std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key[x] > key[y]; });
   }
   std::vector<std::string> line(recs.size());
+  wfb_align_stats_t sum; memset(&sum, 0, sizeof sum);
+  int64_t n_batches = 0;
   std::vector<wfb_record_t> arr;
   std::vector<char> buf;
   for (size_t b0 = 0; b0 < recs.size(); b0 += (size_t)batch) {
@@ -475,6 +490,10 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     }
     for (size_t i = 0; i < st.size(); ++i) written += st[i] == WFB_REC_WRITTEN;
     kernel_ms += as.kernel_ms;
+    sum.break_kernel_ms += as.break_kernel_ms; sum.patch_kernel_ms += as.patch_kernel_ms; sum.cells += as.cells; sum.base_cells += as.base_cells;
+    sum.extend_matches += as.extend_matches; sum.base_extend_matches += as.base_extend_matches; sum.overlap_tests += as.overlap_tests;
+    sum.score_steps += as.score_steps; sum.base_score_steps += as.base_score_steps; sum.h2d_bytes += as.h2d_bytes; sum.d2h_bytes += as.d2h_bytes;
+    ++n_batches;
   }
   std::string text;
   {
@@ -489,6 +508,10 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
   if (stats) {
     memset(stats, 0, sizeof *stats);
     stats->records = (int64_t)recs.size(); stats->written = written; stats->skipped_lines = skipped; stats->aligned_bp = aligned_bp; stats->kernel_ms = kernel_ms;
+    stats->persist_kernel_ms = sum.break_kernel_ms; stats->patch_kernel_ms = sum.patch_kernel_ms; stats->batches = n_batches; stats->cells = sum.cells;
+    stats->base_cells = sum.base_cells; stats->extend_matches = sum.extend_matches; stats->base_extend_matches = sum.base_extend_matches;
+    stats->overlap_tests = sum.overlap_tests; stats->score_steps = sum.score_steps; stats->base_score_steps = sum.base_score_steps;
+    stats->h2d_bytes = sum.h2d_bytes; stats->d2h_bytes = sum.d2h_bytes;
     stats->total_seconds = now_s() - t_begin;
   }
   return WFB_OK;

@@ -10,6 +10,7 @@
 #include "wfa_kernels.h"
 #include "../../include/wfmash_b200.h"
 
+#include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -106,6 +107,8 @@ inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a
 }  // namespace
 
 struct wfb_aligner {
+  double endsfree_kernel_ms = 0; /* CUDA-event time of the ends-free kernel launches since the last reset (wfb_biwfa_paf_batch reads it) */
+  uint64_t endsfree_h2d = 0, endsfree_d2h = 0;
   int device = 0;
   WfbPen pen{};
   uint64_t workspace_bytes = 0;
@@ -431,12 +434,18 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
       WfbPQueue pq;
       pq.tasks = (WfbTask*)a->d_q[0].p; pq.ready = (int*)a->d_q[1].p; pq.head = d_ctrl + 8; pq.tail = d_ctrl + 9;
       pq.outstanding = d_ctrl + 10; pq.error = d_ctrl + 11; pq.cap = (int)qcap;
+      long long* d_cta_log = nullptr;
+      if (getenv("WFB_TRACE")) {
+        if (a->d_tasklog.ensure(sizeof(long long) * (4 * (size_t)ctas + 2 * (size_t)n))) { g_last_error = "device allocation failed (cta log)"; return WFB_ENOMEM; }
+        d_cta_log = (long long*)a->d_tasklog.p;
+        WFB_MEMSET(d_cta_log, 0, sizeof(long long) * (4 * (size_t)ctas + 2 * (size_t)n), s);
+      }
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[2], s));
 #endif
       WFB_LAUNCH(wfb_persist_kernel, ctas, kBreakThreads, s, pq, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq, (int32_t*)a->d_ws.p, ws_stride,
                  W, (int32_t*)a->d_arena.p, arena_stride, (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, pen, d_slots,
-                 d_status, d_counters);
+                 d_status, d_counters, d_cta_log);
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[3], s));
 #endif
@@ -452,6 +461,45 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
         persist_ms = ms;
       }
 #endif
+      if (d_cta_log) { /* WFB_TRACE: how busy were the CTAs, and when did they run out of work? */
+        std::vector<long long> cl((size_t)4 * ctas + 2 * (size_t)n);
+        WFB_D2H(cl.data(), d_cta_log, sizeof(long long) * cl.size(), s);
+        WFB_STREAM_SYNC(s);
+        long long t0 = LLONG_MAX, t1 = 0, busy = 0;
+        std::vector<long long> ends;
+        for (int c = 0; c < ctas; ++c) { if (cl[4 * c + 2]) t0 = std::min(t0, cl[4 * c + 2]); t1 = std::max(t1, cl[4 * c + 1]); busy += cl[4 * c]; ends.push_back(cl[4 * c + 1]); }
+        std::sort(ends.begin(), ends.end());
+        const double span = (double)(t1 - t0) * 1e-6;
+        fprintf(stderr, "[wfb] persist ctas=%d span_ms=%.1f busy=%.3f  CTA exit times (ms): p10=%.1f p50=%.1f p90=%.1f p99=%.1f max=%.1f\n", ctas, span,
+                span > 0 ? (double)busy * 1e-6 / (span * ctas) : 0.0, (ends[ends.size() / 10] - t0) * 1e-6, (ends[ends.size() / 2] - t0) * 1e-6,
+                (ends[ends.size() * 9 / 10] - t0) * 1e-6, (ends[ends.size() * 99 / 100] - t0) * 1e-6, span);
+      }
+      if (d_cta_log) {
+        std::vector<long long> cl((size_t)4 * ctas + 2 * (size_t)n);
+        WFB_D2H(cl.data(), d_cta_log, sizeof(long long) * cl.size(), s);
+        WFB_STREAM_SYNC(s);
+        long long t0 = LLONG_MAX;
+        for (int c = 0; c < ctas; ++c) if (cl[4 * c + 2]) t0 = std::min(t0, cl[4 * c + 2]);
+        std::vector<int> idx((size_t)n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        const long long* pl = cl.data() + 4 * ctas;
+        std::sort(idx.begin(), idx.end(), [&](int x, int y) { return pl[2 * x + 1] > pl[2 * y + 1]; });
+        for (int j = 0; j < std::min(n, 12); ++j) {
+          const int i = idx[j];
+          fprintf(stderr, "[wfb]   late pair %d plen=%d tlen=%d done_at_ms=%.1f cta_ms=%.1f hint=%.0f\n", i, pd[i].plen, pd[i].tlen, (pl[2 * i + 1] - t0) * 1e-6,
+                  pl[2 * i] * 1e-6, cost_hint ? cost_hint[i] : -1.f);
+        }
+        std::sort(idx.begin(), idx.end(), [&](int x, int y) { return pl[2 * x] > pl[2 * y]; });
+        double tot = 0, top = 0;
+        for (int i = 0; i < n; ++i) tot += pl[2 * i] * 1e-6;
+        for (int j = 0; j < std::min(n, 100); ++j) top += pl[2 * idx[j]] * 1e-6;
+        fprintf(stderr, "[wfb]   CTA-ms over all pairs %.0f; the 100 costliest pairs hold %.0f\n", tot, top);
+        for (int j = 0; j < std::min(n, 12); ++j) {
+          const int i = idx[j];
+          fprintf(stderr, "[wfb]   heavy pair %d plen=%d tlen=%d done_at_ms=%.1f cta_ms=%.1f hint=%.0f\n", i, pd[i].plen, pd[i].tlen, (pl[2 * i + 1] - t0) * 1e-6,
+                  pl[2 * i] * 1e-6, cost_hint ? cost_hint[i] : -1.f);
+        }
+      }
       if (ctrl1[11] == 0 && ctrl1[10] == 0) {
         persist_done = true;
       } else {
@@ -604,6 +652,8 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     stats->base_score_steps = h_cnt->base_score_steps;
     stats->levels = levels;
     stats->break_kernel_ms = break_ms;
+    stats->h2d_bytes = (uint64_t)(hpairs ? fwd_bytes : 0) + sizeof(WfbPairDesc) * (uint64_t)n;
+    stats->d2h_bytes = (uint64_t)slot_bytes + sizeof(int) * 2 * (uint64_t)n;
 #ifndef WFB_EMU
     float ms = 0.f;
     cudaEventElapsedTime(&ms, a->ev[0], a->ev[1]);
@@ -698,17 +748,22 @@ extern "C" int wfb_align_endsfree_batch(wfb_aligner_t* a, const wfb_endsfree_pai
     for (size_t j = 0; j < todo.size(); ++j) h_status[todo[j]] = 0;
     WFB_H2D(d_status, h_status.data(), sizeof(int) * (size_t)n, s);
     WFB_STREAM_SYNC(s);
-    const double tr_t0 = getenv("WFB_TRACE") ? (double)clock() / CLOCKS_PER_SEC : 0;
     struct timespec tr_ts0; clock_gettime(CLOCK_MONOTONIC, &tr_ts0);
-    (void)tr_t0;
+#ifndef WFB_EMU
+    WFB_CHECK(cudaEventRecord(a->ev[2], s));
+#endif
     WFB_LAUNCH(wfb_endsfree_kernel, ctas, kBaseThreads, s, (const WfbTask*)a->d_q[0].p, (const WfbEndsFree*)a->d_srcoff.p, (int)todo.size(),
                d_ctrl + 0, (const WfbPairDesc*)a->d_pairs.p, (const uint8_t*)a->d_seq.p, (int32_t*)a->d_arena.p, arena_stride,
                (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, (unsigned char*)a->d_ws.p, runflag_stride, (int)term_group,
                pen, (char*)a->d_slots.p, d_status);
+#ifndef WFB_EMU
+    WFB_CHECK(cudaEventRecord(a->ev[3], s));
+#endif
     WFB_D2H(h_status.data(), d_status, sizeof(int) * (size_t)n, s);
     WFB_STREAM_SYNC(s);
 #ifndef WFB_EMU
     { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { g_last_error = std::string("kernel: ") + cudaGetErrorString(e); return WFB_ECUDA; } }
+    { float ms = 0.f; cudaEventElapsedTime(&ms, a->ev[2], a->ev[3]); a->endsfree_kernel_ms += ms; }
 #endif
     if (getenv("WFB_TRACE")) {
       struct timespec tr_ts1; clock_gettime(CLOCK_MONOTONIC, &tr_ts1);
@@ -725,6 +780,7 @@ extern "C" int wfb_align_endsfree_batch(wfb_aligner_t* a, const wfb_endsfree_pai
   WFB_D2H(a->h_misc.p, a->d_len.p, sizeof(int) * (size_t)n, s);
   WFB_D2H(a->h_dense.p, a->d_dense.p, (size_t)slot_bytes, s);
   WFB_STREAM_SYNC(s);
+  a->endsfree_h2d += (uint64_t)seq_bytes; a->endsfree_d2h += (uint64_t)slot_bytes;
   const int* h_len = (const int*)a->h_misc.p;
   const char* h_dense = (const char*)a->h_dense.p;
   int64_t out_off = 0;
@@ -745,6 +801,12 @@ extern "C" int wfb_align_batch(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_
                                wfb_aln_result_t* results, wfb_align_stats_t* stats) {
   if (n > 0 && !pairs) { g_last_error = "pairs == NULL"; return WFB_EINVAL; }
   return align_impl(a, n, pairs, nullptr, nullptr, nullptr, nullptr, nullptr, ops, ops_cap, results, stats);
+}
+
+/* (library-internal) ends-free kernel time / bytes accumulated since the last call; resets them */
+void wfb_take_endsfree_counters_(wfb_aligner_t* a, double* kernel_ms, uint64_t* h2d, uint64_t* d2h) {
+  *kernel_ms = a->endsfree_kernel_ms; *h2d = a->endsfree_h2d; *d2h = a->endsfree_d2h;
+  a->endsfree_kernel_ms = 0; a->endsfree_h2d = 0; a->endsfree_d2h = 0;
 }
 
 extern "C" int wfb_align_batch_hinted(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_t n, const float* cost_hint, char* ops, int64_t ops_cap,

@@ -1409,9 +1409,12 @@ struct WfbPersistShared {
 
 WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, WfbPQueue q, const WfbPairDesc* pairs, const uint8_t* seq,
               int32_t* ws_all, long long ws_stride, int W, int32_t* arena_all, long long arena_stride, WfbBaseMeta* log_all, int score_cap,
-              WfbRun* runs_all, int maxruns, WfbPen pen, char* ops_all, int* pair_status, WfbCounters* counters) {
+              WfbRun* runs_all, int maxruns, WfbPen pen, char* ops_all, int* pair_status, WfbCounters* counters,
+              long long* cta_log /* optional (WFB_TRACE): per CTA {ns busy in tasks, exit time, start time, tasks} */) {
   WFB_KERNEL_PROLOGUE
   WFB_SHARED WfbPersistShared S;
+  const long long log_t0 = cta_log ? wfb_globaltimer() : 0;
+  long long log_busy = 0;
   int32_t* const ws = ws_all + (long long)bid * ws_stride;
   int32_t* const arena = arena_all + (long long)bid * arena_stride;
   WfbBaseMeta* const log = log_all + (long long)bid * (score_cap + 1) * 5;
@@ -1464,6 +1467,7 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
     t = q.tasks[slot];
 #endif
     const long long pt_task0 = WFB_PT_CLOCK();
+    const long long log_task0 = cta_log ? wfb_globaltimer() : 0;
     if (t.score_remaining <= WFB_FALLBACK_MIN_SCORE && t.pe > t.pb && t.te > t.tb) {
       n_base++;
       wfb_base_task(S.base, t, pairs, seq, arena, arena_stride, log, score_cap, runs, maxruns, pen, ops_all, pair_status, acc_base);
@@ -1475,12 +1479,29 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
     }
     (void)pt_task0;
     WFB_SYNC();
+    if (cta_log) {
+      const long long now = wfb_globaltimer();
+      log_busy += now - log_task0;
+      if (WFB_TID == 0) { /* per pair: CTA time spent on its tasks, time its last task ended (after the per-CTA block) */
+        unsigned long long* pl = (unsigned long long*)cta_log + 4 * nblocks + 2 * (long long)t.pair;
+#ifndef WFB_EMU
+        atomicAdd(pl, (unsigned long long)(now - log_task0));
+        atomicMax(pl + 1, (unsigned long long)now);
+#else
+        (void)pl;
+#endif
+      }
+    }
     if (WFB_TID == 0) {
 #ifndef WFB_EMU
       __threadfence();
 #endif
       wfb_atomic_add(q.outstanding, -1);
     }
+  }
+  if (cta_log && WFB_TID == 0) {
+    cta_log[4 * bid + 0] = log_busy; cta_log[4 * bid + 1] = wfb_globaltimer(); cta_log[4 * bid + 2] = log_t0;
+    cta_log[4 * bid + 3] = (long long)(n_break + n_base);
   }
   {
     unsigned long long m = acc.matches, mb = acc_base.matches;

@@ -642,7 +642,7 @@ typedef struct { /* the align::Parameters fields of the alignment phase */
   uint64_t target_padding;       /* -E [min(window_length, 5000)]                                   */
   uint64_t query_padding;        /* -U [min(window_length, 5000)]                                   */
   uint64_t wflign_max_len_minor; /* [window_length * 128]                                           */
-  int32_t batch_records;         /* records per GPU batch; <= 0 = 4096                              */
+  int32_t batch_records;         /* records per GPU batch; <= 0 = 32768                             */
   int32_t reserved_;
   wfb_paf_params_t output;       /* filters, patching, PAF / SAM                                    */
 } wfb_align_phase_params_t;

@@ -408,7 +408,9 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
   }
   int64_t written = 0;
   double kernel_ms = 0;
-  const int32_t batch = params->batch_records > 0 ? params->batch_records : 8192;
+  /* One launch per batch, and every launch ends with a tail (few CTAs finishing the costliest records alone): as few batches as the
+   * memory allows. A 50 kb record needs ~0.45 MB of device memory (4 sequence copies + 2 x (plen + tlen) operation slots). */
+  const int32_t batch = params->batch_records > 0 ? params->batch_records : 32768;
   /* The records are independent (computeAlignments.hpp:398-435) and their cost is wildly uneven (~ score^2: a 50 kb record at 20 %
    * divergence costs a thousand times one at 1 %). Batches are formed in order of decreasing expected cost — expected edits from the
    * mapping's identity estimate — so that records of similar cost share a launch: the heavy ones keep all CTAs busy together

@@ -116,7 +116,7 @@ struct wfb_aligner {
   wfb_stream_t stream{};
   DevBuf d_seq, d_pairs, d_slots, d_dense, d_len, d_status, d_counters, d_ctrl;
   DevBuf d_q[4]; /* break[0], break[1], base[0], base[1] */
-  DevBuf d_ws, d_arena, d_log, d_runs, d_srcoff, d_tasklog;
+  DevBuf d_ws, d_arena, d_log, d_runs, d_srcoff, d_tasklog, d_team;
   HostBuf h_seq, h_dense, h_misc;
 #ifndef WFB_EMU
   cudaEvent_t ev[4]{};
@@ -214,7 +214,7 @@ extern "C" void wfb_aligner_destroy(wfb_aligner_t* a) {
   cudaStreamDestroy(a->stream);
 #endif
   DevBuf* bufs[] = {&a->d_seq, &a->d_pairs, &a->d_slots, &a->d_dense, &a->d_len, &a->d_status, &a->d_counters, &a->d_ctrl,
-                    &a->d_q[0], &a->d_q[1], &a->d_q[2], &a->d_q[3], &a->d_ws, &a->d_arena, &a->d_log, &a->d_runs, &a->d_srcoff, &a->d_tasklog};
+                    &a->d_q[0], &a->d_q[1], &a->d_q[2], &a->d_q[3], &a->d_ws, &a->d_arena, &a->d_log, &a->d_runs, &a->d_srcoff, &a->d_tasklog, &a->d_team};
   for (DevBuf* b : bufs) b->release();
   a->h_seq.release();
   a->h_dense.release();
@@ -358,7 +358,7 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     });
   /* ---- workspaces ---- */
   const int W = (int)align_up(maxP + maxT + 8, 8);
-  const long long ws_stride = 2LL * pen.R * 5 * W;
+  const long long ws_stride = 2LL * pen.R * 5 * W + 2LL * pen.R * 5 * ((W + 63) / 64) + 64; /* rows + their block maxima (wfb_overlap) */
   const int score_cap = std::max(WFB_RECOVERY_MIN_SCORE, pen.x * WFB_FALLBACK_MIN_LENGTH) + 12;
   const long long arena_stride = 5LL * (score_cap + 2) * (score_cap + 2) + 64;
   const int maxruns = 2 * score_cap + 16;
@@ -440,12 +440,24 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
         d_cta_log = (long long*)a->d_tasklog.p;
         WFB_MEMSET(d_cta_log, 0, sizeof(long long) * (4 * (size_t)ctas + 2 * (size_t)n), s);
       }
+      /* team mode: idle CTAs help the owners of wide wavefronts (WFB_TEAM=0 turns it off) */
+      WfbTeamSlot* d_team = nullptr;
+      int* d_team_list = nullptr;
+#ifndef WFB_EMU
+      if (!(getenv("WFB_TEAM") && atoi(getenv("WFB_TEAM")) == 0)) {
+        const size_t tb = sizeof(WfbTeamSlot) * (size_t)ctas + sizeof(int) * WFB_TEAM_LIST;
+        if (a->d_team.ensure(tb)) { g_last_error = "device allocation failed (team slots)"; return WFB_ENOMEM; }
+        WFB_MEMSET(a->d_team.p, 0, tb, s);
+        d_team = (WfbTeamSlot*)a->d_team.p;
+        d_team_list = (int*)((char*)a->d_team.p + sizeof(WfbTeamSlot) * (size_t)ctas);
+      }
+#endif
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[2], s));
 #endif
       WFB_LAUNCH(wfb_persist_kernel, ctas, kBreakThreads, s, pq, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq, (int32_t*)a->d_ws.p, ws_stride,
                  W, (int32_t*)a->d_arena.p, arena_stride, (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, pen, d_slots,
-                 d_status, d_counters, d_cta_log);
+                 d_status, d_counters, d_cta_log, d_team, d_team_list);
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[3], s));
 #endif
@@ -465,9 +477,10 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
         std::vector<long long> cl((size_t)4 * ctas + 2 * (size_t)n);
         WFB_D2H(cl.data(), d_cta_log, sizeof(long long) * cl.size(), s);
         WFB_STREAM_SYNC(s);
-        long long t0 = LLONG_MAX, t1 = 0, busy = 0;
+        long long t0 = LLONG_MAX, t1 = 0, busy = 0, help = 0;
         std::vector<long long> ends;
-        for (int c = 0; c < ctas; ++c) { if (cl[4 * c + 2]) t0 = std::min(t0, cl[4 * c + 2]); t1 = std::max(t1, cl[4 * c + 1]); busy += cl[4 * c]; ends.push_back(cl[4 * c + 1]); }
+        for (int c = 0; c < ctas; ++c) { if (cl[4 * c + 2]) t0 = std::min(t0, cl[4 * c + 2]); t1 = std::max(t1, cl[4 * c + 1]); busy += cl[4 * c]; help += cl[4 * c + 3]; ends.push_back(cl[4 * c + 1]); }
+        fprintf(stderr, "[wfb] persist helper CTA-ms %.0f\n", help * 1e-6);
         std::sort(ends.begin(), ends.end());
         const double span = (double)(t1 - t0) * 1e-6;
         fprintf(stderr, "[wfb] persist ctas=%d span_ms=%.1f busy=%.3f  CTA exit times (ms): p10=%.1f p50=%.1f p90=%.1f p99=%.1f max=%.1f\n", ctas, span,

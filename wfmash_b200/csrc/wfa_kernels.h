@@ -520,13 +520,9 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
       if (ex_d2) basep[ob[WFB_D2] + k] = rd2;
     }
   }
-#undef WFB_CELL
-#undef WFB_CELL_A
-#undef WFB_CELL_X
 #if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
   const long long pt1 = WFB_PT_CLOCK();
 #endif
-#undef WFB_END_HANDOFF
   /* trimmed [lo,hi] of each component = min / max diagonal holding an in-bounds offset */
   {
     const int lane = wfb_lane();
@@ -607,11 +603,47 @@ struct WfbOverlapShared {
   unsigned hitmask[(WFB_RMAX * 5 + 31) / 32]; /* bit q set <=> found[q] valid */
 };
 
+/* Block maxima of one wavefront's rows (all threads, no barrier inside): bm[(slot * 5 + c) * NB + b] = max offset over the row
+ * positions p = k + kshift in block b (64 positions) that lie in the component's trimmed range. See wfb_overlap. */
+#define WFB_BM_SHIFT 6
+WFB_DEV void wfb_row_bmax(const WfbRing& r, int slot, const int32_t* base, int32_t* bm, int NB, int kshift) {
+#ifndef WFB_EMU
+  const int nwarps = WFB_NT >> 5, warp_id = WFB_TID >> 5, lane = WFB_TID & 31;
+  for (int c = 0; c < 5; ++c) {
+    if (!r.ex[slot][c]) continue;
+    const int lo = r.lo[slot][c], hi = r.hi[slot][c];
+    if (lo > hi) continue;
+    const int32_t* p = base + r.boff[slot][c];
+    int32_t* out = bm + (slot * 5 + c) * NB;
+    const int bfirst = (lo + kshift) >> WFB_BM_SHIFT, blast = (hi + kshift) >> WFB_BM_SHIFT;
+    for (int b = bfirst + 2 * warp_id; b <= blast; b += 2 * nwarps) { /* two blocks per trip: four independent loads per lane */
+      const int ka = (b << WFB_BM_SHIFT) - kshift + lane;
+      const int32_t v0 = (ka >= lo && ka <= hi) ? p[ka] : WFB_OFFSET_NULL;
+      const int32_t v1 = (ka + 32 >= lo && ka + 32 <= hi) ? p[ka + 32] : WFB_OFFSET_NULL;
+      const int32_t v2 = (b + 1 <= blast && ka + 64 >= lo && ka + 64 <= hi) ? p[ka + 64] : WFB_OFFSET_NULL;
+      const int32_t v3 = (b + 1 <= blast && ka + 96 >= lo && ka + 96 <= hi) ? p[ka + 96] : WFB_OFFSET_NULL;
+      const int m0 = wfb_warp_max(max(v0, v1)), m1 = wfb_warp_max(max(v2, v3));
+      if (lane == 0) { out[b] = m0; if (b + 1 <= blast) out[b + 1] = m1; }
+    }
+  }
+#else
+  (void)r; (void)slot; (void)base; (void)bm; (void)NB; (void)kshift;
+#endif
+}
+
+/* bm0 / bm1: block maxima of the rows of r0's / r1's direction (nullptr = none kept: every diagonal is tested). With them a
+ * candidate's diagonal range is first walked block by block: off0[k0] + off1[kinv - k0] >= tlen needs
+ * max(block of r0) + max(the one or two blocks of r1 that face it) >= tlen — a necessary condition, so skipping a block never loses a
+ * hit, and blocks are visited in ascending k0, so the first hit found is still the reference's. While the two directions are
+ * far from meeting (all of phase 2 but its last steps) almost every block is skipped: the reference's hottest function
+ * (wavefront_bialign_breakpoint_indel2indel, 28 % of its alignment time) turns into a walk over 1/64 of the data. */
 WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const WfbRing& r1, const int32_t* base1,
                          const WfbPen& pen, int score_0, int score_1, bool bp_forward, int plen, int tlen,
-                         WfbBreakpoint* bp, WfbOverlapShared* os, WfbAcc& acc) {
+                         WfbBreakpoint* bp, WfbOverlapShared* os, WfbAcc& acc, int32_t* bm0 = nullptr, const int32_t* bm1 = nullptr,
+                         int NB = 0, int kshift = 0) {
   const int R = pen.R, s0 = score_0 % R;
   if (!r0.ex[s0][WFB_M]) return; /* uniform */
+  if (bm0) wfb_row_bmax(r0, s0, base0, bm0, NB, kshift); /* the newest wavefront's maxima: used now, and by the next `scope` calls of the other direction */
   const int s1cur = score_1 % R; /* slots of score_1 - i follow by subtraction (i < scope < R) */
 #if defined(WFB_PHASE_TIMERS) && !defined(WFB_EMU)
   const long long pto = WFB_PT_CLOCK();
@@ -664,6 +696,51 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
     const int32_t* p1 = base1 + r1.boff[si][c];
     int kfound = INT_MAX;
 #ifndef WFB_EMU
+    unsigned long long tested = 0; /* diagonals (and block bounds) actually examined */
+    if (bm0) {
+      const int32_t* m0row = bm0 + (s0 * 5 + c) * NB;
+      const int32_t* m1row = bm1 + (si * 5 + c) * NB;
+      const int bfirst = (max_lo + kshift) >> WFB_BM_SHIFT, blast = (min_hi + kshift) >> WFB_BM_SHIFT;
+      for (int bb = bfirst; bb <= blast && kfound == INT_MAX; bb += 32) {
+        const int b = bb + lane;
+        bool flag = false;
+        if (b <= blast) {
+          const int k0a = max((b << WFB_BM_SHIFT) - kshift, max_lo), k0b = min((b << WFB_BM_SHIFT) + 63 - kshift, min_hi);
+          const int p1lo = kinv - k0b + kshift, p1hi = kinv - k0a + kshift; /* row positions of r1 facing [k0a, k0b] */
+          const int m1 = max(m1row[p1lo >> WFB_BM_SHIFT], m1row[p1hi >> WFB_BM_SHIFT]);
+          flag = m0row[b] + m1 >= tlen;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, flag);
+        tested += (unsigned)min(32, blast - bb + 1);
+        while (bal && kfound == INT_MAX) { /* exact test of the flagged blocks, lowest first */
+          const int bx = bb + __ffs((int)bal) - 1;
+          bal &= bal - 1;
+          const int k0a = max((bx << WFB_BM_SHIFT) - kshift, max_lo), k0b = min((bx << WFB_BM_SHIFT) + 63 - kshift, min_hi);
+          tested += (unsigned)(k0b - k0a + 1);
+          int32_t o0[2], o1[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int k0 = k0a + 32 * u + lane;
+            const bool in = k0 <= k0b;
+            o0[u] = in ? p0[k0] : WFB_OFFSET_NULL;
+            o1[u] = in ? p1[kinv - k0] : WFB_OFFSET_NULL;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int k0 = k0a + 32 * u + lane;
+            bool hit = o0[u] + o1[u] >= tlen;
+            if (hit && c != WFB_M) {
+              const int kk = bp_forward ? k0 : kinv - k0;
+              const int32_t oo = bp_forward ? o0[u] : o1[u];
+              if (oo - kk > plen || oo > tlen) hit = false;
+            }
+            const unsigned hb = __ballot_sync(0xffffffffu, hit);
+            if (hb && kfound == INT_MAX) kfound = k0a + 32 * u + __ffs((int)hb) - 1;
+          }
+        }
+      }
+    } else {
+    tested = (unsigned long long)(min_hi - max_lo + 1);
     /* WFB_OVL_UNROLL chunks of 32 diagonals per trip: their loads are independent and in flight together (the scan
      * is a chain of memory round trips otherwise); the ballots are then examined in ascending order, so the first
      * satisfying diagonal is still the lowest one */
@@ -689,7 +766,9 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
         if (bal && kfound == INT_MAX) kfound = kb + 32 * u + __ffs((int)bal) - 1;
       }
     }
+    }
 #else
+    const unsigned long long tested = (unsigned long long)(min_hi - max_lo + 1);
     for (int k0 = max_lo; k0 <= min_hi; ++k0) { /* one diagonal per trip in the single-thread emulation */
       const int k1 = kinv - k0;
       const int32_t o0 = p0[k0], o1 = p1[k1];
@@ -713,7 +792,7 @@ WFB_STEP_INLINE void wfb_overlap(const WfbRing& r0, const int32_t* base0, const 
         os->hitmask[q >> 5] |= 1u << (q & 31);
 #endif
       }
-      acc.overlap += (unsigned long long)(min_hi - max_lo + 1);
+      acc.overlap += tested;
     }
   }
   WFB_SYNC();
@@ -851,6 +930,382 @@ struct WfbAllocFixed { /* breakpoint kernel: every (slot, component) has a fixed
   }
 };
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Team mode: SEVERAL CTAs on ONE score step of a wide wavefront.
+ *
+ * Why: a record whose alignment runs through tens of kilobases of non-homologous sequence has a score of several 10^4 and
+ * wavefronts of several 10^4 diagonals; its breakpoint task is one long chain of wide score steps that a single CTA needs ~10 s
+ * for (measured on scerevisiae8: six such records hold the kernel for 5 s after every other record has finished). Nothing in a
+ * step depends on another diagonal of the same step, so idle CTAs of the persistent grid lend a hand:
+ *   * the task's owner CTA posts how many helpers it could use (slot.want) on a board in global memory;
+ *   * a CTA waiting for its next task attaches to an owner (slot.members) and from then on serves its steps;
+ *   * per step the owner computes the uniform part (inputs, range, output rows) exactly as wfb_step_work does, publishes it
+ *     as a WfbStepDesc, and everybody — owner included — claims chunks of WFB_TEAM_CHUNK diagonals with a CAS ticket;
+ *     a chunk is the same 4-diagonal-group pass as in wfb_step_work, reading / writing the owner's rows in global memory;
+ *   * trim ranges / anti-diagonal maxima are reduced with global atomics into the slot, `done` counts finished chunks; the owner
+ *     waits for done == total, folds the reductions into its shared-memory ring and finishes the step as usual.
+ * Every cell is computed by exactly one thread with exactly the arithmetic of wfb_step_work, so the results do not depend on who
+ * helped. Two buffers (epoch parity) keep a helper that is still reading step e out of the way of step e + 1; the ticket
+ * carries the epoch, so a stale helper can never claim a chunk of a later step. Visibility: writers fence before counting a chunk
+ * done, readers fence after claiming a ticket (gpu-scope fences also invalidate the SM's L1, B300_MICROARCH.md "L1D flush trigger").
+ * ---------------------------------------------------------------------------------------------- */
+#ifndef WFB_TEAM_CHUNK
+#define WFB_TEAM_CHUNK 1024 /* diagonals per ticket: one 4-diagonal group per thread of a 256-thread CTA */
+#endif
+#ifndef WFB_TEAM_MIN_WIDTH
+#define WFB_TEAM_MIN_WIDTH 4096 /* wavefront width (both directions together in phase 1) from which help is worth asking for */
+#endif
+#define WFB_TEAM_MAX_HELPERS 47
+
+struct WfbStepDesc { /* the uniform part of one score step of one direction */
+  WfbIn in[7];        /* m_misms, m_open1, m_open2, i1_ext, i2_ext, d1_ext, d2_ext */
+  int ob[5];
+  int lo, hi, safe_lo, safe_hi, kfirst;
+  int plen, tlen, cend, nchunks;
+  unsigned flags;     /* bit i (0..6): input i is null; bits 8..11: I1, I2, D1, D2 exist */
+  unsigned pad_;
+  const uint8_t* pseq;
+  const uint8_t* tseq;
+};
+struct WfbTeamRed { int lo[5], hi[5], ak, tmax, end, pad_[3]; };
+struct WfbTeamSlot { /* one per CTA of the persistent grid, in global memory */
+  unsigned epoch;     /* last published step */
+  int want;           /* helpers the owner could use now (0 = none) */
+  int members;        /* helpers attached */
+  int quit;           /* the owner's task is over: helpers leave */
+  int32_t* basep;     /* the owner's wavefront workspace */
+  unsigned long long next[2]; /* (epoch << 32) | next chunk, per parity */
+  int done[2], total[2], ndir[2];
+  WfbStepDesc d[2][2]; /* [parity][direction] */
+  WfbTeamRed red[2][2];
+};
+
+#ifndef WFB_EMU
+WFB_DEV int wfb_ld_vol(const int* p) { return *(const volatile int*)p; }
+WFB_DEV unsigned wfb_ld_volu(const unsigned* p) { return *(const volatile unsigned*)p; }
+
+/* the uniform prologue of wfb_step_work: inputs, range, output rows, ring bookkeeping (thread 0). Returns false for the all-null step. */
+WFB_DEV bool wfb_team_prologue(WfbRing& ring, const WfbPen& pen, int score, const uint8_t* pseq, const uint8_t* tseq, int plen, int tlen, int cend,
+                               const WfbAllocFixed& alloc, int* red_maxak, const int slot, const int par, WfbStepDesc& D) {
+  const int R = pen.R, nslot = slot + 1 == R ? 0 : slot + 1;
+  const int npar = par == 2 ? 0 : par + 1;
+  const int d_x = pen.x, d_o1 = pen.o1 + pen.e1, d_o2 = pen.o2 + pen.e2;
+  const int s_e1 = wfb_slot_back(slot, pen.e1, R), s_e2 = wfb_slot_back(slot, pen.e2, R);
+  D.in[0] = wfb_fetch_slot(ring, WFB_M, score >= d_x, wfb_slot_back(slot, d_x, R));
+  D.in[1] = wfb_fetch_slot(ring, WFB_M, score >= d_o1, wfb_slot_back(slot, d_o1, R));
+  D.in[2] = wfb_fetch_slot(ring, WFB_M, score >= d_o2, wfb_slot_back(slot, d_o2, R));
+  D.in[3] = wfb_fetch_slot(ring, WFB_I1, score >= pen.e1, s_e1);
+  D.in[4] = wfb_fetch_slot(ring, WFB_I2, score >= pen.e2, s_e2);
+  D.in[5] = wfb_fetch_slot(ring, WFB_D1, score >= pen.e1, s_e1);
+  D.in[6] = wfb_fetch_slot(ring, WFB_D2, score >= pen.e2, s_e2);
+  unsigned flags = 0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) if (D.in[i].lo > D.in[i].hi) flags |= 1u << i;
+  D.plen = plen; D.tlen = tlen; D.cend = cend; D.pseq = pseq; D.tseq = tseq; D.pad_ = 0;
+  if ((flags & 0x7fu) == 0x7fu) { /* wavefront_compute_affine2p.c:341-351 + wavefront_extend.c:95-103 */
+    if (WFB_TID == 0) {
+      for (int c = 0; c < 5; ++c) {
+        ring.ex[slot][c] = 0;
+        ring.lo[nslot][c] = INT_MAX;
+        ring.hi[nslot][c] = INT_MIN;
+        ring.mak[nslot][c] = INT_MIN;
+      }
+      ring.cw[slot] = 0;
+      red_maxak[npar] = 0;
+    }
+    D.flags = flags; D.nchunks = 0; D.lo = 1; D.hi = -1; D.safe_lo = 1; D.safe_hi = -1; D.kfirst = 0;
+    for (int c = 0; c < 5; ++c) D.ob[c] = 0;
+    return false;
+  }
+  const bool n_m = flags & 1u, n_o1 = flags & 2u, n_o2 = flags & 4u, n_i1 = flags & 8u, n_i2 = flags & 16u, n_d1 = flags & 32u, n_d2 = flags & 64u;
+  int lo = D.in[0].lo, hi = D.in[0].hi;
+  lo = min(lo, D.in[1].lo - 1); hi = max(hi, D.in[1].hi + 1);
+  lo = min(lo, D.in[3].lo + 1); hi = max(hi, D.in[3].hi + 1);
+  lo = min(lo, D.in[5].lo - 1); hi = max(hi, D.in[5].hi - 1);
+  lo = min(lo, D.in[2].lo - 1); hi = max(hi, D.in[2].hi + 1);
+  lo = min(lo, D.in[4].lo + 1); hi = max(hi, D.in[4].hi + 1);
+  lo = min(lo, D.in[6].lo - 1); hi = max(hi, D.in[6].hi - 1);
+  const bool ex_i1 = !n_o1 || !n_i1, ex_d1 = !n_o1 || !n_d1, ex_i2 = !n_o2 || !n_i2, ex_d2 = !n_o2 || !n_d2;
+  if (ex_i1) flags |= 1u << 8;
+  if (ex_i2) flags |= 1u << 9;
+  if (ex_d1) flags |= 1u << 10;
+  if (ex_d2) flags |= 1u << 11;
+  alloc(slot, lo, hi, D.ob);
+  if (WFB_TID == 0) {
+    ring.ex[slot][WFB_M] = 1;
+    ring.ex[slot][WFB_I1] = ex_i1;
+    ring.ex[slot][WFB_I2] = ex_i2;
+    ring.ex[slot][WFB_D1] = ex_d1;
+    ring.ex[slot][WFB_D2] = ex_d2;
+    for (int c = 0; c < 5; ++c) {
+      ring.boff[slot][c] = D.ob[c];
+      ring.lo[nslot][c] = INT_MAX;
+      ring.hi[nslot][c] = INT_MIN;
+      ring.mak[nslot][c] = INT_MIN;
+    }
+    red_maxak[npar] = 0;
+    ring.cw[slot] = hi - lo + 1;
+  }
+  int safe_lo = lo, safe_hi = hi;
+#pragma unroll
+  for (int i = 0; i < 7; ++i)
+    if (!(flags & (1u << i))) { safe_lo = max(safe_lo, D.in[i].lo + 1); safe_hi = min(safe_hi, D.in[i].hi - 4); }
+  safe_hi = min(safe_hi, hi - 3);
+  D.lo = lo; D.hi = hi; D.safe_lo = safe_lo; D.safe_hi = safe_hi;
+  D.kfirst = lo - ((lo + alloc.kalign) & 3);
+  D.nchunks = (hi - D.kfirst) / WFB_TEAM_CHUNK + 1;
+  D.flags = flags;
+  return true;
+}
+
+/* One chunk of one published step: the 4-diagonal-group pass of wfb_step_work over diagonals
+ * [kfirst + chunk * WFB_TEAM_CHUNK, + WFB_TEAM_CHUNK). Accumulates the caller's trim / anti-diagonal registers. */
+WFB_DEV void wfb_team_chunk(const WfbStepDesc& D, int32_t* basep, int chunk, int* red_end_global, WfbAcc& acc, int tlo[5], int thi[5], int& tak, int& tmax) {
+  const WfbIn m_misms = D.in[0], m_open1 = D.in[1], m_open2 = D.in[2], i1_ext = D.in[3], i2_ext = D.in[4], d1_ext = D.in[5], d2_ext = D.in[6];
+  const bool n_m = D.flags & 1u, n_o1 = D.flags & 2u, n_o2 = D.flags & 4u, n_i1 = D.flags & 8u, n_i2 = D.flags & 16u, n_d1 = D.flags & 32u, n_d2 = D.flags & 64u;
+  const bool ex_i1 = D.flags & (1u << 8), ex_i2 = D.flags & (1u << 9), ex_d1 = D.flags & (1u << 10), ex_d2 = D.flags & (1u << 11);
+  const int plen = D.plen, tlen = D.tlen, cend = D.cend, lo = D.lo, hi = D.hi, safe_lo = D.safe_lo, safe_hi = D.safe_hi;
+  const uint8_t* const pseq = D.pseq;
+  const uint8_t* const tseq = D.tseq;
+  const int ak_end = tlen - plen;
+  int* const red_end = red_end_global; /* WFB_END_HANDOFF writes red_end[par] */
+  const int par = 0;
+  struct { unsigned char* runflag; int runbias; } alloc = {nullptr, 0}; /* no run flags on the end-to-end path */
+  const int* const ob = D.ob;
+  const int kbeg = D.kfirst + chunk * WFB_TEAM_CHUNK;
+  const int kend = min(hi, kbeg + WFB_TEAM_CHUNK - 1);
+  for (int k0 = kbeg + 4 * WFB_TID; k0 <= kend; k0 += 4 * WFB_NT) {
+    int32_t rm[4], ri1[4], ri2[4], rd1[4], rd2[4];
+    const bool safe = k0 >= safe_lo && k0 <= safe_hi;
+    const int4 NUL4 = make_int4(WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL, WFB_OFFSET_NULL);
+    int4 vo1 = NUL4, vo2 = NUL4, vi1 = NUL4, vi2 = NUL4, vd1 = NUL4, vd2 = NUL4, vmm = NUL4;
+    int32_t so1m = WFB_OFFSET_NULL, so1p = WFB_OFFSET_NULL, so2m = WFB_OFFSET_NULL, so2p = WFB_OFFSET_NULL;
+    int32_t si1 = WFB_OFFSET_NULL, si2 = WFB_OFFSET_NULL, sd1 = WFB_OFFSET_NULL, sd2 = WFB_OFFSET_NULL;
+    if (safe) {
+      if (!n_o1) { const int32_t* p = basep + m_open1.off + k0; vo1 = wfb_ld_row4(p); so1m = wfb_ld_row1(p - 1); so1p = wfb_ld_row1(p + 4); }
+      if (!n_o2) { const int32_t* p = basep + m_open2.off + k0; vo2 = wfb_ld_row4(p); so2m = wfb_ld_row1(p - 1); so2p = wfb_ld_row1(p + 4); }
+      if (!n_i1) { const int32_t* p = basep + i1_ext.off + k0; vi1 = wfb_ld_row4(p); si1 = wfb_ld_row1(p - 1); }
+      if (!n_i2) { const int32_t* p = basep + i2_ext.off + k0; vi2 = wfb_ld_row4(p); si2 = wfb_ld_row1(p - 1); }
+      if (!n_d1) { const int32_t* p = basep + d1_ext.off + k0; vd1 = wfb_ld_row4(p); sd1 = wfb_ld_row1(p + 4); }
+      if (!n_d2) { const int32_t* p = basep + d2_ext.off + k0; vd2 = wfb_ld_row4(p); sd2 = wfb_ld_row1(p + 4); }
+      if (!n_m)  { vmm = wfb_ld_row4(basep + m_misms.off + k0); }
+    } else {
+      vo1 = make_int4(wfb_get(basep, m_open1, k0), wfb_get(basep, m_open1, k0 + 1), wfb_get(basep, m_open1, k0 + 2), wfb_get(basep, m_open1, k0 + 3));
+      so1m = wfb_get(basep, m_open1, k0 - 1); so1p = wfb_get(basep, m_open1, k0 + 4);
+      vo2 = make_int4(wfb_get(basep, m_open2, k0), wfb_get(basep, m_open2, k0 + 1), wfb_get(basep, m_open2, k0 + 2), wfb_get(basep, m_open2, k0 + 3));
+      so2m = wfb_get(basep, m_open2, k0 - 1); so2p = wfb_get(basep, m_open2, k0 + 4);
+      vi1 = make_int4(wfb_get(basep, i1_ext, k0), wfb_get(basep, i1_ext, k0 + 1), wfb_get(basep, i1_ext, k0 + 2), WFB_OFFSET_NULL);
+      si1 = wfb_get(basep, i1_ext, k0 - 1);
+      vi2 = make_int4(wfb_get(basep, i2_ext, k0), wfb_get(basep, i2_ext, k0 + 1), wfb_get(basep, i2_ext, k0 + 2), WFB_OFFSET_NULL);
+      si2 = wfb_get(basep, i2_ext, k0 - 1);
+      vd1 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d1_ext, k0 + 1), wfb_get(basep, d1_ext, k0 + 2), wfb_get(basep, d1_ext, k0 + 3));
+      sd1 = wfb_get(basep, d1_ext, k0 + 4);
+      vd2 = make_int4(WFB_OFFSET_NULL, wfb_get(basep, d2_ext, k0 + 1), wfb_get(basep, d2_ext, k0 + 2), wfb_get(basep, d2_ext, k0 + 3));
+      sd2 = wfb_get(basep, d2_ext, k0 + 4);
+      vmm = make_int4(wfb_get(basep, m_misms, k0), wfb_get(basep, m_misms, k0 + 1), wfb_get(basep, m_misms, k0 + 2), wfb_get(basep, m_misms, k0 + 3));
+    }
+    WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+    WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+    WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+    WFB_CELL(k0 + 3, vo1.z, so1p,  vo2.z, so2p,  vi1.z, vi2.z, sd1,   sd2,   vmm.w, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+    if ((unsigned)(ak_end - k0) < 4u) {
+      WFB_END_HANDOFF(k0 + 0, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
+      WFB_END_HANDOFF(k0 + 1, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
+      WFB_END_HANDOFF(k0 + 2, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
+      WFB_END_HANDOFF(k0 + 3, rm[3], ri1[3], ri2[3], rd1[3], rd2[3])
+    }
+    if (k0 >= lo && k0 + 3 <= hi) {
+      *(int4*)(basep + ob[WFB_M] + k0) = make_int4(rm[0], rm[1], rm[2], rm[3]);
+      if (ex_i1) *(int4*)(basep + ob[WFB_I1] + k0) = make_int4(ri1[0], ri1[1], ri1[2], ri1[3]);
+      if (ex_i2) *(int4*)(basep + ob[WFB_I2] + k0) = make_int4(ri2[0], ri2[1], ri2[2], ri2[3]);
+      if (ex_d1) *(int4*)(basep + ob[WFB_D1] + k0) = make_int4(rd1[0], rd1[1], rd1[2], rd1[3]);
+      if (ex_d2) *(int4*)(basep + ob[WFB_D2] + k0) = make_int4(rd2[0], rd2[1], rd2[2], rd2[3]);
+    } else {
+#define WFB_STORE1(U)                                                                  \
+      if (k0 + (U) >= lo && k0 + (U) <= hi) {                                            \
+        basep[ob[WFB_M] + k0 + (U)] = rm[U];                                             \
+        if (ex_i1) basep[ob[WFB_I1] + k0 + (U)] = ri1[U];                                \
+        if (ex_i2) basep[ob[WFB_I2] + k0 + (U)] = ri2[U];                                \
+        if (ex_d1) basep[ob[WFB_D1] + k0 + (U)] = rd1[U];                                \
+        if (ex_d2) basep[ob[WFB_D2] + k0 + (U)] = rd2[U];                                \
+      }
+      WFB_STORE1(0) WFB_STORE1(1) WFB_STORE1(2) WFB_STORE1(3)
+#undef WFB_STORE1
+    }
+  }
+}
+
+struct WfbTeamShared {
+  int ticket; unsigned epoch; int flag; int entry; /* owner side: chunk ticket, mirror of the slot's epoch, a broadcast flag, board entry (-1 = none) */
+  unsigned hepoch, hlast; int hcode;              /* helper side */
+};
+
+/* A CTA that has nothing to do serves the steps of owner `ts` until that task ends, its own next task (queue slot `myslot`) is published,
+ * or the launch is over. Thread 0 has already incremented ts->members. */
+struct WfbPQueue;
+WFB_DEV_NOINLINE void wfb_team_work(WfbTeamSlot* ts, unsigned epoch, WfbTeamShared& tsh, WfbAcc& acc);
+WFB_DEV_NOINLINE void wfb_team_help(WfbTeamSlot* ts, WfbTeamShared& tsh, int* my_ready, int* outstanding, int* error, WfbAcc& acc) {
+  if (WFB_TID == 0) tsh.hlast = wfb_ld_volu(&ts->epoch) - 1u; /* the step in progress (if any) is served too */
+  for (;;) {
+    WFB_SYNC();
+    if (WFB_TID == 0) {
+      int code = 0;
+      unsigned e = 0, spins = 0;
+      for (;;) {
+        e = wfb_ld_volu(&ts->epoch);
+        if (e != tsh.hlast) { code = 1; break; }
+        if (wfb_ld_vol(&ts->quit) || wfb_ld_vol(&ts->want) == 0) break;
+        if (my_ready && wfb_ld_vol(my_ready) != 0) break;
+        if (wfb_ld_vol(outstanding) <= 0 || wfb_ld_vol(error) != 0) break;
+        __nanosleep(32);
+        if (++spins > (1u << 27)) break;
+      }
+      tsh.hepoch = e; tsh.hcode = code;
+      if (code) tsh.hlast = e;
+    }
+    WFB_SYNC();
+    if (!tsh.hcode) break;
+    wfb_team_work(ts, tsh.hepoch, tsh, acc);
+  }
+  WFB_SYNC();
+  if (WFB_TID == 0) atomicSub(&ts->members, 1);
+}
+
+/* Claim and compute chunks of the step published under `epoch` until none is left; fold this CTA's reductions into the slot and count its
+ * chunks done. All threads of the CTA (owner or helper). */
+WFB_DEV_NOINLINE void wfb_team_work(WfbTeamSlot* ts, unsigned epoch, WfbTeamShared& tsh, WfbAcc& acc) {
+  const int p = (int)(epoch & 1u);
+  int mine = 0, cur_dir = -1;
+  int tlo[5], thi[5], tak = INT_MIN, tmax = 0;
+  auto flush = [&](int dir) {
+    const unsigned flags = *(const volatile unsigned*)&ts->d[p][dir].flags;
+    const bool exs[5] = {true, (flags >> 8) & 1u, (flags >> 9) & 1u, (flags >> 10) & 1u, (flags >> 11) & 1u};
+    WfbTeamRed* r = &ts->red[p][dir];
+    const int lane = wfb_lane();
+    const int vak = wfb_warp_max(tak);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      if (!exs[c]) continue;
+      int v = wfb_warp_min(tlo[c]); if (lane == 0 && v != INT_MAX) atomicMin(&r->lo[c], v);
+      v = wfb_warp_max(thi[c]);     if (lane == 0 && v != INT_MIN) atomicMax(&r->hi[c], v);
+    }
+    if (lane == 0 && vak != INT_MIN) atomicMax(&r->ak, vak);
+    const int v = wfb_warp_max(tmax);
+    if (lane == 0 && v > 0) atomicMax(&r->tmax, v);
+  };
+  for (;;) {
+    WFB_SYNC();
+    if (WFB_TID == 0) {
+      int t = -1;
+      for (;;) {
+        const unsigned long long old = *(const volatile unsigned long long*)&ts->next[p];
+        if ((unsigned)(old >> 32) != epoch) break;                                   /* not (or no longer) this step */
+        if ((int)(unsigned)old >= wfb_ld_vol(&ts->total[p])) break;                  /* every chunk is taken */
+        if (atomicCAS(&ts->next[p], old, old + 1) == old) { t = (int)(unsigned)old; break; }
+      }
+      tsh.ticket = t;
+    }
+    WFB_SYNC();
+    const int t = tsh.ticket;
+    if (t < 0) break;
+    __threadfence(); /* acquire: the rows earlier steps wrote (on any SM), the descriptor */
+    const int n0 = wfb_ld_vol(&ts->d[p][0].nchunks);
+    const int dir = t < n0 ? 0 : 1;
+    if (dir != cur_dir) {
+      if (cur_dir >= 0) flush(cur_dir);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { tlo[c] = INT_MAX; thi[c] = INT_MIN; }
+      tak = INT_MIN; tmax = 0;
+      cur_dir = dir;
+    }
+    WfbStepDesc D;
+    { /* the descriptor through L2 (another SM wrote it) */
+      const int* src = (const int*)&ts->d[p][dir];
+      int* dst = (int*)&D;
+#pragma unroll
+      for (int i = 0; i < (int)(sizeof(WfbStepDesc) / sizeof(int)); ++i) dst[i] = __ldcg(src + i);
+    }
+    int32_t* const basep = *(int32_t* const volatile*)&ts->basep;
+    wfb_team_chunk(D, basep, dir == 0 ? t : t - n0, &ts->red[p][dir].end, acc, tlo, thi, tak, tmax);
+    ++mine;
+  }
+  if (cur_dir >= 0) flush(cur_dir);
+  __threadfence(); /* release: this thread's rows and reductions before the chunk count */
+  WFB_SYNC();
+  if (WFB_TID == 0 && mine) atomicAdd(&ts->done[p], mine);
+}
+
+/* Owner: publish one step (one or two directions), take part, wait for the team, fold the reductions into the shared-memory rings.
+ * On return every thread may call wfb_step_finish for the published directions. Returns false on a watchdog / error abort. */
+struct WfbTeamDir {
+  WfbRing* ring; int score; const uint8_t* pseq; const uint8_t* tseq; int cend; WfbAllocFixed alloc; int* red_maxak; int* red_end; int slot, par;
+};
+WFB_DEV_NOINLINE bool wfb_team_step(WfbTeamSlot* ts, WfbTeamShared& tsh, int32_t* ws, const WfbPen& pen, WfbTeamDir* dirs, int ndir, int plen, int tlen, WfbAcc& acc, int* error) {
+  WfbStepDesc D[2];
+  bool live[2] = {false, false};
+  for (int d = 0; d < ndir; ++d)
+    live[d] = wfb_team_prologue(*dirs[d].ring, pen, dirs[d].score, dirs[d].pseq, dirs[d].tseq, plen, tlen, dirs[d].cend, dirs[d].alloc, dirs[d].red_maxak,
+                                dirs[d].slot, dirs[d].par, D[d]);
+  if (ndir == 1) { D[1] = D[0]; D[1].nchunks = 0; }
+  const int total = D[0].nchunks + (ndir == 2 ? D[1].nchunks : 0);
+  const unsigned epoch = tsh.epoch + 1; /* uniform: every thread read tsh.epoch after the caller's barrier */
+  const int p = (int)(epoch & 1u);
+  WFB_SYNC(); /* everybody has read tsh.epoch */
+  if (WFB_TID == 0) {
+    tsh.epoch = epoch;
+    ts->basep = ws;
+    ts->total[p] = total; ts->done[p] = 0; ts->ndir[p] = ndir;
+    for (int d = 0; d < 2; ++d) {
+      ts->d[p][d] = D[d];
+      WfbTeamRed r;
+      for (int c = 0; c < 5; ++c) { r.lo[c] = INT_MAX; r.hi[c] = INT_MIN; }
+      r.ak = INT_MIN; r.tmax = 0; r.end = INT_MIN; r.pad_[0] = r.pad_[1] = r.pad_[2] = 0;
+      ts->red[p][d] = r;
+    }
+    __threadfence();
+    atomicExch(&ts->next[p], (unsigned long long)epoch << 32);
+    __threadfence();
+    *(volatile unsigned*)&ts->epoch = epoch;
+  }
+  if (total > 0) wfb_team_work(ts, epoch, tsh, acc);
+  bool ok = true;
+  if (WFB_TID == 0) {
+    unsigned spins = 0;
+    while (wfb_ld_vol(&ts->done[p]) < total) {
+      if (++spins > (1u << 28)) { *error = 3; ok = false; break; }
+    }
+    __threadfence();
+    for (int d = 0; d < ndir; ++d) {
+      if (!live[d]) continue;
+      WfbRing& ring = *dirs[d].ring;
+      const int slot = dirs[d].slot;
+      const WfbTeamRed* r = &ts->red[p][d];
+      const bool exs[5] = {true, (bool)((D[d].flags >> 8) & 1u), (bool)((D[d].flags >> 9) & 1u), (bool)((D[d].flags >> 10) & 1u), (bool)((D[d].flags >> 11) & 1u)};
+      const int ak = wfb_ld_vol(&r->ak), tmax = wfb_ld_vol(&r->tmax);
+      for (int c = 0; c < 5; ++c) {
+        if (!exs[c]) continue;
+        const int lo = wfb_ld_vol(&r->lo[c]), hi = wfb_ld_vol(&r->hi[c]);
+        if (lo != INT_MAX && lo < ring.lo[slot][c]) ring.lo[slot][c] = lo;
+        if (hi != INT_MIN && hi > ring.hi[slot][c]) ring.hi[slot][c] = hi;
+        if (ak != INT_MIN && ak > ring.mak[slot][c]) ring.mak[slot][c] = ak;
+      }
+      if (tmax > 0 && tmax > dirs[d].red_maxak[dirs[d].par]) dirs[d].red_maxak[dirs[d].par] = tmax;
+      if (tmax > ring.mak[slot][WFB_M]) ring.mak[slot][WFB_M] = tmax;
+      dirs[d].red_end[dirs[d].par] = wfb_ld_vol(&r->end);
+    }
+    tsh.flag = ok ? 1 : 0;
+  }
+  WFB_SYNC();
+  return tsh.flag != 0;
+}
+#endif /* !WFB_EMU */
+
+#undef WFB_CELL
+#undef WFB_CELL_A
+#undef WFB_CELL_X
+#undef WFB_END_HANDOFF
+
 WFB_DEV void wfb_ring_reset(WfbRing& r, int R) {
   for (int i = WFB_TID; i < R * 5; i += WFB_NT) {
     r.lo[i / 5][i % 5] = INT_MAX;
@@ -901,12 +1356,24 @@ struct WfbBreakCtaShared {
   WfbBreakShared sh;
   int sh_st[2];
   int sh_ak[2];
+#ifndef WFB_EMU
+  WfbTeamShared team; /* team.epoch mirrors this CTA's slot epoch for the whole launch */
+#endif
 };
 
 /* One breakpoint sub-problem on one CTA: wavefront_bialign_find_breakpoint (wavefront_bialign.c:974-1082) +
  * the dispatch of both halves (:1188-1212) + the exception path (:1083-1110). */
+#define WFB_TEAM_LIST 32
+struct WfbTeamCtx { /* team mode of the persistent kernel (nullptr slots = off) */
+  WfbTeamSlot* slots; /* one per CTA */
+  int* list;          /* WFB_TEAM_LIST entries: (owner CTA + 1) of the owners that currently want help, 0 = free */
+  int* error;
+  int self;           /* this CTA's slot */
+};
+
 WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const WfbPairDesc* pairs, const uint8_t* seq, int32_t* ws, int W,
-                            const WfbPen& pen, const WfbSink& sink, char* ops_all, int* pair_status, WfbAcc& acc, WfbTaskLog* tasklog) {
+                            const WfbPen& pen, const WfbSink& sink, char* ops_all, int* pair_status, WfbAcc& acc, WfbTaskLog* tasklog,
+                            const WfbTeamCtx* team = nullptr) {
   WfbBreakShared& sh = S.sh;
   int* const sh_st = S.sh_st;
   int* const sh_ak = S.sh_ak;
@@ -967,6 +1434,58 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
    * examined first, and when it ends the phase the reverse step is not accepted — nothing of it is visible afterwards
    * (its ring slot and the slot it resets lie outside the scope window because R = scope + 2, and re-running the step
    * later rewrites the same values). */
+#ifndef WFB_EMU
+  /* Team mode (see above): once the wavefronts are wide, post how many helpers could be used; a step is run by the team whenever
+   * at least one helper is attached, by this CTA alone otherwise — the results are the same either way. */
+  WfbTeamSlot* const tslot = (team && team->slots) ? team->slots + team->self : nullptr;
+  bool team_posted = false;
+  auto team_ready = [&](int width) -> bool { /* uniform; one barrier */
+    if (!tslot || width < WFB_TEAM_MIN_WIDTH) return false;
+    if (WFB_TID == 0) {
+      int desired = width / WFB_TEAM_CHUNK;
+      desired = desired > WFB_TEAM_MAX_HELPERS ? WFB_TEAM_MAX_HELPERS : desired;
+      if (wfb_ld_vol(&tslot->want) != desired) {
+        *(volatile int*)&tslot->want = desired;
+        if (S.team.entry < 0) { /* put this CTA on the board (when it is full the task simply gets no help) */
+          __threadfence();
+          for (int i = 0; i < WFB_TEAM_LIST; ++i)
+            if (atomicCAS(&team->list[i], 0, team->self + 1) == 0) { S.team.entry = i; break; }
+        }
+      }
+      S.team.flag = wfb_ld_vol(&tslot->members) > 0 ? 1 : 0;
+    }
+    team_posted = true;
+    WFB_SYNC();
+    const bool r = S.team.flag != 0;
+    WFB_SYNC(); /* S.team.flag is reused by the step */
+    return r;
+  };
+  auto team_close = [&]() {
+    if (!team_posted) return;
+    WFB_SYNC();
+    if (WFB_TID == 0 && wfb_ld_vol(&tslot->want) != 0) {
+      if (S.team.entry >= 0) { atomicExch(&team->list[S.team.entry], 0); S.team.entry = -1; }
+      *(volatile int*)&tslot->want = 0;
+      *(volatile int*)&tslot->quit = 1;
+      __threadfence();
+      unsigned spins = 0;
+      while (wfb_ld_vol(&tslot->members) > 0) { __nanosleep(64); if (++spins > (1u << 26)) { *team->error = 4; break; } }
+      *(volatile int*)&tslot->quit = 0;
+      __threadfence();
+    }
+    WFB_SYNC();
+  };
+  /* one direction's step by the team; d = 0 forward, 1 reverse. Ends with a barrier (like wfb_step_work + WFB_SYNC). */
+  auto team_one = [&](int d, int score, int slot_i, int par_i) -> bool {
+    WfbTeamDir td;
+    td.ring = &sh.ring[d]; td.score = score; td.pseq = d ? pr : pf; td.tseq = d ? tr : tf; td.cend = d ? t.cbegin : t.cend; td.alloc = d ? ar : af;
+    td.red_maxak = sh.red_maxak[d]; td.red_end = sh.red_end[d]; td.slot = slot_i; td.par = par_i;
+    WfbAcc ta; ta.cells = ta.overlap = ta.matches = ta.steps = 0; /* a separate object: acc must not escape to the out-of-line call */
+    const bool ok = wfb_team_step(tslot, S.team, ws, pen, &td, 1, plen, tlen, ta, team->error);
+    acc.matches += ta.matches;
+    return ok;
+  };
+#endif
 #if WFB_DUAL_PHASE1
   int width_f = 1, width_r = 1;
   /* ring slot / reduction parity of the NEXT forward and reverse score, advanced by hand (no runtime modulo per step) */
@@ -976,6 +1495,19 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
     if (forward_max_ak + reverse_max_ak >= max_antidiagonal) break;
     const unsigned long long m_before = acc.matches;
 #ifndef WFB_EMU
+    bool rev_half = WFB_TID >= (WFB_NT >> 1);
+    if (team_ready(width_f + width_r)) {
+      WfbTeamDir td[2];
+      td[0].ring = &sh.ring[0]; td[0].score = score_forward + 1; td[0].pseq = pf; td[0].tseq = tf; td[0].cend = t.cend; td[0].alloc = af;
+      td[0].red_maxak = sh.red_maxak[0]; td[0].red_end = sh.red_end[0]; td[0].slot = nslot_f; td[0].par = npar_f;
+      td[1].ring = &sh.ring[1]; td[1].score = score_reverse + 1; td[1].pseq = pr; td[1].tseq = tr; td[1].cend = t.cbegin; td[1].alloc = ar;
+      td[1].red_maxak = sh.red_maxak[1]; td[1].red_end = sh.red_end[1]; td[1].slot = nslot_r; td[1].par = npar_r;
+      WfbAcc ta; ta.cells = ta.overlap = ta.matches = ta.steps = 0;
+      const bool ok = wfb_team_step(tslot, S.team, ws, pen, td, 2, plen, tlen, ta, team->error);
+      acc.matches += ta.matches;
+      if (!ok) { status = WFB_ST_END_UNREACHABLE; score_reached = INT_MAX; break; }
+      rev_half = false; /* the statistics of a dropped speculative step stay counted in team mode */
+    } else {
     /* warps are dealt to the two directions in proportion to the widths of their last wavefronts */
     const int nwarps = WFB_NT >> 5;
     int fw = nwarps >> 1; /* eighths of the CTA for the forward direction, without a division */
@@ -985,7 +1517,7 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
     if (width_r > 3 * width_f) fw = nwarps >> 2;
     fw = fw < 1 ? 1 : (fw > nwarps - 1 ? nwarps - 1 : fw);
     const int fnt = fw << 5;
-    const bool rev_half = WFB_TID >= fnt;
+    rev_half = WFB_TID >= fnt;
     { /* one call site (one copy of the step body in the instruction cache); the direction is a per-warp choice */
       const int d = rev_half ? 1 : 0;
       WfbAllocFixed ad = af;
@@ -993,6 +1525,7 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
       wfb_step_work(sh.ring[d], ws, pen, (rev_half ? score_reverse : score_forward) + 1, rev_half ? pr : pf, rev_half ? tr : tf, plen, tlen,
                     rev_half ? t.cbegin : t.cend, ad, sh.red_maxak[d], sh.red_end[d], acc, rev_half ? WFB_TID - fnt : WFB_TID,
                     rev_half ? WFB_NT - fnt : fnt, rev_half ? nslot_r : nslot_f, rev_half ? npar_r : npar_f);
+    }
     }
 #else
     const bool rev_half = true; /* the single emulated thread plays both halves, one after the other */
@@ -1043,23 +1576,53 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
 #endif
   /* phase 2 (:1045-1079): advance while scanning for overlaps */
   const int gap_opening = max(pen.o1, pen.o2);
+  /* block maxima of the wavefront rows for the overlap scan (see wfb_overlap): kept behind the rows in the CTA's workspace */
+  const int NB = (W + 63) >> WFB_BM_SHIFT;
+  int32_t* const bmf = ws + 2 * R * 5 * W;
+  int32_t* const bmr = bmf + R * 5 * NB;
+  if (status == WFB_ST_OK) { /* uniform */
+    for (int i = 0; i < pen.scope; ++i) {
+      if (score_forward - i >= 0) wfb_row_bmax(sh.ring[0], (score_forward - i) % R, ws, bmf, NB, kshift);
+      if (score_reverse - i >= 0) wfb_row_bmax(sh.ring[1], (score_reverse - i) % R, ws, bmr, NB, kshift);
+    }
+    WFB_SYNC();
+  }
   while (status == WFB_ST_OK) {
     if (last_wf_forward) {
       const int min_score_reverse = (score_reverse > pen.scope - 1) ? score_reverse - (pen.scope - 1) : 0;
       if (score_forward + min_score_reverse - gap_opening >= sh.bp.score) break;
-      wfb_overlap(sh.ring[0], ws, sh.ring[1], ws, pen, score_forward, score_reverse, true, plen, tlen, &sh.bp, &sh.os, acc);
+      wfb_overlap(sh.ring[0], ws, sh.ring[1], ws, pen, score_forward, score_reverse, true, plen, tlen, &sh.bp, &sh.os, acc, bmf, bmr, NB, kshift);
       ++score_reverse;
-      const int st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
+      int st;
+#ifndef WFB_EMU
+      if (team_ready(sh.ring[1].cw[(score_reverse - 1) % R])) {
+        const int sl = score_reverse % R, pa = score_reverse % 3;
+        if (!team_one(1, score_reverse, sl, pa)) { status = WFB_ST_END_UNREACHABLE; score_reached = INT_MAX; break; }
+        st = wfb_step_finish(sh.ring[1], pen, score_reverse, plen, tlen, t.cbegin, null_r, sh.red_maxak[1], sh.red_end[1], max_ak, acc, sl, pa);
+      } else
+#endif
+      st = wfb_step(sh.ring[1], ws, pen, score_reverse, pr, tr, plen, tlen, t.cbegin, null_r, ar, sh.red_maxak[1], sh.red_end[1], max_ak, acc);
       if (st != WFB_ST_OK) { status = st; score_reached = score_reverse; break; }
     }
     const int min_score_forward = (score_forward > pen.scope - 1) ? score_forward - (pen.scope - 1) : 0;
     if (min_score_forward + score_reverse - gap_opening >= sh.bp.score) break;
-    wfb_overlap(sh.ring[1], ws, sh.ring[0], ws, pen, score_reverse, score_forward, false, plen, tlen, &sh.bp, &sh.os, acc);
+    wfb_overlap(sh.ring[1], ws, sh.ring[0], ws, pen, score_reverse, score_forward, false, plen, tlen, &sh.bp, &sh.os, acc, bmr, bmf, NB, kshift);
     ++score_forward;
-    const int st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
+    int st;
+#ifndef WFB_EMU
+    if (team_ready(sh.ring[0].cw[(score_forward - 1) % R])) {
+      const int sl = score_forward % R, pa = score_forward % 3;
+      if (!team_one(0, score_forward, sl, pa)) { status = WFB_ST_END_UNREACHABLE; score_reached = INT_MAX; break; }
+      st = wfb_step_finish(sh.ring[0], pen, score_forward, plen, tlen, t.cend, null_f, sh.red_maxak[0], sh.red_end[0], max_ak, acc, sl, pa);
+    } else
+#endif
+    st = wfb_step(sh.ring[0], ws, pen, score_forward, pf, tf, plen, tlen, t.cend, null_f, af, sh.red_maxak[0], sh.red_end[0], max_ak, acc);
     if (st != WFB_ST_OK) { status = st; score_reached = score_forward; break; }
     last_wf_forward = true;
   }
+#ifndef WFB_EMU
+  team_close();
+#endif
   if (tasklog && WFB_TID == 0) {
     WfbTaskLog tl;
     tl.t0 = tl_t0; tl.t1 = wfb_globaltimer(); tl.smid = wfb_smid(); tl.steps = (int)(acc.steps - tl_s0);
@@ -1405,14 +1968,23 @@ struct WfbPersistShared {
   WfbBreakCtaShared brk;
   WfbBaseShared base;
   int slot;
+  int help_owner;
 };
 
 WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, WfbPQueue q, const WfbPairDesc* pairs, const uint8_t* seq,
               int32_t* ws_all, long long ws_stride, int W, int32_t* arena_all, long long arena_stride, WfbBaseMeta* log_all, int score_cap,
               WfbRun* runs_all, int maxruns, WfbPen pen, char* ops_all, int* pair_status, WfbCounters* counters,
-              long long* cta_log /* optional (WFB_TRACE): per CTA {ns busy in tasks, exit time, start time, tasks} */) {
+              long long* cta_log /* optional (WFB_TRACE): per CTA {ns busy in tasks, exit time, start time, tasks} */,
+              WfbTeamSlot* team_slots /* optional: team mode (one zeroed slot per CTA) */, int* team_list /* WFB_TEAM_LIST zeroed ints */) {
   WFB_KERNEL_PROLOGUE
   WFB_SHARED WfbPersistShared S;
+#ifndef WFB_EMU
+  WfbTeamCtx tctx;
+  tctx.slots = team_slots; tctx.list = team_list; tctx.error = q.error; tctx.self = bid;
+  if (WFB_TID == 0) { S.brk.team.epoch = 0; S.brk.team.entry = -1; S.brk.team.flag = 0; }
+  int held_slot = -1; /* thread 0: a queue slot claimed before an excursion as a helper */
+  long long log_help = 0;
+#endif
   const long long log_t0 = cta_log ? wfb_globaltimer() : 0;
   long long log_busy = 0;
   int32_t* const ws = ws_all + (long long)bid * ws_stride;
@@ -1433,7 +2005,12 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
     if (WFB_TID == 0) {
       const long long pt_idle0 = WFB_PT_CLOCK();
       (void)pt_idle0;
+#ifndef WFB_EMU
+      int slot = held_slot >= 0 ? held_slot : wfb_atomic_add(q.head, 1);
+      held_slot = -1;
+#else
       int slot = wfb_atomic_add(q.head, 1);
+#endif
       if (slot >= q.cap) {
         slot = -1;
       } else {
@@ -1441,6 +2018,19 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
         unsigned spins = 0;
         while (atomicAdd(&q.ready[slot], 0) == 0) {
           if (atomicAdd(q.outstanding, 0) <= 0 || atomicAdd(q.error, 0) != 0) { slot = -1; break; }
+          if (team_slots) { /* nothing to do: does a wide task want help? */
+            int owner = -1;
+            for (int i = 0; i < WFB_TEAM_LIST && owner < 0; ++i) {
+              const int o = wfb_ld_vol(&team_list[(i + bid) & (WFB_TEAM_LIST - 1)]) - 1;
+              if (o < 0 || o == bid) continue;
+              WfbTeamSlot* ts = team_slots + o;
+              const int w = wfb_ld_vol(&ts->want);
+              if (w <= 0 || wfb_ld_vol(&ts->quit) || wfb_ld_vol(&ts->members) >= w) continue;
+              if (atomicAdd(&ts->members, 1) < w) owner = o;
+              else atomicSub(&ts->members, 1);
+            }
+            if (owner >= 0) { held_slot = slot; S.help_owner = owner; slot = -2; break; }
+          }
           __nanosleep(256);
           if (++spins > (1u << 26)) { *q.error = 2; slot = -1; break; } /* watchdog (~20 s) */
         }
@@ -1454,6 +2044,18 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
     }
     WFB_SYNC();
     const int slot = S.slot;
+#ifndef WFB_EMU
+    if (slot == -2) { /* lend a hand to a wide task until our own next task is published */
+      const long long h0 = cta_log ? wfb_globaltimer() : 0;
+      int* my_ready = nullptr;
+      if (WFB_TID == 0) my_ready = &q.ready[held_slot];
+      WfbAcc ta; ta.cells = ta.overlap = ta.matches = ta.steps = 0;
+      wfb_team_help(team_slots + S.help_owner, S.brk.team, my_ready, q.outstanding, q.error, ta);
+      acc.matches += ta.matches;
+      if (cta_log) log_help += wfb_globaltimer() - h0;
+      continue;
+    }
+#endif
     if (slot < 0) break;
     WfbTask t;
 #ifndef WFB_EMU
@@ -1474,7 +2076,11 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
       if (WFB_TID == 0) { WFB_PT_ADD(20, WFB_PT_CLOCK() - pt_task0); WFB_PT_ADD(21, 1); }
     } else {
       n_break++;
+#ifndef WFB_EMU
+      wfb_break_task(S.brk, t, slot, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, nullptr, team_slots ? &tctx : nullptr);
+#else
       wfb_break_task(S.brk, t, slot, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, nullptr);
+#endif
       if (WFB_TID == 0) { WFB_PT_ADD(24, WFB_PT_CLOCK() - pt_task0); WFB_PT_ADD(25, 1); }
     }
     (void)pt_task0;
@@ -1501,7 +2107,11 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
   }
   if (cta_log && WFB_TID == 0) {
     cta_log[4 * bid + 0] = log_busy; cta_log[4 * bid + 1] = wfb_globaltimer(); cta_log[4 * bid + 2] = log_t0;
-    cta_log[4 * bid + 3] = (long long)(n_break + n_base);
+#ifndef WFB_EMU
+    cta_log[4 * bid + 3] = log_help;
+#else
+    cta_log[4 * bid + 3] = 0;
+#endif
   }
   {
     unsigned long long m = acc.matches, mb = acc_base.matches;

@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -24,6 +26,7 @@
 void wfb_set_last_error_(const std::string& s); /* wfa_host.cu */
 static inline void wfb_set_last_error(const char* msg) { wfb_set_last_error_(msg); }
 
+void wfb_trace_mark_(const char* tag); /* wfa_host.cu */
 void wfb_take_endsfree_counters_(wfb_aligner_t* a, double* kernel_ms, uint64_t* h2d, uint64_t* d2h); /* wfa_host.cu */
 
 namespace {
@@ -476,8 +479,12 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     pairs[(size_t)i] = {r.target, (int32_t)r.target_length, r.query, (int32_t)r.query_length}; /* wflign.cpp:148 */
     cap += (int64_t)(r.target_length + r.query_length);
   }
-  std::vector<char> ops((size_t)cap);
+  wfb_trace_mark_("paf_batch: begin");
+  std::unique_ptr<char[]> ops_buf(new (std::nothrow) char[(size_t)cap]); /* not zero-filled: a GB of page faults on one thread otherwise */
+  if (!ops_buf) { wfb_set_last_error("out of host memory"); return WFB_ENOMEM; }
+  char* const ops = ops_buf.get();
   std::vector<wfb_aln_result_t> res((size_t)n);
+  wfb_trace_mark_("paf_batch: ops buffer allocated");
   /* scheduling hint: expected edits from the mapping's identity estimate (the same quantity the reference's own progress / cost
    * heuristics use); it only orders the work, the alignments do not depend on it */
   std::vector<float> hint((size_t)n);
@@ -486,22 +493,26 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     const float d = (id > 0.f && id <= 1.f) ? std::max(1.f - id, 0.002f) : 0.05f;
     hint[(size_t)i] = d * (float)std::max(recs[i].query_length, recs[i].target_length);
   }
-  int rc = wfb_align_batch_hinted(a, pairs.data(), n, hint.data(), ops.data(), cap, res.data(), stats);
+  int rc = wfb_align_batch_hinted(a, pairs.data(), n, hint.data(), ops, cap, res.data(), stats);
   if (rc != WFB_OK) return rc;
+  wfb_trace_mark_("paf_batch: main alignments (wfb_align_batch_hinted)");
   std::vector<Cigar> cig((size_t)n);
   std::vector<int32_t> status((size_t)n, WFB_REC_WRITTEN);
   for_each_record(n, cap, [&](int64_t i) {
     if (res[(size_t)i].status != 0) { status[(size_t)i] = WFB_REC_UNALIGNED; return; } /* wflign.cpp:150-152 */
-    cig[(size_t)i] = rle(ops.data() + res[(size_t)i].ops_offset, res[(size_t)i].ops_len);
+    cig[(size_t)i] = rle(ops + res[(size_t)i].ops_offset, res[(size_t)i].ops_len);
   });
-  std::vector<char>().swap(ops);
+  ops_buf.reset();
+  wfb_trace_mark_("paf_batch: run-length conversion");
   if (!params->disable_chain_patching) {
     double ms = 0; uint64_t h2d = 0, d2h = 0;
     wfb_take_endsfree_counters_(a, &ms, &h2d, &d2h);
     rc = patch_round(a, recs, cig, status, true, term_group);
     if (rc != WFB_OK) return rc;
+    wfb_trace_mark_("paf_batch: head patches");
     rc = patch_round(a, recs, cig, status, false, term_group);
     if (rc != WFB_OK) return rc;
+    wfb_trace_mark_("paf_batch: tail patches");
     wfb_take_endsfree_counters_(a, &ms, &h2d, &d2h);
     if (stats) { stats->patch_kernel_ms = ms; stats->h2d_bytes += h2d; stats->d2h_bytes += d2h; }
   }
@@ -518,11 +529,13 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     std::string& text = line[(size_t)i];
     if (!(params->sam_format ? write_sam(text, c, r, *params) : write_paf(text, c, r, *params))) { rec_status[i] = WFB_REC_FILTERED; text.clear(); }
   });
+  wfb_trace_mark_("paf_batch: swizzle + text");
   int64_t total = 0;
   for (int i = 0; i < n; ++i) { line_offset[i] = total; total += (int64_t)line[(size_t)i].size(); }
   line_offset[n] = total;
   *out_len = total;
   if (total > out_cap || !out) { wfb_set_last_error("PAF output buffer too small (see *out_len)"); return WFB_ECAP; }
   for (int i = 0; i < n; ++i) memcpy(out + line_offset[i], line[(size_t)i].data(), line[(size_t)i].size());
+  wfb_trace_mark_("paf_batch: text copied out");
   return WFB_OK;
 }

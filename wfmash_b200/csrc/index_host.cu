@@ -421,7 +421,7 @@ cudaError_t ws_get(const wfb_index_t* ix, int slot, size_t bytes, T** out) {
   return cudaSuccess;
 }
 enum { WS_SEQ, WS_FRAGS, WS_FQ, WS_GROUP, WS_CUT, WS_Q, WS_QN, WS_FN, WS_FST, WS_LFRAG, WS_KC, WS_GS, WS_LTMP, WS_LOCI, WS_LC, WS_FOFF, WS_QMAX,
-       WS_S1, WS_MS, WS_SLAB, WS_MAP, WS_SORTED, WS_CNT, WS_CTR, WS_KP, WS_KP2, WS_KF, WS_KF2, WS_KF3, WS_IDX, WS_IDX2, WS_IDX3, WS_CUBTMP };
+       WS_S1, WS_MS, WS_SLAB, WS_MAP, WS_SORTED, WS_CNT, WS_CTR, WS_KP, WS_KP2, WS_KF, WS_KF2, WS_KF3, WS_IDX, WS_IDX2, WS_IDX3, WS_CUBTMP, WS_REDO };
 
 struct L1Dev { /* what ix_l1_kernel leaves in device memory (views into the index's workspace); the L2 kernel reads it in place */
   uint8_t* d_seq = nullptr; wfb_frag_t* d_frags = nullptr; IxFragQuery* d_fq = nullptr; int *d_group = nullptr, *d_cut = nullptr;
@@ -444,6 +444,10 @@ int l1_run(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_bas
   P.k = k; P.w = w; P.s = s; P.minimum_hits = lp->minimum_hits;
   P.skip_self = lp->skip_self; P.skip_prefix = lp->skip_prefix; P.lower_triangular = lp->lower_triangular;
   P.ncut = lp->n_cutoffs; P.smem_cap = 4096; P.gcap = 1 << 17; P.max_loci = 256; P.complexity_threshold = lp->kmer_complexity_threshold;
+  if (getenv("WFB_L1_FRAG_CAPS")) { /* tests: "gcap,max_loci" of the first pass, to force the redo pass below */
+    int g = 0, m = 0;
+    if (sscanf(getenv("WFB_L1_FRAG_CAPS"), "%d,%d", &g, &m) == 2 && g >= P.smem_cap && m >= 1) { P.gcap = g; P.max_loci = m; }
+  }
   P.par_sweep = getenv("WFB_L1_SERIAL") ? 0 : 1;
   const size_t smem = std::max(std::max(sketch_smem, (size_t)P.smem_cap * 8), (size_t)IX_PAR_CAP * 8 + ix_par_aux_bytes());
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -479,7 +483,7 @@ int l1_run(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_bas
   IX_CHECK(cudaEventCreate(&e0)); IX_CHECK(cudaEventCreate(&e1));
   IX_CHECK(cudaEventRecord(e0));
   IX_LAUNCH(ix_l1_kernel, grid, 128, smem, D.d_seq, D.d_frags, D.d_fq, n, npow2, P, ix->d_table, ix->n_buckets, ix->d_points, D.d_group, D.d_cut,
-            D.d_q, D.d_qn, D.d_kc, D.d_qmax, D.d_gs, D.d_ltmp, D.d_loci, D.d_lfrag, D.d_lc, loci_cap, D.d_foff, D.d_fn, D.d_fst);
+            D.d_q, D.d_qn, D.d_kc, D.d_qmax, D.d_gs, D.d_ltmp, D.d_loci, D.d_lfrag, D.d_lc, loci_cap, D.d_foff, D.d_fn, D.d_fst, (const int*)nullptr, 0);
   IX_CHECK(cudaEventRecord(e1));
   IX_CHECK(cudaEventSynchronize(e1));
   IX_CHECK(cudaGetLastError());
@@ -489,6 +493,35 @@ int l1_run(const wfb_index_t* ix, const wfb_l1_params_t* lp, const char* seq_bas
     D.kernel_ms = t;
   }
   IX_CHECK(cudaMemcpy(&D.n_loci, D.d_lc, 8, cudaMemcpyDeviceToHost));
+  if ((long long)D.n_loci <= loci_cap) {
+    /* Fragments that outgrew the per-fragment scratch of the first pass (> 2^17 interval points after the gather, or > 256 candidate
+     * regions: a repeat-rich fragment, a pangenome of hundreds of haplotypes) are run again, alone, with 32x the scratch — the reference
+     * has no such limit (mappingCore.hpp:88-215), so neither has the phase. Only if a fragment outgrows that too does its status stay set. */
+    std::vector<int> hst((size_t)n), redo;
+    IX_CHECK(cudaMemcpy(hst.data(), D.d_fst, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    for (int f = 0; f < n; ++f) if (hst[(size_t)f] == WFB_ECAP) redo.push_back(f);
+    if (!redo.empty()) {
+      IxL1Params P2 = P;
+      P2.gcap = 1 << 22; P2.max_loci = 8192;
+      const int grid2 = (int)std::min<size_t>(redo.size(), 16);
+      int* d_list = nullptr;
+      IX_CHECK(ws_get(ix, WS_REDO, 4 * redo.size(), &d_list));
+      IX_CHECK(cudaMemcpy(d_list, redo.data(), 4 * redo.size(), cudaMemcpyHostToDevice));
+      IX_CHECK(ws_get(ix, WS_GS, 8 * (size_t)P2.gcap * grid2, &D.d_gs));
+      IX_CHECK(ws_get(ix, WS_LTMP, sizeof(IxL1Locus) * (size_t)2 * P2.max_loci * grid2, &D.d_ltmp));
+      IX_CHECK(cudaEventRecord(e0));
+      IX_LAUNCH(ix_l1_kernel, grid2, 128, smem, D.d_seq, D.d_frags, D.d_fq, n, npow2, P2, ix->d_table, ix->n_buckets, ix->d_points, D.d_group, D.d_cut,
+                D.d_q, D.d_qn, D.d_kc, D.d_qmax, D.d_gs, D.d_ltmp, D.d_loci, D.d_lfrag, D.d_lc, loci_cap, D.d_foff, D.d_fn, D.d_fst, (const int*)d_list,
+                (int)redo.size());
+      IX_CHECK(cudaEventRecord(e1));
+      IX_CHECK(cudaEventSynchronize(e1));
+      IX_CHECK(cudaGetLastError());
+      float t = 0;
+      cudaEventElapsedTime(&t, e0, e1);
+      D.kernel_ms += t;
+      IX_CHECK(cudaMemcpy(&D.n_loci, D.d_lc, 8, cudaMemcpyDeviceToHost));
+    }
+  }
   if ((long long)D.n_loci > loci_cap) { wfb_set_last_error_("loci buffer too small"); rc = WFB_ECAP; goto done; }
 done:
   if (e0) cudaEventDestroy(e0);
@@ -621,8 +654,15 @@ extern "C" int wfb_map_fragments_batch(const wfb_index_t* ix, const wfb_l1_param
 #ifndef WFB_EMU
   std::lock_guard<std::mutex> ws_lock(ix->ws_mu);
   L1Dev D;
-  const long long loci_cap = out->l1 ? out->l1->loci_cap : (64LL * n + 1024);
-  rc = l1_run(ix, lp, seq_base, seq_bytes, frags, fq, n, loci_cap, D);
+  long long loci_cap = out->l1 ? out->l1->loci_cap : (64LL * n + 1024);
+  if (!out->l1 && getenv("WFB_L1_LOCI_CAP0")) loci_cap = std::max<long long>(1, atoll(getenv("WFB_L1_LOCI_CAP0"))); /* tests: force the growth path */
+  for (int attempt = 0;; ++attempt) {
+    rc = l1_run(ix, lp, seq_base, seq_bytes, frags, fq, n, loci_cap, D);
+    /* the library's own loci buffer grows to what the kernel counted (an all-vs-all of many haplotypes averages far more than
+     * 64 candidate regions per fragment); a caller-provided buffer (out->l1) is the caller's to grow */
+    if (rc == WFB_ECAP && !out->l1 && attempt < 3 && (long long)D.n_loci > loci_cap) { loci_cap = (long long)D.n_loci + (long long)D.n_loci / 8 + 1024; continue; }
+    break;
+  }
   if (rc != WFB_OK) return rc;
   if (out->l1) { rc = l1_copy_out(D, n, s, ix->params.window_size, ix->params.kmer_size, out->l1); if (rc != WFB_OK) return rc; }
   out->l1_kernel_ms = D.kernel_ms;

@@ -388,7 +388,7 @@ WFB_KERNEL(ix_l1_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, const
            IxL1Params P, const IxSlot* table, long long nbuckets, const uint64_t* points, const int* ref_group, const int* cutoffs,
            wfb_minmer_t* q_out, int* q_count, float* q_complexity, unsigned long long* q_maxhash, uint64_t* gscratch_all, IxL1Locus* loci_tmp_all,
            IxL1Locus* loci_out, int* loci_frag, unsigned long long* loci_counter, long long loci_cap, long long* frag_loci_off, int* frag_loci_n,
-           int* frag_status
+           int* frag_status, const int* frag_list /* optional: only these fragments (the redo pass with larger per-fragment scratch) */, int n_list
 #ifdef WFB_EMU
            , unsigned char* smem_emu
 #endif
@@ -407,8 +407,16 @@ WFB_KERNEL(ix_l1_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, const
   WFB_SHARED IxParShared sh_par;
   uint64_t* gscratch = gscratch_all + (long long)bid * P.gcap;
   IxL1Locus* ltmp = loci_tmp_all + (long long)bid * 2 * P.max_loci; /* [0,max) = out list, [max,2max) = local */
-  for (int f = bid; f < nfrags; f += nblocks) {
+  const int n_todo = frag_list ? n_list : nfrags;
+  for (int fi = bid; fi < n_todo; fi += nblocks) {
+    const int f = frag_list ? frag_list[fi] : fi;
     WFB_SYNC();
+    if (frag_list) { /* whatever the first pass left of this fragment (a clipped list) is dropped: the L2 kernel skips loci of fragment -1 */
+      const long long o0 = frag_loci_off[f];
+      const int on = frag_loci_n[f];
+      for (int i = WFB_TID; i < on; i += WFB_NT) loci_frag[o0 + i] = -1;
+      WFB_SYNC();
+    }
     const wfb_frag_t fr = frags[f];
     wfb_minmer_t* qo = q_out + (size_t)f * P.s;
     const int qn = sk_sketch_block(smem, sh_warp, seq_base, fr, P.k, P.s, npow2_max, qo);

@@ -295,6 +295,7 @@ WFB_KERNEL(l2_kernel, const wfb_minmer_t* index, long long n_index, const IxL1Lo
   for (long long li = gwarp; li < n_loci; li += nwarps) {
     const IxL1Locus L = loci[li];
     const int f = locus_frag[li];
+    if (f < 0) continue; /* a clipped list that ix_l1_kernel's redo pass replaced */
     const int qn = q_count[f];
     if (qn <= 0) continue;
     /* stage-1 top-ANI test (computeMap.hpp:999-1012): the heap pops the best locus first and stops at the first one

@@ -18,6 +18,8 @@
 
 void wfb_set_last_error_(const std::string& s); /* wfa_host.cu */
 
+void wfb_trace_mark_(const char* tag); /* wfa_host.cu */
+
 namespace {
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -340,6 +342,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     return WFB_EINVAL;
   }
   const double t_begin = now_s();
+  wfb_trace_mark_("align_phase: begin");
   *out = nullptr; *out_len = 0;
   std::unordered_map<std::string, const wfb_seq_t*> tmap, qmap;
   for (int32_t i = 0; i < n_targets; ++i) tmap.emplace(targets[i].name, &targets[i]);
@@ -381,6 +384,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     }
     a = b + 1;
   }
+  wfb_trace_mark_("align_phase: rows parsed");
   /* the records' slices (upper-cased, N-masked, query strand-corrected), over the host cores: records are independent */
   {
     const int64_t nrec = (int64_t)recs.size();
@@ -406,6 +410,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     worker();
     for (auto& t : th) t.join();
   }
+  wfb_trace_mark_("align_phase: slices");
   int64_t written = 0;
   double kernel_ms = 0;
   /* One launch per batch, and every launch ends with a tail (few CTAs finishing the costliest records alone): as few batches as the
@@ -457,6 +462,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
       rc = wfb_biwfa_paf_batch(aligner, arr.data(), (int32_t)(b1 - b0), &params->output, buf.data(), (int64_t)buf.size(), &len, off.data(), st.data(), &as);
     }
     if (rc != WFB_OK) return rc;
+    wfb_trace_mark_("align_phase: batch aligned");
     /* Aligner::processMappingRecord re-emits every line that carries a cg:Z: field as its whitespace-separated fields joined by
      * single tabs (computeAlignments.hpp:486-516): the trailing tab do_biwfa_alignment writes before the newline disappears.
      * Lines without a CIGAR field (SAM records) pass through unchanged. */
@@ -497,6 +503,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     sum.score_steps += as.score_steps; sum.base_score_steps += as.base_score_steps; sum.h2d_bytes += as.h2d_bytes; sum.d2h_bytes += as.d2h_bytes;
     ++n_batches;
   }
+  wfb_trace_mark_("align_phase: lines re-emitted");
   std::string text;
   {
     size_t total = 0;
@@ -505,6 +512,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     for (const std::string& l : line) text += l;
   }
   *out = to_c_text(text);
+  wfb_trace_mark_("align_phase: text assembled");
   if (!*out) { wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
   *out_len = (int64_t)text.size();
   if (stats) {

@@ -18,12 +18,24 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches{0};
 void wfb_set_last_error_(const std::string& s) { g_last_error = s; }
 void wfb_count_launch_() { g_launches.fetch_add(1); }
+/* WFB_TRACE: host-side stage timeline ("[wfb] t+<ms since the previous mark> <tag>") */
+void wfb_trace_mark_(const char* tag) {
+  static const bool on = getenv("WFB_TRACE") != nullptr;
+  if (!on) return;
+  static thread_local double last = 0;
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  fprintf(stderr, "[wfb] t+%9.1f ms  %s\n", last == 0 ? 0.0 : now - last, tag);
+  last = now;
+}
 
 #ifndef WFB_EMU
 #define WFB_CHECK(call)                                                                              \
@@ -37,6 +49,11 @@ void wfb_count_launch_() { g_launches.fetch_add(1); }
 #define WFB_LAUNCH(kernel, grid, block, stream, ...)                                                 \
   do {                                                                                               \
     kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                           \
+    g_launches.fetch_add(1);                                                                         \
+  } while (0)
+#define WFB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                                      \
+  do {                                                                                               \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                      \
     g_launches.fetch_add(1);                                                                         \
   } while (0)
 typedef cudaStream_t wfb_stream_t;
@@ -56,6 +73,7 @@ static void host_free(void* p) { if (p) cudaFreeHost(p); }
     for (int bid_ = 0; bid_ < (int)(grid); ++bid_) kernel(bid_, (int)(grid), __VA_ARGS__);           \
     g_launches.fetch_add(1);                                                                         \
   } while (0)
+#define WFB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) WFB_LAUNCH(kernel, grid, block, stream, __VA_ARGS__)
 typedef int wfb_stream_t;
 static int dev_malloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -1; }
 static void dev_free(void* p) { free(p); }
@@ -116,7 +134,7 @@ struct wfb_aligner {
   wfb_stream_t stream{};
   DevBuf d_seq, d_pairs, d_slots, d_dense, d_len, d_status, d_counters, d_ctrl;
   DevBuf d_q[4]; /* break[0], break[1], base[0], base[1] */
-  DevBuf d_ws, d_arena, d_log, d_runs, d_srcoff, d_tasklog, d_team;
+  DevBuf d_ws, d_arena, d_log, d_runs, d_srcoff, d_tasklog, d_team, d_flags;
   HostBuf h_seq, h_dense, h_misc;
 #ifndef WFB_EMU
   cudaEvent_t ev[4]{};
@@ -214,7 +232,7 @@ extern "C" void wfb_aligner_destroy(wfb_aligner_t* a) {
   cudaStreamDestroy(a->stream);
 #endif
   DevBuf* bufs[] = {&a->d_seq, &a->d_pairs, &a->d_slots, &a->d_dense, &a->d_len, &a->d_status, &a->d_counters, &a->d_ctrl,
-                    &a->d_q[0], &a->d_q[1], &a->d_q[2], &a->d_q[3], &a->d_ws, &a->d_arena, &a->d_log, &a->d_runs, &a->d_srcoff, &a->d_tasklog, &a->d_team};
+                    &a->d_q[0], &a->d_q[1], &a->d_q[2], &a->d_q[3], &a->d_ws, &a->d_arena, &a->d_log, &a->d_runs, &a->d_srcoff, &a->d_tasklog, &a->d_team, &a->d_flags};
   for (DevBuf* b : bufs) b->release();
   a->h_seq.release();
   a->h_dense.release();
@@ -308,6 +326,7 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
 #ifndef WFB_EMU
   WFB_CHECK(cudaEventRecord(a->ev[0], s));
 #endif
+  wfb_trace_mark_("align: layout");
   WFB_H2D(d_pairs, pd.data(), sizeof(WfbPairDesc) * (size_t)n, s);
   if (hpairs) {
     /* pack the forward copies in pinned memory, one H2D */
@@ -315,12 +334,29 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     uint8_t* hs = (uint8_t*)a->h_seq.p;
     /* only the forward regions are written; the device-side reversed regions are filled by a kernel.
      * Copy the span [first p_off, last t_off+tlen) in one go. */
-    for (int i = 0; i < n; ++i) {
-      memcpy(hs + pd[i].p_off, hpairs[i].pattern, (size_t)pd[i].plen);
-      memset(hs + pd[i].p_off + pd[i].plen, 0, 16);
-      memcpy(hs + pd[i].t_off, hpairs[i].text, (size_t)pd[i].tlen);
-      memset(hs + pd[i].t_off + pd[i].tlen, 0, 16);
+    {
+      int nt = (int)std::min<long long>(std::min<unsigned>(std::thread::hardware_concurrency(), 32u), n / 4);
+      if (fwd_bytes < (1 << 20)) nt = 1;
+      std::atomic<int> next(0);
+      auto worker = [&]() {
+        for (;;) {
+          const int b = next.fetch_add(16);
+          if (b >= n) return;
+          const int e = std::min(n, b + 16);
+          for (int i = b; i < e; ++i) {
+            memcpy(hs + pd[i].p_off, hpairs[i].pattern, (size_t)pd[i].plen);
+            memset(hs + pd[i].p_off + pd[i].plen, 0, 16);
+            memcpy(hs + pd[i].t_off, hpairs[i].text, (size_t)pd[i].tlen);
+            memset(hs + pd[i].t_off + pd[i].tlen, 0, 16);
+          }
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+      worker();
+      for (auto& t : th) t.join();
     }
+    wfb_trace_mark_("align: sequences packed in pinned memory");
     WFB_H2D(d_seq, hs, (size_t)fwd_bytes, s);
     WFB_MEMSET(d_seq + fwd_bytes, 0, (size_t)fwd_bytes, s);
   } else {
@@ -333,7 +369,10 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     WFB_MEMSET(d_seq, 0, (size_t)seq_bytes, s);
     WFB_LAUNCH(wfb_gather_kernel, std::min(n, a->sm_count * 8), 256, s, d_pairs, n, (const uint8_t*)d_src, d_off, d_off + n, d_seq);
   }
-  WFB_LAUNCH(wfb_reverse_kernel, std::min(n, a->sm_count * 8), 256, s, d_pairs, n, d_seq);
+  if (a->d_flags.ensure(sizeof(int) * (size_t)n)) { g_last_error = "device allocation failed (pair flags)"; return WFB_ENOMEM; }
+  int* d_flags = (int*)a->d_flags.p;
+  WFB_MEMSET(d_flags, 0, sizeof(int) * (size_t)n, s);
+  WFB_LAUNCH(wfb_reverse_kernel, std::min(n, a->sm_count * 8), 256, s, d_pairs, n, d_seq, d_flags);
   WFB_MEMSET(d_slots, 0, (size_t)slot_bytes, s);
   WFB_MEMSET(d_status, 0, sizeof(int) * (size_t)n, s);
   WFB_MEMSET(d_counters, 0, sizeof(WfbCounters), s);
@@ -401,10 +440,18 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     const char* sched = getenv("WFB_SCHED"); /* "level" selects the level-synchronous driver */
     const bool want_persist = !(sched && strcmp(sched, "level") == 0);
     int ctas = cta_break;
+    int seq_smem_words = 0; /* 2-bit packed sequence windows of the running task (wfa_kernels.h): enough for 2 x (52 kb + 52 kb) by default */
 #ifndef WFB_EMU
     {
+      const int kb = getenv("WFB_SEQ_SMEM_KB") ? atoi(getenv("WFB_SEQ_SMEM_KB")) : 56;
+      seq_smem_words = kb > 0 ? kb * 256 : 0;
+      if (seq_smem_words > 0 &&
+          cudaFuncSetAttribute(wfb_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_words * 4) != cudaSuccess) {
+        cudaGetLastError();
+        seq_smem_words = 0;
+      }
       int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfb_persist_kernel, kBreakThreads, 0) == cudaSuccess && nb > 0) ctas = a->sm_count * nb;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfb_persist_kernel, kBreakThreads, (size_t)seq_smem_words * 4) == cudaSuccess && nb > 0) ctas = a->sm_count * nb;
     }
 #endif
     const size_t per_cta = (size_t)ws_stride * 4 + base_cta_bytes;
@@ -455,9 +502,9 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[2], s));
 #endif
-      WFB_LAUNCH(wfb_persist_kernel, ctas, kBreakThreads, s, pq, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq, (int32_t*)a->d_ws.p, ws_stride,
+      WFB_LAUNCH_SMEM(wfb_persist_kernel, ctas, kBreakThreads, (size_t)seq_smem_words * 4, s, pq, (const WfbPairDesc*)d_pairs, (const uint8_t*)d_seq, (int32_t*)a->d_ws.p, ws_stride,
                  W, (int32_t*)a->d_arena.p, arena_stride, (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, pen, d_slots,
-                 d_status, d_counters, d_cta_log, d_team, d_team_list);
+                 d_status, d_counters, d_cta_log, d_team, d_team_list, (const int*)d_flags, seq_smem_words);
 #ifndef WFB_EMU
       WFB_CHECK(cudaEventRecord(a->ev[3], s));
 #endif
@@ -624,8 +671,10 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
   WFB_D2H(h_len, d_len, sizeof(int) * (size_t)n, s);
   WFB_D2H(h_status, d_status, sizeof(int) * (size_t)n, s);
   WFB_D2H(h_cnt, d_counters, sizeof(WfbCounters), s);
+  wfb_trace_mark_("align: kernels enqueued");
   WFB_D2H(h_dense, d_dense, (size_t)slot_bytes, s);
   WFB_STREAM_SYNC(s);
+  wfb_trace_mark_("align: kernels + D2H done");
   int64_t out_off = 0;
   for (int i = 0; i < n; ++i) {
     wfb_aln_result_t& r = results[i];
@@ -637,12 +686,33 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     if (r.status == 0) {
       const int len = h_len[i];
       if (out_off + len > ops_cap) { g_last_error = "ops buffer too small"; return WFB_ECAP; }
-      memcpy(ops + out_off, h_dense + pd[i].ops_off, (size_t)len);
       r.ops_len = len;
-      r.score = gap_affine2p_score(ops + out_off, len, pen);
       out_off += len;
     }
   }
+  { /* the copies and the score scans are independent per pair (a GB of operations per large batch): over the host cores */
+    int nt = (int)std::min<long long>(std::min<unsigned>(std::thread::hardware_concurrency(), 32u), n / 4);
+    if (out_off < (1 << 20)) nt = 1;
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+      for (;;) {
+        const int b = next.fetch_add(16);
+        if (b >= n) return;
+        const int e = std::min(n, b + 16);
+        for (int i = b; i < e; ++i) {
+          wfb_aln_result_t& r = results[i];
+          if (r.status != 0) continue;
+          memcpy(ops + r.ops_offset, h_dense + pd[i].ops_off, (size_t)r.ops_len);
+          r.score = gap_affine2p_score(ops + r.ops_offset, r.ops_len, pen);
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+  }
+  wfb_trace_mark_("align: ops copied out + scores");
   if (getenv("WFB_TRACE")) {
     float ms = 0.f;
 #ifndef WFB_EMU

@@ -204,6 +204,42 @@ WFB_DEV int wfb_match_run(const uint8_t* p, const uint8_t* t, int limit) {
   return wfb_match_run_words(p, t, limit);
 }
 
+/* ---- 2-bit packed sequence windows in shared memory -----------------------------------------------------------
+ * A breakpoint task keeps its four sequence slices (pattern / text, forward / reversed) packed at 2 bits per base in
+ * shared memory: the extension of a cell — the latency chain of every score step (first byte from L2 / HBM, then 16 bases per
+ * round trip) — becomes shared-memory reads of 16 bases per word pair. Only equality matters, so any injective code works:
+ * (c >> 1) & 3 maps A, C, T, G to 0, 1, 2, 3. Pairs holding any other byte (N after the reference's masking) keep the byte-wise
+ * global path (wfb_reverse_kernel flags them). S[w] holds bases 16w .. 16w+15 of the 16-byte-aligned chunk the slice starts in. */
+WFB_DEV uint32_t wfb_pk16(const uint32_t* S, int i) {
+  const int w = i >> 4;
+  return __funnelshift_r(S[w], S[w + 1], (unsigned)(i & 15) * 2u);
+}
+WFB_DEV int wfb_match_run_packed(const uint32_t* P, int pi, const uint32_t* T, int ti, int limit) {
+  int n = 0;
+  while (n < limit) {
+    const uint32_t x = wfb_pk16(P, pi + n) ^ wfb_pk16(T, ti + n);
+    if (x) { n += (__ffs((int)x) - 1) >> 1; break; }
+    n += 16;
+  }
+  return n < limit ? n : limit;
+}
+/* pack nwords x 16 bases starting at the 16-byte-aligned address g (all threads; the caller syncs) */
+WFB_DEV void wfb_pack_seq(const uint8_t* g, uint32_t* S, int nwords) {
+#ifndef WFB_EMU
+  for (int j = WFB_TID; j < nwords; j += WFB_NT) {
+    const uint4 v = __ldg((const uint4*)(g + 16 * (size_t)j));
+    uint32_t y0 = (v.x >> 1) & 0x03030303u, y1 = (v.y >> 1) & 0x03030303u, y2 = (v.z >> 1) & 0x03030303u, y3 = (v.w >> 1) & 0x03030303u;
+    y0 = (y0 | (y0 >> 6) | (y0 >> 12) | (y0 >> 18)) & 0xffu;
+    y1 = (y1 | (y1 >> 6) | (y1 >> 12) | (y1 >> 18)) & 0xffu;
+    y2 = (y2 | (y2 >> 6) | (y2 >> 12) | (y2 >> 18)) & 0xffu;
+    y3 = (y3 | (y3 >> 6) | (y3 >> 12) | (y3 >> 18)) & 0xffu;
+    S[j] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+  }
+#else
+  (void)g; (void)S; (void)nwords;
+#endif
+}
+
 WFB_DEV void wfb_prefetch_row(const void* p) {
 #ifndef WFB_EMU
 #if (WFB_PF_NEXT & 3) == 2
@@ -369,7 +405,9 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
     WFB_CELL_A(K, O1M, O1P, O2M, O2P, I1V, I2V, D1V, D2V, MMV, OUT_M, OUT_I1, OUT_I2, OUT_D1, OUT_D2)       \
     if ((OUT_M) >= 0) {                                                                                   \
       const int v__ = (OUT_M) - (K);                                                                      \
-      const int run__ = wfb_match_run(pseq + v__, tseq + (OUT_M), min(plen - v__, tlen - (OUT_M)));       \
+      const int lim__ = min(plen - v__, tlen - (OUT_M));                                                  \
+      const int run__ = alloc.sp ? wfb_match_run_packed(alloc.sp, alloc.spo + v__, alloc.st, alloc.sto + (OUT_M), lim__) \
+                                 : wfb_match_run(pseq + v__, tseq + (OUT_M), lim__);                       \
       WFB_CELL_X(K, OUT_M, run__)                                                                         \
     }                                                                                                     \
   }
@@ -920,6 +958,9 @@ struct WfbAllocFixed { /* breakpoint kernel: every (slot, component) has a fixed
   int dirbase; /* dir * R * 5 * W + kshift */
   int W;
   int kalign;  /* (k + kalign) % 4 == 0  <=>  cell(k) is 16-byte aligned, the same for every row (W % 8 == 0) */
+  const uint32_t* sp; /* 2-bit packed pattern / text of this direction in shared memory (nullptr: read the bytes from global) */
+  const uint32_t* st;
+  int spo, sto;       /* base index of pattern[0] / text[0] inside sp / st */
   static constexpr unsigned char* runflag = nullptr;
   static const int runbias = 0;
   static const bool kFixedRows = true; /* the row of (slot, component) is known before the step that fills it */
@@ -1071,7 +1112,7 @@ WFB_DEV void wfb_team_chunk(const WfbStepDesc& D, int32_t* basep, int chunk, int
   const int ak_end = tlen - plen;
   int* const red_end = red_end_global; /* WFB_END_HANDOFF writes red_end[par] */
   const int par = 0;
-  struct { unsigned char* runflag; int runbias; } alloc = {nullptr, 0}; /* no run flags on the end-to-end path */
+  struct { unsigned char* runflag; int runbias; const uint32_t* sp; const uint32_t* st; int spo, sto; } alloc = {nullptr, 0, nullptr, nullptr, 0, 0}; /* helpers read the owner's sequences from global memory */
   const int* const ob = D.ob;
   const int kbeg = D.kfirst + chunk * WFB_TEAM_CHUNK;
   const int kend = min(hi, kbeg + WFB_TEAM_CHUNK - 1);
@@ -1371,9 +1412,19 @@ struct WfbTeamCtx { /* team mode of the persistent kernel (nullptr slots = off) 
   int self;           /* this CTA's slot */
 };
 
-WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const WfbPairDesc* pairs, const uint8_t* seq, int32_t* ws, int W,
+#ifndef WFB_TASK_W
+#define WFB_TASK_W 1 /* rows of a task are laid out with the task's own stride (plen + tlen + 8) instead of the batch's largest */
+#endif
+WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const WfbPairDesc* pairs, const uint8_t* seq, int32_t* ws, int W_batch,
                             const WfbPen& pen, const WfbSink& sink, char* ops_all, int* pair_status, WfbAcc& acc, WfbTaskLog* tasklog,
-                            const WfbTeamCtx* team = nullptr) {
+                            const WfbTeamCtx* team = nullptr, uint32_t* seq_smem = nullptr, int seq_smem_words = 0, const int* pair_flags = nullptr) {
+#if WFB_TASK_W
+  /* a sub-problem of 3 kb x 3 kb touches 270 rows: with the batch's stride (2 x 50 kb) they are 400 KB apart — one DRAM page / TLB entry
+   * each; packed with the task's own stride the whole working set is contiguous */
+  const int W = min(W_batch, (((t.pe - t.pb) + (t.te - t.tb) + 8 + 7) >> 3) << 3);
+#else
+  const int W = W_batch;
+#endif
   WfbBreakShared& sh = S.sh;
   int* const sh_st = S.sh_st;
   int* const sh_ak = S.sh_ak;
@@ -1398,6 +1449,25 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
   af.kalign = ar.kalign = kshift & 3; /* dirbase = (multiple of 8) + kshift */
   af.dirbase = kshift;
   ar.dirbase = R * 5 * W + kshift;
+  af.sp = af.st = ar.sp = ar.st = nullptr;
+  af.spo = af.sto = ar.spo = ar.sto = 0;
+  if (seq_smem && pair_flags && pair_flags[t.pair] == 0) { /* uniform */
+    /* the four slices start at arbitrary bases of the pair's sequences: pack from the 16-byte chunk each one starts in */
+    const long long gpf = pd.p_off + t.pb, gtf = pd.t_off + t.tb, gpr = pd.prev_off + (pd.plen - t.pe), gtr = pd.trev_off + (pd.tlen - t.te);
+    const int opf = (int)(gpf & 15), otf = (int)(gtf & 15), opr = (int)(gpr & 15), otr = (int)(gtr & 15);
+    const int wpf = ((opf + plen + 15) >> 4) + 2, wtf = ((otf + tlen + 15) >> 4) + 2, wpr = ((opr + plen + 15) >> 4) + 2, wtr = ((otr + tlen + 15) >> 4) + 2;
+    if (wpf + wtf + wpr + wtr <= seq_smem_words) {
+      uint32_t* s0 = seq_smem; uint32_t* s1 = s0 + wpf; uint32_t* s2 = s1 + wtf; uint32_t* s3 = s2 + wpr;
+      WFB_SYNC(); /* the previous task's steps are done with the buffer */
+      wfb_pack_seq(seq + (gpf - opf), s0, wpf - 1);
+      wfb_pack_seq(seq + (gtf - otf), s1, wtf - 1);
+      wfb_pack_seq(seq + (gpr - opr), s2, wpr - 1);
+      wfb_pack_seq(seq + (gtr - otr), s3, wtr - 1);
+      af.sp = s0; af.spo = opf; af.st = s1; af.sto = otf;
+      ar.sp = s2; ar.spo = opr; ar.st = s3; ar.sto = otr;
+      /* the barrier after the ring reset below orders the packing before the first step */
+    }
+  }
   wfb_ring_reset(sh.ring[0], R);
   wfb_ring_reset(sh.ring[1], R);
   for (int i = WFB_TID; i < WFB_RMAX * 5; i += WFB_NT) sh.os.found[i] = INT_MAX;
@@ -1520,8 +1590,7 @@ WFB_DEV void wfb_break_task(WfbBreakCtaShared& S, const WfbTask t, int ti, const
     rev_half = WFB_TID >= fnt;
     { /* one call site (one copy of the step body in the instruction cache); the direction is a per-warp choice */
       const int d = rev_half ? 1 : 0;
-      WfbAllocFixed ad = af;
-      ad.dirbase = rev_half ? ar.dirbase : af.dirbase;
+      const WfbAllocFixed ad = rev_half ? ar : af;
       wfb_step_work(sh.ring[d], ws, pen, (rev_half ? score_reverse : score_forward) + 1, rev_half ? pr : pf, rev_half ? tr : tf, plen, tlen,
                     rev_half ? t.cbegin : t.cend, ad, sh.red_maxak[d], sh.red_end[d], acc, rev_half ? WFB_TID - fnt : WFB_TID,
                     rev_half ? WFB_NT - fnt : fnt, rev_half ? nslot_r : nslot_f, rev_half ? npar_r : npar_f);
@@ -1712,6 +1781,9 @@ struct WfbRun {
 
 struct WfbAllocBump {
   static const int kalign = -1; /* rows are packed back to back: no common alignment, scalar path only */
+  static constexpr const uint32_t* sp = nullptr; /* sequences are read from global memory */
+  static constexpr const uint32_t* st = nullptr;
+  static const int spo = 0, sto = 0;
   unsigned char* runflag; /* ends-free only: runflag[k + runbias] = 1 when M(k) matched >= 4 bases this step; else NULL */
   int runbias;
   int bump; /* next free int in the arena */
@@ -1975,9 +2047,14 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
               int32_t* ws_all, long long ws_stride, int W, int32_t* arena_all, long long arena_stride, WfbBaseMeta* log_all, int score_cap,
               WfbRun* runs_all, int maxruns, WfbPen pen, char* ops_all, int* pair_status, WfbCounters* counters,
               long long* cta_log /* optional (WFB_TRACE): per CTA {ns busy in tasks, exit time, start time, tasks} */,
-              WfbTeamSlot* team_slots /* optional: team mode (one zeroed slot per CTA) */, int* team_list /* WFB_TEAM_LIST zeroed ints */) {
+              WfbTeamSlot* team_slots /* optional: team mode (one zeroed slot per CTA) */, int* team_list /* WFB_TEAM_LIST zeroed ints */,
+              const int* pair_flags /* optional: 0 = the pair is pure ACGT */, int seq_smem_words /* dynamic shared memory, in words */) {
   WFB_KERNEL_PROLOGUE
   WFB_SHARED WfbPersistShared S;
+#ifndef WFB_EMU
+  extern __shared__ uint32_t wfb_seq_smem[];
+  uint32_t* const seq_smem = seq_smem_words > 0 ? wfb_seq_smem : nullptr;
+#endif
 #ifndef WFB_EMU
   WfbTeamCtx tctx;
   tctx.slots = team_slots; tctx.list = team_list; tctx.error = q.error; tctx.self = bid;
@@ -2018,7 +2095,8 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
         unsigned spins = 0;
         while (atomicAdd(&q.ready[slot], 0) == 0) {
           if (atomicAdd(q.outstanding, 0) <= 0 || atomicAdd(q.error, 0) != 0) { slot = -1; break; }
-          if (team_slots) { /* nothing to do: does a wide task want help? */
+          if (team_slots && (spins & 3u) == 0) { /* nothing to do: does a wide task want help? (every 4th poll: an idle CTA's instructions
+                                                    compete with the working CTA of the same SM) */
             int owner = -1;
             for (int i = 0; i < WFB_TEAM_LIST && owner < 0; ++i) {
               const int o = wfb_ld_vol(&team_list[(i + bid) & (WFB_TEAM_LIST - 1)]) - 1;
@@ -2077,7 +2155,8 @@ WFB_KERNEL_LB(wfb_persist_kernel, WFB_BREAK_MAXTHREADS, WFB_BREAK_MINBLOCKS, Wfb
     } else {
       n_break++;
 #ifndef WFB_EMU
-      wfb_break_task(S.brk, t, slot, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, nullptr, team_slots ? &tctx : nullptr);
+      wfb_break_task(S.brk, t, slot, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, nullptr, team_slots ? &tctx : nullptr, seq_smem, seq_smem_words,
+                     pair_flags);
 #else
       wfb_break_task(S.brk, t, slot, pairs, seq, ws, W, pen, sink, ops_all, pair_status, acc, nullptr);
 #endif
@@ -2282,12 +2361,23 @@ WFB_KERNEL(wfb_endsfree_kernel, const WfbTask* tasks, const WfbEndsFree* efs, in
 /* ------------------------------------------------------------------------------------------------
  * Sequence staging: reversed copies (wavefront_sequences.c:83-101 does this per aligner on the CPU).
  * ---------------------------------------------------------------------------------------------- */
-WFB_KERNEL(wfb_reverse_kernel, const WfbPairDesc* pairs, int npairs, uint8_t* seq) {
+/* pair_flags (optional): set to 1 for pairs holding a byte other than A, C, G, T (they cannot use the 2-bit shared-memory windows) */
+WFB_KERNEL(wfb_reverse_kernel, const WfbPairDesc* pairs, int npairs, uint8_t* seq, int* pair_flags) {
   WFB_KERNEL_PROLOGUE
   for (int i = bid; i < npairs; i += nblocks) {
     const WfbPairDesc pd = pairs[i];
-    for (int j = WFB_TID; j < pd.plen; j += WFB_NT) seq[pd.prev_off + j] = seq[pd.p_off + pd.plen - 1 - j];
-    for (int j = WFB_TID; j < pd.tlen; j += WFB_NT) seq[pd.trev_off + j] = seq[pd.t_off + pd.tlen - 1 - j];
+    bool other = false;
+    for (int j = WFB_TID; j < pd.plen; j += WFB_NT) {
+      const uint8_t c = seq[pd.p_off + pd.plen - 1 - j];
+      seq[pd.prev_off + j] = c;
+      other |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+    }
+    for (int j = WFB_TID; j < pd.tlen; j += WFB_NT) {
+      const uint8_t c = seq[pd.t_off + pd.tlen - 1 - j];
+      seq[pd.trev_off + j] = c;
+      other |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+    }
+    if (pair_flags && other) pair_flags[i] = 1; /* benign race: every writer stores 1 */
   }
 }
 

@@ -88,6 +88,10 @@ typedef struct {
   double break_kernel_ms; /* ... of the breakpoint (bidirectional wavefront) kernel launches only */
   double patch_kernel_ms; /* wfb_biwfa_paf_batch only: CUDA-event time of the head / tail patch kernel rounds */
   uint64_t h2d_bytes, d2h_bytes; /* bytes the call copied to / from the device                   */
+  uint64_t patch_cap_kept_main;  /* wfb_biwfa_paf_batch only: head / tail patches whose ends-free alignment hit a device capacity; those ends
+                                    keep the main CIGAR, as the reference does when a patch aligner fails (wflign.cpp:299,385) */
+  uint64_t main_device_cap;      /* wfb_biwfa_paf_batch only: records whose MAIN alignment hit a device capacity (task queue, base-case score
+                                    cap) — no reference counterpart; they are reported WFB_REC_UNALIGNED and counted here */
 } wfb_align_stats_t;
 
 typedef struct wfb_aligner wfb_aligner_t;
@@ -189,7 +193,8 @@ typedef struct {
 #define WFB_REC_WRITTEN 0       /* a PAF line was produced                                                    */
 #define WFB_REC_FILTERED 1      /* aligned but rejected by the identity / length filters (nothing written)     */
 #define WFB_REC_UNALIGNED 2     /* main alignment status != 0: the reference returns early (wflign.cpp:150-152) */
-#define WFB_REC_PATCH_CAP (-1)  /* a patch alignment exceeded the ends-free kernel's score/arena caps; no line */
+#define WFB_REC_PATCH_CAP (-1)  /* (no longer produced: a patch that exceeds the ends-free kernel's caps keeps the main CIGAR and is
+                                   counted in wfb_align_stats_t.patch_cap_kept_main) */
 
 /* out receives the PAF lines ('\n'-terminated) of records 0..n-1 back to back; line_offset[n+1] delimits them
  * (empty for records that produce no line); rec_status[n] = WFB_REC_*. WFB_ECAP if out_cap is too small
@@ -655,6 +660,7 @@ typedef struct {
   int64_t batches;                         /* GPU batches (= launches of wfb_persist_kernel)                             */
   uint64_t cells, base_cells, extend_matches, base_extend_matches, overlap_tests, score_steps, base_score_steps; /* wfb_align_stats_t, summed */
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t patch_cap_kept_main, main_device_cap; /* wfb_align_stats_t, summed: output that can differ from the reference's is never silent */
 } wfb_align_phase_stats_t;
 
 /* Alignment phase over mapping PAF text: parseMashmapRow + padding, slices fetched with faidx's clamping, upper-casing /

@@ -49,3 +49,24 @@ def test_c3_all_eight_yeast_genomes_paf_is_byte_identical_to_the_reference(wb):
     # the bench workload: 136 sequences, 96 Mbp, 21 129 mapping records, 659 Mbp aligned
     r = configrun.run(wb, "C3")
     _check(r, "C3")
+
+
+def test_capacity_fallbacks_and_scheduling_variants_do_not_change_the_text(wb, monkeypatch):
+    """The paths that only run when a capacity is exceeded, forced through their test hooks on C3sub (two yeast genomes), and the
+    switches that only reorder work must leave every output byte where it was:
+      * the library's L1 loci buffer starting at 64 entries (grown from the kernel's own count, index_host.cu);
+      * per-fragment L1 scratch of 8192 gathered points / 4 candidate regions (the flagged fragments are re-run alone with larger scratch);
+      * head and tail patches in the reference's two rounds instead of one fused round (epilogue.cu patch_records);
+      * no packed sequences in shared memory (wfa_kernels.h wfb_pack_seq)."""
+    base = configrun.run(wb, "C3sub")
+    _check(base, "C3sub")
+    assert base["align_stats"].patch_cap_kept_main == 0 and base["align_stats"].main_device_cap == 0
+    for env in ({"WFB_L1_LOCI_CAP0": "64"}, {"WFB_L1_FRAG_CAPS": "8192,4"}, {"WFB_PATCH_FUSE": "0"}, {"WFB_SEQ_SMEM_KB": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = configrun.run(wb, "C3sub", align=not any(k.startswith("WFB_L1") for k in env))
+        for k in env:
+            monkeypatch.delenv(k)
+        assert r["mapping_paf"] == base["mapping_paf"], env
+        if "alignment_paf" in r:
+            assert r["alignment_paf"] == base["alignment_paf"], env

@@ -1,6 +1,7 @@
 """GPU parity tests (-m gpu): every call goes through the C ABI of libwfmash_b200.so (ctypes) and is
 compared bit-exactly with the committed golden fixtures and with the oracle on the same seeded inputs."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -96,6 +97,52 @@ def test_biwfa_full_size_records(wb, oracle):
     assert [r.ops for r in res] == [r.ops for r in res2]
     st = al.last_stats
     assert st.cells > 0 and st.break_tasks >= len(pairs) and st.kernel_ms > 0
+
+
+def test_biwfa_high_divergence_full_length_records_match_reference_digests(wb):
+    """BASELINE's C5 regime: 50 kb records at 10 % and 20 % divergence and padded 20-30 kb records at 15 % (scores 3-6 x 10^4,
+    wavefronts of tens of thousands of diagonals, team mode, every fallback size) against digests of the UNMODIFIED reference's
+    operation strings (tests/golden/make_highdiv_golden.py ran oracle/_ref/libwfa2ref.so in the build container). None of the
+    device capacities (task queue, base-case score cap) may fire."""
+    import gzip, hashlib, json
+    from wfmash_b200 import synth
+    gold = json.loads(gzip.open(os.path.join(util.ROOT, "tests", "golden", "highdiv_reference.json.gz")).read())
+    al = wb.Aligner(0)
+    for s in gold:
+        recs = synth.mapping_records(**s["params"])
+        res = al.align_end2end_batch([(p, t) for p, t, _ in recs])
+        for (p, t, _), r, g in zip(recs, res, s["records"]):
+            assert (len(p), len(t)) == (g["plen"], g["tlen"])
+            assert r.status == 0
+            assert r.score == g["score"] and len(r.ops) == g["ops_len"]
+            assert hashlib.sha256(r.ops).hexdigest() == g["sha"]
+    al.close()
+
+
+def test_biwfa_work_counts_equal_the_reference_algorithms(wb, oracle):
+    """The roofline's numerator: the cells (C), extended matches (E) and score steps the kernels count must be the ones the
+    reference's algorithm performs (wavefront_compute_affine2p.c:355-361, wavefront_extend_kernels.c:68-92,
+    wavefront_bialign.c:1010-1079), counted by the oracle's instrumented restatement on the same records — over-computing would
+    inflate roofline.frac. Overlap tests (O) are the exception by design: block maxima of the rows let the scan skip diagonal
+    blocks that cannot hold a breakpoint, so the device examines FEWER diagonals than wavefront_bialign_overlap (:877-955) does."""
+    from wfmash_b200 import synth
+    recs = synth.mapping_records(12, seed=77, len_lo=2000, len_hi=16000, divergences=[0.01, 0.03, 0.08, 0.15], pad=0)
+    recs += synth.mapping_records(4, seed=78, len_lo=3000, len_hi=6000, divergences=[0.05], pad=1000)
+    pairs = [(p, t) for p, t, _ in recs]
+    al = wb.Aligner(0)
+    res = al.align_end2end_batch(pairs)
+    st = al.last_stats
+    al.close()
+    C = util.Counters()
+    for (p, t), r in zip(pairs, res):
+        s_, ops, score = util.orc_biwfa(oracle, p, t, util.WFMASH_PEN, C)
+        assert s_ == 0 and ops == r.ops
+    assert st.cells + st.base_cells == C.cells, (st.cells, st.base_cells, C.cells)
+    # (a speculative reverse step that a TEAM ran and phase 1 then dropped keeps its matches counted: never fewer, at most a trace more)
+    E = st.extend_matches + st.base_extend_matches
+    assert C.extend_matches <= E <= C.extend_matches + C.extend_matches // 50, (st.extend_matches, st.base_extend_matches, C.extend_matches)
+    assert st.score_steps + st.base_score_steps == C.score_steps, (st.score_steps, st.base_score_steps, C.score_steps)
+    assert 0 < st.overlap_tests <= C.overlap_tests, (st.overlap_tests, C.overlap_tests)
 
 
 def test_biwfa_device_resident_entry_point_matches_host_entry_point(wb):

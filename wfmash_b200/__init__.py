@@ -65,7 +65,8 @@ class AlignStats(ctypes.Structure):
                 ("score_steps", ctypes.c_uint64), ("break_tasks", ctypes.c_uint64), ("base_tasks", ctypes.c_uint64),
                 ("base_cells", ctypes.c_uint64), ("base_extend_matches", ctypes.c_uint64), ("base_score_steps", ctypes.c_uint64),
                 ("levels", ctypes.c_uint64), ("kernel_ms", ctypes.c_double), ("break_kernel_ms", ctypes.c_double), ("patch_kernel_ms", ctypes.c_double),
-                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64), ("patch_cap_kept_main", ctypes.c_uint64),
+                ("main_device_cap", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -783,7 +784,8 @@ class AlignPhaseStats(ctypes.Structure):
     _fields_ = [("records", ctypes.c_int64), ("written", ctypes.c_int64), ("skipped_lines", ctypes.c_int64), ("aligned_bp", ctypes.c_uint64),
                 ("kernel_ms", ctypes.c_double), ("total_seconds", ctypes.c_double), ("persist_kernel_ms", ctypes.c_double), ("patch_kernel_ms", ctypes.c_double),
                 ("batches", ctypes.c_int64)] + [(n, ctypes.c_uint64) for n in ("cells", "base_cells", "extend_matches", "base_extend_matches", "overlap_tests",
-                                                                                "score_steps", "base_score_steps", "h2d_bytes", "d2h_bytes")]
+                                                                                "score_steps", "base_score_steps", "h2d_bytes", "d2h_bytes", "patch_cap_kept_main",
+                                                                                "main_device_cap")]
 
 
 def _seq_array(seqs):

@@ -397,17 +397,19 @@ void for_each_record(int64_t n, int64_t work_bytes, F f) {
   for (auto& t : th) t.join();
 }
 
-/* Runs one round of ends-free patches and splices the results into cig[]. head: the patch replaces runs [0,cut);
- * otherwise runs [cut,size). */
-int patch_round(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& cig, std::vector<int32_t>& status, bool head, int term_group) {
-  std::vector<Patch> all;
-  for (size_t i = 0; i < cig.size(); ++i) {
-    if (status[i] != WFB_REC_WRITTEN) continue;
-    Patch p;
-    p.rec = (int)i;
-    p.er = head ? erode_head(cig[i]) : erode_tail(cig[i]); /* O(runs of the eroded end): not worth a thread */
-    if (p.er.q > 3 || p.er.t > 3) all.push_back(p);
-  }
+/* One ends-free patch request: record, which end, and the erosion (wflign.cpp:241-276 head, :311-350 tail) computed on the record's
+ * main CIGAR. */
+struct PatchReq {
+  int rec;
+  bool head;
+  Erosion er;
+};
+
+/* Runs one batch of ends-free patch alignments and splices the results into cig[]: a head patch replaces runs [0,cut), a tail patch
+ * runs [cut,size). Requests are spliced in the order given; a record with both a head and a tail request in the same batch must list
+ * the tail first (the head splice changes the run indices). A patch whose alignment hit a device capacity keeps the main CIGAR, as
+ * the reference does when a patch aligner fails (wflign.cpp:299, :385: `if (head_status == 0)` / `if (tail_status == 0)`), and is counted. */
+int patch_batch(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& cig, const std::vector<PatchReq>& all, int term_group, int64_t* failed) {
   if (all.empty()) return WFB_OK;
   /* the reference aligner answers a zero-length side with a pure gap (verified against the compiled reference);
    * those need no kernel */
@@ -419,7 +421,7 @@ int patch_round(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& 
     const Erosion& e = all[j].er;
     if (e.q == 0 || e.t == 0) continue;
     wfb_endsfree_pair_t p;
-    if (head) { /* wflign.cpp:286-297: alignEndsFree(head_target, target_eroded, 0, head_query, query_eroded, 0) */
+    if (all[j].head) { /* wflign.cpp:286-297: alignEndsFree(head_target, target_eroded, 0, head_query, query_eroded, 0) */
       p.pattern = r.target; p.text = r.query;
       p.pattern_begin_free = (int32_t)e.t; p.pattern_end_free = 0; p.text_begin_free = (int32_t)e.q; p.text_end_free = 0;
     } else {    /* wflign.cpp:368-389: alignEndsFree(tail_target, 0, tail_target_length, tail_query, 0, tail_query_length) */
@@ -440,12 +442,13 @@ int patch_round(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& 
   for (size_t j = 0; j < all.size(); ++j) {
     const int i = all[j].rec;
     const Erosion& e = all[j].er;
+    const bool head = all[j].head;
     Cigar pc;
     if (slot[j] < 0) {
       pc.push_back({(int32_t)(e.q == 0 ? e.t : e.q), e.q == 0 ? 'D' : 'I'});
     } else {
       const wfb_aln_result_t& rr = res[(size_t)slot[j]];
-      if (rr.status != 0) { status[i] = WFB_REC_PATCH_CAP; continue; }
+      if (rr.status != 0) { if (failed) ++*failed; continue; }
       pc = rle(ops.data() + rr.ops_offset, rr.ops_len);
     }
     erode_short_matches(pc, 3, head);
@@ -458,6 +461,43 @@ int patch_round(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& 
     }
   }
   return WFB_OK;
+}
+
+/* Head and tail patches of a batch of records (wflign.cpp:241-405). The reference patches the head, then erodes the tail of the
+ * head-patched CIGAR. The tail erosion examines runs [cut_tail - 1, size) only; when all of them lie behind the run that follows the
+ * head's replaced prefix (the one run the head splice can change, by fusing with the patch's last run), it sees the same runs before
+ * and after the head patch, so both patches are aligned in ONE device round and spliced tail-first. The remaining records (short
+ * CIGARs whose two ends meet) take the reference's order in a second round. */
+int patch_records(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& cig, const std::vector<int32_t>& status, int term_group, int64_t* failed) {
+  std::vector<PatchReq> round1, round2;
+  std::vector<int> dependent;
+  const bool fuse = !(getenv("WFB_PATCH_FUSE") && atoi(getenv("WFB_PATCH_FUSE")) == 0);
+  for (size_t i = 0; i < cig.size(); ++i) {
+    if (status[i] != WFB_REC_WRITTEN) continue;
+    const Erosion eh = erode_head(cig[i]); /* O(runs of the eroded end): not worth a thread */
+    const bool need_head = eh.q > 3 || eh.t > 3;
+    if (!need_head) { /* the CIGAR the tail erosion sees is the main one */
+      const Erosion et = erode_tail(cig[i]);
+      if (et.q > 3 || et.t > 3) round1.push_back({(int)i, false, et});
+      continue;
+    }
+    const Erosion et = erode_tail(cig[i]);
+    const bool independent = fuse && et.cut >= 1 && et.cut - 1 > eh.cut;
+    if (independent) {
+      if (et.q > 3 || et.t > 3) round1.push_back({(int)i, false, et});
+      round1.push_back({(int)i, true, eh});
+    } else {
+      round1.push_back({(int)i, true, eh});
+      dependent.push_back((int)i);
+    }
+  }
+  int rc = patch_batch(a, recs, cig, round1, term_group, failed);
+  if (rc != WFB_OK) return rc;
+  for (int i : dependent) {
+    const Erosion et = erode_tail(cig[(size_t)i]);
+    if (et.q > 3 || et.t > 3) round2.push_back({i, false, et});
+  }
+  return patch_batch(a, recs, cig, round2, term_group, failed);
 }
 
 } // namespace
@@ -498,21 +538,26 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
   wfb_trace_mark_("paf_batch: main alignments (wfb_align_batch_hinted)");
   std::vector<Cigar> cig((size_t)n);
   std::vector<int32_t> status((size_t)n, WFB_REC_WRITTEN);
+  std::atomic<uint64_t> main_cap(0);
   for_each_record(n, cap, [&](int64_t i) {
-    if (res[(size_t)i].status != 0) { status[(size_t)i] = WFB_REC_UNALIGNED; return; } /* wflign.cpp:150-152 */
+    if (res[(size_t)i].status != 0) { /* wflign.cpp:150-152 */
+      status[(size_t)i] = WFB_REC_UNALIGNED;
+      if (res[(size_t)i].status != -3 /* WFB_PAIR_UNATTAINABLE: the reference's own failure */) main_cap.fetch_add(1);
+      return;
+    }
     cig[(size_t)i] = rle(ops + res[(size_t)i].ops_offset, res[(size_t)i].ops_len);
   });
   ops_buf.reset();
   wfb_trace_mark_("paf_batch: run-length conversion");
+  if (stats) stats->main_device_cap = main_cap.load();
   if (!params->disable_chain_patching) {
     double ms = 0; uint64_t h2d = 0, d2h = 0;
     wfb_take_endsfree_counters_(a, &ms, &h2d, &d2h);
-    rc = patch_round(a, recs, cig, status, true, term_group);
+    int64_t patch_failed = 0;
+    rc = patch_records(a, recs, cig, status, term_group, &patch_failed);
     if (rc != WFB_OK) return rc;
-    wfb_trace_mark_("paf_batch: head patches");
-    rc = patch_round(a, recs, cig, status, false, term_group);
-    if (rc != WFB_OK) return rc;
-    wfb_trace_mark_("paf_batch: tail patches");
+    wfb_trace_mark_("paf_batch: head + tail patches");
+    if (stats) stats->patch_cap_kept_main = (uint64_t)patch_failed;
     wfb_take_endsfree_counters_(a, &ms, &h2d, &d2h);
     if (stats) { stats->patch_kernel_ms = ms; stats->h2d_bytes += h2d; stats->d2h_bytes += d2h; }
   }

@@ -11,6 +11,8 @@
 #include <atomic>
 #include <chrono>
 #include <map>
+#include <memory>
+#include <new>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -436,7 +438,8 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
   wfb_align_stats_t sum; memset(&sum, 0, sizeof sum);
   int64_t n_batches = 0;
   std::vector<wfb_record_t> arr;
-  std::vector<char> buf;
+  std::unique_ptr<char[]> buf; /* not a vector: resize() would zero-fill hundreds of MB on one thread */
+  size_t buf_cap = 0;
   for (size_t b0 = 0; b0 < recs.size(); b0 += (size_t)batch) {
     const size_t b1 = std::min(recs.size(), b0 + (size_t)batch);
     arr.assign(b1 - b0, wfb_record_t());
@@ -455,11 +458,13 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     std::vector<int64_t> off(b1 - b0 + 1); std::vector<int32_t> st(b1 - b0);
     int64_t len = 0;
     wfb_align_stats_t as; memset(&as, 0, sizeof as);
-    buf.resize(bytes);
-    int rc = wfb_biwfa_paf_batch(aligner, arr.data(), (int32_t)(b1 - b0), &params->output, buf.data(), (int64_t)buf.size(), &len, off.data(), st.data(), &as);
-    if (rc == WFB_ECAP && len > (int64_t)buf.size()) {
-      buf.resize((size_t)len + 64);
-      rc = wfb_biwfa_paf_batch(aligner, arr.data(), (int32_t)(b1 - b0), &params->output, buf.data(), (int64_t)buf.size(), &len, off.data(), st.data(), &as);
+    if (bytes > buf_cap) { buf.reset(new (std::nothrow) char[bytes]); buf_cap = buf ? bytes : 0; }
+    if (!buf) { wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
+    int rc = wfb_biwfa_paf_batch(aligner, arr.data(), (int32_t)(b1 - b0), &params->output, buf.get(), (int64_t)buf_cap, &len, off.data(), st.data(), &as);
+    if (rc == WFB_ECAP && len > (int64_t)buf_cap) {
+      buf.reset(new (std::nothrow) char[(size_t)len + 64]); buf_cap = buf ? (size_t)len + 64 : 0;
+      if (!buf) { wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
+      rc = wfb_biwfa_paf_batch(aligner, arr.data(), (int32_t)(b1 - b0), &params->output, buf.get(), (int64_t)buf_cap, &len, off.data(), st.data(), &as);
     }
     if (rc != WFB_OK) return rc;
     wfb_trace_mark_("align_phase: batch aligned");
@@ -469,8 +474,8 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     for (size_t i = b0; i < b1; ++i) {
       std::string& text = line[order[i]];
       for (int64_t a = off[i - b0]; a < off[i - b0 + 1];) {
-        const char* nl = (const char*)memchr(buf.data() + a, '\n', (size_t)(off[i - b0 + 1] - a));
-        const int64_t b = nl ? (int64_t)(nl - buf.data()) : off[i - b0 + 1];
+        const char* nl = (const char*)memchr(buf.get() + a, '\n', (size_t)(off[i - b0 + 1] - a));
+        const int64_t b = nl ? (int64_t)(nl - buf.get()) : off[i - b0 + 1];
         if (b > a) {
           std::vector<std::pair<int64_t, int64_t>> fields;
           bool has_cigar = false;
@@ -480,16 +485,16 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
             const int64_t f0 = p;
             while (p < b && !isspace((unsigned char)buf[(size_t)p])) ++p;
             fields.emplace_back(f0, p);
-            if (p - f0 >= 5 && memcmp(buf.data() + f0, "cg:Z:", 5) == 0) has_cigar = true;
+            if (p - f0 >= 5 && memcmp(buf.get() + f0, "cg:Z:", 5) == 0) has_cigar = true;
           }
           if (has_cigar) {
             for (size_t f = 0; f < fields.size(); ++f) {
               if (f) text.push_back('\t');
-              text.append(buf.data() + fields[f].first, (size_t)(fields[f].second - fields[f].first));
+              text.append(buf.get() + fields[f].first, (size_t)(fields[f].second - fields[f].first));
             }
             text.push_back('\n');
           } else {
-            text.append(buf.data() + a, (size_t)(b - a));
+            text.append(buf.get() + a, (size_t)(b - a));
             text.push_back('\n');
           }
         }
@@ -501,6 +506,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     sum.break_kernel_ms += as.break_kernel_ms; sum.patch_kernel_ms += as.patch_kernel_ms; sum.cells += as.cells; sum.base_cells += as.base_cells;
     sum.extend_matches += as.extend_matches; sum.base_extend_matches += as.base_extend_matches; sum.overlap_tests += as.overlap_tests;
     sum.score_steps += as.score_steps; sum.base_score_steps += as.base_score_steps; sum.h2d_bytes += as.h2d_bytes; sum.d2h_bytes += as.d2h_bytes;
+    sum.patch_cap_kept_main += as.patch_cap_kept_main; sum.main_device_cap += as.main_device_cap;
     ++n_batches;
   }
   wfb_trace_mark_("align_phase: lines re-emitted");
@@ -522,6 +528,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     stats->base_cells = sum.base_cells; stats->extend_matches = sum.extend_matches; stats->base_extend_matches = sum.base_extend_matches;
     stats->overlap_tests = sum.overlap_tests; stats->score_steps = sum.score_steps; stats->base_score_steps = sum.base_score_steps;
     stats->h2d_bytes = sum.h2d_bytes; stats->d2h_bytes = sum.d2h_bytes;
+    stats->patch_cap_kept_main = sum.patch_cap_kept_main; stats->main_device_cap = sum.main_device_cap;
     stats->total_seconds = now_s() - t_begin;
   }
   return WFB_OK;

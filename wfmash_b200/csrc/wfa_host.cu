@@ -397,7 +397,7 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     });
   /* ---- workspaces ---- */
   const int W = (int)align_up(maxP + maxT + 8, 8);
-  const long long ws_stride = 2LL * pen.R * 5 * W + 2LL * pen.R * 5 * ((W + 63) / 64) + 64; /* rows + their block maxima (wfb_overlap) */
+  const long long ws_stride = align_up(2LL * pen.R * 5 * W + 2LL * pen.R * 5 * ((W + 63) / 64) + 64, 8); /* rows + their block maxima (wfb_overlap); every CTA's rows 16-byte aligned */
   const int score_cap = std::max(WFB_RECOVERY_MIN_SCORE, pen.x * WFB_FALLBACK_MIN_LENGTH) + 12;
   const long long arena_stride = 5LL * (score_cap + 2) * (score_cap + 2) + 64;
   const int maxruns = 2 * score_cap + 16;
@@ -443,15 +443,25 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     int seq_smem_words = 0; /* 2-bit packed sequence windows of the running task (wfa_kernels.h): enough for 2 x (52 kb + 52 kb) by default */
 #ifndef WFB_EMU
     {
-      const int kb = getenv("WFB_SEQ_SMEM_KB") ? atoi(getenv("WFB_SEQ_SMEM_KB")) : 56;
-      seq_smem_words = kb > 0 ? kb * 256 : 0;
-      if (seq_smem_words > 0 &&
-          cudaFuncSetAttribute(wfb_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_words * 4) != cudaSuccess) {
-        cudaGetLastError();
-        seq_smem_words = 0;
+      /* packed sequences: 52 KB hold 2 x (52 kb + 52 kb); the size must leave 2 CTAs per SM, and what the CTAs do not take stays L1
+       * (the rows are read through it: 98 KB here cost 11 % of the kernel time on scerevisiae8, profiles/r02_row_staging_experiment.md) */
+      const int want = getenv("WFB_SEQ_SMEM_KB") ? atoi(getenv("WFB_SEQ_SMEM_KB")) : 56;
+      const int tries[3] = {want, std::min(want, 56), 0};
+      int nb0 = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, wfb_persist_kernel, kBreakThreads, 0) != cudaSuccess || nb0 <= 0) { cudaGetLastError(); nb0 = 0; }
+      for (int ti = 0; ti < 3; ++ti) {
+        const int kb = tries[ti];
+        seq_smem_words = kb > 0 ? kb * 256 : 0;
+        if (seq_smem_words > 0 &&
+            cudaFuncSetAttribute(wfb_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_words * 4) != cudaSuccess) {
+          cudaGetLastError();
+          continue;
+        }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfb_persist_kernel, kBreakThreads, (size_t)seq_smem_words * 4) != cudaSuccess) { cudaGetLastError(); nb = 0; }
+        if (nb > 0 && (nb >= nb0 || kb == 0)) { ctas = a->sm_count * nb; break; } /* never trade resident CTAs for shared memory */
       }
-      int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfb_persist_kernel, kBreakThreads, (size_t)seq_smem_words * 4) == cudaSuccess && nb > 0) ctas = a->sm_count * nb;
+      if (getenv("WFB_TRACE")) fprintf(stderr, "[wfb] persist: dynamic shared memory %d KB, %d CTAs (%d per SM without it)\n", seq_smem_words / 256, ctas, nb0);
     }
 #endif
     const size_t per_cta = (size_t)ws_stride * 4 + base_cta_bytes;
@@ -815,7 +825,10 @@ extern "C" int wfb_align_endsfree_batch(wfb_aligner_t* a, const wfb_endsfree_pai
     const int maxruns = 2 * score_cap + 16;
     const int runflag_stride = (int)align_up(maxPT + 16, 16);
     const size_t per_cta = (size_t)arena_stride * 4 + (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta) + (size_t)maxruns * sizeof(WfbRun) + (size_t)runflag_stride;
-    int ctas = (int)std::min<size_t>(todo.size(), (size_t)a->sm_count * (pass == 0 ? 4 : 1));
+    /* later passes hold the few patches of score > 1024: as many CTAs as the workspace allows (two per SM), largest patch first */
+    int ctas = (int)std::min<size_t>(todo.size(), (size_t)a->sm_count * (pass == 0 ? 4 : pass == 1 ? 2 : 1));
+    if (pass > 0)
+      std::stable_sort(todo.begin(), todo.end(), [&](int x, int y) { return (long long)pd[x].plen + pd[x].tlen > (long long)pd[y].plen + pd[y].tlen; });
     ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctas, (size_t)(a->workspace_bytes / per_cta)));
     if (a->d_arena.ensure((size_t)ctas * (size_t)arena_stride * 4) || a->d_log.ensure((size_t)ctas * (size_t)(score_cap + 1) * 5 * sizeof(WfbBaseMeta)) ||
         a->d_runs.ensure((size_t)ctas * (size_t)maxruns * sizeof(WfbRun)) || a->d_ws.ensure((size_t)ctas * (size_t)runflag_stride)) {

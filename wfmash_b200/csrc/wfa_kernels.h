@@ -259,6 +259,23 @@ WFB_DEV void wfb_prefetch_l2(const void* p) {
 #endif
 }
 
+/* The 128-bit row loads of a 4-diagonal group fetch one lane no cell reads (I1 / I2: the diagonal k0 + 3, D1 / D2: k0). ptxas hands the
+ * registers of those dead lanes to the scalar halo loads that follow in the same load block, and a load whose destination register is still
+ * owed by an earlier load has to wait for it (write-after-write on the scoreboard): the thirteen loads of a group, meant to be in flight
+ * together, became two memory round trips — one scalar LDG held 9 % of the kernel's stall samples on scerevisiae8
+ * (profiles/r02_persist_c3s8_summary.txt). A real use of the four dead lanes after the block keeps their registers allocated until
+ * every load has been issued. Offsets and nulls only have bits 0-19 and 30-31 set, so the test is never true; if it were, TAK (an upper
+ * bound used to prune the overlap scan) would only grow, which is safe. */
+#ifndef WFB_EMU
+#define WFB_KEEP_DEAD_LANES(VI1, VI2, VD1, VD2, TAK)                                  \
+  {                                                                                   \
+    const int dead__ = ((VI1).w ^ (VI2).w) | ((VD1).x ^ (VD2).x);                     \
+    if (dead__ == 0x5a5a5a5b) (TAK) = max((TAK), dead__);                             \
+  }
+#else
+#define WFB_KEEP_DEAD_LANES(VI1, VI2, VD1, VD2, TAK)
+#endif
+
 WFB_DEV bool wfb_inbounds(int32_t off, int k, int plen, int tlen) {
   return (uint32_t)off <= (uint32_t)tlen && (uint32_t)(off - k) <= (uint32_t)plen;
 }
@@ -509,6 +526,7 @@ WFB_STEP_INLINE void wfb_step_work(WfbRing& ring, int32_t* basep, const WfbPen& 
           sd2 = wfb_get(basep, d2_ext, k0 + 4);
           vmm = make_int4(wfb_get(basep, m_misms, k0), wfb_get(basep, m_misms, k0 + 1), wfb_get(basep, m_misms, k0 + 2), wfb_get(basep, m_misms, k0 + 3));
         }
+        WFB_KEEP_DEAD_LANES(vi1, vi2, vd1, vd2, tak)
         WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
         WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
         WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])
@@ -1146,6 +1164,7 @@ WFB_DEV void wfb_team_chunk(const WfbStepDesc& D, int32_t* basep, int chunk, int
       sd2 = wfb_get(basep, d2_ext, k0 + 4);
       vmm = make_int4(wfb_get(basep, m_misms, k0), wfb_get(basep, m_misms, k0 + 1), wfb_get(basep, m_misms, k0 + 2), wfb_get(basep, m_misms, k0 + 3));
     }
+    WFB_KEEP_DEAD_LANES(vi1, vi2, vd1, vd2, tak)
     WFB_CELL(k0 + 0, so1m,  vo1.y, so2m,  vo2.y, si1,   si2,   vd1.y, vd2.y, vmm.x, rm[0], ri1[0], ri2[0], rd1[0], rd2[0])
     WFB_CELL(k0 + 1, vo1.x, vo1.z, vo2.x, vo2.z, vi1.x, vi2.x, vd1.z, vd2.z, vmm.y, rm[1], ri1[1], ri2[1], rd1[1], rd2[1])
     WFB_CELL(k0 + 2, vo1.y, vo1.w, vo2.y, vo2.w, vi1.y, vi2.y, vd1.w, vd2.w, vmm.z, rm[2], ri1[2], ri2[2], rd1[2], rd2[2])

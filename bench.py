@@ -438,6 +438,7 @@ def main():
                   "mapping_lines_identical": sha_sorted(last["mapping_paf"]) == gold["mapping_sha_sorted"],
                   "paf_lines_identical": sha_sorted(last["paf"]) == gold["alignment_sha_sorted"],
                   "aligned_bp_equals_reference_counter": int(aligned_bp) == gold["aligned_bp"], "stale_absorbed": int(mst.stale_absorbed),
+                  "patch_cap_kept_main": int(ast.patch_cap_kept_main), "main_device_cap": int(ast.main_device_cap),
                   "against": "tests/golden/config_reference.json.gz: the unmodified reference's two phases on the same file (sorted lines, sha256)"}
         mean = lambda k: statistics.mean(s.get(k, 0.0) for s in steps)
         line = {

@@ -250,7 +250,12 @@ class Aligner:
                              r.get("chain_length", 0), r.get("chain_pos", 0), r.get("mashmap_estimated_identity", 0.0), 0)
         pp = _PafParams(1 if disable_chain_patching else 0, term_group, min_identity, min_block_identity, min_alignment_length,
                         int(sam_format), int(emit_md_tag), int(no_seq_in_sam), 0)
-        cap = sum(len(k[0]) + len(k[1]) for k in keep) // 2 + 512 * n + 4096
+        # PAF: the CIGAR is a fraction of the sequences; SAM carries SEQ (the query) + CIGAR (+ MD): size the first buffer for it, so the
+        # WFB_ECAP retry (which repeats the alignment) stays the exception
+        if sam_format:
+            cap = sum((0 if no_seq_in_sam else len(k[0])) + (len(k[0]) + len(k[1])) // 2 + (len(k[1]) // 2 if emit_md_tag else 0) for k in keep) + 1024 * n + 4096
+        else:
+            cap = sum(len(k[0]) + len(k[1]) for k in keep) // 2 + 512 * n + 4096
         offs = (ctypes.c_int64 * (n + 1))()
         st = (ctypes.c_int32 * n)()
         stats = AlignStats()

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -96,13 +97,34 @@ extern "C" void wfb_index_file_release(wfb_index_file_header_t* h, wfb_index_vie
   if (ix) { free(ix->minmers); free(ix->uhash); free(ix->ustart); free(ix->ucount); free(ix->points); memset(ix, 0, sizeof *ix); }
 }
 
+static int index_file_read_impl(const char* path, int64_t* offset, wfb_index_file_header_t* h, wfb_index_view_t* ix);
+
+/* Sizes in the file are not trusted: every count is checked against the bytes the file still holds before anything is allocated, and
+ * an allocation failure returns WFB_ENOMEM instead of unwinding through the C boundary. */
 extern "C" int wfb_index_file_read(const char* path, int64_t* offset, wfb_index_file_header_t* h, wfb_index_view_t* ix) {
+  try {
+    return index_file_read_impl(path, offset, h, ix);
+  } catch (const std::bad_alloc&) {
+    if (h && ix) wfb_index_file_release(h, ix);
+    wfb_set_last_error_("out of host memory while reading the index file");
+    return WFB_ENOMEM;
+  } catch (...) {
+    if (h && ix) wfb_index_file_release(h, ix);
+    wfb_set_last_error_("unexpected failure while reading the index file");
+    return WFB_EINVAL;
+  }
+}
+
+static int index_file_read_impl(const char* path, int64_t* offset, wfb_index_file_header_t* h, wfb_index_view_t* ix) {
   if (!path || !offset || !h || !ix || *offset < 0) { wfb_set_last_error_("bad argument"); return WFB_EINVAL; }
   memset(h, 0, sizeof *h);
   memset(ix, 0, sizeof *ix);
   FILE* f = fopen(path, "rb");
   if (!f) { wfb_set_last_error_(std::string("cannot open index file: ") + path); return WFB_EINVAL; }
   auto fail = [&](const char* why) { fclose(f); wfb_index_file_release(h, ix); wfb_set_last_error_(std::string(why) + ": " + path); return WFB_EINVAL; };
+  if (fseek(f, 0, SEEK_END) != 0) return fail("cannot seek in index file");
+  const uint64_t file_bytes = (uint64_t)ftell(f);
+  auto left = [&]() -> uint64_t { const long at = ftell(f); return at < 0 || (uint64_t)at > file_bytes ? 0 : file_bytes - (uint64_t)at; };
   if (fseek(f, (long)*offset, SEEK_SET) != 0) return fail("cannot seek in index file");
   uint64_t magic = 0, nt = 0, nm = 0;
   if (!get(f, &magic, 8) || magic != IXF_MAGIC) return fail("invalid magic number in index file"); /* readSubIndexHeader, :869-890 */
@@ -119,9 +141,11 @@ extern "C" int wfb_index_file_read(const char* path, int64_t* offset, wfb_index_
   }
   h->n_targets = (int32_t)nt;
   h->target_names = strdup(names.c_str());
+  if (!h->target_names) { fclose(f); wfb_index_file_release(h, ix); wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
   if (!get(f, &nm, 8) || nm > 1000000) return fail("invalid mapping size in index file"); /* importIdMapping, sequenceIds.hpp:140-146 */
   names.clear();
   h->id_values = (int32_t*)malloc(4 * (size_t)(nm ? nm : 1));
+  if (!h->id_values) { fclose(f); wfb_index_file_release(h, ix); wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
   for (uint64_t i = 0; i < nm; ++i) {
     uint64_t l = 0;
     if (!get(f, &l, 8) || l > 10000) return fail("invalid sequence name length in index file");
@@ -131,26 +155,32 @@ extern "C" int wfb_index_file_read(const char* path, int64_t* offset, wfb_index_
   }
   h->n_ids = (int32_t)nm;
   h->id_names = strdup(names.c_str());
+  if (!h->id_names) { fclose(f); wfb_index_file_release(h, ix); wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
   if (!get(f, &h->next_id, 4)) return fail("truncated index file");
   if (!get(f, &h->window_length, 8) || !get(f, &h->sketch_size, 4) || !get(f, &h->kmer_size, 4)) return fail("truncated index file"); /* readParameters */
   uint64_t n = 0, nk = 0;
-  if (!get(f, &n, 8) || n > (1ull << 40)) return fail("truncated index file"); /* readSketchBinary, :682-688 */
+  if (!get(f, &n, 8) || n > left() / sizeof(wfb_minmer_t)) return fail("truncated index file"); /* readSketchBinary, :682-688 */
   ix->n_minmers = (int64_t)n;
   ix->minmers = (wfb_minmer_t*)malloc(sizeof(wfb_minmer_t) * (size_t)(n ? n : 1));
   if (!ix->minmers || !get(f, ix->minmers, sizeof(wfb_minmer_t) * (size_t)n)) return fail("truncated index file");
   for (uint64_t i = 0; i < n; ++i) ix->minmers[i].pad_ = 0; /* the reference writes its struct padding as it happens to be */
-  if (!get(f, &nk, 8) || nk > (1ull << 40)) return fail("truncated index file"); /* readPosListBinary, :693-708 */
+  if (!get(f, &nk, 8) || nk > left() / 16) return fail("truncated index file"); /* readPosListBinary, :693-708: >= 16 bytes per hash */
   /* the file lists the hashes in the writer's hash-map order: collect, then order them by hash (the export layout) */
   std::vector<uint64_t> keys((size_t)nk), cnts((size_t)nk), starts((size_t)nk);
   std::vector<uint64_t> pts;
   std::vector<RefPoint> buf;
   for (uint64_t i = 0; i < nk; ++i) {
     uint64_t cnt = 0;
-    if (!get(f, &keys[(size_t)i], 8) || !get(f, &cnt, 8) || cnt > (1ull << 32)) return fail("truncated index file");
+    if (!get(f, &keys[(size_t)i], 8) || !get(f, &cnt, 8) || cnt > left() / sizeof(RefPoint)) return fail("truncated index file");
+    /* postings offsets are 32-bit (ustart / ucount), a point packs seqId into 22 bits and pos into 40 */
+    if (pts.size() + cnt >= (1ull << 32)) return fail("too many interval points for 32-bit postings offsets in index file");
     buf.resize((size_t)cnt);
     if (!get(f, buf.data(), sizeof(RefPoint) * (size_t)cnt)) return fail("truncated index file");
     starts[(size_t)i] = pts.size(); cnts[(size_t)i] = cnt;
-    for (const RefPoint& r : buf) pts.push_back(((uint64_t)(uint32_t)r.seqId << 41) | ((uint64_t)r.pos << 1) | (r.side == 1 ? 1u : 0u));
+    for (const RefPoint& r : buf) {
+      if ((uint64_t)(uint32_t)r.seqId >= (1ull << 22) || (uint64_t)r.pos >= (1ull << 40)) return fail("sequence id / position out of range in index file");
+      pts.push_back(((uint64_t)(uint32_t)r.seqId << 41) | ((uint64_t)r.pos << 1) | (r.side == 1 ? 1u : 0u));
+    }
   }
   *offset = (int64_t)ftell(f);
   fclose(f);

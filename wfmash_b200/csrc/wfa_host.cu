@@ -848,7 +848,10 @@ extern "C" int wfb_align_endsfree_batch(wfb_aligner_t* a, const wfb_endsfree_pai
 #ifndef WFB_EMU
     WFB_CHECK(cudaEventRecord(a->ev[2], s));
 #endif
-    WFB_LAUNCH(wfb_endsfree_kernel, ctas, kBaseThreads, s, (const WfbTask*)a->d_q[0].p, (const WfbEndsFree*)a->d_srcoff.p, (int)todo.size(),
+    /* a patch starts with a wavefront as wide as its free ends (hundreds of diagonals) and gains two diagonals per score: 128 threads
+     * for the first pass, 256 for the patches of score > 1024 (the kernel's cells are one diagonal per thread per trip) */
+    const int ef_threads = getenv("WFB_EF_THREADS") ? atoi(getenv("WFB_EF_THREADS")) : (pass == 0 ? 128 : 256);
+    WFB_LAUNCH(wfb_endsfree_kernel, ctas, ef_threads, s, (const WfbTask*)a->d_q[0].p, (const WfbEndsFree*)a->d_srcoff.p, (int)todo.size(),
                d_ctrl + 0, (const WfbPairDesc*)a->d_pairs.p, (const uint8_t*)a->d_seq.p, (int32_t*)a->d_arena.p, arena_stride,
                (WfbBaseMeta*)a->d_log.p, score_cap, (WfbRun*)a->d_runs.p, maxruns, (unsigned char*)a->d_ws.p, runflag_stride, (int)term_group,
                pen, (char*)a->d_slots.p, d_status);

@@ -263,6 +263,8 @@ def records_from_paf(paf: bytes, targets, queries, params: Params = None):
             row, qn, tn = wb.mapping_paf_parse(line, P.target_padding, P.query_padding, P.window_length * 128)
         except wb.WfbError:
             continue
+        if tn not in tseq or qn not in qseq:
+            continue  # "sequence not found": the reference reports and drops the record, and so does wfb_align_phase
         # createSeqRecord fetches through faidx, which clamps a range to the sequence (src/common/faigz.h:432-438): merged
         # mappings may end beyond the query (blockLength is the larger of the two spans); an empty fetch drops the record
         t = _UPPER_VALID[np.frombuffer(tseq[tn], dtype=np.uint8)[row.r_start: row.r_end]]

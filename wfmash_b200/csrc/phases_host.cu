@@ -133,6 +133,7 @@ extern "C" int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* pa
     return WFB_EINVAL;
   }
   const double t_begin = now_s();
+  wfb_trace_mark_("map_phase: begin");
   *paf = nullptr; *paf_len = 0;
   wfb_map_phase_params_t P = *params;
   const int k = P.kmer_size;
@@ -173,6 +174,7 @@ extern "C" int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* pa
                                                             (int32_t)tg.size(), 4096, 21, P.ani_percentile, P.ani_adjustment, nullptr);
     if (params->sketch_size <= 0) P.sketch_size = (int32_t)std::min<int64_t>(wfb_sketch_size(P.percentage_identity, w, k), w);
     ani_seconds = now_s() - t_ani;
+    wfb_trace_mark_("map_phase: ids + ANI auto-identity");
   }
   if (P.sketch_size <= 0) P.sketch_size = wfb_sketch_size(P.percentage_identity, w, k);
   const int s = P.sketch_size;
@@ -195,6 +197,7 @@ extern "C" int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* pa
   if (g_emu_nfrag < 0) { wfb_set_last_error_("the mapping kernels are not part of the host emulation (see wfb_emu_inject_l2)"); return WFB_ENODEV; }
 #endif
   const double index_seconds = now_s() - t_ix;
+  wfb_trace_mark_("map_phase: index build");
 
   /* run-level constants (computeMap.hpp:150-160, 224-226, 999-1024) */
   const int32_t min_hits = std::max(P.minimum_hits, wfb_estimate_minimum_hits_relaxed(s, k, P.percentage_identity, 0.95f));
@@ -222,6 +225,7 @@ extern "C" int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* pa
     if (Q.len % w != 0) { frags.push_back(wfb_frag_t{base[m] + Q.len - w, (int32_t)w, qid}); fq.push_back(wfb_frag_query_t{qid, ids.group[(size_t)qid]}); frag_index.push_back((int32_t)nfull); }
     q_frag.push_back((int64_t)frags.size());
   }
+  wfb_trace_mark_("map_phase: query blob + fragments");
   std::string text;
   int64_t n_l2 = 0, n_out = 0;
   double map_ms = 0, filter_seconds = 0;
@@ -259,6 +263,7 @@ extern "C" int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* pa
       for (int32_t f = 0; f < nf; ++f)
         if (fst[(size_t)f] != 0) { wfb_set_last_error_("a fragment exceeded an internal capacity of the mapping kernels"); rc = WFB_ECAP; break; }
     if (rc != WFB_OK) { if (ix) wfb_index_free(ix); return rc; }
+    wfb_trace_mark_("map_phase: L1 + L2 (wfb_map_fragments_batch)");
     const double t_f = now_s();
     /* per query: MappingResult construction + boundary check, then the chain / filter stage for the whole batch */
     std::vector<wfb_mapping_t> all((size_t)n_l2 + 1); /* + 1: never a null pointer, also when no fragment mapped anywhere */
@@ -321,8 +326,10 @@ extern "C" int wfb_map_phase_subset(int device, const wfb_map_phase_params_t* pa
     n_out = oo.back();
     filter_seconds = now_s() - t_f;
   }
+  wfb_trace_mark_("map_phase: chain + filters + text");
   if (ix) wfb_index_free(ix);
   *paf = to_c_text(text);
+  wfb_trace_mark_("map_phase: index freed, text copied");
   if (!*paf) { wfb_set_last_error_("out of host memory"); return WFB_ENOMEM; }
   *paf_len = (int64_t)text.size();
   if (stats) {

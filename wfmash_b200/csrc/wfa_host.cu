@@ -27,8 +27,7 @@ void wfb_set_last_error_(const std::string& s) { g_last_error = s; }
 void wfb_count_launch_() { g_launches.fetch_add(1); }
 /* WFB_TRACE: host-side stage timeline ("[wfb] t+<ms since the previous mark> <tag>") */
 void wfb_trace_mark_(const char* tag) {
-  static const bool on = getenv("WFB_TRACE") != nullptr;
-  if (!on) return;
+  if (!getenv("WFB_TRACE")) return; /* read every time: callers switch it on between phases */
   static thread_local double last = 0;
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -492,7 +491,7 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
       pq.tasks = (WfbTask*)a->d_q[0].p; pq.ready = (int*)a->d_q[1].p; pq.head = d_ctrl + 8; pq.tail = d_ctrl + 9;
       pq.outstanding = d_ctrl + 10; pq.error = d_ctrl + 11; pq.cap = (int)qcap;
       long long* d_cta_log = nullptr;
-      if (getenv("WFB_TRACE")) {
+      if (getenv("WFB_TRACE") && strcmp(getenv("WFB_TRACE"), "stages") != 0) { /* WFB_TRACE=stages: the host-stage timeline only, no in-kernel per-CTA / per-pair log */
         if (a->d_tasklog.ensure(sizeof(long long) * (4 * (size_t)ctas + 2 * (size_t)n))) { g_last_error = "device allocation failed (cta log)"; return WFB_ENOMEM; }
         d_cta_log = (long long*)a->d_tasklog.p;
         WFB_MEMSET(d_cta_log, 0, sizeof(long long) * (4 * (size_t)ctas + 2 * (size_t)n), s);

@@ -18,6 +18,7 @@
 #ifndef WFB_EMU
 #include <cub/cub.cuh>
 #endif
+#include "wfb_pool.h" /* this file's cudaMalloc / cudaFree go through the library's device-memory pool */
 
 void wfb_set_last_error_(const std::string& s);
 void wfb_count_launch_();

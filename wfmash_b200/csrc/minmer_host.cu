@@ -17,6 +17,7 @@
 #ifndef WFB_EMU
 #include <cub/cub.cuh>
 #endif
+#include "wfb_pool.h" /* this file's cudaMalloc / cudaFree go through the library's device-memory pool */
 
 void wfb_set_last_error_(const std::string& s); /* wfa_host.cu */
 void wfb_count_launch_();

@@ -40,6 +40,7 @@ static SkErr sk_last_error;
 
 
 #include "sketch_kernels.h"
+#include "wfb_pool.h" /* this file's cudaMalloc / cudaFree go through the library's device-memory pool */
 
 /* dynamic shared memory: keys[N] u64 | vals[N] u32 | seq[len_pad] u8 */
 WFB_KERNEL(wfb_sketch_kernel, const uint8_t* seq_base, const wfb_frag_t* frags, int nfrags, int ksize, int ssize, int npow2_max,

@@ -37,6 +37,88 @@ void wfb_trace_mark_(const char* tag) {
 }
 
 #ifndef WFB_EMU
+/* ---- device-memory pool of the mapping path's temporaries (wfb_pool.h) ---- */
+#include <map>
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct DevPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;      /* size -> block */
+  std::unordered_map<void*, size_t> block_size;  /* every live or cached block this pool handed out */
+  size_t cached = 0;
+};
+DevPool g_pool[16];
+size_t pool_round(size_t n) {
+  if (n < 256) n = 256;
+  size_t p2 = 256;
+  while (p2 < n) p2 <<= 1;
+  const size_t step = std::max<size_t>(p2 >> 4, 256); /* sizes within a power of two: 8 steps of 1/16 of the upper bound */
+  return (n + step - 1) / step * step;
+}
+size_t pool_cap_bytes() {
+  static const size_t cap = (size_t)(getenv("WFB_POOL_MAX_GB") ? atof(getenv("WFB_POOL_MAX_GB")) : 16.0) * (1ull << 30);
+  return cap;
+}
+void pool_drop_all(DevPool& P) { /* P.mu held */
+  for (auto& kv : P.free_blocks) { P.block_size.erase(kv.second); cudaFree(kv.second); }
+  P.free_blocks.clear();
+  P.cached = 0;
+}
+}  // namespace
+cudaError_t wfb_pool_malloc_(void** p, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevPool& P = g_pool[dev & 15];
+  const size_t want = pool_round(bytes);
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.free_blocks.lower_bound(want);
+    if (it != P.free_blocks.end() && it->first <= want + want / 4) {
+      *p = it->second;
+      P.cached -= it->first;
+      P.free_blocks.erase(it);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) { /* give the cache back to the driver and try once more */
+    cudaGetLastError();
+    { std::lock_guard<std::mutex> lk(P.mu); pool_drop_all(P); }
+    e = cudaMalloc(p, want);
+  }
+  if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(P.mu); P.block_size[*p] = want; }
+  return e;
+}
+cudaError_t wfb_pool_free_(void* p) {
+  if (!p) return cudaSuccess;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevPool& P = g_pool[dev & 15];
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.block_size.find(p);
+    if (it != P.block_size.end()) {
+      if (P.cached + it->second <= pool_cap_bytes()) {
+        P.free_blocks.emplace(it->second, p);
+        P.cached += it->second;
+        return cudaSuccess;
+      }
+      P.block_size.erase(it);
+    }
+  }
+  return cudaFree(p); /* not ours, or the cache is full */
+}
+void wfb_pool_trim_() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevPool& P = g_pool[dev & 15];
+  std::lock_guard<std::mutex> lk(P.mu);
+  pool_drop_all(P);
+}
+#endif
+
+#ifndef WFB_EMU
 #define WFB_CHECK(call)                                                                              \
   do {                                                                                               \
     cudaError_t e_ = (call);                                                                         \
@@ -56,7 +138,14 @@ void wfb_trace_mark_(const char* tag) {
     g_launches.fetch_add(1);                                                                         \
   } while (0)
 typedef cudaStream_t wfb_stream_t;
-static int dev_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess ? 0 : -1; }
+static int dev_malloc(void** p, size_t bytes) {
+  if (cudaMalloc(p, bytes) == cudaSuccess) return 0;
+  cudaGetLastError();
+  wfb_pool_trim_(); /* the mapping path's cached temporaries go back to the driver before the aligner gives up */
+  if (cudaMalloc(p, bytes) == cudaSuccess) return 0;
+  cudaGetLastError();
+  return -1;
+}
 static void dev_free(void* p) { if (p) cudaFree(p); }
 static int host_malloc(void** p, size_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? 0 : -1; }
 static void host_free(void* p) { if (p) cudaFreeHost(p); }

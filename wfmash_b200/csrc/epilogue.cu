@@ -27,6 +27,8 @@ void wfb_set_last_error_(const std::string& s); /* wfa_host.cu */
 static inline void wfb_set_last_error(const char* msg) { wfb_set_last_error_(msg); }
 
 void wfb_trace_mark_(const char* tag); /* wfa_host.cu */
+int wfb_align_batch_view_(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_t n, const float* cost_hint, const char** dense, wfb_aln_result_t* results,
+                          wfb_align_stats_t* stats); /* wfa_host.cu */
 void wfb_take_endsfree_counters_(wfb_aligner_t* a, double* kernel_ms, uint64_t* h2d, uint64_t* d2h); /* wfa_host.cu */
 
 namespace {
@@ -439,27 +441,38 @@ int patch_batch(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>& 
     const int rc = wfb_align_endsfree_batch(a, pairs.data(), (int32_t)pairs.size(), term_group, ops.data(), cap, res.data());
     if (rc != WFB_OK) return rc;
   }
-  for (size_t j = 0; j < all.size(); ++j) {
-    const int i = all[j].rec;
-    const Erosion& e = all[j].er;
-    const bool head = all[j].head;
-    Cigar pc;
-    if (slot[j] < 0) {
-      pc.push_back({(int32_t)(e.q == 0 ? e.t : e.q), e.q == 0 ? 'D' : 'I'});
-    } else {
-      const wfb_aln_result_t& rr = res[(size_t)slot[j]];
-      if (rr.status != 0) { if (failed) ++*failed; continue; }
-      pc = rle(ops.data() + rr.ops_offset, rr.ops_len);
+  /* splice: the requests of a record are adjacent in `all` (tail first) and touch only that record's CIGAR, so the records are spliced on
+   * all host cores (a head splice copies the whole main CIGAR: 21 k records x ~20 KB on one thread was 100 ms of the phase) */
+  std::vector<size_t> group; /* first request of each record */
+  for (size_t j = 0; j < all.size(); ++j) if (j == 0 || all[j].rec != all[j - 1].rec) group.push_back(j);
+  group.push_back(all.size());
+  std::atomic<int64_t> n_failed(0);
+  for_each_record((int64_t)group.size() - 1, cap, [&](int64_t g) {
+    for (size_t j = group[(size_t)g]; j < group[(size_t)g + 1]; ++j) {
+      const int i = all[j].rec;
+      const Erosion& e = all[j].er;
+      const bool head = all[j].head;
+      Cigar pc;
+      if (slot[j] < 0) {
+        pc.push_back({(int32_t)(e.q == 0 ? e.t : e.q), e.q == 0 ? 'D' : 'I'});
+      } else {
+        const wfb_aln_result_t& rr = res[(size_t)slot[j]];
+        if (rr.status != 0) { n_failed.fetch_add(1); continue; }
+        pc = rle(ops.data() + rr.ops_offset, rr.ops_len);
+      }
+      erode_short_matches(pc, 3, head);
+      Cigar& c = cig[(size_t)i];
+      if (head) {
+        c = join(pc, c.data() + e.cut, c.size() - e.cut);
+      } else { /* join(runs [0,cut), patch) in place */
+        c.resize(e.cut);
+        size_t i0 = 0;
+        if (!c.empty() && !pc.empty() && c.back().op == pc[0].op) { c.back().n += pc[0].n; i0 = 1; }
+        c.insert(c.end(), pc.begin() + (long)i0, pc.end());
+      }
     }
-    erode_short_matches(pc, 3, head);
-    Cigar& c = cig[(size_t)i];
-    if (head) {
-      c = join(pc, c.data() + e.cut, c.size() - e.cut);
-    } else {
-      Cigar keep(c.begin(), c.begin() + (long)e.cut);
-      c = join(keep, pc.data(), pc.size());
-    }
-  }
+  });
+  if (failed) *failed += n_failed.load();
   return WFB_OK;
 }
 
@@ -520,11 +533,7 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     cap += (int64_t)(r.target_length + r.query_length);
   }
   wfb_trace_mark_("paf_batch: begin");
-  std::unique_ptr<char[]> ops_buf(new (std::nothrow) char[(size_t)cap]); /* not zero-filled: a GB of page faults on one thread otherwise */
-  if (!ops_buf) { wfb_set_last_error("out of host memory"); return WFB_ENOMEM; }
-  char* const ops = ops_buf.get();
   std::vector<wfb_aln_result_t> res((size_t)n);
-  wfb_trace_mark_("paf_batch: ops buffer allocated");
   /* scheduling hint: expected edits from the mapping's identity estimate (the same quantity the reference's own progress / cost
    * heuristics use); it only orders the work, the alignments do not depend on it */
   std::vector<float> hint((size_t)n);
@@ -533,7 +542,10 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     const float d = (id > 0.f && id <= 1.f) ? std::max(1.f - id, 0.002f) : 0.05f;
     hint[(size_t)i] = d * (float)std::max(recs[i].query_length, recs[i].target_length);
   }
-  int rc = wfb_align_batch_hinted(a, pairs.data(), n, hint.data(), ops, cap, res.data(), stats);
+  /* the operation strings stay in the aligner's pinned D2H buffer and are run-length encoded from there (a GB-sized pageable copy and a
+   * second pass over it otherwise); the buffer is reused by the patch rounds, so the conversion below comes first */
+  const char* ops = nullptr;
+  int rc = wfb_align_batch_view_(a, pairs.data(), n, hint.data(), &ops, res.data(), stats);
   if (rc != WFB_OK) return rc;
   wfb_trace_mark_("paf_batch: main alignments (wfb_align_batch_hinted)");
   std::vector<Cigar> cig((size_t)n);
@@ -547,7 +559,6 @@ extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, i
     }
     cig[(size_t)i] = rle(ops + res[(size_t)i].ops_offset, res[(size_t)i].ops_len);
   });
-  ops_buf.reset();
   wfb_trace_mark_("paf_batch: run-length conversion");
   if (stats) stats->main_device_cap = main_cap.load();
   if (!params->disable_chain_patching) {

@@ -478,7 +478,7 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
     /* Aligner::processMappingRecord re-emits every line that carries a cg:Z: field as its whitespace-separated fields joined by
      * single tabs (computeAlignments.hpp:486-516): the trailing tab do_biwfa_alignment writes before the newline disappears.
      * Lines without a CIGAR field (SAM records) pass through unchanged. */
-    for (size_t i = b0; i < b1; ++i) {
+    auto reemit = [&](size_t i) {
       std::string& text = line[order[i]];
       for (int64_t a = off[i - b0]; a < off[i - b0 + 1];) {
         const char* nl = (const char*)memchr(buf.get() + a, '\n', (size_t)(off[i - b0 + 1] - a));
@@ -507,6 +507,23 @@ extern "C" int wfb_align_phase(wfb_aligner_t* aligner, const wfb_align_phase_par
         }
         a = b + 1;
       }
+    };
+    { /* records are independent, every line lands in its own slot: over the host cores */
+      int nt = (int)std::min<size_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 32u), (b1 - b0) / 4);
+      if (len < (int64_t)WFB_HOST_PAR_MIN_BYTES) nt = 1;
+      std::atomic<size_t> next(b0);
+      auto worker = [&]() {
+        for (;;) {
+          const size_t lo = next.fetch_add(64);
+          if (lo >= b1) return;
+          const size_t hi = std::min(b1, lo + 64);
+          for (size_t i = lo; i < hi; ++i) reemit(i);
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+      worker();
+      for (auto& t : th) t.join();
     }
     for (size_t i = 0; i < st.size(); ++i) written += st[i] == WFB_REC_WRITTEN;
     kernel_ms += as.kernel_ms;

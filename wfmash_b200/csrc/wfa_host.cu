@@ -358,8 +358,10 @@ static int gap_affine2p_score(const char* ops, int n, const WfbPen& p) {
 /* Core: sequences are described by (host pointers) or (device buffer + offsets). */
 static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const char* d_src, const int64_t* src_p_off,
                       const int32_t* src_p_len, const int64_t* src_t_off, const int32_t* src_t_len, char* ops,
-                      int64_t ops_cap, wfb_aln_result_t* results, wfb_align_stats_t* stats, const float* cost_hint = nullptr) {
-  if (!a || n < 0 || (n > 0 && (!results || !ops))) { g_last_error = "bad argument"; return WFB_EINVAL; }
+                      int64_t ops_cap, wfb_aln_result_t* results, wfb_align_stats_t* stats, const float* cost_hint = nullptr,
+                      const char** dense_view = nullptr /* library-internal: leave the operation strings in the aligner's pinned buffer (valid until
+                                                           its next call) instead of copying them to `ops`; results[i].ops_offset points into it */) {
+  if (!a || n < 0 || (n > 0 && (!results || (!ops && !dense_view)))) { g_last_error = "bad argument"; return WFB_EINVAL; }
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n == 0) return WFB_OK;
 #ifndef WFB_EMU
@@ -393,7 +395,7 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     /* worst case a pair needs plen+tlen ops; demand that much so no result can be truncated */
     long long need = 0;
     for (int i = 0; i < n; ++i) need += pd[i].plen + pd[i].tlen;
-    if (need > ops_cap) { g_last_error = "ops buffer too small (need sum(pattern_len+text_len))"; return WFB_ECAP; }
+    if (!dense_view && need > ops_cap) { g_last_error = "ops buffer too small (need sum(pattern_len+text_len))"; return WFB_ECAP; }
   }
   /* ---- device buffers ---- */
   if (a->d_seq.ensure((size_t)seq_bytes + 64) || a->d_pairs.ensure(sizeof(WfbPairDesc) * (size_t)n) ||
@@ -773,6 +775,13 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
   WFB_D2H(h_dense, d_dense, (size_t)slot_bytes, s);
   WFB_STREAM_SYNC(s);
   wfb_trace_mark_("align: kernels + D2H done");
+  if (dense_view) { /* no copy, no score scan: the caller reads the strings where the D2H left them */
+    *dense_view = h_dense;
+    for (int i = 0; i < n; ++i) {
+      wfb_aln_result_t& r = results[i];
+      r.status = h_status[i]; r.ops_offset = pd[i].ops_off; r.ops_len = r.status == 0 ? h_len[i] : 0; r.score = 0; r.reserved_ = 0;
+    }
+  } else {
   int64_t out_off = 0;
   for (int i = 0; i < n; ++i) {
     wfb_aln_result_t& r = results[i];
@@ -809,6 +818,7 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     for (int t = 1; t < nt; ++t) th.emplace_back(worker);
     worker();
     for (auto& t : th) t.join();
+  }
   }
   wfb_trace_mark_("align: ops copied out + scores");
   if (getenv("WFB_TRACE")) {
@@ -994,6 +1004,14 @@ extern "C" int wfb_align_batch(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_
 void wfb_take_endsfree_counters_(wfb_aligner_t* a, double* kernel_ms, uint64_t* h2d, uint64_t* d2h) {
   *kernel_ms = a->endsfree_kernel_ms; *h2d = a->endsfree_h2d; *d2h = a->endsfree_d2h;
   a->endsfree_kernel_ms = 0; a->endsfree_h2d = 0; a->endsfree_d2h = 0;
+}
+
+/* (library-internal, epilogue.cu) the hinted batch with the operation strings left in the aligner's pinned buffer */
+int wfb_align_batch_view_(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_t n, const float* cost_hint, const char** dense, wfb_aln_result_t* results,
+                          wfb_align_stats_t* stats) {
+  if ((n > 0 && !pairs) || !dense) { g_last_error = "bad argument"; return WFB_EINVAL; }
+  *dense = nullptr;
+  return align_impl(a, n, pairs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, results, stats, cost_hint, dense);
 }
 
 extern "C" int wfb_align_batch_hinted(wfb_aligner_t* a, const wfb_pair_t* pairs, int32_t n, const float* cost_hint, char* ops, int64_t ops_cap,

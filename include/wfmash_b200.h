@@ -179,7 +179,9 @@ typedef struct {
 
 typedef struct {
   int32_t disable_chain_patching; /* wflign.cpp:125 */
-  int32_t term_group;             /* 1 / 8 / 16, see wfb_align_endsfree_batch; 0 = 8 */
+  int32_t term_group;             /* 1 / 8 / 16, see wfb_align_endsfree_batch; 0 = 8 (the AVX2 build, what the fixtures were made with);
+                                     -1 = what a -march=native build of the reference would do on this host (cpuid: AVX-512 CD+VL -> 16,
+                                     AVX2 -> 8, else 1): the reference's head / tail patch CIGARs differ between its ISA builds */
   float min_identity;             /* wflign_patch.cpp:2624-2626 filters */
   float min_block_identity;
   uint64_t min_alignment_length;

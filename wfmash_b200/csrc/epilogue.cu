@@ -518,7 +518,15 @@ int patch_records(wfb_aligner_t* a, const wfb_record_t* recs, std::vector<Cigar>
 extern "C" int wfb_biwfa_paf_batch(wfb_aligner_t* a, const wfb_record_t* recs, int32_t n, const wfb_paf_params_t* params, char* out,
                                    int64_t out_cap, int64_t* out_len, int64_t* line_offset, int32_t* rec_status, wfb_align_stats_t* stats) {
   if (!a || n < 0 || !params || !out_len || (n > 0 && (!recs || !line_offset || !rec_status))) { wfb_set_last_error("bad argument"); return WFB_EINVAL; }
-  const int term_group = params->term_group == 0 ? 8 : params->term_group;
+  int term_group = params->term_group == 0 ? 8 : params->term_group;
+  if (term_group < 0) { /* "what a -march=native build of the reference on THIS host does": WFA2-lib compiles its AVX-512 extend kernels under
+                           __AVX512CD__ && __AVX512VL__, its AVX2 kernels under __AVX2__ (wavefront_extend_kernels_avx.h:35,58), scalar otherwise */
+#if defined(__x86_64__) && defined(__GNUC__)
+    term_group = (__builtin_cpu_supports("avx512cd") && __builtin_cpu_supports("avx512vl")) ? 16 : __builtin_cpu_supports("avx2") ? 8 : 1;
+#else
+    term_group = 1;
+#endif
+  }
   *out_len = 0;
   if (n == 0) return WFB_OK;
   std::vector<wfb_pair_t> pairs((size_t)n);

@@ -1369,23 +1369,32 @@ WFB_DEV_NOINLINE bool wfb_team_step(WfbTeamSlot* ts, WfbTeamShared& tsh, int32_t
       if (++spins > (1u << 28)) { *error = 3; ok = false; break; }
     }
     __threadfence();
+    /* both directions' reductions in ONE memory round trip (32 independent L2 loads), not one per value: the fold sits on the chain of
+     * every team step */
+    WfbTeamRed rr[2];
+    {
+      const int* src = (const int*)&ts->red[p][0];
+      int* dst = (int*)&rr[0];
+#pragma unroll
+      for (int i = 0; i < (int)(2 * sizeof(WfbTeamRed) / sizeof(int)); ++i) dst[i] = __ldcg(src + i);
+    }
     for (int d = 0; d < ndir; ++d) {
       if (!live[d]) continue;
       WfbRing& ring = *dirs[d].ring;
       const int slot = dirs[d].slot;
-      const WfbTeamRed* r = &ts->red[p][d];
+      const WfbTeamRed* r = &rr[d];
       const bool exs[5] = {true, (bool)((D[d].flags >> 8) & 1u), (bool)((D[d].flags >> 9) & 1u), (bool)((D[d].flags >> 10) & 1u), (bool)((D[d].flags >> 11) & 1u)};
-      const int ak = wfb_ld_vol(&r->ak), tmax = wfb_ld_vol(&r->tmax);
+      const int ak = r->ak, tmax = r->tmax;
       for (int c = 0; c < 5; ++c) {
         if (!exs[c]) continue;
-        const int lo = wfb_ld_vol(&r->lo[c]), hi = wfb_ld_vol(&r->hi[c]);
+        const int lo = r->lo[c], hi = r->hi[c];
         if (lo != INT_MAX && lo < ring.lo[slot][c]) ring.lo[slot][c] = lo;
         if (hi != INT_MIN && hi > ring.hi[slot][c]) ring.hi[slot][c] = hi;
         if (ak != INT_MIN && ak > ring.mak[slot][c]) ring.mak[slot][c] = ak;
       }
       if (tmax > 0 && tmax > dirs[d].red_maxak[dirs[d].par]) dirs[d].red_maxak[dirs[d].par] = tmax;
       if (tmax > ring.mak[slot][WFB_M]) ring.mak[slot][WFB_M] = tmax;
-      dirs[d].red_end[dirs[d].par] = wfb_ld_vol(&r->end);
+      dirs[d].red_end[dirs[d].par] = r->end;
     }
     tsh.flag = ok ? 1 : 0;
   }

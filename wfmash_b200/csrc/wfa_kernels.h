@@ -1048,7 +1048,9 @@ struct WfbAllocFixed { /* breakpoint kernel: every (slot, component) has a fixed
 #ifndef WFB_TEAM_MIN_WIDTH
 #define WFB_TEAM_MIN_WIDTH 4096 /* wavefront width (both directions together in phase 1) from which help is worth asking for */
 #endif
+#ifndef WFB_TEAM_MAX_HELPERS
 #define WFB_TEAM_MAX_HELPERS 47
+#endif
 
 struct WfbStepDesc { /* the uniform part of one score step of one direction */
   WfbIn in[7];        /* m_misms, m_open1, m_open2, i1_ext, i2_ext, d1_ext, d2_ext */
@@ -1110,7 +1112,7 @@ WFB_DEV bool wfb_team_prologue(WfbRing& ring, const WfbPen& pen, int score, cons
     for (int c = 0; c < 5; ++c) D.ob[c] = 0;
     return false;
   }
-  const bool n_m = flags & 1u, n_o1 = flags & 2u, n_o2 = flags & 4u, n_i1 = flags & 8u, n_i2 = flags & 16u, n_d1 = flags & 32u, n_d2 = flags & 64u;
+  const bool n_o1 = flags & 2u, n_o2 = flags & 4u, n_i1 = flags & 8u, n_i2 = flags & 16u, n_d1 = flags & 32u, n_d2 = flags & 64u;
   int lo = D.in[0].lo, hi = D.in[0].hi;
   lo = min(lo, D.in[1].lo - 1); hi = max(hi, D.in[1].hi + 1);
   lo = min(lo, D.in[3].lo + 1); hi = max(hi, D.in[3].hi + 1);
@@ -1273,7 +1275,7 @@ WFB_DEV_NOINLINE void wfb_team_work(WfbTeamSlot* ts, unsigned epoch, WfbTeamShar
   int tlo[5], thi[5], tak = INT_MIN, tmax = 0;
   auto flush = [&](int dir) {
     const unsigned flags = *(const volatile unsigned*)&ts->d[p][dir].flags;
-    const bool exs[5] = {true, (flags >> 8) & 1u, (flags >> 9) & 1u, (flags >> 10) & 1u, (flags >> 11) & 1u};
+    const bool exs[5] = {true, ((flags >> 8) & 1u) != 0, ((flags >> 9) & 1u) != 0, ((flags >> 10) & 1u) != 0, ((flags >> 11) & 1u) != 0};
     WfbTeamRed* r = &ts->red[p][dir];
     const int lane = wfb_lane();
     const int vak = wfb_warp_max(tak);

@@ -11,4 +11,4 @@ d=json.loads(sys.stdin.read())
 print('value %.1f e2e %.1f Mbp/s n=%d'%(d['value']/1e6,d['e2e']['value']/1e6,d['n_gpus']), d['run']['records_per_gpu'], {k:round(v,1) for k,v in d['phases_ms'].items()}, d['parity'])
 "
 tail -5 $OUT/${TAG}_bench_n2.err
-WFB_LIB=scripts/_build/libwfb_dirsm.so timeout 300 python scripts/c3_align_profile.py C3 32768:1 32768:1 > $OUT/${TAG}_dirsm.log 2> $OUT/${TAG}_dirsm.err; echo "dirsm rc=$? $(tail -1 $OUT/${TAG}_dirsm.log) $(grep 'main n=' $OUT/${TAG}_dirsm.err | tail -1 | cut -c1-70)"
+

@@ -535,7 +535,12 @@ static int align_impl(wfb_aligner* a, int32_t n, const wfb_pair_t* hpairs, const
     {
       /* packed sequences: 52 KB hold 2 x (52 kb + 52 kb); the size must leave 2 CTAs per SM, and what the CTAs do not take stays L1
        * (the rows are read through it: 98 KB here cost 11 % of the kernel time on scerevisiae8, profiles/r02_row_staging_experiment.md) */
-      const int want = getenv("WFB_SEQ_SMEM_KB") ? atoi(getenv("WFB_SEQ_SMEM_KB")) : 56;
+      /* exactly what the batch's largest pair needs (forward + reversed pattern and text at 16 bases per word): every KB not taken
+       * can stay L1, and the driver picks the smallest shared-memory carve-out that fits two CTAs (scerevisiae8: 50 KB -> the 132 KB
+       * carve-out instead of 164 KB, -2.6 % kernel time; 36 / 24 KB, which leave the 100 kb root tasks unpacked: +8 / +11 %) */
+      const long long need_words = 2LL * (((long long)maxP + 30) / 16 + 3) + 2LL * (((long long)maxT + 30) / 16 + 3);
+      const int need_kb = (int)std::min<long long>(56, (need_words * 4 + 1023) / 1024);
+      const int want = getenv("WFB_SEQ_SMEM_KB") ? atoi(getenv("WFB_SEQ_SMEM_KB")) : need_kb;
       const int tries[3] = {want, std::min(want, 56), 0};
       int nb0 = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, wfb_persist_kernel, kBreakThreads, 0) != cudaSuccess || nb0 <= 0) { cudaGetLastError(); nb0 = 0; }

@@ -261,7 +261,25 @@ def allgather_bytes(data: bytes, dev, world):
     return [bytes(out[r][: sizes[r]].cpu().numpy()) for r in range(world)], sum(sizes)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to stdout behind our back (NCCL's "NCCL version ..." banner is a printf): keep the original stdout for the JSON line
+    # and point fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -288,7 +306,7 @@ def main():
         for i in range(total):
             last = reference_step(cfg, targets, queries, gold, cores, per_step, seed=1000 + i)
             if "unavailable" in last:
-                print(json.dumps({"impl": "reference", "unavailable": last["unavailable"]}))
+                emit({"impl": "reference", "unavailable": last["unavailable"]})
                 return 0
             if i >= args.warmup:
                 vals.append(last["value"]); ms.append(last["sample_ms"])
@@ -298,7 +316,7 @@ def main():
                 "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
                 "data": "reference's own example data (data/scerevisiae8.fa.gz)", "config": workload, "cpu_baseline": last,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -306,8 +324,7 @@ def main():
     from tests import configrun
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
+        # (NCCL's version banner is a printf to stdout: see emit() — the process's fd 1 already points at stderr)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
@@ -465,7 +482,7 @@ def main():
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = reference_step(cfg, targets, queries, gold, cores, args.cpu_seconds, seed=1)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -215,50 +215,7 @@ def reference_step(cfg, targets, queries, gold, cores, align_seconds, seed):
 # ---------------------------------------------------------------------------------------------------
 # Our arm
 # ---------------------------------------------------------------------------------------------------
-def partition_queries(queries, w, world):
-    """Whole queries per rank (the chain / filter stage needs every fragment of a query), longest first onto the lightest rank."""
-    load, owner = [0] * world, {}
-    for n, s in sorted(queries, key=lambda x: -len(x[1])):
-        r = min(range(world), key=lambda i: load[i])
-        owner[n] = r
-        load[r] += len(s) if len(s) >= w else 0
-    return owner
-
-
-def partition_rows(rows, world):
-    """Mapping rows over the ranks by expected cost ((1 - identity) * length)^2, heaviest first onto the lightest rank (LPT)."""
-    cost = []
-    for ln in rows:
-        f = ln.split(b"\t")
-        ident = 0.95
-        for x in f[12:]:
-            if x.startswith(b"id:f:"):
-                ident = float(x[5:])
-        d = max(1.0 - ident, 0.002)
-        cost.append((d * (int(f[3]) - int(f[2]))) ** 2 + 1e4)
-    load, owner = [0.0] * world, [0] * len(rows)
-    for i in sorted(range(len(rows)), key=lambda j: -cost[j]):
-        r = min(range(world), key=lambda k: load[k])
-        owner[i] = r
-        load[r] += cost[i]
-    return owner
-
-
-def allgather_bytes(data: bytes, dev, world):
-    """NCCL all-gather of one byte string per rank (sizes first, then the padded payloads)."""
-    import torch
-    import torch.distributed as dist
-    n = torch.tensor([len(data)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(x.item()) for x in sizes]
-    cap = max(max(sizes), 1)
-    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
-    if data:
-        buf[: len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
-    out = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(out, buf)
-    return [bytes(out[r][: sizes[r]].cpu().numpy()) for r in range(world)], sum(sizes)
+from wfmash_b200.shard import allgather_bytes, job_sharded, partition_queries, partition_rows  # noqa: E402,F401  (the library's sharding of one job)
 
 
 _REAL_STDOUT = None
@@ -345,47 +302,10 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        """-> dict of this rank's timings + (rank 0) the whole job's text."""
-        r = {}
-        t0 = time.perf_counter()
-        if world == 1:
-            mp, mst = wb.map_phase(targets, queries, MP, dev)
-        else:
-            # every rank builds the (replicated) index and maps ITS queries; ids / groups come from all sequences
-            mp, mst = wb.map_phase(targets, my_queries, MP, dev, all_queries=queries)
-        r["t_map"] = time.perf_counter() - t0
-        r["gather_bytes"] = 0
-        if world > 1:
-            t1 = time.perf_counter()
-            parts, nb = allgather_bytes(mp, tdev, world)
-            # the job's mapping PAF in the single-GPU order: queries in input order, each query's rows as its rank wrote them
-            per_query = {}
-            for part in parts:
-                for ln in part.split(b"\n"):
-                    if ln:
-                        per_query.setdefault(ln.split(b"\t", 1)[0], []).append(ln)
-            rows = [ln for n, _ in queries for ln in per_query.get(n.encode(), [])]
-            owner = partition_rows(rows, world)
-            mine = [i for i in range(len(rows)) if owner[i] == rank]
-            my_rows = b"".join(rows[i] + b"\n" for i in mine)
-            r["t_exchange_rows"] = time.perf_counter() - t1
-            r["gather_bytes"] += nb
-            full_mp = b"".join(x + b"\n" for x in rows)
-        else:
-            my_rows, full_mp = mp, mp
-        t2 = time.perf_counter()
-        paf, ast = wb.align_phase(al, my_rows, targets, queries if not same else targets, window_length=w, batch_records=args.batch_records)
-        r["t_align"] = time.perf_counter() - t2
-        if world > 1:
-            t3 = time.perf_counter()
-            parts, nb = allgather_bytes(paf, tdev, world)
-            r["t_gather_paf"] = time.perf_counter() - t3
-            r["gather_bytes"] += nb
-            paf_all = b"".join(parts)
-        else:
-            paf_all = paf
-        r["t_total"] = time.perf_counter() - t0
-        r.update(mst=mst, ast=ast, mapping_paf=full_mp, paf=paf_all, my_records=int(ast.records))
+        """-> dict of this rank's timings + the whole job's text (wfmash_b200.shard.job_sharded: the C++ phases, rows / PAF exchanged as
+        all-gathers of byte tensors at N > 1)."""
+        r = job_sharded(wb, al, targets, queries, MP, w, dev, tdev, rank, world, batch_records=args.batch_records, my_queries=my_queries if world > 1 else None)
+        mst, ast = r["mst"], r["ast"]
         # device time of the step: every kernel round's CUDA-event time
         r["device_s"] = (mst.index_kernel_ms + mst.map_kernel_ms + mst.ani_kernel_ms + ast.kernel_ms + ast.patch_kernel_ms) / 1e3
         return r

@@ -65,6 +65,62 @@ def test_partition_is_balanced_and_complete():
     assert shard.partition(costs, 4) == shard.partition(costs, 4)  # deterministic
 
 
+def _job_worker(rank, world, port, q):
+    """wfmash_b200.shard.job_sharded (the flow bench.py --gpus N runs) with stand-ins for the two C-ABI phases: gloo all-gathers of byte
+    tensors, rows re-assembled in the single-process order, rows partitioned by expected cost, PAF gathered on every rank."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import types
+    import torch
+    import torch.distributed as dist
+    from wfmash_b200 import shard
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    queries = [(f"s{i}#1#c", b"A" * (1000 * (i % 5 + 1))) for i in range(11)] + [("short#1#c", b"A" * 10)]
+    calls = {}
+
+    class FakeWb:  # stands in for the ctypes mirror: two rows per mapped query (identity depends on the query), one PAF line per row
+        @staticmethod
+        def map_phase(targets, mine, params, device, all_queries=None):
+            assert all_queries is queries and {n for n, _ in mine} <= {n for n, _ in queries}
+            calls["mapped"] = [n for n, _ in mine]
+            txt = b"".join(b"%s\t%d\t0\t%d\t+\tt%d\t99999\t10\t%d\t5\t100\t30\tid:f:0.%d\tkc:f:1\n" % (n.encode(), len(s), len(s), j, 10 + len(s), 80 + len(s) // 1000)
+                           for n, s in mine if len(s) >= 1000 for j in range(2))
+            return txt, types.SimpleNamespace(rank=rank)
+
+        @staticmethod
+        def align_phase(aligner, rows, targets, qs, window_length=1000, batch_records=0):
+            lines = [ln for ln in rows.split(b"\n") if ln]
+            calls["aligned"] = len(lines)
+            return b"".join(b"paf:" + ln.split(b"\t")[0] + b":" + ln.split(b"\t")[5] + b":%d\n" % rank for ln in lines), types.SimpleNamespace(records=len(lines))
+
+    r = shard.job_sharded(FakeWb, None, queries, queries, None, 1000, 0, torch.device("cpu"), rank, world)
+    q.put((rank, r["mapping_paf"], r["paf"], calls["mapped"], calls["aligned"], r["my_records"], r["gather_bytes"]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_job_through_the_phase_level_sharding():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_job_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, mp0, paf0, mapped0, n0, rec0, gb0), (_, mp1, paf1, mapped1, n1, rec1, gb1) = got
+    assert mp0 == mp1 and paf0 == paf1 and gb0 == gb1 > 0                     # every rank holds the whole job's texts
+    assert sorted(mapped0 + mapped1) == sorted([f"s{i}#1#c" for i in range(11)] + ["short#1#c"]) and mapped0 and mapped1   # queries split, none twice
+    rows = [ln for ln in mp0.split(b"\n") if ln]
+    assert [ln.split(b"\t")[0].decode() for ln in rows] == [f"s{i}#1#c" for i in range(11) for _ in range(2)]   # single-process order restored
+    assert n0 + n1 == len(rows) == rec0 + rec1 and n0 > 0 and n1 > 0            # rows split over both ranks, each aligned once
+    recs = [ln for ln in paf0.split(b"\n") if ln]
+    assert sorted(b":".join(r.split(b":")[1:3]) for r in recs) == sorted(ln.split(b"\t")[0] + b":" + ln.split(b"\t")[5] for ln in rows)
+    assert {r.split(b":")[3] for r in recs} == {b"0", b"1"}
+
+
 def test_two_rank_gloo_shard_and_gather():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

@@ -181,3 +181,45 @@ def test_index_file_is_interchangeable_with_the_reference(oracle, tmp_path):
         wb.index_file_read(our_file, 8)          # not a subset boundary: bad magic number
     with pytest.raises(wb.WfbError):
         wb.index_file_read(str(tmp_path / "missing.idx"))
+
+
+def test_index_file_reader_rejects_truncated_and_forged_files(tmp_path):
+    """wfb_index_file_read trusts nothing in the file: every truncation point and every count forged to a huge value must
+    come back as an error — no crash, no multi-GB allocation, no exception through the C boundary."""
+    import struct
+    import wfmash_b200 as wb
+    rng = np.random.default_rng(5)
+    n_mi, n_u = 40, 12
+    mi = np.zeros(n_mi, dtype=wb.MINMER_DTYPE)
+    mi["hash"] = rng.integers(1, 2**62, n_mi, dtype=np.uint64); mi["wpos"] = np.arange(n_mi) * 7; mi["wpos_end"] = mi["wpos"] + 5
+    mi["seqId"] = rng.integers(0, 3, n_mi); mi["strand"] = 1
+    uhash = np.sort(rng.choice(2**61, n_u, replace=False).astype(np.uint64))
+    ucount = rng.integers(1, 5, n_u).astype(np.uint32)
+    ustart = np.concatenate([[0], np.cumsum(ucount)[:-1]]).astype(np.uint32)
+    pts = ((rng.integers(0, 3, int(ucount.sum())).astype(np.uint64) << np.uint64(41)) | (rng.integers(0, 10**6, int(ucount.sum())).astype(np.uint64) << np.uint64(1)))
+    names = ["g#1#a", "g#1#b", "h#1#c"]
+    path = str(tmp_path / "ok.idx")
+    wb.index_file_write(path, (mi, uhash, ustart, ucount, pts), 15, 1000, 24, names, {nm: i for i, nm in enumerate(names)})
+    hdr, data, nxt = wb.index_file_read(path)
+    assert hdr["target_names"] == names and len(data[0]) == n_mi and len(data[1]) == n_u and nxt == os.path.getsize(path)
+    blob = open(path, "rb").read()
+    # 1) every truncation
+    bad = str(tmp_path / "bad.idx")
+    for cut in list(range(0, 200, 3)) + list(range(200, len(blob), 37)):
+        open(bad, "wb").write(blob[:cut])
+        with pytest.raises(wb.WfbError):
+            wb.index_file_read(bad)
+    # 2) forged counts: find the 8-byte fields holding the minmer count and the hash count and blow them up
+    pos_mi = blob.index(struct.pack("<q", n_mi) + mi.tobytes()[:16]) if struct.pack("<q", n_mi) + mi.tobytes()[:16] in blob else None
+    forged = 0
+    for off in range(0, len(blob) - 8):                      # (fields after the variable-length names are not 8-byte aligned)
+        v = struct.unpack_from("<Q", blob, off)[0]
+        if v in (n_mi, n_u, len(names)) or (0 < v < 6):      # counts / lengths of this small file
+            for huge in (1 << 39, 1 << 62, 0xFFFFFFFFFFFFFFFF):
+                open(bad, "wb").write(blob[:off] + struct.pack("<Q", huge) + blob[off + 8:])
+                try:
+                    wb.index_file_read(bad)                   # a forged field that happens not to be a count may still parse
+                except wb.WfbError:
+                    forged += 1
+    assert forged >= 30          # the sequence count, name lengths, the minmer count, the hash count, postings counts
+    assert pos_mi is None or pos_mi > 0

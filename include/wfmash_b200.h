@@ -257,6 +257,9 @@ typedef struct {
   uint64_t stale_absorbed; /* expired heap entries absorbed into a sketch entry (commonFunc.hpp:635-641):
                               the only situation in which chunking can deviate from the reference  */
   uint64_t stitch_miss;    /* interval starts that could not be inherited across a chunk boundary (0 = exact) */
+  uint64_t filtered;       /* 1 = candidate-filtered build: only k-mers below a hash threshold entered the window machine */
+  uint64_t candidates;     /* ... how many of them (all sequences)                                                       */
+  uint64_t redo_chunks;    /* ... chunks whose filtered run could not vouch for its result and were re-run over every k-mer */
 } wfb_minmer_stats_t;
 
 /* seq_ptrs[i] / seq_lens[i] : raw FASTA bases of target i (any case); seq_ids[i] -> MinmerInfo::seqId.

@@ -20,6 +20,10 @@ CONFIGS = [
     dict(name="C3sub", target="yeast", query=None, subset=dict(genomes=2, chroms=("chrI", "chrVI", "chrIII")), params=dict(), full_only=False),
     # C3: `wfmash data/scerevisiae8.fa.gz -Y '#'` (all 8 genomes)
     dict(name="C3", target="yeast", query=None, params=dict(), full_only=True),
+    # C4 / C5 (synthetic, xoshiro256** seed 42, PanSN names) at 1/50 and 1/1000 of their stated sizes; `-p 90 -P50k` / `-p 80`
+    # explicit as 8(d) asks, so the ANI estimate is not on the path. Pairwise divergence 10 % / 20 %: the regime of C4 / C5's records.
+    dict(name="C4s", target="synth_c4s", query=None, params=dict(percentage_identity=0.90, filter=dict(max_mapping_length=50000)), full_only=True),
+    dict(name="C5s", target="synth_c5s", query=None, params=dict(percentage_identity=0.80), full_only=True),
 ]
 for _c in CONFIGS:
     _c["params"].setdefault("percentage_identity", None)

@@ -38,8 +38,36 @@ def read_fasta(p):
     return out
 
 
+# SURVEY 8(d)'s synthetic configs C4 / C5 at a scale the CPU reference finishes in minutes here (xoshiro256** seed 42, PanSN names,
+# substitution : insertion : deletion = 8 : 1 : 1; wfmash_b200.synth.pansn_pangenome). Generated, not shipped: every byte is a pure
+# function of the shape, so the build container (fixture) and the GPU box (test / bench) see the same sequences.
+SYNTH = {
+    "synth_c4s": dict(kind="C4", contigs=8, contig_len=2_500_000, ani=0.90),     # 2 genomes x 8 contigs x 2.5 Mbp (C4 is 2 x 20 x 50 Mbp)
+    "synth_c5s": dict(kind="C5", haplotypes=5, contig_len=1_000_000, ani=0.80),  # 5 haplotypes x 1 Mbp (C5 is 100 x 50 Mbp)
+}
+
+
 def load(key):
+    if key in SYNTH:
+        return synthetic(key)
     return read_fasta(path(key))
+
+
+# sha256 over name + sequence of what the generator produced when the reference fixture was made: a different numpy / platform that
+# changed a single base would otherwise show up as an unexplained parity failure
+SYNTH_SHA = {
+    "synth_c4s": "f4b9eaddfe05d2a05110099df1223bedd31004f7c2005285d9a89c2029bdc9c3",
+    "synth_c5s": "17c50ab4113f6955974881aec105672a9c7f4638871674bcd421e536e40428c9",
+}
+
+
+def synthetic(key):
+    import hashlib
+    from wfmash_b200 import synth
+    seqs = synth.pansn_pangenome(SYNTH[key], seed=42)
+    got = hashlib.sha256(b"".join(n.encode() + b"\n" + x + b"\n" for n, x in seqs)).hexdigest()
+    assert got == SYNTH_SHA[key], f"{key}: the generated sequences are not the ones the reference fixture was made from ({got})"
+    return seqs
 
 
 def yeast_subset(seqs, genomes=2, chroms=None):

@@ -17,6 +17,9 @@
 #ifndef WFB_EMU
 #include <cub/cub.cuh>
 #endif
+#ifndef WFB_MM_FILTER_DEFAULT
+#define WFB_MM_FILTER_DEFAULT 1 /* candidate-filtered minmer build (minmer_kernels.h); WFB_MM_FILTER=0/1 overrides */
+#endif
 #include "wfb_pool.h" /* this file's cudaMalloc / cudaFree go through the library's device-memory pool */
 
 void wfb_set_last_error_(const std::string& s); /* wfa_host.cu */
@@ -52,12 +55,13 @@ struct MmFinal { /* post-pass record */
 };
 
 /* post pass 1 (:660-693): number of output pieces of every raw record (0 = dropped) */
-WFB_KERNEL(mm_pieces_kernel, const MmRecord* recs, long long n, int w, int* pieces) {
+WFB_KERNEL(mm_pieces_kernel, const MmRecord* recs, long long n, int w, int* pieces, const int* chunk_flag, long long nrec_filtered) {
   WFB_KERNEL_PROLOGUE
   for (long long r = (long long)bid * WFB_NT + WFB_TID; r < n; r += (long long)nblocks * WFB_NT) {
     const MmRecord m = recs[r];
     int p = 1;
-    if (m.wpos < 0 || m.wpos_end < 0 || m.wpos == m.wpos_end) p = 0;
+    if (r < nrec_filtered && chunk_flag[m.chunk]) p = 0; /* a filtered run that gave up: the exact re-run wrote this chunk's records again */
+    else if (m.wpos < 0 || m.wpos_end < 0 || m.wpos == m.wpos_end) p = 0;
     else if (m.wpos_end > m.wpos + w) p = (int)ceilf((float)(m.wpos_end - m.wpos) / (float)w);
     pieces[r] = p;
   }
@@ -153,10 +157,24 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   if (ns == 0) return WFB_OK;
   MmParams P;
   P.k = k; P.w = w; P.s = s;
-  P.chunk = 1024; P.warm = w; /* tuned in profiles/r01_minmer_chunk_sweep.txt: latency-bound, more chunks = more threads */
-  { const char* e = getenv("WFB_MM_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
+  /* Filtered build (minmer_kernels.h): only k-mers whose hash is <= T enter the window machine, T such that a window holds
+   * lambda = 2s + 40 of them on average (s = 24: the chance that a window holds fewer than s is ~1e-16; a chunk that meets one re-runs
+   * exactly). Off when the candidates would be every other k-mer anyway (tiny windows), or with WFB_MM_FILTER=0. */
+  const double lambda = 2.0 * s + 40.0;
+  const double density = lambda / (double)(w - k + 1);
+  int use_filter = WFB_MM_FILTER_DEFAULT;
+  { const char* e = getenv("WFB_MM_FILTER"); if (e && *e) use_filter = atoi(e) != 0; }
+  if (density > 0.45) use_filter = 0;
+  /* the canonical hash is the smaller of two uniform hashes: P(min <= t) = 1 - (1 - t)^2 */
+  const uint64_t T = use_filter ? (uint64_t)ldexp(1.0 - sqrt(1.0 - density), 64) : ~0ULL;
+  int cand_cap = std::min<int>(MMC_TILE, (int)(density * MMC_TILE * 1.25 + 8.0 * sqrt(density * MMC_TILE)) + 64);
+  { const char* e = getenv("WFB_MM_CAND_CAP"); if (e && atoi(e) > 0) cand_cap = std::min<int>(MMC_TILE, atoi(e)); } /* test hook: forces the tile-overflow fallback */
+  P.chunk = use_filter ? 512 : 1024; P.warm = w; /* full run tuned in profiles/r01_minmer_chunk_sweep.txt: latency-bound, more chunks = more threads */
+  { const char* e = getenv(use_filter ? "WFB_MM_FCHUNK" : "WFB_MM_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
   { const char* e = getenv("WFB_MM_WARM"); if (e && atoi(e) >= w) P.warm = atoi(e); }
   P.qcap = w + 2; P.heap_cap = 3 * w + 64; P.pool_cap = 4 * w + 64;
+  MmParams PF = P; /* the filtered run's containers only ever hold candidates */
+  PF.qcap = PF.heap_cap = PF.pool_cap = (int)(3.0 * lambda) + 64;
   std::vector<MmChunk> chunks;
   for (int q = 0; q < ns; ++q) {
     const long long npos = seqs[q].len - k + 1;
@@ -173,6 +191,22 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   const int nchunks = (int)chunks.size();
   const long long scratch_stride = ((long long)sizeof(MmKmer) * (P.qcap + P.heap_cap) + (long long)sizeof(MmNode) * P.pool_cap +
                                     (long long)sizeof(MmWent) * (s + 2) + 255) / 256 * 256;
+  const long long scratch_stride_f = ((long long)sizeof(MmKmer) * (PF.qcap + PF.heap_cap) + (long long)sizeof(MmNode) * PF.pool_cap +
+                                      (long long)sizeof(MmWent) * (s + 2) + 255) / 256 * 256;
+  std::vector<MmTile> tiles;
+  std::vector<int> seq_tile0((size_t)ns, 0);
+  if (use_filter)
+    for (int q = 0; q < ns; ++q) {
+      const long long npos = seqs[q].len - k + 1;
+      seq_tile0[q] = (int)tiles.size();
+      for (long long tb = 0; tb < npos; tb += MMC_TILE) {
+        MmTile t;
+        t.seq = q; t.start = tb; t.npos = (int)std::min<long long>(MMC_TILE, npos - tb);
+        tiles.push_back(t);
+      }
+    }
+  const int ntiles = (int)tiles.size();
+  long long nrec_filtered = 0, n_redo = 0; /* records written by the filtered run; chunks re-run exactly */
   /* expected density ~0.0027*s windows per base; generous cap, overflow is detected */
   long long rec_cap = (long long)((double)total * (0.01 * s + 0.05)) + 65536;
 #ifndef WFB_EMU
@@ -186,6 +220,9 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   MmRecord* d_rec = nullptr; MmEndEnt* d_end = nullptr; int* d_endcount = nullptr; MmCounters* d_cnt = nullptr;
   int* d_pieces = nullptr; long long* d_offs = nullptr; MmFinal* d_fin = nullptr; unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
   int *d_perm = nullptr, *d_perm2 = nullptr, *d_keep = nullptr; wfb_minmer_t* d_out = nullptr; void* d_tmp = nullptr;
+  MmTile* d_tiles = nullptr; int *d_tile0 = nullptr, *d_cand_lp = nullptr, *d_cand_cnt = nullptr, *d_flag = nullptr, *d_redo = nullptr;
+  uint64_t* d_cand_hash = nullptr;
+  MmCandView CV;
   size_t tmp_bytes = 0;
   uint8_t* h_seq = nullptr;
   MmCounters hc;
@@ -200,7 +237,20 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   MM_CHECK(cudaMalloc(&d_seq, (size_t)total));
   MM_CHECK(cudaMalloc(&d_seqs, sizeof(MmSeq) * ns));
   MM_CHECK(cudaMalloc(&d_chunks, sizeof(MmChunk) * (size_t)nchunks));
-  MM_CHECK(cudaMalloc(&d_scratch, (size_t)scratch_stride * (((size_t)nchunks + MM_LANES - 1) / MM_LANES * MM_LANES))); /* whole warps: the slabs are interleaved */
+  MM_CHECK(cudaMalloc(&d_scratch, (size_t)(use_filter ? scratch_stride_f : scratch_stride) *
+                                       (((size_t)nchunks + MM_LANES - 1) / MM_LANES * MM_LANES))); /* whole warps: the slabs are interleaved */
+  if (use_filter) {
+    MM_CHECK(cudaMalloc(&d_tiles, sizeof(MmTile) * (size_t)ntiles));
+    MM_CHECK(cudaMalloc(&d_tile0, sizeof(int) * (size_t)ns));
+    MM_CHECK(cudaMalloc(&d_cand_hash, sizeof(uint64_t) * (size_t)ntiles * cand_cap));
+    MM_CHECK(cudaMalloc(&d_cand_lp, sizeof(int) * (size_t)ntiles * cand_cap));
+    MM_CHECK(cudaMalloc(&d_cand_cnt, sizeof(int) * (size_t)ntiles));
+    MM_CHECK(cudaMalloc(&d_flag, sizeof(int) * (size_t)nchunks));
+    MM_CHECK(cudaMalloc(&d_redo, sizeof(int) * (size_t)nchunks));
+    MM_CHECK(cudaMemset(d_flag, 0, sizeof(int) * (size_t)nchunks));
+    MM_CHECK(cudaMemcpy(d_tiles, tiles.data(), sizeof(MmTile) * (size_t)ntiles, cudaMemcpyHostToDevice));
+    MM_CHECK(cudaMemcpy(d_tile0, seq_tile0.data(), sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice));
+  }
   MM_CHECK(cudaMalloc(&d_rec, sizeof(MmRecord) * (size_t)rec_cap));
   MM_CHECK(cudaMalloc(&d_end, sizeof(MmEndEnt) * (size_t)nchunks * s));
   MM_CHECK(cudaMalloc(&d_endcount, sizeof(int) * (size_t)nchunks));
@@ -212,8 +262,25 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   MM_CHECK(cudaMemcpy(d_chunks, chunks.data(), sizeof(MmChunk) * (size_t)nchunks, cudaMemcpyHostToDevice));
   MM_CHECK(cudaEventRecord(e0));
   MM_LAUNCH(mm_clean_kernel, 148 * 8, 256, d_seq, total);
-  MM_LAUNCH(mm_stream_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, P, d_scratch, scratch_stride, d_rec,
-            rec_cap, d_end, d_endcount, d_cnt);
+  if (use_filter) {
+    CV.hash = d_cand_hash; CV.lp = d_cand_lp; CV.cnt = d_cand_cnt; CV.cap = cand_cap;
+    MM_LAUNCH(mm_cand_kernel, std::min(ntiles, 148 * MMC_MINBLOCKS), MMC_THREADS, d_seq, d_seqs, d_tiles, ntiles, k, T, cand_cap, d_cand_hash, d_cand_lp,
+              d_cand_cnt, &d_cnt->candidates);
+    MM_LAUNCH(mm_stream_cand_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, PF, d_scratch, scratch_stride_f, d_rec,
+              rec_cap, d_end, d_endcount, d_cnt, CV, d_tile0, d_flag, d_redo);
+    MM_CHECK(cudaMemcpy(&hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost));
+    nrec_filtered = (long long)std::min<unsigned long long>(hc.n_records, (unsigned long long)rec_cap);
+    n_redo = (long long)hc.flagged;
+    if (n_redo > 0) { /* exact re-run of the chunks whose filtered run gave up (short windows around N runs, capacity) */
+      cudaFree(d_scratch); d_scratch = nullptr;
+      MM_CHECK(cudaMalloc(&d_scratch, (size_t)scratch_stride * (((size_t)n_redo + MM_LANES - 1) / MM_LANES * MM_LANES)));
+      MM_LAUNCH(mm_stream_kernel, (int)((n_redo + TPB - 1) / TPB), TPB, d_seq, d_seqs, d_chunks, (int)n_redo, P, d_scratch, scratch_stride, d_rec,
+                rec_cap, d_end, d_endcount, d_cnt, d_redo);
+    }
+  } else {
+    MM_LAUNCH(mm_stream_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, P, d_scratch, scratch_stride, d_rec,
+              rec_cap, d_end, d_endcount, d_cnt, (const int*)nullptr);
+  }
   MM_CHECK(cudaEventRecord(e1));
   { /* stitch 1: parallel passes over all (chunk, entry) pairs until every inherited start is settled */
     int* d_pending = nullptr;
@@ -235,11 +302,11 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     goto done;
   }
   nrec = (long long)hc.n_records;
-  MM_LAUNCH(mm_stitch_records_kernel, 148 * 8, 256, d_rec, nrec, d_chunks, s, d_end, d_endcount, d_cnt);
+  MM_LAUNCH(mm_stitch_records_kernel, 148 * 8, 256, d_rec, nrec, d_chunks, s, d_end, d_endcount, d_cnt, d_flag, nrec_filtered);
   /* post passes */
   MM_CHECK(cudaMalloc(&d_pieces, sizeof(int) * (size_t)(nrec + 1)));
   MM_CHECK(cudaMalloc(&d_offs, sizeof(long long) * (size_t)(nrec + 1)));
-  MM_LAUNCH(mm_pieces_kernel, 148 * 8, 256, d_rec, nrec, w, d_pieces);
+  MM_LAUNCH(mm_pieces_kernel, 148 * 8, 256, d_rec, nrec, w, d_pieces, d_flag, nrec_filtered);
   MM_CHECK(cudaMemset(d_pieces + nrec, 0, sizeof(int)));
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_pieces, d_offs, nrec + 1);
   MM_CHECK(cudaMalloc(&d_tmp, tmp_bytes + (size_t)nrec * 32 + (1 << 20)));
@@ -291,6 +358,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     stats->stream_kernel_ms = a; stats->total_kernel_ms = b;
     stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed;
     stats->stitch_miss = hc.stitch_miss; stats->bases = 0;
+    stats->candidates = hc.candidates; stats->redo_chunks = (uint64_t)n_redo; stats->filtered = (uint64_t)use_filter;
     for (int q = 0; q < ns; ++q) stats->bases += (uint64_t)seqs[q].len;
   }
   if (d_out_keep) { *d_out_keep = d_out; d_out = nullptr; goto done; }
@@ -301,6 +369,7 @@ done:
   cudaFree(d_seq); cudaFree(d_seqs); cudaFree(d_chunks); cudaFree(d_scratch); cudaFree(d_rec); cudaFree(d_end); cudaFree(d_endcount);
   cudaFree(d_cnt); cudaFree(d_pieces); cudaFree(d_offs); cudaFree(d_fin); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_perm);
   cudaFree(d_perm2); cudaFree(d_keep); cudaFree(d_out); cudaFree(d_tmp);
+  cudaFree(d_tiles); cudaFree(d_tile0); cudaFree(d_cand_hash); cudaFree(d_cand_lp); cudaFree(d_cand_cnt); cudaFree(d_flag); cudaFree(d_redo);
   if (h_seq) cudaFreeHost(h_seq);
   return rc;
 #else
@@ -312,20 +381,40 @@ done:
   std::vector<MmRecord> rec((size_t)rec_cap);
   std::vector<MmEndEnt> endst((size_t)nchunks * s);
   std::vector<int> endcount((size_t)nchunks);
+  std::vector<int> flag((size_t)nchunks, 0), redo((size_t)nchunks, 0);
   MmCounters hc;
   memset(&hc, 0, sizeof(hc));
-  for (int c = 0; c < nchunks; ++c) /* scratch reused: chunk c uses slot 0 */
-    mm_stream_kernel(c, nchunks, buf.data(), seqs.data(), chunks.data(), nchunks, P, scratch.data() - (long long)c * scratch_stride,
-                     scratch_stride, rec.data(), rec_cap, endst.data(), endcount.data(), &hc);
+  if (use_filter) {
+    std::vector<uint64_t> cand_hash((size_t)ntiles * cand_cap);
+    std::vector<int> cand_lp((size_t)ntiles * cand_cap), cand_cnt((size_t)ntiles);
+    std::vector<unsigned char> smem((size_t)MMC_SEQ_BYTES + 16 + (size_t)MMC_TILE * 12 + MMC_THREADS * 4 + 64);
+    for (int t = 0; t < ntiles; ++t)
+      mm_cand_kernel(t, ntiles, buf.data(), seqs.data(), tiles.data(), ntiles, k, T, cand_cap, cand_hash.data(), cand_lp.data(), cand_cnt.data(),
+                     &hc.candidates, smem.data());
+    MmCandView CV;
+    CV.hash = cand_hash.data(); CV.lp = cand_lp.data(); CV.cnt = cand_cnt.data(); CV.cap = cand_cap;
+    for (int c = 0; c < nchunks; ++c)
+      mm_stream_cand_kernel(c, nchunks, buf.data(), seqs.data(), chunks.data(), nchunks, PF, scratch.data() - (long long)c * scratch_stride_f,
+                            scratch_stride_f, rec.data(), rec_cap, endst.data(), endcount.data(), &hc, CV, seq_tile0.data(), flag.data(), redo.data());
+    nrec_filtered = (long long)std::min<unsigned long long>(hc.n_records, (unsigned long long)rec_cap);
+    n_redo = (long long)hc.flagged;
+    for (long long c = 0; c < n_redo; ++c)
+      mm_stream_kernel((int)c, (int)n_redo, buf.data(), seqs.data(), chunks.data(), (int)n_redo, P, scratch.data() - c * scratch_stride, scratch_stride,
+                       rec.data(), rec_cap, endst.data(), endcount.data(), &hc, redo.data());
+  } else {
+    for (int c = 0; c < nchunks; ++c) /* scratch reused: chunk c uses slot 0 */
+      mm_stream_kernel(c, nchunks, buf.data(), seqs.data(), chunks.data(), nchunks, P, scratch.data() - (long long)c * scratch_stride,
+                       scratch_stride, rec.data(), rec_cap, endst.data(), endcount.data(), &hc, (const int*)nullptr);
+  }
   for (int pending = 1, passes = 0; pending > 0 && passes <= nchunks; ++passes) {
     pending = 0;
     mm_stitch_ends_pass_kernel(0, 1, chunks.data(), nchunks, s, endst.data(), endcount.data(), &hc, &pending);
   }
   if (hc.overflow || (long long)hc.n_records > rec_cap) { wfb_set_last_error_("minmer stream: capacity overflow"); return WFB_ECAP; }
   const long long nrec = (long long)hc.n_records;
-  mm_stitch_records_kernel(0, 1, rec.data(), nrec, chunks.data(), s, endst.data(), endcount.data(), &hc);
+  mm_stitch_records_kernel(0, 1, rec.data(), nrec, chunks.data(), s, endst.data(), endcount.data(), &hc, flag.data(), nrec_filtered);
   std::vector<int> pieces((size_t)nrec + 1, 0);
-  mm_pieces_kernel(0, 1, rec.data(), nrec, w, pieces.data());
+  mm_pieces_kernel(0, 1, rec.data(), nrec, w, pieces.data(), flag.data(), nrec_filtered);
   std::vector<long long> offs((size_t)nrec + 1);
   long long acc = 0;
   for (long long i = 0; i <= nrec; ++i) { offs[i] = acc; if (i < nrec) acc += pieces[i]; }
@@ -347,7 +436,10 @@ done:
   acc = 0;
   for (long long i = 0; i <= nfin; ++i) { offs2[i] = acc; if (i < nfin) acc += keep[i]; }
   *out_count = acc;
-  if (stats) { stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed; stats->stitch_miss = hc.stitch_miss; }
+  if (stats) {
+    stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed; stats->stitch_miss = hc.stitch_miss;
+    stats->candidates = hc.candidates; stats->redo_chunks = (uint64_t)n_redo; stats->filtered = (uint64_t)use_filter;
+  }
   if (acc > out_cap) { wfb_set_last_error_("minmer output buffer too small"); return WFB_ECAP; }
   if (nfin) mm_gather_out_kernel(0, 1, fin.data(), perm.data(), keep.data(), offs2.data(), nfin, seqs.data(), out);
   (void)device;

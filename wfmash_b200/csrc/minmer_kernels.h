@@ -14,6 +14,13 @@
 //     pass replaces with the true start taken from the previous chunk's end state (same hash);
 //   * the post passes (:660-706: degenerate drop, strand sign, > w splitting, sort, unique) run as
 //     separate data-parallel kernels / library sorts (minmer_host.cu).
+//   * round 2: the state machine no longer sees every k-mer. mm_cand_kernel hashes all positions of a tile in parallel (one CTA
+//     per tile, rolling byte-shift registers, shared-memory staging) and keeps the CANDIDATES whose canonical hash is below a
+//     threshold that leaves ~2s + 40 of them per window; mm_stream_cand_kernel runs the state machine over the candidate stream
+//     only (events: a candidate arrives, a candidate leaves, the first fill), 5 - 15 % of the positions with containers of a
+//     few hundred entries. A chunk that cannot vouch for the result (sketch short of s entries, expired heap entry met while
+//     filling, a capacity hit, a tile with too many candidates) flags itself and is re-run over every k-mer by mm_stream_kernel,
+//     the exact instantiation of the same step function (see "candidate stream" below for why the filter is exact otherwise).
 // Exactness: the chunk state after >= w warm-up positions equals the reference's state restricted to
 // live entries; entries the reference keeps past their expiry ("stale" heap entries, :596-641) can make
 // the two differ. Every such absorption is counted (stale_absorbed) so callers can tell; the parity
@@ -64,6 +71,7 @@ struct MmSeq {
 };
 struct MmCounters {
   unsigned long long n_records, stale_absorbed, overflow, stitch_miss;
+  unsigned long long candidates, flagged; /* filtered build: k-mers below the threshold; chunks left to the exact re-run */
 };
 
 WFB_DEV uint64_t mm_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
@@ -253,167 +261,384 @@ struct MmParams {
   int qcap, heap_cap, pool_cap; /* per-thread capacities */
 };
 
-/* One thread = one chunk. scratch layout per WARP (scratch_stride bytes per chunk, MM_LANES chunks per slab):
- * Q[qcap][lanes] | heap[heap_cap][lanes] | pool[pool_cap][lanes] | W[s+2][lanes]. */
-WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P,
-           unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
-           int* endcount, MmCounters* counters) {
+/* ---- candidate stream (the data-parallel half of the filtered build) ----
+ * A k-mer whose hash is above every hash the window sketch ever holds is a no-op for addMinmers: it goes to the heap when it
+ * arrives (:581-585), is never the heap's front while a smaller live k-mer exists, and is ignored when it leaves (:520). With
+ * T chosen so that a window holds ~2s + 40 k-mers <= T, the state machine only has to see those CANDIDATES (5 - 15 % of the
+ * positions); the chunk flags itself for an exact re-run over all positions whenever that assumption is visibly broken (the
+ * sketch is short of s entries after a step, an expired heap entry is met while filling, a capacity is hit).
+ * mm_cand_kernel: one CTA per tile of MMC_TILE k-mer start positions: the bytes (+ k-1 halo) are staged in shared memory, a thread
+ * rolls the forward / reverse-complement k-mers of MMC_RUN consecutive positions through byte-shift registers (two Murmur3 per
+ * position, nothing else), candidates are staged in shared memory and written to the tile's region in position order. */
+#define MMC_THREADS 256
+#ifndef MMC_MINBLOCKS
+#define MMC_MINBLOCKS 4
+#endif
+#define MMC_RUN 9 /* odd: the 32 lanes of a warp start in 32 different shared-memory banks */
+#define MMC_TILE (MMC_RUN * MMC_THREADS)
+#define MMC_SEQ_BYTES (MMC_TILE + 32 + 48)
+struct MmTile {
+  int seq, npos;   /* sequence index, k-mer start positions in the tile */
+  long long start; /* first k-mer start position */
+};
+struct MmCandView { /* candidates of tile t: hash[t * cap + j], lp[t * cap + j] = (position - tile start) << 1 | (strand > 0), j < cnt[t] */
+  const uint64_t* hash;
+  const int* lp;
+  const int* cnt; /* -1 = the tile's region overflowed */
+  int cap;
+};
+
+WFB_DEV void mm_cand_tile(unsigned char* smem, const uint8_t* seqbuf, const MmSeq* seqs, const MmTile t, int tile_index, int k, uint64_t T, int cap,
+                          uint64_t* cand_hash, int* cand_lp, int* cand_cnt, unsigned long long* n_cand) {
+  uint8_t* sb = (uint8_t*)smem;
+  uint64_t* st_h = (uint64_t*)(smem + ((MMC_SEQ_BYTES + 15) & ~15));
+  int* st_lp = (int*)(st_h + MMC_TILE);
+  int* cnt = st_lp + MMC_TILE;
+  const long long g0 = seqs[t.seq].off + t.start; /* first byte of the tile in the (cleaned) buffer */
+  const int nbytes = t.npos + k - 1;
+#ifndef WFB_EMU
+  {
+    const long long a0 = g0 & ~(long long)15;
+    const int lead = (int)(g0 - a0);
+    const int nvec = (lead + nbytes + 15) >> 4;
+    for (int v = WFB_TID; v < nvec; v += WFB_NT) ((uint4*)sb)[v] = __ldg((const uint4*)(seqbuf + a0) + v);
+    sb += lead;
+  }
+#else
+  for (int i = 0; i < nbytes; ++i) sb[i] = seqbuf[g0 + i];
+#endif
+  WFB_SYNC();
+  const int nruns = (t.npos + MMC_RUN - 1) / MMC_RUN;
+  for (int r = WFB_TID; r < MMC_THREADS; r += WFB_NT) {
+    int c = 0;
+    if (r < nruns) {
+      const int p0 = r * MMC_RUN;
+      const int p1 = min(t.npos, p0 + MMC_RUN);
+      MmRoll roll;
+      mm_roll_init(roll, sb + p0, k);
+      /* the reference's ambiguity counter (:553-556) only sees an N at sequence index >= k-1: the k-mers holding that base are skipped */
+      int nbad = 0;
+      for (int j = 0; j < k; ++j) nbad += (sb[p0 + j] == 'N') && (t.start + p0 + j >= (long long)(k - 1));
+      for (int p = p0; p < p1; ++p) {
+        if (nbad == 0) {
+          const uint64_t hf = mm_murmur3_lo64(roll.f0, roll.f1, roll.f2, roll.f3, k), hb = mm_murmur3_lo64(roll.r0, roll.r1, roll.r2, roll.r3, k);
+          const uint64_t h = hf < hb ? hf : hb;
+          if (hf != hb && h <= T) {
+            st_h[p0 + c] = h;
+            st_lp[p0 + c] = (p << 1) | (hf < hb ? 1 : 0);
+            ++c;
+          }
+        }
+        if (p + 1 < p1) {
+          nbad += (sb[p + k] == 'N') - ((sb[p] == 'N') && (t.start + p >= (long long)(k - 1)));
+          mm_roll_step(roll, sb[p + k], k);
+        }
+      }
+    }
+    cnt[r] = c;
+  }
+  WFB_SYNC();
+  int total = 0;
+  for (int r = 0; r < MMC_THREADS; ++r) total += cnt[r]; /* every thread reads the same words: shared-memory broadcasts */
+  if (total <= cap) {
+    for (int r = WFB_TID; r < MMC_THREADS; r += WFB_NT) {
+      int off = 0;
+      for (int q = 0; q < r; ++q) off += cnt[q];
+      const int c = cnt[r];
+      for (int j = 0; j < c; ++j) {
+        cand_hash[(long long)tile_index * cap + off + j] = st_h[r * MMC_RUN + j];
+        cand_lp[(long long)tile_index * cap + off + j] = st_lp[r * MMC_RUN + j];
+      }
+    }
+  }
+  if (WFB_TID == 0) {
+    cand_cnt[tile_index] = total <= cap ? total : -1;
+    atomicAdd_compat(n_cand, (unsigned long long)total);
+  }
+  WFB_SYNC();
+}
+
+WFB_KERNEL_LB(mm_cand_kernel, MMC_THREADS, MMC_MINBLOCKS, const uint8_t* seqbuf, const MmSeq* seqs, const MmTile* tiles, int ntiles, int k, uint64_t T, int cap,
+              uint64_t* cand_hash, int* cand_lp, int* cand_cnt, unsigned long long* n_cand
+#ifdef WFB_EMU
+              , unsigned char* smem_emu
+#endif
+) {
   WFB_KERNEL_PROLOGUE
-  const int c = bid * WFB_NT + WFB_TID;
-  if (c >= nchunks) return;
+#ifndef WFB_EMU
+  __shared__ __align__(16) unsigned char smem[((MMC_SEQ_BYTES + 15) & ~15) + MMC_TILE * 12 + MMC_THREADS * 4];
+#else
+  unsigned char* smem = smem_emu;
+#endif
+  for (int i = bid; i < ntiles; i += nblocks) mm_cand_tile(smem, seqbuf, seqs, tiles[i], i, k, T, cap, cand_hash, cand_lp, cand_cnt, n_cand);
+}
+
+/* ---- the reference's loop state of one chunk ---- */
+struct MmRun {
+  MmArr<MmKmer> Q;
+  int qh, qn, qcap;
+  MmHeap H;
+  MmPool pool;
+  MmArr<MmWent> W;
+  int wn;
+  int k, w, s;
+  long long keep_from, body_win0, run_begin;
+  int seq, chunk;
+  MmRecord* out;
+  long long out_cap;
+  MmCounters* counters;
+  unsigned long long stale, overflow;
+  int shortfall; /* filtered run only: the sketch could not be kept at s entries from the candidates alone */
+};
+WFB_DEV void mm_emit(MmRun& R, long long i, const MmWent& e, long long wend) {
+  if (i < R.keep_from) return;
+  const unsigned long long idx = (unsigned long long)atomicAdd_compat(&R.counters->n_records, 1ULL);
+  if ((long long)idx < R.out_cap) {
+    MmRecord r;
+    r.hash = e.hash; r.wpos = e.wpos; r.wpos_end = wend; r.seq = R.seq; r.strand = e.strand;
+    r.chunk = R.chunk; r.inherited = (e.wpos < R.body_win0 && R.run_begin > 0) ? 1 : 0;
+    R.out[idx] = r;
+  } else R.overflow++;
+}
+
+/* One iteration of the reference's loop (:479-644) at k-mer start position i; `arrive` = a k-mer enters the window here (kk).
+ * FILT = the run only visits the positions where something happens (candidate arrivals, departures, the first fill). */
+template <bool FILT>
+WFB_DEV void mm_position(MmRun& R, const long long i, const bool arrive, const MmKmer kk) {
+  MmHeap& H = R.H;
+  MmPool& pool = R.pool;
+  const MmArr<MmWent>& W = R.W;
+  const int s = R.s;
+  const long long win = i + R.k - R.w; /* currentWindowId, :482 */
+  if (FILT ? (H.n >= H.cap) : (H.n > 2 * R.w)) { /* :485-495 (the filtered heap is small: it is purged when it is full) */
+    int m = 0;
+    for (int j = 0; j < H.n; ++j) if (!((long long)H.a[j].pos < win)) H.a[m++] = H.a[j];
+    H.n = m;
+    for (int j = H.n / 2 - 1; j >= 0; --j) mm_heap_sift_down(H, j);
+  }
+  /* leaving k-mer, :517-551 */
+  if (R.qn > 0 && (long long)R.Q[R.qh].pos < win) {
+    const MmKmer lv = R.Q[R.qh];
+    if (R.wn > 0 && lv.hash <= W[R.wn - 1].hash) {
+      const int lo = mm_lower_bound(W, R.wn, lv.hash);
+      if (lo < R.wn && W[lo].hash == lv.hash) {
+        MmWent& e = W[lo];
+        if (e.count == 1) {
+          mm_emit(R, i, e, win);
+          mm_went_clear(pool, e);
+          for (int j = lo; j + 1 < R.wn; ++j) W[j] = W[j + 1];
+          --R.wn;
+        } else {
+          if (e.strand - lv.strand == 0 || e.strand == 0) {
+            mm_emit(R, i, e, win);
+            e.wpos = win;
+          }
+          e.strand -= lv.strand;
+          mm_went_pop_front(pool, e);
+        }
+      }
+    }
+    R.qh = (R.qh + 1) % R.qcap;
+    --R.qn;
+  }
+  if (arrive) { /* :559-586 */
+    if (R.qn < R.qcap) { R.Q[(R.qh + R.qn) % R.qcap] = kk; ++R.qn; } else R.overflow++;
+    const int lo = mm_lower_bound(W, R.wn, kk.hash);
+    if (lo < R.wn && W[lo].hash == kk.hash) {
+      MmWent& e = W[lo];
+      if (!mm_went_push_back(pool, e, kk.pos, kk.strand)) R.overflow++;
+      if (e.strand + kk.strand == 0 || e.strand == 0) {
+        mm_emit(R, i, e, win);
+        e.wpos = win;
+      }
+      e.strand += kk.strand;
+    } else {
+      if (!mm_heap_push(H, kk)) R.overflow++;
+    }
+  }
+  if (win >= R.run_begin) { /* :593-643 (win >= 0 for a run from the sequence start) */
+    while (H.n > 0 && (long long)H.a[0].pos < win) mm_heap_pop(H);
+    if (R.wn > 0 && H.n > 0 && R.wn == s && H.a[0].hash < W[R.wn - 1].hash) {
+      MmWent& e = W[R.wn - 1];
+      mm_emit(R, i, e, win);
+      for (int n = e.head; n >= 0; n = pool.nodes[n].next)
+        if ((long long)pool.nodes[n].pos > win) {
+          MmKmer b;
+          b.hash = e.hash; b.pos = pool.nodes[n].pos; b.strand = pool.nodes[n].strand;
+          if (!mm_heap_push(H, b)) R.overflow++;
+        }
+      mm_went_clear(pool, e);
+      --R.wn;
+    }
+    while (H.n > 0 && R.wn < s) {
+      if ((long long)H.a[0].pos < win) { /* may empty the heap; a[0] stays readable, see :627-633 */
+        mm_heap_pop(H);
+        if (FILT) R.shortfall = 1; /* the reference's next front may be a k-mer the filter dropped */
+      }
+      const MmKmer nk = H.a[0];
+      const int lo = mm_lower_bound(W, R.wn, nk.hash);
+      if (!(lo < R.wn && W[lo].hash == nk.hash)) {
+        for (int j = R.wn; j > lo; --j) W[j] = W[j - 1];
+        ++R.wn;
+        W[lo].head = W[lo].tail = -1;
+        W[lo].count = 0;
+      }
+      W[lo].hash = nk.hash;
+      W[lo].wpos = win;
+      W[lo].strand = 0;
+      while (H.n > 0 && H.a[0].hash == nk.hash) {
+        if ((long long)H.a[0].pos < win) R.stale++; /* the reference absorbs expired entries too (:635-641) */
+        if (!mm_went_push_back(pool, W[lo], H.a[0].pos, H.a[0].strand)) R.overflow++;
+        W[lo].strand += H.a[0].strand;
+        mm_heap_pop(H);
+      }
+    }
+    if (FILT && R.wn < s) R.shortfall = 1; /* the reference would have filled the sketch from k-mers above the threshold */
+  }
+}
+
+/* One thread = one chunk. scratch layout per WARP (scratch_stride bytes per chunk, MM_LANES chunks per slab):
+ * Q[qcap][lanes] | heap[heap_cap][lanes] | pool[pool_cap][lanes] | W[s+2][lanes].
+ * FILT = false: every position of the chunk (the exact run; `redo` != NULL lists the chunks to run, c indexes it).
+ * FILT = true : only the candidates of mm_cand_kernel; a chunk that cannot vouch for its result sets chunk_flag[c] and is re-run
+ *               by the exact instantiation (its records, recognisable by their chunk id, are dropped by the post pass). */
+template <bool FILT>
+WFB_DEV void mm_stream_chunk(const int slot, const int c, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, const MmParams P,
+                             unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
+                             int* endcount, MmCounters* counters, const MmCandView CV, const int* seq_tile0, int* chunk_flag, int* redo_list) {
   const MmChunk ch = chunks[c];
   const MmSeq sq = seqs[ch.seq];
   const uint8_t* seq = seqbuf + sq.off;
   const long long len = sq.len;
   const int k = P.k, w = P.w, s = P.s;
-  const int lane = c % MM_LANES;
-  unsigned char* sp = scratch_all + (long long)(c / MM_LANES) * scratch_stride * MM_LANES;
-  const MmArr<MmKmer> Q{(MmKmer*)sp + lane};
-  MmHeap H;
-  H.a = MmArr<MmKmer>{(MmKmer*)(sp + sizeof(MmKmer) * (size_t)P.qcap * MM_LANES) + lane};
-  H.n = 0;
-  H.cap = P.heap_cap;
-  MmPool pool;
-  pool.nodes = MmArr<MmNode>{(MmNode*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) * MM_LANES) + lane};
-  const MmArr<MmWent> W{(MmWent*)(sp + (sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) + sizeof(MmNode) * (size_t)P.pool_cap) * MM_LANES) + lane};
-  for (int i = 0; i < P.pool_cap; ++i) pool.nodes[i].next = (i + 1 < P.pool_cap) ? i + 1 : -1;
-  pool.free_head = 0;
-  int qh = 0, qn = 0, wn = 0;
-  unsigned long long stale = 0, overflow = 0;
-  const long long run_begin = ch.run_begin, run_end = ch.body_end, keep_from = ch.body_begin;
-  const long long body_win0 = keep_from + k - w; /* window id of the first body step */
-  int ambig = 0;
-  if (run_begin > 0) { /* the counter a run from position 0 holds here (only N at index >= k-1 arm it, :553-556) */
-    for (long long j = run_begin + k - 2; j >= run_begin && j >= k - 1; --j)
-      if (seq[j] == 'N') { ambig = (int)(j - run_begin + 1); break; }
-  }
-#define MM_EMIT(E, WEND)                                                                             \
-  {                                                                                                  \
-    if (i >= keep_from) {                                                                            \
-      const unsigned long long idx_ = (unsigned long long)atomicAdd_compat(&counters->n_records, 1ULL); \
-      if ((long long)idx_ < out_cap) {                                                               \
-        MmRecord r_;                                                                                 \
-        r_.hash = (E).hash; r_.wpos = (E).wpos; r_.wpos_end = (WEND); r_.seq = ch.seq; r_.strand = (E).strand; \
-        r_.chunk = c; r_.inherited = ((E).wpos < body_win0 && run_begin > 0) ? 1 : 0;                \
-        out[idx_] = r_;                                                                              \
-      } else overflow++;                                                                             \
-    }                                                                                                \
-  }
-  long long i = run_begin;
-  MmRoll roll;
-  if (run_begin < run_end) mm_roll_init(roll, seq + run_begin, k);
-  for (; i < run_end; ++i) {
-    const long long win = i + k - w; /* currentWindowId, :482 */
-    if (H.n > 2 * w) { /* :485-495 */
-      int m = 0;
-      for (int j = 0; j < H.n; ++j) if (!((long long)H.a[j].pos < win)) H.a[m++] = H.a[j];
-      H.n = m;
-      for (int j = H.n / 2 - 1; j >= 0; --j) mm_heap_sift_down(H, j);
+  const int lane = slot % MM_LANES;
+  unsigned char* sp = scratch_all + (long long)(slot / MM_LANES) * scratch_stride * MM_LANES;
+  MmRun R;
+  R.Q = MmArr<MmKmer>{(MmKmer*)sp + lane};
+  R.H.a = MmArr<MmKmer>{(MmKmer*)(sp + sizeof(MmKmer) * (size_t)P.qcap * MM_LANES) + lane};
+  R.H.n = 0;
+  R.H.cap = P.heap_cap;
+  R.pool.nodes = MmArr<MmNode>{(MmNode*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) * MM_LANES) + lane};
+  R.W = MmArr<MmWent>{(MmWent*)(sp + (sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) + sizeof(MmNode) * (size_t)P.pool_cap) * MM_LANES) + lane};
+  for (int i = 0; i < P.pool_cap; ++i) R.pool.nodes[i].next = (i + 1 < P.pool_cap) ? i + 1 : -1;
+  R.pool.free_head = 0;
+  R.qh = 0; R.qn = 0; R.qcap = P.qcap; R.wn = 0;
+  R.k = k; R.w = w; R.s = s;
+  R.stale = 0; R.overflow = 0; R.shortfall = 0;
+  const long long run_begin = ch.run_begin, run_end = ch.body_end;
+  R.run_begin = run_begin; R.keep_from = ch.body_begin;
+  R.body_win0 = ch.body_begin + k - w; /* window id of the first body step */
+  R.seq = ch.seq; R.chunk = c; R.out = out; R.out_cap = out_cap; R.counters = counters;
+  if (!FILT) {
+    int ambig = 0;
+    if (run_begin > 0) { /* the counter a run from position 0 holds here (only N at index >= k-1 arm it, :553-556) */
+      for (long long j = run_begin + k - 2; j >= run_begin && j >= k - 1; --j)
+        if (seq[j] == 'N') { ambig = (int)(j - run_begin + 1); break; }
     }
-    const uint64_t hf = mm_murmur3_lo64(roll.f0, roll.f1, roll.f2, roll.f3, k), hb = mm_murmur3_lo64(roll.r0, roll.r1, roll.r2, roll.r3, k);
-    if (i + 1 < run_end) mm_roll_step(roll, seq[i + k], k);
-    const uint64_t cur = hf < hb ? hf : hb;
-    const int cur_strand = hf < hb ? 1 : -1;
-    /* leaving k-mer, :517-551 */
-    if (qn > 0 && (long long)Q[qh].pos < win) {
-      const MmKmer lv = Q[qh];
-      if (wn > 0 && lv.hash <= W[wn - 1].hash) {
-        const int lo = mm_lower_bound(W, wn, lv.hash);
-        if (lo < wn && W[lo].hash == lv.hash) {
-          MmWent& e = W[lo];
-          if (e.count == 1) {
-            MM_EMIT(e, win)
-            mm_went_clear(pool, e);
-            for (int j = lo; j + 1 < wn; ++j) W[j] = W[j + 1];
-            --wn;
-          } else {
-            if (e.strand - lv.strand == 0 || e.strand == 0) {
-              MM_EMIT(e, win)
-              e.wpos = win;
-            }
-            e.strand -= lv.strand;
-            mm_went_pop_front(pool, e);
-          }
-        }
-      }
-      qh = (qh + 1) % P.qcap;
-      --qn;
-    }
-    if (seq[i + k - 1] == 'N') ambig = k;
-    if (hb != hf && ambig == 0) {
+    MmRoll roll;
+    if (run_begin < run_end) mm_roll_init(roll, seq + run_begin, k);
+    for (long long i = run_begin; i < run_end; ++i) {
+      const uint64_t hf = mm_murmur3_lo64(roll.f0, roll.f1, roll.f2, roll.f3, k), hb = mm_murmur3_lo64(roll.r0, roll.r1, roll.r2, roll.r3, k);
+      if (i + 1 < run_end) mm_roll_step(roll, seq[i + k], k);
+      if (seq[i + k - 1] == 'N') ambig = k;
       MmKmer kk;
-      kk.hash = cur; kk.pos = (int)i; kk.strand = cur_strand;
-      if (qn < P.qcap) { Q[(qh + qn) % P.qcap] = kk; ++qn; } else overflow++;
-      const int lo = mm_lower_bound(W, wn, cur);
-      if (lo < wn && W[lo].hash == cur) {
-        MmWent& e = W[lo];
-        if (!mm_went_push_back(pool, e, (int)i, cur_strand)) overflow++;
-        if (e.strand + cur_strand == 0 || e.strand == 0) {
-          MM_EMIT(e, win)
-          e.wpos = win;
-        }
-        e.strand += cur_strand;
-      } else {
-        if (!mm_heap_push(H, kk)) overflow++;
+      kk.hash = hf < hb ? hf : hb; kk.pos = (int)i; kk.strand = hf < hb ? 1 : -1;
+      mm_position<false>(R, i, hb != hf && ambig == 0, kk);
+      if (ambig > 0) --ambig;
+    }
+  } else {
+    /* cursor over the candidates of the tiles that cover [run_begin, run_end) */
+    long long tile = (long long)seq_tile0[ch.seq] + run_begin / MMC_TILE;
+    const long long tile_end = (long long)seq_tile0[ch.seq] + (run_end + MMC_TILE - 1) / MMC_TILE;
+    long long tpos0 = run_begin / MMC_TILE * MMC_TILE;
+    bool bad = false;
+    for (long long t = tile; t < tile_end; ++t) bad = bad || CV.cnt[t] < 0;
+    int j = 0, n = (tile < tile_end && !bad) ? CV.cnt[tile] : 0;
+    const long long NONE = LLONG_MAX;
+    long long nc = NONE;
+    int nc_strand = 0;
+    uint64_t nc_hash = 0;
+#define MM_CAND_FETCH()                                                               \
+    {                                                                                 \
+      nc = NONE;                                                                      \
+      while (tile < tile_end) {                                                       \
+        if (j < n) {                                                                  \
+          const int lp_ = CV.lp[tile * CV.cap + j];                                   \
+          nc = tpos0 + (lp_ >> 1);                                                    \
+          nc_strand = (lp_ & 1) ? 1 : -1;                                             \
+          nc_hash = CV.hash[tile * CV.cap + j];                                       \
+          ++j;                                                                        \
+          break;                                                                      \
+        }                                                                             \
+        ++tile; tpos0 += MMC_TILE; j = 0;                                             \
+        n = tile < tile_end ? CV.cnt[tile] : 0;                                       \
+      }                                                                               \
+    }
+    if (!bad) {
+      MM_CAND_FETCH()
+      while (nc != NONE && nc < run_begin) MM_CAND_FETCH()
+      const long long i0 = run_begin + w - k; /* the first step that fills the sketch (its window id is every entry's start) */
+      bool did_i0 = false;
+      for (;;) {
+        const long long nl = R.qn > 0 ? (long long)R.Q[R.qh].pos + (w - k + 1) : NONE;
+        long long i = nc < nl ? nc : nl;
+        if (!did_i0 && i0 <= i) { i = i0; did_i0 = true; }
+        if (i >= run_end) break;
+        const bool arrive = i == nc;
+        MmKmer kk;
+        kk.hash = nc_hash; kk.pos = (int)i; kk.strand = nc_strand;
+        mm_position<true>(R, i, arrive, kk);
+        if (arrive) MM_CAND_FETCH()
+        if (R.shortfall | (R.overflow != 0) | (R.stale != 0)) break;
       }
     }
-    if (ambig > 0) --ambig;
-    if (win >= run_begin) { /* :593-643 (win >= 0 for a run from the sequence start) */
-      while (H.n > 0 && (long long)H.a[0].pos < win) mm_heap_pop(H);
-      if (wn > 0 && H.n > 0 && wn == s && H.a[0].hash < W[wn - 1].hash) {
-        MmWent& e = W[wn - 1];
-        MM_EMIT(e, win)
-        for (int n = e.head; n >= 0; n = pool.nodes[n].next)
-          if ((long long)pool.nodes[n].pos > win) {
-            MmKmer kk;
-            kk.hash = e.hash; kk.pos = pool.nodes[n].pos; kk.strand = pool.nodes[n].strand;
-            if (!mm_heap_push(H, kk)) overflow++;
-          }
-        mm_went_clear(pool, e);
-        --wn;
-      }
-      while (H.n > 0 && wn < s) {
-        if ((long long)H.a[0].pos < win) mm_heap_pop(H); /* may empty the heap; a[0] stays readable, see :627-633 */
-        const MmKmer nk = H.a[0];
-        const int lo = mm_lower_bound(W, wn, nk.hash);
-        if (!(lo < wn && W[lo].hash == nk.hash)) {
-          for (int j = wn; j > lo; --j) W[j] = W[j - 1];
-          ++wn;
-          W[lo].head = W[lo].tail = -1;
-          W[lo].count = 0;
-        }
-        W[lo].hash = nk.hash;
-        W[lo].wpos = win;
-        W[lo].strand = 0;
-        while (H.n > 0 && H.a[0].hash == nk.hash) {
-          if ((long long)H.a[0].pos < win) stale++; /* the reference absorbs expired entries too (:635-641) */
-          if (!mm_went_push_back(pool, W[lo], H.a[0].pos, H.a[0].strand)) overflow++;
-          W[lo].strand += H.a[0].strand;
-          mm_heap_pop(H);
-        }
-      }
+#undef MM_CAND_FETCH
+    if (bad || R.shortfall || R.overflow || R.stale) { /* the exact instantiation re-runs this chunk */
+      chunk_flag[c] = 1;
+      redo_list[atomicAdd_compat(&counters->flagged, 1ULL)] = c;
+      endcount[c] = 0;
+      return;
     }
   }
   /* membership at the end of the body, for the stitch of the next chunk */
   {
     MmEndEnt* es = endstate + (long long)c * s;
-    for (int j = 0; j < wn && j < s; ++j) {
-      es[j].hash = W[j].hash;
-      es[j].wpos = W[j].wpos;
-      es[j].inherited = (W[j].wpos < body_win0 && run_begin > 0) ? 1 : 0;
+    for (int j = 0; j < R.wn && j < s; ++j) {
+      es[j].hash = R.W[j].hash;
+      es[j].wpos = R.W[j].wpos;
+      es[j].inherited = (R.W[j].wpos < R.body_win0 && run_begin > 0) ? 1 : 0;
       es[j].pad_ = 0;
     }
-    endcount[c] = wn < s ? wn : s;
+    endcount[c] = R.wn < s ? R.wn : s;
   }
   /* :646-658: still-open members are closed at len - k + 1 */
   if (ch.last_of_seq) {
-    i = run_end; /* emissions of the flush count as body emissions */
-    for (int j = 0; j < wn && j < s; ++j)
-      if (W[j].wpos != -1) MM_EMIT(W[j], len - k + 1)
+    for (int j = 0; j < R.wn && j < s; ++j)
+      if (R.W[j].wpos != -1) mm_emit(R, run_end, R.W[j], len - k + 1); /* emissions of the flush count as body emissions */
   }
-#undef MM_EMIT
-  if (stale) atomicAdd_compat(&counters->stale_absorbed, stale);
-  if (overflow) atomicAdd_compat(&counters->overflow, overflow);
+  if (R.stale) atomicAdd_compat(&counters->stale_absorbed, R.stale);
+  if (R.overflow) atomicAdd_compat(&counters->overflow, R.overflow);
+}
+
+WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P,
+           unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
+           int* endcount, MmCounters* counters, const int* redo) {
+  WFB_KERNEL_PROLOGUE
+  const int t = bid * WFB_NT + WFB_TID;
+  if (t >= nchunks) return;
+  MmCandView none;
+  none.hash = nullptr; none.lp = nullptr; none.cnt = nullptr; none.cap = 0;
+  mm_stream_chunk<false>(t, redo ? redo[t] : t, seqbuf, seqs, chunks, P, scratch_all, scratch_stride, out, out_cap, endstate, endcount, counters,
+                         none, nullptr, nullptr, nullptr);
+}
+WFB_KERNEL(mm_stream_cand_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P,
+           unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
+           int* endcount, MmCounters* counters, MmCandView CV, const int* seq_tile0, int* chunk_flag, int* redo_list) {
+  WFB_KERNEL_PROLOGUE
+  const int t = bid * WFB_NT + WFB_TID;
+  if (t >= nchunks) return;
+  mm_stream_chunk<true>(t, t, seqbuf, seqs, chunks, P, scratch_all, scratch_stride, out, out_cap, endstate, endcount, counters, CV, seq_tile0,
+                        chunk_flag, redo_list);
 }
 
 /* Stitch 1: resolve the true interval starts of the chunk end states (each end state has <= s entries sorted by hash),
@@ -454,11 +679,12 @@ WFB_KERNEL(mm_stitch_ends_pass_kernel, const MmChunk* chunks, int nchunks, int s
 
 /* Stitch 2: records that inherited their start take it from the previous chunk's (resolved) end state. */
 WFB_KERNEL(mm_stitch_records_kernel, MmRecord* recs, long long nrec, const MmChunk* chunks, int s, const MmEndEnt* endstate,
-           const int* endcount, MmCounters* counters) {
+           const int* endcount, MmCounters* counters, const int* chunk_flag, long long nrec_filtered) {
   WFB_KERNEL_PROLOGUE
   for (long long r = (long long)bid * WFB_NT + WFB_TID; r < nrec; r += (long long)nblocks * WFB_NT) {
     if (!recs[r].inherited) continue;
     const int c = recs[r].chunk;
+    if (r < nrec_filtered && chunk_flag[c]) continue; /* written by a filtered run that gave up: dropped by the post pass */
     if (chunks[c].first_of_seq) continue;
     const MmEndEnt* prev = endstate + (long long)(c - 1) * s;
     const int np = endcount[c - 1];

@@ -260,6 +260,9 @@ typedef struct {
   uint64_t filtered;       /* 1 = candidate-filtered build: only k-mers below a hash threshold entered the window machine */
   uint64_t candidates;     /* ... how many of them (all sequences)                                                       */
   uint64_t redo_chunks;    /* ... chunks whose filtered run could not vouch for its result and were re-run over every k-mer */
+  double cand_kernel_ms;     /* filtered build: CUDA-event time of the cleaning + candidate kernels ...  */
+  double filtered_stream_ms; /* ... of the window machine over the candidate stream ...                  */
+  double redo_ms;            /* ... of the exact re-run of the flagged chunks (all three inside stream_kernel_ms) */
 } wfb_minmer_stats_t;
 
 /* seq_ptrs[i] / seq_lens[i] : raw FASTA bases of target i (any case); seq_ids[i] -> MinmerInfo::seqId.

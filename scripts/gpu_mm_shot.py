@@ -29,8 +29,9 @@ ids = list(range(len(seqs)))
 base = None
 modes = [("unfiltered", {"WFB_MM_FILTER": "0"}), ("filtered", {"WFB_MM_FILTER": "1"}), ("filtered", {"WFB_MM_FILTER": "1"}),
          ("unfiltered", {"WFB_MM_FILTER": "0"}),
+         ("filtered-redo-global", {"WFB_MM_FILTER": "1", "WFB_MM_REDO_SMEM": "0"}),
          ("filtered-chunk256", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "256"}), ("filtered-chunk1024", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "1024"}),
-         ("filtered-chunk2048", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "2048"}),
+         ("filtered-chunk384", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "384"}), ("filtered-chunk768", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "768"}),
          ("filtered-overflow", {"WFB_MM_FILTER": "1", "WFB_MM_CAND_CAP": "150"})]
 for mode, env in modes:
     os.environ.update(env)
@@ -50,7 +51,7 @@ for mode, env in modes:
     print(json.dumps(r), flush=True)
     flush()
 
-for mode, env in (("default", {}), ("unfiltered", {"WFB_MM_FILTER": "0"})):
+for mode, env in (("default", {}),):
     os.environ.update(env)
     try:
         for rep in range(2):

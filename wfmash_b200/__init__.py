@@ -279,7 +279,8 @@ class MinmerStats(ctypes.Structure):
     _fields_ = [("stream_kernel_ms", ctypes.c_double), ("total_kernel_ms", ctypes.c_double), ("bases", ctypes.c_uint64),
                 ("raw_records", ctypes.c_uint64), ("chunks", ctypes.c_uint64), ("stale_absorbed", ctypes.c_uint64),
                 ("stitch_miss", ctypes.c_uint64), ("filtered", ctypes.c_uint64), ("candidates", ctypes.c_uint64),
-                ("redo_chunks", ctypes.c_uint64)]
+                ("redo_chunks", ctypes.c_uint64), ("cand_kernel_ms", ctypes.c_double), ("filtered_stream_ms", ctypes.c_double),
+                ("redo_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -226,7 +226,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   size_t tmp_bytes = 0;
   uint8_t* h_seq = nullptr;
   MmCounters hc;
-  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, ec = nullptr, ef = nullptr; /* ec: candidates done, ef: filtered stream done */
   long long nrec = 0, nfin = 0, nout = 0;
   const int TPB = 64;
   std::vector<long long> tmpll(2);
@@ -257,6 +257,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   MM_CHECK(cudaMalloc(&d_cnt, sizeof(MmCounters)));
   MM_CHECK(cudaMemset(d_cnt, 0, sizeof(MmCounters)));
   MM_CHECK(cudaEventCreate(&e0)); MM_CHECK(cudaEventCreate(&e1)); MM_CHECK(cudaEventCreate(&e2));
+  MM_CHECK(cudaEventCreate(&ec)); MM_CHECK(cudaEventCreate(&ef));
   MM_CHECK(cudaMemcpy(d_seq, h_seq, (size_t)total, cudaMemcpyHostToDevice));
   MM_CHECK(cudaMemcpy(d_seqs, seqs.data(), sizeof(MmSeq) * ns, cudaMemcpyHostToDevice));
   MM_CHECK(cudaMemcpy(d_chunks, chunks.data(), sizeof(MmChunk) * (size_t)nchunks, cudaMemcpyHostToDevice));
@@ -266,16 +267,27 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     CV.hash = d_cand_hash; CV.lp = d_cand_lp; CV.cnt = d_cand_cnt; CV.cap = cand_cap;
     MM_LAUNCH(mm_cand_kernel, std::min(ntiles, 148 * MMC_MINBLOCKS), MMC_THREADS, d_seq, d_seqs, d_tiles, ntiles, k, T, cand_cap, d_cand_hash, d_cand_lp,
               d_cand_cnt, &d_cnt->candidates);
+    MM_CHECK(cudaEventRecord(ec));
     MM_LAUNCH(mm_stream_cand_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, PF, d_scratch, scratch_stride_f, d_rec,
               rec_cap, d_end, d_endcount, d_cnt, CV, d_tile0, d_flag, d_redo);
     MM_CHECK(cudaMemcpy(&hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost));
     nrec_filtered = (long long)std::min<unsigned long long>(hc.n_records, (unsigned long long)rec_cap);
     n_redo = (long long)hc.flagged;
+    MM_CHECK(cudaEventRecord(ef));
     if (n_redo > 0) { /* exact re-run of the chunks whose filtered run gave up (short windows around N runs, capacity) */
-      cudaFree(d_scratch); d_scratch = nullptr;
-      MM_CHECK(cudaMalloc(&d_scratch, (size_t)scratch_stride * (((size_t)n_redo + MM_LANES - 1) / MM_LANES * MM_LANES)));
-      MM_LAUNCH(mm_stream_kernel, (int)((n_redo + TPB - 1) / TPB), TPB, d_seq, d_seqs, d_chunks, (int)n_redo, P, d_scratch, scratch_stride, d_rec,
-                rec_cap, d_end, d_endcount, d_cnt, d_redo);
+      int redo_smem = 1; /* few chunks: one CTA each, containers in shared memory; many (every tile overflowed): the global slabs */
+      { const char* e = getenv("WFB_MM_REDO_SMEM"); if (e && *e) redo_smem = atoi(e) != 0; }
+      if (redo_smem && scratch_stride <= 200 * 1024 && n_redo <= 148 * 64) {
+        MM_CHECK(cudaFuncSetAttribute(mm_stream_redo_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch_stride));
+        mm_stream_redo_smem_kernel<<<(int)n_redo, 32, (size_t)scratch_stride>>>(d_seq, d_seqs, d_chunks, (int)n_redo, P, scratch_stride, d_rec, rec_cap,
+                                                                                 d_end, d_endcount, d_cnt, d_redo);
+        wfb_count_launch_();
+      } else {
+        cudaFree(d_scratch); d_scratch = nullptr;
+        MM_CHECK(cudaMalloc(&d_scratch, (size_t)scratch_stride * (((size_t)n_redo + MM_LANES - 1) / MM_LANES * MM_LANES)));
+        MM_LAUNCH(mm_stream_kernel, (int)((n_redo + TPB - 1) / TPB), TPB, d_seq, d_seqs, d_chunks, (int)n_redo, P, d_scratch, scratch_stride, d_rec,
+                  rec_cap, d_end, d_endcount, d_cnt, d_redo);
+      }
     }
   } else {
     MM_LAUNCH(mm_stream_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, P, d_scratch, scratch_stride, d_rec,
@@ -356,6 +368,11 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     cudaEventElapsedTime(&a, e0, e1);
     cudaEventElapsedTime(&b, e0, e2);
     stats->stream_kernel_ms = a; stats->total_kernel_ms = b;
+    if (use_filter) {
+      float c1 = 0, c2 = 0, c3 = 0;
+      cudaEventElapsedTime(&c1, e0, ec); cudaEventElapsedTime(&c2, ec, ef); cudaEventElapsedTime(&c3, ef, e1);
+      stats->cand_kernel_ms = c1; stats->filtered_stream_ms = c2; stats->redo_ms = c3;
+    }
     stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed;
     stats->stitch_miss = hc.stitch_miss; stats->bases = 0;
     stats->candidates = hc.candidates; stats->redo_chunks = (uint64_t)n_redo; stats->filtered = (uint64_t)use_filter;
@@ -365,7 +382,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   if (nout > out_cap) { wfb_set_last_error_("minmer output buffer too small"); rc = WFB_ECAP; goto done; }
   if (nout > 0) MM_CHECK(cudaMemcpy(out, d_out, sizeof(wfb_minmer_t) * (size_t)nout, cudaMemcpyDeviceToHost));
 done:
-  if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2);
+  if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2); if (ec) cudaEventDestroy(ec); if (ef) cudaEventDestroy(ef);
   cudaFree(d_seq); cudaFree(d_seqs); cudaFree(d_chunks); cudaFree(d_scratch); cudaFree(d_rec); cudaFree(d_end); cudaFree(d_endcount);
   cudaFree(d_cnt); cudaFree(d_pieces); cudaFree(d_offs); cudaFree(d_fin); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_perm);
   cudaFree(d_perm2); cudaFree(d_keep); cudaFree(d_out); cudaFree(d_tmp);
@@ -398,9 +415,10 @@ done:
                             scratch_stride_f, rec.data(), rec_cap, endst.data(), endcount.data(), &hc, CV, seq_tile0.data(), flag.data(), redo.data());
     nrec_filtered = (long long)std::min<unsigned long long>(hc.n_records, (unsigned long long)rec_cap);
     n_redo = (long long)hc.flagged;
-    for (long long c = 0; c < n_redo; ++c)
+    for (long long c = 0; c < n_redo; ++c) {
       mm_stream_kernel((int)c, (int)n_redo, buf.data(), seqs.data(), chunks.data(), (int)n_redo, P, scratch.data() - c * scratch_stride, scratch_stride,
                        rec.data(), rec_cap, endst.data(), endcount.data(), &hc, redo.data());
+    }
   } else {
     for (int c = 0; c < nchunks; ++c) /* scratch reused: chunk c uses slot 0 */
       mm_stream_kernel(c, nchunks, buf.data(), seqs.data(), chunks.data(), nchunks, P, scratch.data() - (long long)c * scratch_stride,

@@ -176,17 +176,19 @@ WFB_DEV void mm_roll_step(MmRoll& R, uint8_t in, int k) { /* k-mer at i -> k-mer
 #else
 #define MM_LANES 32
 #endif
-template <class T>
+template <class T, int L> /* L = lane stride: MM_LANES in an interleaved global slab, 1 in a private (shared-memory) one */
 struct MmArr {
   T* p; /* this lane's element 0 */
-  WFB_DEV_MEMBER T& operator[](long long i) const { return p[i * MM_LANES]; }
+  WFB_DEV_MEMBER T& operator[](long long i) const { return p[i * L]; }
 };
+template <int L>
 struct MmHeap {
-  MmArr<MmKmer> a;
+  MmArr<MmKmer, L> a;
   int n, cap;
 };
 WFB_DEV bool mm_less(const MmKmer& x, const MmKmer& y) { return x.hash < y.hash || (x.hash == y.hash && x.pos < y.pos); }
-WFB_DEV bool mm_heap_push(MmHeap& h, const MmKmer& v) {
+template <int L>
+WFB_DEV bool mm_heap_push(MmHeap<L>& h, const MmKmer& v) {
   if (h.n >= h.cap) return false;
   int i = h.n++;
   while (i > 0) {
@@ -198,7 +200,8 @@ WFB_DEV bool mm_heap_push(MmHeap& h, const MmKmer& v) {
   h.a[i] = v;
   return true;
 }
-WFB_DEV void mm_heap_sift_down(MmHeap& h, int i) {
+template <int L>
+WFB_DEV void mm_heap_sift_down(MmHeap<L>& h, int i) {
   const MmKmer v = h.a[i];
   for (;;) {
     int c = 2 * i + 1;
@@ -210,7 +213,8 @@ WFB_DEV void mm_heap_sift_down(MmHeap& h, int i) {
   }
   h.a[i] = v;
 }
-WFB_DEV void mm_heap_pop(MmHeap& h) { /* leaves the popped element readable in a[0] when the heap empties */
+template <int L>
+WFB_DEV void mm_heap_pop(MmHeap<L>& h) { /* leaves the popped element readable in a[0] when the heap empties */
   --h.n;
   if (h.n > 0) {
     h.a[0] = h.a[h.n];
@@ -218,17 +222,21 @@ WFB_DEV void mm_heap_pop(MmHeap& h) { /* leaves the popped element readable in a
   }
 }
 
+template <int L>
 struct MmPool {
-  MmArr<MmNode> nodes;
+  MmArr<MmNode, L> nodes;
   int free_head;
 };
-WFB_DEV int mm_pool_alloc(MmPool& p) {
+template <int L>
+WFB_DEV int mm_pool_alloc(MmPool<L>& p) {
   const int i = p.free_head;
   if (i >= 0) p.free_head = p.nodes[i].next;
   return i;
 }
-WFB_DEV void mm_pool_free(MmPool& p, int i) { p.nodes[i].next = p.free_head; p.free_head = i; }
-WFB_DEV bool mm_went_push_back(MmPool& p, MmWent& e, int pos, int strand) {
+template <int L>
+WFB_DEV void mm_pool_free(MmPool<L>& p, int i) { p.nodes[i].next = p.free_head; p.free_head = i; }
+template <int L>
+WFB_DEV bool mm_went_push_back(MmPool<L>& p, MmWent& e, int pos, int strand) {
   const int n = mm_pool_alloc(p);
   if (n < 0) return false;
   p.nodes[n].pos = pos; p.nodes[n].strand = strand; p.nodes[n].next = -1;
@@ -237,16 +245,19 @@ WFB_DEV bool mm_went_push_back(MmPool& p, MmWent& e, int pos, int strand) {
   e.count++;
   return true;
 }
-WFB_DEV void mm_went_pop_front(MmPool& p, MmWent& e) {
+template <int L>
+WFB_DEV void mm_went_pop_front(MmPool<L>& p, MmWent& e) {
   const int n = e.head;
   e.head = p.nodes[n].next;
   if (e.head < 0) e.tail = -1;
   e.count--;
   mm_pool_free(p, n);
 }
-WFB_DEV void mm_went_clear(MmPool& p, MmWent& e) { while (e.head >= 0) mm_went_pop_front(p, e); }
+template <int L>
+WFB_DEV void mm_went_clear(MmPool<L>& p, MmWent& e) { while (e.head >= 0) mm_went_pop_front(p, e); }
 
-WFB_DEV int mm_lower_bound(const MmArr<MmWent>& W, int wn, uint64_t h) {
+template <int L>
+WFB_DEV int mm_lower_bound(const MmArr<MmWent, L>& W, int wn, uint64_t h) {
   int lo = 0, hi = wn;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -374,12 +385,13 @@ WFB_KERNEL_LB(mm_cand_kernel, MMC_THREADS, MMC_MINBLOCKS, const uint8_t* seqbuf,
 }
 
 /* ---- the reference's loop state of one chunk ---- */
+template <int L>
 struct MmRun {
-  MmArr<MmKmer> Q;
+  MmArr<MmKmer, L> Q;
   int qh, qn, qcap;
-  MmHeap H;
-  MmPool pool;
-  MmArr<MmWent> W;
+  MmHeap<L> H;
+  MmPool<L> pool;
+  MmArr<MmWent, L> W;
   int wn;
   int k, w, s;
   long long keep_from, body_win0, run_begin;
@@ -390,7 +402,8 @@ struct MmRun {
   unsigned long long stale, overflow;
   int shortfall; /* filtered run only: the sketch could not be kept at s entries from the candidates alone */
 };
-WFB_DEV void mm_emit(MmRun& R, long long i, const MmWent& e, long long wend) {
+template <int L>
+WFB_DEV void mm_emit(MmRun<L>& R, long long i, const MmWent& e, long long wend) {
   if (i < R.keep_from) return;
   const unsigned long long idx = (unsigned long long)atomicAdd_compat(&R.counters->n_records, 1ULL);
   if ((long long)idx < R.out_cap) {
@@ -403,11 +416,11 @@ WFB_DEV void mm_emit(MmRun& R, long long i, const MmWent& e, long long wend) {
 
 /* One iteration of the reference's loop (:479-644) at k-mer start position i; `arrive` = a k-mer enters the window here (kk).
  * FILT = the run only visits the positions where something happens (candidate arrivals, departures, the first fill). */
-template <bool FILT>
-WFB_DEV void mm_position(MmRun& R, const long long i, const bool arrive, const MmKmer kk) {
-  MmHeap& H = R.H;
-  MmPool& pool = R.pool;
-  const MmArr<MmWent>& W = R.W;
+template <bool FILT, int L>
+WFB_DEV void mm_position(MmRun<L>& R, const long long i, const bool arrive, const MmKmer kk) {
+  MmHeap<L>& H = R.H;
+  MmPool<L>& pool = R.pool;
+  const MmArr<MmWent, L>& W = R.W;
   const int s = R.s;
   const long long win = i + R.k - R.w; /* currentWindowId, :482 */
   if (FILT ? (H.n >= H.cap) : (H.n > 2 * R.w)) { /* :485-495 (the filtered heap is small: it is purged when it is full) */
@@ -502,7 +515,7 @@ WFB_DEV void mm_position(MmRun& R, const long long i, const bool arrive, const M
  * FILT = false: every position of the chunk (the exact run; `redo` != NULL lists the chunks to run, c indexes it).
  * FILT = true : only the candidates of mm_cand_kernel; a chunk that cannot vouch for its result sets chunk_flag[c] and is re-run
  *               by the exact instantiation (its records, recognisable by their chunk id, are dropped by the post pass). */
-template <bool FILT>
+template <bool FILT, int L>
 WFB_DEV void mm_stream_chunk(const int slot, const int c, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, const MmParams P,
                              unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
                              int* endcount, MmCounters* counters, const MmCandView CV, const int* seq_tile0, int* chunk_flag, int* redo_list) {
@@ -511,15 +524,15 @@ WFB_DEV void mm_stream_chunk(const int slot, const int c, const uint8_t* seqbuf,
   const uint8_t* seq = seqbuf + sq.off;
   const long long len = sq.len;
   const int k = P.k, w = P.w, s = P.s;
-  const int lane = slot % MM_LANES;
-  unsigned char* sp = scratch_all + (long long)(slot / MM_LANES) * scratch_stride * MM_LANES;
-  MmRun R;
-  R.Q = MmArr<MmKmer>{(MmKmer*)sp + lane};
-  R.H.a = MmArr<MmKmer>{(MmKmer*)(sp + sizeof(MmKmer) * (size_t)P.qcap * MM_LANES) + lane};
+  const int lane = slot % L;
+  unsigned char* sp = scratch_all + (long long)(slot / L) * scratch_stride * L;
+  MmRun<L> R;
+  R.Q = MmArr<MmKmer, L>{(MmKmer*)sp + lane};
+  R.H.a = MmArr<MmKmer, L>{(MmKmer*)(sp + sizeof(MmKmer) * (size_t)P.qcap * L) + lane};
   R.H.n = 0;
   R.H.cap = P.heap_cap;
-  R.pool.nodes = MmArr<MmNode>{(MmNode*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) * MM_LANES) + lane};
-  R.W = MmArr<MmWent>{(MmWent*)(sp + (sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) + sizeof(MmNode) * (size_t)P.pool_cap) * MM_LANES) + lane};
+  R.pool.nodes = MmArr<MmNode, L>{(MmNode*)(sp + sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) * L) + lane};
+  R.W = MmArr<MmWent, L>{(MmWent*)(sp + (sizeof(MmKmer) * ((size_t)P.qcap + P.heap_cap) + sizeof(MmNode) * (size_t)P.pool_cap) * L) + lane};
   for (int i = 0; i < P.pool_cap; ++i) R.pool.nodes[i].next = (i + 1 < P.pool_cap) ? i + 1 : -1;
   R.pool.free_head = 0;
   R.qh = 0; R.qn = 0; R.qcap = P.qcap; R.wn = 0;
@@ -628,16 +641,31 @@ WFB_KERNEL(mm_stream_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmC
   if (t >= nchunks) return;
   MmCandView none;
   none.hash = nullptr; none.lp = nullptr; none.cnt = nullptr; none.cap = 0;
-  mm_stream_chunk<false>(t, redo ? redo[t] : t, seqbuf, seqs, chunks, P, scratch_all, scratch_stride, out, out_cap, endstate, endcount, counters,
+  mm_stream_chunk<false, MM_LANES>(t, redo ? redo[t] : t, seqbuf, seqs, chunks, P, scratch_all, scratch_stride, out, out_cap, endstate, endcount, counters,
                          none, nullptr, nullptr, nullptr);
 }
+#ifndef WFB_EMU
+/* The exact re-run of the few chunks a filtered run flagged: a lone thread walking 1500 positions with its containers in global
+ * memory is a chain of ~40 dependent L2 round trips per position (the whole build waited ~20 ms for 355 such threads). One CTA per
+ * chunk, its containers private in dynamic shared memory (lane stride 1), one working thread. */
+__global__ void __launch_bounds__(32, 1) mm_stream_redo_smem_kernel(const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nredo, MmParams P,
+                                                                    long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
+                                                                    int* endcount, MmCounters* counters, const int* redo) {
+  extern __shared__ __align__(16) unsigned char mm_redo_smem[];
+  if (threadIdx.x != 0 || (int)blockIdx.x >= nredo) return;
+  MmCandView none;
+  none.hash = nullptr; none.lp = nullptr; none.cnt = nullptr; none.cap = 0;
+  mm_stream_chunk<false, 1>(0, redo[blockIdx.x], seqbuf, seqs, chunks, P, mm_redo_smem, scratch_stride, out, out_cap, endstate, endcount, counters,
+                            none, nullptr, nullptr, nullptr);
+}
+#endif
 WFB_KERNEL(mm_stream_cand_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P,
            unsigned char* scratch_all, long long scratch_stride, MmRecord* out, long long out_cap, MmEndEnt* endstate,
            int* endcount, MmCounters* counters, MmCandView CV, const int* seq_tile0, int* chunk_flag, int* redo_list) {
   WFB_KERNEL_PROLOGUE
   const int t = bid * WFB_NT + WFB_TID;
   if (t >= nchunks) return;
-  mm_stream_chunk<true>(t, t, seqbuf, seqs, chunks, P, scratch_all, scratch_stride, out, out_cap, endstate, endcount, counters, CV, seq_tile0,
+  mm_stream_chunk<true, MM_LANES>(t, t, seqbuf, seqs, chunks, P, scratch_all, scratch_stride, out, out_cap, endstate, endcount, counters, CV, seq_tile0,
                         chunk_flag, redo_list);
 }
 

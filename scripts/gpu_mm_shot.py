@@ -27,12 +27,18 @@ def flush():
 seqs = [x for _, x in datasets.load("yeast")]
 ids = list(range(len(seqs)))
 base = None
-modes = [("unfiltered", {"WFB_MM_FILTER": "0"}), ("filtered", {"WFB_MM_FILTER": "1"}), ("filtered", {"WFB_MM_FILTER": "1"}),
-         ("unfiltered", {"WFB_MM_FILTER": "0"}),
-         ("filtered-redo-global", {"WFB_MM_FILTER": "1", "WFB_MM_REDO_SMEM": "0"}),
-         ("filtered-chunk256", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "256"}), ("filtered-chunk1024", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "1024"}),
-         ("filtered-chunk384", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "384"}), ("filtered-chunk768", {"WFB_MM_FILTER": "1", "WFB_MM_FCHUNK": "768"}),
-         ("filtered-overflow", {"WFB_MM_FILTER": "1", "WFB_MM_CAND_CAP": "150"})]
+F = {"WFB_MM_FILTER": "1"}
+modes = [("unfiltered", {"WFB_MM_FILTER": "0"}),
+         ("filtered-1024", dict(F, WFB_MM_FCHUNK="1024")), ("filtered-1024", dict(F, WFB_MM_FCHUNK="1024")),
+         ("filtered-1024-lcur", dict(F, WFB_MM_FCHUNK="1024", WFB_MM_LCUR="1")),
+         ("filtered-1024-lcur-smem", dict(F, WFB_MM_FCHUNK="1024", WFB_MM_LCUR="1", WFB_MM_FSMEM="1")),
+         ("filtered-512-lcur-smem", dict(F, WFB_MM_FCHUNK="512", WFB_MM_LCUR="1", WFB_MM_FSMEM="1")),
+         ("filtered-2048-lcur-smem", dict(F, WFB_MM_FCHUNK="2048", WFB_MM_LCUR="1", WFB_MM_FSMEM="1")),
+         ("filtered-4096-lcur-smem", dict(F, WFB_MM_FCHUNK="4096", WFB_MM_LCUR="1", WFB_MM_FSMEM="1")),
+         ("filtered-1536-lcur", dict(F, WFB_MM_FCHUNK="1536", WFB_MM_LCUR="1")),
+         ("filtered-2048-lcur", dict(F, WFB_MM_FCHUNK="2048", WFB_MM_LCUR="1"))]
+if len(sys.argv) > 2 and sys.argv[2] == "ncu":  # the two candidate defaults only, once each, no mapping phase (run under ncu)
+    modes = [modes[3], modes[4]]
 for mode, env in modes:
     os.environ.update(env)
     try:
@@ -51,7 +57,7 @@ for mode, env in modes:
     print(json.dumps(r), flush=True)
     flush()
 
-for mode, env in (("default", {}),):
+for mode, env in ((("default", {}),) if not (len(sys.argv) > 2 and sys.argv[2] == "ncu") else ()):
     os.environ.update(env)
     try:
         for rep in range(2):

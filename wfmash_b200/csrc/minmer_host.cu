@@ -17,6 +17,12 @@
 #ifndef WFB_EMU
 #include <cub/cub.cuh>
 #endif
+#ifndef WFB_MM_FSMEM_DEFAULT
+#define WFB_MM_FSMEM_DEFAULT 0
+#endif
+#ifndef WFB_MM_LCUR_DEFAULT
+#define WFB_MM_LCUR_DEFAULT 0
+#endif
 #ifndef WFB_MM_FILTER_DEFAULT
 #define WFB_MM_FILTER_DEFAULT 1 /* candidate-filtered minmer build (minmer_kernels.h); WFB_MM_FILTER=0/1 overrides */
 #endif
@@ -173,8 +179,17 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   { const char* e = getenv(use_filter ? "WFB_MM_FCHUNK" : "WFB_MM_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
   { const char* e = getenv("WFB_MM_WARM"); if (e && atoi(e) >= w) P.warm = atoi(e); }
   P.qcap = w + 2; P.heap_cap = 3 * w + 64; P.pool_cap = 4 * w + 64;
+  P.lcur = 0;
   MmParams PF = P; /* the filtered run's containers only ever hold candidates */
   PF.qcap = PF.heap_cap = PF.pool_cap = (int)(3.0 * lambda) + 64;
+  PF.lcur = WFB_MM_LCUR_DEFAULT;
+  { const char* e = getenv("WFB_MM_LCUR"); if (e && *e) PF.lcur = atoi(e) != 0; }
+  if (PF.lcur) PF.qcap = 1; /* the window queue of a filtered run is the candidate list itself */
+  /* shared-memory variant of the filtered run (needs lcur): tight containers, a chunk that outgrows them flags itself like any other */
+  int fsmem = WFB_MM_FSMEM_DEFAULT;
+  { const char* e = getenv("WFB_MM_FSMEM"); if (e && *e) fsmem = atoi(e) != 0; }
+  if (!PF.lcur) fsmem = 0;
+  if (fsmem) { PF.heap_cap = std::max(64, (int)(1.5 * lambda) + 32); PF.pool_cap = std::max(64, (int)lambda + 32); }
   std::vector<MmChunk> chunks;
   for (int q = 0; q < ns; ++q) {
     const long long npos = seqs[q].len - k + 1;
@@ -191,8 +206,15 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   const int nchunks = (int)chunks.size();
   const long long scratch_stride = ((long long)sizeof(MmKmer) * (P.qcap + P.heap_cap) + (long long)sizeof(MmNode) * P.pool_cap +
                                     (long long)sizeof(MmWent) * (s + 2) + 255) / 256 * 256;
-  const long long scratch_stride_f = ((long long)sizeof(MmKmer) * (PF.qcap + PF.heap_cap) + (long long)sizeof(MmNode) * PF.pool_cap +
-                                      (long long)sizeof(MmWent) * (s + 2) + 255) / 256 * 256;
+  long long scratch_stride_f = ((long long)sizeof(MmKmer) * (PF.qcap + PF.heap_cap) + (long long)sizeof(MmNode) * PF.pool_cap +
+                                (long long)sizeof(MmWent) * (s + 2) + 255) / 256 * 256;
+  int fsmem_threads = 0;
+  if (fsmem) { /* + 16: consecutive threads' slices start in different banks */
+    scratch_stride_f = ((long long)sizeof(MmKmer) * (PF.qcap + PF.heap_cap) + (long long)sizeof(MmNode) * PF.pool_cap +
+                        (long long)sizeof(MmWent) * (s + 2) + 127) / 128 * 128 + 16;
+    fsmem_threads = (int)std::min<long long>(64, 220 * 1024 / scratch_stride_f) / 8 * 8;
+    if (fsmem_threads < 16) fsmem = 0;
+  }
   std::vector<MmTile> tiles;
   std::vector<int> seq_tile0((size_t)ns, 0);
   if (use_filter)
@@ -268,6 +290,12 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     MM_LAUNCH(mm_cand_kernel, std::min(ntiles, 148 * MMC_MINBLOCKS), MMC_THREADS, d_seq, d_seqs, d_tiles, ntiles, k, T, cand_cap, d_cand_hash, d_cand_lp,
               d_cand_cnt, &d_cnt->candidates);
     MM_CHECK(cudaEventRecord(ec));
+    if (fsmem) {
+      MM_CHECK(cudaFuncSetAttribute(mm_stream_cand_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fsmem_threads * scratch_stride_f)));
+      mm_stream_cand_smem_kernel<<<(nchunks + fsmem_threads - 1) / fsmem_threads, fsmem_threads, (size_t)(fsmem_threads * scratch_stride_f)>>>(
+          d_seq, d_seqs, d_chunks, nchunks, PF, scratch_stride_f, d_rec, rec_cap, d_end, d_endcount, d_cnt, CV, d_tile0, d_flag, d_redo);
+      wfb_count_launch_();
+    } else
     MM_LAUNCH(mm_stream_cand_kernel, (nchunks + TPB - 1) / TPB, TPB, d_seq, d_seqs, d_chunks, nchunks, PF, d_scratch, scratch_stride_f, d_rec,
               rec_cap, d_end, d_endcount, d_cnt, CV, d_tile0, d_flag, d_redo);
     MM_CHECK(cudaMemcpy(&hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost));

@@ -270,6 +270,7 @@ struct MmParams {
   int k, w, s;
   int chunk, warm;
   int qcap, heap_cap, pool_cap; /* per-thread capacities */
+  int lcur;                     /* filtered run: departures read from the candidate stream (no window queue) */
 };
 
 /* ---- candidate stream (the data-parallel half of the filtered build) ----
@@ -384,6 +385,29 @@ WFB_KERNEL_LB(mm_cand_kernel, MMC_THREADS, MMC_MINBLOCKS, const uint8_t* seqbuf,
   for (int i = bid; i < ntiles; i += nblocks) mm_cand_tile(smem, seqbuf, seqs, tiles[i], i, k, T, cap, cand_hash, cand_lp, cand_cnt, n_cand);
 }
 
+struct MmCursor { /* a position in the candidate stream of one sequence */
+  long long tile, tile_end, tpos0;
+  int j, n;
+  long long pos; /* LLONG_MAX = exhausted */
+  uint64_t hash;
+  int strand;
+};
+WFB_DEV void mm_cursor_next(MmCursor& c, const MmCandView& CV) {
+  c.pos = LLONG_MAX;
+  while (c.tile < c.tile_end) {
+    if (c.j < c.n) {
+      const int lp = CV.lp[c.tile * CV.cap + c.j];
+      c.pos = c.tpos0 + (lp >> 1);
+      c.strand = (lp & 1) ? 1 : -1;
+      c.hash = CV.hash[c.tile * CV.cap + c.j];
+      ++c.j;
+      return;
+    }
+    ++c.tile; c.tpos0 += MMC_TILE; c.j = 0;
+    c.n = c.tile < c.tile_end ? CV.cnt[c.tile] : 0;
+  }
+}
+
 /* ---- the reference's loop state of one chunk ---- */
 template <int L>
 struct MmRun {
@@ -414,10 +438,11 @@ WFB_DEV void mm_emit(MmRun<L>& R, long long i, const MmWent& e, long long wend) 
   } else R.overflow++;
 }
 
-/* One iteration of the reference's loop (:479-644) at k-mer start position i; `arrive` = a k-mer enters the window here (kk).
+/* One iteration of the reference's loop (:479-644) at k-mer start position i; `arrive` = a k-mer enters the window here (kk), `leave` =
+ * the oldest k-mer of the window (lv) falls out of it here (:517). The window queue itself is the caller's business.
  * FILT = the run only visits the positions where something happens (candidate arrivals, departures, the first fill). */
 template <bool FILT, int L>
-WFB_DEV void mm_position(MmRun<L>& R, const long long i, const bool arrive, const MmKmer kk) {
+WFB_DEV void mm_position(MmRun<L>& R, const long long i, const bool leave, const MmKmer lv, const bool arrive, const MmKmer kk) {
   MmHeap<L>& H = R.H;
   MmPool<L>& pool = R.pool;
   const MmArr<MmWent, L>& W = R.W;
@@ -430,8 +455,7 @@ WFB_DEV void mm_position(MmRun<L>& R, const long long i, const bool arrive, cons
     for (int j = H.n / 2 - 1; j >= 0; --j) mm_heap_sift_down(H, j);
   }
   /* leaving k-mer, :517-551 */
-  if (R.qn > 0 && (long long)R.Q[R.qh].pos < win) {
-    const MmKmer lv = R.Q[R.qh];
+  if (leave) { /* lv = the window's oldest k-mer, which the caller has already taken off the queue */
     if (R.wn > 0 && lv.hash <= W[R.wn - 1].hash) {
       const int lo = mm_lower_bound(W, R.wn, lv.hash);
       if (lo < R.wn && W[lo].hash == lv.hash) {
@@ -451,11 +475,8 @@ WFB_DEV void mm_position(MmRun<L>& R, const long long i, const bool arrive, cons
         }
       }
     }
-    R.qh = (R.qh + 1) % R.qcap;
-    --R.qn;
   }
-  if (arrive) { /* :559-586 */
-    if (R.qn < R.qcap) { R.Q[(R.qh + R.qn) % R.qcap] = kk; ++R.qn; } else R.overflow++;
+  if (arrive) { /* :559-586 (the caller has queued kk) */
     const int lo = mm_lower_bound(W, R.wn, kk.hash);
     if (lo < R.wn && W[lo].hash == kk.hash) {
       MmWent& e = W[lo];
@@ -554,58 +575,55 @@ WFB_DEV void mm_stream_chunk(const int slot, const int c, const uint8_t* seqbuf,
       const uint64_t hf = mm_murmur3_lo64(roll.f0, roll.f1, roll.f2, roll.f3, k), hb = mm_murmur3_lo64(roll.r0, roll.r1, roll.r2, roll.r3, k);
       if (i + 1 < run_end) mm_roll_step(roll, seq[i + k], k);
       if (seq[i + k - 1] == 'N') ambig = k;
-      MmKmer kk;
+      MmKmer kk, lv;
       kk.hash = hf < hb ? hf : hb; kk.pos = (int)i; kk.strand = hf < hb ? 1 : -1;
-      mm_position<false>(R, i, hb != hf && ambig == 0, kk);
+      lv = kk;
+      const bool arrive = hb != hf && ambig == 0;
+      const bool leave = R.qn > 0 && (long long)R.Q[R.qh].pos < i + k - w; /* :517 */
+      if (leave) { lv = R.Q[R.qh]; R.qh = (R.qh + 1) % R.qcap; --R.qn; }
+      if (arrive) { if (R.qn < R.qcap) { R.Q[(R.qh + R.qn) % R.qcap] = kk; ++R.qn; } else R.overflow++; }
+      mm_position<false>(R, i, leave, lv, arrive, kk);
       if (ambig > 0) --ambig;
     }
   } else {
-    /* cursor over the candidates of the tiles that cover [run_begin, run_end) */
-    long long tile = (long long)seq_tile0[ch.seq] + run_begin / MMC_TILE;
-    const long long tile_end = (long long)seq_tile0[ch.seq] + (run_end + MMC_TILE - 1) / MMC_TILE;
-    long long tpos0 = run_begin / MMC_TILE * MMC_TILE;
+    /* two cursors over the candidates of the tiles that cover [run_begin, run_end): arrivals, and (P.lcur) the same stream again
+     * w - k + 1 positions later as the departures — the window queue of a filtered run IS the candidate list */
+    MmCursor A, D;
+    A.tile = (long long)seq_tile0[ch.seq] + run_begin / MMC_TILE;
+    A.tile_end = (long long)seq_tile0[ch.seq] + (run_end + MMC_TILE - 1) / MMC_TILE;
+    A.tpos0 = run_begin / MMC_TILE * MMC_TILE;
     bool bad = false;
-    for (long long t = tile; t < tile_end; ++t) bad = bad || CV.cnt[t] < 0;
-    int j = 0, n = (tile < tile_end && !bad) ? CV.cnt[tile] : 0;
+    for (long long t = A.tile; t < A.tile_end; ++t) bad = bad || CV.cnt[t] < 0;
+    A.j = 0; A.n = (A.tile < A.tile_end && !bad) ? CV.cnt[A.tile] : 0;
+    A.pos = LLONG_MAX; A.hash = 0; A.strand = 0;
     const long long NONE = LLONG_MAX;
-    long long nc = NONE;
-    int nc_strand = 0;
-    uint64_t nc_hash = 0;
-#define MM_CAND_FETCH()                                                               \
-    {                                                                                 \
-      nc = NONE;                                                                      \
-      while (tile < tile_end) {                                                       \
-        if (j < n) {                                                                  \
-          const int lp_ = CV.lp[tile * CV.cap + j];                                   \
-          nc = tpos0 + (lp_ >> 1);                                                    \
-          nc_strand = (lp_ & 1) ? 1 : -1;                                             \
-          nc_hash = CV.hash[tile * CV.cap + j];                                       \
-          ++j;                                                                        \
-          break;                                                                      \
-        }                                                                             \
-        ++tile; tpos0 += MMC_TILE; j = 0;                                             \
-        n = tile < tile_end ? CV.cnt[tile] : 0;                                       \
-      }                                                                               \
-    }
     if (!bad) {
-      MM_CAND_FETCH()
-      while (nc != NONE && nc < run_begin) MM_CAND_FETCH()
+      mm_cursor_next(A, CV);
+      while (A.pos != NONE && A.pos < run_begin) mm_cursor_next(A, CV);
+      D = A;
+      const bool lcur = P.lcur != 0;
       const long long i0 = run_begin + w - k; /* the first step that fills the sketch (its window id is every entry's start) */
       bool did_i0 = false;
       for (;;) {
-        const long long nl = R.qn > 0 ? (long long)R.Q[R.qh].pos + (w - k + 1) : NONE;
-        long long i = nc < nl ? nc : nl;
+        const long long oldest = lcur ? D.pos : (R.qn > 0 ? (long long)R.Q[R.qh].pos : NONE);
+        const long long nl = oldest != NONE ? oldest + (w - k + 1) : NONE;
+        long long i = A.pos < nl ? A.pos : nl;
         if (!did_i0 && i0 <= i) { i = i0; did_i0 = true; }
         if (i >= run_end) break;
-        const bool arrive = i == nc;
-        MmKmer kk;
-        kk.hash = nc_hash; kk.pos = (int)i; kk.strand = nc_strand;
-        mm_position<true>(R, i, arrive, kk);
-        if (arrive) MM_CAND_FETCH()
+        const bool arrive = i == A.pos, leave = i == nl;
+        MmKmer kk, lv;
+        kk.hash = A.hash; kk.pos = (int)i; kk.strand = A.strand;
+        lv = kk;
+        if (leave) {
+          if (lcur) { lv.hash = D.hash; lv.pos = (int)D.pos; lv.strand = D.strand; mm_cursor_next(D, CV); }
+          else { lv = R.Q[R.qh]; R.qh = (R.qh + 1) % R.qcap; --R.qn; }
+        }
+        if (arrive && !lcur) { if (R.qn < R.qcap) { R.Q[(R.qh + R.qn) % R.qcap] = kk; ++R.qn; } else R.overflow++; }
+        mm_position<true>(R, i, leave, lv, arrive, kk);
+        if (arrive) mm_cursor_next(A, CV);
         if (R.shortfall | (R.overflow != 0) | (R.stale != 0)) break;
       }
     }
-#undef MM_CAND_FETCH
     if (bad || R.shortfall || R.overflow || R.stale) { /* the exact instantiation re-runs this chunk */
       chunk_flag[c] = 1;
       redo_list[atomicAdd_compat(&counters->flagged, 1ULL)] = c;
@@ -657,6 +675,19 @@ __global__ void __launch_bounds__(32, 1) mm_stream_redo_smem_kernel(const uint8_
   none.hash = nullptr; none.lp = nullptr; none.cnt = nullptr; none.cap = 0;
   mm_stream_chunk<false, 1>(0, redo[blockIdx.x], seqbuf, seqs, chunks, P, mm_redo_smem, scratch_stride, out, out_cap, endstate, endcount, counters,
                             none, nullptr, nullptr, nullptr);
+}
+#endif
+#ifndef WFB_EMU
+/* The filtered run with every chunk's (small) containers in dynamic shared memory: thread t owns the slice at t * scratch_stride, lane
+ * stride 1; needs P.lcur (no window queue). Few threads per SM, but an event is a chain of shared-memory accesses instead of L2 / HBM ones. */
+__global__ void mm_stream_cand_smem_kernel(const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P, long long scratch_stride,
+                                           MmRecord* out, long long out_cap, MmEndEnt* endstate, int* endcount, MmCounters* counters, MmCandView CV,
+                                           const int* seq_tile0, int* chunk_flag, int* redo_list) {
+  extern __shared__ __align__(16) unsigned char mm_filt_smem[];
+  const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (t >= nchunks) return;
+  mm_stream_chunk<true, 1>((int)threadIdx.x, t, seqbuf, seqs, chunks, P, mm_filt_smem, scratch_stride, out, out_cap, endstate, endcount, counters, CV,
+                           seq_tile0, chunk_flag, redo_list);
 }
 #endif
 WFB_KERNEL(mm_stream_cand_kernel, const uint8_t* seqbuf, const MmSeq* seqs, const MmChunk* chunks, int nchunks, MmParams P,

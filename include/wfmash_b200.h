@@ -266,7 +266,12 @@ typedef struct {
 } wfb_minmer_stats_t;
 
 /* seq_ptrs[i] / seq_lens[i] : raw FASTA bases of target i (any case); seq_ids[i] -> MinmerInfo::seqId.
- * Sequences shorter than window_size are skipped like Sketch::build does (winSketch.hpp:218-232). */
+ * Sequences shorter than window_size are skipped like Sketch::build does (winSketch.hpp:218-232).
+ * Environment switches (tuning and tests only; every setting returns the same bytes): WFB_MM_FILTER=0 runs the window machine over every
+ * k-mer instead of the candidates below the hash threshold; WFB_MM_FCHUNK / WFB_MM_CHUNK = positions per chunk thread of the filtered /
+ * unfiltered run [1024]; WFB_MM_LCUR=0 keeps a window queue in the filtered run; WFB_MM_FSMEM=1 puts the filtered run's containers in
+ * shared memory (slower); WFB_MM_REDO_SMEM=0 re-runs flagged chunks from global-memory slabs; WFB_MM_CAND_CAP=n caps a tile's candidate
+ * region (forces the overflow path). */
 int wfb_minmers_build(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
                       int32_t kmer_size, int32_t window_size, int32_t sketch_size, wfb_minmer_t* out, int64_t out_cap,
                       int64_t* out_count, wfb_minmer_stats_t* stats);

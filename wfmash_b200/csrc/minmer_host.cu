@@ -18,10 +18,10 @@
 #include <cub/cub.cuh>
 #endif
 #ifndef WFB_MM_FSMEM_DEFAULT
-#define WFB_MM_FSMEM_DEFAULT 0
+#define WFB_MM_FSMEM_DEFAULT 0 /* shared-memory containers for the filtered run: measured 3.6 x SLOWER (40 threads per SM), kept as a switch */
 #endif
 #ifndef WFB_MM_LCUR_DEFAULT
-#define WFB_MM_LCUR_DEFAULT 0
+#define WFB_MM_LCUR_DEFAULT 1 /* departures read from the candidate stream (measured: filtered stream 12.2 -> 11.5 ms on scerevisiae8) */
 #endif
 #ifndef WFB_MM_FILTER_DEFAULT
 #define WFB_MM_FILTER_DEFAULT 1 /* candidate-filtered minmer build (minmer_kernels.h); WFB_MM_FILTER=0/1 overrides */
@@ -175,7 +175,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   const uint64_t T = use_filter ? (uint64_t)ldexp(1.0 - sqrt(1.0 - density), 64) : ~0ULL;
   int cand_cap = std::min<int>(MMC_TILE, (int)(density * MMC_TILE * 1.25 + 8.0 * sqrt(density * MMC_TILE)) + 64);
   { const char* e = getenv("WFB_MM_CAND_CAP"); if (e && atoi(e) > 0) cand_cap = std::min<int>(MMC_TILE, atoi(e)); } /* test hook: forces the tile-overflow fallback */
-  P.chunk = use_filter ? 512 : 1024; P.warm = w; /* full run tuned in profiles/r01_minmer_chunk_sweep.txt: latency-bound, more chunks = more threads */
+  P.chunk = 1024; P.warm = w; /* full run tuned in profiles/r01_minmer_chunk_sweep.txt: latency-bound, more chunks = more threads */
   { const char* e = getenv(use_filter ? "WFB_MM_FCHUNK" : "WFB_MM_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
   { const char* e = getenv("WFB_MM_WARM"); if (e && atoi(e) >= w) P.warm = atoi(e); }
   P.qcap = w + 2; P.heap_cap = 3 * w + 64; P.pool_cap = 4 * w + 64;

@@ -253,6 +253,12 @@ def main():
     cores = os.cpu_count() or 1
     cfg, targets, queries, gold = load_config(args.config)
     workload = dict(WORKLOAD, config=args.config)
+    data_desc = ("reference's own example data (data/scerevisiae8.fa.gz)" if args.config.startswith("C3") else
+                 "synthetic (wfmash_b200/synth.py: xoshiro256** seed 42, SURVEY 8d's model)" if str(cfg["target"]).startswith("synth") else "reference's own example data")
+    if args.config != CONFIG_NAME:  # a parity-test config run as a bench (tests/configs.py): say what it is, not what the default is
+        workload["workload"] = (f"tests/configs.py {args.config}: {len(targets)} target / {len(queries)} query sequences, {sum(len(x) for _, x in targets)} target bp, "
+                                f"parameters {cfg['params']}; mapping phase + alignment phase, host sequences in, PAF text out")
+        workload["input"] = f"tests/configs.py target={cfg['target']} query={cfg['query']}"
 
     if args.impl == "reference":
         if rank != 0:
@@ -271,7 +277,7 @@ def main():
         last["value"] = v
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
-                "data": "reference's own example data (data/scerevisiae8.fa.gz)", "config": workload, "cpu_baseline": last,
+                "data": data_desc, "config": workload, "cpu_baseline": last,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit(line)
         return 0
@@ -384,7 +390,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
-            "data": "reference's own example data (data/scerevisiae8.fa.gz)" if args.config.startswith("C3") else "reference's own example data",
+            "data": data_desc,
             "config": workload,
             "run": dict(sequence_bp=total_seq, mapping_records=parity["mapping_lines"], aligned_bp=int(aligned_bp), records_per_gpu=records_per_gpu,
                         percentage_identity=float(mst.percentage_identity), sketch_size=int(mst.sketch_size)),

@@ -153,6 +153,10 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
   long long total = 16;
   for (int i = 0; i < nseq; ++i) {
     if (seq_lens[i] < w) continue;
+    if (seq_lens[i] > (int64_t)INT_MAX) { /* the stream keeps k-mer positions as 32-bit integers (the reference's offset_t is 64-bit) */
+      wfb_set_last_error_("a target sequence longer than 2^31 - 1 bases is not supported by the minmer build");
+      return WFB_EINVAL;
+    }
     MmSeq q;
     q.off = total; q.len = seq_lens[i]; q.seq_id = seq_ids[i]; q.first_chunk = 0; q.n_chunks = 0;
     total += (seq_lens[i] + 63) / 64 * 64 + 64;
@@ -305,7 +309,8 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     if (n_redo > 0) { /* exact re-run of the chunks whose filtered run gave up (short windows around N runs, capacity) */
       int redo_smem = 1; /* few chunks: one CTA each, containers in shared memory; many (every tile overflowed): the global slabs */
       { const char* e = getenv("WFB_MM_REDO_SMEM"); if (e && *e) redo_smem = atoi(e) != 0; }
-      if (redo_smem && scratch_stride <= 200 * 1024 && n_redo <= 148 * 64) {
+      /* one CTA per SM at 115 KB each: a wave of 148 chunks takes ~2.9 ms, the global-slab kernel ~35 ms whatever the count (measured, profiles/r02_minmer_filtered_run2.json) */
+      if (redo_smem && scratch_stride <= 200 * 1024 && n_redo <= 148 * 8) {
         MM_CHECK(cudaFuncSetAttribute(mm_stream_redo_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch_stride));
         mm_stream_redo_smem_kernel<<<(int)n_redo, 32, (size_t)scratch_stride>>>(d_seq, d_seqs, d_chunks, (int)n_redo, P, scratch_stride, d_rec, rec_cap,
                                                                                  d_end, d_endcount, d_cnt, d_redo);

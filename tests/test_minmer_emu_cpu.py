@@ -60,3 +60,17 @@ def test_minmer_stream_kernel_body_under_emulation_matches_oracle(mode):
     assert (res["redo"] == 0) == (mode == "unfiltered")
     if mode == "filtered":
         assert res["records"] > 120000 and res["redo"] < 200
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_minmer_build_differential_fuzz_under_emulation():
+    """600 random cases (tests/minmer_fuzz.py: parameters, boundary lengths, degenerate sequences) of the default (candidate-filtered) build against
+    the oracle; 63 000 cases / 61 M records of the same generator ran clean when the filtered build was written."""
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
+    for k in ("WFB_MM_FILTER", "WFB_MM_CAND_CAP", "WFB_MM_LCUR", "WFB_MM_FCHUNK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "minmer_fuzz.py"), "11", "120", "600"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["mismatches"] == 0 and res["cases"] == 600 and res["filtered_builds"] > 400 and res["redo_chunks"] > 100, res

@@ -19,8 +19,11 @@
 //     threshold that leaves ~2s + 40 of them per window; mm_stream_cand_kernel runs the state machine over the candidate stream
 //     only (events: a candidate arrives, a candidate leaves, the first fill), 5 - 15 % of the positions with containers of a
 //     few hundred entries. A chunk that cannot vouch for the result (sketch short of s entries, expired heap entry met while
-//     filling, a capacity hit, a tile with too many candidates) flags itself and is re-run over every k-mer by mm_stream_kernel,
-//     the exact instantiation of the same step function (see "candidate stream" below for why the filter is exact otherwise).
+//     filling, a capacity hit, a tile with too many candidates) flags itself and is re-run over every k-mer by the exact
+//     instantiation of the same step function (mm_stream_redo_smem_kernel: one CTA per flagged chunk, containers in shared memory;
+//     mm_stream_kernel when there are thousands). See "candidate stream" below for why the filter is exact otherwise.
+//     Measured on scerevisiae8 (96 Mbp, s = 24): 35.4 -> 16.3 ms; candidates 1.8 ms (58 G positions/s), filtered stream 11.5, re-run 3.0
+//     (profiles/r02_ncu_minmer_filtered_summary.txt).
 // Exactness: the chunk state after >= w warm-up positions equals the reference's state restricted to
 // live entries; entries the reference keeps past their expiry ("stale" heap entries, :596-641) can make
 // the two differ. Every such absorption is counted (stale_absorbed) so callers can tell; the parity

@@ -90,6 +90,46 @@ def test_l2_kernel_body_under_emulation_matches_oracle(oracle):
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_l2_kernel_body_under_emulation_on_random_parameter_sets(oracle):
+    """Random (k, w, s), filter modes, frequency cut-offs, index partitions, identity thresholds and sequence sets: the L2 kernel body against the
+    oracle (L2_CASES above pins four hand-picked sets). 5 200 cases / 6 M mappings of this generator ran clean at the end of round 2; 12 here."""
+    import random
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    emu = ctypes.CDLL(os.path.join(util.ROOT, so))
+    rnd = random.Random(77)
+    total = 0
+    for _ in range(12):
+        seed = rnd.randrange(1, 1 << 20)
+        k, w, s = rnd.choice([(15, 1000, 29), (15, 1000, 59), (19, 500, 17), (15, 256, 11), (15, 1000, 24), (17, 2000, 39), (15, 1000, 5), (11, 300, 40)])
+        mode = (rnd.choice([0, 1]), rnd.choice([0, 1]), rnd.choice([0, 1]), rnd.choice([1, 2, 3, 5]))
+        seqs, ids, groups = maputil.l2_case(seed=seed)
+        index = maputil.oracle_index(oracle, seqs, ids, k, w, s, rnd.choice([0.0002, 0.001, 0.01]), rnd.choice([1, 2, 3]))
+        kept = np.ascontiguousarray(index[0])
+        stage1 = rnd.random() < 0.5
+        s1 = np.zeros(s + 1, dtype=np.int32)
+        assert emu.wfb_stage1_min_hits(ctypes.c_double(1.0), ctypes.c_float(0.0), k, s, vp(s1)) == 0
+        ms = np.zeros(s + 1, dtype=np.int32)
+        assert emu.wfb_l2_min_shared(ctypes.c_float(rnd.choice([0.7, 0.85, 0.95])), k, s, vp(ms)) == 0
+        frs, q_all, q_count, loci, want = maputil.oracle_map_fragments(oracle, index, seqs, ids, groups, k, w, s, mode, stage1=stage1,
+                                                                       min_shared=ms if not stage1 else None)
+        if len(loci) == 0:
+            continue
+        l1 = np.zeros(len(loci), dtype=maputil.L1PUBDT)
+        l1["seqId"], l1["rangeStartPos"], l1["rangeEndPos"], l1["intersectionSize"] = loci[:, 1], loci[:, 2], loci[:, 3], loci[:, 4]
+        lfrag = np.ascontiguousarray(loci[:, 0].astype(np.int32))
+        out = np.zeros(len(want) + 64, dtype=maputil.L2MAPDT)
+        n_out, steps = ctypes.c_int64(0), ctypes.c_uint64(0)
+        status = np.zeros(len(frs), dtype=np.int32)
+        rc = emu.wfb_emu_l2_loci(vp(kept), ctypes.c_int64(len(kept)), vp(l1), vp(lfrag), ctypes.c_int64(len(l1)), vp(q_all), vp(q_count), len(frs),
+                                 k, w, s, vp(s1) if stage1 else None, None if stage1 else vp(ms), vp(out), ctypes.c_int64(len(out)),
+                                 ctypes.byref(n_out), vp(status), ctypes.byref(steps))
+        assert rc == 0 and (status == 0).all(), (seed, k, w, s, mode)
+        assert same_mappings(out[: n_out.value], want), (seed, k, w, s, mode, stage1)
+        total += n_out.value
+    assert total > 3000
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
 def test_l1_parallel_sweep_equals_serial_walk_under_emulation():
     """The data-parallel L1 sweep (ix_l1_regions_par: prefix sums / segment ids over the sorted interval points) against
     the literal two-pass walk of computeL1CandidateRegions (ix_l1_regions, itself checked against the oracle and the

@@ -246,7 +246,8 @@ int wfb_sketch_fragments(int device, const char* seq_base, int64_t seq_bytes, co
  * (src/map/include/commonFunc.hpp:439-708; src/map/include/winSketch.hpp:467-499) for a BATCH of target
  * sequences. Output = the concatenation Sketch::build makes of the per-sequence results
  * (winSketch.hpp:424-429): ordered by sequence (input order), then (wpos, wpos_end); records with equal
- * (wpos, wpos_end) — whose order the reference's unstable std::sort leaves unspecified — by hash.
+ * (wpos, wpos_end) in the order the reference's unstable std::sort (GNU libstdc++) leaves them — the L2 stage
+ * depends on it for targets of one to two windows (such sequences are put in order on the host: tie_sequences).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   double stream_kernel_ms; /* CUDA-event time of the streaming-window kernel             */
@@ -263,6 +264,7 @@ typedef struct {
   double cand_kernel_ms;     /* filtered build: CUDA-event time of the cleaning + candidate kernels ...  */
   double filtered_stream_ms; /* ... of the window machine over the candidate stream ...                  */
   double redo_ms;            /* ... of the exact re-run of the flagged chunks (all three inside stream_kernel_ms) */
+  uint64_t tie_sequences;    /* sequences with records tying on (wpos, wpos_end), put in the reference's std::sort order on the host */
 } wfb_minmer_stats_t;
 
 /* seq_ptrs[i] / seq_lens[i] : raw FASTA bases of target i (any case); seq_ids[i] -> MinmerInfo::seqId.

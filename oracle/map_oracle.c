@@ -332,11 +332,122 @@ static void add_minmers_stream_range(const char* seq, int64_t len, int k, int w,
   free(Q); free(W); free(H.a); free(P.nodes); free(rc);
 }
 
-/* Post passes (:660-706): drop degenerate, strand sign, chunk > w, sort by (wpos,wpos_end), unique on
- * (wpos,hash). std::sort is unstable: records with equal (wpos,wpos_end) may come out in any order in
- * the reference; this restatement breaks such ties by hash, tests compare per-key multisets. */
+/* ---- the reference's final std::sort (:696), restated ----
+ * The comparator looks at (wpos, wpos_end) only and std::sort is not stable, so the order of records with equal keys is whatever the
+ * library's algorithm leaves — unspecified by the standard, but a pure function of the input order for a given library. The reference
+ * is built with GNU libstdc++, whose std::sort is: introsort (median-of-three of first+1 / middle / last-1 moved to first, Hoare-style
+ * unguarded partition, recursion on the right part, depth limit 2*floor(log2 n) with a heapsort fall-back) down to runs of <= 16
+ * elements, then one insertion sort over the whole range (guarded for the first 16 elements, unguarded after). That order decides which
+ * of several minmers opened and closed by the same windows the L2 stage sees first (mappingCore.hpp:352-384 evaluates the sketch after
+ * every single insertion), i.e. it is visible in the mappings of targets barely longer than one window. Restated here step by step so
+ * that the oracle's order IS the reference's; pinned by tests/test_map_oracle_cpu.py against the compiled reference (exact order). */
+static int mi_less(const orc_minmer_t* l, const orc_minmer_t* r) {
+  return l->wpos < r->wpos || (l->wpos == r->wpos && l->wpos_end < r->wpos_end);
+}
+static void mi_swap(orc_minmer_t* a, orc_minmer_t* b) { const orc_minmer_t t = *a; *a = *b; *b = t; }
+static void gss_push_heap(orc_minmer_t* first, int64_t hole, int64_t top, orc_minmer_t value) {
+  int64_t parent = (hole - 1) / 2;
+  while (hole > top && mi_less(&first[parent], &value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+static void gss_adjust_heap(orc_minmer_t* first, int64_t hole, int64_t len, orc_minmer_t value) {
+  const int64_t top = hole;
+  int64_t child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (mi_less(&first[child], &first[child - 1])) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  gss_push_heap(first, hole, top, value);
+}
+static void gss_heapsort(orc_minmer_t* first, int64_t len) { /* partial_sort(first, last, last): make_heap, then sort_heap */
+  if (len >= 2) {
+    int64_t parent = (len - 2) / 2;
+    for (;;) {
+      gss_adjust_heap(first, parent, len, first[parent]);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  for (int64_t last = len; last > 1;) {
+    --last;
+    const orc_minmer_t value = first[last];
+    first[last] = first[0];
+    gss_adjust_heap(first, 0, last, value);
+  }
+}
+static void gss_unguarded_linear_insert(orc_minmer_t* last) {
+  const orc_minmer_t val = *last;
+  orc_minmer_t* next = last - 1;
+  while (mi_less(&val, next)) {
+    *last = *next;
+    last = next;
+    --next;
+  }
+  *last = val;
+}
+static void gss_insertion_sort(orc_minmer_t* first, orc_minmer_t* last) {
+  if (first == last) return;
+  for (orc_minmer_t* i = first + 1; i != last; ++i) {
+    if (mi_less(i, first)) {
+      const orc_minmer_t val = *i;
+      memmove(first + 1, first, (size_t)(i - first) * sizeof(orc_minmer_t));
+      *first = val;
+    } else gss_unguarded_linear_insert(i);
+  }
+}
+static void gss_introsort_loop(orc_minmer_t* first, orc_minmer_t* last, int64_t depth_limit) {
+  while (last - first > 16) {
+    if (depth_limit == 0) { gss_heapsort(first, last - first); return; }
+    --depth_limit;
+    /* median of (first + 1, mid, last - 1) to *first */
+    orc_minmer_t *a = first + 1, *b = first + (last - first) / 2, *c = last - 1;
+    if (mi_less(a, b)) {
+      if (mi_less(b, c)) mi_swap(first, b);
+      else if (mi_less(a, c)) mi_swap(first, c);
+      else mi_swap(first, a);
+    } else if (mi_less(a, c)) mi_swap(first, a);
+    else if (mi_less(b, c)) mi_swap(first, c);
+    else mi_swap(first, b);
+    /* unguarded partition of [first + 1, last) around *first */
+    orc_minmer_t *lo = first + 1, *hi = last;
+    for (;;) {
+      while (mi_less(lo, first)) ++lo;
+      --hi;
+      while (mi_less(first, hi)) --hi;
+      if (!(lo < hi)) break;
+      mi_swap(lo, hi);
+      ++lo;
+    }
+    gss_introsort_loop(lo, last, depth_limit);
+    last = lo;
+  }
+}
+static void gnu_std_sort(orc_minmer_t* first, int64_t n) {
+  if (n <= 0) return;
+  int64_t lg = 0;
+  for (int64_t t = n; t > 1; t >>= 1) ++lg;
+  gss_introsort_loop(first, first + n, 2 * lg);
+  if (n > 16) {
+    gss_insertion_sort(first, first + 16);
+    for (orc_minmer_t* i = first + 16; i != first + n; ++i) gss_unguarded_linear_insert(i);
+  } else gss_insertion_sort(first, first + n);
+}
+
+/* Post passes (:660-706) in the reference's own order of operations: drop degenerate records, strand sign, records longer than w are
+ * REMOVED and their pieces appended after all the others (:670-694), std::sort by (wpos, wpos_end) (above), std::unique on (wpos, hash). */
 static int64_t add_minmers_post(orc_mivec_t* raw, int w, orc_minmer_t* out, int64_t cap) {
-  orc_mivec_t v = {0, 0, 0};
+  orc_mivec_t v = {0, 0, 0}, pieces = {0, 0, 0};
   for (int64_t i = 0; i < raw->n; ++i) {
     orc_minmer_t m = raw->v[i];
     if (m.wpos < 0 || m.wpos_end < 0 || m.wpos == m.wpos_end) continue;
@@ -347,26 +458,21 @@ static int64_t add_minmers_post(orc_mivec_t* raw, int w, orc_minmer_t* out, int6
         orc_minmer_t p = m;
         p.wpos = m.wpos + (int64_t)c * w;
         p.wpos_end = (m.wpos + (int64_t)c * w + w < m.wpos_end) ? m.wpos + (int64_t)c * w + w : m.wpos_end;
-        mivec_push(&v, p);
+        mivec_push(&pieces, p);
       }
     } else {
       mivec_push(&v, m);
     }
   }
-  /* the reference appends the chunked pieces after the unchunked ones before sorting; with a total
-   * order on (wpos,wpos_end,hash) the result is the same */
-  for (int64_t i = 1; i < v.n; ++i) (void)0;
-  qsort(v.v, (size_t)v.n, sizeof(orc_minmer_t), cmp_mi_pos);
-  /* stable tie-break by hash inside equal (wpos,wpos_end) runs */
-  for (int64_t i = 0; i < v.n;) {
-    int64_t j = i;
-    while (j < v.n && v.v[j].wpos == v.v[i].wpos && v.v[j].wpos_end == v.v[i].wpos_end) ++j;
-    if (j - i > 1) qsort(v.v + i, (size_t)(j - i), sizeof(orc_minmer_t), cmp_minmer_hash);
-    i = j;
-  }
+  for (int64_t i = 0; i < pieces.n; ++i) mivec_push(&v, pieces.v[i]);
+  free(pieces.v);
+  gnu_std_sort(v.v, v.n);
   int64_t n = 0;
-  for (int64_t i = 0; i < v.n; ++i) {
-    if (n > 0 && i > 0 && v.v[i].wpos == v.v[i - 1].wpos && v.v[i].hash == v.v[i - 1].hash) continue; /* std::unique vs previous KEPT == previous element here */
+  orc_minmer_t prev;
+  memset(&prev, 0, sizeof(prev));
+  for (int64_t i = 0; i < v.n; ++i) { /* std::unique compares with the last KEPT element */
+    if (n > 0 && v.v[i].wpos == prev.wpos && v.v[i].hash == prev.hash) continue;
+    prev = v.v[i];
     if (n < cap) out[n] = v.v[i];
     ++n;
   }

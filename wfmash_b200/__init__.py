@@ -280,7 +280,7 @@ class MinmerStats(ctypes.Structure):
                 ("raw_records", ctypes.c_uint64), ("chunks", ctypes.c_uint64), ("stale_absorbed", ctypes.c_uint64),
                 ("stitch_miss", ctypes.c_uint64), ("filtered", ctypes.c_uint64), ("candidates", ctypes.c_uint64),
                 ("redo_chunks", ctypes.c_uint64), ("cand_kernel_ms", ctypes.c_double), ("filtered_stream_ms", ctypes.c_double),
-                ("redo_ms", ctypes.c_double)]
+                ("redo_ms", ctypes.c_double), ("tie_sequences", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -132,6 +132,139 @@ WFB_KERNEL(mm_gather_out_kernel, const MmFinal* f, const int* perm, const int* k
   }
 }
 
+/* Neighbours of the final order that tie on (sequence, wpos, wpos_end): their order is what the reference's unstable std::sort leaves. */
+WFB_KERNEL(mm_tie_count_kernel, const wfb_minmer_t* out, long long n, unsigned long long* ties) {
+  WFB_KERNEL_PROLOGUE
+  unsigned long long t = 0;
+  for (long long i = (long long)bid * WFB_NT + WFB_TID; i + 1 < n; i += (long long)nblocks * WFB_NT)
+    t += out[i].seqId == out[i + 1].seqId && out[i].wpos == out[i + 1].wpos && out[i].wpos_end == out[i + 1].wpos_end;
+  if (t) atomicAdd_compat(ties, t);
+}
+
+/* ---- the reference's order inside (wpos, wpos_end) ties (host; runs only for sequences that have such ties) ----
+ * addMinmers ends with std::sort on (wpos, wpos_end) (commonFunc.hpp:696). Records that tie on both come out in the order GNU
+ * libstdc++'s introsort leaves them, a function of the order in which the loop pushed them — and computeL2MappedRegions evaluates the
+ * sketch after every single insertion (mappingCore.hpp:352-384), so that order shows in the mappings of targets barely longer than one
+ * window (all minmers of a sequence of w .. 2w bases are opened by window 0 and closed together by the final flush). Real chromosomes
+ * have no such ties (0 on scerevisiae8 / LPA). When a sequence has one, its records are put back in the reference's push order —
+ * by closing position; at one position: the leaving k-mer's record, the arriving k-mer's, the evicted one (:517-617); the final flush in
+ * hash order (:646-658) — and the reference's post passes (:660-706) are applied literally, with the same library's std::sort. */
+static uint64_t mmh_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static uint64_t mmh_fmix64(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k; }
+static uint64_t mmh_murmur3_lo64(const uint8_t* p, int len) { /* MurmurHash3_x64_128, seed 42, low word (murmur3.h:226-303), len <= 32 */
+  const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+  uint64_t h1 = 42, h2 = 42;
+  const int nblocks = len / 16;
+  for (int i = 0; i < nblocks; ++i) {
+    uint64_t k1, k2;
+    memcpy(&k1, p + 16 * i, 8); memcpy(&k2, p + 16 * i + 8, 8);
+    k1 *= c1; k1 = mmh_rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    h1 = mmh_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+    k2 *= c2; k2 = mmh_rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    h2 = mmh_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+  }
+  const uint8_t* tail = p + 16 * nblocks;
+  uint64_t k1 = 0, k2 = 0;
+  const int rem = len & 15;
+  for (int j = rem - 1; j >= 8; --j) k2 = (k2 << 8) | tail[j];
+  for (int j = (rem < 8 ? rem : 8) - 1; j >= 0; --j) k1 = (k1 << 8) | tail[j];
+  if (rem > 8) { k2 *= c2; k2 = mmh_rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+  if (rem > 0) { k1 *= c1; k1 = mmh_rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+  h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+  h1 += h2; h2 += h1;
+  h1 = mmh_fmix64(h1); h2 = mmh_fmix64(h2);
+  h1 += h2;
+  return h1;
+}
+static uint64_t mmh_canonical(const uint8_t* s, int k) { /* s: cleaned bases */
+  uint8_t rc[32];
+  for (int j = 0; j < k; ++j) { const uint8_t c = s[k - 1 - j]; rc[j] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+  const uint64_t f = mmh_murmur3_lo64(s, k), b = mmh_murmur3_lo64(rc, k);
+  return f < b ? f : b;
+}
+struct MmhRaw { wfb_minmer_t m; int stage; };
+/* cleaned: the cleaned sequence buffer (MmSeq::off offsets); rec: every raw record after the stitch; out: the final array.
+ * Returns the rebuilt array in `fixed` (== out when nothing had to change) and the number of sequences rebuilt. */
+static long long mm_fix_tie_order_host(const uint8_t* cleaned, const std::vector<MmSeq>& seqs, int k, int w, const MmRecord* rec, long long nrec,
+                                       const int* chunk_flag, long long nrec_filtered, const wfb_minmer_t* out, long long nout,
+                                       std::vector<wfb_minmer_t>& fixed) {
+  const int ns = (int)seqs.size();
+  { /* the output is segmented by seqId: ids given twice make the segments ambiguous, leave the order as it is */
+    std::vector<int> idsort((size_t)ns);
+    for (int q = 0; q < ns; ++q) idsort[q] = seqs[q].seq_id;
+    std::sort(idsort.begin(), idsort.end());
+    if (std::adjacent_find(idsort.begin(), idsort.end()) != idsort.end()) { fixed.assign(out, out + nout); return 0; }
+  }
+  std::vector<char> has_tie((size_t)ns, 0);
+  std::vector<long long> seg_begin((size_t)ns + 1, 0);
+  { /* the output is ordered by sequence INDEX (input order); map seqId -> index through the segment walk */
+    long long i = 0;
+    for (int q = 0; q < ns; ++q) {
+      seg_begin[q] = i;
+      while (i < nout && out[i].seqId == seqs[q].seq_id) {
+        if (i + 1 < nout && out[i + 1].seqId == out[i].seqId && out[i + 1].wpos == out[i].wpos && out[i + 1].wpos_end == out[i].wpos_end) has_tie[q] = 1;
+        ++i;
+      }
+    }
+    seg_begin[ns] = i;
+    if (i != nout) { fixed.assign(out, out + nout); return 0; } /* cannot happen (the output is in input order); never lose records over it */
+  }
+  std::vector<std::vector<MmhRaw>> raws((size_t)ns);
+  for (long long r = 0; r < nrec; ++r) {
+    const MmRecord& x = rec[r];
+    if (!has_tie[x.seq]) continue;
+    if (r < nrec_filtered && chunk_flag && chunk_flag[x.chunk]) continue;
+    MmhRaw e;
+    e.m.hash = x.hash; e.m.wpos = x.wpos; e.m.wpos_end = x.wpos_end; e.m.seqId = seqs[x.seq].seq_id; e.m.strand = (int16_t)(x.strand < 0 ? -1 : 1); e.m.pad_ = 0;
+    e.stage = 2;
+    raws[x.seq].push_back(e);
+  }
+  long long rebuilt = 0;
+  fixed.clear();
+  fixed.reserve((size_t)nout);
+  for (int q = 0; q < ns; ++q) {
+    if (!has_tie[q]) { fixed.insert(fixed.end(), out + seg_begin[q], out + seg_begin[q + 1]); continue; }
+    std::vector<MmhRaw>& v = raws[q];
+    const uint8_t* sq = cleaned + seqs[q].off;
+    const long long len = seqs[q].len, flush_end = len - k + 1;
+    for (MmhRaw& e : v) {
+      if (e.m.wpos_end == flush_end) { e.stage = 3; continue; } /* final flush */
+      const long long win = e.m.wpos_end, i = win - k + w;       /* closed at loop position i */
+      if (win - 1 >= 0 && mmh_canonical(sq + (win - 1), k) == e.m.hash) e.stage = 0;       /* the k-mer that left the window */
+      else if (i >= 0 && i <= len - k && mmh_canonical(sq + i, k) == e.m.hash) e.stage = 1; /* the k-mer that entered it */
+    }
+    std::sort(v.begin(), v.end(), [](const MmhRaw& a, const MmhRaw& b) { /* a total order: the push order of the reference's loop */
+      const bool fa = a.stage == 3, fb = b.stage == 3;
+      if (fa != fb) return fb;
+      if (fa) return a.m.hash < b.m.hash;
+      if (a.m.wpos_end != b.m.wpos_end) return a.m.wpos_end < b.m.wpos_end;
+      if (a.stage != b.stage) return a.stage < b.stage;
+      if (a.m.wpos != b.m.wpos) return a.m.wpos > b.m.wpos; /* same entry emitted twice at one position: the second one is degenerate */
+      return a.m.hash < b.m.hash;
+    });
+    std::vector<wfb_minmer_t> mi, pieces;
+    for (const MmhRaw& e : v) { /* :660-694 */
+      const wfb_minmer_t& m = e.m;
+      if (m.wpos < 0 || m.wpos_end < 0 || m.wpos == m.wpos_end) continue;
+      if (m.wpos_end > m.wpos + w) {
+        const int nch = (int)ceilf((float)(m.wpos_end - m.wpos) / (float)w);
+        for (int c = 0; c < nch; ++c) {
+          wfb_minmer_t p = m;
+          p.wpos = m.wpos + (int64_t)c * w;
+          p.wpos_end = std::min<int64_t>(m.wpos + (int64_t)c * w + w, m.wpos_end);
+          pieces.push_back(p);
+        }
+      } else mi.push_back(m);
+    }
+    mi.insert(mi.end(), pieces.begin(), pieces.end());
+    std::sort(mi.begin(), mi.end(), [](const wfb_minmer_t& l, const wfb_minmer_t& r) { return l.wpos < r.wpos || (l.wpos == r.wpos && l.wpos_end < r.wpos_end); }); /* :696 */
+    mi.erase(std::unique(mi.begin(), mi.end(), [](const wfb_minmer_t& l, const wfb_minmer_t& r) { return l.wpos == r.wpos && l.hash == r.hash; }), mi.end()); /* :701-706 */
+    fixed.insert(fixed.end(), mi.begin(), mi.end());
+    ++rebuilt;
+  }
+  return rebuilt;
+}
+
 /* Shared by wfb_minmers_build (results copied to the caller's host buffer) and wfb_index_build (d_out_keep != NULL:
  * the result stays in device memory, ownership of *d_out_keep passes to the caller, `out` is not touched). */
 int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_t* seq_lens, const int32_t* seq_ids, int32_t nseq,
@@ -233,6 +366,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     }
   const int ntiles = (int)tiles.size();
   long long nrec_filtered = 0, n_redo = 0; /* records written by the filtered run; chunks re-run exactly */
+  long long tie_sequences = 0;             /* sequences whose tied records were put in the reference's order on the host */
   /* expected density ~0.0027*s windows per base; generous cap, overflow is detected */
   long long rec_cap = (long long)((double)total * (0.01 * s + 0.05)) + 65536;
 #ifndef WFB_EMU
@@ -392,9 +526,30 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     MM_CHECK(cudaMalloc(&d_out, sizeof(wfb_minmer_t) * (size_t)std::max<long long>(nout, 1)));
     MM_LAUNCH(mm_gather_out_kernel, 148 * 8, 256, d_fin, d_perm, d_keep, d_offs, nfin, d_seqs, d_out);
   }
+  if (nout > 1) MM_LAUNCH(mm_tie_count_kernel, 148 * 8, 256, d_out, nout, &d_cnt->ties);
   MM_CHECK(cudaEventRecord(e2));
   MM_CHECK(cudaEventSynchronize(e2));
   MM_CHECK(cudaMemcpy(&hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (hc.ties > 0) { /* rare (tiny targets, degenerate sequence): put the tied records in the reference's own order on the host */
+    std::vector<wfb_minmer_t> h_out((size_t)nout), fixed;
+    std::vector<MmRecord> h_rec((size_t)nrec);
+    std::vector<int> h_flag;
+    std::vector<uint8_t> cleaned((size_t)total);
+    MM_CHECK(cudaMemcpy(h_out.data(), d_out, sizeof(wfb_minmer_t) * (size_t)nout, cudaMemcpyDeviceToHost));
+    MM_CHECK(cudaMemcpy(h_rec.data(), d_rec, sizeof(MmRecord) * (size_t)nrec, cudaMemcpyDeviceToHost));
+    MM_CHECK(cudaMemcpy(cleaned.data(), d_seq, (size_t)total, cudaMemcpyDeviceToHost));
+    if (use_filter) {
+      h_flag.resize((size_t)nchunks);
+      MM_CHECK(cudaMemcpy(h_flag.data(), d_flag, sizeof(int) * (size_t)nchunks, cudaMemcpyDeviceToHost));
+    }
+    tie_sequences = mm_fix_tie_order_host(cleaned.data(), seqs, k, w, h_rec.data(), nrec, use_filter ? h_flag.data() : nullptr, nrec_filtered, h_out.data(), nout, fixed);
+    if ((long long)fixed.size() != nout) {
+      cudaFree(d_out); d_out = nullptr;
+      nout = (long long)fixed.size();
+      MM_CHECK(cudaMalloc(&d_out, sizeof(wfb_minmer_t) * (size_t)std::max<long long>(nout, 1)));
+    }
+    if (nout > 0) MM_CHECK(cudaMemcpy(d_out, fixed.data(), sizeof(wfb_minmer_t) * (size_t)nout, cudaMemcpyHostToDevice));
+  }
   *out_count = nout;
   if (stats) {
     float a = 0, b = 0;
@@ -409,6 +564,7 @@ int wfb_minmers_build_impl(int device, const char* const* seq_ptrs, const int64_
     stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed;
     stats->stitch_miss = hc.stitch_miss; stats->bases = 0;
     stats->candidates = hc.candidates; stats->redo_chunks = (uint64_t)n_redo; stats->filtered = (uint64_t)use_filter;
+    stats->tie_sequences = (uint64_t)tie_sequences;
     for (int q = 0; q < ns; ++q) stats->bases += (uint64_t)seqs[q].len;
   }
   if (d_out_keep) { *d_out_keep = d_out; d_out = nullptr; goto done; }
@@ -486,13 +642,23 @@ done:
   std::vector<long long> offs2((size_t)nfin + 1);
   acc = 0;
   for (long long i = 0; i <= nfin; ++i) { offs2[i] = acc; if (i < nfin) acc += keep[i]; }
-  *out_count = acc;
-  if (stats) {
-    stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed; stats->stitch_miss = hc.stitch_miss;
-    stats->candidates = hc.candidates; stats->redo_chunks = (uint64_t)n_redo; stats->filtered = (uint64_t)use_filter;
+  {
+    std::vector<wfb_minmer_t> tmp((size_t)std::max<long long>(acc, 1)), fixed;
+    if (nfin) mm_gather_out_kernel(0, 1, fin.data(), perm.data(), keep.data(), offs2.data(), nfin, seqs.data(), tmp.data());
+    if (acc > 1) mm_tie_count_kernel(0, 1, tmp.data(), acc, &hc.ties);
+    if (hc.ties > 0) {
+      tie_sequences = mm_fix_tie_order_host(buf.data(), seqs, k, w, rec.data(), nrec, use_filter ? flag.data() : nullptr, nrec_filtered, tmp.data(), acc, fixed);
+      acc = (long long)fixed.size();
+    } else fixed.assign(tmp.begin(), tmp.begin() + acc);
+    *out_count = acc;
+    if (stats) {
+      stats->raw_records = (uint64_t)nrec; stats->chunks = (uint64_t)nchunks; stats->stale_absorbed = hc.stale_absorbed; stats->stitch_miss = hc.stitch_miss;
+      stats->candidates = hc.candidates; stats->redo_chunks = (uint64_t)n_redo; stats->filtered = (uint64_t)use_filter;
+      stats->tie_sequences = (uint64_t)tie_sequences;
+    }
+    if (acc > out_cap) { wfb_set_last_error_("minmer output buffer too small"); return WFB_ECAP; }
+    if (acc) memcpy(out, fixed.data(), sizeof(wfb_minmer_t) * (size_t)acc);
   }
-  if (acc > out_cap) { wfb_set_last_error_("minmer output buffer too small"); return WFB_ECAP; }
-  if (nfin) mm_gather_out_kernel(0, 1, fin.data(), perm.data(), keep.data(), offs2.data(), nfin, seqs.data(), out);
   (void)device;
   return rc;
 #endif

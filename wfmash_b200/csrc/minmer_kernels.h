@@ -75,6 +75,7 @@ struct MmSeq {
 struct MmCounters {
   unsigned long long n_records, stale_absorbed, overflow, stitch_miss;
   unsigned long long candidates, flagged; /* filtered build: k-mers below the threshold; chunks left to the exact re-run */
+  unsigned long long ties;               /* neighbours of the final order with equal (seqId, wpos, wpos_end) */
 };
 
 WFB_DEV uint64_t mm_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }

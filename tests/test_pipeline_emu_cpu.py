@@ -70,3 +70,19 @@ def test_align_phase_under_emulation_matches_reference_do_biwfa_alignment():
     assert res["sam"][0] == res["ref_paf"].splitlines()[1].split("\t")[0] and res["sam"][1] in ("0", "16") and res["sam"][4] == "MD:Z:"
     spans = [int(f[3]) - int(f[2]) for f in (ln.split("\t") for ln in res["ref_map"].splitlines())]
     assert res["aligned_bp"] >= sum(spans)  # + the query padding of the chain ends
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_align_phase_differential_fuzz_against_the_unmodified_aligner():
+    """tests/alignphase_fuzz.py: hand-made mapping rows (sequence ends, both strands, shifted / resized target intervals, random chain tags; PAF
+    and SAM + MD) through wfb_align_phase under emulation against the unmodified align::Aligner::compute. 1 430 cases / 5 100 rows ran clean at the
+    end of round 2; 12 cases here."""
+    if util.load_ref("libalignref.so") is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "alignphase_fuzz.py"), "3", "200", "12"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["mismatches"] == 0 and res["cases"] == 12 and res["rows"] >= 20, res

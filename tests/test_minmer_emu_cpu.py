@@ -74,3 +74,15 @@ def test_minmer_build_differential_fuzz_under_emulation():
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["mismatches"] == 0 and res["cases"] == 600 and res["filtered_builds"] > 400 and res["redo_chunks"] > 100, res
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_fragment_sketch_differential_fuzz_under_emulation():
+    """tests/sketch_fuzz.py: the query-fragment sketch kernel body against the oracle on random parameters and degenerate sequences
+    (535 000 fragments ran clean at the end of round 2; 3 000 here)."""
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "sketch_fuzz.py"), "4", "120", "3000"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["mismatches"] == 0 and res["fragments"] >= 3000, res

@@ -70,3 +70,18 @@ def test_ani_kernel_body_and_identity_under_emulation():
         assert res["ref"] == res["ident"]                              # live
     ident = float.fromhex(res["auto"][0])
     assert 0.85 < ident < 0.99 and res["auto"][1] == int(0.02 * (1 + (1 - ident) / 0.1) * (1000 - 15))
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the host emulation build")
+def test_ani_identity_differential_fuzz_against_the_unmodified_reference():
+    """tests/ani_fuzz.py: random sequence sets / slices / percentiles / adjustments; the estimated identity must be the double the unmodified
+    estimate_identity_for_groups returns, bit for bit (9 600 cases ran clean at the end of round 2; 60 here)."""
+    if util.load_ref("libstatsref.so") is None:
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    so = subprocess.run([os.path.join(util.ROOT, "tests", "emu", "build_emu.sh")], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    env = dict(os.environ, WFB_LIB=os.path.join(util.ROOT, so))
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "ani_fuzz.py"), "6", "200", "60"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["mismatches"] == 0 and res["cases"] == 60, res
